@@ -1,0 +1,322 @@
+/* Test/bench harness around the UNMODIFIED reference engine (oracle/_ref/libmujoco_ref.so).
+ *
+ * TEST INFRASTRUCTURE ONLY: nothing in the product path (mujoco_inversedynamicstest_b200/)
+ * may link or call this file. It is compiled against the reference's own headers
+ * (/root/reference/include) and linked into libmujoco_ref.so by oracle/Makefile.
+ *
+ * It provides
+ *   - name-based access to every mjModel / mjData array through the reference's X-macro
+ *     lists (include/mujoco/mjxmacro.h:69,183,594,703-760), so the Python tests never
+ *     restate a struct layout;
+ *   - refh_inverse_batch(): the CPU loop that mjb_inverse() replaces, i.e.
+ *         for i in batch: copy (qpos,qvel,qacc)_i -> d ; mj_inverse(m, d) ; copy outputs
+ *     spread over host cores with the reference's own thread pool exactly as SURVEY.md
+ *     §8(d) prescribes (mju_threadPoolCreate src/thread/thread_pool.cc:163, one mjData per
+ *     worker, chunk = max(1, nbatch/(10*P)) following python/mujoco/rollout.cc:308-312).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <mujoco/mujoco.h>
+#include <mujoco/mjxmacro.h>
+#include "thread/thread_pool.h"
+
+#define REFH_API __attribute__((visibility("default")))
+
+enum { REFH_DOUBLE = 0, REFH_INT = 1, REFH_BYTE = 2, REFH_FLOAT = 3, REFH_OTHER = 4 };
+
+#define refh_code_mjtNum REFH_DOUBLE
+#define refh_code_int REFH_INT
+#define refh_code_mjtByte REFH_BYTE
+#define refh_code_float REFH_FLOAT
+#define refh_code_char REFH_BYTE
+#define refh_code_uintptr_t REFH_OTHER
+#define refh_code_mjContact REFH_OTHER
+#define refh_code_mjWarningStat REFH_OTHER
+#define refh_code_mjTimerStat REFH_OTHER
+#define refh_code_mjSolverStat REFH_OTHER
+#define refh_code_size_t REFH_OTHER
+#define refh_code_mjtSize REFH_OTHER
+
+/* ------------------------------------------------------------------ model access */
+
+REFH_API int refh_model_int(const mjModel* m, const char* name, long long* out) {
+#define X(field) if (!strcmp(name, #field)) { *out = (long long)m->field; return 0; }
+  MJMODEL_INTS
+#undef X
+  return -1;
+}
+
+REFH_API int refh_model_array(const mjModel* m, const char* name, const void** ptr,
+                              int* nr, int* nc, int* code) {
+  MJMODEL_POINTERS_PREAMBLE(m)
+  (void)nuser_body; (void)nuser_jnt; (void)nuser_geom; (void)nuser_site; (void)nuser_cam;
+  (void)nuser_tendon; (void)nuser_actuator; (void)nuser_sensor; (void)nq; (void)nv; (void)na;
+  (void)nu; (void)nmocap;
+#define X(type, field, r, c) \
+  if (!strcmp(name, #field)) { *ptr = m->field; *nr = (int)m->r; *nc = (int)(c); *code = refh_code_##type; return 0; }
+  MJMODEL_POINTERS
+#undef X
+  return -1;
+}
+
+REFH_API int refh_opt_num(mjModel* m, const char* name, double** ptr, int* n) {
+#define X(type, field) if (!strcmp(name, #field)) { *ptr = &m->opt.field; *n = 1; return 0; }
+  MJOPTION_FLOATS
+#undef X
+#define X(field, cnt) if (!strcmp(name, #field)) { *ptr = m->opt.field; *n = (cnt); return 0; }
+  MJOPTION_VECTORS
+#undef X
+  return -1;
+}
+
+REFH_API int refh_opt_int(mjModel* m, const char* name, int** ptr) {
+#define X(type, field) if (!strcmp(name, #field)) { *ptr = &m->opt.field; return 0; }
+  MJOPTION_INTS
+#undef X
+  return -1;
+}
+
+/* ------------------------------------------------------------------ data access */
+
+REFH_API int refh_data_int(const mjData* d, const char* name, long long* out) {
+#define X(type, field) if (!strcmp(name, #field)) { *out = (long long)d->field; return 0; }
+  MJDATA_SCALAR
+#undef X
+  return -1;
+}
+
+/* Fixed-size (buffer) arrays and arena arrays of mjData. */
+REFH_API int refh_data_array(const mjModel* m, const mjData* d, const char* name,
+                             const void** ptr, int* nr, int* nc, int* code) {
+  MJDATA_POINTERS_PREAMBLE(m)
+  (void)nv;
+#define X(type, field, r, c) \
+  if (!strcmp(name, #field)) { *ptr = d->field; *nr = (int)m->r; *nc = (int)(c); *code = refh_code_##type; return 0; }
+  MJDATA_POINTERS
+#undef X
+#undef MJ_M
+#undef MJ_D
+#define MJ_M(n) m->n
+#define MJ_D(n) d->n
+#define X(type, field, r, c) \
+  if (!strcmp(name, #field)) { *ptr = d->field; *nr = (int)(r); *nc = (int)(c); *code = refh_code_##type; return 0; }
+  MJDATA_ARENA_POINTERS_SOLVER
+#undef X
+#undef MJ_M
+#undef MJ_D
+#define MJ_M(n) n
+#define MJ_D(n) n
+  return -1;
+}
+
+/* ------------------------------------------------------------------ batch outputs
+ * A request names an mjData field (or a contact_* pseudo-field) and gives an output
+ * buffer with room for `maxrows` rows per state; rows beyond the state's actual row count
+ * are filled with 0 (numbers) / -1 (ints). */
+
+typedef struct {
+  const char* name;
+  void* out;       /* [nbatch][maxrows*nc] of double or int */
+  int maxrows;
+} refhRequest;
+
+enum {
+  CF_NONE = 0, CF_GEOM, CF_DIST, CF_POS, CF_FRAME, CF_DIM, CF_EXCLUDE, CF_EFCADR,
+  CF_INCLUDEMARGIN, CF_FRICTION, CF_SOLREF, CF_SOLREFFRICTION, CF_SOLIMP, CF_MU
+};
+
+static int contact_field(const char* name, int* nc, int* code) {
+  static const struct { const char* n; int id, nc, code; } tab[] = {
+    {"contact_geom", CF_GEOM, 2, REFH_INT}, {"contact_dist", CF_DIST, 1, REFH_DOUBLE},
+    {"contact_pos", CF_POS, 3, REFH_DOUBLE}, {"contact_frame", CF_FRAME, 9, REFH_DOUBLE},
+    {"contact_dim", CF_DIM, 1, REFH_INT}, {"contact_exclude", CF_EXCLUDE, 1, REFH_INT},
+    {"contact_efc_address", CF_EFCADR, 1, REFH_INT},
+    {"contact_includemargin", CF_INCLUDEMARGIN, 1, REFH_DOUBLE},
+    {"contact_friction", CF_FRICTION, 5, REFH_DOUBLE}, {"contact_solref", CF_SOLREF, 2, REFH_DOUBLE},
+    {"contact_solreffriction", CF_SOLREFFRICTION, 2, REFH_DOUBLE},
+    {"contact_solimp", CF_SOLIMP, 5, REFH_DOUBLE}, {"contact_mu", CF_MU, 1, REFH_DOUBLE},
+  };
+  for (size_t i = 0; i < sizeof(tab)/sizeof(tab[0]); i++) {
+    if (!strcmp(name, tab[i].n)) { *nc = tab[i].nc; *code = tab[i].code; return tab[i].id; }
+  }
+  return CF_NONE;
+}
+
+static void copy_contact_field(const mjData* d, int id, int nc, int code, void* out, int maxrows) {
+  for (int r = 0; r < maxrows; r++) {
+    double* od = (double*)out + (size_t)r*nc;
+    int* oi = (int*)out + (size_t)r*nc;
+    if (r >= d->ncon) {
+      for (int c = 0; c < nc; c++) { if (code == REFH_INT) oi[c] = -1; else od[c] = 0; }
+      continue;
+    }
+    const mjContact* con = d->contact + r;
+    switch (id) {
+      case CF_GEOM: oi[0] = con->geom[0]; oi[1] = con->geom[1]; break;
+      case CF_DIST: od[0] = con->dist; break;
+      case CF_POS: memcpy(od, con->pos, 3*sizeof(double)); break;
+      case CF_FRAME: memcpy(od, con->frame, 9*sizeof(double)); break;
+      case CF_DIM: oi[0] = con->dim; break;
+      case CF_EXCLUDE: oi[0] = con->exclude; break;
+      case CF_EFCADR: oi[0] = con->efc_address; break;
+      case CF_INCLUDEMARGIN: od[0] = con->includemargin; break;
+      case CF_FRICTION: memcpy(od, con->friction, 5*sizeof(double)); break;
+      case CF_SOLREF: memcpy(od, con->solref, 2*sizeof(double)); break;
+      case CF_SOLREFFRICTION: memcpy(od, con->solreffriction, 2*sizeof(double)); break;
+      case CF_SOLIMP: memcpy(od, con->solimp, 5*sizeof(double)); break;
+      case CF_MU: od[0] = con->mu; break;
+    }
+  }
+}
+
+/* Returns -1 for an unknown name. */
+static int copy_request(const mjModel* m, const mjData* d, const refhRequest* rq, size_t i) {
+  int nc, code;
+  int cf = contact_field(rq->name, &nc, &code);
+  if (cf != CF_NONE) {
+    size_t esz = code == REFH_INT ? sizeof(int) : sizeof(double);
+    copy_contact_field(d, cf, nc, code, (char*)rq->out + i*(size_t)rq->maxrows*nc*esz, rq->maxrows);
+    return 0;
+  }
+  long long sc;
+  if (!refh_data_int(d, rq->name, &sc)) {   /* scalar ints: ncon, nefc, ne, nf, nl, nJ ... */
+    ((int*)rq->out)[i] = (int)sc;
+    return 0;
+  }
+  const void* ptr; int nr;
+  if (refh_data_array(m, d, rq->name, &ptr, &nr, &nc, &code)) return -1;
+  if (code != REFH_DOUBLE && code != REFH_INT) return -1;
+  size_t esz = code == REFH_INT ? sizeof(int) : sizeof(double);
+  char* out = (char*)rq->out + i*(size_t)rq->maxrows*nc*esz;
+  int rows = nr < rq->maxrows ? nr : rq->maxrows;
+  if (rows > 0) memcpy(out, ptr, (size_t)rows*nc*esz);
+  for (size_t k = (size_t)rows*nc; k < (size_t)rq->maxrows*nc; k++) {
+    if (code == REFH_INT) ((int*)out)[k] = -1; else ((double*)out)[k] = 0;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ the batch loop */
+
+typedef struct {
+  const mjModel* m;
+  mjData** d;             /* one per worker (index = worker id, 0 = calling thread) */
+  mjThreadPool* pool;
+  const double *qpos, *qvel, *qacc;
+  double* qfrc_inverse;   /* may be NULL */
+  const refhRequest* req;
+  int nreq;
+  size_t begin, end;
+  int err;
+} refhChunk;
+
+static void* run_chunk(void* arg) {
+  refhChunk* c = (refhChunk*)arg;
+  const mjModel* m = c->m;
+  size_t wid = c->pool ? mju_threadPoolCurrentWorkerId(c->pool) : 0;
+  mjData* d = c->d[wid];
+  for (size_t i = c->begin; i < c->end; i++) {
+    mju_copy(d->qpos, c->qpos + i*m->nq, m->nq);
+    mju_copy(d->qvel, c->qvel + i*m->nv, m->nv);
+    mju_copy(d->qacc, c->qacc + i*m->nv, m->nv);
+    mj_inverse(m, d);
+    if (c->qfrc_inverse) mju_copy(c->qfrc_inverse + i*m->nv, d->qfrc_inverse, m->nv);
+    for (int r = 0; r < c->nreq; r++) {
+      if (copy_request(m, d, c->req + r, i)) c->err = 1;
+    }
+  }
+  return NULL;
+}
+
+/* Loop mj_inverse over nbatch states with nthread workers; returns wall seconds, <0 on error. */
+REFH_API double refh_inverse_batch(const mjModel* m, long long nbatch, const double* qpos,
+                                   const double* qvel, const double* qacc, double* qfrc_inverse,
+                                   const refhRequest* req, int nreq, int nthread) {
+  if (nthread < 1) nthread = 1;
+  if (nthread > mjMAXTHREAD - 1) nthread = mjMAXTHREAD - 1;
+  mjThreadPool* pool = nthread > 1 ? mju_threadPoolCreate((size_t)nthread) : NULL;
+  int nd = nthread + 1;
+  mjData** d = (mjData**)calloc((size_t)nd, sizeof(mjData*));
+  for (int i = 0; i < nd; i++) d[i] = mj_makeData(m);
+
+  size_t chunk = (size_t)(nbatch/(10*(long long)nthread));
+  if (chunk < 1) chunk = 1;
+  size_t nchunk = ((size_t)nbatch + chunk - 1)/chunk;
+  refhChunk* chunks = (refhChunk*)calloc(nchunk ? nchunk : 1, sizeof(refhChunk));
+  mjTask* tasks = (mjTask*)calloc(nchunk ? nchunk : 1, sizeof(mjTask));
+
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (size_t k = 0; k < nchunk; k++) {
+    refhChunk* c = chunks + k;
+    c->m = m; c->d = d; c->pool = pool;
+    c->qpos = qpos; c->qvel = qvel; c->qacc = qacc; c->qfrc_inverse = qfrc_inverse;
+    c->req = req; c->nreq = nreq;
+    c->begin = k*chunk;
+    c->end = (k + 1)*chunk < (size_t)nbatch ? (k + 1)*chunk : (size_t)nbatch;
+    if (pool) {
+      mju_defaultTask(tasks + k);
+      tasks[k].func = run_chunk;
+      tasks[k].args = c;
+      mju_threadPoolEnqueue(pool, tasks + k);   /* spins when the 640-slot queue is full */
+    } else {
+      run_chunk(c);
+    }
+  }
+  if (pool) for (size_t k = 0; k < nchunk; k++) mju_taskJoin(tasks + k);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+
+  int err = 0;
+  for (size_t k = 0; k < nchunk; k++) err |= chunks[k].err;
+  free(tasks); free(chunks);
+  for (int i = 0; i < nd; i++) mj_deleteData(d[i]);
+  free(d);
+  if (pool) mju_threadPoolDestroy(pool);
+  if (err) return -1.0;
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9*(double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* Per-stage split of one thread's mj_inverse using the reference's own TM_START/TM_END timers
+ * (src/engine/engine_macro.h:35-40, include/mujoco/mjdata.h:67-92). out[mjNTIMER] in seconds. */
+static mjtNum refh_clock(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (mjtNum)t.tv_sec*1e6 + (mjtNum)t.tv_nsec*1e-3;   /* microseconds */
+}
+
+REFH_API void refh_inverse_timers(const mjModel* m, long long nbatch, const double* qpos,
+                                  const double* qvel, const double* qacc, double* out) {
+  mjfTime old = mjcb_time;
+  mjcb_time = refh_clock;
+  mjData* d = mj_makeData(m);
+  for (long long i = 0; i < nbatch; i++) {
+    mju_copy(d->qpos, qpos + i*m->nq, m->nq);
+    mju_copy(d->qvel, qvel + i*m->nv, m->nv);
+    mju_copy(d->qacc, qacc + i*m->nv, m->nv);
+    mj_inverse(m, d);
+  }
+  for (int t = 0; t < mjNTIMER; t++) out[t] = 1e-6*d->timer[t].duration;
+  mj_deleteData(d);
+  mjcb_time = old;
+}
+
+/* forward dynamics + compareFwdInv on one state (restates test/engine/engine_inverse_test.cc:35-56):
+ * returns solver_fwdinv[0..1]. */
+REFH_API void refh_compare_fwdinv(const mjModel* m, const double* qpos, const double* qvel,
+                                  const double* ctrl, int nstep, double fwdinv[2]) {
+  mjData* d = mj_makeData(m);
+  mju_copy(d->qpos, qpos, m->nq);
+  mju_copy(d->qvel, qvel, m->nv);
+  if (ctrl) mju_copy(d->ctrl, ctrl, m->nu);
+  for (int i = 0; i < nstep; i++) mj_step(m, d);
+  mj_forward(m, d);
+  mj_compareFwdInv(m, d);
+  fwdinv[0] = d->solver_fwdinv[0];
+  fwdinv[1] = d->solver_fwdinv[1];
+  mj_deleteData(d);
+}
+
+REFH_API int refh_sizeof_request(void) { return (int)sizeof(refhRequest); }
