@@ -1,0 +1,136 @@
+/* mjb.h -- batched inverse dynamics on NVIDIA B200 behind the MuJoCo 3.3.1 C API.
+ *
+ * Drop-in boundary for the reference fork's inverse-dynamics entry points
+ *   void mj_inverse(const mjModel* m, mjData* d);              include/mujoco/mujoco.h:131
+ *   void mj_inverseSkip(const mjModel*, mjData*, int, int);    include/mujoco/mujoco.h:137
+ * evaluated over `nbatch` independent (qpos, qvel, qacc) states:
+ *
+ *   for (i = 0; i < nbatch; i++) {            // what the caller does today, cf.
+ *     mju_copy(d->qpos, qpos + i*nq, nq);     //   src/inverse/inverse_test.cpp:43-112
+ *     mju_copy(d->qvel, qvel + i*nv, nv);     //   python/mujoco/rollout.cc:73-178
+ *     mju_copy(d->qacc, qacc + i*nv, nv);
+ *     mj_inverse(m, d);
+ *     mju_copy(out + i*nv, d->qfrc_inverse, nv);
+ *   }
+ *
+ * becomes mjb_setState(...); mjb_inverse(m, bd, nbatch); mjb_getQfrcInverse(bd, out).
+ *
+ * The model stays the caller's mjModel (same struct, same headers); one mjbData is the batched
+ * counterpart of mjData and owns the device copies. Like mjData it is not re-entrant: one
+ * mjbData per calling thread. All entry points are plain C (pointers and sizes only).
+ *
+ * Host arrays use the reference's row-major "array of states" layout (nbatch x nq etc., as in
+ * python/mujoco/rollout.cc:41-66). Device arrays are structure-of-arrays: element (row r, state i)
+ * of a field lives at ptr[r*stride + i], stride = mjb_stride(d).
+ */
+#ifndef MJB_H_
+#define MJB_H_
+
+#include <mujoco/mujoco.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define MJB_API __attribute__((visibility("default")))
+
+typedef struct mjbData_ mjbData;
+
+/* which optional per-state outputs mjb_inverse fills (qfrc_inverse is always produced) */
+typedef enum mjbOut_ {
+  mjbOUT_QFRC      = 1 << 0,  /* qfrc_constraint, qfrc_passive                    mjdata.h qfrc_*   */
+  mjbOUT_COUNTS    = 1 << 1,  /* ncon, ne, nf, nl, nefc                                               */
+  mjbOUT_CONTACT   = 1 << 2,  /* contact[].geom, dim, exclude, efc_address, dist, pos, frame          */
+  mjbOUT_EFC       = 1 << 3,  /* efc_type, efc_id, efc_state, efc_pos, margin, D, R, vel, aref, force */
+  mjbOUT_INERTIA   = 1 << 4,  /* qM, qLD, qLDiagInv (mj_crb, mj_factorM)                              */
+  mjbOUT_INTERNAL  = 1 << 5   /* every position/velocity-stage intermediate (xpos ... cfrc), debug    */
+} mjbOut;
+
+/* per-state status bits, the batched form of d->warning[] (engine_forward.c:53-102,
+ * engine_core_constraint.c:68,237,252) */
+typedef enum mjbStatus_ {
+  mjbSTATUS_BADQPOS     = 1 << 0,
+  mjbSTATUS_BADQVEL     = 1 << 1,
+  mjbSTATUS_BADQACC     = 1 << 2,
+  mjbSTATUS_CONTACTFULL = 1 << 3,  /* more contacts than nconmax: contact outputs truncated */
+  mjbSTATUS_CNSTRFULL   = 1 << 4   /* more rows than njmax: efc outputs truncated           */
+} mjbStatus;
+
+/* output fields addressable through mjb_get / mjb_devicePtr */
+typedef enum mjbField_ {
+  mjbF_QFRC_INVERSE = 0,  /* double nv                       */
+  mjbF_QFRC_CONSTRAINT,   /* double nv            (QFRC)     */
+  mjbF_QFRC_PASSIVE,      /* double nv            (QFRC)     */
+  mjbF_COUNTS,            /* int    5: ncon ne nf nl nefc (COUNTS) */
+  mjbF_STATUS,            /* int    1                        */
+  mjbF_CONTACT_GEOM,      /* int    nconmax*2     (CONTACT)  */
+  mjbF_CONTACT_INFO,      /* int    nconmax*3: dim exclude efc_address (CONTACT) */
+  mjbF_CONTACT_NUM,       /* double nconmax*13: dist pos[3] frame[9]   (CONTACT) */
+  mjbF_EFC_INT,           /* int    njmax*3: type id state             (EFC)     */
+  mjbF_EFC_NUM,           /* double njmax*8: pos margin D R vel aref force diagApprox (EFC) */
+  mjbF_QM,                /* double nM            (INERTIA)  */
+  mjbF_QLD,               /* double nC            (INERTIA)  */
+  mjbF_QLDIAGINV,         /* double nv            (INERTIA)  */
+  mjbF_INTERNAL,          /* double mjb_internalSize() (INTERNAL) */
+  mjbF_COUNT
+} mjbField;
+
+/* Validate `m`, flatten its constant tables, upload them to CUDA device `device` and allocate
+ * batch buffers for up to nbatch_max states. Returns NULL and writes a message into err (if not
+ * NULL) when the model uses a feature outside the supported path (convex/mesh/hfield/SDF geom
+ * pairs that survive the static collision filters, flex, plugins, fluid forces, gravity
+ * compensation, spatial tendons, equality constraints, sensors, INVDISCRETE) or when CUDA fails.
+ * nconmax / njmax bound the per-state contact / constraint-row OUTPUT arrays (they do not limit
+ * the physics); pass 0 for defaults. */
+MJB_API mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned outmask,
+                              int nconmax, int njmax, char* err, int err_sz);
+MJB_API void mjb_deleteData(mjbData* d);
+
+/* run subsequent work on this CUDA stream (a cudaStream_t passed as void*); default stream 0 */
+MJB_API void mjb_setStream(mjbData* d, void* cuda_stream);
+
+/* copy nbatch states from HOST arrays (nbatch x nq, nbatch x nv, nbatch x nv) to the device */
+MJB_API int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
+                         const mjtNum* qacc);
+/* adopt DEVICE structure-of-arrays inputs without a copy: (nq|nv) x stride, stride >= nbatch.
+ * Pass NULL pointers to return to the internal buffers. */
+MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel,
+                               const mjtNum* qacc, long long stride);
+
+/* mj_inverse over states [0, nbatch). Returns the number of states with a non-zero status word,
+ * or a negative value on a CUDA error (message via mjb_lastError). Synchronous with respect to
+ * the host only through the getters; the launch itself is asynchronous on the stream. */
+MJB_API int mjb_inverse(const mjModel* m, mjbData* d, int nbatch);
+/* same, without reading back the status count (fully asynchronous) */
+MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
+
+/* copy a field of the last mjb_inverse to a HOST array laid out nbatch x rows (row-major) */
+MJB_API int mjb_get(mjbData* d, int field, void* host_out);
+MJB_API int mjb_getQfrcInverse(mjbData* d, mjtNum* qfrc_inverse);
+/* DEVICE structure-of-arrays view of a field (rows x stride), valid until mjb_deleteData */
+MJB_API const void* mjb_devicePtr(mjbData* d, int field);
+MJB_API int mjb_fieldRows(const mjbData* d, int field);
+MJB_API long long mjb_stride(const mjbData* d);
+
+/* layout of mjbF_INTERNAL: offset (in doubles) and length of a named intermediate, e.g. "xpos",
+ * "cdof", "cvel"; returns -1 for an unknown name */
+MJB_API int mjb_internalSlot(const mjbData* d, const char* name, int* offset, int* size);
+MJB_API int mjb_internalSize(const mjbData* d);
+
+/* candidate geom pairs that survived the static filters, in contact order (for tests/tools) */
+MJB_API int mjb_ncandidate(const mjbData* d);
+MJB_API void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int* func);
+
+MJB_API const char* mjb_lastError(const mjbData* d);
+
+/* wait for the stream */
+MJB_API int mjb_synchronize(mjbData* d);
+
+/* measured FP64 FMA peak of the device in TFLOP/s (roofline denominator; not on the data path) */
+MJB_API double mjb_fp64PeakTflops(int device);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif  /* MJB_H_ */

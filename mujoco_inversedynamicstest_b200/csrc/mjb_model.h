@@ -1,0 +1,257 @@
+// Device-side model image ("model blob") for the batched inverse-dynamics kernels.
+//
+// mjb_makeData() flattens the constant tables of an mjModel that the mj_inverse pipeline reads
+// (reference: include/mujoco/mjmodel.h:593-1155) into ONE contiguous buffer:
+//
+//     [ mjbHdr | int section | double section ]          (16-byte aligned, size % 16 == 0)
+//
+// so a CTA can stage it into shared memory with a single TMA bulk copy (cp.async.bulk) and every
+// thread then reads topology through warp-uniform shared-memory broadcasts. Arrays copied verbatim
+// from mjModel keep their reference names; derived tables (candidate geom pairs with pre-mixed
+// contact parameters, pre-clamped solver parameters, the sparse C layout of qLD) are built once on
+// the host by mjb_upload.cc following the reference functions cited there.
+//
+// This header is shared by host C++ (upload) and device code; it has no dependency on the
+// reference headers.
+#ifndef MJB_MODEL_H_
+#define MJB_MODEL_H_
+
+#include <stdint.h>
+
+// ---- integer arrays copied 1:1 from mjModel (name, rows-expression evaluated on mjModel* m)
+#define MJB_INT_ARRAYS(X)        \
+  X(body_parentid, nbody)        \
+  X(body_rootid, nbody)          \
+  X(body_weldid, nbody)          \
+  X(body_mocapid, nbody)         \
+  X(body_jntnum, nbody)          \
+  X(body_jntadr, nbody)          \
+  X(body_dofnum, nbody)          \
+  X(body_dofadr, nbody)          \
+  X(jnt_type, njnt)              \
+  X(jnt_qposadr, njnt)           \
+  X(jnt_dofadr, njnt)            \
+  X(jnt_bodyid, njnt)            \
+  X(dof_bodyid, nv)              \
+  X(dof_jntid, nv)               \
+  X(dof_parentid, nv)            \
+  X(dof_Madr, nv)                \
+  X(dof_simplenum, nv)           \
+  X(geom_type, ngeom)            \
+  X(geom_bodyid, ngeom)          \
+  X(tendon_adr, ntendon)         \
+  X(tendon_num, ntendon)         \
+  X(wrap_type, nwrap)            \
+  X(wrap_objid, nwrap)
+
+// ---- byte arrays of mjModel widened to int
+#define MJB_BYTE_ARRAYS(X)       \
+  X(body_sameframe, nbody)       \
+  X(jnt_limited, njnt)           \
+  X(jnt_actgravcomp, njnt)       \
+  X(geom_sameframe, ngeom)       \
+  X(tendon_limited, ntendon)
+
+// ---- derived integer tables (built by mjb_upload.cc)
+#define MJB_DERIVED_INT_ARRAYS(X) \
+  X(C_rownnz)  /* nv   : qLD row lengths   (engine_io.c:929-1018)              */ \
+  X(C_rowadr)  /* nv   : qLD row starts                                         */ \
+  X(C_colind)  /* nC   : qLD column indices (ancestors ascending, self last)    */ \
+  X(mapM2C)    /* nC   : qLD[k] = qM[mapM2C[k]] (engine_io.c:1135-1188)         */ \
+  X(cand_int)  /* ncand*MJB_CAND_NI : candidate geom pairs, see MJB_CI_*        */ \
+  X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
+  X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */
+
+// ---- double arrays copied 1:1 from mjModel (name, rows, cols)
+#define MJB_NUM_ARRAYS(X)         \
+  X(qpos0, nq, 1)                 \
+  X(qpos_spring, nq, 1)           \
+  X(body_pos, nbody, 3)           \
+  X(body_quat, nbody, 4)          \
+  X(body_ipos, nbody, 3)          \
+  X(body_iquat, nbody, 4)         \
+  X(body_mass, nbody, 1)          \
+  X(body_inertia, nbody, 3)       \
+  X(body_invweight0, nbody, 2)    \
+  X(body_gravcomp, nbody, 1)      \
+  X(jnt_pos, njnt, 3)             \
+  X(jnt_axis, njnt, 3)            \
+  X(jnt_stiffness, njnt, 1)       \
+  X(jnt_range, njnt, 2)           \
+  X(jnt_margin, njnt, 1)          \
+  X(dof_armature, nv, 1)          \
+  X(dof_damping, nv, 1)           \
+  X(dof_frictionloss, nv, 1)      \
+  X(dof_invweight0, nv, 1)        \
+  X(dof_M0, nv, 1)                \
+  X(geom_size, ngeom, 3)          \
+  X(geom_rbound, ngeom, 1)        \
+  X(geom_pos, ngeom, 3)           \
+  X(geom_quat, ngeom, 4)          \
+  X(tendon_range, ntendon, 2)     \
+  X(tendon_margin, ntendon, 1)    \
+  X(tendon_stiffness, ntendon, 1) \
+  X(tendon_damping, ntendon, 1)   \
+  X(tendon_frictionloss, ntendon, 1) \
+  X(tendon_lengthspring, ntendon, 2) \
+  X(tendon_invweight0, ntendon, 1)   \
+  X(wrap_prm, nwrap, 1)
+
+// ---- derived double tables: pre-clamped solver parameters, MJB_SP_N doubles per record
+#define MJB_DERIVED_NUM_ARRAYS(X) \
+  X(sp_jnt_limit)     /* njnt    */ \
+  X(sp_tendon_limit)  /* ntendon */ \
+  X(sp_dof_friction)  /* nv      */ \
+  X(sp_tendon_friction) /* ntendon */ \
+  X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */
+
+enum {
+#define X(name, rows) MJB_I_##name,
+  MJB_INT_ARRAYS(X)
+  MJB_BYTE_ARRAYS(X)
+#undef X
+#define X(name) MJB_I_##name,
+  MJB_DERIVED_INT_ARRAYS(X)
+#undef X
+  MJB_NI
+};
+
+enum {
+#define X(name, rows, cols) MJB_N_##name,
+  MJB_NUM_ARRAYS(X)
+#undef X
+#define X(name) MJB_N_##name,
+  MJB_DERIVED_NUM_ARRAYS(X)
+#undef X
+  MJB_NN
+};
+
+// solver-parameter record (doubles): solimp after the clamps of getsolparam
+// (engine_core_constraint.c:1379-1384) and K, B of mj_makeImpedance (:1523-1545), which depend
+// only on model constants and opt.timestep.
+enum { MJB_SP_D0 = 0, MJB_SP_D1, MJB_SP_WIDTH, MJB_SP_MID, MJB_SP_POWER, MJB_SP_K, MJB_SP_B, MJB_SP_N };
+
+// candidate geom pair: integer columns
+enum {
+  MJB_CI_G1 = 0,   // geom ids, already ordered so that geom_type[g1] <= geom_type[g2]
+  MJB_CI_G2,
+  MJB_CI_FUNC,     // narrow-phase function id, MJB_FN_*
+  MJB_CI_DIM,      // condim after mj_contactParam / pair_dim
+  MJB_CI_B1,       // geom_bodyid[g1], geom_bodyid[g2]
+  MJB_CI_B2,
+  MJB_CI_FLAGS,    // bit0: both bodies static (contact gets exclude=3, engine_core_constraint.c:1072)
+  MJB_CI_PLANE,    // bit0: g1 is a plane (sphere filter uses plane distance)
+  MJB_CAND_NI
+};
+
+// candidate geom pair: double columns
+enum {
+  MJB_CN_MARGIN = 0,      // mj_assignMargin(max geom_margin) or pair_margin
+  MJB_CN_INCLUDEMARGIN,   // margin - gap
+  MJB_CN_RBOUND,          // geom_rbound[g1] + geom_rbound[g2] + margin (0-plane case: rbound[g2] + margin)
+  MJB_CN_FRICTION,        // 5 doubles after mj_assignFriction
+  MJB_CN_SP = MJB_CN_FRICTION + 5,        // MJB_SP_N doubles for the normal direction
+  MJB_CN_BFRIC = MJB_CN_SP + MJB_SP_N,    // B for elliptic friction rows (solreffriction or solref)
+  MJB_CN_DA_TRAN,         // body_invweight0[2*b1] + body_invweight0[2*b2]
+  MJB_CN_DA_ROT,          // body_invweight0[2*b1+1] + body_invweight0[2*b2+1]
+  MJB_CN_SOLREF,          // 2: contact.solref as stored in mjContact (for output)
+  MJB_CN_SOLIMP = MJB_CN_SOLREF + 2,      // 5: contact.solimp as stored (unclamped)
+  MJB_CAND_NN = MJB_CN_SOLIMP + 5
+};
+
+// narrow-phase function ids (engine_collision_driver.c:41-52, only primitive pairs)
+enum {
+  MJB_FN_PLANE_SPHERE = 0,
+  MJB_FN_PLANE_CAPSULE,
+  MJB_FN_PLANE_CYLINDER,
+  MJB_FN_PLANE_BOX,
+  MJB_FN_PLANE_ELLIPSOID,
+  MJB_FN_SPHERE_SPHERE,
+  MJB_FN_SPHERE_CAPSULE,
+  MJB_FN_SPHERE_CYLINDER,
+  MJB_FN_SPHERE_BOX,
+  MJB_FN_CAPSULE_CAPSULE,
+  MJB_FN_CAPSULE_BOX,
+  MJB_FN_BOX_BOX,
+  MJB_FN_COUNT
+};
+
+// per-thread scratch slots (doubles), offsets in units of one double per thread
+enum {
+  MJB_SC_xpos = 0,     // nbody*3
+  MJB_SC_xquat,        // nbody*4
+  MJB_SC_xmat,         // nbody*9
+  MJB_SC_xipos,        // nbody*3
+  MJB_SC_ximat,        // nbody*9
+  MJB_SC_xanchor,      // njnt*3
+  MJB_SC_xaxis,        // njnt*3
+  MJB_SC_geom_xpos,    // ngeom*3
+  MJB_SC_geom_xmat,    // ngeom*9
+  MJB_SC_subtree_com,  // nbody*3
+  MJB_SC_mass_subtree, // nbody
+  MJB_SC_cinert,       // nbody*10
+  MJB_SC_cdof,         // nv*6
+  MJB_SC_cvel,         // nbody*6
+  MJB_SC_cdof_dot,     // nv*6
+  MJB_SC_cacc_lin,     // nbody*6   sum cdof*qacc over the dof chain (J*qacc carrier)
+  MJB_SC_cacc,         // nbody*6   rne accelerations
+  MJB_SC_cfrc,         // nbody*6   rne body forces
+  MJB_SC_cfrc_ext,     // nbody*6   constraint wrenches on bodies
+  MJB_SC_qfrc_c,       // nv        joint-space constraint force (limits, friction loss, tendons)
+  MJB_SC_qfrc_passive, // nv
+  MJB_SC_ten_length,   // ntendon
+  MJB_SC_ten_velocity, // ntendon
+  MJB_SC_crb,          // nbody*10
+  MJB_SC_qM,           // nM
+  MJB_SC_qLD,          // nC
+  MJB_SC_COUNT
+};
+
+typedef struct mjbHdr_ {
+  uint32_t magic;
+  int32_t bytes;            // total blob size (multiple of 16)
+  // sizes (reference names)
+  int32_t nq, nv, nbody, njnt, ngeom, ntendon, nwrap, neq, nM, nC;
+  int32_t ncand;            // candidate geom pairs
+  int32_t disableflags, enableflags, cone;
+  int32_t has_gravcomp;     // ngravcomp>0 && gravity enabled && |gravity|>0 (engine_passive.c:383)
+  int32_t has_fixed_tendon_only;
+  int32_t nscratch;         // doubles of scratch per thread
+  int32_t pad0;
+  double timestep, impratio;
+  double gravity[3];
+  double pad1;
+  int32_t ioff[MJB_NI];     // element offsets into the int section
+  int32_t noff[MJB_NN];     // element offsets into the double section
+  int32_t scoff[MJB_SC_COUNT];  // scratch slot offsets (doubles per thread)
+  int32_t int_section;      // byte offset of the int section from blob start
+  int32_t num_section;      // byte offset of the double section from blob start
+} mjbHdr;
+
+#define MJB_MAGIC 0x6d6a6231u  /* "mjb1" */
+
+// reference enum values restated (include/mujoco/mjmodel.h:49-82, :85-118, :160-170, :273-292, :379-385)
+enum { MJB_DSBL_CONSTRAINT = 1<<0, MJB_DSBL_EQUALITY = 1<<1, MJB_DSBL_FRICTIONLOSS = 1<<2,
+       MJB_DSBL_LIMIT = 1<<3, MJB_DSBL_CONTACT = 1<<4, MJB_DSBL_PASSIVE = 1<<5,
+       MJB_DSBL_GRAVITY = 1<<6, MJB_DSBL_FILTERPARENT = 1<<9, MJB_DSBL_REFSAFE = 1<<11,
+       MJB_DSBL_SENSOR = 1<<12, MJB_DSBL_MIDPHASE = 1<<13 };
+enum { MJB_ENBL_OVERRIDE = 1<<0, MJB_ENBL_ENERGY = 1<<1, MJB_ENBL_INVDISCRETE = 1<<3 };
+enum { MJB_JNT_FREE = 0, MJB_JNT_BALL, MJB_JNT_SLIDE, MJB_JNT_HINGE };
+enum { MJB_GEOM_PLANE = 0, MJB_GEOM_HFIELD, MJB_GEOM_SPHERE, MJB_GEOM_CAPSULE, MJB_GEOM_ELLIPSOID,
+       MJB_GEOM_CYLINDER, MJB_GEOM_BOX, MJB_GEOM_MESH, MJB_GEOM_SDF };
+enum { MJB_CNSTR_EQUALITY = 0, MJB_CNSTR_FRICTION_DOF, MJB_CNSTR_FRICTION_TENDON,
+       MJB_CNSTR_LIMIT_JOINT, MJB_CNSTR_LIMIT_TENDON, MJB_CNSTR_CONTACT_FRICTIONLESS,
+       MJB_CNSTR_CONTACT_PYRAMIDAL, MJB_CNSTR_CONTACT_ELLIPTIC };
+enum { MJB_STATE_SATISFIED = 0, MJB_STATE_QUADRATIC, MJB_STATE_LINEARNEG, MJB_STATE_LINEARPOS,
+       MJB_STATE_CONE };
+enum { MJB_SAMEFRAME_NONE = 0, MJB_SAMEFRAME_BODY, MJB_SAMEFRAME_INERTIA, MJB_SAMEFRAME_BODYROT,
+       MJB_SAMEFRAME_INERTIAROT };
+enum { MJB_WRAP_JOINT = 1 };
+#define MJB_MINVAL 1E-15
+#define MJB_MINMU 1E-5
+#define MJB_MINIMP 0.0001
+#define MJB_MAXIMP 0.9999
+#define MJB_PI 3.14159265358979323846
+#define MJB_MAXVAL 1E+10
+
+#endif  // MJB_MODEL_H_

@@ -1,0 +1,1421 @@
+// The mj_inverse pipeline for ONE state, written for one CUDA thread per state.
+//
+// Every function below is the per-thread body of a stage of MuJoCo 3.3.1's mj_inverse
+// (reference src/engine/engine_inverse.c:197-261); all control flow that depends only on the
+// model (tree topology, joint types, candidate geom pairs) is warp-uniform, so the 32 lanes of a
+// warp execute the same instruction stream on 32 different states. Intermediates live in a
+// per-thread scratch laid out [slot][MJB_NT] so that lanes touch consecutive doubles.
+//
+// Constraint rows are evaluated WITHOUT forming efc_J: a contact row's J*qvel / J*qacc is the
+// relative spatial velocity / acceleration of the two bodies at the contact point projected on
+// the contact frame (identical to jacdif*q by mj_jac, engine_support.c:389-439), and J'*force is
+// applied as a wrench on the two bodies and folded into the backward pass of mj_rne. Joint and
+// tendon limit rows touch single dofs directly.
+//
+// The file compiles as CUDA device code (nvcc) and, for the CPU-side unit tests only, as plain
+// C++ (tests/hostemu); libmjb.so never contains or calls the host build.
+#ifndef MJB_PIPELINE_H_
+#define MJB_PIPELINE_H_
+
+#include <stddef.h>
+
+#include "mjb_math.h"
+#include "mjb_model.h"
+
+#ifndef MJB_NT
+#error "define MJB_NT (scratch thread-slot stride) before including mjb_pipeline.h"
+#endif
+
+#if defined(__CUDACC__)
+#define MJB_HD __host__ __device__
+#else
+#define MJB_HD
+#endif
+
+namespace mjb {
+
+// status bits (mirrored in include/mjb.h)
+enum { kStatusBadQpos = 1, kStatusBadQvel = 2, kStatusBadQacc = 4, kStatusContactFull = 8,
+       kStatusCnstrFull = 16 };
+
+// optional per-state outputs, all structure-of-arrays [row][stride]
+struct Outputs {
+  double* qfrc_inverse;     // [nv][stride]            always
+  double* qfrc_constraint;  // [nv][stride]            or null
+  double* qfrc_passive;     // [nv][stride]            or null
+  int* counts;              // [5][stride]: ncon, ne, nf, nl, nefc          or null
+  int* status;              // [stride] bit flags
+  // contacts, nconmax rows per state (null when not requested)
+  int* contact_geom;        // [nconmax*2][stride]
+  int* contact_info;        // [nconmax*3][stride]: dim, exclude, efc_address
+  double* contact_num;      // [nconmax*13][stride]: dist, pos[3], frame[9]
+  // constraint rows, njmax rows per state (null when not requested)
+  int* efc_int;             // [njmax*3][stride]: type, id, state
+  double* efc_num;          // [njmax*8][stride]: pos, margin, D, R, vel, aref, force, diagApprox
+  // inertia (null when not requested)
+  double* qM;               // [nM][stride]
+  double* qLD;              // [nC][stride]
+  double* qLDiagInv;        // [nv][stride]
+  // debug dump: every scratch slot copied out as [nscratch][stride] (null when not requested)
+  double* scratch_dump;
+};
+
+struct Ctx {
+  const mjbHdr* H;
+  const int* I;         // int section of the model blob
+  const double* D;      // double section of the model blob
+  double* sc;           // scratch, already offset to this thread's slot
+  const double* qpos;   // already offset to this state
+  const double* qvel;
+  const double* qacc;
+  long long N;          // stride of state-indexed arrays
+  long long s;          // state index
+  int nconmax, njmax;
+  Outputs out;
+  int ncon, ne, nf, nl, nefc, status;
+};
+
+#define MI(name) (c.I + c.H->ioff[MJB_I_##name])
+#define MD(name) (c.D + c.H->noff[MJB_N_##name])
+#define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * (size_t)MJB_NT)
+#define AT(p, k) (p)[(size_t)(k) * (size_t)MJB_NT]
+#define QPOS(i) c.qpos[(size_t)(i) * (size_t)c.N]
+#define QVEL(i) c.qvel[(size_t)(i) * (size_t)c.N]
+#define QACC(i) c.qacc[(size_t)(i) * (size_t)c.N]
+
+MJB_DI void ldn(double* dst, const double* p, int first, int n) {
+  for (int k = 0; k < n; k++) dst[k] = AT(p, first + k);
+}
+MJB_DI void stn(double* p, int first, const double* src, int n) {
+  for (int k = 0; k < n; k++) AT(p, first + k) = src[k];
+}
+
+// engine_util_blas.c:677 with n == 6 (same association as the reference's 4-lane order)
+MJB_DI double dot6(const double* a, const double* b) {
+  double res = (a[0]*b[0] + a[2]*b[2]) + (a[1]*b[1] + a[3]*b[3]);
+  res += a[4]*b[4] + a[5]*b[5];
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_checkPos / mj_checkVel / mj_checkAcc (engine_forward.c:53-102): flag, do not reset
+MJB_HD inline void check_inputs(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  for (int i = 0; i < H.nq; i++) {
+    double v = QPOS(i);
+    if (!(v == v) || v > MJB_MAXVAL || v < -MJB_MAXVAL) c.status |= kStatusBadQpos;
+  }
+  for (int i = 0; i < H.nv; i++) {
+    double v = QVEL(i), a = QACC(i);
+    if (!(v == v) || v > MJB_MAXVAL || v < -MJB_MAXVAL) c.status |= kStatusBadQvel;
+    if (!(a == a) || a > MJB_MAXVAL || a < -MJB_MAXVAL) c.status |= kStatusBadQacc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_kinematics (engine_core_smooth.c:38-178) incl. mj_local2Global (engine_support.c:1565)
+MJB_HD inline void kinematics(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody, ngeom = H.ngeom;
+  double* xpos = SC(xpos); double* xquat = SC(xquat); double* xmat = SC(xmat);
+  double* xipos = SC(xipos); double* ximat = SC(ximat);
+  double* xanchor = SC(xanchor); double* xaxis = SC(xaxis);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_jntadr = MI(body_jntadr);
+  const int* body_jntnum = MI(body_jntnum);
+  const int* body_mocapid = MI(body_mocapid);
+  const int* body_sameframe = MI(body_sameframe);
+  const int* jnt_type = MI(jnt_type);
+  const int* jnt_qposadr = MI(jnt_qposadr);
+  const double* body_pos = MD(body_pos); const double* body_quat = MD(body_quat);
+  const double* body_ipos = MD(body_ipos); const double* body_iquat = MD(body_iquat);
+  const double* jnt_pos = MD(jnt_pos); const double* jnt_axis = MD(jnt_axis);
+  const double* qpos0 = MD(qpos0);
+
+  // world
+  for (int k = 0; k < 3; k++) { AT(xpos, k) = 0; AT(xipos, k) = 0; }
+  AT(xquat, 0) = 1; AT(xquat, 1) = 0; AT(xquat, 2) = 0; AT(xquat, 3) = 0;
+  for (int k = 0; k < 9; k++) { double v = (k % 4 == 0) ? 1.0 : 0.0; AT(xmat, k) = v; AT(ximat, k) = v; }
+
+  for (int b = 1; b < nbody; b++) {
+    double pos[3], quat[4];
+    const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
+
+    if (jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE) {
+      const int qadr = jnt_qposadr[jntadr];
+      for (int k = 0; k < 3; k++) pos[k] = QPOS(qadr + k);
+      for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + 3 + k);
+      normalize4(quat);
+      for (int k = 0; k < 3; k++) {
+        AT(xanchor, 3*jntadr + k) = pos[k];
+        AT(xaxis, 3*jntadr + k) = jnt_axis[3*jntadr + k];
+      }
+    } else {
+      const int pid = body_parentid[b];
+      double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
+      if (body_mocapid[b] >= 0) normalize4(bquat);   // mocap pose = model pose (mj_resetData default)
+      if (pid) {
+        double pm[9], pp[3], pq[4];
+        ldn(pm, xmat, 9*pid, 9); ldn(pp, xpos, 3*pid, 3); ldn(pq, xquat, 4*pid, 4);
+        mulMatVec3(pos, pm, body_pos + 3*b);
+        pos[0] += pp[0]; pos[1] += pp[1]; pos[2] += pp[2];
+        mulQuat(quat, pq, bquat);
+      } else {
+        for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
+        for (int k = 0; k < 4; k++) quat[k] = bquat[k];
+      }
+
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        const int qadr = jnt_qposadr[jid];
+        const int jtype = jnt_type[jid];
+        double ax[3], anc[3];
+        rotVecQuat(ax, jnt_axis + 3*jid, quat);
+        rotVecQuat(anc, jnt_pos + 3*jid, quat);
+        anc[0] += pos[0]; anc[1] += pos[1]; anc[2] += pos[2];
+
+        if (jtype == MJB_JNT_SLIDE) {
+          const double q = QPOS(qadr) - qpos0[qadr];
+          pos[0] += ax[0]*q; pos[1] += ax[1]*q; pos[2] += ax[2]*q;
+        } else {
+          double qloc[4];
+          if (jtype == MJB_JNT_BALL) {
+            for (int k = 0; k < 4; k++) qloc[k] = QPOS(qadr + k);
+            normalize4(qloc);
+          } else {
+            // mju_axisAngle2Quat (engine_util_spatial.c:97)
+            const double angle = QPOS(qadr) - qpos0[qadr];
+            double sn, cs;
+            sincos(angle*0.5, &sn, &cs);
+            qloc[0] = cs;
+            qloc[1] = jnt_axis[3*jid]*sn; qloc[2] = jnt_axis[3*jid+1]*sn; qloc[3] = jnt_axis[3*jid+2]*sn;
+          }
+          mulQuat(quat, quat, qloc);
+          double vec[3];
+          rotVecQuat(vec, jnt_pos + 3*jid, quat);
+          pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
+        }
+        stn(xanchor, 3*jid, anc, 3);
+        stn(xaxis, 3*jid, ax, 3);
+      }
+    }
+
+    normalize4(quat);
+    double mat[9];
+    quat2Mat(mat, quat);
+    stn(xquat, 4*b, quat, 4);
+    stn(xpos, 3*b, pos, 3);
+    stn(xmat, 9*b, mat, 9);
+
+    // inertial frame
+    const int sf = body_sameframe[b];
+    double ip[3], im[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      ip[0] = pos[0]; ip[1] = pos[1]; ip[2] = pos[2];
+    } else {
+      mulMatVec3(ip, mat, body_ipos + 3*b);
+      ip[0] += pos[0]; ip[1] += pos[1]; ip[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, body_iquat + 4*b);
+      quat2Mat(im, tq);
+    } else {
+      for (int k = 0; k < 9; k++) im[k] = mat[k];
+    }
+    stn(xipos, 3*b, ip, 3);
+    stn(ximat, 9*b, im, 9);
+  }
+
+  // geoms
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const int* geom_bodyid = MI(geom_bodyid);
+  const int* geom_sameframe = MI(geom_sameframe);
+  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
+  for (int g = 0; g < ngeom; g++) {
+    const int b = geom_bodyid[g];
+    const int sf = geom_sameframe[g];
+    double gp[3], gm[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      ldn(gp, xpos, 3*b, 3);
+    } else if (sf == MJB_SAMEFRAME_INERTIA) {
+      ldn(gp, xipos, 3*b, 3);
+    } else {
+      double bm[9], bp[3];
+      ldn(bm, xmat, 9*b, 9); ldn(bp, xpos, 3*b, 3);
+      mulMatVec3(gp, bm, geom_pos + 3*g);
+      gp[0] += bp[0]; gp[1] += bp[1]; gp[2] += bp[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double bq[4], tq[4];
+      ldn(bq, xquat, 4*b, 4);
+      mulQuat(tq, bq, geom_quat + 4*g);
+      quat2Mat(gm, tq);
+    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
+      ldn(gm, xmat, 9*b, 9);
+    } else {
+      ldn(gm, ximat, 9*b, 9);
+    }
+    stn(gxpos, 3*g, gp, 3);
+    stn(gxmat, 9*g, gm, 9);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_comPos (engine_core_smooth.c:183-270)
+MJB_HD inline void com_pos(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody, njnt = H.njnt;
+  double* com = SC(subtree_com); double* msub = SC(mass_subtree);
+  double* xipos = SC(xipos); double* ximat = SC(ximat); double* xmat = SC(xmat);
+  double* xanchor = SC(xanchor); double* xaxis = SC(xaxis);
+  double* cinert = SC(cinert); double* cdof = SC(cdof);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_rootid = MI(body_rootid);
+  const double* body_mass = MD(body_mass);
+  const double* body_inertia = MD(body_inertia);
+
+  for (int i = 0; i < nbody; i++) {
+    AT(msub, i) = 0;
+    AT(com, 3*i) = 0; AT(com, 3*i+1) = 0; AT(com, 3*i+2) = 0;
+  }
+  for (int i = nbody - 1; i >= 0; i--) {
+    const double mass = body_mass[i];
+    double ci[3], xi[3];
+    ldn(ci, com, 3*i, 3); ldn(xi, xipos, 3*i, 3);
+    ci[0] += xi[0]*mass; ci[1] += xi[1]*mass; ci[2] += xi[2]*mass;
+    double ms = AT(msub, i) + mass;
+    AT(msub, i) = ms;
+    if (i) {
+      const int j = body_parentid[i];
+      AT(com, 3*j) += ci[0]; AT(com, 3*j+1) += ci[1]; AT(com, 3*j+2) += ci[2];
+      AT(msub, j) += ms;
+    }
+    if (ms < MJB_MINVAL) {
+      ci[0] = xi[0]; ci[1] = xi[1]; ci[2] = xi[2];
+    } else {
+      const double inv = 1.0 / fmax(MJB_MINVAL, ms);
+      ci[0] *= inv; ci[1] *= inv; ci[2] *= inv;
+    }
+    stn(com, 3*i, ci, 3);
+  }
+
+  for (int k = 0; k < 10; k++) AT(cinert, k) = 0;
+  for (int i = 1; i < nbody; i++) {
+    double off[3], xi[3], rc[3], im[9], res[10];
+    ldn(xi, xipos, 3*i, 3); ldn(rc, com, 3*body_rootid[i], 3); ldn(im, ximat, 9*i, 9);
+    off[0] = xi[0] - rc[0]; off[1] = xi[1] - rc[1]; off[2] = xi[2] - rc[2];
+    inertCom(res, body_inertia + 3*i, im, off, body_mass[i]);
+    stn(cinert, 10*i, res, 10);
+  }
+
+  const int* jnt_type = MI(jnt_type);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* jnt_bodyid = MI(jnt_bodyid);
+  for (int j = 0; j < njnt; j++) {
+    const int da = 6*jnt_dofadr[j];
+    const int bi = jnt_bodyid[j];
+    double off[3], rc[3], an[3];
+    ldn(rc, com, 3*body_rootid[bi], 3); ldn(an, xanchor, 3*j, 3);
+    off[0] = rc[0] - an[0]; off[1] = rc[1] - an[1]; off[2] = rc[2] - an[2];
+    const int jt = jnt_type[j];
+    int skip = 0;
+    if (jt == MJB_JNT_FREE) {
+      for (int k = 0; k < 18; k++) AT(cdof, da + k) = 0;
+      for (int i = 0; i < 3; i++) AT(cdof, da + 3 + 7*i) = 1;
+      skip = 18;
+    }
+    if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
+      double bm[9];
+      ldn(bm, xmat, 9*bi, 9);
+      for (int i = 0; i < 3; i++) {
+        double axis[3] = {bm[i], bm[i+3], bm[i+6]};
+        double cr[3];
+        cross3(cr, axis, off);
+        stn(cdof, da + skip + 6*i, axis, 3);
+        stn(cdof, da + skip + 6*i + 3, cr, 3);
+      }
+    } else if (jt == MJB_JNT_SLIDE) {
+      double ax[3];
+      ldn(ax, xaxis, 3*j, 3);
+      AT(cdof, da) = 0; AT(cdof, da+1) = 0; AT(cdof, da+2) = 0;
+      stn(cdof, da + 3, ax, 3);
+    } else {
+      double ax[3], cr[3];
+      ldn(ax, xaxis, 3*j, 3);
+      cross3(cr, ax, off);
+      stn(cdof, da, ax, 3);
+      stn(cdof, da + 3, cr, 3);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fixed tendons of mj_tendon (engine_core_smooth.c:699-723) and ten_velocity = ten_J*qvel
+// (engine_forward.c:205-210); spatial tendons are rejected at upload.
+MJB_HD inline void tendon_fixed(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (!H.ntendon) return;
+  double* L = SC(ten_length); double* V = SC(ten_velocity);
+  const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+  const int* wrap_objid = MI(wrap_objid);
+  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+  const double* wrap_prm = MD(wrap_prm);
+  for (int t = 0; t < H.ntendon; t++) {
+    const int adr = tendon_adr[t], num = tendon_num[t];
+    double len = 0, vel = 0;
+    for (int j = 0; j < num; j++) {
+      const int k = wrap_objid[adr + j];
+      len += wrap_prm[adr + j] * QPOS(jnt_qposadr[k]);
+      vel += wrap_prm[adr + j] * QVEL(jnt_dofadr[k]);
+    }
+    AT(L, t) = len;
+    AT(V, t) = vel;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_comVel (engine_core_smooth.c:1833-1896); also accumulates cacc_lin = sum cdof*qacc along
+// the dof chain, the carrier of J*qacc for point constraints.
+MJB_HD inline void com_vel(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody;
+  double* cvel = SC(cvel); double* cdof = SC(cdof); double* cdof_dot = SC(cdof_dot);
+  double* cal = SC(cacc_lin);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
+  const int* dof_jntid = MI(dof_jntid);
+  const int* jnt_type = MI(jnt_type);
+
+  for (int k = 0; k < 6; k++) { AT(cvel, k) = 0; AT(cal, k) = 0; }
+
+  for (int b = 1; b < nbody; b++) {
+    const int bda = body_dofadr[b];
+    const int dofnum = body_dofnum[b];
+    double v[6], a[6];
+    ldn(v, cvel, 6*body_parentid[b], 6);
+    ldn(a, cal, 6*body_parentid[b], 6);
+
+    for (int j = 0; j < dofnum; j++) {
+      const int jt = jnt_type[dof_jntid[bda + j]];
+      if (jt == MJB_JNT_FREE) {
+        // translational dofs: cdofdot = 0 ; cvel += cdof(0..2)' * qvel(0..2)
+        for (int k = 0; k < 18; k++) AT(cdof_dot, 6*bda + k) = 0;
+        for (int r = 0; r < 3; r++) {
+          const double qv = QVEL(bda + r), qa = QACC(bda + r);
+          double cd[6];
+          ldn(cd, cdof, 6*(bda + r), 6);
+          for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; a[k] += cd[k]*qa; }
+        }
+        j += 3;
+      }
+      if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
+        // all three rotational dofs use the velocity BEFORE this joint's rotation
+        double cd[3][6];
+        for (int r = 0; r < 3; r++) {
+          double dd[6];
+          ldn(cd[r], cdof, 6*(bda + j + r), 6);
+          crossMotion(dd, v, cd[r]);
+          stn(cdof_dot, 6*(bda + j + r), dd, 6);
+        }
+        for (int r = 0; r < 3; r++) {
+          const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
+          for (int k = 0; k < 6; k++) { v[k] += cd[r][k]*qv; a[k] += cd[r][k]*qa; }
+        }
+        j += 2;
+      } else {
+        double cd[6], dd[6];
+        ldn(cd, cdof, 6*(bda + j), 6);
+        crossMotion(dd, v, cd);
+        stn(cdof_dot, 6*(bda + j), dd, 6);
+        const double qv = QVEL(bda + j), qa = QACC(bda + j);
+        for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; a[k] += cd[k]*qa; }
+      }
+    }
+    stn(cvel, 6*b, v, 6);
+    stn(cal, 6*b, a, 6);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_passive: joint springs, dof dampers, tendon spring-dampers (engine_passive.c:57-379,436-497)
+// gravcomp, fluid, flex, callbacks and plugins are rejected at upload.
+MJB_HD inline void passive(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  double* qp = SC(qfrc_passive);
+  const int nv = H.nv;
+  for (int i = 0; i < nv; i++) AT(qp, i) = 0;
+  if (H.disableflags & MJB_DSBL_PASSIVE) return;
+
+  const int* jnt_type = MI(jnt_type);
+  const int* jnt_qposadr = MI(jnt_qposadr);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const double* jnt_stiffness = MD(jnt_stiffness);
+  const double* qpos_spring = MD(qpos_spring);
+  for (int i = 0; i < H.njnt; i++) {
+    const double k = jnt_stiffness[i];
+    if (k == 0) continue;
+    int padr = jnt_qposadr[i], dadr = jnt_dofadr[i];
+    const int jt = jnt_type[i];
+    if (jt == MJB_JNT_FREE) {
+      for (int r = 0; r < 3; r++) AT(qp, dadr + r) = -k*(QPOS(padr + r) - qpos_spring[padr + r]);
+      dadr += 3; padr += 3;
+    }
+    if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
+      double quat[4] = {QPOS(padr), QPOS(padr+1), QPOS(padr+2), QPOS(padr+3)};
+      double dif[3];
+      normalize4(quat);
+      subQuat(dif, quat, qpos_spring + padr);
+      for (int r = 0; r < 3; r++) AT(qp, dadr + r) = -k*dif[r];
+    } else {
+      AT(qp, dadr) = -k*(QPOS(padr) - qpos_spring[padr]);
+    }
+  }
+
+  // qfrc_passive = qfrc_spring + qfrc_damper
+  const double* dof_damping = MD(dof_damping);
+  for (int i = 0; i < nv; i++) {
+    const double dmp = dof_damping[i];
+    if (dmp != 0) AT(qp, i) += -dmp*QVEL(i);
+  }
+
+  if (H.ntendon) {
+    const double* stiff = MD(tendon_stiffness); const double* damp = MD(tendon_damping);
+    const double* ls = MD(tendon_lengthspring);
+    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+    const int* wrap_objid = MI(wrap_objid);
+    const double* wrap_prm = MD(wrap_prm);
+    double* L = SC(ten_length); double* V = SC(ten_velocity);
+    for (int t = 0; t < H.ntendon; t++) {
+      const double ks = stiff[t], kd = damp[t];
+      if (ks == 0 && kd == 0) continue;
+      const double len = AT(L, t), lower = ls[2*t], upper = ls[2*t+1];
+      double fs = 0;
+      if (len > upper) fs = ks*(upper - len);
+      else if (len < lower) fs = ks*(lower - len);
+      const double fd = -kd*AT(V, t);
+      const int adr = tendon_adr[t], num = tendon_num[t];
+      for (int j = 0; j < num; j++) {
+        const int dof = jnt_dofadr[wrap_objid[adr + j]];
+        const double J = wrap_prm[adr + j];
+        // spring and damper are accumulated separately in the reference, then added
+        AT(qp, dof) += J*fs + J*fd;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// constraint-row arithmetic shared by all row types
+
+// getimpedance (engine_core_constraint.c:1441-1489) on pre-clamped solimp
+MJB_HD inline double impedance(const double* sp, double pos, double margin) {
+  const double d0 = sp[MJB_SP_D0], d1 = sp[MJB_SP_D1], width = sp[MJB_SP_WIDTH];
+  if (d0 == d1 || width <= MJB_MINVAL) return 0.5*(d0 + d1);
+  double x = (pos - margin) / width;
+  if (x < 0) x = -x;
+  if (x >= 1 || x <= 0) return x >= 1 ? d1 : d0;
+  const double mid = sp[MJB_SP_MID], p = sp[MJB_SP_POWER];
+  double y;
+  if (p == 1) {
+    y = x;
+  } else if (x <= mid) {
+    // a = 1/power(mid, p-1) ; y = a*power(x, p)
+    const double a = 1/(p == 2 ? mid : pow(mid, p - 1));
+    y = a*(p == 2 ? x*x : pow(x, p));
+  } else {
+    const double b = 1/(p == 2 ? 1 - mid : pow(1 - mid, p - 1));
+    y = 1 - b*(p == 2 ? (1 - x)*(1 - x) : pow(1 - x, p));
+  }
+  return d0 + y*(d1 - d0);
+}
+
+// write one constraint row to the optional efc outputs; returns its row index
+MJB_HD inline int emit_row(Ctx& c, int type, int id, double pos, double margin, double D, double R,
+                           double vel, double aref, double force, int state, double imp) {
+  const int row = c.nefc++;
+  if (c.out.efc_int) {
+    if (row < c.njmax) {
+      const size_t N = (size_t)c.N;
+      int* ei = c.out.efc_int + c.s;
+      double* en = c.out.efc_num + c.s;
+      ei[(size_t)(3*row + 0)*N] = type;
+      ei[(size_t)(3*row + 1)*N] = id;
+      ei[(size_t)(3*row + 2)*N] = state;
+      en[(size_t)(8*row + 0)*N] = pos;
+      en[(size_t)(8*row + 1)*N] = margin;
+      en[(size_t)(8*row + 2)*N] = D;
+      en[(size_t)(8*row + 3)*N] = R;
+      en[(size_t)(8*row + 4)*N] = vel;
+      en[(size_t)(8*row + 5)*N] = aref;
+      en[(size_t)(8*row + 6)*N] = force;
+      en[(size_t)(8*row + 7)*N] = R*imp/(1 - imp);   // efc_diagApprox after mj_makeImpedance:1605
+    } else {
+      c.status |= kStatusCnstrFull;
+    }
+  }
+  return row;
+}
+
+// one scalar row of type friction / limit: returns the constraint force.
+//   pos, margin -> impedance ; dA = diagApprox ; vel = J*qvel ; jacc = J*qacc
+// mj_makeImpedance (engine_core_constraint.c:1494-1608), mj_referenceConstraint (:2362),
+// mj_invConstraint (engine_inverse.c:169) and mj_constraintUpdate (:2387-2457) for this row.
+MJB_HD inline double scalar_row(Ctx& c, int type, int id, const double* sp, double pos,
+                                double margin, double dA, double vel, double jacc, double floss) {
+  const double imp = impedance(sp, pos, margin);
+  const double R = fmax(MJB_MINVAL, (1 - imp)*dA/imp);
+  const double D = 1 / R;
+  const bool isfriction = (type == MJB_CNSTR_FRICTION_DOF || type == MJB_CNSTR_FRICTION_TENDON);
+  const double K = isfriction ? 0.0 : sp[MJB_SP_K];
+  const double aref = -sp[MJB_SP_B]*vel - K*imp*(pos - margin);
+  const double jar = jacc - aref;
+  double force = -D*jar;
+  int state = MJB_STATE_QUADRATIC;
+  if (isfriction) {
+    if (jar <= -R*floss) { force = floss; state = MJB_STATE_LINEARNEG; }
+    else if (jar >= R*floss) { force = -floss; state = MJB_STATE_LINEARPOS; }
+  } else if (type != MJB_CNSTR_EQUALITY) {
+    if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
+  }
+  emit_row(c, type, id, pos, margin, D, R, vel, aref, force, state, imp);
+  return force;
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_instantiateFriction (engine_core_constraint.c:768-819) for dofs and fixed tendons
+MJB_HD inline void friction_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (H.disableflags & MJB_DSBL_FRICTIONLOSS) return;
+  double* qc = SC(qfrc_c);
+  const double* floss = MD(dof_frictionloss);
+  const double* iw = MD(dof_invweight0);
+  const double* sp = MD(sp_dof_friction);
+  for (int i = 0; i < H.nv; i++) {
+    if (floss[i] > 0) {
+      const double f = scalar_row(c, MJB_CNSTR_FRICTION_DOF, i, sp + MJB_SP_N*i, 0, 0, iw[i],
+                                  QVEL(i), QACC(i), floss[i]);
+      AT(qc, i) += f;
+      c.nf++;
+    }
+  }
+  if (H.ntendon) {
+    const double* tfl = MD(tendon_frictionloss);
+    const double* tiw = MD(tendon_invweight0);
+    const double* tsp = MD(sp_tendon_friction);
+    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+    const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
+    const double* wrap_prm = MD(wrap_prm);
+    double* V = SC(ten_velocity);
+    for (int t = 0; t < H.ntendon; t++) {
+      if (tfl[t] > 0) {
+        const int adr = tendon_adr[t], num = tendon_num[t];
+        double jacc = 0;
+        for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
+        const double f = scalar_row(c, MJB_CNSTR_FRICTION_TENDON, t, tsp + MJB_SP_N*t, 0, 0, tiw[t],
+                                    AT(V, t), jacc, tfl[t]);
+        for (int j = 0; j < num; j++) AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
+        c.nf++;
+      }
+    }
+  }
+}
+
+// mj_instantiateLimit (engine_core_constraint.c:824-959)
+MJB_HD inline void limit_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (H.disableflags & MJB_DSBL_LIMIT) return;
+  double* qc = SC(qfrc_c);
+  const int* jnt_limited = MI(jnt_limited);
+  const int* jnt_type = MI(jnt_type);
+  const int* jnt_qposadr = MI(jnt_qposadr);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const double* jnt_range = MD(jnt_range);
+  const double* jnt_margin = MD(jnt_margin);
+  const double* iw = MD(dof_invweight0);
+  const double* sp = MD(sp_jnt_limit);
+  for (int i = 0; i < H.njnt; i++) {
+    if (!jnt_limited[i]) continue;
+    const double margin = jnt_margin[i];
+    const int jt = jnt_type[i];
+    const int dof = jnt_dofadr[i];
+    if (jt == MJB_JNT_SLIDE || jt == MJB_JNT_HINGE) {
+      const double value = QPOS(jnt_qposadr[i]);
+      for (int side = -1; side <= 1; side += 2) {
+        const double dist = side * (jnt_range[2*i + (side + 1)/2] - value);
+        if (dist < margin) {
+          // J = -side at this dof
+          const double f = scalar_row(c, MJB_CNSTR_LIMIT_JOINT, i, sp + MJB_SP_N*i, dist, margin,
+                                      iw[dof], -side*QVEL(dof), -side*QACC(dof), 0);
+          AT(qc, dof) += -side*f;
+          c.nl++;
+        }
+      }
+    } else if (jt == MJB_JNT_BALL) {
+      const int adr = jnt_qposadr[i];
+      double quat[4] = {QPOS(adr), QPOS(adr+1), QPOS(adr+2), QPOS(adr+3)};
+      double aa[3];
+      normalize4(quat);
+      quat2Vel(aa, quat, 1);
+      const double value = normalize3(aa);
+      const double dist = fmax(jnt_range[2*i], jnt_range[2*i+1]) - value;
+      if (dist < margin) {
+        // J = -angleAxis on the three dofs
+        double vel = 0, jacc = 0;
+        for (int r = 0; r < 3; r++) { vel += -aa[r]*QVEL(dof + r); jacc += -aa[r]*QACC(dof + r); }
+        const double f = scalar_row(c, MJB_CNSTR_LIMIT_JOINT, i, sp + MJB_SP_N*i, dist, margin,
+                                    iw[dof], vel, jacc, 0);
+        for (int r = 0; r < 3; r++) AT(qc, dof + r) += -aa[r]*f;
+        c.nl++;
+      }
+    }
+  }
+
+  if (H.ntendon) {
+    const int* tendon_limited = MI(tendon_limited);
+    const double* tendon_range = MD(tendon_range);
+    const double* tendon_margin = MD(tendon_margin);
+    const double* tiw = MD(tendon_invweight0);
+    const double* tsp = MD(sp_tendon_limit);
+    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+    const int* wrap_objid = MI(wrap_objid);
+    const double* wrap_prm = MD(wrap_prm);
+    double* L = SC(ten_length); double* V = SC(ten_velocity);
+    for (int t = 0; t < H.ntendon; t++) {
+      if (!tendon_limited[t]) continue;
+      const double value = AT(L, t), margin = tendon_margin[t];
+      for (int side = -1; side <= 1; side += 2) {
+        const double dist = side * (tendon_range[2*t + (side + 1)/2] - value);
+        if (dist < margin) {
+          const int adr = tendon_adr[t], num = tendon_num[t];
+          double jacc = 0;
+          for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
+          const double f = scalar_row(c, MJB_CNSTR_LIMIT_TENDON, t, tsp + MJB_SP_N*t, dist, margin,
+                                      tiw[t], -side*AT(V, t), -side*jacc, 0);
+          for (int j = 0; j < num; j++) {
+            AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += -side*wrap_prm[adr + j]*f;
+          }
+          c.nl++;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// contacts
+
+struct Con { double dist; double pos[3]; double frame[9]; };
+
+// relative spatial motion of body b2 minus body b1 at point p, from a per-body carrier array
+// (cvel or cacc_lin): lin = (lin2 + ang2 x (p - O2)) - (lin1 + ang1 x (p - O1)), ang = ang2 - ang1
+MJB_HD inline void rel_motion(Ctx& c, const double* carrier, int b1, int b2, const double* p,
+                              double* lin, double* ang) {
+  const int* rootid = MI(body_rootid);
+  double* com = SC(subtree_com);
+  double v1[6], v2[6], o1[3], o2[3], r[3], cr1[3], cr2[3];
+  ldn(v1, carrier, 6*b1, 6); ldn(v2, carrier, 6*b2, 6);
+  ldn(o1, com, 3*rootid[b1], 3); ldn(o2, com, 3*rootid[b2], 3);
+  r[0] = p[0] - o1[0]; r[1] = p[1] - o1[1]; r[2] = p[2] - o1[2];
+  cross3(cr1, v1, r);
+  r[0] = p[0] - o2[0]; r[1] = p[1] - o2[1]; r[2] = p[2] - o2[2];
+  cross3(cr2, v2, r);
+  for (int k = 0; k < 3; k++) {
+    lin[k] = (v2[3+k] + cr2[k]) - (v1[3+k] + cr1[k]);
+    ang[k] = v2[k] - v1[k];
+  }
+}
+
+// add the wrench (torque T about point p, force F at p) to body b2 and its opposite to body b1,
+// expressed in each body's com-based frame:  cfrc_ext[b] += [ (p - O_b) x F + T ; F ]
+MJB_HD inline void apply_wrench(Ctx& c, int b1, int b2, const double* p, const double* F,
+                                const double* T) {
+  const int* rootid = MI(body_rootid);
+  double* com = SC(subtree_com);
+  double* fe = SC(cfrc_ext);
+  double o[3], r[3], cr[3];
+  ldn(o, com, 3*rootid[b2], 3);
+  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+  cross3(cr, r, F);
+  for (int k = 0; k < 3; k++) { AT(fe, 6*b2 + k) += cr[k] + T[k]; AT(fe, 6*b2 + 3 + k) += F[k]; }
+  ldn(o, com, 3*rootid[b1], 3);
+  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+  cross3(cr, r, F);
+  for (int k = 0; k < 3; k++) { AT(fe, 6*b1 + k) -= cr[k] + T[k]; AT(fe, 6*b1 + 3 + k) -= F[k]; }
+}
+
+// One detected contact of candidate pair `ci`: mj_setContact (engine_collision_driver.c:1387),
+// mj_instantiateContact (engine_core_constraint.c:964-1131), mj_diagApprox (:1245-1306),
+// mj_makeImpedance (:1494-1608), mj_referenceConstraint, mj_invConstraint and the contact part of
+// mj_constraintUpdate (:2446-2540), then J'*force as body wrenches.
+MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
+  const mjbHdr& H = *c.H;
+  const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
+  const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
+  const int dim = cint[MJB_CI_DIM];
+  const int b1 = cint[MJB_CI_B1], b2 = cint[MJB_CI_B2];
+  const double includemargin = cn[MJB_CN_INCLUDEMARGIN];
+
+  makeFrame(con.frame);
+  int exclude = (con.dist >= includemargin) ? 1 : 0;
+  const bool constraints_on = !(H.disableflags & MJB_DSBL_CONSTRAINT);  // contacts imply !DSBL_CONTACT
+  int efc_address = -1;
+  if (!exclude && constraints_on && H.nv > 0) {
+    if (cint[MJB_CI_FLAGS] & 1) exclude = 3;     // no dof on either side (NV == 0)
+    else efc_address = c.nefc;
+  }
+
+  const int k = c.ncon++;
+  if (c.out.contact_geom) {
+    if (k < c.nconmax) {
+      const size_t N = (size_t)c.N;
+      int* cg = c.out.contact_geom + c.s;
+      int* cinfo = c.out.contact_info + c.s;
+      double* cnum = c.out.contact_num + c.s;
+      cg[(size_t)(2*k)*N] = cint[MJB_CI_G1];
+      cg[(size_t)(2*k + 1)*N] = cint[MJB_CI_G2];
+      cinfo[(size_t)(3*k)*N] = dim;
+      cinfo[(size_t)(3*k + 1)*N] = exclude;
+      cinfo[(size_t)(3*k + 2)*N] = efc_address;
+      cnum[(size_t)(13*k)*N] = con.dist;
+      for (int j = 0; j < 3; j++) cnum[(size_t)(13*k + 1 + j)*N] = con.pos[j];
+      for (int j = 0; j < 9; j++) cnum[(size_t)(13*k + 4 + j)*N] = con.frame[j];
+    } else {
+      c.status |= kStatusContactFull;
+    }
+  }
+  if (efc_address < 0) return;
+
+  const double* sp = cn + MJB_CN_SP;
+  const double* friction = cn + MJB_CN_FRICTION;
+  const double tran = cn[MJB_CN_DA_TRAN], rot = cn[MJB_CN_DA_ROT];
+  const double imp = impedance(sp, con.dist, includemargin);
+  const double K = sp[MJB_SP_K], B = sp[MJB_SP_B];
+  const double pen = con.dist - includemargin;
+
+  // relative motion in the contact frame: index 0..2 translation, 3..5 rotation
+  double lin[3], ang[3], vel[6], acc[6];
+  rel_motion(c, SC(cvel), b1, b2, con.pos, lin, ang);
+  for (int j = 0; j < 3; j++) {
+    vel[j] = dot3(con.frame + 3*j, lin);
+    vel[3 + j] = dot3(con.frame + 3*j, ang);
+  }
+  rel_motion(c, SC(cacc_lin), b1, b2, con.pos, lin, ang);
+  for (int j = 0; j < 3; j++) {
+    acc[j] = dot3(con.frame + 3*j, lin);
+    acc[3 + j] = dot3(con.frame + 3*j, ang);
+  }
+
+  // force coefficients along the 6 contact-frame directions (J' f)
+  double fc[6] = {0, 0, 0, 0, 0, 0};
+
+  if (dim == 1) {
+    const double R = fmax(MJB_MINVAL, (1 - imp)*tran/imp);
+    const double D = 1/R;
+    const double aref = -B*vel[0] - K*imp*pen;
+    const double jar = acc[0] - aref;
+    double force = -D*jar;
+    int state = MJB_STATE_QUADRATIC;
+    if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
+    emit_row(c, MJB_CNSTR_CONTACT_FRICTIONLESS, k, con.dist, includemargin, D, R, vel[0], aref,
+             force, state, imp);
+    fc[0] = force;
+  } else if (H.cone == 0) {
+    // pyramidal: R of all 2(dim-1) rows = Rpy (engine_core_constraint.c:1557-1597)
+    const double dA0 = tran + friction[0]*friction[0]*tran;
+    const double R0 = fmax(MJB_MINVAL, (1 - imp)*dA0/imp);
+    const double R1 = R0/fmax(MJB_MINVAL, H.impratio);
+    const double mu = friction[0]*sqrt(R1/R0);
+    const double Rpy = 2*mu*mu*R0;
+    const double D = 1/Rpy;
+    for (int j = 1; j < dim; j++) {
+      const double fr = friction[j - 1];
+      for (int sgn = 1; sgn >= -1; sgn -= 2) {
+        const double v = vel[0] + sgn*fr*vel[j];
+        const double a = acc[0] + sgn*fr*acc[j];
+        const double aref = -B*v - K*imp*pen;
+        const double jar = a - aref;
+        double force = -D*jar;
+        int state = MJB_STATE_QUADRATIC;
+        if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
+        emit_row(c, MJB_CNSTR_CONTACT_PYRAMIDAL, k, con.dist, includemargin, D, Rpy, v, aref, force,
+                 state, imp);
+        fc[0] += force;
+        fc[j] += sgn*fr*force;
+      }
+    }
+  } else {
+    // elliptic
+    double R[6], jar[6], aref[6], force[6];
+    const double Bf = cn[MJB_CN_BFRIC];
+    R[0] = fmax(MJB_MINVAL, (1 - imp)*tran/imp);
+    R[1] = R[0]/fmax(MJB_MINVAL, H.impratio);
+    const double mu = friction[0]*sqrt(R[1]/R[0]);
+    for (int j = 1; j < dim - 1; j++) {
+      R[j + 1] = R[1]*friction[0]*friction[0]/(friction[j]*friction[j]);
+    }
+    aref[0] = -B*vel[0] - K*imp*pen;
+    jar[0] = acc[0] - aref[0];
+    for (int j = 1; j < dim; j++) {
+      aref[j] = -Bf*vel[j];   // K = 0, pos = margin = 0 on friction rows
+      jar[j] = acc[j] - aref[j];
+    }
+    for (int j = 0; j < dim; j++) force[j] = -(1/R[j])*jar[j];
+
+    // mj_constraintUpdate elliptic branch (:2459-2540)
+    double U[6];
+    U[0] = jar[0]*mu;
+    double tt = 0;
+    for (int j = 1; j < dim; j++) { U[j] = jar[j]*friction[j - 1]; tt += U[j]*U[j]; }
+    const double Nn = U[0];
+    const double T = sqrt(tt);
+    int state;
+    if (Nn >= mu*T || (T <= 0 && Nn >= 0)) {
+      for (int j = 0; j < dim; j++) force[j] = 0;
+      state = MJB_STATE_SATISFIED;
+    } else if (mu*Nn + T <= 0 || (T <= 0 && Nn < 0)) {
+      state = MJB_STATE_QUADRATIC;
+    } else {
+      const double Dm = (1/R[0]) / (mu*mu*(1 + mu*mu));
+      const double NmT = Nn - mu*T;
+      force[0] = -Dm*NmT*mu;
+      for (int j = 1; j < dim; j++) force[j] = -force[0]/T*U[j]*friction[j - 1];
+      state = MJB_STATE_CONE;
+    }
+    for (int j = 0; j < dim; j++) {
+      emit_row(c, MJB_CNSTR_CONTACT_ELLIPTIC, k, j == 0 ? con.dist : 0.0,
+               j == 0 ? includemargin : 0.0, 1/R[j], R[j], vel[j], aref[j], force[j], state, imp);
+      fc[j] = force[j];
+    }
+  }
+
+  // J' f : world-frame force and torque at the contact point, applied as +/- wrenches
+  double F[3], T3[3];
+  for (int a = 0; a < 3; a++) {
+    F[a] = con.frame[a]*fc[0] + con.frame[3 + a]*fc[1] + con.frame[6 + a]*fc[2];
+    T3[a] = con.frame[a]*fc[3] + con.frame[3 + a]*fc[4] + con.frame[6 + a]*fc[5];
+  }
+  apply_wrench(c, b1, b2, con.pos, F, T3);
+}
+
+// ---- narrow phase: primitives of engine_collision_primitive.c -----------------------------
+
+// mjraw_PlaneSphere (:28)
+MJB_HD inline int plane_sphere(Con* con, double margin, const double* pos1, const double* mat1,
+                               const double* pos2, double radius) {
+  con->frame[0] = mat1[2]; con->frame[1] = mat1[5]; con->frame[2] = mat1[8];
+  double tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  const double cdist = dot3(tmp, con->frame);
+  if (cdist > margin + radius) return 0;
+  con->dist = cdist - radius;
+  const double s = -con->dist/2 - radius;
+  con->pos[0] = pos2[0] + con->frame[0]*s;
+  con->pos[1] = pos2[1] + con->frame[1]*s;
+  con->pos[2] = pos2[2] + con->frame[2]*s;
+  con->frame[3] = 0; con->frame[4] = 0; con->frame[5] = 0;
+  return 1;
+}
+
+// mjc_PlaneCapsule (:64)
+MJB_HD inline int plane_capsule(Con* con, double margin, const double* pos1, const double* mat1,
+                                const double* pos2, const double* mat2, const double* size2) {
+  const double axis[3] = {mat2[2], mat2[5], mat2[8]};
+  const double seg[3] = {size2[1]*axis[0], size2[1]*axis[1], size2[1]*axis[2]};
+  double p[3] = {pos2[0] + seg[0], pos2[1] + seg[1], pos2[2] + seg[2]};
+  const int n1 = plane_sphere(con, margin, pos1, mat1, p, size2[0]);
+  p[0] = pos2[0] - seg[0]; p[1] = pos2[1] - seg[1]; p[2] = pos2[2] - seg[2];
+  const int n2 = plane_sphere(con + n1, margin, pos1, mat1, p, size2[0]);
+  if (n1) { con[0].frame[3] = axis[0]; con[0].frame[4] = axis[1]; con[0].frame[5] = axis[2]; }
+  if (n2) { con[n1].frame[3] = axis[0]; con[n1].frame[4] = axis[1]; con[n1].frame[5] = axis[2]; }
+  return n1 + n2;
+}
+
+// mjc_PlaneCylinder (:95)
+MJB_HD inline int plane_cylinder(Con* con, double margin, const double* pos1, const double* mat1,
+                                 const double* pos2, const double* mat2, const double* size2) {
+  const double normal[3] = {mat1[2], mat1[5], mat1[8]};
+  double axis[3] = {mat2[2], mat2[5], mat2[8]};
+  double prjaxis = dot3(normal, axis);
+  if (prjaxis > 0) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }
+  double vec[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  const double dist0 = dot3(vec, normal);
+  vec[0] = axis[0]*prjaxis - normal[0]; vec[1] = axis[1]*prjaxis - normal[1];
+  vec[2] = axis[2]*prjaxis - normal[2];
+  const double len_sqr = dot3(vec, vec);
+  if (len_sqr >= MJB_MINVAL*MJB_MINVAL) {
+    const double scl = size2[0]/sqrt(len_sqr);
+    vec[0] *= scl; vec[1] *= scl; vec[2] *= scl;
+  } else {
+    vec[0] = mat2[0]*size2[0]; vec[1] = mat2[3]*size2[0]; vec[2] = mat2[6]*size2[0];
+  }
+  const double prjvec = dot3(vec, normal);
+  axis[0] *= size2[1]; axis[1] *= size2[1]; axis[2] *= size2[1];
+  prjaxis *= size2[1];
+
+  int cnt = 0;
+  if (dist0 + prjaxis + prjvec <= margin) {
+    Con& q = con[cnt];
+    q.dist = dist0 + prjaxis + prjvec;
+    for (int k = 0; k < 3; k++) {
+      q.pos[k] = pos2[k] + vec[k]; q.pos[k] += axis[k]; q.pos[k] += normal[k]*(-q.dist*0.5);
+      q.frame[k] = normal[k]; q.frame[3 + k] = 0;
+    }
+    cnt++;
+  } else {
+    return 0;
+  }
+  if (dist0 - prjaxis + prjvec <= margin) {
+    Con& q = con[cnt];
+    q.dist = dist0 - prjaxis + prjvec;
+    for (int k = 0; k < 3; k++) {
+      q.pos[k] = pos2[k] + vec[k]; q.pos[k] -= axis[k]; q.pos[k] += normal[k]*(-q.dist*0.5);
+      q.frame[k] = normal[k]; q.frame[3 + k] = 0;
+    }
+    cnt++;
+  }
+  const double prjvec1 = -prjvec*0.5;
+  if (dist0 + prjaxis + prjvec1 <= margin) {
+    double vec1[3];
+    cross3(vec1, vec, axis);
+    normalize3(vec1);
+    const double sc = size2[0]*sqrt(3.0)/2;
+    vec1[0] *= sc; vec1[1] *= sc; vec1[2] *= sc;
+    for (int pt = 0; pt < 2; pt++) {
+      Con& q = con[cnt];
+      q.dist = dist0 + prjaxis + prjvec1;
+      for (int k = 0; k < 3; k++) {
+        q.pos[k] = pt == 0 ? pos2[k] + vec1[k] : pos2[k] - vec1[k];
+        q.pos[k] += axis[k];
+        q.pos[k] += vec[k]*(-0.5);
+        q.pos[k] += normal[k]*(-q.dist*0.5);
+        q.frame[k] = normal[k]; q.frame[3 + k] = 0;
+      }
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+// mjc_PlaneBox (:200)
+MJB_HD inline int plane_box(Con* con, double margin, const double* pos1, const double* mat1,
+                            const double* pos2, const double* mat2, const double* size2) {
+  const double norm[3] = {mat1[2], mat1[5], mat1[8]};
+  const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  const double dist = dot3(dif, norm);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    double vec[3], corner[3];
+    vec[0] = (i & 1 ? size2[0] : -size2[0]);
+    vec[1] = (i & 2 ? size2[1] : -size2[1]);
+    vec[2] = (i & 4 ? size2[2] : -size2[2]);
+    mulMatVec3(corner, mat2, vec);
+    const double ldist = dot3(norm, corner);
+    if (dist + ldist > margin || ldist > 0) continue;
+    Con& q = con[cnt];
+    q.dist = dist + ldist;
+    for (int k = 0; k < 3; k++) {
+      q.frame[k] = norm[k]; q.frame[3 + k] = 0;
+      corner[k] += pos2[k];
+      q.pos[k] = corner[k] + norm[k]*(-q.dist/2);
+    }
+    if (++cnt >= 4) return 4;
+  }
+  return cnt;
+}
+
+// mjraw_SphereSphere (:250)
+MJB_HD inline int sphere_sphere(Con* con, double margin, const double* pos1, const double* mat1,
+                                double r1, const double* pos2, const double* mat2, double r2) {
+  const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const double cdist_sqr = dot3(dif, dif);
+  const double min_dist = margin + r1 + r2;
+  if (cdist_sqr > min_dist*min_dist) return 0;
+  con->dist = sqrt(cdist_sqr) - r1 - r2;
+  con->frame[0] = pos2[0] - pos1[0]; con->frame[1] = pos2[1] - pos1[1]; con->frame[2] = pos2[2] - pos1[2];
+  const double len = normalize3(con->frame);
+  if (len < MJB_MINVAL) {
+    const double axis1[3] = {mat1[2], mat1[5], mat1[8]};
+    const double axis2[3] = {mat2[2], mat2[5], mat2[8]};
+    cross3(con->frame, axis1, axis2);
+    normalize3(con->frame);
+  }
+  const double s = r1 + con->dist/2;
+  con->pos[0] = con->frame[0]*s + pos1[0];
+  con->pos[1] = con->frame[1]*s + pos1[1];
+  con->pos[2] = con->frame[2]*s + pos1[2];
+  con->frame[3] = 0; con->frame[4] = 0; con->frame[5] = 0;
+  return 1;
+}
+
+MJB_DI double clip(double x, double lo, double hi) {  // mju_clip
+  return fmax(lo, fmin(hi, x));
+}
+
+// mjraw_SphereCapsule (:295)
+MJB_HD inline int sphere_capsule(Con* con, double margin, const double* pos1, const double* mat1,
+                                 const double* size1, const double* pos2, const double* mat2,
+                                 const double* size2) {
+  const double len = size2[1];
+  const double axis[3] = {mat2[2], mat2[5], mat2[8]};
+  double vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const double x = clip(dot3(axis, vec), -len, len);
+  vec[0] = axis[0]*x + pos2[0]; vec[1] = axis[1]*x + pos2[1]; vec[2] = axis[2]*x + pos2[2];
+  return sphere_sphere(con, margin, pos1, mat1, size1[0], vec, mat2, size2[0]);
+}
+
+// mjc_SphereCylinder (:324)
+MJB_HD inline int sphere_cylinder(Con* con, double margin, const double* pos1, const double* mat1,
+                                  const double* size1, const double* pos2, const double* mat2,
+                                  const double* size2) {
+  const double radius = size2[0], height = size2[1];
+  const double axis[3] = {mat2[2], mat2[5], mat2[8]};
+  double vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const double x = dot3(axis, vec);
+  double a_proj[3] = {axis[0]*x, axis[1]*x, axis[2]*x};
+  double p_proj[3] = {vec[0] - a_proj[0], vec[1] - a_proj[1], vec[2] - a_proj[2]};
+  const double p_proj_sqr = dot3(p_proj, p_proj);
+  int collide_side = fabs(x) < height;
+  int collide_cap = p_proj_sqr < radius*radius;
+  if (collide_side && collide_cap) {
+    const double dist_cap = height - fabs(x);
+    const double dist_radius = radius - sqrt(p_proj_sqr);
+    if (dist_cap < dist_radius) collide_side = 0; else collide_cap = 0;
+  }
+  if (collide_side) {
+    a_proj[0] += pos2[0]; a_proj[1] += pos2[1]; a_proj[2] += pos2[2];
+    return sphere_sphere(con, margin, pos1, mat1, size1[0], a_proj, mat2, size2[0]);
+  }
+  if (collide_cap) {
+    double flipmat[9] = {-mat2[0], mat2[1], -mat2[2], -mat2[3], mat2[4], -mat2[5],
+                         -mat2[6], mat2[7], -mat2[8]};
+    double pos_cap[3];
+    const double hs = x > 0 ? height : -height;
+    pos_cap[0] = pos2[0] + axis[0]*hs; pos_cap[1] = pos2[1] + axis[1]*hs; pos_cap[2] = pos2[2] + axis[2]*hs;
+    const int n = plane_sphere(con, margin, pos_cap, x > 0 ? mat2 : flipmat, pos1, size1[0]);
+    if (n) { con->frame[0] = -con->frame[0]; con->frame[1] = -con->frame[1]; con->frame[2] = -con->frame[2]; }
+    return n;
+  }
+  const double scl = size2[0] / sqrt(p_proj_sqr);
+  const double hs = x > 0 ? height : -height;
+  for (int k = 0; k < 3; k++) {
+    p_proj[k] *= scl;
+    vec[k] = axis[k]*hs;
+    vec[k] += p_proj[k];
+    vec[k] += pos2[k];
+  }
+  return sphere_sphere(con, margin, pos1, mat1, size1[0], vec, mat2, 0.0);
+}
+
+// mjraw_CapsuleCapsule (:398)
+MJB_HD inline int capsule_capsule(Con* con, double margin, const double* pos1, const double* mat1,
+                                  const double* size1, const double* pos2, const double* mat2,
+                                  const double* size2) {
+  const double axis1[3] = {mat1[2]*size1[1], mat1[5]*size1[1], mat1[8]*size1[1]};
+  const double axis2[3] = {mat2[2]*size2[1], mat2[5]*size2[1], mat2[8]*size2[1]};
+  const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const double ma = dot3(axis1, axis1);
+  const double mb = -dot3(axis1, axis2);
+  const double mc = dot3(axis2, axis2);
+  const double u = -dot3(axis1, dif);
+  const double v = dot3(axis2, dif);
+  const double det = ma*mc - mb*mb;
+  double vec1[3], vec2[3];
+
+  if (fabs(det) >= MJB_MINVAL) {
+    double x1 = (mc*u - mb*v) / det;
+    double x2 = (ma*v - mb*u) / det;
+    if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; }
+    else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+    if (x2 > 1) { x2 = 1; x1 = clip((u - mb) / ma, -1, 1); }
+    else if (x2 < -1) { x2 = -1; x1 = clip((u + mb) / ma, -1, 1); }
+    for (int k = 0; k < 3; k++) {
+      vec1[k] = axis1[k]*x1 + pos1[k];
+      vec2[k] = axis2[k]*x2 + pos2[k];
+    }
+    return sphere_sphere(con, margin, vec1, mat1, size1[0], vec2, mat2, size2[0]);
+  }
+
+  // parallel axes
+  for (int k = 0; k < 3; k++) vec1[k] = pos1[k] + axis1[k];
+  double x2 = clip((v - mb) / mc, -1, 1);
+  for (int k = 0; k < 3; k++) vec2[k] = axis2[k]*x2 + pos2[k];
+  const int n1 = sphere_sphere(con, margin, vec1, mat1, size1[0], vec2, mat2, size2[0]);
+
+  for (int k = 0; k < 3; k++) vec1[k] = pos1[k] - axis1[k];
+  x2 = clip((v + mb) / mc, -1, 1);
+  for (int k = 0; k < 3; k++) vec2[k] = axis2[k]*x2 + pos2[k];
+  const int n2 = sphere_sphere(con + n1, margin, vec1, mat1, size1[0], vec2, mat2, size2[0]);
+  if (n1 + n2 >= 2) return n1 + n2;
+
+  for (int k = 0; k < 3; k++) vec2[k] = pos2[k] + axis2[k];
+  double x1 = clip((u - mb) / ma, -1, 1);
+  for (int k = 0; k < 3; k++) vec1[k] = axis1[k]*x1 + pos1[k];
+  const int n3 = sphere_sphere(con + n1 + n2, margin, vec1, mat1, size1[0], vec2, mat2, size2[0]);
+  if (n1 + n2 + n3 >= 2) return n1 + n2 + n3;
+
+  for (int k = 0; k < 3; k++) vec2[k] = pos2[k] - axis2[k];
+  x1 = clip((u + mb) / ma, -1, 1);
+  for (int k = 0; k < 3; k++) vec1[k] = axis1[k]*x1 + pos1[k];
+  const int n4 = sphere_sphere(con + n1 + n2 + n3, margin, vec1, mat1, size1[0], vec2, mat2, size2[0]);
+  return n1 + n2 + n3 + n4;
+}
+
+// mj_collision over the static candidate list (engine_collision_driver.c:265-484) followed by the
+// contact rows of mj_makeConstraint. The candidate list already encodes the body-pair filters,
+// explicit pairs, and the reference's contact ordering (see mjb_upload.cc).
+MJB_HD inline void collide_and_contact_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if ((H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) || H.ncand == 0) return;
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const double* geom_size = MD(geom_size);
+  const int* cand_int = MI(cand_int);
+  const double* cand_num = MD(cand_num);
+
+  for (int ci = 0; ci < H.ncand; ci++) {
+    const int* cint = cand_int + MJB_CAND_NI*ci;
+    const double* cn = cand_num + MJB_CAND_NN*ci;
+    const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
+    const double margin = cn[MJB_CN_MARGIN];
+    double pos1[3], pos2[3];
+    ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
+
+    // mj_filterSphere (:146-163)
+    const int planeflag = cint[MJB_CI_PLANE];
+    if (planeflag == 0) {
+      const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+      const double bound = cn[MJB_CN_RBOUND];
+      if (dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound) continue;
+    } else if (planeflag == 1) {
+      // plane vs bounded geom: normal distance of the geom centre
+      const double nrm[3] = {AT(gxmat, 9*g1 + 2), AT(gxmat, 9*g1 + 5), AT(gxmat, 9*g1 + 8)};
+      const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+      if (dot3(dif, nrm) > cn[MJB_CN_RBOUND]) continue;
+    }
+
+    double mat1[9], mat2[9];
+    ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
+    const double* size1 = geom_size + 3*g1;
+    const double* size2 = geom_size + 3*g2;
+    Con con[4];
+    int num = 0;
+    switch (cint[MJB_CI_FUNC]) {
+      case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
+      case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
+      case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
+      case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
+      case MJB_FN_SPHERE_SPHERE:
+        num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
+      case MJB_FN_SPHERE_CAPSULE:
+        num = sphere_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+      case MJB_FN_SPHERE_CYLINDER:
+        num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+      case MJB_FN_CAPSULE_CAPSULE:
+        num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+      default: break;
+    }
+    for (int k = 0; k < num; k++) process_contact(c, ci, con[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_rne(flg_acc=1) (engine_core_smooth.c:1969-2023) fused with the last loop of mj_inverseSkip
+// (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree separately and
+// projected with the same cdof, which is J'*efc_force for the point constraints.
+MJB_HD inline void rne_and_output(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody, nv = H.nv;
+  double* cacc = SC(cacc); double* cfrc = SC(cfrc); double* fext = SC(cfrc_ext);
+  double* cdof = SC(cdof); double* cdof_dot = SC(cdof_dot); double* cvel = SC(cvel);
+  double* cinert = SC(cinert);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
+
+  AT(cacc, 0) = 0; AT(cacc, 1) = 0; AT(cacc, 2) = 0;
+  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+    AT(cacc, 3) = -H.gravity[0]; AT(cacc, 4) = -H.gravity[1]; AT(cacc, 5) = -H.gravity[2];
+  } else {
+    AT(cacc, 3) = 0; AT(cacc, 4) = 0; AT(cacc, 5) = 0;
+  }
+
+  for (int b = 1; b < nbody; b++) {
+    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
+    double acc[6], tmp[6] = {0, 0, 0, 0, 0, 0};
+    // tmp = cdof_dot' * qvel  (mju_mulDofVec: n==1 scales, n>1 accumulates row by row)
+    for (int j = 0; j < dofnum; j++) {
+      const double qv = QVEL(bda + j);
+      double dd[6];
+      ldn(dd, cdof_dot, 6*(bda + j), 6);
+      for (int k = 0; k < 6; k++) tmp[k] += dd[k]*qv;
+    }
+    ldn(acc, cacc, 6*body_parentid[b], 6);
+    for (int k = 0; k < 6; k++) acc[k] += tmp[k];
+    for (int k = 0; k < 6; k++) tmp[k] = 0;
+    for (int j = 0; j < dofnum; j++) {
+      const double qa = QACC(bda + j);
+      double cd[6];
+      ldn(cd, cdof, 6*(bda + j), 6);
+      for (int k = 0; k < 6; k++) tmp[k] += cd[k]*qa;
+    }
+    for (int k = 0; k < 6; k++) acc[k] += tmp[k];
+    stn(cacc, 6*b, acc, 6);
+
+    double ci[10], v[6], f[6], t1[6], t2[6];
+    ldn(ci, cinert, 10*b, 10); ldn(v, cvel, 6*b, 6);
+    mulInertVec(f, ci, acc);
+    mulInertVec(t1, ci, v);
+    crossForce(t2, v, t1);
+    for (int k = 0; k < 6; k++) f[k] += t2[k];
+    stn(cfrc, 6*b, f, 6);
+  }
+
+  // backward accumulation of inertial forces and of constraint wrenches
+  for (int b = nbody - 1; b > 0; b--) {
+    const int p = body_parentid[b];
+    if (p) {
+      for (int k = 0; k < 6; k++) {
+        AT(cfrc, 6*p + k) += AT(cfrc, 6*b + k);
+        AT(fext, 6*p + k) += AT(fext, 6*b + k);
+      }
+    }
+  }
+
+  const int* dof_bodyid = MI(dof_bodyid);
+  const double* armature = MD(dof_armature);
+  double* qc = SC(qfrc_c); double* qp = SC(qfrc_passive);
+  const size_t N = (size_t)c.N;
+  for (int i = 0; i < nv; i++) {
+    const int b = dof_bodyid[i];
+    double cd[6], f[6], w[6];
+    ldn(cd, cdof, 6*i, 6); ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6);
+    const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
+    const double passive_i = AT(qp, i);
+    double res = dot6(cd, f);
+    res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
+    c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
+    if (c.out.qfrc_constraint) c.out.qfrc_constraint[(size_t)i*N + c.s] = qfrc_constraint;
+    if (c.out.qfrc_passive) c.out.qfrc_passive[(size_t)i*N + c.s] = passive_i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_crb (engine_core_smooth.c:1353-1401) and mj_factorM / mj_factorI (:1470-1511)
+MJB_HD inline void inertia(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody, nv = H.nv;
+  double* crb = SC(crb); double* cinert = SC(cinert); double* cdof = SC(cdof);
+  double* qM = SC(qM); double* qLD = SC(qLD);
+  const int* body_parentid = MI(body_parentid);
+  const int* dof_bodyid = MI(dof_bodyid);
+  const int* dof_parentid = MI(dof_parentid);
+  const int* dof_Madr = MI(dof_Madr);
+  const int* dof_simplenum = MI(dof_simplenum);
+  const double* armature = MD(dof_armature);
+  const double* dof_M0 = MD(dof_M0);
+  const size_t N = (size_t)c.N;
+
+  for (int k = 0; k < 10*nbody; k++) AT(crb, k) = AT(cinert, k);
+  for (int i = nbody - 1; i > 0; i--) {
+    const int p = body_parentid[i];
+    if (p > 0) for (int k = 0; k < 10; k++) AT(crb, 10*p + k) += AT(crb, 10*i + k);
+  }
+  for (int k = 0; k < H.nM; k++) AT(qM, k) = 0;
+  for (int i = 0; i < nv; i++) {
+    if (dof_simplenum[i]) {
+      const int n = i + dof_simplenum[i];
+      for (; i < n; i++) AT(qM, dof_Madr[i]) = dof_M0[i];
+      if (i == nv) break;
+    }
+    int adr = dof_Madr[i];
+    AT(qM, adr) = armature[i];
+    double ci[10], cd[6], buf[6];
+    ldn(ci, crb, 10*dof_bodyid[i], 10); ldn(cd, cdof, 6*i, 6);
+    mulInertVec(buf, ci, cd);
+    for (int j = i; j >= 0; j = dof_parentid[j]) {
+      double cj[6];
+      ldn(cj, cdof, 6*j, 6);
+      AT(qM, adr) += dot6(cj, buf);
+      adr++;
+    }
+  }
+  if (c.out.qM) for (int k = 0; k < H.nM; k++) c.out.qM[(size_t)k*N + c.s] = AT(qM, k);
+
+  const int* rownnz = MI(C_rownnz); const int* rowadr = MI(C_rowadr);
+  const int* colind = MI(C_colind); const int* mapM2C = MI(mapM2C);
+  for (int k = 0; k < H.nC; k++) AT(qLD, k) = AT(qM, mapM2C[k]);
+  for (int k = nv - 1; k >= 0; k--) {
+    const int rowadr_k = rowadr[k];
+    const int diag_k = rowadr_k + rownnz[k] - 1;
+    const double invD = 1 / AT(qLD, diag_k);
+    if (c.out.qLDiagInv) c.out.qLDiagInv[(size_t)k*N + c.s] = invD;
+    if (dof_simplenum[k]) continue;
+    for (int adr = diag_k - 1; adr >= rowadr_k; adr--) {
+      const double tmp = AT(qLD, adr) * invD;
+      const int i = colind[adr];
+      const int ra = rowadr[i], n = rownnz[i];
+      for (int e = 0; e < n; e++) AT(qLD, ra + e) += AT(qLD, rowadr_k + e) * (-tmp);
+      AT(qLD, adr) = tmp;
+    }
+  }
+  if (c.out.qLD) for (int k = 0; k < H.nC; k++) c.out.qLD[(size_t)k*N + c.s] = AT(qLD, k);
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_inverseSkip(m, d, mjSTAGE_NONE, skipsensor=1) for one state (engine_inverse.c:197-261)
+MJB_HD inline void inverse_one_state(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
+  c.status = 0;
+  check_inputs(c);
+
+  // mj_invPosition
+  kinematics(c);
+  com_pos(c);
+  tendon_fixed(c);
+  if (c.out.qM || c.out.qLD || c.out.qLDiagInv) inertia(c);
+
+  // mj_invVelocity -> mj_fwdVelocity
+  com_vel(c);
+  passive(c);
+
+  // mj_collision + mj_makeConstraint + mj_referenceConstraint + mj_invConstraint, row by row in
+  // the reference's order: equality, friction loss, limits, contacts
+  {
+    double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext);
+    for (int i = 0; i < H.nv; i++) AT(qc, i) = 0;
+    for (int i = 0; i < 6*H.nbody; i++) AT(fe, i) = 0;
+  }
+  if (!(H.disableflags & MJB_DSBL_CONSTRAINT)) {
+    friction_rows(c);
+    limit_rows(c);
+    collide_and_contact_rows(c);
+  }
+
+  rne_and_output(c);
+
+  const size_t N = (size_t)c.N;
+  if (c.out.counts) {
+    c.out.counts[0*N + c.s] = c.ncon;
+    c.out.counts[1*N + c.s] = c.ne;
+    c.out.counts[2*N + c.s] = c.nf;
+    c.out.counts[3*N + c.s] = c.nl;
+    c.out.counts[4*N + c.s] = c.nefc;
+  }
+  if (c.out.status) c.out.status[c.s] = c.status;
+  if (c.out.scratch_dump) {
+    for (int k = 0; k < H.nscratch; k++) c.out.scratch_dump[(size_t)k*N + c.s] = AT(c.sc, k);
+  }
+}
+
+#undef MI
+#undef MD
+#undef SC
+#undef AT
+#undef QPOS
+#undef QVEL
+#undef QACC
+
+}  // namespace mjb
+
+#endif  // MJB_PIPELINE_H_

@@ -1,0 +1,543 @@
+// Model upload: validate an mjModel and flatten what the batched mj_inverse kernels read into the
+// single device blob described in mjb_model.h.
+//
+// Host-only code; the only file of libmjb.so that sees the reference's struct layouts
+// (<mujoco/mujoco.h>). Runs once per mjb_makeData.
+#include "mjb_upload.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+#include <mujoco/mujoco.h>
+
+#include "mjb_model.h"
+
+namespace mjb {
+namespace {
+
+// engine_collision_driver.c:100
+bool filterBitmask(int contype1, int conaffinity1, int contype2, int conaffinity2) {
+  return !(contype1 & conaffinity2) && !(contype2 & conaffinity1);
+}
+
+// engine_collision_driver.c:168
+bool filterBodyPair(int weldbody1, int weldparent1, int weldbody2, int weldparent2,
+                    bool dsbl_filterparent) {
+  if (weldbody1 == weldbody2) return true;
+  if ((!dsbl_filterparent && weldbody1 != 0 && weldbody2 != 0) &&
+      (weldbody1 == weldparent2 || weldbody2 == weldparent1)) return true;
+  return false;
+}
+
+bool canCollide(const mjModel* m, int b) {  // engine_collision_driver.c:187
+  return m->body_contype[b] || m->body_conaffinity[b];
+}
+
+bool hasPlane(const mjModel* m, int b) {
+  for (int g = m->body_geomadr[b]; g < m->body_geomadr[b] + m->body_geomnum[b]; g++) {
+    if (m->geom_type[g] == mjGEOM_PLANE) return true;
+  }
+  return false;
+}
+
+// add_pair's geom-level contype/conaffinity OR test (engine_collision_driver.c:937-990)
+bool bodyGeomMasksCompatible(const mjModel* m, int b1, int b2) {
+  int ct1 = 0, ca1 = 0, ct2 = 0, ca2 = 0;
+  for (int g = m->body_geomadr[b1]; g < m->body_geomadr[b1] + m->body_geomnum[b1]; g++) {
+    ct1 |= m->geom_contype[g]; ca1 |= m->geom_conaffinity[g];
+  }
+  for (int g = m->body_geomadr[b2]; g < m->body_geomadr[b2] + m->body_geomnum[b2]; g++) {
+    ct2 |= m->geom_contype[g]; ca2 |= m->geom_conaffinity[g];
+  }
+  return (ct1 & ca2) || (ct2 & ca1);
+}
+
+// narrow-phase id of a type-ordered geom pair; -1: no function in the reference's table (pair
+// silently skipped there too); -2: a function this library does not implement
+int narrowphaseId(int t1, int t2) {
+  switch (t1) {
+    case mjGEOM_PLANE:
+      switch (t2) {
+        case mjGEOM_PLANE: case mjGEOM_HFIELD: return -1;
+        case mjGEOM_SPHERE: return MJB_FN_PLANE_SPHERE;
+        case mjGEOM_CAPSULE: return MJB_FN_PLANE_CAPSULE;
+        case mjGEOM_CYLINDER: return MJB_FN_PLANE_CYLINDER;
+        case mjGEOM_BOX: return MJB_FN_PLANE_BOX;
+        default: return -2;
+      }
+    case mjGEOM_HFIELD:
+      return (t2 == mjGEOM_HFIELD) ? -1 : -2;
+    case mjGEOM_SPHERE:
+      switch (t2) {
+        case mjGEOM_SPHERE: return MJB_FN_SPHERE_SPHERE;
+        case mjGEOM_CAPSULE: return MJB_FN_SPHERE_CAPSULE;
+        case mjGEOM_CYLINDER: return MJB_FN_SPHERE_CYLINDER;
+        default: return -2;
+      }
+    case mjGEOM_CAPSULE:
+      switch (t2) {
+        case mjGEOM_CAPSULE: return MJB_FN_CAPSULE_CAPSULE;
+        default: return -2;
+      }
+    default:
+      return -2;
+  }
+}
+
+const char* geomTypeName(int t) {
+  static const char* names[] = {"plane", "hfield", "sphere", "capsule", "ellipsoid", "cylinder",
+                                "box", "mesh", "sdf"};
+  return (t >= 0 && t < 9) ? names[t] : "?";
+}
+
+// getsolparam's reference checks and solimp clamps (engine_core_constraint.c:1362-1384) and the
+// K, B of mj_makeImpedance (:1523-1545), all functions of model constants only.
+void makeSolParam(const mjModel* m, const mjtNum* solref_in, const mjtNum* solimp_in, double* sp) {
+  mjtNum solref[mjNREF] = {solref_in[0], solref_in[1]};
+  mjtNum solimp[mjNIMP];
+  for (int i = 0; i < mjNIMP; i++) solimp[i] = solimp_in[i];
+  if ((solref[0] > 0) ^ (solref[1] > 0)) {   // mixed format: replaced by the default
+    solref[0] = 0.02; solref[1] = 1;         // mj_defaultSolRefImp (engine_io.c)
+  }
+  if (!(m->opt.disableflags & mjDSBL_REFSAFE) && solref[0] > 0) {
+    solref[0] = std::max(solref[0], 2*m->opt.timestep);
+  }
+  solimp[0] = std::min(mjMAXIMP, std::max(mjMINIMP, solimp[0]));
+  solimp[1] = std::min(mjMAXIMP, std::max(mjMINIMP, solimp[1]));
+  solimp[2] = std::max(0.0, solimp[2]);
+  solimp[3] = std::min(mjMAXIMP, std::max(mjMINIMP, solimp[3]));
+  solimp[4] = std::max(1.0, solimp[4]);
+  sp[MJB_SP_D0] = solimp[0];
+  sp[MJB_SP_D1] = solimp[1];
+  sp[MJB_SP_WIDTH] = solimp[2];
+  sp[MJB_SP_MID] = solimp[3];
+  sp[MJB_SP_POWER] = solimp[4];
+  if (solref[0] > 0) {
+    sp[MJB_SP_K] = 1 / std::max(mjMINVAL, solimp[1]*solimp[1] * solref[0]*solref[0] * solref[1]*solref[1]);
+  } else {
+    sp[MJB_SP_K] = -solref[0] / std::max(mjMINVAL, solimp[1]*solimp[1]);
+  }
+  if (solref[1] > 0) {
+    sp[MJB_SP_B] = 2 / std::max(mjMINVAL, solimp[1]*solref[0]);
+  } else {
+    sp[MJB_SP_B] = -solref[1] / std::max(mjMINVAL, solimp[1]);
+  }
+}
+
+struct Candidate {
+  int g1, g2;      // as passed to mj_collideGeoms (before the type swap)
+  int ipair;       // explicit pair index or -1
+};
+
+// mj_contactParam (engine_collision_driver.c:1289-1382) for a dynamic geom pair
+void contactParam(const mjModel* m, int g1, int g2, int* condim, mjtNum* gap, mjtNum* solref,
+                  mjtNum* solimp, mjtNum* friction) {
+  mjtNum fri[3];
+  const int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
+  *gap = std::max(m->geom_gap[g1], m->geom_gap[g2]);
+  if (p1 != p2) {
+    const int g = p1 > p2 ? g1 : g2;
+    *condim = m->geom_condim[g];
+    for (int i = 0; i < mjNREF; i++) solref[i] = m->geom_solref[mjNREF*g + i];
+    for (int i = 0; i < mjNIMP; i++) solimp[i] = m->geom_solimp[mjNIMP*g + i];
+    for (int i = 0; i < 3; i++) fri[i] = m->geom_friction[3*g + i];
+  } else {
+    *condim = std::max(m->geom_condim[g1], m->geom_condim[g2]);
+    const mjtNum s1 = m->geom_solmix[g1], s2 = m->geom_solmix[g2];
+    mjtNum mix;
+    if (s1 >= mjMINVAL && s2 >= mjMINVAL) mix = s1 / (s1 + s2);
+    else if (s1 < mjMINVAL && s2 < mjMINVAL) mix = 0.5;
+    else if (s1 < mjMINVAL) mix = 0.0;
+    else mix = 1.0;
+    const mjtNum* r1 = m->geom_solref + mjNREF*g1;
+    const mjtNum* r2 = m->geom_solref + mjNREF*g2;
+    if (r1[0] > 0 && r2[0] > 0) {
+      for (int i = 0; i < mjNREF; i++) solref[i] = mix*r1[i] + (1 - mix)*r2[i];
+    } else {
+      for (int i = 0; i < mjNREF; i++) solref[i] = std::min(r1[i], r2[i]);
+    }
+    for (int i = 0; i < mjNIMP; i++) {
+      solimp[i] = mix*m->geom_solimp[mjNIMP*g1 + i] + (1 - mix)*m->geom_solimp[mjNIMP*g2 + i];
+    }
+    for (int i = 0; i < 3; i++) fri[i] = std::max(m->geom_friction[3*g1 + i], m->geom_friction[3*g2 + i]);
+  }
+  friction[0] = fri[0]; friction[1] = fri[0]; friction[2] = fri[1]; friction[3] = fri[2];
+  friction[4] = fri[2];
+}
+
+template <typename T>
+void setError(std::string& err, const char* fmt, T a) {
+  char buf[512];
+  std::snprintf(buf, sizeof(buf), fmt, a);
+  err = buf;
+}
+
+}  // namespace
+
+bool isSparseJacobian(const mjModel* m) {  // mj_isSparse (engine_core_constraint.c:99-106)
+  return m->opt.jacobian == mjJAC_SPARSE || (m->opt.jacobian == mjJAC_AUTO && m->nv >= 60);
+}
+
+bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::string& err) {
+  const int dsbl = m->opt.disableflags, enbl = m->opt.enableflags;
+  const bool constraints = !(dsbl & mjDSBL_CONSTRAINT);
+  const bool contacts = constraints && !(dsbl & mjDSBL_CONTACT) && m->nconmax != 0 && m->nbody >= 2;
+
+  // ---- validation: everything outside the supported path is refused here, never approximated
+  if (m->nflex) { err = "flex objects are not supported (nflex > 0)"; return false; }
+  if (m->nplugin) { err = "engine plugins are not supported (nplugin > 0)"; return false; }
+  if (!(dsbl & mjDSBL_PASSIVE) && (m->opt.density > 0 || m->opt.viscosity > 0)) {
+    err = "fluid forces are not supported (opt.density / opt.viscosity > 0)"; return false;
+  }
+  if (!(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
+      (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0)) {
+    err = "gravity compensation is not supported (ngravcomp > 0)"; return false;
+  }
+  if (enbl & mjENBL_INVDISCRETE) { err = "mjENBL_INVDISCRETE is not supported"; return false; }
+  if (m->nsensor && !(dsbl & mjDSBL_SENSOR)) {
+    err = "sensors are not supported (nsensor > 0): set mjDSBL_SENSOR to run without sensordata";
+    return false;
+  }
+  if (m->neq && constraints && !(dsbl & mjDSBL_EQUALITY)) {
+    err = "equality constraints are not supported (neq > 0): set mjDSBL_EQUALITY to run without";
+    return false;
+  }
+  for (int t = 0; t < m->ntendon; t++) {
+    const int adr = m->tendon_adr[t];
+    if (m->wrap_type[adr] != mjWRAP_JOINT) {
+      setError(err, "spatial tendons are not supported (tendon %d)", t); return false;
+    }
+    std::set<int> seen;
+    for (int j = 0; j < m->tendon_num[t]; j++) {
+      if (!seen.insert(m->wrap_objid[adr + j]).second) {
+        setError(err, "fixed tendon %d lists the same joint twice", t); return false;
+      }
+      const int jt = m->jnt_type[m->wrap_objid[adr + j]];
+      if (jt != mjJNT_HINGE && jt != mjJNT_SLIDE) {
+        setError(err, "fixed tendon %d uses a non-scalar joint", t); return false;
+      }
+    }
+  }
+  if (m->nbody >= 65536) { err = "too many bodies for 16-bit pair signatures"; return false; }
+
+  // ---- candidate geom pairs: mj_collision with the broadphase/midphase replaced by the static
+  // superset of body pairs they can return (engine_collision_driver.c:1148-1282, :265-484)
+  std::vector<Candidate> cands;
+  if (contacts) {
+    const bool dsbl_filterparent = dsbl & mjDSBL_FILTERPARENT;
+    std::set<unsigned> sigs;
+    auto add_pair = [&](int b1, int b2) {
+      if (!bodyGeomMasksCompatible(m, b1, b2)) return;
+      sigs.insert(b1 < b2 ? ((unsigned)b1 << 16) + b2 : ((unsigned)b2 << 16) + b1);
+    };
+    for (int b1 = 0; b1 < m->nbody; b1++) {
+      if (!canCollide(m, b1)) continue;
+      if ((b1 == 0 && m->body_geomnum[b1] > 0) || (m->body_weldid[b1] == 0 && hasPlane(m, b1))) {
+        for (int b2 = 0; b2 < m->nbody; b2++) {
+          if (!canCollide(m, b2)) continue;
+          const int weld2 = m->body_weldid[b2];
+          const int parent_weld2 = m->body_weldid[m->body_parentid[weld2]];
+          if (filterBodyPair(0, 0, weld2, parent_weld2, dsbl_filterparent)) continue;
+          add_pair(b1, b2);
+        }
+      }
+    }
+    for (int b1 = 1; b1 < m->nbody; b1++) {
+      if (!canCollide(m, b1)) continue;
+      for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+        if (!canCollide(m, b2)) continue;
+        const int weld1 = m->body_weldid[b1], weld2 = m->body_weldid[b2];
+        const int pw1 = m->body_weldid[m->body_parentid[weld1]];
+        const int pw2 = m->body_weldid[m->body_parentid[weld2]];
+        if (filterBodyPair(weld1, pw1, weld2, pw2, dsbl_filterparent)) continue;
+        add_pair(b1, b2);
+      }
+    }
+
+    int pairadr = 0;
+    const int npair = m->npair;
+    for (unsigned signature : sigs) {
+      const int bf1 = (signature >> 16) & 0xFFFF, bf2 = signature & 0xFFFF;
+      bool merged = false;
+      const int startadr = pairadr;
+      while (pairadr < npair && (unsigned)m->pair_signature[pairadr] <= signature) {
+        if ((unsigned)m->pair_signature[pairadr] == signature) merged = true;
+        cands.push_back({pairadr, -1, pairadr});
+        pairadr++;
+      }
+      if (filterBitmask(m->body_contype[bf1], m->body_conaffinity[bf1], m->body_contype[bf2],
+                        m->body_conaffinity[bf2])) continue;
+      bool excluded = false;
+      for (int e = 0; e < m->nexclude; e++) {
+        if ((unsigned)m->exclude_signature[e] == signature) excluded = true;
+      }
+      if (excluded) continue;
+
+      auto collideGeomPair = [&](int g1, int g2, std::vector<Candidate>& out) {
+        if (merged) {
+          for (int k = startadr; k < pairadr; k++) {
+            if ((m->pair_geom1[k] == g1 && m->pair_geom2[k] == g2) ||
+                (m->pair_geom1[k] == g2 && m->pair_geom2[k] == g1)) return;
+          }
+        }
+        out.push_back({g1, g2, -1});
+      };
+      const int ga1 = m->body_geomadr[bf1], gn1 = m->body_geomnum[bf1];
+      const int ga2 = m->body_geomadr[bf2], gn2 = m->body_geomnum[bf2];
+      if (gn1 == 1 && gn2 == 1) {
+        collideGeomPair(ga1, ga2, cands);
+      } else if (!(dsbl & mjDSBL_MIDPHASE) && m->body_bvhadr[bf1] >= 0 && m->body_bvhadr[bf2] >= 0) {
+        // mj_collideTree visits leaf pairs in BVH order, then contacts are stably sorted by their
+        // STORED (geom[0], geom[1]), i.e. after the type swap of mj_collideGeoms (:227-257,:367)
+        std::vector<Candidate> local;
+        for (int g1 = ga1; g1 < ga1 + gn1; g1++) {
+          for (int g2 = ga2; g2 < ga2 + gn2; g2++) collideGeomPair(g1, g2, local);
+        }
+        auto key = [&](const Candidate& c) {
+          int a = c.g1, b = c.g2;
+          if (m->geom_type[a] > m->geom_type[b]) std::swap(a, b);
+          return std::make_pair(a, b);
+        };
+        std::stable_sort(local.begin(), local.end(),
+                         [&](const Candidate& x, const Candidate& y) { return key(x) < key(y); });
+        cands.insert(cands.end(), local.begin(), local.end());
+      } else {
+        for (int g1 = ga1; g1 < ga1 + gn1; g1++) {
+          for (int g2 = ga2; g2 < ga2 + gn2; g2++) collideGeomPair(g1, g2, cands);
+        }
+      }
+    }
+    while (pairadr < npair) { cands.push_back({pairadr, -1, pairadr}); pairadr++; }
+  }
+
+  // ---- per-candidate static part of mj_collideGeoms (engine_collision_driver.c:1440-1632)
+  const bool override_ = enbl & mjENBL_OVERRIDE;
+  const bool sparse = isSparseJacobian(m);
+  std::vector<int> cand_int;
+  std::vector<double> cand_num;
+  int ncand = 0;
+  for (const Candidate& cd : cands) {
+    int g1 = cd.g1, g2 = cd.g2;
+    const int ipair = cd.ipair;
+    if (ipair >= 0) { g1 = m->pair_geom1[ipair]; g2 = m->pair_geom2[ipair]; }
+    if (m->geom_type[g1] > m->geom_type[g2]) std::swap(g1, g2);
+    const int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+    const int fn = narrowphaseId(t1, t2);
+    if (fn == -1) continue;
+    if (ipair < 0 && filterBitmask(m->geom_contype[g1], m->geom_conaffinity[g1],
+                                   m->geom_contype[g2], m->geom_conaffinity[g2])) continue;
+    if (fn == -2) {
+      char buf[256];
+      std::snprintf(buf, sizeof(buf),
+                    "geom pair (%d:%s, %d:%s) needs a collision function outside the supported "
+                    "primitive set; filter it with contype/conaffinity/<exclude> or disable contacts",
+                    g1, geomTypeName(t1), g2, geomTypeName(t2));
+      err = buf;
+      return false;
+    }
+
+    int condim;
+    mjtNum gap, solref[mjNREF], solimp[mjNIMP], friction[5], solreffriction[mjNREF] = {0, 0};
+    mjtNum margin;
+    if (ipair < 0) {
+      margin = std::max(m->geom_margin[g1], m->geom_margin[g2]);
+      contactParam(m, g1, g2, &condim, &gap, solref, solimp, friction);
+    } else {
+      margin = m->pair_margin[ipair];
+      condim = m->pair_dim[ipair];
+      gap = m->pair_gap[ipair];
+      for (int i = 0; i < mjNREF; i++) solref[i] = m->pair_solref[mjNREF*ipair + i];
+      for (int i = 0; i < mjNIMP; i++) solimp[i] = m->pair_solimp[mjNIMP*ipair + i];
+      for (int i = 0; i < 5; i++) friction[i] = m->pair_friction[5*ipair + i];
+      if (m->pair_solreffriction[mjNREF*ipair] || m->pair_solreffriction[mjNREF*ipair + 1]) {
+        solreffriction[0] = m->pair_solreffriction[mjNREF*ipair];
+        solreffriction[1] = m->pair_solreffriction[mjNREF*ipair + 1];
+      }
+    }
+    if (condim < 1 || condim > 6) {
+      setError(err, "invalid condim %d", condim); return false;
+    }
+    if (override_) {   // mj_assignMargin / Ref / Imp / Friction (engine_core_constraint.c:122-165)
+      margin = m->opt.o_margin;
+      for (int i = 0; i < mjNREF; i++) { solref[i] = m->opt.o_solref[i]; solreffriction[i] = m->opt.o_solref[i]; }
+      for (int i = 0; i < mjNIMP; i++) solimp[i] = m->opt.o_solimp[i];
+      for (int i = 0; i < 5; i++) friction[i] = m->opt.o_friction[i];
+    }
+    for (int i = 0; i < 5; i++) friction[i] = std::max(mjMINMU, friction[i]);
+
+    const int b1 = m->geom_bodyid[g1], b2 = m->geom_bodyid[g2];
+    int ci[MJB_CAND_NI];
+    double cn[MJB_CAND_NN];
+    ci[MJB_CI_G1] = g1; ci[MJB_CI_G2] = g2; ci[MJB_CI_FUNC] = fn; ci[MJB_CI_DIM] = condim;
+    ci[MJB_CI_B1] = b1; ci[MJB_CI_B2] = b2;
+    // NV == 0 only arises for the sparse Jacobian's merged chain (engine_support.c:659-690)
+    const bool static1 = m->body_weldid[b1] == 0, static2 = m->body_weldid[b2] == 0;
+    ci[MJB_CI_FLAGS] = (sparse && static1 && static2) ? 1 : 0;
+    // mj_filterSphere variant (:146-163)
+    const mjtNum rb1 = m->geom_rbound[g1], rb2 = m->geom_rbound[g2];
+    if (rb1 > 0 && rb2 > 0) {
+      ci[MJB_CI_PLANE] = 0;
+      cn[MJB_CN_RBOUND] = rb1 + rb2 + margin;
+    } else if (t1 == mjGEOM_PLANE && rb2 > 0) {
+      ci[MJB_CI_PLANE] = 1;
+      cn[MJB_CN_RBOUND] = margin + rb2;
+    } else {
+      ci[MJB_CI_PLANE] = 2;   // no bounding-sphere test
+      cn[MJB_CN_RBOUND] = 0;
+    }
+    cn[MJB_CN_MARGIN] = margin;
+    cn[MJB_CN_INCLUDEMARGIN] = margin - gap;
+    for (int i = 0; i < 5; i++) cn[MJB_CN_FRICTION + i] = friction[i];
+    makeSolParam(m, solref, solimp, cn + MJB_CN_SP);
+    {
+      // elliptic friction rows use solreffriction when non-zero (:1517-1545); K = 0 there
+      mjtNum ref[mjNREF] = {solref[0], solref[1]};
+      mjtNum srf[mjNREF] = {solreffriction[0], solreffriction[1]};
+      if ((srf[0] > 0) ^ (srf[1] > 0)) { srf[0] = 0; srf[1] = 0; }
+      if (srf[0] || srf[1]) { ref[0] = srf[0]; ref[1] = srf[1]; }
+      double sp2[MJB_SP_N];
+      makeSolParam(m, ref, solimp, sp2);
+      cn[MJB_CN_BFRIC] = sp2[MJB_SP_B];
+    }
+    cn[MJB_CN_DA_TRAN] = m->body_invweight0[2*b1] + m->body_invweight0[2*b2];
+    cn[MJB_CN_DA_ROT] = m->body_invweight0[2*b1 + 1] + m->body_invweight0[2*b2 + 1];
+    for (int i = 0; i < mjNREF; i++) cn[MJB_CN_SOLREF + i] = solref[i];
+    for (int i = 0; i < mjNIMP; i++) cn[MJB_CN_SOLIMP + i] = solimp[i];
+    cand_int.insert(cand_int.end(), ci, ci + MJB_CAND_NI);
+    cand_num.insert(cand_num.end(), cn, cn + MJB_CAND_NN);
+    ncand++;
+  }
+
+  // ---- sparse structure of qLD: row i = ancestors of dof i ascending, then i
+  // (makeDofDofSparse with reduced/upper flags as used for C, engine_io.c:929-1018; mapM2C :1135)
+  const int nv = m->nv;
+  std::vector<int> C_rownnz(nv), C_rowadr(nv), C_colind, mapM2C;
+  for (int i = 0; i < nv; i++) {
+    std::vector<int> chain;
+    for (int j = i; j >= 0; j = m->dof_parentid[j]) chain.push_back(j);
+    C_rownnz[i] = (int)chain.size();
+    C_rowadr[i] = (int)C_colind.size();
+    for (int s = 0; s < (int)chain.size(); s++) {
+      C_colind.push_back(chain[chain.size() - 1 - s]);
+      mapM2C.push_back(m->dof_Madr[i] + (int)chain.size() - 1 - s);
+    }
+  }
+  if ((int)C_colind.size() != m->nC || m->nC != m->nM) {
+    err = "unexpected sparse inertia structure (nC != nM)"; return false;
+  }
+
+  std::vector<int> body_static(m->nbody), jnt_dofnum(m->njnt);
+  for (int b = 0; b < m->nbody; b++) body_static[b] = (m->body_weldid[b] == 0);
+  for (int j = 0; j < m->njnt; j++) {
+    const int t = m->jnt_type[j];
+    jnt_dofnum[j] = t == mjJNT_FREE ? 6 : (t == mjJNT_BALL ? 3 : 1);
+  }
+
+  // solver parameter tables
+  std::vector<double> sp_jnt(MJB_SP_N*m->njnt), sp_tl(MJB_SP_N*m->ntendon),
+      sp_df(MJB_SP_N*nv), sp_tf(MJB_SP_N*m->ntendon);
+  for (int j = 0; j < m->njnt; j++) {
+    makeSolParam(m, m->jnt_solref + mjNREF*j, m->jnt_solimp + mjNIMP*j, sp_jnt.data() + MJB_SP_N*j);
+  }
+  for (int i = 0; i < nv; i++) {
+    makeSolParam(m, m->dof_solref + mjNREF*i, m->dof_solimp + mjNIMP*i, sp_df.data() + MJB_SP_N*i);
+  }
+  for (int t = 0; t < m->ntendon; t++) {
+    makeSolParam(m, m->tendon_solref_lim + mjNREF*t, m->tendon_solimp_lim + mjNIMP*t,
+                 sp_tl.data() + MJB_SP_N*t);
+    makeSolParam(m, m->tendon_solref_fri + mjNREF*t, m->tendon_solimp_fri + mjNIMP*t,
+                 sp_tf.data() + MJB_SP_N*t);
+  }
+
+  // ---- assemble
+  mjbHdr H;
+  std::memset(&H, 0, sizeof(H));
+  H.magic = MJB_MAGIC;
+  H.nq = m->nq; H.nv = nv; H.nbody = m->nbody; H.njnt = m->njnt; H.ngeom = m->ngeom;
+  H.ntendon = m->ntendon; H.nwrap = m->nwrap; H.neq = m->neq; H.nM = m->nM; H.nC = m->nC;
+  H.ncand = ncand;
+  H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
+  H.has_gravcomp = 0;
+  H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
+  for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
+
+  std::vector<int> ints;
+  std::vector<double> nums;
+  auto pushInts = [&](int id, const int* src, size_t n) {
+    H.ioff[id] = (int)ints.size();
+    ints.insert(ints.end(), src, src + n);
+  };
+  auto pushNums = [&](int id, const double* src, size_t n) {
+    H.noff[id] = (int)nums.size();
+    nums.insert(nums.end(), src, src + n);
+  };
+#define X(name, rows) pushInts(MJB_I_##name, m->name, (size_t)m->rows);
+  MJB_INT_ARRAYS(X)
+#undef X
+#define X(name, rows) { std::vector<int> w(m->name, m->name + m->rows); \
+                        pushInts(MJB_I_##name, w.data(), w.size()); }
+  MJB_BYTE_ARRAYS(X)
+#undef X
+  pushInts(MJB_I_C_rownnz, C_rownnz.data(), C_rownnz.size());
+  pushInts(MJB_I_C_rowadr, C_rowadr.data(), C_rowadr.size());
+  pushInts(MJB_I_C_colind, C_colind.data(), C_colind.size());
+  pushInts(MJB_I_mapM2C, mapM2C.data(), mapM2C.size());
+  pushInts(MJB_I_cand_int, cand_int.data(), cand_int.size());
+  pushInts(MJB_I_body_static, body_static.data(), body_static.size());
+  pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
+#define X(name, rows, cols) pushNums(MJB_N_##name, m->name, (size_t)m->rows * (cols));
+  MJB_NUM_ARRAYS(X)
+#undef X
+  pushNums(MJB_N_sp_jnt_limit, sp_jnt.data(), sp_jnt.size());
+  pushNums(MJB_N_sp_tendon_limit, sp_tl.data(), sp_tl.size());
+  pushNums(MJB_N_sp_dof_friction, sp_df.data(), sp_df.size());
+  pushNums(MJB_N_sp_tendon_friction, sp_tf.data(), sp_tf.size());
+  pushNums(MJB_N_cand_num, cand_num.data(), cand_num.size());
+
+  // scratch layout
+  {
+    const int nb = m->nbody, nj = m->njnt, ng = m->ngeom, nt = m->ntendon;
+    int sizes[MJB_SC_COUNT];
+    sizes[MJB_SC_xpos] = 3*nb; sizes[MJB_SC_xquat] = 4*nb; sizes[MJB_SC_xmat] = 9*nb;
+    sizes[MJB_SC_xipos] = 3*nb; sizes[MJB_SC_ximat] = 9*nb;
+    sizes[MJB_SC_xanchor] = 3*nj; sizes[MJB_SC_xaxis] = 3*nj;
+    sizes[MJB_SC_geom_xpos] = 3*ng; sizes[MJB_SC_geom_xmat] = 9*ng;
+    sizes[MJB_SC_subtree_com] = 3*nb; sizes[MJB_SC_mass_subtree] = nb;
+    sizes[MJB_SC_cinert] = 10*nb; sizes[MJB_SC_cdof] = 6*nv; sizes[MJB_SC_cvel] = 6*nb;
+    sizes[MJB_SC_cdof_dot] = 6*nv; sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
+    sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
+    sizes[MJB_SC_qfrc_passive] = nv;
+    sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
+    sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_qM] = m->nM; sizes[MJB_SC_qLD] = m->nC;
+    int off = 0;
+    for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
+    H.nscratch = off;
+  }
+
+  const size_t hdr_bytes = (sizeof(mjbHdr) + 15) & ~(size_t)15;
+  const size_t int_bytes = (ints.size()*sizeof(int) + 15) & ~(size_t)15;
+  const size_t num_bytes = (nums.size()*sizeof(double) + 15) & ~(size_t)15;
+  H.int_section = (int)hdr_bytes;
+  H.num_section = (int)(hdr_bytes + int_bytes);
+  H.bytes = (int)(hdr_bytes + int_bytes + num_bytes);
+  blob.assign((size_t)H.bytes, 0);
+  std::memcpy(blob.data(), &H, sizeof(H));
+  if (!ints.empty()) std::memcpy(blob.data() + H.int_section, ints.data(), ints.size()*sizeof(int));
+  if (!nums.empty()) std::memcpy(blob.data() + H.num_section, nums.data(), nums.size()*sizeof(double));
+  return true;
+}
+
+const char* scratchSlotName(int slot) {
+  static const char* names[MJB_SC_COUNT] = {
+    "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
+    "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cdof_dot", "cacc_lin", "cacc", "cfrc",
+    "cfrc_ext", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "qM", "qLD"};
+  return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
+}
+
+}  // namespace mjb
