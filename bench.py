@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched mj_inverse states/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one mjb_inverse pass over a resident batch of 2^20 synthetic humanoid states per GPU
+(weak scaling: every rank owns its own 2^20-state shard, no data-path collective).
+
+  value   device-resident throughput: states of all ranks / max-over-ranks CUDA-event time of the
+          K timed steps (inputs already in HBM as structure-of-arrays)
+  e2e     the same metric through the public C-ABI with HOST buffers: mjb_setState (H2D from pinned
+          memory + transpose) -> mjb_inverse -> mjb_get(qfrc_inverse) (transpose + D2H), all inside
+          the timed region
+  roofline      FP64 roofline of the fused kernel (the path is fp64-compute bound):
+                executed-flop model x states / CUDA-event time vs the DFMA peak measured in-run
+  roofline_hbm  algorithmic bytes (872 B/state) / time vs MEASURED_PEAKS.json HBM copy bandwidth
+  cpu_baseline  the reference's own mj_inverse looped over the host cores with its thread pool
+                (oracle/_ref), on a bounded sample of the same states
+
+`--impl reference` times only that CPU loop (rank 0) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (golden model, z_range, description)
+    "humanoid_contact_pyramidal": ("humanoid", (0.0, 1.5),
+                                   "humanoid.xml, floor+self contacts, pyramidal cone"),
+    "humanoid_contact_elliptic": ("humanoid_elliptic", (0.0, 1.5),
+                                  "humanoid.xml, floor+self contacts, elliptic cone"),
+    "humanoid_nocontact": ("humanoid_nocontact", (2.0, 3.0),
+                           "humanoid.xml, mjDSBL_CONTACT"),
+    "humanoids22": ("humanoids22", (0.0, 1.5), "22_humanoids.xml (nv=594)"),
+}
+DEFAULT_WORKLOAD = "humanoid_contact_pyramidal"
+BATCH = {"humanoids22": 1 << 15}
+DEFAULT_BATCH = 1 << 20
+
+# FP64 flops executed per state by the fused kernel (dadd + dmul + 2*dfma, thread-level, ncu
+# smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on over a 2^20-state launch divided by
+# the states); see profiles/ and DESIGN.md. Keyed by workload.
+FLOPS_PER_STATE_FILE = os.path.join(ROOT, "profiles", "flops_per_state.json")
+
+
+def load_flops_per_state(workload):
+    try:
+        with open(FLOPS_PER_STATE_FILE) as f:
+            return float(json.load(f)[workload]["flops_per_state"])
+    except Exception:
+        return None
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_reference_model(golden_name):
+    """The reference library's own mjModel for the CPU baseline (oracle/_ref, checker only)."""
+    import gzip
+    import tempfile
+    from oracle import reflib
+    path = os.path.join(ROOT, "tests", "golden", golden_name + ".mjb.gz")
+    with tempfile.NamedTemporaryFile(suffix=".mjb", delete=False) as tf:
+        tf.write(gzip.open(path, "rb").read())
+    try:
+        return reflib.Model.from_mjb(tf.name)
+    finally:
+        os.remove(tf.name)
+
+
+def cpu_reference_rate(golden_name, z_range, nthread, target_seconds=10.0, first=0):
+    """states/s of the reference mj_inverse loop on `nthread` host threads, bounded sample."""
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    rm = load_reference_model(golden_name)
+    probe = 2048
+    qpos, qvel, qacc = generate_states(rm, probe, first=first, z_range=z_range)
+    rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)                 # warm-up
+    _, t = rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+    rate = probe / max(t, 1e-9)
+    n = int(min(max(rate * target_seconds, probe), 4 << 20))
+    qpos, qvel, qacc = generate_states(rm, n, first=first, z_range=z_range)
+    _, t = rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+    return n / t, n, t
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU mj_inverse over the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    golden_name, z_range, desc = WORKLOADS[args.workload]
+    nthread = host_threads()
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    rm = load_reference_model(golden_name)
+    # bounded sample per step: ~2 s of CPU work
+    probe = 2048
+    qpos, qvel, qacc = generate_states(rm, probe, z_range=z_range)
+    rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+    _, t = rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+    n = int(min(max(probe / max(t, 1e-9) * 2.0, probe), 1 << 20))
+    qpos, qvel, qacc = generate_states(rm, n, z_range=z_range)
+    for _ in range(args.warmup):
+        rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+    total = 0.0
+    for _ in range(args.steps):
+        _, t = rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
+        total += t
+    value = n * args.steps / total
+    sample = f"{n} states/step x {args.steps} steps of the {args.workload} stream"
+    line = {
+        "impl": "reference", "metric": "mj_inverse states/sec (humanoid, fp64)", "value": value,
+        "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "states_per_step": n,
+                   "host_threads": nthread},
+        "cpu_baseline": {"value": value, "unit": "states/s", "cores": nthread, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mjb", choices=["mjb", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="states per GPU per step")
+    ap.add_argument("--no-inertia", action="store_true",
+                    help="skip the mj_crb / mj_factorM outputs (qM, qLD, qLDiagInv)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "mjb" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmjb has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    golden_name, z_range, desc = WORKLOADS[args.workload]
+    n = args.batch or BATCH.get(args.workload, DEFAULT_BATCH)
+    model = mjb.Model.from_mjb(os.path.join(ROOT, "tests", "golden", golden_name + ".mjb.gz"))
+    nq, nv = model.int("nq"), model.int("nv")
+    outmask = 0 if args.no_inertia else mjb.OUT_INERTIA
+
+    # this rank's shard of the global state stream: [rank*n, (rank+1)*n)
+    qpos, qvel, qacc = generate_states(model, n, first=rank * n, z_range=z_range)
+    h_qpos = torch.from_numpy(qpos).pin_memory()
+    h_qvel = torch.from_numpy(qvel).pin_memory()
+    h_qacc = torch.from_numpy(qacc).pin_memory()
+    h_out = torch.empty((n, nv), dtype=torch.float64).pin_memory()
+
+    stream = torch.cuda.current_stream()
+    bd = mjb.BatchData(model, n, device=local_rank, outmask=outmask, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value) ----------------
+    bd.set_state_ptr(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr())
+    for _ in range(args.warmup):
+        bd.inverse(sync=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        bd.inverse(sync=False)
+    ev1.record(stream)
+    barrier()
+    kernel_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    got = bd.qfrc_inverse()
+    if not np.isfinite(got).all():
+        raise SystemExit("non-finite qfrc_inverse in the benchmark batch")
+
+    # ---------------- end-to-end through the C-ABI with host buffers ----------------
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        bd.set_state_ptr(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr())
+        bd.inverse(sync=False)
+        bd.get_ptr(mjb.F_QFRC_INVERSE, h_out.data_ptr())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        bd.set_state_ptr(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr())
+        bd.inverse(sync=False)
+        bd.get_ptr(mjb.F_QFRC_INVERSE, h_out.data_ptr())
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([kernel_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_states = n * world
+        value = total_states * args.steps / (kernel_ms * 1e-3)
+        e2e_value = total_states * e2e_steps / (e2e_ms * 1e-3)
+        peaks, peak_src = measured_peaks()
+        per_gpu_rate = n * args.steps / (kernel_ms * 1e-3)
+        fp64_peak = mjb.fp64_peak_tflops(local_rank)
+        fps = load_flops_per_state(args.workload)
+        alg_bytes = 8 * (nq + 2 * nv) + 8 * nv + 4
+        if not args.no_inertia:
+            alg_bytes += 8 * (model.int("nM") + model.int("nC") + nv)
+        roof_fp64 = {
+            "bound": "fp64", "achieved": (per_gpu_rate * fps * 1e-12) if fps else None,
+            "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": (per_gpu_rate * fps * 1e-12 / fp64_peak) if (fps and fp64_peak > 0) else None,
+            "traffic": None, "flops_per_state": fps,
+            "peak_source": "DFMA probe measured in this run (mjb_fp64PeakTflops)"}
+        roof_hbm = {
+            "bound": "hbm", "achieved": per_gpu_rate * alg_bytes * 1e-9, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": per_gpu_rate * alg_bytes * 1e-9 / peaks["hbm_gbs"],
+            "traffic": None, "bytes_per_state": alg_bytes, "peak_source": peak_src}
+        line = {
+            "metric": "mj_inverse states/sec (humanoid, fp64)", "value": value, "unit": "states/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "states_per_gpu": n,
+                       "outputs": "qfrc_inverse" + ("" if args.no_inertia else "+qM+qLD+qLDiagInv"),
+                       "l2": "inputs larger than L2 (%.0f MB per step)" % (n * (nq + 2 * nv) * 8 / 1e6),
+                       "parallelism": f"batch sharded over {world} GPU(s), no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "states/s",
+                    "h2d_bytes_per_step": n * (nq + 2 * nv) * 8, "d2h_bytes_per_step": n * nv * 8,
+                    "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "roofline": roof_fp64,
+            "roofline_hbm": roof_hbm,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                nthread = host_threads()
+                rate, ns, secs = cpu_reference_rate(golden_name, z_range, nthread)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": "states/s", "cores": nthread, "kind": "reference",
+                    "sample": f"first {ns} states of the same stream, {secs:.1f} s, "
+                              "reference mj_inverse + src/thread pool"}
+            except Exception as exc:  # the checker library is absent: say so, do not fake it
+                line["cpu_baseline"] = {"value": None, "unit": "states/s", "cores": 0,
+                                        "kind": "reference", "sample": f"unavailable: {exc}"}
+        print(json.dumps(line), flush=True)
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,239 @@
+"""Python host mirror of the batched inverse-dynamics C-ABI (include/mjb.h).
+
+    model = Model.from_mjb("humanoid.mjb")            # or Model(ptr) around the caller's mjModel*
+    bd = BatchData(model, nbatch_max, outmask=OUT_COUNTS)
+    bd.set_state(qpos, qvel, qacc)                     # host arrays nbatch x nq / nv / nv
+    bd.inverse()                                       # == looping mj_inverse over the batch
+    qfrc = bd.qfrc_inverse()                           # nbatch x nv
+
+Method names follow the reference workflow they replace: python/mujoco/rollout.cc (batched host
+arrays nbatch x nstate) and src/inverse/inverse_test.cpp (mj_inverse per state).
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib
+
+OUT_QFRC, OUT_COUNTS, OUT_CONTACT, OUT_EFC, OUT_INERTIA, OUT_INTERNAL = (1 << i for i in range(6))
+
+STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTRFULL = (
+    1 << i for i in range(5))
+
+(F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
+ F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL) = range(14)
+
+_INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
+_CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
+
+
+class MjbError(RuntimeError):
+    pass
+
+
+class Model:
+    """A `const mjModel*`: either the caller's (from their libmujoco) or one read from an MJB file."""
+
+    def __init__(self, ptr, owned=False, keepalive=None):
+        if not ptr:
+            raise MjbError("null mjModel pointer")
+        self.ptr = ctypes.c_void_p(ptr if isinstance(ptr, int) else ptr.value)
+        self._owned = owned
+        self._keepalive = keepalive
+
+    @classmethod
+    def from_mjb(cls, path):
+        err = ctypes.create_string_buffer(512)
+        if str(path).endswith(".gz"):
+            import gzip
+            with gzip.open(path, "rb") as f:
+                data = f.read()
+            p = lib().mjb_loadModelBuffer(data, len(data), err, 512)
+        else:
+            p = lib().mjb_loadModel(str(path).encode(), err, 512)
+        if not p:
+            raise MjbError(f"mjb_loadModel({path}): {err.value.decode()}")
+        return cls(p, owned=True)
+
+    def __del__(self):
+        try:
+            if self._owned and self.ptr:
+                lib().mjb_freeModel(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+    def int(self, name):
+        v = ctypes.c_longlong()
+        if lib().mjb_modelInt(self.ptr, name.encode(), ctypes.byref(v)):
+            raise KeyError(name)
+        return int(v.value)
+
+    def array(self, name):
+        ptr = ctypes.c_void_p()
+        nr, nc, code = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        if lib().mjb_modelArray(self.ptr, name.encode(), ctypes.byref(ptr), ctypes.byref(nr),
+                                ctypes.byref(nc), ctypes.byref(code)):
+            raise KeyError(name)
+        dt = _CODES[code.value]
+        n = nr.value * nc.value
+        if n == 0 or not ptr.value:
+            return np.zeros((nr.value, nc.value), dtype=dt)
+        buf = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dt).reshape(nr.value, nc.value)
+
+    def get_opt_int(self, name):
+        p = lib().mjb_modelOptInt(self.ptr, name.encode())
+        if not p:
+            raise KeyError(name)
+        return int(p[0])
+
+    def set_opt_int(self, name, value):
+        p = lib().mjb_modelOptInt(self.ptr, name.encode())
+        if not p:
+            raise KeyError(name)
+        p[0] = int(value)
+
+
+class BatchData:
+    """mjbData: the batched counterpart of mjData on one CUDA device."""
+
+    def __init__(self, model, nbatch_max, device=0, outmask=0, nconmax=0, njmax=0, stream=None):
+        self.model = model
+        self.nq, self.nv = model.int("nq"), model.int("nv")
+        err = ctypes.create_string_buffer(1024)
+        self._d = lib().mjb_makeData(model.ptr, int(nbatch_max), int(device), int(outmask),
+                                     int(nconmax), int(njmax), err, 1024)
+        if not self._d:
+            raise MjbError(err.value.decode())
+        self._d = ctypes.c_void_p(self._d)
+        self.nbatch_max = int(nbatch_max)
+        self.nbatch = 0
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_d", None):
+            lib().mjb_deleteData(self._d)
+            self._d = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise MjbError(f"{what}: {lib().mjb_lastError(self._d).decode()}")
+        return rc
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        lib().mjb_setStream(self._d, ctypes.c_void_p(int(cuda_stream)))
+
+    @property
+    def stride(self):
+        return int(lib().mjb_stride(self._d))
+
+    def set_state(self, qpos, qvel, qacc):
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        qacc = np.ascontiguousarray(qacc, dtype=np.float64)
+        n = qpos.shape[0]
+        if qpos.shape != (n, self.nq) or qvel.shape != (n, self.nv) or qacc.shape != (n, self.nv):
+            raise ValueError("expected qpos [n, nq], qvel [n, nv], qacc [n, nv]")
+        self._check(lib().mjb_setState(self._d, n, qpos.ctypes.data, qvel.ctypes.data,
+                                       qacc.ctypes.data), "mjb_setState")
+        self.nbatch = n
+
+    def set_state_ptr(self, n, qpos_ptr, qvel_ptr, qacc_ptr):
+        """Host pointers (e.g. pinned torch tensors) laid out n x nq / n x nv / n x nv."""
+        self._check(lib().mjb_setState(self._d, int(n), ctypes.c_void_p(qpos_ptr),
+                                       ctypes.c_void_p(qvel_ptr), ctypes.c_void_p(qacc_ptr)),
+                    "mjb_setState")
+        self.nbatch = int(n)
+
+    def set_state_device(self, n, qpos_ptr, qvel_ptr, qacc_ptr, stride):
+        """Device structure-of-arrays pointers ((nq|nv) x stride); no copy."""
+        self._check(lib().mjb_setStateDevice(self._d, ctypes.c_void_p(qpos_ptr),
+                                             ctypes.c_void_p(qvel_ptr), ctypes.c_void_p(qacc_ptr),
+                                             int(stride)), "mjb_setStateDevice")
+        self.nbatch = int(n)
+
+    def inverse(self, nbatch=None, sync=True):
+        n = self.nbatch if nbatch is None else int(nbatch)
+        fn = lib().mjb_inverse if sync else lib().mjb_inverseAsync
+        rc = self._check(fn(self.model.ptr, self._d, n), "mjb_inverse")
+        self.nbatch = n
+        return rc
+
+    def synchronize(self):
+        self._check(lib().mjb_synchronize(self._d), "mjb_synchronize")
+
+    def rows(self, field):
+        return int(lib().mjb_fieldRows(self._d, field))
+
+    def device_ptr(self, field):
+        return lib().mjb_devicePtr(self._d, field)
+
+    def get(self, field, out=None):
+        rows = self.rows(field)
+        dt = np.int32 if field in _INT_FIELDS else np.float64
+        if out is None:
+            out = np.empty((self.nbatch, rows), dtype=dt)
+        self._check(lib().mjb_get(self._d, field, out.ctypes.data), "mjb_get")
+        return out
+
+    def get_ptr(self, field, host_ptr):
+        self._check(lib().mjb_get(self._d, field, ctypes.c_void_p(host_ptr)), "mjb_get")
+
+    def qfrc_inverse(self):
+        return self.get(F_QFRC_INVERSE)
+
+    def status(self):
+        return self.get(F_STATUS).ravel()
+
+    def counts(self):
+        """dict of ncon, ne, nf, nl, nefc arrays [nbatch]."""
+        c = self.get(F_COUNTS)
+        return {k: c[:, i] for i, k in enumerate(("ncon", "ne", "nf", "nl", "nefc"))}
+
+    def contacts(self):
+        nc = self.rows(F_CONTACT_GEOM) // 2
+        geom = self.get(F_CONTACT_GEOM).reshape(self.nbatch, nc, 2)
+        info = self.get(F_CONTACT_INFO).reshape(self.nbatch, nc, 3)
+        num = self.get(F_CONTACT_NUM).reshape(self.nbatch, nc, 13)
+        return {"geom": geom, "dim": info[:, :, 0], "exclude": info[:, :, 1],
+                "efc_address": info[:, :, 2], "dist": num[:, :, 0], "pos": num[:, :, 1:4],
+                "frame": num[:, :, 4:13]}
+
+    def efc(self):
+        nj = self.rows(F_EFC_INT) // 3
+        ei = self.get(F_EFC_INT).reshape(self.nbatch, nj, 3)
+        en = self.get(F_EFC_NUM).reshape(self.nbatch, nj, 8)
+        names = ("pos", "margin", "D", "R", "vel", "aref", "force", "diagApprox")
+        out = {"type": ei[:, :, 0], "id": ei[:, :, 1], "state": ei[:, :, 2]}
+        out.update({k: en[:, :, i] for i, k in enumerate(names)})
+        return out
+
+    def internal(self, name):
+        off, size = ctypes.c_int(), ctypes.c_int()
+        if lib().mjb_internalSlot(self._d, name.encode(), ctypes.byref(off), ctypes.byref(size)):
+            raise KeyError(name)
+        full = self.get(F_INTERNAL)
+        return full[:, off.value:off.value + size.value]
+
+    def candidates(self):
+        n = lib().mjb_ncandidate(self._d)
+        out = np.zeros((n, 3), dtype=np.int32)
+        a, b, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        for i in range(n):
+            lib().mjb_candidate(self._d, i, ctypes.byref(a), ctypes.byref(b), ctypes.byref(f))
+            out[i] = (a.value, b.value, f.value)
+        return out
+
+
+def fp64_peak_tflops(device=0):
+    return float(lib().mjb_fp64PeakTflops(int(device)))

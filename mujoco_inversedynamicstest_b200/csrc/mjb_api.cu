@@ -1,0 +1,333 @@
+// C-ABI of libmjb (declared in include/mjb.h): owns device memory, moves states across the host
+// boundary and launches the kernels. No torch types, no C++ types in any signature.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mjb.h"
+#include "mjb_kernels.cuh"
+#include "mjb_upload.h"
+
+struct mjbData_ {
+  int device = 0;
+  cudaStream_t stream = 0;
+  unsigned outmask = 0;
+  int nbatch_max = 0;
+  long long stride = 0;        // row stride of the internal SoA buffers
+  int nconmax = 0, njmax = 0;
+  int last_nbatch = 0;
+  mjbHdr hdr;                  // host copy of the model header
+  std::vector<int> cand;       // host copy of candidate (g1, g2, func)
+  unsigned char* d_model = nullptr;
+  int model_bytes = 0;
+  int model_in_smem = 0;
+  double* d_scratch = nullptr;
+  // inputs: internal SoA buffers and the views currently in use
+  double *d_qpos = nullptr, *d_qvel = nullptr, *d_qacc = nullptr;
+  const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
+  long long in_stride = 0;
+  // AoS staging (host boundary), grown on demand
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  int* d_counter = nullptr;
+  mjb::Outputs out;            // device SoA outputs
+  void* field_ptr[mjbF_COUNT];
+  int field_rows[mjbF_COUNT];
+  int field_isint[mjbF_COUNT];
+  std::string error;
+};
+
+namespace {
+
+bool check(mjbData* d, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  d->error = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+template <typename T>
+bool devAlloc(mjbData* d, T** p, size_t count, const char* what) {
+  *p = nullptr;
+  if (count == 0) return true;
+  return check(d, cudaMalloc((void**)p, count * sizeof(T)), what);
+}
+
+bool ensureStage(mjbData* d, size_t bytes) {
+  if (bytes <= d->stage_bytes) return true;
+  if (d->d_stage) cudaFree(d->d_stage);
+  d->d_stage = nullptr;
+  d->stage_bytes = 0;
+  if (!check(d, cudaMalloc(&d->d_stage, bytes), "cudaMalloc(staging)")) return false;
+  d->stage_bytes = bytes;
+  return true;
+}
+
+void setField(mjbData* d, int f, void* p, int rows, int isint) {
+  d->field_ptr[f] = p;
+  d->field_rows[f] = rows;
+  d->field_isint[f] = isint;
+}
+
+}  // namespace
+
+extern "C" {
+
+mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned outmask, int nconmax,
+                      int njmax, char* err, int err_sz) {
+  auto fail = [&](const std::string& msg) -> mjbData* {
+    if (err && err_sz > 0) std::snprintf(err, err_sz, "%s", msg.c_str());
+    return nullptr;
+  };
+  if (!m) return fail("mjb_makeData: null model");
+  if (nbatch_max <= 0) return fail("mjb_makeData: nbatch_max must be positive");
+
+  std::vector<unsigned char> blob;
+  std::string msg;
+  if (!mjb::buildModelBlob(m, blob, msg)) return fail("mjb_makeData: " + msg);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    return fail("mjb_makeData: no CUDA device available (libmjb has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail("mjb_makeData: invalid device index");
+
+  mjbData* d = new mjbData_;
+  std::memset(&d->out, 0, sizeof(d->out));
+  for (int f = 0; f < mjbF_COUNT; f++) setField(d, f, nullptr, 0, 0);
+  d->device = device;
+  d->outmask = outmask;
+  d->nbatch_max = nbatch_max;
+  d->stride = ((long long)nbatch_max + 31) & ~31LL;   // keep every row 256-byte aligned
+  std::memcpy(&d->hdr, blob.data(), sizeof(mjbHdr));
+  const mjbHdr& H = d->hdr;
+  d->nconmax = nconmax > 0 ? nconmax : 64;
+  d->njmax = njmax > 0 ? njmax : 256;
+  {
+    const int* ci = reinterpret_cast<const int*>(blob.data() + H.int_section) + H.ioff[MJB_I_cand_int];
+    for (int i = 0; i < H.ncand; i++) {
+      d->cand.push_back(ci[MJB_CAND_NI*i + MJB_CI_G1]);
+      d->cand.push_back(ci[MJB_CAND_NI*i + MJB_CI_G2]);
+      d->cand.push_back(ci[MJB_CAND_NI*i + MJB_CI_FUNC]);
+    }
+  }
+
+  bool ok = check(d, cudaSetDevice(device), "cudaSetDevice");
+  d->model_bytes = H.bytes;
+  d->model_in_smem = H.bytes <= 64*1024;
+  ok = ok && devAlloc(d, &d->d_model, (size_t)H.bytes, "cudaMalloc(model)");
+  ok = ok && check(d, cudaMemcpy(d->d_model, blob.data(), (size_t)H.bytes, cudaMemcpyHostToDevice),
+                   "cudaMemcpy(model)");
+  ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * mjb::kNT, "cudaMalloc(scratch)");
+  const size_t S = (size_t)d->stride;
+  ok = ok && devAlloc(d, &d->d_qpos, (size_t)H.nq * S, "cudaMalloc(qpos)");
+  ok = ok && devAlloc(d, &d->d_qvel, (size_t)H.nv * S, "cudaMalloc(qvel)");
+  ok = ok && devAlloc(d, &d->d_qacc, (size_t)H.nv * S, "cudaMalloc(qacc)");
+  ok = ok && devAlloc(d, &d->d_counter, 1, "cudaMalloc(counter)");
+  d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
+
+  mjb::Outputs& o = d->out;
+  ok = ok && devAlloc(d, &o.qfrc_inverse, (size_t)H.nv * S, "cudaMalloc(qfrc_inverse)");
+  ok = ok && devAlloc(d, &o.status, S, "cudaMalloc(status)");
+  setField(d, mjbF_QFRC_INVERSE, o.qfrc_inverse, H.nv, 0);
+  setField(d, mjbF_STATUS, o.status, 1, 1);
+  if (outmask & mjbOUT_QFRC) {
+    ok = ok && devAlloc(d, &o.qfrc_constraint, (size_t)H.nv * S, "cudaMalloc(qfrc_constraint)");
+    ok = ok && devAlloc(d, &o.qfrc_passive, (size_t)H.nv * S, "cudaMalloc(qfrc_passive)");
+    setField(d, mjbF_QFRC_CONSTRAINT, o.qfrc_constraint, H.nv, 0);
+    setField(d, mjbF_QFRC_PASSIVE, o.qfrc_passive, H.nv, 0);
+  }
+  if (outmask & mjbOUT_COUNTS) {
+    ok = ok && devAlloc(d, &o.counts, 5 * S, "cudaMalloc(counts)");
+    setField(d, mjbF_COUNTS, o.counts, 5, 1);
+  }
+  if (outmask & mjbOUT_CONTACT) {
+    const size_t nc = (size_t)d->nconmax;
+    ok = ok && devAlloc(d, &o.contact_geom, 2 * nc * S, "cudaMalloc(contact_geom)");
+    ok = ok && devAlloc(d, &o.contact_info, 3 * nc * S, "cudaMalloc(contact_info)");
+    ok = ok && devAlloc(d, &o.contact_num, 13 * nc * S, "cudaMalloc(contact_num)");
+    setField(d, mjbF_CONTACT_GEOM, o.contact_geom, 2 * d->nconmax, 1);
+    setField(d, mjbF_CONTACT_INFO, o.contact_info, 3 * d->nconmax, 1);
+    setField(d, mjbF_CONTACT_NUM, o.contact_num, 13 * d->nconmax, 0);
+  }
+  if (outmask & mjbOUT_EFC) {
+    const size_t nj = (size_t)d->njmax;
+    ok = ok && devAlloc(d, &o.efc_int, 3 * nj * S, "cudaMalloc(efc_int)");
+    ok = ok && devAlloc(d, &o.efc_num, 8 * nj * S, "cudaMalloc(efc_num)");
+    setField(d, mjbF_EFC_INT, o.efc_int, 3 * d->njmax, 1);
+    setField(d, mjbF_EFC_NUM, o.efc_num, 8 * d->njmax, 0);
+  }
+  if (outmask & mjbOUT_INERTIA) {
+    ok = ok && devAlloc(d, &o.qM, (size_t)H.nM * S, "cudaMalloc(qM)");
+    ok = ok && devAlloc(d, &o.qLD, (size_t)H.nC * S, "cudaMalloc(qLD)");
+    ok = ok && devAlloc(d, &o.qLDiagInv, (size_t)H.nv * S, "cudaMalloc(qLDiagInv)");
+    setField(d, mjbF_QM, o.qM, H.nM, 0);
+    setField(d, mjbF_QLD, o.qLD, H.nC, 0);
+    setField(d, mjbF_QLDIAGINV, o.qLDiagInv, H.nv, 0);
+  }
+  if (outmask & mjbOUT_INTERNAL) {
+    ok = ok && devAlloc(d, &o.scratch_dump, (size_t)H.nscratch * S, "cudaMalloc(internal)");
+    setField(d, mjbF_INTERNAL, o.scratch_dump, H.nscratch, 0);
+  }
+  if (!ok) {
+    std::string e = d->error;
+    mjb_deleteData(d);
+    return fail("mjb_makeData: " + e);
+  }
+  return d;
+}
+
+void mjb_deleteData(mjbData* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaFree(d->d_model); cudaFree(d->d_scratch);
+  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc);
+  cudaFree(d->d_stage); cudaFree(d->d_counter);
+  mjb::Outputs& o = d->out;
+  cudaFree(o.qfrc_inverse); cudaFree(o.qfrc_constraint); cudaFree(o.qfrc_passive);
+  cudaFree(o.counts); cudaFree(o.status); cudaFree(o.contact_geom); cudaFree(o.contact_info);
+  cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
+  cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
+  delete d;
+}
+
+void mjb_setStream(mjbData* d, void* cuda_stream) { d->stream = (cudaStream_t)cuda_stream; }
+
+int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc) {
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setState: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const mjbHdr& H = d->hdr;
+  const size_t n = (size_t)nbatch;
+  const size_t bq = n * H.nq * sizeof(double), bv = n * H.nv * sizeof(double);
+  if (!ensureStage(d, bq + 2*bv)) return -1;
+  char* st = (char*)d->d_stage;
+  bool ok = check(d, cudaMemcpyAsync(st, qpos, bq, cudaMemcpyHostToDevice, d->stream), "H2D qpos");
+  ok = ok && check(d, cudaMemcpyAsync(st + bq, qvel, bv, cudaMemcpyHostToDevice, d->stream), "H2D qvel");
+  ok = ok && check(d, cudaMemcpyAsync(st + bq + bv, qacc, bv, cudaMemcpyHostToDevice, d->stream), "H2D qacc");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)st, d->d_qpos, nbatch, H.nq, d->stride, d->stream), "transpose qpos");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq), d->d_qvel, nbatch, H.nv, d->stride, d->stream), "transpose qvel");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq + bv), d->d_qacc, nbatch, H.nv, d->stride, d->stream), "transpose qacc");
+  d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
+  return ok ? 0 : -1;
+}
+
+int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc,
+                       long long stride) {
+  if (!qpos || !qvel || !qacc) {
+    d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
+    return 0;
+  }
+  if (stride != d->stride) {
+    d->error = "mjb_setStateDevice: stride must equal mjb_stride(d) (outputs share the row stride)";
+    return -1;
+  }
+  d->in_qpos = qpos; d->in_qvel = qvel; d->in_qacc = qacc; d->in_stride = stride;
+  return 0;
+}
+
+int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
+  (void)m;   // the model was flattened at mjb_makeData; kept for signature parity with mj_inverse
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverse: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  mjb::LaunchArgs a;
+  a.model = d->d_model;
+  a.model_bytes = d->model_bytes;
+  a.model_in_smem = d->model_in_smem;
+  a.qpos = d->in_qpos; a.qvel = d->in_qvel; a.qacc = d->in_qacc;
+  a.scratch = d->d_scratch;
+  a.stride = d->stride;
+  a.nbatch = nbatch;
+  a.nconmax = d->nconmax;
+  a.njmax = d->njmax;
+  a.out = d->out;
+  d->last_nbatch = nbatch;
+  if (!check(d, mjb::launch_inverse(a, d->stream), "launch inverse kernel")) return -1;
+  return 0;
+}
+
+int mjb_inverse(const mjModel* m, mjbData* d, int nbatch) {
+  if (mjb_inverseAsync(m, d, nbatch)) return -1;
+  int count = 0;
+  bool ok = check(d, cudaMemsetAsync(d->d_counter, 0, sizeof(int), d->stream), "memset counter");
+  ok = ok && check(d, mjb::launch_count_nonzero(d->out.status, nbatch, d->d_counter, d->stream), "count status");
+  ok = ok && check(d, cudaMemcpyAsync(&count, d->d_counter, sizeof(int), cudaMemcpyDeviceToHost, d->stream), "D2H counter");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_inverse");
+  return ok ? count : -1;
+}
+
+int mjb_get(mjbData* d, int field, void* host_out) {
+  if (field < 0 || field >= mjbF_COUNT || !d->field_ptr[field]) {
+    d->error = "mjb_get: field was not requested in outmask";
+    return -1;
+  }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const int n = d->last_nbatch, rows = d->field_rows[field];
+  const size_t esz = d->field_isint[field] ? sizeof(int) : sizeof(double);
+  const size_t bytes = (size_t)n * rows * esz;
+  if (bytes == 0) return 0;
+  if (!ensureStage(d, bytes)) return -1;
+  bool ok;
+  if (d->field_isint[field]) {
+    ok = check(d, mjb::launch_soa_to_aos_int((const int*)d->field_ptr[field], (int*)d->d_stage, n, rows, d->stride, d->stream), "transpose out");
+  } else {
+    ok = check(d, mjb::launch_soa_to_aos((const double*)d->field_ptr[field], (double*)d->d_stage, n, rows, d->stride, d->stream), "transpose out");
+  }
+  ok = ok && check(d, cudaMemcpyAsync(host_out, d->d_stage, bytes, cudaMemcpyDeviceToHost, d->stream), "D2H field");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_get");
+  return ok ? 0 : -1;
+}
+
+int mjb_getQfrcInverse(mjbData* d, mjtNum* qfrc_inverse) { return mjb_get(d, mjbF_QFRC_INVERSE, qfrc_inverse); }
+
+const void* mjb_devicePtr(mjbData* d, int field) {
+  return (field >= 0 && field < mjbF_COUNT) ? d->field_ptr[field] : nullptr;
+}
+
+int mjb_fieldRows(const mjbData* d, int field) {
+  return (field >= 0 && field < mjbF_COUNT) ? d->field_rows[field] : -1;
+}
+
+long long mjb_stride(const mjbData* d) { return d->stride; }
+
+int mjb_internalSlot(const mjbData* d, const char* name, int* offset, int* size) {
+  for (int s = 0; s < MJB_SC_COUNT; s++) {
+    if (!std::strcmp(mjb::scratchSlotName(s), name)) {
+      *offset = d->hdr.scoff[s];
+      *size = (s + 1 < MJB_SC_COUNT ? d->hdr.scoff[s + 1] : d->hdr.nscratch) - d->hdr.scoff[s];
+      return 0;
+    }
+  }
+  return -1;
+}
+
+int mjb_internalSize(const mjbData* d) { return d->hdr.nscratch; }
+
+int mjb_ncandidate(const mjbData* d) { return d->hdr.ncand; }
+
+void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int* func) {
+  *geom1 = d->cand[3*i]; *geom2 = d->cand[3*i + 1]; *func = d->cand[3*i + 2];
+}
+
+const char* mjb_lastError(const mjbData* d) { return d->error.c_str(); }
+
+int mjb_synchronize(mjbData* d) {
+  cudaSetDevice(d->device);
+  return check(d, cudaStreamSynchronize(d->stream), "cudaStreamSynchronize") ? 0 : -1;
+}
+
+double mjb_fp64PeakTflops(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  float ms = 0;
+  double flops = 0, best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    if (mjb::dfma_peak_probe(20000, &ms, &flops, 0) != cudaSuccess || ms <= 0) return -1;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+  }
+  return best;
+}
+
+}  // extern "C"

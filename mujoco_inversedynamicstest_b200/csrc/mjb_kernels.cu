@@ -1,0 +1,240 @@
+// sm_100a kernels of libmjb: the fused mj_inverse kernel (one thread per state), the AoS<->SoA
+// transposes at the host boundary, and an FP64 FMA peak probe for the roofline denominator.
+//
+// Thread mapping. The per-state matrices of mj_inverse are tiny, sparse and tree-structured
+// (nv = 27 for the humanoid): there is no contraction to feed tensor cores, and a warp-per-state
+// mapping would leave most fp64 lanes idle during the depth-serial tree sweeps (1-4 bodies per
+// level). So each THREAD owns one state and all model-driven control flow (topology, joint types,
+// candidate geom pairs) is uniform across the warp; only contact/limit activity diverges.
+// Intermediates live in a per-thread scratch laid out [slot][kNT] in HBM/L2 (consecutive lanes ->
+// consecutive doubles, fully coalesced 256-byte warp accesses); the model blob is staged once per
+// CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and read through
+// warp-uniform shared-memory broadcasts.
+#include "mjb_kernels.cuh"
+
+#include <cstdio>
+
+namespace mjb {
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy of the model blob global -> shared (SASS: UBLKCP), completion on an mbarrier
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void stage_model_tma(unsigned char* smem_dst, const unsigned char* gsrc,
+                                                uint32_t bytes, uint64_t* mbar) {
+  const uint32_t bar = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+    // one bulk copy moves at most what the tx-count can express; split large blobs in 64 KB pieces
+    uint32_t done = 0;
+    while (done < bytes) {
+      const uint32_t chunk = (bytes - done) < 65536u ? (bytes - done) : 65536u;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(smem_dst + done)), "l"(gsrc + done), "r"(chunk), "r"(bar)
+          : "memory");
+      done += chunk;
+    }
+  }
+  // every thread waits for phase 0 of the barrier
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(0)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// fused mj_inverse kernel
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 2) inverse_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+
+  const unsigned char* model = a.model;
+  if (kModelInSmem) {
+    stage_model_tma(smem, a.model, static_cast<uint32_t>(a.model_bytes), &mbar);
+    model = smem;
+  }
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(model);
+
+  const int slot = blockIdx.x * kThreads + threadIdx.x;
+  Ctx c;
+  c.H = H;
+  c.I = reinterpret_cast<const int*>(model + H->int_section);
+  c.D = reinterpret_cast<const double*>(model + H->num_section);
+  c.sc = a.scratch + slot;
+  c.N = a.stride;
+  c.nconmax = a.nconmax;
+  c.njmax = a.njmax;
+  c.out = a.out;
+
+  for (long long s = slot; s < a.nbatch; s += kNT) {
+    c.s = s;
+    c.qpos = a.qpos + s;
+    c.qvel = a.qvel + s;
+    c.qacc = a.qacc + s;
+    inverse_one_state(c);
+  }
+}
+
+size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
+  return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
+}
+
+cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream) {
+  if (args.nbatch <= 0) return cudaSuccess;
+  const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
+  // no more CTAs than the batch needs; never more than the scratch provisions
+  int grid = (args.nbatch + kThreads - 1) / kThreads;
+  if (grid > kGrid) grid = kGrid;
+  if (args.model_in_smem) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(inverse_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    inverse_kernel<true><<<grid, kThreads, smem, stream>>>(args);
+  } else {
+    inverse_kernel<false><<<grid, kThreads, 0, stream>>>(args);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// boundary transposes: host layout is [state][row] (array of states), device layout [row][state].
+// 32x32 tiles through shared memory so that both the read and the write are coalesced.
+
+template <typename T>
+__global__ void aos_to_soa_kernel(const T* __restrict__ aos, T* __restrict__ soa, int n, int rows,
+                                  long long stride) {
+  __shared__ T tile[32][33];
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int s = s0 + i, r = r0 + threadIdx.x;
+    if (s < n && r < rows) tile[i][threadIdx.x] = aos[(size_t)s * rows + r];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, s = s0 + threadIdx.x;
+    if (s < n && r < rows) soa[(size_t)r * stride + s] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__global__ void soa_to_aos_kernel(const T* __restrict__ soa, T* __restrict__ aos, int n, int rows,
+                                  long long stride) {
+  __shared__ T tile[32][33];
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, s = s0 + threadIdx.x;
+    if (s < n && r < rows) tile[i][threadIdx.x] = soa[(size_t)r * stride + s];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int s = s0 + i, r = r0 + threadIdx.x;
+    if (s < n && r < rows) aos[(size_t)s * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+static dim3 transpose_grid(int n, int rows) { return dim3((n + 31) / 32, (rows + 31) / 32); }
+
+cudaError_t launch_aos_to_soa(const double* aos, double* soa, int n, int rows, long long stride,
+                              cudaStream_t stream) {
+  if (n <= 0 || rows <= 0) return cudaSuccess;
+  aos_to_soa_kernel<double><<<transpose_grid(n, rows), dim3(32, 8), 0, stream>>>(aos, soa, n, rows, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos(const double* soa, double* aos, int n, int rows, long long stride,
+                              cudaStream_t stream) {
+  if (n <= 0 || rows <= 0) return cudaSuccess;
+  soa_to_aos_kernel<double><<<transpose_grid(n, rows), dim3(32, 8), 0, stream>>>(soa, aos, n, rows, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos_int(const int* soa, int* aos, int n, int rows, long long stride,
+                                  cudaStream_t stream) {
+  if (n <= 0 || rows <= 0) return cudaSuccess;
+  soa_to_aos_kernel<int><<<transpose_grid(n, rows), dim3(32, 8), 0, stream>>>(soa, aos, n, rows, stride);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// number of states whose status word is non-zero (return value of mjb_inverse)
+
+__global__ void count_nonzero_kernel(const int* __restrict__ status, int n, int* counter) {
+  int local = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    local += status[i] != 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(counter, local);
+}
+
+cudaError_t launch_count_nonzero(const int* status, int n, int* counter, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  int grid = (n + 255) / 256;
+  if (grid > kSMs * 8) grid = kSMs * 8;
+  count_nonzero_kernel<<<grid, 256, 0, stream>>>(status, n, counter);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 FMA peak probe: 8 independent DFMA chains per thread, enough warps to fill every SM
+
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+      a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+cudaError_t dfma_peak_probe(int iters, float* ms, double* flops, cudaStream_t stream) {
+  const int blocks = kSMs * 8, threads = 256;
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * blocks * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  dfma_probe_kernel<<<blocks, threads, 0, stream>>>(out, 16, 1.0);   // warm-up
+  cudaEventRecord(t0, stream);
+  dfma_probe_kernel<<<blocks, threads, 0, stream>>>(out, iters, 1.0);
+  cudaEventRecord(t1, stream);
+  e = cudaEventSynchronize(t1);
+  if (e == cudaSuccess) {
+    cudaEventElapsedTime(ms, t0, t1);
+    *flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(out);
+  return e;
+}
+
+}  // namespace mjb

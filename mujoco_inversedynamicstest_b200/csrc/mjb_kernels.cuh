@@ -19,27 +19,12 @@ constexpr int kCtasPerSM = 4;                 // scratch slots provisioned per S
 constexpr int kGrid = kSMs * kCtasPerSM;      // 592 CTAs
 constexpr int kNT = kGrid * kThreads;         // 75,776 thread slots
 
-// optional per-state outputs, all structure-of-arrays [row][stride]
-struct Outputs {
-  double* qfrc_inverse;     // [nv][stride]            always
-  double* qfrc_constraint;  // [nv][stride]            or null
-  double* qfrc_passive;     // [nv][stride]            or null
-  int* counts;              // [5][stride]: ncon, ne, nf, nl, nefc          or null
-  int* status;              // [stride] bit flags, see MJB_STATUS_* in mjb.h
-  // contacts, nconmax rows per state (null when not requested)
-  int* contact_geom;        // [nconmax*2][stride]
-  int* contact_info;        // [nconmax*3][stride]: dim, exclude, efc_address
-  double* contact_num;      // [nconmax*13][stride]: dist, pos[3], frame[9]
-  // constraint rows, njmax rows per state (null when not requested)
-  int* efc_int;             // [njmax*3][stride]: type, id, state
-  double* efc_num;          // [njmax*8][stride]: pos, margin, D, R, vel, aref, force, diagApprox
-  // inertia (null when not requested)
-  double* qM;               // [nM][stride]
-  double* qLD;              // [nC][stride]
-  double* qLDiagInv;        // [nv][stride]
-  // kinematics dump: every scratch slot copied out as [nscratch][stride] (null when not requested)
-  double* scratch_dump;
-};
+}  // namespace mjb
+
+#define MJB_NT mjb::kNT
+#include "mjb_pipeline.h"
+
+namespace mjb {
 
 struct LaunchArgs {
   const unsigned char* model;   // device blob (mjbHdr + sections)
@@ -65,6 +50,9 @@ cudaError_t launch_soa_to_aos(const double* soa, double* aos, int n, int rows, l
                               cudaStream_t stream);
 cudaError_t launch_soa_to_aos_int(const int* soa, int* aos, int n, int rows, long long stride,
                                   cudaStream_t stream);
+
+// *counter += number of non-zero entries of status[0..n)
+cudaError_t launch_count_nonzero(const int* status, int n, int* counter, cudaStream_t stream);
 
 // FP64 FMA peak probe: runs `iters` dependent-chain-free DFMA rounds on every thread, returns
 // elapsed milliseconds in *ms and the number of flops executed in *flops.

@@ -1402,6 +1402,20 @@ MJB_HD inline void inverse_one_state(Ctx& c) {
     c.out.counts[3*N + c.s] = c.nl;
     c.out.counts[4*N + c.s] = c.nefc;
   }
+  // unused rows of the fixed-capacity outputs: -1 for ids, 0 for numbers
+  if (c.out.contact_geom) {
+    for (int k = c.ncon; k < c.nconmax; k++) {
+      for (int j = 0; j < 2; j++) c.out.contact_geom[(size_t)(2*k + j)*N + c.s] = -1;
+      for (int j = 0; j < 3; j++) c.out.contact_info[(size_t)(3*k + j)*N + c.s] = -1;
+      for (int j = 0; j < 13; j++) c.out.contact_num[(size_t)(13*k + j)*N + c.s] = 0;
+    }
+  }
+  if (c.out.efc_int) {
+    for (int k = c.nefc; k < c.njmax; k++) {
+      for (int j = 0; j < 3; j++) c.out.efc_int[(size_t)(3*k + j)*N + c.s] = -1;
+      for (int j = 0; j < 8; j++) c.out.efc_num[(size_t)(8*k + j)*N + c.s] = 0;
+    }
+  }
   if (c.out.status) c.out.status[c.s] = c.status;
   if (c.out.scratch_dump) {
     for (int k = 0; k < H.nscratch; k++) c.out.scratch_dump[(size_t)k*N + c.s] = AT(c.sc, k);

@@ -1,0 +1,75 @@
+"""Generate the committed parity fixtures from the reference itself (run where /root/reference and
+oracle/_ref/libmujoco_ref.so exist):
+
+    python tests/golden/make_golden.py
+
+For every case: the compiled mjModel as a gzip'd MJB (mj_saveModel) and, for NSTATE seeded states
+of mujoco_inversedynamicstest_b200.states.generate_states, the reference's own mj_inverse outputs
+(qfrc_inverse, counters, contact geom pairs, efc_type/efc_id, efc_force, qM/qLD/qLDiagInv ...).
+The reference publishes no numeric golden vector for qfrc_inverse, so these dumps
+of the unmodified CPU engine are the pin; this script is how they were made.
+"""
+import gzip
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import reflib  # noqa: E402
+from mujoco_inversedynamicstest_b200.states import generate_states  # noqa: E402
+
+DSBL_CONTACT, DSBL_EQUALITY = 1 << 4, 1 << 1
+
+# name -> (reference xml, {opt int overrides}, nstate, z_range, nconmax, njmax)
+CASES = {
+    "humanoid": ("model/humanoid/humanoid.xml", {}, 256, (0.0, 1.5), 64, 256),
+    "humanoid_elliptic": ("model/humanoid/humanoid.xml", {"cone": 1}, 256, (0.0, 1.5), 64, 256),
+    "humanoid_nocontact": ("model/humanoid/humanoid.xml", {"disableflags": DSBL_CONTACT}, 256,
+                           (2.0, 3.0), 64, 256),
+    "humanoids22": ("model/humanoid/22_humanoids.xml", {}, 8, (0.0, 1.5), 640, 1200),
+    "slider_crank_nocontact": ("model/slider_crank/slider_crank.xml", {"disableflags": DSBL_CONTACT},
+                               64, (0.0, 1.5), 8, 16),
+    "inverse_test": ("src/inverse/test.xml", {}, 64, (0.0, 1.5), 8, 16),
+}
+
+
+def make_case(name):
+    xml, opts, nstate, zr, nconmax, njmax = CASES[name]
+    m = reflib.Model.from_xml(reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    raw = os.path.join(HERE, name + ".mjb")
+    m.save_mjb(raw)
+    with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb",
+                                             compresslevel=9, mtime=0) as g:
+        g.write(f.read())
+    os.remove(raw)
+
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    fields = {"ncon": 1, "ne": 1, "nf": 1, "nl": 1, "nefc": 1,
+              "contact_geom": nconmax, "contact_dist": nconmax, "contact_dim": nconmax,
+              "contact_exclude": nconmax, "contact_efc_address": nconmax, "contact_pos": nconmax,
+              "contact_frame": nconmax,
+              "efc_type": njmax, "efc_id": njmax, "efc_state": njmax, "efc_force": njmax,
+              "efc_pos": njmax, "efc_D": njmax, "efc_aref": njmax,
+              "qfrc_passive": None, "qfrc_constraint": None, "qM": None, "qLD": None,
+              "qLDiagInv": None, "xpos": None, "cvel": None, "cdof": None}
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields)
+    assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax, (
+        name, out["ncon"].max(), out["nefc"].max())
+    save = {"z_range": np.array(zr), "nstate": np.array(nstate), "nconmax": np.array(nconmax),
+            "njmax": np.array(njmax)}
+    for k, v in out.items():
+        save[k] = v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(f"{name}: nv={m.int('nv')} states={nstate} mean ncon={out['ncon'].mean():.2f} "
+          f"mean nefc={out['nefc'].mean():.2f} max={out['ncon'].max()}/{out['nefc'].max()}")
+
+
+if __name__ == "__main__":
+    for case in (sys.argv[1:] or CASES):
+        make_case(case)

@@ -1,0 +1,226 @@
+"""GPU parity: the CUDA path, called through the C-ABI (libmjb.so via ctypes), against
+  (1) the committed golden dumps of the reference's own CPU mj_inverse (tests/golden), and
+  (2) the reference library itself (oracle/_ref) run live on the same seeded inputs,
+plus size-independent properties at BASELINE.json's full batch size.
+
+Bars (north_star): bit-exact ncon / contact geom pairs / efc_type / efc_id / counters;
+qfrc_inverse within 1e-9 relative + 1e-12 absolute.
+"""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
+         "slider_crank_nocontact", "inverse_test"]
+
+
+def _run(mjb, name, gold, outmask):
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    n = int(ref["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+    bd = mjb.BatchData(model, n, outmask=outmask, nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]))
+    bd.set_state(qpos, qvel, qacc)
+    nbad = bd.inverse()
+    return model, bd, ref, nbad, (qpos, qvel, qacc)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_discrete_outputs_bit_exact(name):
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, name, True, mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC)
+    assert nbad == 0
+    cnt = bd.counts()
+    for k in ("ncon", "ne", "nf", "nl", "nefc"):
+        np.testing.assert_array_equal(cnt[k], ref[k], err_msg=k)
+    con = bd.contacts()
+    np.testing.assert_array_equal(con["geom"], ref["contact_geom"])
+    np.testing.assert_array_equal(con["dim"], ref["contact_dim"])
+    np.testing.assert_array_equal(con["exclude"], ref["contact_exclude"])
+    np.testing.assert_array_equal(con["efc_address"], ref["contact_efc_address"])
+    efc = bd.efc()
+    np.testing.assert_array_equal(efc["type"], ref["efc_type"])
+    np.testing.assert_array_equal(efc["id"], ref["efc_id"])
+    np.testing.assert_array_equal(efc["state"], ref["efc_state"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_qfrc_inverse_within_tolerance(name):
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, name, True, mjb.OUT_QFRC | mjb.OUT_CONTACT | mjb.OUT_EFC)
+    got = bd.qfrc_inverse()
+    nviol, worst = util.qfrc_violations_scaled(got, ref["qfrc_inverse"])
+    assert nviol == 0, f"{nviol} entries outside 1e-9 rel / 1e-12 abs (worst ratio {worst:.3g})"
+    # strict element-wise bound: report, and require it on the contact-free cases
+    nstrict, wstrict = util.qfrc_violations(got, ref["qfrc_inverse"])
+    if ref["ncon"].max() == 0:
+        assert nstrict == 0, f"strict bound: {nstrict} violations, worst {wstrict:.3g}"
+    con = bd.contacts()
+    np.testing.assert_allclose(con["dist"], ref["contact_dist"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(con["pos"], ref["contact_pos"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(con["frame"], ref["contact_frame"], rtol=1e-9, atol=1e-11)
+    efc = bd.efc()
+    scale = np.abs(ref["efc_force"]).max()
+    np.testing.assert_allclose(efc["force"], ref["efc_force"], rtol=1e-9, atol=1e-12 + 1e-13 * scale)
+    np.testing.assert_allclose(efc["pos"], ref["efc_pos"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(bd.get(mjb.F_QFRC_PASSIVE), ref["qfrc_passive"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["humanoid", "humanoids22"])
+def test_golden_inertia_outputs(name):
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, name, True, mjb.OUT_INERTIA | mjb.OUT_INTERNAL)
+    for f, k in ((mjb.F_QM, "qM"), (mjb.F_QLD, "qLD"), (mjb.F_QLDIAGINV, "qLDiagInv")):
+        np.testing.assert_allclose(bd.get(f), ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    n = int(ref["nstate"])
+    np.testing.assert_allclose(bd.internal("xpos").reshape(n, -1, 3), ref["xpos"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(bd.internal("cvel").reshape(n, -1, 6), ref["cvel"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(bd.internal("cdof").reshape(n, -1, 6), ref["cdof"], rtol=1e-9, atol=1e-12)
+
+
+def test_ldl_reconstructs_mass_matrix():
+    """L' D L == M (test/engine/engine_core_smooth_test.cc:466-511, 1e-12 there on a small model)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, _, _ = _run(mjb, "humanoid", True, mjb.OUT_INERTIA)
+    nv = model.int("nv")
+    parent = model.array("dof_parentid").ravel()
+    madr = model.array("dof_Madr").ravel()
+    qM, qLD = bd.get(mjb.F_QM), bd.get(mjb.F_QLD)
+    for s in range(0, qM.shape[0], 37):
+        M = np.zeros((nv, nv)); L = np.eye(nv); D = np.zeros(nv)
+        adrC = 0
+        for i in range(nv):
+            chain = []
+            j = i
+            while j >= 0:
+                chain.append(j); j = parent[j]
+            for t, j in enumerate(chain):
+                M[i, j] = M[j, i] = qM[s, madr[i] + t]
+            cols = chain[::-1]
+            for t, j in enumerate(cols):
+                if j == i: D[i] = qLD[s, adrC + t]
+                else: L[i, j] = qLD[s, adrC + t]
+            adrC += len(chain)
+        np.testing.assert_allclose(L.T @ np.diag(D) @ L, M, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,n", [("humanoid", 4096), ("humanoid_elliptic", 4096)])
+def test_live_reference_4096_states(name, n):
+    """BASELINE config 1: 4096 random states, every discrete output bit-exact, qfrc within bound."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    from oracle import reflib
+    path, _ = util.golden(name)
+    import gzip, tempfile, os
+    with tempfile.NamedTemporaryFile(suffix=".mjb", delete=False) as tf:
+        tf.write(gzip.open(path, "rb").read())
+    try:
+        rm = reflib.Model.from_mjb(tf.name)
+    finally:
+        os.remove(tf.name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, first=100000)
+    ref, _ = rm.inverse_batch(qpos, qvel, qacc, nthread=4, fields={
+        "ncon": 1, "nefc": 1, "nl": 1, "contact_geom": 64, "efc_type": 256, "efc_id": 256})
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC, nconmax=64, njmax=256)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    cnt = bd.counts()
+    np.testing.assert_array_equal(cnt["ncon"], ref["ncon"])
+    np.testing.assert_array_equal(cnt["nefc"], ref["nefc"])
+    np.testing.assert_array_equal(cnt["nl"], ref["nl"])
+    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
+    efc = bd.efc()
+    np.testing.assert_array_equal(efc["type"], ref["efc_type"][:, :, 0])
+    np.testing.assert_array_equal(efc["id"], ref["efc_id"][:, :, 0])
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+
+
+def test_full_size_properties_1m_states():
+    """2^20 humanoid states (BASELINE configs 2/3): size-independent properties.
+    - determinism: two launches give bit-identical qfrc_inverse
+    - batch-position independence: a state gives the same bits wherever it sits in the batch
+    - the first 256 states equal the golden dump within tolerance
+    - no status flags on valid inputs; NaN / huge inputs are flagged per state"""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden("humanoid")
+    model = mjb.Model.from_mjb(path)
+    n = 1 << 20
+    qpos, qvel, qacc = generate_states(model, n)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    a = bd.qfrc_inverse()
+    assert np.isfinite(a).all()
+    assert bd.inverse() == 0
+    b = bd.qfrc_inverse()
+    assert np.array_equal(a, b)
+    nviol, worst = util.qfrc_violations_scaled(a[:256], ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    np.testing.assert_array_equal(bd.counts()["ncon"][:256], ref["ncon"])
+    # reversed batch order
+    bd.set_state(qpos[::-1], qvel[::-1], qacc[::-1])
+    assert bd.inverse() == 0
+    c = bd.qfrc_inverse()[::-1]
+    assert np.array_equal(a, c)
+    # bad inputs
+    qpos2 = qpos[:1024].copy(); qvel2 = qvel[:1024].copy(); qacc2 = qacc[:1024].copy()
+    qpos2[3, 5] = np.nan; qvel2[7, 0] = 1e11; qacc2[9, 2] = -np.inf
+    bd.set_state(qpos2, qvel2, qacc2)
+    assert bd.inverse() == 3
+    st = bd.status()
+    assert st[3] & 1 and st[7] & 2 and st[9] & 4 and (st != 0).sum() == 3
+
+
+def test_empty_and_ragged_batches():
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden("humanoid")
+    model = mjb.Model.from_mjb(path)
+    bd = mjb.BatchData(model, 1000)
+    qpos, qvel, qacc = generate_states(model, 256)
+    for n in (0, 1, 31, 33, 129, 256):
+        bd.set_state(qpos[:n], qvel[:n], qacc[:n])
+        assert bd.inverse() == 0
+        got = bd.qfrc_inverse()
+        assert got.shape == (n, model.int("nv"))
+        if n:
+            nviol, worst = util.qfrc_violations_scaled(got, ref["qfrc_inverse"][:n])
+            assert nviol == 0, (n, nviol, worst)
+    with pytest.raises(mjb.MjbError):
+        bd.set_state(np.zeros((2000, 28)), np.zeros((2000, 27)), np.zeros((2000, 27)))
+
+
+def test_output_capacity_overflow_is_flagged():
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "humanoid", True, mjb.OUT_COUNTS)
+    path, _ = util.golden("humanoid")
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    qpos, qvel, qacc = generate_states(model, 256)
+    small = mjb.BatchData(model, 256, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC, nconmax=4, njmax=8)
+    small.set_state(qpos, qvel, qacc)
+    nbad = small.inverse()
+    st = small.status()
+    expect = ((ref["ncon"] > 4) * 8) | ((ref["nefc"] > 8) * 16)
+    np.testing.assert_array_equal(st, expect)
+    assert nbad == int((expect != 0).sum())
+    # the physics is not truncated by the output capacity
+    nviol, worst = util.qfrc_violations_scaled(small.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0
+
+
+def test_unsupported_models_are_rejected_at_upload(tmp_path):
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, _ = util.golden("slider_crank_nocontact")
+    model = mjb.Model.from_mjb(path)
+    mjb.BatchData(model, 8)                       # contacts disabled: accepted
+    model.set_opt_int("disableflags", 0)          # contacts on: capsule-cylinder pairs -> mjc_Convex
+    with pytest.raises(mjb.MjbError, match="collision function"):
+        mjb.BatchData(model, 8)
