@@ -40,7 +40,7 @@ def _normal(seed, idx, field):
 
 
 def generate_states(model, n, first=0, seed=SEED, z_range=(0.0, 1.5)):
-    """model: object with .int(name) and .array(name) (mjb.Model or oracle.reflib.Model).
+    """model: object with .int(name) and .array(name) (the package Model or the test-side reference wrapper).
 
     Returns qpos [n, nq], qvel [n, nv], qacc [n, nv] for state indices first .. first+n-1."""
     nq, nv, njnt = model.int("nq"), model.int("nv"), model.int("njnt")

@@ -73,4 +73,23 @@ int hostemu_slot(const mjModel_* m, const char* name, int* offset, int* size) {
   return -1;
 }
 
+// candidate geom pairs (g1, g2, func) in contact order; returns the count (or -1)
+__attribute__((visibility("default")))
+int hostemu_candidates(const mjModel_* m, int* out, int max_pairs, char* err, int err_sz) {
+  std::vector<unsigned char> blob;
+  std::string msg;
+  if (!mjb::buildModelBlob(m, blob, msg)) {
+    if (err && err_sz > 0) std::snprintf(err, err_sz, "%s", msg.c_str());
+    return -1;
+  }
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
+  const int* ci = reinterpret_cast<const int*>(blob.data() + H->int_section) + H->ioff[MJB_I_cand_int];
+  for (int i = 0; i < H->ncand && i < max_pairs; i++) {
+    out[3*i] = ci[MJB_CAND_NI*i + MJB_CI_G1];
+    out[3*i + 1] = ci[MJB_CAND_NI*i + MJB_CI_G2];
+    out[3*i + 2] = ci[MJB_CAND_NI*i + MJB_CI_FUNC];
+  }
+  return H->ncand;
+}
+
 }  // extern "C"

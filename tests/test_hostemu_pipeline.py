@@ -1,0 +1,95 @@
+"""CPU check of the per-state pipeline (the exact functions the CUDA kernel runs, compiled as plain
+C++ for this purpose only, tests/hostemu) against the golden dumps of the reference.
+
+This is what lets the algorithmic restructuring -- Jacobian-free constraint rows, static candidate
+pairs instead of broadphase/midphase, wrench accumulation inside RNE -- be verified in a container
+without a GPU. Built with -ffp-contract=off, so even the kinematics are bit-identical here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import util
+
+sys.path.insert(0, os.path.join(util.ROOT, "tests", "hostemu"))
+import emu  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation library not buildable")
+
+CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
+         "slider_crank_nocontact", "inverse_test"]
+
+
+def _run(name):
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    n = int(ref["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+    out = emu.run(model, qpos, qvel, qacc, nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]))
+    return model, out, ref
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_discrete_outputs_bit_exact(name):
+    model, out, ref = _run(name)
+    assert (out["status"] == 0).all()
+    for k in ("ncon", "ne", "nf", "nl", "nefc", "contact_geom", "contact_dim", "contact_exclude",
+              "contact_efc_address", "efc_type", "efc_id", "efc_state"):
+        np.testing.assert_array_equal(out[k], ref[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_continuous_outputs(name):
+    model, out, ref = _run(name)
+    nviol, worst = util.qfrc_violations_scaled(out["qfrc_inverse"], ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    n = out["qfrc_inverse"].shape[0]
+    # position stage is bit-identical on the CPU build
+    np.testing.assert_array_equal(emu.slot(model, out, "xpos").reshape(n, -1, 3), ref["xpos"])
+    np.testing.assert_array_equal(emu.slot(model, out, "cdof").reshape(n, -1, 6), ref["cdof"])
+    np.testing.assert_array_equal(out["contact_dist"], ref["contact_dist"])
+    np.testing.assert_array_equal(out["contact_pos"], ref["contact_pos"])
+    np.testing.assert_array_equal(out["contact_frame"], ref["contact_frame"])
+    np.testing.assert_array_equal(out["qM"], ref["qM"])
+    np.testing.assert_array_equal(out["qLD"], ref["qLD"])
+    np.testing.assert_array_equal(out["qLDiagInv"], ref["qLDiagInv"])
+    np.testing.assert_array_equal(out["qfrc_passive"], ref["qfrc_passive"])
+    np.testing.assert_array_equal(out["efc_pos"], ref["efc_pos"])
+    np.testing.assert_allclose(out["efc_D"], ref["efc_D"], rtol=1e-14)
+    scale = max(1.0, np.abs(ref["efc_force"]).max())
+    np.testing.assert_allclose(out["efc_force"], ref["efc_force"], rtol=1e-9, atol=1e-15 * scale)
+    np.testing.assert_allclose(out["efc_aref"], ref["efc_aref"], rtol=1e-9, atol=1e-15 * scale)
+    cs = np.abs(ref["qfrc_constraint"]).max(axis=1, keepdims=True)
+    assert (np.abs(out["qfrc_constraint"] - ref["qfrc_constraint"]) <= 1e-12 + 1e-12 * cs).all()
+
+
+def test_candidate_list_contains_reference_contacts_in_order():
+    """Every contact the reference reports (after its broadphase/midphase) appears in the static
+    candidate list, in the same relative order (engine_collision_driver.c:265-484)."""
+    for name in ("humanoid", "humanoids22"):
+        import mujoco_inversedynamicstest_b200 as mjb
+        path, ref = util.golden(name)
+        model = mjb.Model.from_mjb(path)
+        cand = emu.candidates(model)
+        index = {(a, b): i for i, (a, b, f) in enumerate(cand)}
+        assert len(index) == len(cand)          # no duplicate candidate
+        for s in range(ref["contact_geom"].shape[0]):
+            pairs = [tuple(p) for p in ref["contact_geom"][s] if p[0] >= 0]
+            pos = [index[p] for p in pairs]
+            assert pos == sorted(pos), (name, s)
+
+
+def test_upload_rejections():
+    import mujoco_inversedynamicstest_b200 as mjb
+    model = mjb.Model.from_mjb(util.golden("slider_crank_nocontact")[0])
+    assert len(emu.candidates(model)) == 0
+    model.set_opt_int("disableflags", 0)
+    with pytest.raises(RuntimeError, match="collision function"):
+        emu.candidates(model)
+    h = mjb.Model.from_mjb(util.golden("humanoid")[0])
+    h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE
+    with pytest.raises(RuntimeError, match="INVDISCRETE"):
+        emu.candidates(h)
