@@ -259,10 +259,12 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = bd.kernel_launches()
     ev0.record(stream)
     for _ in range(args.steps):
         bd.inverse(sync=False)
     ev1.record(stream)
+    gpu_launches = bd.kernel_launches() - launches0
     barrier()
     kernel_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -326,7 +328,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "states/s",
                     "h2d_bytes_per_step": n * (nq + 2 * nv) * 8, "d2h_bytes_per_step": n * nv * 8,
                     "steps": e2e_steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": roof_fp64,
             "roofline_hbm": roof_hbm,
         }

@@ -123,6 +123,9 @@ MJB_API void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int*
 
 MJB_API const char* mjb_lastError(const mjbData* d);
 
+/* number of mj_inverse phase kernels this mjbData has launched so far (diagnostics / benchmark) */
+MJB_API long long mjb_kernelLaunches(const mjbData* d);
+
 /* wait for the stream */
 MJB_API int mjb_synchronize(mjbData* d);
 

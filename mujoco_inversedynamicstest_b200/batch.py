@@ -169,6 +169,9 @@ class BatchData:
         self.nbatch = n
         return rc
 
+    def kernel_launches(self):
+        return int(lib().mjb_kernelLaunches(self._d))
+
     def synchronize(self):
         self._check(lib().mjb_synchronize(self._d), "mjb_synchronize")
 

@@ -25,7 +25,10 @@ struct mjbData_ {
   unsigned char* d_model = nullptr;
   int model_bytes = 0;
   int model_in_smem = 0;
-  double* d_scratch = nullptr;
+  double* d_scratch = nullptr;   // [nscratch][chunk_stride]
+  int* d_iscratch = nullptr;      // [MJB_ISC_COUNT][chunk_stride]
+  long long chunk_stride = 0;     // states per chunk (intermediates are allocated per chunk)
+  long long kernel_launches = 0;  // phase kernels launched so far (reported by the benchmark)
   // inputs: internal SoA buffers and the views currently in use
   double *d_qpos = nullptr, *d_qvel = nullptr, *d_qacc = nullptr;
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
@@ -121,7 +124,18 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   ok = ok && devAlloc(d, &d->d_model, (size_t)H.bytes, "cudaMalloc(model)");
   ok = ok && check(d, cudaMemcpy(d->d_model, blob.data(), (size_t)H.bytes, cudaMemcpyHostToDevice),
                    "cudaMemcpy(model)");
-  ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * mjb::kNT, "cudaMalloc(scratch)");
+  // intermediates live per chunk of states: at most 2^20 states and at most ~12 GB
+  {
+    const double bytes_per_state = 8.0 * H.nscratch + 4.0 * mjb::MJB_ISC_COUNT;
+    long long chunk = (long long)(12.0e9 / bytes_per_state);
+    if (chunk > (1LL << 20)) chunk = 1LL << 20;
+    if (chunk > d->stride) chunk = d->stride;
+    chunk &= ~127LL;
+    if (chunk < 128) chunk = 128;
+    d->chunk_stride = chunk;
+  }
+  ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
+  ok = ok && devAlloc(d, &d->d_iscratch, (size_t)mjb::MJB_ISC_COUNT * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
   const size_t S = (size_t)d->stride;
   ok = ok && devAlloc(d, &d->d_qpos, (size_t)H.nq * S, "cudaMalloc(qpos)");
   ok = ok && devAlloc(d, &d->d_qvel, (size_t)H.nv * S, "cudaMalloc(qvel)");
@@ -183,7 +197,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
 void mjb_deleteData(mjbData* d) {
   if (!d) return;
   cudaSetDevice(d->device);
-  cudaFree(d->d_model); cudaFree(d->d_scratch);
+  cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   mjb::Outputs& o = d->out;
@@ -238,13 +252,23 @@ int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
   a.model_in_smem = d->model_in_smem;
   a.qpos = d->in_qpos; a.qvel = d->in_qvel; a.qacc = d->in_qacc;
   a.scratch = d->d_scratch;
+  a.iscratch = d->d_iscratch;
+  a.chunk_stride = d->chunk_stride;
   a.stride = d->stride;
-  a.nbatch = nbatch;
   a.nconmax = d->nconmax;
   a.njmax = d->njmax;
+  a.has_contacts = d->hdr.ncand > 0 &&
+                   !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
   a.out = d->out;
   d->last_nbatch = nbatch;
-  if (!check(d, mjb::launch_inverse(a, d->stream), "launch inverse kernel")) return -1;
+  // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
+  for (long long start = 0; start < nbatch; start += d->chunk_stride) {
+    a.chunk_start = start;
+    a.chunk_n = (int)((nbatch - start) < d->chunk_stride ? (nbatch - start) : d->chunk_stride);
+    int launches = 0;
+    if (!check(d, mjb::launch_inverse(a, d->stream, &launches), "launch mj_inverse kernels")) return -1;
+    d->kernel_launches += launches;
+  }
   return 0;
 }
 
@@ -312,6 +336,8 @@ void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int* func) {
 }
 
 const char* mjb_lastError(const mjbData* d) { return d->error.c_str(); }
+
+long long mjb_kernelLaunches(const mjbData* d) { return d->kernel_launches; }
 
 int mjb_synchronize(mjbData* d) {
   cudaSetDevice(d->device);

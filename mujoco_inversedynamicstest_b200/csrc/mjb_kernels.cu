@@ -1,4 +1,4 @@
-// sm_100a kernels of libmjb: the fused mj_inverse kernel (one thread per state), the AoS<->SoA
+// sm_100a kernels of libmjb: the mj_inverse phase kernels (one thread per state), the AoS<->SoA
 // transposes at the host boundary, and an FP64 FMA peak probe for the roofline denominator.
 //
 // Thread mapping. The per-state matrices of mj_inverse are tiny, sparse and tree-structured
@@ -6,10 +6,11 @@
 // mapping would leave most fp64 lanes idle during the depth-serial tree sweeps (1-4 bodies per
 // level). So each THREAD owns one state and all model-driven control flow (topology, joint types,
 // candidate geom pairs) is uniform across the warp; only contact/limit activity diverges.
-// Intermediates live in a per-thread scratch laid out [slot][kNT] in HBM/L2 (consecutive lanes ->
-// consecutive doubles, fully coalesced 256-byte warp accesses); the model blob is staged once per
-// CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) and read through
-// warp-uniform shared-memory broadcasts.
+// The pipeline is cut into four phase kernels so that each gets its own register budget and
+// occupancy; intermediates are handed over through a per-state scratch laid out [slot][chunk] in
+// HBM (consecutive lanes -> consecutive doubles, fully coalesced 256-byte warp accesses). The model
+// blob is staged once per CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier)
+// and read through warp-uniform shared-memory broadcasts.
 #include "mjb_kernels.cuh"
 
 #include <cstdio>
@@ -59,37 +60,95 @@ __device__ __forceinline__ void stage_model_tma(unsigned char* smem_dst, const u
 }
 
 // ------------------------------------------------------------------------------------------
-// fused mj_inverse kernel
+// phase kernels (see mjb_pipeline.h: phase_smooth / phase_inertia / phase_contact / phase_backward)
+
+struct Prologue {
+  const unsigned char* model;
+};
 
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 2) inverse_kernel(LaunchArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t mbar;
-
+__device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned char* smem,
+                                         uint64_t* mbar) {
   const unsigned char* model = a.model;
   if (kModelInSmem) {
-    stage_model_tma(smem, a.model, static_cast<uint32_t>(a.model_bytes), &mbar);
+    stage_model_tma(smem, a.model, static_cast<uint32_t>(a.model_bytes), mbar);
     model = smem;
   }
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(model);
-
-  const int slot = blockIdx.x * kThreads + threadIdx.x;
-  Ctx c;
   c.H = H;
   c.I = reinterpret_cast<const int*>(model + H->int_section);
   c.D = reinterpret_cast<const double*>(model + H->num_section);
-  c.sc = a.scratch + slot;
   c.N = a.stride;
+  c.NS = static_cast<size_t>(a.chunk_stride);
   c.nconmax = a.nconmax;
   c.njmax = a.njmax;
   c.out = a.out;
+  c.ncon = c.ne = c.nf = c.nl = c.nefc = c.status = 0;
+}
 
-  for (long long s = slot; s < a.nbatch; s += kNT) {
-    c.s = s;
-    c.qpos = a.qpos + s;
-    c.qvel = a.qvel + s;
-    c.qacc = a.qacc + s;
-    inverse_one_state(c);
+__device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long long local) {
+  const long long s = a.chunk_start + local;
+  c.s = s;
+  c.sc = a.scratch + local;
+  c.isc = a.iscratch + local;
+  c.qpos = a.qpos + s;
+  c.qvel = a.qvel + s;
+  c.qacc = a.qacc + s;
+}
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) smooth_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    phase_smooth(c);
+  }
+}
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) inertia_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    phase_inertia(c);
+  }
+}
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) contact_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int lists[kListCap * kThreads];
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  // block-uniform trip count: lanes past the end of the chunk still take part in the warp votes
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n;
+       i0 += (long long)gridDim.x * kThreads) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < a.chunk_n;
+    bind_state(c, a, valid ? i : (long long)a.chunk_n - 1);
+    phase_contact(c, valid, lists + threadIdx.x, kThreads, kListCap);
+  }
+}
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) backward_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    phase_backward(c);
   }
 }
 
@@ -97,25 +156,48 @@ size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
   return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
 }
 
-cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream) {
-  if (args.nbatch <= 0) return cudaSuccess;
-  const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
-  // no more CTAs than the batch needs; never more than the scratch provisions
-  int grid = (args.nbatch + kThreads - 1) / kThreads;
-  if (grid > kGrid) grid = kGrid;
-  if (args.model_in_smem) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(inverse_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-    }
-    inverse_kernel<true><<<grid, kThreads, smem, stream>>>(args);
-  } else {
-    inverse_kernel<false><<<grid, kThreads, 0, stream>>>(args);
+template <typename K>
+static cudaError_t launch_phase(K kernel, const LaunchArgs& args, size_t smem, int ctas_per_sm,
+                                cudaStream_t stream) {
+  int grid = (args.chunk_n + kThreads - 1) / kThreads;
+  const int cap = kSMs * ctas_per_sm;
+  if (grid > cap) grid = cap;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
   }
+  kernel<<<grid, kThreads, smem, stream>>>(args);
   return cudaGetLastError();
+}
+
+cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches) {
+  *launches = 0;
+  if (args.chunk_n <= 0) return cudaSuccess;
+  const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
+  const bool in_smem = args.model_in_smem != 0;
+  const bool want_inertia = args.out.qM || args.out.qLD || args.out.qLDiagInv;
+  cudaError_t e;
+  e = in_smem ? launch_phase(smooth_kernel<true>, args, smem, 8, stream)
+              : launch_phase(smooth_kernel<false>, args, 0, 8, stream);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  if (want_inertia) {
+    e = in_smem ? launch_phase(inertia_kernel<true>, args, smem, 8, stream)
+                : launch_phase(inertia_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  if (args.has_contacts) {
+    e = in_smem ? launch_phase(contact_kernel<true>, args, smem, 8, stream)
+                : launch_phase(contact_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  e = in_smem ? launch_phase(backward_kernel<true>, args, smem, 8, stream)
+              : launch_phase(backward_kernel<false>, args, 0, 8, stream);
+  if (e != cudaSuccess) return e;
+  ++*launches;
+  return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -8,23 +8,15 @@
 
 #include "mjb_model.h"
 
-namespace mjb {
-
-// Resident-thread geometry of the main kernel. The per-thread scratch is laid out
-// [slot][kNT] (structure of arrays over thread slots), so consecutive lanes touch consecutive
-// doubles; kNT is a compile-time constant so that `slot + k` offsets fold into immediates.
-constexpr int kThreads = 128;                 // threads per CTA (4 warps)
-constexpr int kSMs = 148;                     // B200
-constexpr int kCtasPerSM = 4;                 // scratch slots provisioned per SM
-constexpr int kGrid = kSMs * kCtasPerSM;      // 592 CTAs
-constexpr int kNT = kGrid * kThreads;         // 75,776 thread slots
-
-}  // namespace mjb
-
-#define MJB_NT mjb::kNT
 #include "mjb_pipeline.h"
 
 namespace mjb {
+
+// launch geometry: 128-thread CTAs (4 warps), grids capped at a multiple of the 148 SMs; every
+// kernel walks its chunk of states with a block-stride loop
+constexpr int kThreads = 128;
+constexpr int kSMs = 148;
+constexpr int kListCap = 32;                  // per-lane survivor list of the contact kernel
 
 struct LaunchArgs {
   const unsigned char* model;   // device blob (mjbHdr + sections)
@@ -33,15 +25,20 @@ struct LaunchArgs {
   const double* qpos;           // [nq][stride]
   const double* qvel;           // [nv][stride]
   const double* qacc;           // [nv][stride]
-  double* scratch;              // [nscratch][kNT]
-  long long stride;             // row stride of every state-indexed array (>= nbatch)
-  int nbatch;
+  double* scratch;              // [nscratch][chunk_stride]  intermediates of one chunk of states
+  int* iscratch;                // [MJB_ISC_COUNT][chunk_stride]
+  long long chunk_stride;       // scratch row stride
+  long long chunk_start;        // first state of the chunk
+  int chunk_n;                  // states in the chunk
+  long long stride;             // row stride of every state-indexed input/output array
   int nconmax, njmax;
+  int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
   Outputs out;
 };
 
-// launches the fused mj_inverse kernel on `stream`; returns cudaGetLastError()
-cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream);
+// launches the phase kernels (smooth, [inertia], [contact], backward) for one chunk on `stream`;
+// *launches receives the number of kernels launched
+cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches);
 
 // AoS [n][rows] (host layout, as in looping mju_copy into d->qpos) <-> SoA [rows][stride]
 cudaError_t launch_aos_to_soa(const double* aos, double* soa, int n, int rows, long long stride,

@@ -4,7 +4,7 @@
 // (reference src/engine/engine_inverse.c:197-261); all control flow that depends only on the
 // model (tree topology, joint types, candidate geom pairs) is warp-uniform, so the 32 lanes of a
 // warp execute the same instruction stream on 32 different states. Intermediates live in a
-// per-thread scratch laid out [slot][MJB_NT] so that lanes touch consecutive doubles.
+// per-state scratch laid out [slot][NS] (NS = states per chunk) so that lanes touch consecutive doubles.
 //
 // Constraint rows are evaluated WITHOUT forming efc_J: a contact row's J*qvel / J*qacc is the
 // relative spatial velocity / acceleration of the two bodies at the contact point projected on
@@ -22,14 +22,19 @@
 #include "mjb_math.h"
 #include "mjb_model.h"
 
-#ifndef MJB_NT
-#error "define MJB_NT (scratch thread-slot stride) before including mjb_pipeline.h"
-#endif
-
 #if defined(__CUDACC__)
 #define MJB_HD __host__ __device__
 #else
 #define MJB_HD
+#endif
+
+// warp votes used to keep compaction loops warp-uniform; identity in the single-lane host build
+#if defined(__CUDA_ARCH__)
+#define MJB_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define MJB_WARP_MAX(x) (__reduce_max_sync(0xffffffffu, (x)))
+#else
+#define MJB_WARP_ANY(p) (p)
+#define MJB_WARP_MAX(x) (x)
 #endif
 
 namespace mjb {
@@ -64,7 +69,9 @@ struct Ctx {
   const mjbHdr* H;
   const int* I;         // int section of the model blob
   const double* D;      // double section of the model blob
-  double* sc;           // scratch, already offset to this thread's slot
+  double* sc;           // double scratch [nscratch][NS], already offset to this state
+  int* isc;             // int scratch [MJB_ISC_COUNT][NS], already offset to this state
+  size_t NS;            // scratch row stride (states per chunk)
   const double* qpos;   // already offset to this state
   const double* qvel;
   const double* qacc;
@@ -77,17 +84,34 @@ struct Ctx {
 
 #define MI(name) (c.I + c.H->ioff[MJB_I_##name])
 #define MD(name) (c.D + c.H->noff[MJB_N_##name])
-#define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * (size_t)MJB_NT)
-#define AT(p, k) (p)[(size_t)(k) * (size_t)MJB_NT]
+#define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * c.NS)
+#define AT(p, k) (p)[(size_t)(k) * c.NS]
 #define QPOS(i) c.qpos[(size_t)(i) * (size_t)c.N]
 #define QVEL(i) c.qvel[(size_t)(i) * (size_t)c.N]
 #define QACC(i) c.qacc[(size_t)(i) * (size_t)c.N]
 
-MJB_DI void ldn(double* dst, const double* p, int first, int n) {
-  for (int k = 0; k < n; k++) dst[k] = AT(p, first + k);
+MJB_DI void ldn_(double* dst, const double* p, int first, int n, size_t stride) {
+  for (int k = 0; k < n; k++) dst[k] = p[(size_t)(first + k) * stride];
 }
-MJB_DI void stn(double* p, int first, const double* src, int n) {
-  for (int k = 0; k < n; k++) AT(p, first + k) = src[k];
+MJB_DI void stn_(double* p, int first, const double* src, int n, size_t stride) {
+  for (int k = 0; k < n; k++) p[(size_t)(first + k) * stride] = src[k];
+}
+#define ldn(dst, p, first, n) ldn_(dst, p, first, n, c.NS)
+#define stn(p, first, src, n) stn_(p, first, src, n, c.NS)
+
+// per-state integer scratch rows: counters carried between the phase kernels
+enum { MJB_ISC_NCON = 0, MJB_ISC_NE, MJB_ISC_NF, MJB_ISC_NL, MJB_ISC_NEFC, MJB_ISC_STATUS,
+       MJB_ISC_COUNT };
+
+MJB_HD inline void save_counters(Ctx& c) {
+  c.isc[MJB_ISC_NCON * c.NS] = c.ncon; c.isc[MJB_ISC_NE * c.NS] = c.ne;
+  c.isc[MJB_ISC_NF * c.NS] = c.nf; c.isc[MJB_ISC_NL * c.NS] = c.nl;
+  c.isc[MJB_ISC_NEFC * c.NS] = c.nefc; c.isc[MJB_ISC_STATUS * c.NS] = c.status;
+}
+MJB_HD inline void load_counters(Ctx& c) {
+  c.ncon = c.isc[MJB_ISC_NCON * c.NS]; c.ne = c.isc[MJB_ISC_NE * c.NS];
+  c.nf = c.isc[MJB_ISC_NF * c.NS]; c.nl = c.isc[MJB_ISC_NL * c.NS];
+  c.nefc = c.isc[MJB_ISC_NEFC * c.NS]; c.status = c.isc[MJB_ISC_STATUS * c.NS];
 }
 
 // engine_util_blas.c:677 with n == 6 (same association as the reference's 4-lane order)
@@ -1161,60 +1185,94 @@ MJB_HD inline int capsule_capsule(Con* con, double margin, const double* pos1, c
   return n1 + n2 + n3 + n4;
 }
 
+// narrow phase of one candidate pair followed by the rows of every contact it yields
+MJB_HD inline void collide_pair(Ctx& c, int ci) {
+  const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
+  const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
+  const double* geom_size = MD(geom_size);
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
+  const double margin = cn[MJB_CN_MARGIN];
+  double pos1[3], pos2[3], mat1[9], mat2[9];
+  ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
+  ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
+  const double* size1 = geom_size + 3*g1;
+  const double* size2 = geom_size + 3*g2;
+  Con con[4];
+  int num = 0;
+  switch (cint[MJB_CI_FUNC]) {
+    case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
+    case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_SPHERE_SPHERE:
+      num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
+    case MJB_FN_SPHERE_CAPSULE:
+      num = sphere_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_SPHERE_CYLINDER:
+      num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_CAPSULE_CAPSULE:
+      num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    default: break;
+  }
+  for (int k = 0; k < num; k++) process_contact(c, ci, con[k]);
+}
+
 // mj_collision over the static candidate list (engine_collision_driver.c:265-484) followed by the
 // contact rows of mj_makeConstraint. The candidate list already encodes the body-pair filters,
 // explicit pairs, and the reference's contact ordering (see mjb_upload.cc).
-MJB_HD inline void collide_and_contact_rows(Ctx& c) {
+//
+// Divergence control: the warp first SCANS candidates with the cheap bounding-sphere filter
+// (mj_filterSphere :146-163; uniform control flow, every lane tests the same pair on its own
+// state) and each lane appends the survivors to its private list; then all lanes PROCESS their
+// own k-th survivor together (narrow phase + contact rows), so a lane is busy whenever it has work
+// instead of idling while another lane's pair is expanded. Lists are bounded (kListCap): when one
+// lane fills up, the warp drains and resumes scanning. Per-lane order is candidate order, so the
+// contact order of the reference is preserved.
+//   valid: false for lanes past the end of the batch (they only take part in the votes)
+//   list / lstride: per-lane survivor list, element k at list[k*lstride]
+MJB_HD inline void collide_and_contact_rows(Ctx& c, bool valid, int* list, int lstride, int cap) {
   const mjbHdr& H = *c.H;
   if ((H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) || H.ncand == 0) return;
   double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
-  const double* geom_size = MD(geom_size);
   const int* cand_int = MI(cand_int);
   const double* cand_num = MD(cand_num);
+  const int ncand = H.ncand;
 
-  for (int ci = 0; ci < H.ncand; ci++) {
-    const int* cint = cand_int + MJB_CAND_NI*ci;
-    const double* cn = cand_num + MJB_CAND_NN*ci;
-    const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
-    const double margin = cn[MJB_CN_MARGIN];
-    double pos1[3], pos2[3];
-    ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
-
-    // mj_filterSphere (:146-163)
-    const int planeflag = cint[MJB_CI_PLANE];
-    if (planeflag == 0) {
-      const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
-      const double bound = cn[MJB_CN_RBOUND];
-      if (dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound) continue;
-    } else if (planeflag == 1) {
-      // plane vs bounded geom: normal distance of the geom centre
-      const double nrm[3] = {AT(gxmat, 9*g1 + 2), AT(gxmat, 9*g1 + 5), AT(gxmat, 9*g1 + 8)};
-      const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
-      if (dot3(dif, nrm) > cn[MJB_CN_RBOUND]) continue;
+  int ci = 0;
+  int last_g1 = -1;
+  double pos1[3] = {0, 0, 0}, nrm[3] = {0, 0, 0};
+  while (ci < ncand) {
+    int cnt = 0;
+    for (; ci < ncand; ci++) {
+      const int* cint = cand_int + MJB_CAND_NI*ci;
+      const double bound = cand_num[MJB_CAND_NN*ci + MJB_CN_RBOUND];
+      const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
+      const int planeflag = cint[MJB_CI_PLANE];
+      bool pass = valid;
+      if (valid) {
+        if (g1 != last_g1) {          // candidates are grouped by geom 1: keep it in registers
+          ldn(pos1, gxpos, 3*g1, 3);
+          if (planeflag == 1) { nrm[0] = AT(gxmat, 9*g1 + 2); nrm[1] = AT(gxmat, 9*g1 + 5); nrm[2] = AT(gxmat, 9*g1 + 8); }
+        }
+        double pos2[3];
+        ldn(pos2, gxpos, 3*g2, 3);
+        if (planeflag == 0) {
+          const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+          pass = !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
+        } else if (planeflag == 1) {
+          const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+          pass = !(dot3(dif, nrm) > bound);
+        }
+      }
+      last_g1 = g1;
+      if (pass) { list[cnt*lstride] = ci; cnt++; }
+      if (MJB_WARP_ANY(cnt == cap)) { ci++; break; }
     }
-
-    double mat1[9], mat2[9];
-    ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
-    const double* size1 = geom_size + 3*g1;
-    const double* size2 = geom_size + 3*g2;
-    Con con[4];
-    int num = 0;
-    switch (cint[MJB_CI_FUNC]) {
-      case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
-      case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
-      case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
-      case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
-      case MJB_FN_SPHERE_SPHERE:
-        num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
-      case MJB_FN_SPHERE_CAPSULE:
-        num = sphere_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
-      case MJB_FN_SPHERE_CYLINDER:
-        num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
-      case MJB_FN_CAPSULE_CAPSULE:
-        num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
-      default: break;
+    const int maxcnt = MJB_WARP_MAX(cnt);
+    for (int k = 0; k < maxcnt; k++) {
+      if (k < cnt) collide_pair(c, list[k*lstride]);
     }
-    for (int k = 0; k < num; k++) process_contact(c, ci, con[k]);
   }
 }
 
@@ -1362,25 +1420,25 @@ MJB_HD inline void inertia(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_inverseSkip(m, d, mjSTAGE_NONE, skipsensor=1) for one state (engine_inverse.c:197-261)
-MJB_HD inline void inverse_one_state(Ctx& c) {
+// mj_inverseSkip(m, d, mjSTAGE_NONE, skipsensor=1) for one state (engine_inverse.c:197-261), cut
+// into four phases that run as separate kernels (each with its own register budget / occupancy)
+// and hand their intermediates over through the per-state scratch in HBM:
+//   smooth   : mj_kinematics, mj_comPos, fixed tendons, mj_comVel, mj_passive,
+//              friction-loss and limit rows of mj_makeConstraint .. mj_invConstraint
+//   inertia  : mj_crb, mj_factorM                      (only when qM/qLD/qLDiagInv are requested)
+//   contact  : mj_collision + contact rows             (only when contacts are enabled)
+//   backward : mj_rne(flg_acc=1), J'f, final combine, output bookkeeping
+
+MJB_HD inline void phase_smooth(Ctx& c) {
   const mjbHdr& H = *c.H;
   c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
   c.status = 0;
   check_inputs(c);
-
-  // mj_invPosition
   kinematics(c);
   com_pos(c);
   tendon_fixed(c);
-  if (c.out.qM || c.out.qLD || c.out.qLDiagInv) inertia(c);
-
-  // mj_invVelocity -> mj_fwdVelocity
   com_vel(c);
   passive(c);
-
-  // mj_collision + mj_makeConstraint + mj_referenceConstraint + mj_invConstraint, row by row in
-  // the reference's order: equality, friction loss, limits, contacts
   {
     double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext);
     for (int i = 0; i < H.nv; i++) AT(qc, i) = 0;
@@ -1389,9 +1447,21 @@ MJB_HD inline void inverse_one_state(Ctx& c) {
   if (!(H.disableflags & MJB_DSBL_CONSTRAINT)) {
     friction_rows(c);
     limit_rows(c);
-    collide_and_contact_rows(c);
   }
+  save_counters(c);
+}
 
+MJB_HD inline void phase_inertia(Ctx& c) { inertia(c); }
+
+MJB_HD inline void phase_contact(Ctx& c, bool valid, int* list, int lstride, int cap) {
+  if (valid) load_counters(c);
+  collide_and_contact_rows(c, valid, list, lstride, cap);
+  if (valid) save_counters(c);
+}
+
+MJB_HD inline void phase_backward(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  load_counters(c);
   rne_and_output(c);
 
   const size_t N = (size_t)c.N;
@@ -1422,10 +1492,21 @@ MJB_HD inline void inverse_one_state(Ctx& c) {
   }
 }
 
+// all phases for one state in sequence (single-lane host build of the tests)
+MJB_HD inline void inverse_one_state(Ctx& c) {
+  int list[64];
+  phase_smooth(c);
+  if (c.out.qM || c.out.qLD || c.out.qLDiagInv) phase_inertia(c);
+  phase_contact(c, true, list, 1, 64);
+  phase_backward(c);
+}
+
 #undef MI
 #undef MD
 #undef SC
 #undef AT
+#undef ldn
+#undef stn
 #undef QPOS
 #undef QVEL
 #undef QACC

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#define MJB_NT 1
+
 #include "mjb_pipeline.h"
 #include "mjb_upload.h"
 
@@ -30,12 +30,15 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
   }
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
   std::vector<double> scratch((size_t)H->nscratch + 1);
+  int iscratch[mjb::MJB_ISC_COUNT];
   for (int s = 0; s < nbatch; s++) {
     mjb::Ctx c;
     c.H = H;
     c.I = reinterpret_cast<const int*>(blob.data() + H->int_section);
     c.D = reinterpret_cast<const double*>(blob.data() + H->num_section);
     c.sc = scratch.data();
+    c.isc = iscratch;
+    c.NS = 1;
     c.qpos = qpos_soa + s;
     c.qvel = qvel_soa + s;
     c.qacc = qacc_soa + s;

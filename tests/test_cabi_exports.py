@@ -51,7 +51,7 @@ def test_kernels_are_compiled_for_sm_100a_with_tma():
     elf = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "inverse_kernel" in sass
+    assert "smooth_kernel" in sass and "contact_kernel" in sass and "backward_kernel" in sass
     assert "UBLKCP" in sass, "model blob staging is not a TMA bulk copy"
     assert "DFMA" in sass
 
