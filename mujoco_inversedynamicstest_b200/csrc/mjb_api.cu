@@ -26,7 +26,7 @@ struct mjbData_ {
   int model_bytes = 0;
   int model_in_smem = 0;
   double* d_scratch = nullptr;   // [nscratch][chunk_stride]
-  int* d_iscratch = nullptr;      // [MJB_ISC_COUNT][chunk_stride]
+  int* d_iscratch = nullptr;      // [MJB_ISC_MASK + ceil(ncand/32)][chunk_stride]
   long long chunk_stride = 0;     // states per chunk (intermediates are allocated per chunk)
   long long kernel_launches = 0;  // phase kernels launched so far (reported by the benchmark)
   // inputs: internal SoA buffers and the views currently in use
@@ -126,7 +126,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
                    "cudaMemcpy(model)");
   // intermediates live per chunk of states: at most 2^20 states and at most ~12 GB
   {
-    const double bytes_per_state = 8.0 * H.nscratch + 4.0 * mjb::MJB_ISC_COUNT;
+    const double bytes_per_state = 8.0 * H.nscratch + 4.0 * (mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1);
     long long chunk = (long long)(12.0e9 / bytes_per_state);
     if (chunk > (1LL << 20)) chunk = 1LL << 20;
     if (chunk > d->stride) chunk = d->stride;
@@ -135,7 +135,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     d->chunk_stride = chunk;
   }
   ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
-  ok = ok && devAlloc(d, &d->d_iscratch, (size_t)mjb::MJB_ISC_COUNT * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
+  ok = ok && devAlloc(d, &d->d_iscratch, (size_t)(mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1) * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
   const size_t S = (size_t)d->stride;
   ok = ok && devAlloc(d, &d->d_qpos, (size_t)H.nq * S, "cudaMalloc(qpos)");
   ok = ok && devAlloc(d, &d->d_qvel, (size_t)H.nv * S, "cudaMalloc(qvel)");

@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(kThreads, 4) inertia_kernel(LaunchArgs a) {
   }
 }
 
+// contact scan: bounding-sphere survivors of every state as a bit mask + count
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    contact_scan(c);
+  }
+}
+
 template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, 4) contact_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 4) contact_kernel(LaunchArgs a) {
        i0 += (long long)gridDim.x * kThreads) {
     const long long i = i0 + threadIdx.x;
     const bool valid = i < a.chunk_n;
-    bind_state(c, a, valid ? i : (long long)a.chunk_n - 1);
+    bind_state(c, a, valid ? i : 0LL);
     phase_contact(c, valid, lists + threadIdx.x, kThreads, kListCap);
   }
 }
@@ -188,10 +202,13 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     ++*launches;
   }
   if (args.has_contacts) {
+    e = in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
+                : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
     e = in_smem ? launch_phase(contact_kernel<true>, args, smem, 8, stream)
                 : launch_phase(contact_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
-    ++*launches;
+    *launches += 2;
   }
   e = in_smem ? launch_phase(backward_kernel<true>, args, smem, 8, stream)
               : launch_phase(backward_kernel<false>, args, 0, 8, stream);

@@ -26,7 +26,7 @@ struct LaunchArgs {
   const double* qvel;           // [nv][stride]
   const double* qacc;           // [nv][stride]
   double* scratch;              // [nscratch][chunk_stride]  intermediates of one chunk of states
-  int* iscratch;                // [MJB_ISC_COUNT][chunk_stride]
+  int* iscratch;                // [MJB_ISC_MASK + ceil(ncand/32)][chunk_stride]
   long long chunk_stride;       // scratch row stride
   long long chunk_start;        // first state of the chunk
   int chunk_n;                  // states in the chunk

@@ -201,9 +201,8 @@ enum {
   MJB_SC_qfrc_passive, // nv
   MJB_SC_ten_length,   // ntendon
   MJB_SC_ten_velocity, // ntendon
-  MJB_SC_crb,          // nbody*10
-  MJB_SC_qM,           // nM
-  MJB_SC_qLD,          // nC
+  MJB_SC_crb,          // nbody*10  composite rigid-body inertias
+  MJB_SC_ia,           // nbody*21  articulated-body inertias (symmetric 6x6, upper triangle)
   MJB_SC_COUNT
 };
 

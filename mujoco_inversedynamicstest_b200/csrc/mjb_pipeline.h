@@ -100,8 +100,9 @@ MJB_DI void stn_(double* p, int first, const double* src, int n, size_t stride) 
 #define stn(p, first, src, n) stn_(p, first, src, n, c.NS)
 
 // per-state integer scratch rows: counters carried between the phase kernels
+// MJB_ISC_NSURV / MJB_ISC_MASK..: survivors of the contact scan (count, then ceil(ncand/32) words)
 enum { MJB_ISC_NCON = 0, MJB_ISC_NE, MJB_ISC_NF, MJB_ISC_NL, MJB_ISC_NEFC, MJB_ISC_STATUS,
-       MJB_ISC_COUNT };
+       MJB_ISC_NSURV, MJB_ISC_MASK, MJB_ISC_COUNT = MJB_ISC_MASK };
 
 MJB_HD inline void save_counters(Ctx& c) {
   c.isc[MJB_ISC_NCON * c.NS] = c.ncon; c.isc[MJB_ISC_NE * c.NS] = c.ne;
@@ -1222,54 +1223,83 @@ MJB_HD inline void collide_pair(Ctx& c, int ci) {
 // contact rows of mj_makeConstraint. The candidate list already encodes the body-pair filters,
 // explicit pairs, and the reference's contact ordering (see mjb_upload.cc).
 //
-// Divergence control: the warp first SCANS candidates with the cheap bounding-sphere filter
-// (mj_filterSphere :146-163; uniform control flow, every lane tests the same pair on its own
-// state) and each lane appends the survivors to its private list; then all lanes PROCESS their
-// own k-th survivor together (narrow phase + contact rows), so a lane is busy whenever it has work
-// instead of idling while another lane's pair is expanded. Lists are bounded (kListCap): when one
-// lane fills up, the warp drains and resumes scanning. Per-lane order is candidate order, so the
-// contact order of the reference is preserved.
-//   valid: false for lanes past the end of the batch (they only take part in the votes)
-//   list / lstride: per-lane survivor list, element k at list[k*lstride]
-MJB_HD inline void collide_and_contact_rows(Ctx& c, bool valid, int* list, int lstride, int cap) {
+// Divergence control, in two kernels:
+//  contact_scan   : every lane tests the same candidate on its own state with the cheap
+//                   bounding-sphere filter (mj_filterSphere :146-163; uniform control flow) and
+//                   records the survivors as a bit mask plus their count.
+//  contact_process: each lane expands its mask into a private list and all lanes process their own
+//                   k-th survivor together (narrow phase + contact rows), so a lane is busy
+//                   whenever it has work instead of idling while another lane's pair is expanded.
+//                   Per-lane order is candidate order, so the reference's contact order is kept.
+// (A counting sort of the states by survivor count in front of contact_process was measured and
+//  dropped: lane occupancy did not improve -- the idle lanes come from the contact / no-contact
+//  outcome of the narrow phase -- while the permuted, uncoalesced scratch accesses tripled the
+//  DRAM traffic; profiles/r01_launches_sorted_contact_experiment.csv.)
+MJB_HD inline int contact_scan(Ctx& c) {
   const mjbHdr& H = *c.H;
-  if ((H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) || H.ncand == 0) return;
   double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
   const int* cand_int = MI(cand_int);
   const double* cand_num = MD(cand_num);
   const int ncand = H.ncand;
-
-  int ci = 0;
-  int last_g1 = -1;
+  int last_g1 = -1, total = 0;
   double pos1[3] = {0, 0, 0}, nrm[3] = {0, 0, 0};
-  while (ci < ncand) {
-    int cnt = 0;
-    for (; ci < ncand; ci++) {
-      const int* cint = cand_int + MJB_CAND_NI*ci;
-      const double bound = cand_num[MJB_CAND_NN*ci + MJB_CN_RBOUND];
-      const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
-      const int planeflag = cint[MJB_CI_PLANE];
-      bool pass = valid;
-      if (valid) {
-        if (g1 != last_g1) {          // candidates are grouped by geom 1: keep it in registers
-          ldn(pos1, gxpos, 3*g1, 3);
-          if (planeflag == 1) { nrm[0] = AT(gxmat, 9*g1 + 2); nrm[1] = AT(gxmat, 9*g1 + 5); nrm[2] = AT(gxmat, 9*g1 + 8); }
-        }
-        double pos2[3];
-        ldn(pos2, gxpos, 3*g2, 3);
-        if (planeflag == 0) {
-          const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
-          pass = !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
-        } else if (planeflag == 1) {
-          const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
-          pass = !(dot3(dif, nrm) > bound);
-        }
-      }
+  unsigned bits = 0;
+  for (int ci = 0; ci < ncand; ci++) {
+    const int* cint = cand_int + MJB_CAND_NI*ci;
+    const double bound = cand_num[MJB_CAND_NN*ci + MJB_CN_RBOUND];
+    const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
+    const int planeflag = cint[MJB_CI_PLANE];
+    if (g1 != last_g1) {          // candidates are grouped by geom 1: keep it in registers
+      ldn(pos1, gxpos, 3*g1, 3);
+      if (planeflag == 1) { nrm[0] = AT(gxmat, 9*g1 + 2); nrm[1] = AT(gxmat, 9*g1 + 5); nrm[2] = AT(gxmat, 9*g1 + 8); }
       last_g1 = g1;
-      if (pass) { list[cnt*lstride] = ci; cnt++; }
-      if (MJB_WARP_ANY(cnt == cap)) { ci++; break; }
+    }
+    double pos2[3];
+    ldn(pos2, gxpos, 3*g2, 3);
+    bool pass = true;
+    if (planeflag == 0) {
+      const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+      pass = !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
+    } else if (planeflag == 1) {
+      const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+      pass = !(dot3(dif, nrm) > bound);
+    }
+    if (pass) { bits |= 1u << (ci & 31); total++; }
+    if ((ci & 31) == 31 || ci == ncand - 1) {
+      c.isc[(size_t)(MJB_ISC_MASK + (ci >> 5)) * c.NS] = (int)bits;
+      bits = 0;
+    }
+  }
+  c.isc[(size_t)MJB_ISC_NSURV * c.NS] = total;
+  return total;
+}
+
+MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, int cap) {
+  const mjbHdr& H = *c.H;
+  const int nwords = (H.ncand + 31) >> 5;
+  int w = 0;
+  unsigned bits = (valid && nwords > 0) ? (unsigned)c.isc[(size_t)MJB_ISC_MASK * c.NS] : 0u;
+  while (true) {
+    int cnt = 0;
+    if (valid) {
+      while (cnt < cap) {
+        while (bits == 0 && w + 1 < nwords) {
+          w++;
+          bits = (unsigned)c.isc[(size_t)(MJB_ISC_MASK + w) * c.NS];
+        }
+        if (bits == 0) break;
+#if defined(__CUDA_ARCH__)
+        const int b = __ffs((int)bits) - 1;
+#else
+        const int b = __builtin_ctz(bits);
+#endif
+        bits &= bits - 1;
+        list[cnt*lstride] = (w << 5) + b;
+        cnt++;
+      }
     }
     const int maxcnt = MJB_WARP_MAX(cnt);
+    if (maxcnt == 0) break;
     for (int k = 0; k < maxcnt; k++) {
       if (k < cnt) collide_pair(c, list[k*lstride]);
     }
@@ -1358,65 +1388,116 @@ MJB_HD inline void rne_and_output(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_crb (engine_core_smooth.c:1353-1401) and mj_factorM / mj_factorI (:1470-1511)
+// mj_crb (engine_core_smooth.c:1353-1401) and mj_factorM / mj_factorI (:1470-1511) in one
+// leaves-to-root sweep.
+//
+// qM is the reference's composite-rigid-body form: M(k,i) = cdof_i . (crb_body(k) cdof_k) for i on
+// the ancestor chain of k. For qLD the reference eliminates rows of M in place, O(sum depth^2)
+// read-modify-writes of a matrix that would have to live in HBM here. The same unique L'DL factors
+// are obtained without touching M from the articulated-body recursion (Featherstone, RBDA ch. 6/7):
+// with every spatial quantity already expressed in the common com-based frame,
+//     IA_b   = cinert_b + sum_children IA_c          (6x6 symmetric, 21 numbers)
+//     U_k    = IA_b cdof_k ,  D_k = cdof_k.U_k + armature_k        (dofs of b, last to first)
+//     L(k,i) = cdof_i.U_k / D_k  for every ancestor dof i ;  IA_b -= U_k U_k' / D_k
+// so each entry of qLD is computed once (one dot product) and written once, and the ancestor walk
+// is shared with the qM entries. Values agree with mj_factorI to rounding.
+
+// y = A x for a symmetric 6x6 stored as its 21 upper-triangular entries (row-major)
+MJB_DI void sym6_mul(double* y, const double* A, const double* x) {
+  y[0] = A[0]*x[0] + A[1]*x[1] + A[2]*x[2] + A[3]*x[3] + A[4]*x[4] + A[5]*x[5];
+  y[1] = A[1]*x[0] + A[6]*x[1] + A[7]*x[2] + A[8]*x[3] + A[9]*x[4] + A[10]*x[5];
+  y[2] = A[2]*x[0] + A[7]*x[1] + A[11]*x[2] + A[12]*x[3] + A[13]*x[4] + A[14]*x[5];
+  y[3] = A[3]*x[0] + A[8]*x[1] + A[12]*x[2] + A[15]*x[3] + A[16]*x[4] + A[17]*x[5];
+  y[4] = A[4]*x[0] + A[9]*x[1] + A[13]*x[2] + A[16]*x[3] + A[18]*x[4] + A[19]*x[5];
+  y[5] = A[5]*x[0] + A[10]*x[1] + A[14]*x[2] + A[17]*x[3] + A[19]*x[4] + A[20]*x[5];
+}
+
+// the 10-number rigid inertia of mju_inertCom as a symmetric 6x6 (layout of mju_mulInertVec)
+MJB_DI void inert_to_sym6(double* A, const double* i) {
+  A[0] = i[0];  A[1] = i[3];  A[2] = i[4];  A[3] = 0;     A[4] = -i[8]; A[5] = i[7];
+  A[6] = i[1];  A[7] = i[5];  A[8] = i[8];  A[9] = 0;     A[10] = -i[6];
+  A[11] = i[2]; A[12] = -i[7]; A[13] = i[6]; A[14] = 0;
+  A[15] = i[9]; A[16] = 0;    A[17] = 0;
+  A[18] = i[9]; A[19] = 0;
+  A[20] = i[9];
+}
+
 MJB_HD inline void inertia(Ctx& c) {
   const mjbHdr& H = *c.H;
-  const int nbody = H.nbody, nv = H.nv;
-  double* crb = SC(crb); double* cinert = SC(cinert); double* cdof = SC(cdof);
-  double* qM = SC(qM); double* qLD = SC(qLD);
+  const int nbody = H.nbody;
+  double* crb = SC(crb); double* ia = SC(ia); double* cinert = SC(cinert); double* cdof = SC(cdof);
   const int* body_parentid = MI(body_parentid);
-  const int* dof_bodyid = MI(dof_bodyid);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
   const int* dof_parentid = MI(dof_parentid);
   const int* dof_Madr = MI(dof_Madr);
   const int* dof_simplenum = MI(dof_simplenum);
+  const int* rownnz = MI(C_rownnz); const int* rowadr = MI(C_rowadr);
   const double* armature = MD(dof_armature);
   const double* dof_M0 = MD(dof_M0);
   const size_t N = (size_t)c.N;
+  double* qM = c.out.qM + c.s; double* qLD = c.out.qLD + c.s; double* qLDiagInv = c.out.qLDiagInv + c.s;
 
-  for (int k = 0; k < 10*nbody; k++) AT(crb, k) = AT(cinert, k);
-  for (int i = nbody - 1; i > 0; i--) {
-    const int p = body_parentid[i];
-    if (p > 0) for (int k = 0; k < 10; k++) AT(crb, 10*p + k) += AT(crb, 10*i + k);
+  // crb = cinert, IA = cinert as 6x6 (world body stays zero and is never read)
+  for (int b = 1; b < nbody; b++) {
+    double ci[10], A[21];
+    ldn(ci, cinert, 10*b, 10);
+    inert_to_sym6(A, ci);
+    stn(crb, 10*b, ci, 10);
+    stn(ia, 21*b, A, 21);
   }
-  for (int k = 0; k < H.nM; k++) AT(qM, k) = 0;
-  for (int i = 0; i < nv; i++) {
-    if (dof_simplenum[i]) {
-      const int n = i + dof_simplenum[i];
-      for (; i < n; i++) AT(qM, dof_Madr[i]) = dof_M0[i];
-      if (i == nv) break;
-    }
-    int adr = dof_Madr[i];
-    AT(qM, adr) = armature[i];
-    double ci[10], cd[6], buf[6];
-    ldn(ci, crb, 10*dof_bodyid[i], 10); ldn(cd, cdof, 6*i, 6);
-    mulInertVec(buf, ci, cd);
-    for (int j = i; j >= 0; j = dof_parentid[j]) {
-      double cj[6];
-      ldn(cj, cdof, 6*j, 6);
-      AT(qM, adr) += dot6(cj, buf);
-      adr++;
-    }
-  }
-  if (c.out.qM) for (int k = 0; k < H.nM; k++) c.out.qM[(size_t)k*N + c.s] = AT(qM, k);
 
-  const int* rownnz = MI(C_rownnz); const int* rowadr = MI(C_rowadr);
-  const int* colind = MI(C_colind); const int* mapM2C = MI(mapM2C);
-  for (int k = 0; k < H.nC; k++) AT(qLD, k) = AT(qM, mapM2C[k]);
-  for (int k = nv - 1; k >= 0; k--) {
-    const int rowadr_k = rowadr[k];
-    const int diag_k = rowadr_k + rownnz[k] - 1;
-    const double invD = 1 / AT(qLD, diag_k);
-    if (c.out.qLDiagInv) c.out.qLDiagInv[(size_t)k*N + c.s] = invD;
-    if (dof_simplenum[k]) continue;
-    for (int adr = diag_k - 1; adr >= rowadr_k; adr--) {
-      const double tmp = AT(qLD, adr) * invD;
-      const int i = colind[adr];
-      const int ra = rowadr[i], n = rownnz[i];
-      for (int e = 0; e < n; e++) AT(qLD, ra + e) += AT(qLD, rowadr_k + e) * (-tmp);
-      AT(qLD, adr) = tmp;
+  for (int b = nbody - 1; b > 0; b--) {
+    double cr[10], A[21];
+    ldn(cr, crb, 10*b, 10);
+    ldn(A, ia, 21*b, 21);
+    const int adr0 = body_dofadr[b], num = body_dofnum[b];
+    for (int k = adr0 + num - 1; k >= adr0; k--) {
+      const int madr = dof_Madr[k];
+      const int diag = rowadr[k] + rownnz[k] - 1;
+      if (dof_simplenum[k]) {
+        // simple body: M is diagonal and constant (engine_core_smooth.c:1375-1385, :1498)
+        const double m0 = dof_M0[k];
+        qM[(size_t)madr*N] = m0;
+        qLD[(size_t)diag*N] = m0;
+        qLDiagInv[(size_t)k*N] = 1/m0;
+        int t = 1;
+        for (int i = dof_parentid[k]; i >= 0; i = dof_parentid[i], t++) {
+          qM[(size_t)(madr + t)*N] = 0;
+          qLD[(size_t)(diag - t)*N] = 0;
+        }
+        continue;
+      }
+      double S[6], buf[6], U[6];
+      ldn(S, cdof, 6*k, 6);
+      mulInertVec(buf, cr, S);
+      sym6_mul(U, A, S);
+      const double Mkk = armature[k] + dot6(S, buf);
+      const double D = armature[k] + dot6(S, U);
+      const double invD = 1/D;
+      qM[(size_t)madr*N] = Mkk;
+      qLD[(size_t)diag*N] = D;
+      qLDiagInv[(size_t)k*N] = invD;
+      int t = 1;
+      for (int i = dof_parentid[k]; i >= 0; i = dof_parentid[i], t++) {
+        double Si[6];
+        ldn(Si, cdof, 6*i, 6);
+        qM[(size_t)(madr + t)*N] = dot6(Si, buf);
+        qLD[(size_t)(diag - t)*N] = dot6(Si, U) * invD;
+      }
+      // IA -= U U' / D
+      int e = 0;
+      for (int r = 0; r < 6; r++) {
+        const double ur = U[r]*invD;
+        for (int q = r; q < 6; q++) A[e++] -= ur*U[q];
+      }
+    }
+    const int p = body_parentid[b];
+    if (p > 0) {
+      for (int j = 0; j < 10; j++) AT(crb, 10*p + j) += cr[j];
+      for (int j = 0; j < 21; j++) AT(ia, 21*p + j) += A[j];
     }
   }
-  if (c.out.qLD) for (int k = 0; k < H.nC; k++) c.out.qLD[(size_t)k*N + c.s] = AT(qLD, k);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1453,9 +1534,13 @@ MJB_HD inline void phase_smooth(Ctx& c) {
 
 MJB_HD inline void phase_inertia(Ctx& c) { inertia(c); }
 
+MJB_HD inline bool contacts_enabled(const mjbHdr& H) {
+  return !(H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) && H.ncand > 0;
+}
+
 MJB_HD inline void phase_contact(Ctx& c, bool valid, int* list, int lstride, int cap) {
   if (valid) load_counters(c);
-  collide_and_contact_rows(c, valid, list, lstride, cap);
+  contact_process(c, valid, list, lstride, cap);
   if (valid) save_counters(c);
 }
 
@@ -1497,7 +1582,10 @@ MJB_HD inline void inverse_one_state(Ctx& c) {
   int list[64];
   phase_smooth(c);
   if (c.out.qM || c.out.qLD || c.out.qLDiagInv) phase_inertia(c);
-  phase_contact(c, true, list, 1, 64);
+  if (contacts_enabled(*c.H)) {
+    contact_scan(c);
+    phase_contact(c, true, list, 1, 64);
+  }
   phase_backward(c);
 }
 

@@ -513,7 +513,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
     sizes[MJB_SC_qfrc_passive] = nv;
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
-    sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_qM] = m->nM; sizes[MJB_SC_qLD] = m->nC;
+    sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;
@@ -536,7 +536,7 @@ const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
     "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
     "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cdof_dot", "cacc_lin", "cacc", "cfrc",
-    "cfrc_ext", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "qM", "qLD"};
+    "cfrc_ext", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
 

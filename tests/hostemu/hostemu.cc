@@ -30,7 +30,8 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
   }
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
   std::vector<double> scratch((size_t)H->nscratch + 1);
-  int iscratch[mjb::MJB_ISC_COUNT];
+  std::vector<int> iscratch_v((size_t)mjb::MJB_ISC_MASK + (size_t)((H->ncand + 31) / 32) + 1);
+  int* iscratch = iscratch_v.data();
   for (int s = 0; s < nbatch; s++) {
     mjb::Ctx c;
     c.H = H;
