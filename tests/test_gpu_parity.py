@@ -224,3 +224,28 @@ def test_unsupported_models_are_rejected_at_upload(tmp_path):
     model.set_opt_int("disableflags", 0)          # contacts on: capsule-cylinder pairs -> mjc_Convex
     with pytest.raises(mjb.MjbError, match="collision function"):
         mjb.BatchData(model, 8)
+
+
+def test_cuda_vs_c_restatement_on_fresh_states():
+    """Third leg of the three-way check: CUDA path vs oracle/mjinv_oracle.c (dense-Jacobian
+    restatement) on states that are in no fixture."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    from oracle import restatement
+    from test_oracle_restatement import ctypes_opt
+    for name in ("humanoid", "humanoid_elliptic"):
+        model = mjb.Model.from_mjb(util.golden(name)[0])
+        r = restatement.Restatement(model, ctypes_opt(model))
+        n = 512
+        qpos, qvel, qacc = generate_states(model, n, first=7_000_000)
+        ref = r.inverse_batch(qpos, qvel, qacc, inertia=False)
+        bd = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC, nconmax=64, njmax=256)
+        bd.set_state(qpos, qvel, qacc)
+        assert bd.inverse() == 0
+        cnt = bd.counts()
+        np.testing.assert_array_equal(cnt["ncon"], ref["ncon"])
+        np.testing.assert_array_equal(cnt["nefc"], ref["nefc"])
+        np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
+        np.testing.assert_array_equal(bd.efc()["type"], ref["efc_type"])
+        nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+        assert nviol == 0, (name, nviol, worst)
