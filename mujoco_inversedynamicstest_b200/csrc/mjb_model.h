@@ -59,6 +59,7 @@
   X(C_colind)  /* nC   : qLD column indices (ancestors ascending, self last)    */ \
   X(mapM2C)    /* nC   : qLD[k] = qM[mapM2C[k]] (engine_io.c:1135-1188)         */ \
   X(cand_int)  /* ncand*MJB_CAND_NI : candidate geom pairs, see MJB_CI_*        */ \
+  X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */
 
@@ -95,6 +96,8 @@
   X(tendon_frictionloss, ntendon, 1) \
   X(tendon_lengthspring, ntendon, 2) \
   X(tendon_invweight0, ntendon, 1)   \
+  X(tendon_length0, ntendon, 1)      \
+  X(eq_data, neq, 11)                \
   X(wrap_prm, nwrap, 1)
 
 // ---- derived double tables: pre-clamped solver parameters, MJB_SP_N doubles per record
@@ -103,6 +106,8 @@
   X(sp_tendon_limit)  /* ntendon */ \
   X(sp_dof_friction)  /* nv      */ \
   X(sp_tendon_friction) /* ntendon */ \
+  X(sp_eq)            /* neq     */ \
+  X(eq_num)           /* neq*MJB_EQ_NN: site offsets / quaternions of site-defined constraints */ \
   X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */
 
 enum {
@@ -157,6 +162,28 @@ enum {
   MJB_CN_SOLREF,          // 2: contact.solref as stored in mjContact (for output)
   MJB_CN_SOLIMP = MJB_CN_SOLREF + 2,      // 5: contact.solimp as stored (unclamped)
   MJB_CAND_NN = MJB_CN_SOLIMP + 5
+};
+
+// equality constraint: integer columns (mj_instantiateEquality, engine_core_constraint.c:493-763)
+enum {
+  MJB_EQI_TYPE = 0,   // mjtEq: 0 connect, 1 weld, 2 joint, 3 tendon
+  MJB_EQI_ACTIVE,     // eq_active0
+  MJB_EQI_B0,         // body of object 1 / joint id / tendon id
+  MJB_EQI_B1,         // body of object 2 / joint id / tendon id (-1: none)
+  MJB_EQI_SITE,       // 1: site semantics (anchors and orientations come from MJB_EQ_NN numbers)
+  MJB_EQI_SKIP,       // 1: both bodies static -> all-zero Jacobian, constraint dropped (:284-336)
+  MJB_EQ_NI
+};
+// equality constraint: double columns
+enum {
+  MJB_EQN_ANCHOR0 = 0,   // 3: point on object-1 body, body frame
+  MJB_EQN_ANCHOR1 = 3,   // 3: point on object-2 body, body frame
+  MJB_EQN_Q0 = 6,        // 4: orientation offset applied to xquat of body 0 (relpose / site_quat)
+  MJB_EQN_Q1 = 10,       // 4: orientation offset applied to xquat of body 1 (identity / site_quat)
+  MJB_EQN_TORQUESCALE = 14,
+  MJB_EQN_DA_TRAN = 15,  // body_invweight0 sums (translation, rotation) / dof or tendon invweight sum
+  MJB_EQN_DA_ROT = 16,
+  MJB_EQ_NN = 17
 };
 
 // narrow-phase function ids (engine_collision_driver.c:41-52, only primitive pairs)

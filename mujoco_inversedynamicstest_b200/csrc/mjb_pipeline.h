@@ -383,13 +383,15 @@ MJB_HD inline void tendon_fixed(Ctx& c) {
   if (!H.ntendon) return;
   double* L = SC(ten_length); double* V = SC(ten_velocity);
   const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
-  const int* wrap_objid = MI(wrap_objid);
+  const int* wrap_objid = MI(wrap_objid); const int* wrap_type = MI(wrap_type);
   const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
   const double* wrap_prm = MD(wrap_prm);
   for (int t = 0; t < H.ntendon; t++) {
     const int adr = tendon_adr[t], num = tendon_num[t];
     double len = 0, vel = 0;
-    for (int j = 0; j < num; j++) {
+    // spatial tendons are accepted only when they carry no force: their length is not computed
+    const bool fixed = wrap_type[adr] == MJB_WRAP_JOINT;
+    for (int j = 0; fixed && j < num; j++) {
       const int k = wrap_objid[adr + j];
       len += wrap_prm[adr + j] * QPOS(jnt_qposadr[k]);
       vel += wrap_prm[adr + j] * QVEL(jnt_dofadr[k]);
@@ -606,6 +608,182 @@ MJB_HD inline double scalar_row(Ctx& c, int type, int id, const double* sp, doub
   }
   emit_row(c, type, id, pos, margin, D, R, vel, aref, force, state, imp);
   return force;
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_instantiateEquality (engine_core_constraint.c:493-763): connect, weld, joint and (fixed)
+// tendon couplings, evaluated without forming the Jacobian.
+//   connect / weld translation rows: J = jacp(body0, pos0) - jacp(body1, pos1), world axes
+//   weld rotation rows: J = torquescale * 0.5 * vec( neg(q1) (0, jacr0 - jacr1) q0 relpose ), a
+//     linear map L of the angular-velocity difference; J*v = L(w0 - w1), J'f = torque L'f
+//   joint / tendon rows: single dofs (tendons: their joint list) with the polynomial's derivative
+
+// spatial motion of body b at world point p from a carrier array (cvel or cacc_lin)
+MJB_HD inline void point_motion(Ctx& c, const double* carrier, int b, const double* p, double* lin,
+                                double* ang) {
+  const int* rootid = MI(body_rootid);
+  double* com = SC(subtree_com);
+  double v[6], o[3], r[3], cr[3];
+  ldn(v, carrier, 6*b, 6); ldn(o, com, 3*rootid[b], 3);
+  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+  cross3(cr, v, r);
+  for (int k = 0; k < 3; k++) { lin[k] = v[3 + k] + cr[k]; ang[k] = v[k]; }
+}
+
+// cfrc_ext[b] += sign * [ (p - O_b) x F + T ; F ]
+MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, const double* T,
+                              double sign) {
+  const int* rootid = MI(body_rootid);
+  double* com = SC(subtree_com);
+  double* fe = SC(cfrc_ext);
+  double o[3], r[3], cr[3];
+  ldn(o, com, 3*rootid[b], 3);
+  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+  cross3(cr, r, F);
+  for (int k = 0; k < 3; k++) {
+    AT(fe, 6*b + k) += sign*(cr[k] + T[k]);
+    AT(fe, 6*b + 3 + k) += sign*F[k];
+  }
+}
+
+// 0.5 * vec( quat1 * (0, a) * quat )   (engine_core_constraint.c:617-635)
+MJB_DI void weld_rot_map(double* res, const double* quat1, const double* quat, const double* a) {
+  double q2[4] = {-quat1[1]*a[0] - quat1[2]*a[1] - quat1[3]*a[2],
+                  quat1[0]*a[0] + quat1[2]*a[2] - quat1[3]*a[1],
+                  quat1[0]*a[1] + quat1[3]*a[0] - quat1[1]*a[2],
+                  quat1[0]*a[2] + quat1[1]*a[1] - quat1[2]*a[0]};   // mju_mulQuatAxis
+  double q3[4];
+  mulQuat(q3, q2, quat);
+  res[0] = 0.5*q3[1]; res[1] = 0.5*q3[2]; res[2] = 0.5*q3[3];
+}
+
+MJB_HD inline void equality_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (H.neq == 0 || (H.disableflags & MJB_DSBL_EQUALITY)) return;
+  const int* eq_int = MI(eq_int);
+  const double* eq_num = MD(eq_num);
+  const double* eq_data = MD(eq_data);
+  const double* sp_eq = MD(sp_eq);
+  double* xpos = SC(xpos); double* xmat = SC(xmat); double* xquat = SC(xquat);
+  double* qc = SC(qfrc_c);
+  for (int i = 0; i < H.neq; i++) {
+    const int* ei = eq_int + MJB_EQ_NI*i;
+    const double* en = eq_num + MJB_EQ_NN*i;
+    const double* sp = sp_eq + MJB_SP_N*i;
+    if (!ei[MJB_EQI_ACTIVE]) continue;
+    const int type = ei[MJB_EQI_TYPE];
+    if (type == 0 || type == 1) {
+      if (ei[MJB_EQI_SKIP]) continue;
+      const int b0 = ei[MJB_EQI_B0], b1 = ei[MJB_EQI_B1];
+      double pos0[3], pos1[3], m0[9], m1[9], p[3];
+      ldn(m0, xmat, 9*b0, 9); ldn(m1, xmat, 9*b1, 9);
+      mulMatVec3(pos0, m0, en + MJB_EQN_ANCHOR0); ldn(p, xpos, 3*b0, 3);
+      pos0[0] += p[0]; pos0[1] += p[1]; pos0[2] += p[2];
+      mulMatVec3(pos1, m1, en + MJB_EQN_ANCHOR1); ldn(p, xpos, 3*b1, 3);
+      pos1[0] += p[0]; pos1[1] += p[1]; pos1[2] += p[2];
+      const int nrow = type == 0 ? 3 : 6;
+      double cpos[6], vel[6], acc[6], l0[3], a0[3], l1[3], a1[3];
+      for (int k = 0; k < 3; k++) cpos[k] = pos0[k] - pos1[k];
+      point_motion(c, SC(cvel), b0, pos0, l0, a0);
+      point_motion(c, SC(cvel), b1, pos1, l1, a1);
+      double wv[3] = {a0[0] - a1[0], a0[1] - a1[1], a0[2] - a1[2]};
+      for (int k = 0; k < 3; k++) vel[k] = l0[k] - l1[k];
+      point_motion(c, SC(cacc_lin), b0, pos0, l0, a0);
+      point_motion(c, SC(cacc_lin), b1, pos1, l1, a1);
+      double wa[3] = {a0[0] - a1[0], a0[1] - a1[1], a0[2] - a1[2]};
+      for (int k = 0; k < 3; k++) acc[k] = l0[k] - l1[k];
+      double quat[4] = {1, 0, 0, 0}, quat1[4] = {1, 0, 0, 0};
+      const double ts = en[MJB_EQN_TORQUESCALE];
+      if (type == 1) {
+        double q0[4], q1[4], t[4], q2[4];
+        ldn(q0, xquat, 4*b0, 4); ldn(q1, xquat, 4*b1, 4);
+        mulQuat(quat, q0, en + MJB_EQN_Q0);            // q0 * relpose   (or body0 * site_quat0)
+        if (ei[MJB_EQI_SITE]) { mulQuat(t, q1, en + MJB_EQN_Q1); }
+        else { t[0] = q1[0]; t[1] = q1[1]; t[2] = q1[2]; t[3] = q1[3]; }
+        quat1[0] = t[0]; quat1[1] = -t[1]; quat1[2] = -t[2]; quat1[3] = -t[3];
+        mulQuat(q2, quat1, quat);
+        cpos[3] = q2[1]*ts; cpos[4] = q2[2]*ts; cpos[5] = q2[3]*ts;
+        double r[3];
+        weld_rot_map(r, quat1, quat, wv);
+        vel[3] = r[0]*ts; vel[4] = r[1]*ts; vel[5] = r[2]*ts;
+        weld_rot_map(r, quat1, quat, wa);
+        acc[3] = r[0]*ts; acc[4] = r[1]*ts; acc[5] = r[2]*ts;
+      }
+      // getposdim (:1392-1425): all rows share the impedance of the norm of the residual
+      double nn = 0;
+      for (int k = 0; k < nrow; k++) nn += cpos[k]*cpos[k];
+      const double imp = impedance(sp, sqrt(nn), 0);
+      double f[6] = {0, 0, 0, 0, 0, 0};
+      for (int r = 0; r < nrow; r++) {
+        const double dA = r < 3 ? en[MJB_EQN_DA_TRAN] : en[MJB_EQN_DA_ROT];
+        const double R = fmax(MJB_MINVAL, (1 - imp)*dA/imp);
+        const double D = 1/R;
+        const double aref = -sp[MJB_SP_B]*vel[r] - sp[MJB_SP_K]*imp*cpos[r];
+        const double jar = acc[r] - aref;
+        f[r] = -D*jar;
+        emit_row(c, MJB_CNSTR_EQUALITY, i, cpos[r], 0, D, R, vel[r], aref, f[r], MJB_STATE_QUADRATIC, imp);
+      }
+      c.ne += nrow;
+      double T[3] = {0, 0, 0};
+      if (type == 1) {
+        // torque = L' f_rot, with the columns of L obtained by mapping the unit vectors
+        double fr[3] = {f[3]*ts, f[4]*ts, f[5]*ts};
+        for (int k = 0; k < 3; k++) {
+          double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0}, col[3];
+          weld_rot_map(col, quat1, quat, e);
+          T[k] = col[0]*fr[0] + col[1]*fr[1] + col[2]*fr[2];
+        }
+      }
+      add_wrench(c, b0, pos0, f, T, 1.0);
+      add_wrench(c, b1, pos1, f, T, -1.0);
+    } else {
+      // joint / tendon coupling (:640-719)
+      const double* data = eq_data + 11*i;
+      const int id0 = ei[MJB_EQI_B0], id1 = ei[MJB_EQI_B1];
+      const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+      const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+      const int* wrap_objid = MI(wrap_objid);
+      const double* wrap_prm = MD(wrap_prm);
+      double pos[2] = {0, 0}, ref[2] = {0, 0}, v[2] = {0, 0}, a[2] = {0, 0};
+      for (int j = 0; j < 1 + (id1 >= 0); j++) {
+        const int id = j == 0 ? id0 : id1;
+        if (type == 2) {
+          pos[j] = QPOS(jnt_qposadr[id]); ref[j] = MD(qpos0)[jnt_qposadr[id]];
+          v[j] = QVEL(jnt_dofadr[id]); a[j] = QACC(jnt_dofadr[id]);
+        } else {
+          pos[j] = AT(SC(ten_length), id); ref[j] = MD(tendon_length0)[id];
+          for (int w = 0; w < tendon_num[id]; w++) {
+            const int dof = jnt_dofadr[wrap_objid[tendon_adr[id] + w]];
+            v[j] += wrap_prm[tendon_adr[id] + w]*QVEL(dof);
+            a[j] += wrap_prm[tendon_adr[id] + w]*QACC(dof);
+          }
+        }
+      }
+      double cpos, deriv = 0;
+      if (id1 >= 0) {
+        const double dif = pos[1] - ref[1];
+        cpos = pos[0] - ref[0] - data[0] -
+               (data[1]*dif + data[2]*dif*dif + data[3]*dif*dif*dif + data[4]*dif*dif*dif*dif);
+        deriv = data[1] + 2*data[2]*dif + 3*data[3]*dif*dif + 4*data[4]*dif*dif*dif;
+      } else {
+        cpos = pos[0] - ref[0] - data[0];
+      }
+      const double vel = v[0] - deriv*v[1], acc = a[0] - deriv*a[1];
+      const double f = scalar_row(c, MJB_CNSTR_EQUALITY, i, sp, cpos, 0, en[MJB_EQN_DA_TRAN], vel, acc, 0);
+      c.ne++;
+      for (int j = 0; j < 1 + (id1 >= 0); j++) {
+        const int id = j == 0 ? id0 : id1;
+        const double fj = j == 0 ? f : -deriv*f;
+        if (type == 2) {
+          AT(qc, jnt_dofadr[id]) += fj;
+        } else {
+          for (int w = 0; w < tendon_num[id]; w++) {
+            AT(qc, jnt_dofadr[wrap_objid[tendon_adr[id] + w]]) += wrap_prm[tendon_adr[id] + w]*fj;
+          }
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1461,11 +1639,8 @@ MJB_HD inline void inertia(Ctx& c) {
         qM[(size_t)madr*N] = m0;
         qLD[(size_t)diag*N] = m0;
         qLDiagInv[(size_t)k*N] = 1/m0;
-        int t = 1;
-        for (int i = dof_parentid[k]; i >= 0; i = dof_parentid[i], t++) {
-          qM[(size_t)(madr + t)*N] = 0;
-          qLD[(size_t)(diag - t)*N] = 0;
-        }
+        int t = 1;    // legacy qM keeps the (zero) ancestor entries, the reduced qLD row does not
+        for (int i = dof_parentid[k]; i >= 0; i = dof_parentid[i], t++) qM[(size_t)(madr + t)*N] = 0;
         continue;
       }
       double S[6], buf[6], U[6];
@@ -1526,6 +1701,7 @@ MJB_HD inline void phase_smooth(Ctx& c) {
     for (int i = 0; i < 6*H.nbody; i++) AT(fe, i) = 0;
   }
   if (!(H.disableflags & MJB_DSBL_CONSTRAINT)) {
+    equality_rows(c);
     friction_rows(c);
     limit_rows(c);
   }

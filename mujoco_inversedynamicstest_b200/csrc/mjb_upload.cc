@@ -203,14 +203,40 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     err = "sensors are not supported (nsensor > 0): set mjDSBL_SENSOR to run without sensordata";
     return false;
   }
-  if (m->neq && constraints && !(dsbl & mjDSBL_EQUALITY)) {
-    err = "equality constraints are not supported (neq > 0): set mjDSBL_EQUALITY to run without";
-    return false;
+  const bool equalities = constraints && !(dsbl & mjDSBL_EQUALITY) && m->nemax != 0;
+  std::vector<char> tendon_in_equality(m->ntendon, 0);
+  for (int i = 0; i < m->neq && equalities; i++) {
+    const int t = m->eq_type[i];
+    if (t != mjEQ_CONNECT && t != mjEQ_WELD && t != mjEQ_JOINT && t != mjEQ_TENDON) {
+      setError(err, "equality constraint %d has an unsupported type (flex / distance)", i); return false;
+    }
+    if (t == mjEQ_TENDON) {
+      tendon_in_equality[m->eq_obj1id[i]] = 1;
+      if (m->eq_obj2id[i] >= 0) tendon_in_equality[m->eq_obj2id[i]] = 1;
+    }
+    if (t == mjEQ_JOINT) {
+      for (int j : {m->eq_obj1id[i], m->eq_obj2id[i]}) {
+        if (j >= 0 && m->jnt_type[j] != mjJNT_HINGE && m->jnt_type[j] != mjJNT_SLIDE) {
+          setError(err, "joint equality %d couples a non-scalar joint", i); return false;
+        }
+      }
+    }
   }
   for (int t = 0; t < m->ntendon; t++) {
     const int adr = m->tendon_adr[t];
     if (m->wrap_type[adr] != mjWRAP_JOINT) {
-      setError(err, "spatial tendons are not supported (tendon %d)", t); return false;
+      // a spatial tendon only produces outputs (ten_length, ten_J) unless one of these is set;
+      // those outputs are not computed here, its effect on qfrc_inverse would need mju_wrap
+      const bool dynamic = (m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints) ||
+                           (m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints) ||
+                           ((m->tendon_stiffness[t] != 0 || m->tendon_damping[t] != 0) && !(dsbl & mjDSBL_PASSIVE)) ||
+                           tendon_in_equality[t];
+      if (dynamic) {
+        setError(err, "spatial tendon %d has a limit / spring / damper / friction loss / equality: "
+                      "spatial tendons are only supported when they carry no force", t);
+        return false;
+      }
+      continue;
     }
     std::set<int> seen;
     for (int j = 0; j < m->tendon_num[t]; j++) {
@@ -419,7 +445,11 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   std::vector<int> C_rownnz(nv), C_rowadr(nv), C_colind, mapM2C;
   for (int i = 0; i < nv; i++) {
     std::vector<int> chain;
-    for (int j = i; j >= 0; j = m->dof_parentid[j]) chain.push_back(j);
+    // reduced layout: a simple dof keeps only its diagonal (engine_io.c:952-962)
+    for (int j = i; j >= 0; j = m->dof_parentid[j]) {
+      chain.push_back(j);
+      if (m->dof_simplenum[i]) break;
+    }
     C_rownnz[i] = (int)chain.size();
     C_rowadr[i] = (int)C_colind.size();
     for (int s = 0; s < (int)chain.size(); s++) {
@@ -427,8 +457,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       mapM2C.push_back(m->dof_Madr[i] + (int)chain.size() - 1 - s);
     }
   }
-  if ((int)C_colind.size() != m->nC || m->nC != m->nM) {
-    err = "unexpected sparse inertia structure (nC != nM)"; return false;
+  if ((int)C_colind.size() != m->nC) {
+    err = "unexpected sparse inertia structure (nC mismatch)"; return false;
   }
 
   std::vector<int> body_static(m->nbody), jnt_dofnum(m->njnt);
@@ -454,12 +484,62 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
                  sp_tf.data() + MJB_SP_N*t);
   }
 
+  // ---- equality constraints (mj_instantiateEquality, engine_core_constraint.c:493-763)
+  const int neq = equalities ? m->neq : 0;
+  std::vector<int> eq_int((size_t)neq * MJB_EQ_NI, 0);
+  std::vector<double> eq_num((size_t)neq * MJB_EQ_NN, 0.0), sp_eq((size_t)neq * MJB_SP_N, 0.0);
+  for (int i = 0; i < neq; i++) {
+    int* ei = eq_int.data() + (size_t)i * MJB_EQ_NI;
+    double* en = eq_num.data() + (size_t)i * MJB_EQ_NN;
+    const mjtNum* data = m->eq_data + mjNEQDATA * i;
+    const int type = m->eq_type[i], id0 = m->eq_obj1id[i], id1 = m->eq_obj2id[i];
+    ei[MJB_EQI_TYPE] = type;
+    ei[MJB_EQI_ACTIVE] = m->eq_active0[i];
+    makeSolParam(m, m->eq_solref + mjNREF*i, m->eq_solimp + mjNIMP*i, sp_eq.data() + (size_t)i * MJB_SP_N);
+    en[MJB_EQN_Q0] = 1; en[MJB_EQN_Q1] = 1;
+    if (type == mjEQ_CONNECT || type == mjEQ_WELD) {
+      const bool site = m->eq_objtype[i] == mjOBJ_SITE;
+      const int b0 = site ? m->site_bodyid[id0] : id0, b1 = site ? m->site_bodyid[id1] : id1;
+      ei[MJB_EQI_B0] = b0; ei[MJB_EQI_B1] = b1; ei[MJB_EQI_SITE] = site;
+      ei[MJB_EQI_SKIP] = (m->body_weldid[b0] == 0 && m->body_weldid[b1] == 0);
+      for (int k = 0; k < 3; k++) {
+        if (site) {
+          en[MJB_EQN_ANCHOR0 + k] = m->site_pos[3*id0 + k];
+          en[MJB_EQN_ANCHOR1 + k] = m->site_pos[3*id1 + k];
+        } else if (type == mjEQ_CONNECT) {
+          en[MJB_EQN_ANCHOR0 + k] = data[k];
+          en[MJB_EQN_ANCHOR1 + k] = data[3 + k];
+        } else {                       // weld: anchor of body j is data + 3*(1-j) (:565)
+          en[MJB_EQN_ANCHOR0 + k] = data[3 + k];
+          en[MJB_EQN_ANCHOR1 + k] = data[k];
+        }
+      }
+      if (type == mjEQ_WELD) {
+        for (int k = 0; k < 4; k++) {
+          en[MJB_EQN_Q0 + k] = site ? m->site_quat[4*id0 + k] : data[6 + k];
+          en[MJB_EQN_Q1 + k] = site ? m->site_quat[4*id1 + k] : (k == 0 ? 1.0 : 0.0);
+        }
+        en[MJB_EQN_TORQUESCALE] = data[10];
+      }
+      en[MJB_EQN_DA_TRAN] = m->body_invweight0[2*b0] + m->body_invweight0[2*b1];
+      en[MJB_EQN_DA_ROT] = m->body_invweight0[2*b0 + 1] + m->body_invweight0[2*b1 + 1];
+    } else {
+      ei[MJB_EQI_B0] = id0; ei[MJB_EQI_B1] = id1;
+      if (type == mjEQ_JOINT) {
+        en[MJB_EQN_DA_TRAN] = m->dof_invweight0[m->jnt_dofadr[id0]] +
+                              (id1 >= 0 ? m->dof_invweight0[m->jnt_dofadr[id1]] : 0.0);
+      } else {
+        en[MJB_EQN_DA_TRAN] = m->tendon_invweight0[id0] + (id1 >= 0 ? m->tendon_invweight0[id1] : 0.0);
+      }
+    }
+  }
+
   // ---- assemble
   mjbHdr H;
   std::memset(&H, 0, sizeof(H));
   H.magic = MJB_MAGIC;
   H.nq = m->nq; H.nv = nv; H.nbody = m->nbody; H.njnt = m->njnt; H.ngeom = m->ngeom;
-  H.ntendon = m->ntendon; H.nwrap = m->nwrap; H.neq = m->neq; H.nM = m->nM; H.nC = m->nC;
+  H.ntendon = m->ntendon; H.nwrap = m->nwrap; H.neq = neq; H.nM = m->nM; H.nC = m->nC;
   H.ncand = ncand;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = 0;
@@ -488,6 +568,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_C_colind, C_colind.data(), C_colind.size());
   pushInts(MJB_I_mapM2C, mapM2C.data(), mapM2C.size());
   pushInts(MJB_I_cand_int, cand_int.data(), cand_int.size());
+  pushInts(MJB_I_eq_int, eq_int.data(), eq_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
 #define X(name, rows, cols) pushNums(MJB_N_##name, m->name, (size_t)m->rows * (cols));
@@ -497,6 +578,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_sp_tendon_limit, sp_tl.data(), sp_tl.size());
   pushNums(MJB_N_sp_dof_friction, sp_df.data(), sp_df.size());
   pushNums(MJB_N_sp_tendon_friction, sp_tf.data(), sp_tf.size());
+  pushNums(MJB_N_sp_eq, sp_eq.data(), sp_eq.size());
+  pushNums(MJB_N_eq_num, eq_num.data(), eq_num.size());
   pushNums(MJB_N_cand_num, cand_num.data(), cand_num.size());
 
   // scratch layout

@@ -28,14 +28,14 @@
 
 /* model arrays by reference name (include/mujoco/mjmodel.h:593-1155); bytes widened to int */
 typedef struct {
-  int nq, nv, nbody, njnt, ngeom, ntendon, nwrap, nexclude, nM;
+  int nq, nv, nbody, njnt, ngeom, ntendon, nwrap, nexclude, nM, nC;
   int disableflags, cone;
   double timestep, impratio, gravity[3];
   const int *body_parentid, *body_rootid, *body_weldid, *body_jntnum, *body_jntadr, *body_dofnum,
       *body_dofadr, *body_geomnum, *body_geomadr, *body_sameframe, *body_contype,
       *body_conaffinity, *body_bvhadr;
   const int *jnt_type, *jnt_qposadr, *jnt_dofadr, *jnt_bodyid, *jnt_limited;
-  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr, *dof_simplenum;
   const int *geom_type, *geom_bodyid, *geom_contype, *geom_conaffinity, *geom_condim,
       *geom_priority, *geom_sameframe;
   const int *tendon_adr, *tendon_num, *tendon_limited, *wrap_objid, *exclude_signature;
@@ -44,7 +44,7 @@ typedef struct {
   const double *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_margin, *jnt_solref,
       *jnt_solimp;
   const double *dof_armature, *dof_damping, *dof_frictionloss, *dof_invweight0, *dof_solref,
-      *dof_solimp;
+      *dof_solimp, *dof_M0;
   const double *geom_size, *geom_rbound, *geom_pos, *geom_quat, *geom_friction, *geom_margin,
       *geom_gap, *geom_solmix, *geom_solref, *geom_solimp;
   const double *tendon_range, *tendon_margin, *tendon_stiffness, *tendon_damping,
@@ -830,6 +830,7 @@ static void inertia(const OrcModel* m, const Work* w, double* qM, double* qLD, d
   for (int i = 0; i < nv; i++) {
     double buf[6];
     int adr = m->dof_Madr[i];
+    if (m->dof_simplenum[i]) { qM[adr] = m->dof_M0[i]; continue; }   /* :1375-1385 */
     qM[adr] = m->dof_armature[i];
     mul_inert(buf, crb + 10*m->dof_bodyid[i], w->cdof + 6*i);
     for (int j = i; j >= 0; j = m->dof_parentid[j]) qM[adr++] += dotn(w->cdof + 6*j, buf, 6);
@@ -842,6 +843,7 @@ static void inertia(const OrcModel* m, const Work* w, double* qM, double* qLD, d
   for (int k = nv - 1; k >= 0; k--) {
     double invD = 1/A[k*nv + k];
     diaginv[k] = invD;
+    if (m->dof_simplenum[k]) continue;                                  /* :1498 */
     for (int i = m->dof_parentid[k]; i >= 0; i = m->dof_parentid[i]) {
       double tmp = A[k*nv + i]*invD;
       for (int j = i; j >= 0; j = m->dof_parentid[j]) A[i*nv + j] -= tmp*A[k*nv + j];
@@ -851,8 +853,8 @@ static void inertia(const OrcModel* m, const Work* w, double* qM, double* qLD, d
   int adr = 0;
   for (int i = 0; i < nv; i++) {
     int chain[4096], n = 0;
-    for (int j = i; j >= 0; j = m->dof_parentid[j]) chain[n++] = j;
-    for (int s = n - 1; s >= 0; s--) qLD[adr++] = A[i*nv + chain[s]];
+    for (int j = i; j >= 0; j = m->dof_parentid[j]) { chain[n++] = j; if (m->dof_simplenum[i]) break; }
+    for (int s = n - 1; s >= 0; s--) qLD[adr++] = A[i*nv + chain[s]];   /* reduced C layout, engine_io.c:952 */
   }
   free(A);
 }

@@ -10,12 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "mjinv_oracle.c")
 LIB = os.path.join(HERE, "lib", "libmjinv_oracle.so")
 
-_INT_SCALARS = ["nq", "nv", "nbody", "njnt", "ngeom", "ntendon", "nwrap", "nexclude", "nM"]
+_INT_SCALARS = ["nq", "nv", "nbody", "njnt", "ngeom", "ntendon", "nwrap", "nexclude", "nM", "nC"]
 _INT_ARRAYS = ["body_parentid", "body_rootid", "body_weldid", "body_jntnum", "body_jntadr",
                "body_dofnum", "body_dofadr", "body_geomnum", "body_geomadr", "body_sameframe",
                "body_contype", "body_conaffinity", "body_bvhadr",
                "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
-               "dof_bodyid", "dof_jntid", "dof_parentid", "dof_Madr",
+               "dof_bodyid", "dof_jntid", "dof_parentid", "dof_Madr", "dof_simplenum",
                "geom_type", "geom_bodyid", "geom_contype", "geom_conaffinity", "geom_condim",
                "geom_priority", "geom_sameframe",
                "tendon_adr", "tendon_num", "tendon_limited", "wrap_objid", "exclude_signature"]
@@ -24,7 +24,7 @@ _NUM_ARRAYS = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "bo
                "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref",
                "jnt_solimp",
                "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "dof_solref",
-               "dof_solimp",
+               "dof_solimp", "dof_M0",
                "geom_size", "geom_rbound", "geom_pos", "geom_quat", "geom_friction", "geom_margin",
                "geom_gap", "geom_solmix", "geom_solref", "geom_solimp",
                "tendon_range", "tendon_margin", "tendon_stiffness", "tendon_damping",
@@ -93,12 +93,12 @@ class Restatement:
             self.keep.append(a)
             setattr(m, n, a.ctypes.data)
         self.m = m
-        self.nv, self.nM = model.int("nv"), model.int("nM")
+        self.nv, self.nM, self.nC = model.int("nv"), model.int("nM"), model.int("nC")
 
     def inverse_batch(self, qpos, qvel, qacc, maxcon=64, maxefc=256, inertia=True):
         n = qpos.shape[0]
         out = {"qfrc_inverse": np.zeros((n, self.nv)), "qM": np.zeros((n, self.nM)),
-               "qLD": np.zeros((n, self.nM)), "qLDiagInv": np.zeros((n, self.nv)),
+               "qLD": np.zeros((n, self.nC)), "qLDiagInv": np.zeros((n, self.nv)),
                "counts": np.zeros((n, 5), np.int32), "contact_geom": np.zeros((n, maxcon, 2), np.int32),
                "efc_type": np.zeros((n, maxefc), np.int32), "efc_id": np.zeros((n, maxefc), np.int32),
                "efc_force": np.zeros((n, maxefc))}

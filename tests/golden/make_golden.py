@@ -34,12 +34,20 @@ CASES = {
     "slider_crank_nocontact": ("model/slider_crank/slider_crank.xml", {"disableflags": DSBL_CONTACT},
                                64, (0.0, 1.5), 8, 16),
     "inverse_test": ("src/inverse/test.xml", {}, 64, (0.0, 1.5), 8, 16),
+    # BASELINE config 4: tendons, equality constraints, joint limits
+    "arm26": ("model/tendon_arm/arm26.xml", {}, 128, (0.0, 1.5), 8, 16),
+    "weld": ("test/engine/testdata/weld.xml", {}, 64, (0.0, 1.5), 8, 64),
+    "connect": ("test/engine/testdata/connect.xml", {}, 64, (0.0, 1.5), 8, 32),
+    # this repository's own coverage scene (tests/golden/models/zoo.xml)
+    "zoo": ("repo:tests/golden/models/zoo.xml", {}, 256, (0.0, 0.6), 32, 128),
+    "zoo_elliptic": ("repo:tests/golden/models/zoo.xml", {"cone": 1}, 256, (0.0, 0.6), 32, 128),
 }
 
 
 def make_case(name):
     xml, opts, nstate, zr, nconmax, njmax = CASES[name]
-    m = reflib.Model.from_xml(reflib.reference_path(xml))
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
     for k, v in opts.items():
         m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
     raw = os.path.join(HERE, name + ".mjb")

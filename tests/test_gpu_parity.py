@@ -14,7 +14,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
-         "slider_crank_nocontact", "inverse_test"]
+         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -55,9 +55,10 @@ def test_golden_qfrc_inverse_within_tolerance(name):
     got = bd.qfrc_inverse()
     nviol, worst = util.qfrc_violations_scaled(got, ref["qfrc_inverse"])
     assert nviol == 0, f"{nviol} entries outside 1e-9 rel / 1e-12 abs (worst ratio {worst:.3g})"
-    # strict element-wise bound: report, and require it on the contact-free cases
+    # strict element-wise bound: required where no large constraint forces cancel (no contacts, no
+    # equality constraints); elsewhere the state-scaled bound above is the criterion
     nstrict, wstrict = util.qfrc_violations(got, ref["qfrc_inverse"])
-    if ref["ncon"].max() == 0:
+    if ref["ncon"].max() == 0 and ref["ne"].max() == 0:
         assert nstrict == 0, f"strict bound: {nstrict} violations, worst {wstrict:.3g}"
     con = bd.contacts()
     np.testing.assert_allclose(con["dist"], ref["contact_dist"], rtol=1e-9, atol=1e-12)

@@ -18,7 +18,7 @@ import emu  # noqa: E402
 pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation library not buildable")
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
-         "slider_crank_nocontact", "inverse_test"]
+         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic"]
 
 
 def _run(name):
@@ -57,7 +57,8 @@ def test_continuous_outputs(name):
     # qLD comes from the articulated-body recursion, not from eliminating M: equal to rounding
     np.testing.assert_allclose(out["qLD"], ref["qLD"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(out["qLDiagInv"], ref["qLDiagInv"], rtol=1e-9, atol=1e-12)
-    np.testing.assert_array_equal(out["qfrc_passive"], ref["qfrc_passive"])
+    # tendon spring and damper terms are summed in one accumulator here, in two in the reference
+    np.testing.assert_allclose(out["qfrc_passive"], ref["qfrc_passive"], rtol=1e-12, atol=1e-14)
     np.testing.assert_array_equal(out["efc_pos"], ref["efc_pos"])
     np.testing.assert_allclose(out["efc_D"], ref["efc_D"], rtol=1e-14)
     scale = max(1.0, np.abs(ref["efc_force"]).max())
