@@ -259,6 +259,7 @@ int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
   a.njmax = d->njmax;
   a.has_contacts = d->hdr.ncand > 0 &&
                    !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
+  a.max_pair_contacts = d->hdr.max_pair_contacts;
   a.out = d->out;
   d->last_nbatch = nbatch;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream

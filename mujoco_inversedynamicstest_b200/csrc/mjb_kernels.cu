@@ -136,21 +136,225 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// contact kernel: warp-pooled narrow phase and contact rows.
+//
+// A warp owns 32 consecutive states. Work per state is very uneven (0..60 bounding-sphere
+// survivors, 0..36 contacts for the humanoid), so instead of each lane expanding only its own
+// state, the warp pools the work items of its 32 states and deals them out 32 at a time:
+//   1. every lane expands its survivor bit mask into a private list (shared memory);
+//   2. NARROW PHASE over the pooled survivors: item j belongs to (owner lane, k-th survivor),
+//      found by a shuffle binary search over the exclusive prefix of the list lengths; the lane
+//      binds its context to the owner's state (scratch column, outputs) and runs the narrow phase;
+//      the resulting contacts are appended to a per-warp pool in shared memory at positions given
+//      by a warp prefix sum, which keeps them in (owner, candidate) order;
+//   3. CONTACT ROWS over the pooled contacts: contact index and first efc row of every record come
+//      from a segmented warp scan on top of the owner lane's running counters (read by shuffle),
+//      so the numbering equals the sequential order of the reference; the lane evaluates the rows
+//      on the owner's state and leaves the world force/torque in the record;
+//   4. each owner lane applies the wrenches of its own records in order (deterministic sums).
+// Lanes are ~fully occupied in 2 and 3, and all memory traffic stays inside the 32 scratch
+// columns of the warp (same 256-byte lines), unlike a global sort of states.
+
+struct PoolRec {
+  int owner;
+  int ci;
+  double dist;
+  double pos[3];
+  double frame[6];     // normal, tangent; after step 3: force, torque
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// inclusive scan of v restricted to runs of equal key (keys are non-decreasing across lanes)
+__device__ __forceinline__ int warp_seg_incl_scan(int v, int key, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, v, d);
+    const int k = __shfl_up_sync(0xffffffffu, key, d);
+    if (lane >= d && k == key) v += t;
+  }
+  return v;
+}
+
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 4) contact_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
-  __shared__ int lists[kListCap * kThreads];
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
-  // block-uniform trip count: lanes past the end of the chunk still take part in the warp votes
+  const mjbHdr& H = *c.H;
+
+  // dynamic shared memory after the model blob: survivor lists, then per-warp pools and counters
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int maxper = H.max_pair_contacts;
+  const int pool_cap = 32*maxper + 32;
+  size_t off = kModelInSmem ? (size_t)((a.model_bytes + 127) & ~127) : 0;
+  int* lists = reinterpret_cast<int*>(smem + off);
+  off += sizeof(int) * kListCap * kThreads;
+  int* wcnt = reinterpret_cast<int*>(smem + off) + warp * 128;   // [upd_rows | upd_cons | pcount | wstatus]
+  off += sizeof(int) * 128 * (kThreads / 32);
+  off = (off + 15) & ~(size_t)15;
+  PoolRec* pool = reinterpret_cast<PoolRec*>(smem + off) + (size_t)warp * pool_cap;
+  int* upd_rows = wcnt; int* upd_cons = wcnt + 32; int* pcount = wcnt + 64; int* wstatus = wcnt + 96;
+  int* mylist = lists + threadIdx.x;
+  upd_rows[lane] = 0; upd_cons[lane] = 0; pcount[lane] = 0; wstatus[lane] = 0;
+  __syncwarp();
+
+  const int nwords = (H.ncand + 31) >> 5;
   for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n;
        i0 += (long long)gridDim.x * kThreads) {
-    const long long i = i0 + threadIdx.x;
+    const long long wbase = i0 + warp * 32;          // first state (chunk-local) of this warp
+    const long long i = wbase + lane;
     const bool valid = i < a.chunk_n;
-    bind_state(c, a, valid ? i : 0LL);
-    phase_contact(c, valid, lists + threadIdx.x, kThreads, kListCap);
+    Ctx own = c;
+    bind_state(own, a, valid ? i : 0LL);
+    if (valid) load_counters(own);
+    int ncon = own.ncon, nefc = own.nefc;            // running counters of the state this lane owns
+    int w = 0;
+    unsigned bits = (valid && nwords > 0) ? (unsigned)own.isc[(size_t)MJB_ISC_MASK * own.NS] : 0u;
+    int pool_n = 0;
+
+    // steps 3 + 4 on the current pool
+    auto drain = [&]() {
+      for (int r0 = 0; r0 < pool_n; r0 += 32) {
+        const int r = r0 + lane;
+        const bool has = r < pool_n;
+        int owner = 64 + lane, ci = 0, rows = 0, exclude = 0;
+        Ctx co = c;
+        if (has) {
+          owner = pool[r].owner; ci = pool[r].ci;
+          bind_state(co, a, wbase + owner);
+          rows = contact_row_count(co, ci, pool[r].dist, &exclude);
+        }
+        const int rows_incl = warp_seg_incl_scan(rows, owner, lane);
+        const int cons_incl = warp_seg_incl_scan(has ? 1 : 0, owner, lane);
+        const int src = has ? owner : lane;
+        const int base_ncon = __shfl_sync(0xffffffffu, ncon, src);
+        const int base_nefc = __shfl_sync(0xffffffffu, nefc, src);
+        const int next_owner = __shfl_down_sync(0xffffffffu, owner, 1);
+        if (has) {
+          Con con;
+          con.dist = pool[r].dist;
+          for (int k = 0; k < 3; k++) con.pos[k] = pool[r].pos[k];
+          for (int k = 0; k < 6; k++) con.frame[k] = pool[r].frame[k];
+          cross3(con.frame + 6, con.frame, con.frame + 3);         // as mju_makeFrame's last step
+          double F[3], T3[3];
+          co.status = 0;
+          contact_rows(co, ci, con, base_ncon + cons_incl - 1, exclude,
+                       rows ? base_nefc + rows_incl - rows : -1, F, T3);
+          for (int k = 0; k < 3; k++) { pool[r].frame[k] = F[k]; pool[r].frame[3 + k] = T3[k]; }
+          pool[r].owner = rows ? owner : (owner | 0x100);           // bit 8: nothing to apply
+          if (co.status) atomicOr(&wstatus[owner], co.status);
+          if (lane == 31 || next_owner != owner) { upd_rows[owner] = rows_incl; upd_cons[owner] = cons_incl; }
+        }
+        __syncwarp();
+        ncon += upd_cons[lane]; nefc += upd_rows[lane];
+        upd_cons[lane] = 0; upd_rows[lane] = 0;
+        __syncwarp();
+      }
+      // step 4: every owner applies its own records, in pool order
+      const int n = pcount[lane];
+      const int start = warp_incl_scan(n, lane) - n;
+      const int nmax = __reduce_max_sync(0xffffffffu, n);
+      for (int q = 0; q < nmax; q++) {
+        if (q < n) {
+          const PoolRec& rec = pool[start + q];
+          if (!(rec.owner & 0x100)) {
+            const int* cint = c.I + H.ioff[MJB_I_cand_int] + MJB_CAND_NI*rec.ci;
+            double p[3] = {rec.pos[0], rec.pos[1], rec.pos[2]};
+            double F[3] = {rec.frame[0], rec.frame[1], rec.frame[2]};
+            double T3[3] = {rec.frame[3], rec.frame[4], rec.frame[5]};
+            apply_wrench(own, cint[MJB_CI_B1], cint[MJB_CI_B2], p, F, T3);
+          }
+        }
+      }
+      __syncwarp();
+      pcount[lane] = 0;
+      pool_n = 0;
+      __syncwarp();
+    };
+
+    while (true) {
+      // step 1: expand the mask into the private list
+      int cnt = 0;
+      if (valid) {
+        while (cnt < kListCap) {
+          while (bits == 0 && w + 1 < nwords) {
+            w++;
+            bits = (unsigned)own.isc[(size_t)(MJB_ISC_MASK + w) * own.NS];
+          }
+          if (bits == 0) break;
+          const int b = __ffs((int)bits) - 1;
+          bits &= bits - 1;
+          mylist[cnt * kThreads] = (w << 5) + b;
+          cnt++;
+        }
+      }
+      const int incl = warp_incl_scan(cnt, lane);
+      const int excl = incl - cnt;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total == 0) break;
+      __syncwarp();
+
+      // step 2: pooled narrow phase
+      for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        const bool has = j < total;
+        int o = 0;                                   // largest lane with excl <= j
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int t = o + step;
+          const int e = __shfl_sync(0xffffffffu, excl, t & 31);
+          if (t < 32 && e <= j) o = t;
+        }
+        const int eo = __shfl_sync(0xffffffffu, excl, o);
+        Con con[4];
+        int num = 0, ci = 0;
+        if (has) {
+          ci = lists[(j - eo) * kThreads + warp * 32 + o];
+          Ctx co = c;
+          bind_state(co, a, wbase + o);
+          num = narrow_pair(co, ci, con);
+        }
+        const int nincl = warp_incl_scan(num, lane);
+        const int dst = pool_n + nincl - num;
+        for (int k = 0; k < num; k++) {
+          PoolRec& rec = pool[dst + k];
+          rec.owner = o; rec.ci = ci; rec.dist = con[k].dist;
+          for (int q = 0; q < 3; q++) rec.pos[q] = con[k].pos[q];
+          for (int q = 0; q < 6; q++) rec.frame[q] = con[k].frame[q];
+        }
+        if (num) atomicAdd(&pcount[o], num);
+        pool_n += __shfl_sync(0xffffffffu, nincl, 31);
+        __syncwarp();
+        if (pool_n + 32*maxper > pool_cap) drain();
+      }
+      if (pool_n) drain();      // keep every owner's records contiguous: one pool per list batch
+    }
+
+    own.ncon = ncon; own.nefc = nefc;
+    own.status |= wstatus[lane];
+    wstatus[lane] = 0;
+    if (valid) save_counters(own);
+    __syncwarp();
   }
+}
+
+size_t contact_smem_bytes(int model_bytes, int model_in_smem, int max_pair_contacts) {
+  size_t off = model_in_smem ? (size_t)((model_bytes + 127) & ~127) : 0;
+  off += sizeof(int) * kListCap * kThreads;
+  off += sizeof(int) * 128 * (kThreads / 32);
+  off = (off + 15) & ~(size_t)15;
+  off += sizeof(PoolRec) * (size_t)(32*max_pair_contacts + 32) * (kThreads / 32);
+  return off;
 }
 
 template <bool kModelInSmem>
@@ -205,8 +409,9 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     e = in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
                 : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
-    e = in_smem ? launch_phase(contact_kernel<true>, args, smem, 8, stream)
-                : launch_phase(contact_kernel<false>, args, 0, 8, stream);
+    const size_t csmem = contact_smem_bytes(args.model_bytes, args.model_in_smem, args.max_pair_contacts);
+    e = in_smem ? launch_phase(contact_kernel<true>, args, csmem, 8, stream)
+                : launch_phase(contact_kernel<false>, args, csmem, 8, stream);
     if (e != cudaSuccess) return e;
     *launches += 2;
   }

@@ -242,8 +242,8 @@ typedef struct mjbHdr_ {
   int32_t disableflags, enableflags, cone;
   int32_t has_gravcomp;     // ngravcomp>0 && gravity enabled && |gravity|>0 (engine_passive.c:383)
   int32_t has_fixed_tendon_only;
-  int32_t nscratch;         // doubles of scratch per thread
-  int32_t pad0;
+  int32_t nscratch;         // doubles of scratch per state
+  int32_t max_pair_contacts; // most contacts one candidate pair can yield (1, 2 or 4)
   double timestep, impratio;
   double gravity[3];
   double pad1;

@@ -952,24 +952,32 @@ MJB_HD inline void apply_wrench(Ctx& c, int b1, int b2, const double* p, const d
 // mj_instantiateContact (engine_core_constraint.c:964-1131), mj_diagApprox (:1245-1306),
 // mj_makeImpedance (:1494-1608), mj_referenceConstraint, mj_invConstraint and the contact part of
 // mj_constraintUpdate (:2446-2540), then J'*force as body wrenches.
-MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
+// rows a contact will occupy and its exclude flag (mj_setContact :1387-1413 exclude-in-gap rule,
+// mj_instantiateContact :1072-1076 NV == 0 rule, :1084-1126 row counts)
+MJB_HD inline int contact_row_count(Ctx& c, int ci, double dist, int* exclude) {
+  const mjbHdr& H = *c.H;
+  const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
+  const double includemargin = MD(cand_num)[MJB_CAND_NN*ci + MJB_CN_INCLUDEMARGIN];
+  *exclude = (dist >= includemargin) ? 1 : 0;
+  if (*exclude || (H.disableflags & MJB_DSBL_CONSTRAINT) || H.nv == 0) return 0;
+  if (cint[MJB_CI_FLAGS] & 1) { *exclude = 3; return 0; }     // no dof on either side (NV == 0)
+  const int dim = cint[MJB_CI_DIM];
+  return dim == 1 ? 1 : (H.cone == 0 ? 2*(dim - 1) : dim);
+}
+
+// Contact k of the state bound to c (frame already completed by mju_makeFrame): writes the contact
+// outputs, evaluates its rows starting at row efc_address (< 0: none) and returns J'f as the world
+// force F and torque T3 at con.pos (+ on body 2, - on body 1). c.nefc is left after the last row.
+MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclude, int efc_address,
+                                double* F, double* T3) {
   const mjbHdr& H = *c.H;
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
   const int dim = cint[MJB_CI_DIM];
   const int b1 = cint[MJB_CI_B1], b2 = cint[MJB_CI_B2];
   const double includemargin = cn[MJB_CN_INCLUDEMARGIN];
+  F[0] = F[1] = F[2] = 0; T3[0] = T3[1] = T3[2] = 0;
 
-  makeFrame(con.frame);
-  int exclude = (con.dist >= includemargin) ? 1 : 0;
-  const bool constraints_on = !(H.disableflags & MJB_DSBL_CONSTRAINT);  // contacts imply !DSBL_CONTACT
-  int efc_address = -1;
-  if (!exclude && constraints_on && H.nv > 0) {
-    if (cint[MJB_CI_FLAGS] & 1) exclude = 3;     // no dof on either side (NV == 0)
-    else efc_address = c.nefc;
-  }
-
-  const int k = c.ncon++;
   if (c.out.contact_geom) {
     if (k < c.nconmax) {
       const size_t N = (size_t)c.N;
@@ -989,6 +997,7 @@ MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
     }
   }
   if (efc_address < 0) return;
+  c.nefc = efc_address;
 
   const double* sp = cn + MJB_CN_SP;
   const double* friction = cn + MJB_CN_FRICTION;
@@ -1093,13 +1102,26 @@ MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
     }
   }
 
-  // J' f : world-frame force and torque at the contact point, applied as +/- wrenches
-  double F[3], T3[3];
+  // J' f : world-frame force and torque at the contact point
   for (int a = 0; a < 3; a++) {
     F[a] = con.frame[a]*fc[0] + con.frame[3 + a]*fc[1] + con.frame[6 + a]*fc[2];
     T3[a] = con.frame[a]*fc[3] + con.frame[3 + a]*fc[4] + con.frame[6 + a]*fc[5];
   }
-  apply_wrench(c, b1, b2, con.pos, F, T3);
+}
+
+// One detected contact handled entirely by the thread that owns the state: mj_setContact
+// (engine_collision_driver.c:1387), mj_instantiateContact (engine_core_constraint.c:964-1131),
+// mj_diagApprox (:1245-1306), mj_makeImpedance (:1494-1608), mj_referenceConstraint,
+// mj_invConstraint and the contact part of mj_constraintUpdate (:2446-2540), then J'*force as
+// body wrenches. (The warp-pooled contact kernel calls the pieces separately.)
+MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
+  const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
+  int exclude;
+  const int rows = contact_row_count(c, ci, con.dist, &exclude);
+  const int k = c.ncon++;
+  double F[3], T3[3];
+  contact_rows(c, ci, con, k, exclude, rows ? c.nefc : -1, F, T3);
+  if (rows) apply_wrench(c, cint[MJB_CI_B1], cint[MJB_CI_B2], con.pos, F, T3);
 }
 
 // ---- narrow phase: primitives of engine_collision_primitive.c -----------------------------
@@ -1364,8 +1386,9 @@ MJB_HD inline int capsule_capsule(Con* con, double margin, const double* pos1, c
   return n1 + n2 + n3 + n4;
 }
 
-// narrow phase of one candidate pair followed by the rows of every contact it yields
-MJB_HD inline void collide_pair(Ctx& c, int ci) {
+// narrow phase of candidate pair ci on the state bound to c; contact frames are completed
+// (mju_makeFrame) before returning. Returns the number of contacts (<= 4).
+MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
   const double* geom_size = MD(geom_size);
@@ -1377,7 +1400,6 @@ MJB_HD inline void collide_pair(Ctx& c, int ci) {
   ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
   const double* size1 = geom_size + 3*g1;
   const double* size2 = geom_size + 3*g2;
-  Con con[4];
   int num = 0;
   switch (cint[MJB_CI_FUNC]) {
     case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
@@ -1394,6 +1416,14 @@ MJB_HD inline void collide_pair(Ctx& c, int ci) {
       num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     default: break;
   }
+  for (int k = 0; k < num; k++) makeFrame(con[k].frame);
+  return num;
+}
+
+// narrow phase of one candidate pair followed by the rows of every contact it yields
+MJB_HD inline void collide_pair(Ctx& c, int ci) {
+  Con con[4];
+  const int num = narrow_pair(c, ci, con);
   for (int k = 0; k < num; k++) process_contact(c, ci, con[k]);
 }
 

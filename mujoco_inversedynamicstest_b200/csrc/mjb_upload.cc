@@ -346,7 +346,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   const bool sparse = isSparseJacobian(m);
   std::vector<int> cand_int;
   std::vector<double> cand_num;
-  int ncand = 0;
+  int ncand = 0, max_pair_contacts = 1;
   for (const Candidate& cd : cands) {
     int g1 = cd.g1, g2 = cd.g2;
     const int ipair = cd.ipair;
@@ -400,6 +400,11 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     int ci[MJB_CAND_NI];
     double cn[MJB_CAND_NN];
     ci[MJB_CI_G1] = g1; ci[MJB_CI_G2] = g2; ci[MJB_CI_FUNC] = fn; ci[MJB_CI_DIM] = condim;
+    {
+      const int per = (fn == MJB_FN_PLANE_CYLINDER || fn == MJB_FN_PLANE_BOX) ? 4
+                      : (fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE) ? 2 : 1;
+      max_pair_contacts = std::max(max_pair_contacts, per);
+    }
     ci[MJB_CI_B1] = b1; ci[MJB_CI_B2] = b2;
     // NV == 0 only arises for the sparse Jacobian's merged chain (engine_support.c:659-690)
     const bool static1 = m->body_weldid[b1] == 0, static2 = m->body_weldid[b2] == 0;
@@ -541,6 +546,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nq = m->nq; H.nv = nv; H.nbody = m->nbody; H.njnt = m->njnt; H.ngeom = m->ngeom;
   H.ntendon = m->ntendon; H.nwrap = m->nwrap; H.neq = neq; H.nM = m->nM; H.nC = m->nC;
   H.ncand = ncand;
+  H.max_pair_contacts = max_pair_contacts;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
