@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
 //   3. CONTACT ROWS over the pooled contacts: contact index and first efc row of every record come
 //      from a segmented warp scan on top of the owner lane's running counters (read by shuffle),
 //      so the numbering equals the sequential order of the reference; the lane evaluates the rows
-//      on the owner's state and leaves the world force/torque in the record;
-//   4. each owner lane applies the wrenches of its own records in order (deterministic sums).
+//      on the owner's state and adds the resulting wrench to the two bodies of the owner's state.
+//      Records of one round that hit the same (owner, body) are found with __match_any_sync and
+//      applied one after the other in pool order, so the sums are conflict-free and bitwise
+//      deterministic (same order as a sequential sweep over the state's contacts).
 // Lanes are ~fully occupied in 2 and 3, and all memory traffic stays inside the 32 scratch
 // columns of the warp (same 256-byte lines), unlike a global sort of states.
 
@@ -161,7 +163,7 @@ struct PoolRec {
   int ci;
   double dist;
   double pos[3];
-  double frame[6];     // normal, tangent; after step 3: force, torque
+  double frame[6];     // normal, tangent (third axis is their cross product)
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -203,9 +205,9 @@ __global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
   off += sizeof(int) * 128 * (kThreads / 32);
   off = (off + 15) & ~(size_t)15;
   PoolRec* pool = reinterpret_cast<PoolRec*>(smem + off) + (size_t)warp * pool_cap;
-  int* upd_rows = wcnt; int* upd_cons = wcnt + 32; int* pcount = wcnt + 64; int* wstatus = wcnt + 96;
+  int* upd_rows = wcnt; int* upd_cons = wcnt + 32; int* wstatus = wcnt + 96;
   int* mylist = lists + threadIdx.x;
-  upd_rows[lane] = 0; upd_cons[lane] = 0; pcount[lane] = 0; wstatus[lane] = 0;
+  upd_rows[lane] = 0; upd_cons[lane] = 0; wstatus[lane] = 0;
   __syncwarp();
 
   const int nwords = (H.ncand + 31) >> 5;
@@ -222,8 +224,9 @@ __global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
     unsigned bits = (valid && nwords > 0) ? (unsigned)own.isc[(size_t)MJB_ISC_MASK * own.NS] : 0u;
     int pool_n = 0;
 
-    // steps 3 + 4 on the current pool
+    // step 3 on the current pool
     auto drain = [&]() {
+      const int* body_static = c.I + H.ioff[MJB_I_body_static];
       for (int r0 = 0; r0 < pool_n; r0 += 32) {
         const int r = r0 + lane;
         const bool has = r < pool_n;
@@ -240,46 +243,43 @@ __global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
         const int base_ncon = __shfl_sync(0xffffffffu, ncon, src);
         const int base_nefc = __shfl_sync(0xffffffffu, nefc, src);
         const int next_owner = __shfl_down_sync(0xffffffffu, owner, 1);
+        double F[3] = {0, 0, 0}, T3[3] = {0, 0, 0}, p[3] = {0, 0, 0};
+        int b1 = 0, b2 = 0;
         if (has) {
           Con con;
           con.dist = pool[r].dist;
-          for (int k = 0; k < 3; k++) con.pos[k] = pool[r].pos[k];
+          for (int k = 0; k < 3; k++) { con.pos[k] = pool[r].pos[k]; p[k] = con.pos[k]; }
           for (int k = 0; k < 6; k++) con.frame[k] = pool[r].frame[k];
           cross3(con.frame + 6, con.frame, con.frame + 3);         // as mju_makeFrame's last step
-          double F[3], T3[3];
           co.status = 0;
           contact_rows(co, ci, con, base_ncon + cons_incl - 1, exclude,
                        rows ? base_nefc + rows_incl - rows : -1, F, T3);
-          for (int k = 0; k < 3; k++) { pool[r].frame[k] = F[k]; pool[r].frame[3 + k] = T3[k]; }
-          pool[r].owner = rows ? owner : (owner | 0x100);           // bit 8: nothing to apply
+          const int* cint = c.I + H.ioff[MJB_I_cand_int] + MJB_CAND_NI*ci;
+          b1 = cint[MJB_CI_B1]; b2 = cint[MJB_CI_B2];
           if (co.status) atomicOr(&wstatus[owner], co.status);
           if (lane == 31 || next_owner != owner) { upd_rows[owner] = rows_incl; upd_cons[owner] = cons_incl; }
+        }
+        // J'f: + wrench on body 2, - wrench on body 1 of the owner's state (static bodies never
+        // reach a dof and are skipped); same-target records go in pool order
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+          const int body = side == 0 ? b2 : b1;
+          const bool act = has && rows > 0 && !body_static[body];
+          const unsigned key = act ? (((unsigned)owner << 20) | (unsigned)body) : (0x80000000u | lane);
+          const unsigned grp = __match_any_sync(0xffffffffu, key);
+          const int rank = __popc(grp & ((1u << lane) - 1u));
+          const int maxrank = __reduce_max_sync(0xffffffffu, rank);
+          for (int t = 0; t <= maxrank; t++) {
+            if (act && rank == t) add_wrench(co, body, p, F, T3, side == 0);
+            __syncwarp();
+          }
         }
         __syncwarp();
         ncon += upd_cons[lane]; nefc += upd_rows[lane];
         upd_cons[lane] = 0; upd_rows[lane] = 0;
         __syncwarp();
       }
-      // step 4: every owner applies its own records, in pool order
-      const int n = pcount[lane];
-      const int start = warp_incl_scan(n, lane) - n;
-      const int nmax = __reduce_max_sync(0xffffffffu, n);
-      for (int q = 0; q < nmax; q++) {
-        if (q < n) {
-          const PoolRec& rec = pool[start + q];
-          if (!(rec.owner & 0x100)) {
-            const int* cint = c.I + H.ioff[MJB_I_cand_int] + MJB_CAND_NI*rec.ci;
-            double p[3] = {rec.pos[0], rec.pos[1], rec.pos[2]};
-            double F[3] = {rec.frame[0], rec.frame[1], rec.frame[2]};
-            double T3[3] = {rec.frame[3], rec.frame[4], rec.frame[5]};
-            apply_wrench(own, cint[MJB_CI_B1], cint[MJB_CI_B2], p, F, T3);
-          }
-        }
-      }
-      __syncwarp();
-      pcount[lane] = 0;
       pool_n = 0;
-      __syncwarp();
     };
 
     while (true) {
@@ -332,12 +332,11 @@ __global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
           for (int q = 0; q < 3; q++) rec.pos[q] = con[k].pos[q];
           for (int q = 0; q < 6; q++) rec.frame[q] = con[k].frame[q];
         }
-        if (num) atomicAdd(&pcount[o], num);
         pool_n += __shfl_sync(0xffffffffu, nincl, 31);
         __syncwarp();
         if (pool_n + 32*maxper > pool_cap) drain();
       }
-      if (pool_n) drain();      // keep every owner's records contiguous: one pool per list batch
+      if (pool_n) drain();
     }
 
     own.ncon = ncon; own.nefc = nefc;

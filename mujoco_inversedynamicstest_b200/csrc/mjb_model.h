@@ -223,7 +223,8 @@ enum {
   MJB_SC_cacc_lin,     // nbody*6   sum cdof*qacc over the dof chain (J*qacc carrier)
   MJB_SC_cacc,         // nbody*6   rne accelerations
   MJB_SC_cfrc,         // nbody*6   rne body forces
-  MJB_SC_cfrc_ext,     // nbody*6   constraint wrenches on bodies
+  MJB_SC_cfrc_ext,     // nbody*6   constraint wrenches on bodies, '+' side (body 2 of a pair)
+  MJB_SC_cfrc_ext1,    // nbody*6   '-' side (body 1 of a pair); kept apart so that each sum runs in contact order
   MJB_SC_qfrc_c,       // nv        joint-space constraint force (limits, friction loss, tendons)
   MJB_SC_qfrc_passive, // nv
   MJB_SC_ten_length,   // ntendon

@@ -630,19 +630,21 @@ MJB_HD inline void point_motion(Ctx& c, const double* carrier, int b, const doub
   for (int k = 0; k < 3; k++) { lin[k] = v[3 + k] + cr[k]; ang[k] = v[k]; }
 }
 
-// cfrc_ext[b] += sign * [ (p - O_b) x F + T ; F ]
+// wrench [ (p - O_b) x F + T ; F ] on body b: added to cfrc_ext (positive side) or to cfrc_ext1
+// (negative side; subtracted in the backward pass). Two accumulators keep every running sum in
+// contact order whatever the interleaving of the two sides (see the pooled contact kernel).
 MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, const double* T,
-                              double sign) {
+                              bool positive) {
   const int* rootid = MI(body_rootid);
   double* com = SC(subtree_com);
-  double* fe = SC(cfrc_ext);
+  double* fe = positive ? SC(cfrc_ext) : SC(cfrc_ext1);
   double o[3], r[3], cr[3];
   ldn(o, com, 3*rootid[b], 3);
   r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
   cross3(cr, r, F);
   for (int k = 0; k < 3; k++) {
-    AT(fe, 6*b + k) += sign*(cr[k] + T[k]);
-    AT(fe, 6*b + 3 + k) += sign*F[k];
+    AT(fe, 6*b + k) += cr[k] + T[k];
+    AT(fe, 6*b + 3 + k) += F[k];
   }
 }
 
@@ -734,8 +736,8 @@ MJB_HD inline void equality_rows(Ctx& c) {
           T[k] = col[0]*fr[0] + col[1]*fr[1] + col[2]*fr[2];
         }
       }
-      add_wrench(c, b0, pos0, f, T, 1.0);
-      add_wrench(c, b1, pos1, f, T, -1.0);
+      add_wrench(c, b0, pos0, f, T, true);
+      add_wrench(c, b1, pos1, f, T, false);
     } else {
       // joint / tendon coupling (:640-719)
       const double* data = eq_data + 11*i;
@@ -930,28 +932,13 @@ MJB_HD inline void rel_motion(Ctx& c, const double* carrier, int b1, int b2, con
   }
 }
 
-// add the wrench (torque T about point p, force F at p) to body b2 and its opposite to body b1,
-// expressed in each body's com-based frame:  cfrc_ext[b] += [ (p - O_b) x F + T ; F ]
+// add the wrench (torque T about point p, force F at p) to body b2 and its opposite to body b1
 MJB_HD inline void apply_wrench(Ctx& c, int b1, int b2, const double* p, const double* F,
                                 const double* T) {
-  const int* rootid = MI(body_rootid);
-  double* com = SC(subtree_com);
-  double* fe = SC(cfrc_ext);
-  double o[3], r[3], cr[3];
-  ldn(o, com, 3*rootid[b2], 3);
-  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
-  cross3(cr, r, F);
-  for (int k = 0; k < 3; k++) { AT(fe, 6*b2 + k) += cr[k] + T[k]; AT(fe, 6*b2 + 3 + k) += F[k]; }
-  ldn(o, com, 3*rootid[b1], 3);
-  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
-  cross3(cr, r, F);
-  for (int k = 0; k < 3; k++) { AT(fe, 6*b1 + k) -= cr[k] + T[k]; AT(fe, 6*b1 + 3 + k) -= F[k]; }
+  add_wrench(c, b2, p, F, T, true);
+  add_wrench(c, b1, p, F, T, false);
 }
 
-// One detected contact of candidate pair `ci`: mj_setContact (engine_collision_driver.c:1387),
-// mj_instantiateContact (engine_core_constraint.c:964-1131), mj_diagApprox (:1245-1306),
-// mj_makeImpedance (:1494-1608), mj_referenceConstraint, mj_invConstraint and the contact part of
-// mj_constraintUpdate (:2446-2540), then J'*force as body wrenches.
 // rows a contact will occupy and its exclude flag (mj_setContact :1387-1413 exclude-in-gap rule,
 // mj_instantiateContact :1072-1076 NV == 0 rule, :1084-1126 row counts)
 MJB_HD inline int contact_row_count(Ctx& c, int ci, double dist, int* exclude) {
@@ -1566,13 +1553,16 @@ MJB_HD inline void rne_and_output(Ctx& c) {
     stn(cfrc, 6*b, f, 6);
   }
 
-  // backward accumulation of inertial forces and of constraint wrenches
+  // backward accumulation of inertial forces and of constraint wrenches ('+' minus '-' side)
+  double* fext1 = SC(cfrc_ext1);
   for (int b = nbody - 1; b > 0; b--) {
     const int p = body_parentid[b];
+    double w[6];
+    for (int k = 0; k < 6; k++) { w[k] = AT(fext, 6*b + k) - AT(fext1, 6*b + k); AT(fext, 6*b + k) = w[k]; }
     if (p) {
       for (int k = 0; k < 6; k++) {
         AT(cfrc, 6*p + k) += AT(cfrc, 6*b + k);
-        AT(fext, 6*p + k) += AT(fext, 6*b + k);
+        AT(fext1, 6*p + k) -= w[k];      // parent's net = own '+' - own '-' + children's nets
       }
     }
   }
@@ -1726,9 +1716,9 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   com_vel(c);
   passive(c);
   {
-    double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext);
+    double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);
     for (int i = 0; i < H.nv; i++) AT(qc, i) = 0;
-    for (int i = 0; i < 6*H.nbody; i++) AT(fe, i) = 0;
+    for (int i = 0; i < 6*H.nbody; i++) { AT(fe, i) = 0; AT(fe1, i) = 0; }
   }
   if (!(H.disableflags & MJB_DSBL_CONSTRAINT)) {
     equality_rows(c);

@@ -599,7 +599,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_subtree_com] = 3*nb; sizes[MJB_SC_mass_subtree] = nb;
     sizes[MJB_SC_cinert] = 10*nb; sizes[MJB_SC_cdof] = 6*nv; sizes[MJB_SC_cvel] = 6*nb;
     sizes[MJB_SC_cdof_dot] = 6*nv; sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
-    sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
+    sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_cfrc_ext1] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
     sizes[MJB_SC_qfrc_passive] = nv;
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
     sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
@@ -625,7 +625,7 @@ const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
     "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
     "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cdof_dot", "cacc_lin", "cacc", "cfrc",
-    "cfrc_ext", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
+    "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
 
