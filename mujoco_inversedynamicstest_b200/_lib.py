@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmjb.so")
+LIB_PATH = os.environ.get("MJB_LIB") or os.path.join(_PKG, "lib", "libmjb.so")
 
 _lib = None
 

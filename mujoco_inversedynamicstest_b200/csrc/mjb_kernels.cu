@@ -15,6 +15,20 @@
 
 #include <cstdio>
 
+// resident CTAs per SM each phase kernel is compiled for (register budget = 65536 / (128 * CTAS))
+#ifndef MJB_CTAS_SMOOTH
+#define MJB_CTAS_SMOOTH 4
+#endif
+#ifndef MJB_CTAS_INERTIA
+#define MJB_CTAS_INERTIA 4
+#endif
+#ifndef MJB_CTAS_BACKWARD
+#define MJB_CTAS_BACKWARD 4
+#endif
+#ifndef MJB_CTAS_CONTACT
+#define MJB_CTAS_CONTACT 3
+#endif
+
 namespace mjb {
 
 // ------------------------------------------------------------------------------------------
@@ -97,7 +111,7 @@ __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long lon
 }
 
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 4) smooth_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, MJB_CTAS_SMOOTH) smooth_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 4) smooth_kernel(LaunchArgs a) {
 }
 
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 4) inertia_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, MJB_CTAS_INERTIA) inertia_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;
@@ -187,7 +201,7 @@ __device__ __forceinline__ int warp_seg_incl_scan(int v, int key, int lane) {
 }
 
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 3) contact_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;
@@ -357,7 +371,7 @@ size_t contact_smem_bytes(int model_bytes, int model_in_smem, int max_pair_conta
 }
 
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 4) backward_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, MJB_CTAS_BACKWARD) backward_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;

@@ -61,7 +61,8 @@
   X(cand_int)  /* ncand*MJB_CAND_NI : candidate geom pairs, see MJB_CI_*        */ \
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
-  X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */
+  X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
+  X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent */
 
 // ---- double arrays copied 1:1 from mjModel (name, rows, cols)
 #define MJB_NUM_ARRAYS(X)         \
@@ -219,7 +220,6 @@ enum {
   MJB_SC_cinert,       // nbody*10
   MJB_SC_cdof,         // nv*6
   MJB_SC_cvel,         // nbody*6
-  MJB_SC_cdof_dot,     // nv*6
   MJB_SC_cacc_lin,     // nbody*6   sum cdof*qacc over the dof chain (J*qacc carrier)
   MJB_SC_cacc,         // nbody*6   rne accelerations
   MJB_SC_cfrc,         // nbody*6   rne body forces

@@ -402,13 +402,18 @@ MJB_HD inline void tendon_fixed(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_comVel (engine_core_smooth.c:1833-1896); also accumulates cacc_lin = sum cdof*qacc along
-// the dof chain, the carrier of J*qacc for point constraints.
-MJB_HD inline void com_vel(Ctx& c) {
+// mj_comVel (engine_core_smooth.c:1833-1896) fused with the forward half of mj_rne(flg_acc=1)
+// (:1969-2005): one root-to-leaves sweep yields, per body,
+//   cvel      spatial velocity                                     (contacts, cfrc)
+//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
+//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
+//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                  (backward pass)
+// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
+MJB_HD inline void com_vel_rne_forward(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
-  double* cvel = SC(cvel); double* cdof = SC(cdof); double* cdof_dot = SC(cdof_dot);
-  double* cal = SC(cacc_lin);
+  double* cvel = SC(cvel); double* cdof = SC(cdof); double* cinert = SC(cinert);
+  double* cal = SC(cacc_lin); double* cacc = SC(cacc); double* cfrc = SC(cfrc);
   const int* body_parentid = MI(body_parentid);
   const int* body_dofadr = MI(body_dofadr);
   const int* body_dofnum = MI(body_dofnum);
@@ -416,24 +421,31 @@ MJB_HD inline void com_vel(Ctx& c) {
   const int* jnt_type = MI(jnt_type);
 
   for (int k = 0; k < 6; k++) { AT(cvel, k) = 0; AT(cal, k) = 0; }
+  AT(cacc, 0) = 0; AT(cacc, 1) = 0; AT(cacc, 2) = 0;
+  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+    AT(cacc, 3) = -H.gravity[0]; AT(cacc, 4) = -H.gravity[1]; AT(cacc, 5) = -H.gravity[2];
+  } else {
+    AT(cacc, 3) = 0; AT(cacc, 4) = 0; AT(cacc, 5) = 0;
+  }
 
   for (int b = 1; b < nbody; b++) {
     const int bda = body_dofadr[b];
     const int dofnum = body_dofnum[b];
-    double v[6], a[6];
-    ldn(v, cvel, 6*body_parentid[b], 6);
-    ldn(a, cal, 6*body_parentid[b], 6);
+    const int pid = body_parentid[b];
+    double v[6];
+    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
+    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
+    ldn(v, cvel, 6*pid, 6);
 
     for (int j = 0; j < dofnum; j++) {
       const int jt = jnt_type[dof_jntid[bda + j]];
       if (jt == MJB_JNT_FREE) {
-        // translational dofs: cdofdot = 0 ; cvel += cdof(0..2)' * qvel(0..2)
-        for (int k = 0; k < 18; k++) AT(cdof_dot, 6*bda + k) = 0;
+        // translational dofs: cdof_dot = 0 ; cvel += cdof(0..2)' * qvel(0..2)
         for (int r = 0; r < 3; r++) {
           const double qv = QVEL(bda + r), qa = QACC(bda + r);
           double cd[6];
           ldn(cd, cdof, 6*(bda + r), 6);
-          for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; a[k] += cd[k]*qa; }
+          for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
         }
         j += 3;
       }
@@ -444,24 +456,38 @@ MJB_HD inline void com_vel(Ctx& c) {
           double dd[6];
           ldn(cd[r], cdof, 6*(bda + j + r), 6);
           crossMotion(dd, v, cd[r]);
-          stn(cdof_dot, 6*(bda + j + r), dd, 6);
+          const double qv = QVEL(bda + j + r);
+          for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
         }
         for (int r = 0; r < 3; r++) {
           const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
-          for (int k = 0; k < 6; k++) { v[k] += cd[r][k]*qv; a[k] += cd[r][k]*qa; }
+          for (int k = 0; k < 6; k++) { v[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
         }
         j += 2;
       } else {
         double cd[6], dd[6];
         ldn(cd, cdof, 6*(bda + j), 6);
         crossMotion(dd, v, cd);
-        stn(cdof_dot, 6*(bda + j), dd, 6);
         const double qv = QVEL(bda + j), qa = QACC(bda + j);
-        for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; a[k] += cd[k]*qa; }
+        for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; v[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
       }
     }
     stn(cvel, 6*b, v, 6);
-    stn(cal, 6*b, a, 6);
+
+    double acc[6], al[6];
+    ldn(acc, cacc, 6*pid, 6);
+    ldn(al, cal, 6*pid, 6);
+    for (int k = 0; k < 6; k++) { acc[k] += t1[k]; acc[k] += t2[k]; al[k] += t2[k]; }
+    stn(cacc, 6*b, acc, 6);
+    stn(cal, 6*b, al, 6);
+
+    double ci[10], f[6], u1[6], u2[6];
+    ldn(ci, cinert, 10*b, 10);
+    mulInertVec(f, ci, acc);
+    mulInertVec(u1, ci, v);
+    crossForce(u2, v, u1);
+    for (int k = 0; k < 6; k++) f[k] += u2[k];
+    stn(cfrc, 6*b, f, 6);
   }
 }
 
@@ -1502,56 +1528,15 @@ MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, i
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_rne(flg_acc=1) (engine_core_smooth.c:1969-2023) fused with the last loop of mj_inverseSkip
-// (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree separately and
-// projected with the same cdof, which is J'*efc_force for the point constraints.
+// backward half of mj_rne(flg_acc=1) (engine_core_smooth.c:2008-2020) fused with the last loop of
+// mj_inverseSkip (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree
+// separately and projected with the same cdof, which is J'*efc_force for the point constraints.
 MJB_HD inline void rne_and_output(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody, nv = H.nv;
-  double* cacc = SC(cacc); double* cfrc = SC(cfrc); double* fext = SC(cfrc_ext);
-  double* cdof = SC(cdof); double* cdof_dot = SC(cdof_dot); double* cvel = SC(cvel);
-  double* cinert = SC(cinert);
+  double* cfrc = SC(cfrc); double* fext = SC(cfrc_ext);
+  double* cdof = SC(cdof);
   const int* body_parentid = MI(body_parentid);
-  const int* body_dofadr = MI(body_dofadr);
-  const int* body_dofnum = MI(body_dofnum);
-
-  AT(cacc, 0) = 0; AT(cacc, 1) = 0; AT(cacc, 2) = 0;
-  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
-    AT(cacc, 3) = -H.gravity[0]; AT(cacc, 4) = -H.gravity[1]; AT(cacc, 5) = -H.gravity[2];
-  } else {
-    AT(cacc, 3) = 0; AT(cacc, 4) = 0; AT(cacc, 5) = 0;
-  }
-
-  for (int b = 1; b < nbody; b++) {
-    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
-    double acc[6], tmp[6] = {0, 0, 0, 0, 0, 0};
-    // tmp = cdof_dot' * qvel  (mju_mulDofVec: n==1 scales, n>1 accumulates row by row)
-    for (int j = 0; j < dofnum; j++) {
-      const double qv = QVEL(bda + j);
-      double dd[6];
-      ldn(dd, cdof_dot, 6*(bda + j), 6);
-      for (int k = 0; k < 6; k++) tmp[k] += dd[k]*qv;
-    }
-    ldn(acc, cacc, 6*body_parentid[b], 6);
-    for (int k = 0; k < 6; k++) acc[k] += tmp[k];
-    for (int k = 0; k < 6; k++) tmp[k] = 0;
-    for (int j = 0; j < dofnum; j++) {
-      const double qa = QACC(bda + j);
-      double cd[6];
-      ldn(cd, cdof, 6*(bda + j), 6);
-      for (int k = 0; k < 6; k++) tmp[k] += cd[k]*qa;
-    }
-    for (int k = 0; k < 6; k++) acc[k] += tmp[k];
-    stn(cacc, 6*b, acc, 6);
-
-    double ci[10], v[6], f[6], t1[6], t2[6];
-    ldn(ci, cinert, 10*b, 10); ldn(v, cvel, 6*b, 6);
-    mulInertVec(f, ci, acc);
-    mulInertVec(t1, ci, v);
-    crossForce(t2, v, t1);
-    for (int k = 0; k < 6; k++) f[k] += t2[k];
-    stn(cfrc, 6*b, f, 6);
-  }
 
   // backward accumulation of inertial forces and of constraint wrenches ('+' minus '-' side)
   double* fext1 = SC(cfrc_ext1);
@@ -1636,19 +1621,20 @@ MJB_HD inline void inertia(Ctx& c) {
   const size_t N = (size_t)c.N;
   double* qM = c.out.qM + c.s; double* qLD = c.out.qLD + c.s; double* qLDiagInv = c.out.qLDiagInv + c.s;
 
-  // crb = cinert, IA = cinert as 6x6 (world body stays zero and is never read)
-  for (int b = 1; b < nbody; b++) {
-    double ci[10], A[21];
-    ldn(ci, cinert, 10*b, 10);
-    inert_to_sym6(A, ci);
-    stn(crb, 10*b, ci, 10);
-    stn(ia, 21*b, A, 21);
-  }
-
+  // A parent's accumulators are INITIALISED (own rigid inertia + child) by its highest-index
+  // child, the first one visited, and added to by the others: the same summation order as the
+  // reference's "crb = cinert; add children backwards", without a clearing pass over the scratch.
+  const int* tree_flags = MI(body_tree_flags);   // bit0: has children, bit1: first visited child
   for (int b = nbody - 1; b > 0; b--) {
     double cr[10], A[21];
-    ldn(cr, crb, 10*b, 10);
-    ldn(A, ia, 21*b, 21);
+    const int flags = tree_flags[b];
+    if (flags & 1) {
+      ldn(cr, crb, 10*b, 10);
+      ldn(A, ia, 21*b, 21);
+    } else {
+      ldn(cr, cinert, 10*b, 10);
+      inert_to_sym6(A, cr);
+    }
     const int adr0 = body_dofadr[b], num = body_dofnum[b];
     for (int k = adr0 + num - 1; k >= adr0; k--) {
       const int madr = dof_Madr[k];
@@ -1689,8 +1675,18 @@ MJB_HD inline void inertia(Ctx& c) {
     }
     const int p = body_parentid[b];
     if (p > 0) {
-      for (int j = 0; j < 10; j++) AT(crb, 10*p + j) += cr[j];
-      for (int j = 0; j < 21; j++) AT(ia, 21*p + j) += A[j];
+      if (flags & 2) {
+        double pc[10], pA[21];
+        ldn(pc, cinert, 10*p, 10);
+        inert_to_sym6(pA, pc);
+        for (int j = 0; j < 10; j++) pc[j] += cr[j];
+        for (int j = 0; j < 21; j++) pA[j] += A[j];
+        stn(crb, 10*p, pc, 10);
+        stn(ia, 21*p, pA, 21);
+      } else {
+        for (int j = 0; j < 10; j++) AT(crb, 10*p + j) += cr[j];
+        for (int j = 0; j < 21; j++) AT(ia, 21*p + j) += A[j];
+      }
     }
   }
 }
@@ -1713,7 +1709,7 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   kinematics(c);
   com_pos(c);
   tendon_fixed(c);
-  com_vel(c);
+  com_vel_rne_forward(c);
   passive(c);
   {
     double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);

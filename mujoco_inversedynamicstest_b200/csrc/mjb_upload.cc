@@ -577,6 +577,15 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_eq_int, eq_int.data(), eq_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
+  {
+    std::vector<int> flags(m->nbody, 0), seen(m->nbody, 0);
+    for (int b = m->nbody - 1; b > 0; b--) {
+      const int p = m->body_parentid[b];
+      flags[p] |= 1;
+      if (!seen[p]) { flags[b] |= 2; seen[p] = 1; }
+    }
+    pushInts(MJB_I_body_tree_flags, flags.data(), flags.size());
+  }
 #define X(name, rows, cols) pushNums(MJB_N_##name, m->name, (size_t)m->rows * (cols));
   MJB_NUM_ARRAYS(X)
 #undef X
@@ -598,7 +607,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_geom_xpos] = 3*ng; sizes[MJB_SC_geom_xmat] = 9*ng;
     sizes[MJB_SC_subtree_com] = 3*nb; sizes[MJB_SC_mass_subtree] = nb;
     sizes[MJB_SC_cinert] = 10*nb; sizes[MJB_SC_cdof] = 6*nv; sizes[MJB_SC_cvel] = 6*nb;
-    sizes[MJB_SC_cdof_dot] = 6*nv; sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
+    sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
     sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_cfrc_ext1] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
     sizes[MJB_SC_qfrc_passive] = nv;
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
@@ -624,7 +633,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
     "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
-    "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cdof_dot", "cacc_lin", "cacc", "cfrc",
+    "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
     "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
