@@ -8,9 +8,9 @@ One "step" = one mjb_inverse pass over a resident batch of 2^20 synthetic humano
 
   value   device-resident throughput: states of all ranks / max-over-ranks CUDA-event time of the
           K timed steps (inputs already in HBM as structure-of-arrays)
-  e2e     the same metric through the public C-ABI with HOST buffers: mjb_setState (H2D from pinned
-          memory + transpose) -> mjb_inverse -> mjb_get(qfrc_inverse) (transpose + D2H), all inside
-          the timed region
+  e2e     the same metric through the public C-ABI with HOST buffers: mjb_inverseHost (H2D from
+          pinned memory + transposes, kernels, transpose + D2H of qfrc_inverse, pipelined in pieces
+          over three streams), all inside the timed region
   roofline      FP64 roofline of the fused kernel (the path is fp64-compute bound):
                 executed-flop model x states / CUDA-event time vs the DFMA peak measured in-run
   roofline_hbm  algorithmic bytes (872 B/state) / time vs MEASURED_PEAKS.json HBM copy bandwidth
@@ -275,16 +275,12 @@ def main():
     # ---------------- end-to-end through the C-ABI with host buffers ----------------
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        bd.set_state_ptr(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr())
-        bd.inverse(sync=False)
-        bd.get_ptr(mjb.F_QFRC_INVERSE, h_out.data_ptr())
+        bd.inverse_host(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr(), h_out.data_ptr())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(e2e_steps):
-        bd.set_state_ptr(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr())
-        bd.inverse(sync=False)
-        bd.get_ptr(mjb.F_QFRC_INVERSE, h_out.data_ptr())
+        bd.inverse_host(n, h_qpos.data_ptr(), h_qvel.data_ptr(), h_qacc.data_ptr(), h_out.data_ptr())
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)

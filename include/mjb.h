@@ -104,6 +104,13 @@ MJB_API int mjb_inverse(const mjModel* m, mjbData* d, int nbatch);
 /* same, without reading back the status count (fully asynchronous) */
 MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 
+/* host-to-host form of the loop: qpos/qvel/qacc in (nbatch x nq|nv, HOST, pinned for best speed),
+ * qfrc_inverse out (nbatch x nv, HOST). The batch is pipelined in pieces over three CUDA streams
+ * (H2D copy | kernels | D2H copy) so transfers overlap compute. Asynchronous: the results are valid
+ * after mjb_synchronize(d). Returns 0, or a negative value on a CUDA error. */
+MJB_API int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos,
+                            const mjtNum* qvel, const mjtNum* qacc, mjtNum* qfrc_inverse);
+
 /* copy a field of the last mjb_inverse to a HOST array laid out nbatch x rows (row-major) */
 MJB_API int mjb_get(mjbData* d, int field, void* host_out);
 MJB_API int mjb_getQfrcInverse(mjbData* d, mjtNum* qfrc_inverse);

@@ -172,6 +172,25 @@ class BatchData:
     def kernel_launches(self):
         return int(lib().mjb_kernelLaunches(self._d))
 
+    def inverse_host(self, n, qpos_ptr, qvel_ptr, qacc_ptr, out_ptr):
+        """Pipelined host-to-host pass (mjb_inverseHost): pointers to HOST arrays n x nq|nv|nv and
+        the n x nv output; asynchronous, call synchronize() before reading the output."""
+        self._check(lib().mjb_inverseHost(self.model.ptr, self._d, int(n), ctypes.c_void_p(qpos_ptr),
+                                          ctypes.c_void_p(qvel_ptr), ctypes.c_void_p(qacc_ptr),
+                                          ctypes.c_void_p(out_ptr)), "mjb_inverseHost")
+        self.nbatch = int(n)
+
+    def inverse_host_arrays(self, qpos, qvel, qacc):
+        """numpy convenience around inverse_host (synchronous)."""
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        qacc = np.ascontiguousarray(qacc, dtype=np.float64)
+        out = np.empty((qpos.shape[0], self.nv))
+        self.inverse_host(qpos.shape[0], qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data,
+                          out.ctypes.data)
+        self.synchronize()
+        return out
+
     def synchronize(self):
         self._check(lib().mjb_synchronize(self._d), "mjb_synchronize")
 

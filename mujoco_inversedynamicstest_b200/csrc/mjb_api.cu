@@ -37,6 +37,13 @@ struct mjbData_ {
   void* d_stage = nullptr;
   size_t stage_bytes = 0;
   int* d_counter = nullptr;
+  // host pipeline of mjb_inverseHost: copy-in / copy-out streams, double-buffered staging, events
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  void* pipe_in[2] = {nullptr, nullptr};
+  void* pipe_out[2] = {nullptr, nullptr};
+  size_t pipe_piece = 0;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_tr[2] = {nullptr, nullptr},
+              ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   mjb::Outputs out;            // device SoA outputs
   void* field_ptr[mjbF_COUNT];
   int field_rows[mjbF_COUNT];
@@ -200,6 +207,15 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(d->pipe_in[b]); cudaFree(d->pipe_out[b]);
+    if (d->ev_in[b]) cudaEventDestroy(d->ev_in[b]);
+    if (d->ev_tr[b]) cudaEventDestroy(d->ev_tr[b]);
+    if (d->ev_comp[b]) cudaEventDestroy(d->ev_comp[b]);
+    if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
+  }
+  if (d->s_in) cudaStreamDestroy(d->s_in);
+  if (d->s_out) cudaStreamDestroy(d->s_out);
   mjb::Outputs& o = d->out;
   cudaFree(o.qfrc_inverse); cudaFree(o.qfrc_constraint); cudaFree(o.qfrc_passive);
   cudaFree(o.counts); cudaFree(o.status); cudaFree(o.contact_geom); cudaFree(o.contact_info);
@@ -242,10 +258,12 @@ int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel, const
   return 0;
 }
 
-int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
-  (void)m;   // the model was flattened at mjb_makeData; kept for signature parity with mj_inverse
-  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverse: nbatch out of range"; return -1; }
-  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+}  // extern "C"
+
+namespace {
+
+// launch the phase kernels for states [first, first + count) on the compute stream
+bool launchRange(mjbData* d, long long first, long long count) {
   mjb::LaunchArgs a;
   a.model = d->d_model;
   a.model_bytes = d->model_bytes;
@@ -261,16 +279,98 @@ int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
                    !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
   a.max_pair_contacts = d->hdr.max_pair_contacts;
   a.out = d->out;
-  d->last_nbatch = nbatch;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
-  for (long long start = 0; start < nbatch; start += d->chunk_stride) {
+  for (long long start = first; start < first + count; start += d->chunk_stride) {
     a.chunk_start = start;
-    a.chunk_n = (int)((nbatch - start) < d->chunk_stride ? (nbatch - start) : d->chunk_stride);
+    a.chunk_n = (int)((first + count - start) < d->chunk_stride ? (first + count - start) : d->chunk_stride);
     int launches = 0;
-    if (!check(d, mjb::launch_inverse(a, d->stream, &launches), "launch mj_inverse kernels")) return -1;
+    if (!check(d, mjb::launch_inverse(a, d->stream, &launches), "launch mj_inverse kernels")) return false;
     d->kernel_launches += launches;
   }
-  return 0;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
+  (void)m;   // the model was flattened at mjb_makeData; kept for signature parity with mj_inverse
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverse: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  d->last_nbatch = nbatch;
+  return launchRange(d, 0, nbatch) ? 0 : -1;
+}
+
+// Host-to-host mj_inverse over the batch: for i: copy state i -> mj_inverse -> copy qfrc_inverse,
+// as one call. The batch is cut into pieces that flow through a three-stage pipeline -- H2D copy,
+// kernels, D2H copy -- on three streams with double-buffered staging, so PCIe transfers in both
+// directions overlap the compute of neighbouring pieces. Host buffers should be pinned.
+int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
+                    const mjtNum* qacc, mjtNum* qfrc_inverse) {
+  (void)m;
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseHost: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const mjbHdr& H = d->hdr;
+  d->last_nbatch = nbatch;
+  d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
+  if (nbatch == 0) return 0;
+  const size_t piece = 131072;
+  const size_t in_doubles = piece * (size_t)(H.nq + 2*H.nv), out_doubles = piece * (size_t)H.nv;
+  bool ok = true;
+  if (!d->s_in) {
+    ok = ok && check(d, cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && check(d, cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int b = 0; b < 2 && ok; b++) {
+      ok = ok && check(d, cudaMalloc(&d->pipe_in[b], in_doubles * sizeof(double)), "cudaMalloc(pipe_in)");
+      ok = ok && check(d, cudaMalloc(&d->pipe_out[b], out_doubles * sizeof(double)), "cudaMalloc(pipe_out)");
+      ok = ok && check(d, cudaEventCreateWithFlags(&d->ev_in[b], cudaEventDisableTiming), "cudaEventCreate");
+      ok = ok && check(d, cudaEventCreateWithFlags(&d->ev_tr[b], cudaEventDisableTiming), "cudaEventCreate");
+      ok = ok && check(d, cudaEventCreateWithFlags(&d->ev_comp[b], cudaEventDisableTiming), "cudaEventCreate");
+      ok = ok && check(d, cudaEventCreateWithFlags(&d->ev_out[b], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    d->pipe_piece = piece;
+    if (!ok) return -1;
+  }
+  // order the pipeline after whatever is already queued on the caller's stream
+  cudaEvent_t ev_start;
+  ok = ok && check(d, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming), "cudaEventCreate");
+  ok = ok && check(d, cudaEventRecord(ev_start, d->stream), "cudaEventRecord");
+  ok = ok && check(d, cudaStreamWaitEvent(d->s_in, ev_start, 0), "cudaStreamWaitEvent");
+  ok = ok && check(d, cudaStreamWaitEvent(d->s_out, ev_start, 0), "cudaStreamWaitEvent");
+  int p = 0;
+  for (size_t first = 0; first < (size_t)nbatch && ok; first += piece, p++) {
+    const int b = p & 1;
+    const size_t n = ((size_t)nbatch - first) < piece ? ((size_t)nbatch - first) : piece;
+    const size_t bq = n * H.nq * sizeof(double), bv = n * H.nv * sizeof(double);
+    char* st = (char*)d->pipe_in[b];
+    // stage 1: host -> device (waits until the transposes of piece p-2 released this buffer)
+    if (p >= 2) ok = ok && check(d, cudaStreamWaitEvent(d->s_in, d->ev_tr[b], 0), "wait tr");
+    ok = ok && check(d, cudaMemcpyAsync(st, qpos + first * H.nq, bq, cudaMemcpyHostToDevice, d->s_in), "H2D qpos");
+    ok = ok && check(d, cudaMemcpyAsync(st + bq, qvel + first * H.nv, bv, cudaMemcpyHostToDevice, d->s_in), "H2D qvel");
+    ok = ok && check(d, cudaMemcpyAsync(st + bq + bv, qacc + first * H.nv, bv, cudaMemcpyHostToDevice, d->s_in), "H2D qacc");
+    ok = ok && check(d, cudaEventRecord(d->ev_in[b], d->s_in), "record in");
+    // stage 2: transposes + kernels on the compute stream
+    ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_in[b], 0), "wait in");
+    ok = ok && check(d, mjb::launch_aos_to_soa((const double*)st, d->d_qpos + first, (int)n, H.nq, d->stride, d->stream), "transpose qpos");
+    ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq), d->d_qvel + first, (int)n, H.nv, d->stride, d->stream), "transpose qvel");
+    ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq + bv), d->d_qacc + first, (int)n, H.nv, d->stride, d->stream), "transpose qacc");
+    ok = ok && check(d, cudaEventRecord(d->ev_tr[b], d->stream), "record tr");
+    ok = ok && launchRange(d, (long long)first, (long long)n);
+    if (p >= 2) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[b], 0), "wait out");
+    ok = ok && check(d, mjb::launch_soa_to_aos(d->out.qfrc_inverse + first, (double*)d->pipe_out[b], (int)n, H.nv, d->stride, d->stream), "transpose out");
+    ok = ok && check(d, cudaEventRecord(d->ev_comp[b], d->stream), "record comp");
+    // stage 3: device -> host
+    ok = ok && check(d, cudaStreamWaitEvent(d->s_out, d->ev_comp[b], 0), "wait comp");
+    ok = ok && check(d, cudaMemcpyAsync(qfrc_inverse + first * H.nv, d->pipe_out[b], bv, cudaMemcpyDeviceToHost, d->s_out), "D2H qfrc");
+    ok = ok && check(d, cudaEventRecord(d->ev_out[b], d->s_out), "record out");
+  }
+  // the caller's stream completes when the last copies have landed
+  for (int b = 0; b < 2 && ok; b++) {
+    if (p > b) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[(p - 1 - b) & 1], 0), "join");
+  }
+  cudaEventDestroy(ev_start);
+  return ok ? 0 : -1;
 }
 
 int mjb_inverse(const mjModel* m, mjbData* d, int nbatch) {

@@ -250,3 +250,22 @@ def test_cuda_vs_c_restatement_on_fresh_states():
         np.testing.assert_array_equal(bd.efc()["type"], ref["efc_type"])
         nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
         assert nviol == 0, (name, nviol, worst)
+
+
+def test_pipelined_host_entry_point_matches_staged_calls():
+    """mjb_inverseHost (three-stream pipeline over pieces) == setState + inverse + get, bit for bit,
+    including a batch that is not a multiple of the piece size and repeated use of the buffers."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    model = mjb.Model.from_mjb(util.golden("humanoid")[0])
+    n = 300_000
+    qpos, qvel, qacc = generate_states(model, n, first=12345)
+    bd = mjb.BatchData(model, n)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    a = bd.qfrc_inverse()
+    for _ in range(2):
+        b = bd.inverse_host_arrays(qpos, qvel, qacc)
+        assert np.array_equal(a, b)
+    c = bd.inverse_host_arrays(qpos[:1000], qvel[:1000], qacc[:1000])
+    assert np.array_equal(a[:1000], c)
