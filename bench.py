@@ -235,7 +235,9 @@ def main():
     outmask = 0 if args.no_inertia else mjb.OUT_INERTIA
 
     # this rank's shard of the global state stream: [rank*n, (rank+1)*n)
-    qpos, qvel, qacc = generate_states(model, n, first=rank * n, z_range=z_range)
+    from mujoco_inversedynamicstest_b200.shard import weak_shard
+    first_state, _ = weak_shard(n, rank)
+    qpos, qvel, qacc = generate_states(model, n, first=first_state, z_range=z_range)
     h_qpos = torch.from_numpy(qpos).pin_memory()
     h_qvel = torch.from_numpy(qvel).pin_memory()
     h_qacc = torch.from_numpy(qacc).pin_memory()
