@@ -1262,6 +1262,81 @@ MJB_HD inline int plane_box(Con* con, double margin, const double* pos1, const d
   return cnt;
 }
 
+// mjc_PlaneConvex for an ellipsoid (engine_collision_convex.c:1045-1080; support function :570-581
+// with zero margin, local direction :553, back to the global frame :700-705)
+MJB_HD inline int plane_ellipsoid(Con* con, double margin, const double* pos1, const double* mat1,
+                                  const double* pos2, const double* mat2, const double* size2) {
+  const double normal[3] = {mat1[2], mat1[5], mat1[8]};
+  const double dir[3] = {-mat1[2], -mat1[5], -mat1[8]};
+  double res[3];
+  for (int i = 0; i < 3; i++) {
+    const double local = mat2[i]*dir[0] + mat2[3 + i]*dir[1] + mat2[6 + i]*dir[2];   // mat2' * dir
+    res[i] = local * size2[i];
+  }
+  normalize3(res);
+  for (int i = 0; i < 3; i++) res[i] *= size2[i];
+  double vec[3];
+  mulMatVec3(vec, mat2, res);
+  vec[0] += pos2[0]; vec[1] += pos2[1]; vec[2] += pos2[2];
+  const double dif[3] = {vec[0] - pos1[0], vec[1] - pos1[1], vec[2] - pos1[2]};
+  const double dist = dot3(normal, dif);
+  if (dist > margin) return 0;
+  con->dist = dist;
+  for (int k = 0; k < 3; k++) {
+    con->pos[k] = vec[k] + normal[k]*(-0.5*dist);
+    con->frame[k] = normal[k];
+    con->frame[3 + k] = 0;
+  }
+  return 1;
+}
+
+// mjraw_SphereBox (engine_collision_box.c:39-106)
+MJB_HD inline int sphere_box(Con* con, double margin, const double* pos1, const double* size1,
+                             const double* pos2, const double* mat2, const double* size2) {
+  double tmp[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  double center[3], clamped[3], deepest[3], pos[3];
+  for (int i = 0; i < 3; i++) center[i] = mat2[i]*tmp[0] + mat2[3 + i]*tmp[1] + mat2[6 + i]*tmp[2];
+  for (int i = 0; i < 3; i++) {
+    clamped[i] = center[i];
+    if (size2[i] > 0) {                                   // mju_clampVec (:22-35)
+      if (clamped[i] < -size2[i]) clamped[i] = -size2[i];
+      else if (clamped[i] > size2[i]) clamped[i] = size2[i];
+    }
+    deepest[i] = center[i];
+    tmp[i] = clamped[i] - center[i];
+  }
+  double dist = normalize3(tmp);
+  if (dist - size1[0] > margin) return 0;
+
+  if (dist <= MJB_MINVAL) {                               // sphere centre inside the box
+    double closest = (size2[0] + size2[1] + size2[2]) * 2;
+    int k = 0;
+    for (int i = 0; i < 6; i++) {
+      const double face = fabs((i % 2 ? 1 : -1)*size2[i / 2] - center[i / 2]);
+      if (closest > face) { closest = face; k = i; }
+    }
+    double nearest[3] = {0, 0, 0};
+    nearest[k / 2] = (k % 2 ? -1 : 1);
+    for (int i = 0; i < 3; i++) pos[i] = center[i] + nearest[i]*((size1[0] - closest) / 2);
+    mulMatVec3(con->frame, mat2, nearest);
+    dist = -closest;
+  } else {
+    for (int i = 0; i < 3; i++) {
+      deepest[i] += tmp[i]*size1[0];
+      pos[i] = 0;
+      pos[i] += clamped[i]*0.5;
+      pos[i] += deepest[i]*0.5;
+    }
+    mulMatVec3(con->frame, mat2, tmp);
+  }
+  double g[3];
+  mulMatVec3(g, mat2, pos);
+  con->pos[0] = g[0] + pos2[0]; con->pos[1] = g[1] + pos2[1]; con->pos[2] = g[2] + pos2[2];
+  con->dist = dist - size1[0];
+  con->frame[3] = 0; con->frame[4] = 0; con->frame[5] = 0;
+  return 1;
+}
+
 // mjraw_SphereSphere (:250)
 MJB_HD inline int sphere_sphere(Con* con, double margin, const double* pos1, const double* mat1,
                                 double r1, const double* pos2, const double* mat2, double r2) {
@@ -1419,6 +1494,8 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
     case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_ELLIPSOID: num = plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_SPHERE_BOX: num = sphere_box(con, margin, pos1, size1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_SPHERE:
       num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
     case MJB_FN_SPHERE_CAPSULE:

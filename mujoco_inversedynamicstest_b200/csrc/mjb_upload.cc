@@ -68,6 +68,7 @@ int narrowphaseId(int t1, int t2) {
         case mjGEOM_CAPSULE: return MJB_FN_PLANE_CAPSULE;
         case mjGEOM_CYLINDER: return MJB_FN_PLANE_CYLINDER;
         case mjGEOM_BOX: return MJB_FN_PLANE_BOX;
+        case mjGEOM_ELLIPSOID: return MJB_FN_PLANE_ELLIPSOID;
         default: return -2;
       }
     case mjGEOM_HFIELD:
@@ -77,6 +78,7 @@ int narrowphaseId(int t1, int t2) {
         case mjGEOM_SPHERE: return MJB_FN_SPHERE_SPHERE;
         case mjGEOM_CAPSULE: return MJB_FN_SPHERE_CAPSULE;
         case mjGEOM_CYLINDER: return MJB_FN_SPHERE_CYLINDER;
+        case mjGEOM_BOX: return MJB_FN_SPHERE_BOX;
         default: return -2;
       }
     case mjGEOM_CAPSULE:
