@@ -11,9 +11,11 @@ One "step" = one mjb_inverse pass over a resident batch of 2^20 synthetic humano
   e2e     the same metric through the public C-ABI with HOST buffers: mjb_inverseHost (H2D from
           pinned memory + transposes, kernels, transpose + D2H of qfrc_inverse, pipelined in pieces
           over three streams), all inside the timed region
-  roofline      FP64 roofline of the fused kernel (the path is fp64-compute bound):
-                executed-flop model x states / CUDA-event time vs the DFMA peak measured in-run
-  roofline_hbm  algorithmic bytes (872 B/state) / time vs MEASURED_PEAKS.json HBM copy bandwidth
+  roofline      FP64 roofline of the step's phase kernels: executed fp64 flops per state (ncu,
+                profiles/flops_per_state.json) x states / CUDA-event time vs the DFMA peak measured
+                in the same run
+  roofline_hbm  algorithmic bytes (in + out per state) / time vs MEASURED_PEAKS.json HBM copy
+                bandwidth, with the measured DRAM traffic of the step next to it
   cpu_baseline  the reference's own mj_inverse looped over the host cores with its thread pool
                 (oracle/_ref), on a bounded sample of the same states
 
@@ -53,11 +55,13 @@ FLOPS_PER_STATE_FILE = os.path.join(ROOT, "profiles", "flops_per_state.json")
 
 
 def load_flops_per_state(workload):
+    """(fp64 flops per state, measured DRAM bytes per state) of the phase kernels, from ncu."""
     try:
         with open(FLOPS_PER_STATE_FILE) as f:
-            return float(json.load(f)[workload]["flops_per_state"])
+            rec = json.load(f)[workload]
+        return float(rec["flops_per_state"]), rec.get("dram_bytes_per_state")
     except Exception:
-        return None
+        return None, None
 
 
 def measured_peaks():
@@ -299,7 +303,9 @@ def main():
         peaks, peak_src = measured_peaks()
         per_gpu_rate = n * args.steps / (kernel_ms * 1e-3)
         fp64_peak = mjb.fp64_peak_tflops(local_rank)
-        fps = load_flops_per_state(args.workload)
+        fps, dram_per_state = load_flops_per_state(args.workload)
+        if args.no_inertia:
+            fps, dram_per_state = None, None     # the frozen counts include the inertia kernel
         alg_bytes = 8 * (nq + 2 * nv) + 8 * nv + 4
         if not args.no_inertia:
             alg_bytes += 8 * (model.int("nM") + model.int("nC") + nv)
@@ -308,11 +314,14 @@ def main():
             "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (per_gpu_rate * fps * 1e-12 / fp64_peak) if (fps and fp64_peak > 0) else None,
             "traffic": None, "flops_per_state": fps,
+            "kernel": "the step = smooth + inertia + contact_scan + contact + backward kernels",
             "peak_source": "DFMA probe measured in this run (mjb_fp64PeakTflops)"}
         roof_hbm = {
             "bound": "hbm", "achieved": per_gpu_rate * alg_bytes * 1e-9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": per_gpu_rate * alg_bytes * 1e-9 / peaks["hbm_gbs"],
-            "traffic": None, "bytes_per_state": alg_bytes, "peak_source": peak_src}
+            "traffic": (dram_per_state * n) if dram_per_state else None,
+            "traffic_unit": "DRAM bytes per step per GPU (ncu dram__bytes_read+write, profiles/)",
+            "bytes_per_state": alg_bytes, "peak_source": peak_src}
         line = {
             "metric": "mj_inverse states/sec (humanoid, fp64)", "value": value, "unit": "states/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
