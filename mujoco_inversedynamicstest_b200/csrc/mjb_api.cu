@@ -25,7 +25,7 @@ struct mjbData_ {
   unsigned char* d_model = nullptr;
   int model_bytes = 0;
   int model_in_smem = 0;
-  double* d_scratch = nullptr;   // [nscratch][chunk_stride]
+  double* d_scratch = nullptr;   // [chunk_stride/32][nscratch][32]
   int* d_iscratch = nullptr;      // [MJB_ISC_MASK + ceil(ncand/32)][chunk_stride]
   long long chunk_stride = 0;     // states per chunk (intermediates are allocated per chunk)
   long long kernel_launches = 0;  // phase kernels launched so far (reported by the benchmark)
@@ -272,6 +272,8 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.scratch = d->d_scratch;
   a.iscratch = d->d_iscratch;
   a.chunk_stride = d->chunk_stride;
+  a.nscratch = d->hdr.nscratch;
+  a.niscratch = mjb::MJB_ISC_MASK + (d->hdr.ncand + 31) / 32 + 1;
   a.stride = d->stride;
   a.nconmax = d->nconmax;
   a.njmax = d->njmax;

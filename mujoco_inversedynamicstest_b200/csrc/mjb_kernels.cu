@@ -93,7 +93,6 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned c
   c.I = reinterpret_cast<const int*>(model + H->int_section);
   c.D = reinterpret_cast<const double*>(model + H->num_section);
   c.N = a.stride;
-  c.NS = static_cast<size_t>(a.chunk_stride);
   c.nconmax = a.nconmax;
   c.njmax = a.njmax;
   c.out = a.out;
@@ -103,8 +102,10 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned c
 __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long long local) {
   const long long s = a.chunk_start + local;
   c.s = s;
-  c.sc = a.scratch + local;
-  c.isc = a.iscratch + local;
+  // warp-blocked scratch: block (local/32) holds every slot of 32 consecutive states
+  const long long blk = local >> 5, ln = local & 31;
+  c.sc = a.scratch + (blk * a.nscratch << 5) + ln;
+  c.isc = a.iscratch + (blk * a.niscratch << 5) + ln;
   c.qpos = a.qpos + s;
   c.qvel = a.qvel + s;
   c.qacc = a.qacc + s;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
     if (valid) load_counters(own);
     int ncon = own.ncon, nefc = own.nefc;            // running counters of the state this lane owns
     int w = 0;
-    unsigned bits = (valid && nwords > 0) ? (unsigned)own.isc[(size_t)MJB_ISC_MASK * own.NS] : 0u;
+    unsigned bits = (valid && nwords > 0) ? (unsigned)own.isc[(size_t)MJB_ISC_MASK * MJB_LS] : 0u;
     int pool_n = 0;
 
     // step 3 on the current pool
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
         while (cnt < kListCap) {
           while (bits == 0 && w + 1 < nwords) {
             w++;
-            bits = (unsigned)own.isc[(size_t)(MJB_ISC_MASK + w) * own.NS];
+            bits = (unsigned)own.isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
           }
           if (bits == 0) break;
           const int b = __ffs((int)bits) - 1;

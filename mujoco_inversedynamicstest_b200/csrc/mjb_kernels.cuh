@@ -25,9 +25,10 @@ struct LaunchArgs {
   const double* qpos;           // [nq][stride]
   const double* qvel;           // [nv][stride]
   const double* qacc;           // [nv][stride]
-  double* scratch;              // [nscratch][chunk_stride]  intermediates of one chunk of states
-  int* iscratch;                // [MJB_ISC_MASK + ceil(ncand/32)][chunk_stride]
-  long long chunk_stride;       // scratch row stride
+  double* scratch;              // [chunk_stride/32][nscratch][32]  intermediates of one chunk of states
+  int* iscratch;                // [chunk_stride/32][niscratch][32]
+  int nscratch, niscratch;      // slots per state: mjbHdr::nscratch, MJB_ISC_MASK + ceil(ncand/32) + 1
+  long long chunk_stride;       // states per chunk (multiple of 32)
   long long chunk_start;        // first state of the chunk
   int chunk_n;                  // states in the chunk
   long long stride;             // row stride of every state-indexed input/output array

@@ -28,6 +28,8 @@
   X(body_jntadr, nbody)          \
   X(body_dofnum, nbody)          \
   X(body_dofadr, nbody)          \
+  X(body_geomnum, nbody)         \
+  X(body_geomadr, nbody)         \
   X(jnt_type, njnt)              \
   X(jnt_qposadr, njnt)           \
   X(jnt_dofadr, njnt)            \
@@ -62,7 +64,8 @@
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
-  X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent */
+  X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
+                                 bit2 has a child other than body+1 (forward-sweep carry must be stored) */
 
 // ---- double arrays copied 1:1 from mjModel (name, rows, cols)
 #define MJB_NUM_ARRAYS(X)         \
@@ -208,20 +211,14 @@ enum {
 enum {
   MJB_SC_xpos = 0,     // nbody*3
   MJB_SC_xquat,        // nbody*4
-  MJB_SC_xmat,         // nbody*9
-  MJB_SC_xipos,        // nbody*3
-  MJB_SC_ximat,        // nbody*9
-  MJB_SC_xanchor,      // njnt*3
-  MJB_SC_xaxis,        // njnt*3
+  MJB_SC_origin,       // nbody*3   origin of the spatial frame of a kinematic tree, stored at its ROOT body
   MJB_SC_geom_xpos,    // ngeom*3
   MJB_SC_geom_xmat,    // ngeom*9
-  MJB_SC_subtree_com,  // nbody*3
-  MJB_SC_mass_subtree, // nbody
   MJB_SC_cinert,       // nbody*10
   MJB_SC_cdof,         // nv*6
   MJB_SC_cvel,         // nbody*6
   MJB_SC_cacc_lin,     // nbody*6   sum cdof*qacc over the dof chain (J*qacc carrier)
-  MJB_SC_cacc,         // nbody*6   rne accelerations
+  MJB_SC_cacc,         // nbody*6   rne accelerations (forward-sweep carry; stored where a later child reads it)
   MJB_SC_cfrc,         // nbody*6   rne body forces
   MJB_SC_cfrc_ext,     // nbody*6   constraint wrenches on bodies, '+' side (body 2 of a pair)
   MJB_SC_cfrc_ext1,    // nbody*6   '-' side (body 1 of a pair); kept apart so that each sum runs in contact order

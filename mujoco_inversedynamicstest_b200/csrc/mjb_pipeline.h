@@ -71,7 +71,6 @@ struct Ctx {
   const double* D;      // double section of the model blob
   double* sc;           // double scratch [nscratch][NS], already offset to this state
   int* isc;             // int scratch [MJB_ISC_COUNT][NS], already offset to this state
-  size_t NS;            // scratch row stride (states per chunk)
   const double* qpos;   // already offset to this state
   const double* qvel;
   const double* qacc;
@@ -82,10 +81,19 @@ struct Ctx {
   int ncon, ne, nf, nl, nefc, status;
 };
 
+// lane stride of the per-state scratch: device scratch is blocked per warp, element (slot, state i)
+// at ((i/32)*nslots + slot)*32 + i%32, so the 32 lanes of a warp touch one 256-byte line per slot and
+// a warp's whole working set is one contiguous block (slot offsets fold into load/store immediates)
+#if defined(__CUDACC__)
+#define MJB_LS 32
+#else
+#define MJB_LS 1
+#endif
+
 #define MI(name) (c.I + c.H->ioff[MJB_I_##name])
 #define MD(name) (c.D + c.H->noff[MJB_N_##name])
-#define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * c.NS)
-#define AT(p, k) (p)[(size_t)(k) * c.NS]
+#define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * MJB_LS)
+#define AT(p, k) (p)[(size_t)(k) * MJB_LS]
 #define QPOS(i) c.qpos[(size_t)(i) * (size_t)c.N]
 #define QVEL(i) c.qvel[(size_t)(i) * (size_t)c.N]
 #define QACC(i) c.qacc[(size_t)(i) * (size_t)c.N]
@@ -96,8 +104,8 @@ MJB_DI void ldn_(double* dst, const double* p, int first, int n, size_t stride) 
 MJB_DI void stn_(double* p, int first, const double* src, int n, size_t stride) {
   for (int k = 0; k < n; k++) p[(size_t)(first + k) * stride] = src[k];
 }
-#define ldn(dst, p, first, n) ldn_(dst, p, first, n, c.NS)
-#define stn(p, first, src, n) stn_(p, first, src, n, c.NS)
+#define ldn(dst, p, first, n) ldn_(dst, p, first, n, MJB_LS)
+#define stn(p, first, src, n) stn_(p, first, src, n, MJB_LS)
 
 // per-state integer scratch rows: counters carried between the phase kernels
 // MJB_ISC_NSURV / MJB_ISC_MASK..: survivors of the contact scan (count, then ceil(ncand/32) words)
@@ -105,14 +113,14 @@ enum { MJB_ISC_NCON = 0, MJB_ISC_NE, MJB_ISC_NF, MJB_ISC_NL, MJB_ISC_NEFC, MJB_I
        MJB_ISC_NSURV, MJB_ISC_MASK, MJB_ISC_COUNT = MJB_ISC_MASK };
 
 MJB_HD inline void save_counters(Ctx& c) {
-  c.isc[MJB_ISC_NCON * c.NS] = c.ncon; c.isc[MJB_ISC_NE * c.NS] = c.ne;
-  c.isc[MJB_ISC_NF * c.NS] = c.nf; c.isc[MJB_ISC_NL * c.NS] = c.nl;
-  c.isc[MJB_ISC_NEFC * c.NS] = c.nefc; c.isc[MJB_ISC_STATUS * c.NS] = c.status;
+  c.isc[MJB_ISC_NCON * MJB_LS] = c.ncon; c.isc[MJB_ISC_NE * MJB_LS] = c.ne;
+  c.isc[MJB_ISC_NF * MJB_LS] = c.nf; c.isc[MJB_ISC_NL * MJB_LS] = c.nl;
+  c.isc[MJB_ISC_NEFC * MJB_LS] = c.nefc; c.isc[MJB_ISC_STATUS * MJB_LS] = c.status;
 }
 MJB_HD inline void load_counters(Ctx& c) {
-  c.ncon = c.isc[MJB_ISC_NCON * c.NS]; c.ne = c.isc[MJB_ISC_NE * c.NS];
-  c.nf = c.isc[MJB_ISC_NF * c.NS]; c.nl = c.isc[MJB_ISC_NL * c.NS];
-  c.nefc = c.isc[MJB_ISC_NEFC * c.NS]; c.status = c.isc[MJB_ISC_STATUS * c.NS];
+  c.ncon = c.isc[MJB_ISC_NCON * MJB_LS]; c.ne = c.isc[MJB_ISC_NE * MJB_LS];
+  c.nf = c.isc[MJB_ISC_NF * MJB_LS]; c.nl = c.isc[MJB_ISC_NL * MJB_LS];
+  c.nefc = c.isc[MJB_ISC_NEFC * MJB_LS]; c.status = c.isc[MJB_ISC_STATUS * MJB_LS];
 }
 
 // engine_util_blas.c:677 with n == 6 (same association as the reference's 4-lane order)
@@ -138,75 +146,167 @@ MJB_HD inline void check_inputs(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_kinematics (engine_core_smooth.c:38-178) incl. mj_local2Global (engine_support.c:1565)
-MJB_HD inline void kinematics(Ctx& c) {
+// Forward sweep: ONE root-to-leaves pass that does, per body, the work the reference spreads over
+//   mj_kinematics  (engine_core_smooth.c:38-178, mj_local2Global engine_support.c:1565)
+//   mj_comPos      (:183-270; cinert via mju_inertCom, cdof via mju_dofCom)
+//   mj_comVel      (:1833-1896)
+//   mj_rne forward (:1969-2005, flg_acc = 1)
+// so that a body's pose, joint axes, velocity and acceleration never leave registers between those
+// stages; only what later phases read is written to the per-state scratch.
+//
+// Frame of the spatial quantities. The reference expresses cdof/cvel/cacc/cinert/cfrc about the
+// centre of mass of the kinematic tree (subtree_com[body_rootid]), which is known only after a
+// full kinematics pass. Spatial algebra holds about ANY fixed world point, and qfrc_inverse, qM,
+// qLD, J*v, J'*f are independent of it, so the sweep uses the tree origin
+//     O_tree = position of the tree's root body before its joints act
+//            = qpos[0:3] of a free root, body_pos of a jointed or welded root
+// which is known when the root is entered (|x - O| stays of the order of the tree's size, like the
+// reference's com-based offsets). Bodies of one tree are contiguous in the body order, so O is
+// carried in registers; it is also stored per root body for the constraint phases.
+//
+// Carry. Bodies are in depth-first order, so a body's parent is very often the body just
+// processed: its pose/velocity/acceleration are then still in registers (P, Q, V, A, AL) and are
+// read from scratch only when the parent is an earlier body (warp-uniform test).
+//
+//   cvel      spatial velocity about O                              (contact rows, cfrc)
+//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
+//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
+//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                   (backward pass)
+// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
+
+// pose of the geoms of body b from the body's frames held in registers (mj_local2Global)
+MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* quat, const double* mat,
+                              const double* ip, const double* im) {
+  const int* body_geomadr = MI(body_geomadr);
+  const int* body_geomnum = MI(body_geomnum);
+  const int* geom_sameframe = MI(geom_sameframe);
+  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const int g0 = body_geomadr[b], gn = body_geomnum[b];
+  for (int g = g0; g < g0 + gn; g++) {
+    const int sf = geom_sameframe[g];
+    double gp[3], gm[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      gp[0] = pos[0]; gp[1] = pos[1]; gp[2] = pos[2];
+    } else if (sf == MJB_SAMEFRAME_INERTIA) {
+      gp[0] = ip[0]; gp[1] = ip[1]; gp[2] = ip[2];
+    } else {
+      mulMatVec3(gp, mat, geom_pos + 3*g);
+      gp[0] += pos[0]; gp[1] += pos[1]; gp[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, geom_quat + 4*g);
+      quat2Mat(gm, tq);
+    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
+      for (int k = 0; k < 9; k++) gm[k] = mat[k];
+    } else {
+      for (int k = 0; k < 9; k++) gm[k] = im[k];
+    }
+    stn(gxpos, 3*g, gp, 3);
+    stn(gxmat, 9*g, gm, 9);
+  }
+}
+
+MJB_HD inline void forward_sweep(Ctx& c) {
   const mjbHdr& H = *c.H;
-  const int nbody = H.nbody, ngeom = H.ngeom;
-  double* xpos = SC(xpos); double* xquat = SC(xquat); double* xmat = SC(xmat);
-  double* xipos = SC(xipos); double* ximat = SC(ximat);
-  double* xanchor = SC(xanchor); double* xaxis = SC(xaxis);
+  const int nbody = H.nbody;
+  double* xpos = SC(xpos); double* xquat = SC(xquat); double* org = SC(origin);
+  double* cvel = SC(cvel); double* cal = SC(cacc_lin); double* cacc = SC(cacc);
+  double* cfrc = SC(cfrc); double* cinert = SC(cinert); double* cdof = SC(cdof);
   const int* body_parentid = MI(body_parentid);
   const int* body_jntadr = MI(body_jntadr);
   const int* body_jntnum = MI(body_jntnum);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
   const int* body_mocapid = MI(body_mocapid);
   const int* body_sameframe = MI(body_sameframe);
+  const int* tree_flags = MI(body_tree_flags);
   const int* jnt_type = MI(jnt_type);
   const int* jnt_qposadr = MI(jnt_qposadr);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* dof_jntid = MI(dof_jntid);
   const double* body_pos = MD(body_pos); const double* body_quat = MD(body_quat);
   const double* body_ipos = MD(body_ipos); const double* body_iquat = MD(body_iquat);
+  const double* body_mass = MD(body_mass); const double* body_inertia = MD(body_inertia);
   const double* jnt_pos = MD(jnt_pos); const double* jnt_axis = MD(jnt_axis);
   const double* qpos0 = MD(qpos0);
 
-  // world
-  for (int k = 0; k < 3; k++) { AT(xpos, k) = 0; AT(xipos, k) = 0; }
-  AT(xquat, 0) = 1; AT(xquat, 1) = 0; AT(xquat, 2) = 0; AT(xquat, 3) = 0;
-  for (int k = 0; k < 9; k++) { double v = (k % 4 == 0) ? 1.0 : 0.0; AT(xmat, k) = v; AT(ximat, k) = v; }
+  // world body: identity pose, zero velocity, acceleration = -gravity (mj_rne :1979-1982)
+  double P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
+  double V[6] = {0, 0, 0, 0, 0, 0}, AL[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
+  double O[3] = {0, 0, 0};
+  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+    A[3] = -H.gravity[0]; A[4] = -H.gravity[1]; A[5] = -H.gravity[2];
+  }
+  stn(xpos, 0, P, 3); stn(xquat, 0, Q, 4); stn(org, 0, O, 3);
+  stn(cvel, 0, V, 6); stn(cal, 0, AL, 6); stn(cacc, 0, A, 6);
+  {
+    const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    body_geoms(c, 0, P, Q, I9, P, I9);
+  }
+  int carry = 0;          // body whose P, Q, V, A, AL are in registers
 
   for (int b = 1; b < nbody; b++) {
-    double pos[3], quat[4];
+    const int pid = body_parentid[b];
     const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
+    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
+    if (pid != carry) {
+      ldn(P, xpos, 3*pid, 3); ldn(Q, xquat, 4*pid, 4);
+      ldn(V, cvel, 6*pid, 6); ldn(A, cacc, 6*pid, 6); ldn(AL, cal, 6*pid, 6);
+    }
+    double pos[3], quat[4];
+    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
+    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
+    const bool isfree = jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE;
+    bool has_ball = false;
 
-    if (jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE) {
+    if (isfree) {
       const int qadr = jnt_qposadr[jntadr];
       for (int k = 0; k < 3; k++) pos[k] = QPOS(qadr + k);
       for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + 3 + k);
       normalize4(quat);
-      for (int k = 0; k < 3; k++) {
-        AT(xanchor, 3*jntadr + k) = pos[k];
-        AT(xaxis, 3*jntadr + k) = jnt_axis[3*jntadr + k];
-      }
+      if (pid == 0) { O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2]; stn(org, 3*b, O, 3); }
     } else {
-      const int pid = body_parentid[b];
       double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
       if (body_mocapid[b] >= 0) normalize4(bquat);   // mocap pose = model pose (mj_resetData default)
       if (pid) {
-        double pm[9], pp[3], pq[4];
-        ldn(pm, xmat, 9*pid, 9); ldn(pp, xpos, 3*pid, 3); ldn(pq, xquat, 4*pid, 4);
+        double pm[9];
+        quat2Mat(pm, Q);                 // == the parent's xmat (same function of the same xquat)
         mulMatVec3(pos, pm, body_pos + 3*b);
-        pos[0] += pp[0]; pos[1] += pp[1]; pos[2] += pp[2];
-        mulQuat(quat, pq, bquat);
+        pos[0] += P[0]; pos[1] += P[1]; pos[2] += P[2];
+        mulQuat(quat, Q, bquat);
       } else {
         for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
         for (int k = 0; k < 4; k++) quat[k] = bquat[k];
+        O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
+        stn(org, 3*b, O, 3);
       }
+      for (int j = 0; j < jntnum; j++) has_ball = has_ball || jnt_type[jntadr + j] == MJB_JNT_BALL;
 
       for (int j = 0; j < jntnum; j++) {
         const int jid = jntadr + j;
         const int qadr = jnt_qposadr[jid];
+        const int dadr = jnt_dofadr[jid];
         const int jtype = jnt_type[jid];
-        double ax[3], anc[3];
+        double ax[3], anc[3], cd[6];
         rotVecQuat(ax, jnt_axis + 3*jid, quat);
         rotVecQuat(anc, jnt_pos + 3*jid, quat);
         anc[0] += pos[0]; anc[1] += pos[1]; anc[2] += pos[2];
+        const double off[3] = {O[0] - anc[0], O[1] - anc[1], O[2] - anc[2]};
 
         if (jtype == MJB_JNT_SLIDE) {
           const double q = QPOS(qadr) - qpos0[qadr];
           pos[0] += ax[0]*q; pos[1] += ax[1]*q; pos[2] += ax[2]*q;
+          cd[0] = 0; cd[1] = 0; cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2];
         } else {
           double qloc[4];
           if (jtype == MJB_JNT_BALL) {
             for (int k = 0; k < 4; k++) qloc[k] = QPOS(qadr + k);
             normalize4(qloc);
+            // cdof of a ball joint uses the body's FINAL orientation (mj_comPos :243-252): keep
+            // the anchor offset in the dof's slots until the pose is complete
+            stn(cdof, 6*dadr, off, 3);
           } else {
             // mju_axisAngle2Quat (engine_util_spatial.c:97)
             const double angle = QPOS(qadr) - qpos0[qadr];
@@ -214,14 +314,24 @@ MJB_HD inline void kinematics(Ctx& c) {
             sincos(angle*0.5, &sn, &cs);
             qloc[0] = cs;
             qloc[1] = jnt_axis[3*jid]*sn; qloc[2] = jnt_axis[3*jid+1]*sn; qloc[3] = jnt_axis[3*jid+2]*sn;
+            cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+            cross3(cd + 3, ax, off);
           }
           mulQuat(quat, quat, qloc);
           double vec[3];
           rotVecQuat(vec, jnt_pos + 3*jid, quat);
           pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
         }
-        stn(xanchor, 3*jid, anc, 3);
-        stn(xaxis, 3*jid, ax, 3);
+        if (jtype != MJB_JNT_BALL) {
+          stn(cdof, 6*dadr, cd, 6);
+          if (!has_ball) {
+            // mj_comVel / mj_rne for a scalar dof, fused: cdof_dot uses the velocity so far
+            double dd[6];
+            crossMotion(dd, V, cd);
+            const double qv = QVEL(dadr), qa = QACC(dadr);
+            for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
+          }
+        }
       }
     }
 
@@ -230,9 +340,81 @@ MJB_HD inline void kinematics(Ctx& c) {
     quat2Mat(mat, quat);
     stn(xquat, 4*b, quat, 4);
     stn(xpos, 3*b, pos, 3);
-    stn(xmat, 9*b, mat, 9);
 
-    // inertial frame
+    if (isfree) {
+      // translational dofs: cdof = [0, e_r], cdof_dot = 0
+      for (int r = 0; r < 3; r++) {
+        double cd[6] = {0, 0, 0, r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0};
+        stn(cdof, 6*(bda + r), cd, 6);
+        V[3 + r] += QVEL(bda + r);
+        t2[3 + r] += QACC(bda + r);
+      }
+      // rotational dofs: body axes; the anchor is the body origin, O - anchor = (O - pos)
+      const double off[3] = {O[0] - pos[0], O[1] - pos[1], O[2] - pos[2]};
+      double cd[3][6];
+      for (int r = 0; r < 3; r++) {
+        cd[r][0] = mat[r]; cd[r][1] = mat[r + 3]; cd[r][2] = mat[r + 6];
+        cross3(cd[r] + 3, cd[r], off);
+        stn(cdof, 6*(bda + 3 + r), cd[r], 6);
+      }
+      // all three use the velocity BEFORE this joint's rotation (mj_comVel :1855-1876)
+      for (int r = 0; r < 3; r++) {
+        double dd[6];
+        crossMotion(dd, V, cd[r]);
+        const double qv = QVEL(bda + 3 + r);
+        for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+      }
+      for (int r = 0; r < 3; r++) {
+        const double qv = QVEL(bda + 3 + r), qa = QACC(bda + 3 + r);
+        for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+      }
+    } else if (has_ball) {
+      // general path: finish the ball-joint cdofs with the final orientation, then run the dof
+      // loop of mj_comVel over the body's dofs from scratch
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        if (jnt_type[jid] != MJB_JNT_BALL) continue;
+        const int dadr = jnt_dofadr[jid];
+        double off[3];
+        ldn(off, cdof, 6*dadr, 3);
+        for (int r = 0; r < 3; r++) {
+          double cd[6] = {mat[r], mat[r + 3], mat[r + 6], 0, 0, 0};
+          cross3(cd + 3, cd, off);
+          stn(cdof, 6*(dadr + r), cd, 6);
+        }
+      }
+      for (int j = 0; j < dofnum; j++) {
+        const int jt = jnt_type[dof_jntid[bda + j]];
+        if (jt == MJB_JNT_BALL) {
+          double cd[3][6];
+          for (int r = 0; r < 3; r++) {
+            double dd[6];
+            ldn(cd[r], cdof, 6*(bda + j + r), 6);
+            crossMotion(dd, V, cd[r]);
+            const double qv = QVEL(bda + j + r);
+            for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+          }
+          for (int r = 0; r < 3; r++) {
+            const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
+            for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+          }
+          j += 2;
+        } else {
+          double cd[6], dd[6];
+          ldn(cd, cdof, 6*(bda + j), 6);
+          crossMotion(dd, V, cd);
+          const double qv = QVEL(bda + j), qa = QACC(bda + j);
+          for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
+        }
+      }
+    }
+
+    for (int k = 0; k < 6; k++) { A[k] += t1[k]; A[k] += t2[k]; AL[k] += t2[k]; }
+    stn(cvel, 6*b, V, 6);
+    stn(cal, 6*b, AL, 6);
+    if (tree_flags[b] & 4) stn(cacc, 6*b, A, 6);   // read back only by a child that is not b+1
+
+    // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
     const int sf = body_sameframe[b];
     double ip[3], im[9];
     if (sf == MJB_SAMEFRAME_BODY) {
@@ -248,130 +430,23 @@ MJB_HD inline void kinematics(Ctx& c) {
     } else {
       for (int k = 0; k < 9; k++) im[k] = mat[k];
     }
-    stn(xipos, 3*b, ip, 3);
-    stn(ximat, 9*b, im, 9);
-  }
+    {
+      const double off[3] = {ip[0] - O[0], ip[1] - O[1], ip[2] - O[2]};
+      double ci[10], f[6], u1[6], u2[6];
+      inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
+      stn(cinert, 10*b, ci, 10);
+      mulInertVec(f, ci, A);
+      mulInertVec(u1, ci, V);
+      crossForce(u2, V, u1);
+      for (int k = 0; k < 6; k++) f[k] += u2[k];
+      stn(cfrc, 6*b, f, 6);
+    }
 
-  // geoms
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
-  const int* geom_bodyid = MI(geom_bodyid);
-  const int* geom_sameframe = MI(geom_sameframe);
-  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
-  for (int g = 0; g < ngeom; g++) {
-    const int b = geom_bodyid[g];
-    const int sf = geom_sameframe[g];
-    double gp[3], gm[9];
-    if (sf == MJB_SAMEFRAME_BODY) {
-      ldn(gp, xpos, 3*b, 3);
-    } else if (sf == MJB_SAMEFRAME_INERTIA) {
-      ldn(gp, xipos, 3*b, 3);
-    } else {
-      double bm[9], bp[3];
-      ldn(bm, xmat, 9*b, 9); ldn(bp, xpos, 3*b, 3);
-      mulMatVec3(gp, bm, geom_pos + 3*g);
-      gp[0] += bp[0]; gp[1] += bp[1]; gp[2] += bp[2];
-    }
-    if (sf == MJB_SAMEFRAME_NONE) {
-      double bq[4], tq[4];
-      ldn(bq, xquat, 4*b, 4);
-      mulQuat(tq, bq, geom_quat + 4*g);
-      quat2Mat(gm, tq);
-    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
-      ldn(gm, xmat, 9*b, 9);
-    } else {
-      ldn(gm, ximat, 9*b, 9);
-    }
-    stn(gxpos, 3*g, gp, 3);
-    stn(gxmat, 9*g, gm, 9);
-  }
-}
+    body_geoms(c, b, pos, quat, mat, ip, im);
 
-// ------------------------------------------------------------------------------------------
-// mj_comPos (engine_core_smooth.c:183-270)
-MJB_HD inline void com_pos(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  const int nbody = H.nbody, njnt = H.njnt;
-  double* com = SC(subtree_com); double* msub = SC(mass_subtree);
-  double* xipos = SC(xipos); double* ximat = SC(ximat); double* xmat = SC(xmat);
-  double* xanchor = SC(xanchor); double* xaxis = SC(xaxis);
-  double* cinert = SC(cinert); double* cdof = SC(cdof);
-  const int* body_parentid = MI(body_parentid);
-  const int* body_rootid = MI(body_rootid);
-  const double* body_mass = MD(body_mass);
-  const double* body_inertia = MD(body_inertia);
-
-  for (int i = 0; i < nbody; i++) {
-    AT(msub, i) = 0;
-    AT(com, 3*i) = 0; AT(com, 3*i+1) = 0; AT(com, 3*i+2) = 0;
-  }
-  for (int i = nbody - 1; i >= 0; i--) {
-    const double mass = body_mass[i];
-    double ci[3], xi[3];
-    ldn(ci, com, 3*i, 3); ldn(xi, xipos, 3*i, 3);
-    ci[0] += xi[0]*mass; ci[1] += xi[1]*mass; ci[2] += xi[2]*mass;
-    double ms = AT(msub, i) + mass;
-    AT(msub, i) = ms;
-    if (i) {
-      const int j = body_parentid[i];
-      AT(com, 3*j) += ci[0]; AT(com, 3*j+1) += ci[1]; AT(com, 3*j+2) += ci[2];
-      AT(msub, j) += ms;
-    }
-    if (ms < MJB_MINVAL) {
-      ci[0] = xi[0]; ci[1] = xi[1]; ci[2] = xi[2];
-    } else {
-      const double inv = 1.0 / fmax(MJB_MINVAL, ms);
-      ci[0] *= inv; ci[1] *= inv; ci[2] *= inv;
-    }
-    stn(com, 3*i, ci, 3);
-  }
-
-  for (int k = 0; k < 10; k++) AT(cinert, k) = 0;
-  for (int i = 1; i < nbody; i++) {
-    double off[3], xi[3], rc[3], im[9], res[10];
-    ldn(xi, xipos, 3*i, 3); ldn(rc, com, 3*body_rootid[i], 3); ldn(im, ximat, 9*i, 9);
-    off[0] = xi[0] - rc[0]; off[1] = xi[1] - rc[1]; off[2] = xi[2] - rc[2];
-    inertCom(res, body_inertia + 3*i, im, off, body_mass[i]);
-    stn(cinert, 10*i, res, 10);
-  }
-
-  const int* jnt_type = MI(jnt_type);
-  const int* jnt_dofadr = MI(jnt_dofadr);
-  const int* jnt_bodyid = MI(jnt_bodyid);
-  for (int j = 0; j < njnt; j++) {
-    const int da = 6*jnt_dofadr[j];
-    const int bi = jnt_bodyid[j];
-    double off[3], rc[3], an[3];
-    ldn(rc, com, 3*body_rootid[bi], 3); ldn(an, xanchor, 3*j, 3);
-    off[0] = rc[0] - an[0]; off[1] = rc[1] - an[1]; off[2] = rc[2] - an[2];
-    const int jt = jnt_type[j];
-    int skip = 0;
-    if (jt == MJB_JNT_FREE) {
-      for (int k = 0; k < 18; k++) AT(cdof, da + k) = 0;
-      for (int i = 0; i < 3; i++) AT(cdof, da + 3 + 7*i) = 1;
-      skip = 18;
-    }
-    if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
-      double bm[9];
-      ldn(bm, xmat, 9*bi, 9);
-      for (int i = 0; i < 3; i++) {
-        double axis[3] = {bm[i], bm[i+3], bm[i+6]};
-        double cr[3];
-        cross3(cr, axis, off);
-        stn(cdof, da + skip + 6*i, axis, 3);
-        stn(cdof, da + skip + 6*i + 3, cr, 3);
-      }
-    } else if (jt == MJB_JNT_SLIDE) {
-      double ax[3];
-      ldn(ax, xaxis, 3*j, 3);
-      AT(cdof, da) = 0; AT(cdof, da+1) = 0; AT(cdof, da+2) = 0;
-      stn(cdof, da + 3, ax, 3);
-    } else {
-      double ax[3], cr[3];
-      ldn(ax, xaxis, 3*j, 3);
-      cross3(cr, ax, off);
-      stn(cdof, da, ax, 3);
-      stn(cdof, da + 3, cr, 3);
-    }
+    P[0] = pos[0]; P[1] = pos[1]; P[2] = pos[2];
+    Q[0] = quat[0]; Q[1] = quat[1]; Q[2] = quat[2]; Q[3] = quat[3];
+    carry = b;
   }
 }
 
@@ -398,96 +473,6 @@ MJB_HD inline void tendon_fixed(Ctx& c) {
     }
     AT(L, t) = len;
     AT(V, t) = vel;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// mj_comVel (engine_core_smooth.c:1833-1896) fused with the forward half of mj_rne(flg_acc=1)
-// (:1969-2005): one root-to-leaves sweep yields, per body,
-//   cvel      spatial velocity                                     (contacts, cfrc)
-//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
-//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
-//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                  (backward pass)
-// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
-MJB_HD inline void com_vel_rne_forward(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  const int nbody = H.nbody;
-  double* cvel = SC(cvel); double* cdof = SC(cdof); double* cinert = SC(cinert);
-  double* cal = SC(cacc_lin); double* cacc = SC(cacc); double* cfrc = SC(cfrc);
-  const int* body_parentid = MI(body_parentid);
-  const int* body_dofadr = MI(body_dofadr);
-  const int* body_dofnum = MI(body_dofnum);
-  const int* dof_jntid = MI(dof_jntid);
-  const int* jnt_type = MI(jnt_type);
-
-  for (int k = 0; k < 6; k++) { AT(cvel, k) = 0; AT(cal, k) = 0; }
-  AT(cacc, 0) = 0; AT(cacc, 1) = 0; AT(cacc, 2) = 0;
-  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
-    AT(cacc, 3) = -H.gravity[0]; AT(cacc, 4) = -H.gravity[1]; AT(cacc, 5) = -H.gravity[2];
-  } else {
-    AT(cacc, 3) = 0; AT(cacc, 4) = 0; AT(cacc, 5) = 0;
-  }
-
-  for (int b = 1; b < nbody; b++) {
-    const int bda = body_dofadr[b];
-    const int dofnum = body_dofnum[b];
-    const int pid = body_parentid[b];
-    double v[6];
-    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
-    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
-    ldn(v, cvel, 6*pid, 6);
-
-    for (int j = 0; j < dofnum; j++) {
-      const int jt = jnt_type[dof_jntid[bda + j]];
-      if (jt == MJB_JNT_FREE) {
-        // translational dofs: cdof_dot = 0 ; cvel += cdof(0..2)' * qvel(0..2)
-        for (int r = 0; r < 3; r++) {
-          const double qv = QVEL(bda + r), qa = QACC(bda + r);
-          double cd[6];
-          ldn(cd, cdof, 6*(bda + r), 6);
-          for (int k = 0; k < 6; k++) { v[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
-        }
-        j += 3;
-      }
-      if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
-        // all three rotational dofs use the velocity BEFORE this joint's rotation
-        double cd[3][6];
-        for (int r = 0; r < 3; r++) {
-          double dd[6];
-          ldn(cd[r], cdof, 6*(bda + j + r), 6);
-          crossMotion(dd, v, cd[r]);
-          const double qv = QVEL(bda + j + r);
-          for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
-        }
-        for (int r = 0; r < 3; r++) {
-          const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
-          for (int k = 0; k < 6; k++) { v[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
-        }
-        j += 2;
-      } else {
-        double cd[6], dd[6];
-        ldn(cd, cdof, 6*(bda + j), 6);
-        crossMotion(dd, v, cd);
-        const double qv = QVEL(bda + j), qa = QACC(bda + j);
-        for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; v[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
-      }
-    }
-    stn(cvel, 6*b, v, 6);
-
-    double acc[6], al[6];
-    ldn(acc, cacc, 6*pid, 6);
-    ldn(al, cal, 6*pid, 6);
-    for (int k = 0; k < 6; k++) { acc[k] += t1[k]; acc[k] += t2[k]; al[k] += t2[k]; }
-    stn(cacc, 6*b, acc, 6);
-    stn(cal, 6*b, al, 6);
-
-    double ci[10], f[6], u1[6], u2[6];
-    ldn(ci, cinert, 10*b, 10);
-    mulInertVec(f, ci, acc);
-    mulInertVec(u1, ci, v);
-    crossForce(u2, v, u1);
-    for (int k = 0; k < 6; k++) f[k] += u2[k];
-    stn(cfrc, 6*b, f, 6);
   }
 }
 
@@ -648,7 +633,7 @@ MJB_HD inline double scalar_row(Ctx& c, int type, int id, const double* sp, doub
 MJB_HD inline void point_motion(Ctx& c, const double* carrier, int b, const double* p, double* lin,
                                 double* ang) {
   const int* rootid = MI(body_rootid);
-  double* com = SC(subtree_com);
+  double* com = SC(origin);
   double v[6], o[3], r[3], cr[3];
   ldn(v, carrier, 6*b, 6); ldn(o, com, 3*rootid[b], 3);
   r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
@@ -662,7 +647,7 @@ MJB_HD inline void point_motion(Ctx& c, const double* carrier, int b, const doub
 MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, const double* T,
                               bool positive) {
   const int* rootid = MI(body_rootid);
-  double* com = SC(subtree_com);
+  double* com = SC(origin);
   double* fe = positive ? SC(cfrc_ext) : SC(cfrc_ext1);
   double o[3], r[3], cr[3];
   ldn(o, com, 3*rootid[b], 3);
@@ -692,7 +677,7 @@ MJB_HD inline void equality_rows(Ctx& c) {
   const double* eq_num = MD(eq_num);
   const double* eq_data = MD(eq_data);
   const double* sp_eq = MD(sp_eq);
-  double* xpos = SC(xpos); double* xmat = SC(xmat); double* xquat = SC(xquat);
+  double* xpos = SC(xpos); double* xquat = SC(xquat);
   double* qc = SC(qfrc_c);
   for (int i = 0; i < H.neq; i++) {
     const int* ei = eq_int + MJB_EQ_NI*i;
@@ -703,8 +688,9 @@ MJB_HD inline void equality_rows(Ctx& c) {
     if (type == 0 || type == 1) {
       if (ei[MJB_EQI_SKIP]) continue;
       const int b0 = ei[MJB_EQI_B0], b1 = ei[MJB_EQI_B1];
-      double pos0[3], pos1[3], m0[9], m1[9], p[3];
-      ldn(m0, xmat, 9*b0, 9); ldn(m1, xmat, 9*b1, 9);
+      double pos0[3], pos1[3], m0[9], m1[9], p[3], bq0[4], bq1[4];
+      ldn(bq0, xquat, 4*b0, 4); ldn(bq1, xquat, 4*b1, 4);
+      quat2Mat(m0, bq0); quat2Mat(m1, bq1);            // == xmat of the two bodies
       mulMatVec3(pos0, m0, en + MJB_EQN_ANCHOR0); ldn(p, xpos, 3*b0, 3);
       pos0[0] += p[0]; pos0[1] += p[1]; pos0[2] += p[2];
       mulMatVec3(pos1, m1, en + MJB_EQN_ANCHOR1); ldn(p, xpos, 3*b1, 3);
@@ -723,8 +709,8 @@ MJB_HD inline void equality_rows(Ctx& c) {
       double quat[4] = {1, 0, 0, 0}, quat1[4] = {1, 0, 0, 0};
       const double ts = en[MJB_EQN_TORQUESCALE];
       if (type == 1) {
-        double q0[4], q1[4], t[4], q2[4];
-        ldn(q0, xquat, 4*b0, 4); ldn(q1, xquat, 4*b1, 4);
+        double t[4], q2[4];
+        const double* q0 = bq0; const double* q1 = bq1;
         mulQuat(quat, q0, en + MJB_EQN_Q0);            // q0 * relpose   (or body0 * site_quat0)
         if (ei[MJB_EQI_SITE]) { mulQuat(t, q1, en + MJB_EQN_Q1); }
         else { t[0] = q1[0]; t[1] = q1[1]; t[2] = q1[2]; t[3] = q1[3]; }
@@ -944,7 +930,7 @@ struct Con { double dist; double pos[3]; double frame[9]; };
 MJB_HD inline void rel_motion(Ctx& c, const double* carrier, int b1, int b2, const double* p,
                               double* lin, double* ang) {
   const int* rootid = MI(body_rootid);
-  double* com = SC(subtree_com);
+  double* com = SC(origin);
   double v1[6], v2[6], o1[3], o2[3], r[3], cr1[3], cr2[3];
   ldn(v1, carrier, 6*b1, 6); ldn(v2, carrier, 6*b2, 6);
   ldn(o1, com, 3*rootid[b1], 3); ldn(o2, com, 3*rootid[b2], 3);
@@ -1564,11 +1550,11 @@ MJB_HD inline int contact_scan(Ctx& c) {
     }
     if (pass) { bits |= 1u << (ci & 31); total++; }
     if ((ci & 31) == 31 || ci == ncand - 1) {
-      c.isc[(size_t)(MJB_ISC_MASK + (ci >> 5)) * c.NS] = (int)bits;
+      c.isc[(size_t)(MJB_ISC_MASK + (ci >> 5)) * MJB_LS] = (int)bits;
       bits = 0;
     }
   }
-  c.isc[(size_t)MJB_ISC_NSURV * c.NS] = total;
+  c.isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
   return total;
 }
 
@@ -1576,14 +1562,14 @@ MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, i
   const mjbHdr& H = *c.H;
   const int nwords = (H.ncand + 31) >> 5;
   int w = 0;
-  unsigned bits = (valid && nwords > 0) ? (unsigned)c.isc[(size_t)MJB_ISC_MASK * c.NS] : 0u;
+  unsigned bits = (valid && nwords > 0) ? (unsigned)c.isc[(size_t)MJB_ISC_MASK * MJB_LS] : 0u;
   while (true) {
     int cnt = 0;
     if (valid) {
       while (cnt < cap) {
         while (bits == 0 && w + 1 < nwords) {
           w++;
-          bits = (unsigned)c.isc[(size_t)(MJB_ISC_MASK + w) * c.NS];
+          bits = (unsigned)c.isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
         }
         if (bits == 0) break;
 #if defined(__CUDA_ARCH__)
@@ -1783,10 +1769,8 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
   c.status = 0;
   check_inputs(c);
-  kinematics(c);
-  com_pos(c);
+  forward_sweep(c);
   tendon_fixed(c);
-  com_vel_rne_forward(c);
   passive(c);
   {
     double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);

@@ -585,6 +585,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       const int p = m->body_parentid[b];
       flags[p] |= 1;
       if (!seen[p]) { flags[b] |= 2; seen[p] = 1; }
+      if (b != p + 1) flags[p] |= 4;
     }
     pushInts(MJB_I_body_tree_flags, flags.data(), flags.size());
   }
@@ -601,13 +602,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 
   // scratch layout
   {
-    const int nb = m->nbody, nj = m->njnt, ng = m->ngeom, nt = m->ntendon;
+    const int nb = m->nbody, ng = m->ngeom, nt = m->ntendon;
     int sizes[MJB_SC_COUNT];
-    sizes[MJB_SC_xpos] = 3*nb; sizes[MJB_SC_xquat] = 4*nb; sizes[MJB_SC_xmat] = 9*nb;
-    sizes[MJB_SC_xipos] = 3*nb; sizes[MJB_SC_ximat] = 9*nb;
-    sizes[MJB_SC_xanchor] = 3*nj; sizes[MJB_SC_xaxis] = 3*nj;
+    sizes[MJB_SC_xpos] = 3*nb; sizes[MJB_SC_xquat] = 4*nb; sizes[MJB_SC_origin] = 3*nb;
     sizes[MJB_SC_geom_xpos] = 3*ng; sizes[MJB_SC_geom_xmat] = 9*ng;
-    sizes[MJB_SC_subtree_com] = 3*nb; sizes[MJB_SC_mass_subtree] = nb;
     sizes[MJB_SC_cinert] = 10*nb; sizes[MJB_SC_cdof] = 6*nv; sizes[MJB_SC_cvel] = 6*nb;
     sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
     sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_cfrc_ext1] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
@@ -634,8 +632,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 
 const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
-    "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
-    "subtree_com", "mass_subtree", "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
+    "xpos", "xquat", "origin", "geom_xpos", "geom_xmat",
+    "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
     "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }

@@ -39,7 +39,6 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
     c.D = reinterpret_cast<const double*>(blob.data() + H->num_section);
     c.sc = scratch.data();
     c.isc = iscratch;
-    c.NS = 1;
     c.qpos = qpos_soa + s;
     c.qvel = qvel_soa + s;
     c.qacc = qacc_soa + s;

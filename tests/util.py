@@ -37,3 +37,36 @@ def qfrc_violations_scaled(got, ref, rtol=RTOL, atol=ATOL):
 def ref_available():
     from oracle import reflib
     return reflib.available()
+
+
+def to_com_frame(model, xpos, xquat, origin, vec, per):
+    """Re-express motion vectors [ang, lin] given about the engine's tree origin (the
+    position of the tree's root body before its joints) about the reference's frame origin, the
+    centre of mass of the kinematic tree (subtree_com[body_rootid], engine_core_smooth.c:183-270):
+        lin_com = lin_O + ang x (com - O).
+    xpos [n, nbody, 3], xquat [n, nbody, 4], origin [n, nbody, 3] (valid at root bodies),
+    vec [n, k, 6] with k bodies (per='body') or dofs (per='dof')."""
+    mass = model.array("body_mass").ravel()
+    ipos = model.array("body_ipos").reshape(-1, 3)
+    rootid = model.array("body_rootid").ravel()
+    q = xquat
+    w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    R = np.stack([1 - 2*(y*y + z*z), 2*(x*y - w*z), 2*(x*z + w*y),
+                  2*(x*y + w*z), 1 - 2*(x*x + z*z), 2*(y*z - w*x),
+                  2*(x*z - w*y), 2*(y*z + w*x), 1 - 2*(x*x + y*y)], axis=-1).reshape(q.shape[:-1] + (3, 3))
+    xipos = xpos + np.einsum("nbij,bj->nbi", R, ipos)
+    nbody = mass.shape[0]
+    com = np.zeros_like(xpos)
+    for r in np.unique(rootid):
+        sel = rootid == r
+        m = mass[sel]
+        if m.sum() < 1e-15:
+            com[:, sel] = xipos[:, [r]]
+        else:
+            com[:, sel] = (xipos[:, sel] * m[None, :, None]).sum(axis=1, keepdims=True) / m.sum()
+    shift = com - origin[:, rootid]                  # [n, nbody, 3]
+    if per == "dof":
+        shift = shift[:, model.array("dof_bodyid").ravel()]
+    out = vec.copy()
+    out[..., 3:] += np.cross(vec[..., :3], shift)
+    return out
