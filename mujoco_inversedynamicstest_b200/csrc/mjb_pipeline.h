@@ -483,39 +483,50 @@ MJB_HD inline void passive(Ctx& c) {
   const mjbHdr& H = *c.H;
   double* qp = SC(qfrc_passive);
   const int nv = H.nv;
-  for (int i = 0; i < nv; i++) AT(qp, i) = 0;
-  if (H.disableflags & MJB_DSBL_PASSIVE) return;
+  if (H.disableflags & MJB_DSBL_PASSIVE) {
+    for (int i = 0; i < nv; i++) AT(qp, i) = 0;
+    return;
+  }
 
+  // qfrc_passive = qfrc_spring + qfrc_damper, one joint at a time (every dof belongs to exactly
+  // one joint), each entry written once
   const int* jnt_type = MI(jnt_type);
   const int* jnt_qposadr = MI(jnt_qposadr);
   const int* jnt_dofadr = MI(jnt_dofadr);
   const double* jnt_stiffness = MD(jnt_stiffness);
   const double* qpos_spring = MD(qpos_spring);
+  const double* dof_damping = MD(dof_damping);
   for (int i = 0; i < H.njnt; i++) {
     const double k = jnt_stiffness[i];
-    if (k == 0) continue;
-    int padr = jnt_qposadr[i], dadr = jnt_dofadr[i];
+    int padr = jnt_qposadr[i];
+    const int dadr = jnt_dofadr[i];
     const int jt = jnt_type[i];
+    double spring[6] = {0, 0, 0, 0, 0, 0};
+    int nd = 1, r0 = 0;
     if (jt == MJB_JNT_FREE) {
-      for (int r = 0; r < 3; r++) AT(qp, dadr + r) = -k*(QPOS(padr + r) - qpos_spring[padr + r]);
-      dadr += 3; padr += 3;
+      nd = 6; r0 = 3;
+      if (k != 0) for (int r = 0; r < 3; r++) spring[r] = -k*(QPOS(padr + r) - qpos_spring[padr + r]);
+      padr += 3;
+    } else if (jt == MJB_JNT_BALL) {
+      nd = 3;
     }
-    if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
-      double quat[4] = {QPOS(padr), QPOS(padr+1), QPOS(padr+2), QPOS(padr+3)};
-      double dif[3];
-      normalize4(quat);
-      subQuat(dif, quat, qpos_spring + padr);
-      for (int r = 0; r < 3; r++) AT(qp, dadr + r) = -k*dif[r];
-    } else {
-      AT(qp, dadr) = -k*(QPOS(padr) - qpos_spring[padr]);
+    if (k != 0) {
+      if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
+        double quat[4] = {QPOS(padr), QPOS(padr+1), QPOS(padr+2), QPOS(padr+3)};
+        double dif[3];
+        normalize4(quat);
+        subQuat(dif, quat, qpos_spring + padr);
+        for (int r = 0; r < 3; r++) spring[r0 + r] = -k*dif[r];
+      } else {
+        spring[0] = -k*(QPOS(padr) - qpos_spring[padr]);
+      }
     }
-  }
-
-  // qfrc_passive = qfrc_spring + qfrc_damper
-  const double* dof_damping = MD(dof_damping);
-  for (int i = 0; i < nv; i++) {
-    const double dmp = dof_damping[i];
-    if (dmp != 0) AT(qp, i) += -dmp*QVEL(i);
+    for (int r = 0; r < nd; r++) {
+      const double dmp = dof_damping[dadr + r];
+      double val = spring[r];
+      if (dmp != 0) val += -dmp*QVEL(dadr + r);
+      AT(qp, dadr + r) = val;
+    }
   }
 
   if (H.ntendon) {
@@ -653,10 +664,11 @@ MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, c
   ldn(o, com, 3*rootid[b], 3);
   r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
   cross3(cr, r, F);
-  for (int k = 0; k < 3; k++) {
-    AT(fe, 6*b + k) += cr[k] + T[k];
-    AT(fe, 6*b + 3 + k) += F[k];
-  }
+  // one batched read-modify-write (loads first, stores last): a single memory round trip
+  double w[6];
+  ldn(w, fe, 6*b, 6);
+  for (int k = 0; k < 3; k++) { w[k] += cr[k] + T[k]; w[3 + k] += F[k]; }
+  stn(fe, 6*b, w, 6);
 }
 
 // 0.5 * vec( quat1 * (0, a) * quat )   (engine_core_constraint.c:617-635)
@@ -1596,40 +1608,43 @@ MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, i
 // separately and projected with the same cdof, which is J'*efc_force for the point constraints.
 MJB_HD inline void rne_and_output(Ctx& c) {
   const mjbHdr& H = *c.H;
-  const int nbody = H.nbody, nv = H.nv;
-  double* cfrc = SC(cfrc); double* fext = SC(cfrc_ext);
+  const int nbody = H.nbody;
+  double* cfrc = SC(cfrc); double* fext = SC(cfrc_ext); double* fext1 = SC(cfrc_ext1);
   double* cdof = SC(cdof);
   const int* body_parentid = MI(body_parentid);
-
-  // backward accumulation of inertial forces and of constraint wrenches ('+' minus '-' side)
-  double* fext1 = SC(cfrc_ext1);
-  for (int b = nbody - 1; b > 0; b--) {
-    const int p = body_parentid[b];
-    double w[6];
-    for (int k = 0; k < 6; k++) { w[k] = AT(fext, 6*b + k) - AT(fext1, 6*b + k); AT(fext, 6*b + k) = w[k]; }
-    if (p) {
-      for (int k = 0; k < 6; k++) {
-        AT(cfrc, 6*p + k) += AT(cfrc, 6*b + k);
-        AT(fext1, 6*p + k) -= w[k];      // parent's net = own '+' - own '-' + children's nets
-      }
-    }
-  }
-
-  const int* dof_bodyid = MI(dof_bodyid);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
   const double* armature = MD(dof_armature);
   double* qc = SC(qfrc_c); double* qp = SC(qfrc_passive);
   const size_t N = (size_t)c.N;
-  for (int i = 0; i < nv; i++) {
-    const int b = dof_bodyid[i];
-    double cd[6], f[6], w[6];
-    ldn(cd, cdof, 6*i, 6); ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6);
-    const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
-    const double passive_i = AT(qp, i);
-    double res = dot6(cd, f);
-    res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
-    c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
-    if (c.out.qfrc_constraint) c.out.qfrc_constraint[(size_t)i*N + c.s] = qfrc_constraint;
-    if (c.out.qfrc_passive) c.out.qfrc_passive[(size_t)i*N + c.s] = passive_i;
+
+  // Leaves-to-root: when body b is visited all its children have already pushed their sums into
+  // it, so its inertial force f and net constraint wrench w ('+' minus '-' side) are final: push
+  // them to the parent and project them on the body's own dofs right away. Every body does its
+  // loads first and its stores last (one memory round trip per body).
+  for (int b = nbody - 1; b > 0; b--) {
+    const int p = body_parentid[b];
+    double f[6], w[6], w1[6], pf[6], pw1[6];
+    ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
+    if (p) { ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6); }
+    for (int k = 0; k < 6; k++) w[k] -= w1[k];
+    const int d0 = body_dofadr[b], dn = body_dofnum[b];
+    for (int i = d0; i < d0 + dn; i++) {
+      double cd[6];
+      ldn(cd, cdof, 6*i, 6);
+      const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
+      const double passive_i = AT(qp, i);
+      double res = dot6(cd, f);
+      res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
+      c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
+      if (c.out.qfrc_constraint) c.out.qfrc_constraint[(size_t)i*N + c.s] = qfrc_constraint;
+      if (c.out.qfrc_passive) c.out.qfrc_passive[(size_t)i*N + c.s] = passive_i;
+    }
+    if (p) {
+      // parent's net = own '+' - own '-' + children's nets: children are folded into its '-' side
+      for (int k = 0; k < 6; k++) { pf[k] += f[k]; pw1[k] -= w[k]; }
+      stn(cfrc, 6*p, pf, 6); stn(fext1, 6*p, pw1, 6);
+    }
   }
 }
 
@@ -1747,8 +1762,11 @@ MJB_HD inline void inertia(Ctx& c) {
         stn(crb, 10*p, pc, 10);
         stn(ia, 21*p, pA, 21);
       } else {
-        for (int j = 0; j < 10; j++) AT(crb, 10*p + j) += cr[j];
-        for (int j = 0; j < 21; j++) AT(ia, 21*p + j) += A[j];
+        double pc[10], pA[21];
+        ldn(pc, crb, 10*p, 10); ldn(pA, ia, 21*p, 21);
+        for (int j = 0; j < 10; j++) pc[j] += cr[j];
+        for (int j = 0; j < 21; j++) pA[j] += A[j];
+        stn(crb, 10*p, pc, 10); stn(ia, 21*p, pA, 21);
       }
     }
   }

@@ -1,0 +1,8 @@
+#!/bin/bash
+# run on the GPU box: parity tests, a bench line, and the ncu launch list of one bench step
+tag=${1:-run}
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/t_$tag.log
+python bench.py --no-cpu-baseline > gpurun_out/b_$tag.json 2> gpurun_out/b_$tag.err
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread \
+  --clock-control none -c 40 --csv --log-file gpurun_out/l_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$tag.log 2>&1
+tail -3 gpurun_out/t_$tag.log; cut -c1-200 gpurun_out/b_$tag.json
