@@ -20,7 +20,7 @@
 #define MJB_CTAS_SMOOTH 4
 #endif
 #ifndef MJB_CTAS_INERTIA
-#define MJB_CTAS_INERTIA 4
+#define MJB_CTAS_INERTIA 3
 #endif
 #ifndef MJB_CTAS_BACKWARD
 #define MJB_CTAS_BACKWARD 4

@@ -90,6 +90,10 @@ struct Ctx {
 #define MJB_LS 1
 #endif
 
+#ifndef MJB_ANC
+#define MJB_ANC 2
+#endif
+
 #define MI(name) (c.I + c.H->ioff[MJB_I_##name])
 #define MD(name) (c.D + c.H->noff[MJB_N_##name])
 #define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * MJB_LS)
@@ -1622,12 +1626,18 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   // it, so its inertial force f and net constraint wrench w ('+' minus '-' side) are final: push
   // them to the parent and project them on the body's own dofs right away. Every body does its
   // loads first and its stores last (one memory round trip per body).
+  int carry_for = -1;
+  double cf[6], cw[6];
   for (int b = nbody - 1; b > 0; b--) {
     const int p = body_parentid[b];
+    const bool push = p && b != p + 1;       // child p+1 hands over in registers (depth-first order)
     double f[6], w[6], w1[6], pf[6], pw1[6];
     ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
-    if (p) { ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6); }
+    if (push) { ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6); }
     for (int k = 0; k < 6; k++) w[k] -= w1[k];
+    if (carry_for == b) {
+      for (int k = 0; k < 6; k++) { f[k] += cf[k]; w[k] += cw[k]; }
+    }
     const int d0 = body_dofadr[b], dn = body_dofnum[b];
     for (int i = d0; i < d0 + dn; i++) {
       double cd[6];
@@ -1640,10 +1650,13 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       if (c.out.qfrc_constraint) c.out.qfrc_constraint[(size_t)i*N + c.s] = qfrc_constraint;
       if (c.out.qfrc_passive) c.out.qfrc_passive[(size_t)i*N + c.s] = passive_i;
     }
-    if (p) {
+    if (push) {
       // parent's net = own '+' - own '-' + children's nets: children are folded into its '-' side
       for (int k = 0; k < 6; k++) { pf[k] += f[k]; pw1[k] -= w[k]; }
       stn(cfrc, 6*p, pf, 6); stn(fext1, 6*p, pw1, 6);
+    } else if (p) {
+      for (int k = 0; k < 6; k++) { cf[k] = f[k]; cw[k] = w[k]; }
+      carry_for = p;
     }
   }
 }
@@ -1683,6 +1696,16 @@ MJB_DI void inert_to_sym6(double* A, const double* i) {
   A[20] = i[9];
 }
 
+// A += the symmetric 6x6 of a 10-number rigid inertia (same layout as inert_to_sym6)
+MJB_DI void inert_add_sym6(double* A, const double* i) {
+  A[0] += i[0];  A[1] += i[3];  A[2] += i[4];  A[4] -= i[8]; A[5] += i[7];
+  A[6] += i[1];  A[7] += i[5];  A[8] += i[8];  A[10] -= i[6];
+  A[11] += i[2]; A[12] -= i[7]; A[13] += i[6];
+  A[15] += i[9];
+  A[18] += i[9];
+  A[20] += i[9];
+}
+
 MJB_HD inline void inertia(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
@@ -1699,19 +1722,31 @@ MJB_HD inline void inertia(Ctx& c) {
   const size_t N = (size_t)c.N;
   double* qM = c.out.qM + c.s; double* qLD = c.out.qLD + c.s; double* qLDiagInv = c.out.qLDiagInv + c.s;
 
-  // A parent's accumulators are INITIALISED (own rigid inertia + child) by its highest-index
-  // child, the first one visited, and added to by the others: the same summation order as the
-  // reference's "crb = cinert; add children backwards", without a clearing pass over the scratch.
-  const int* tree_flags = MI(body_tree_flags);   // bit0: has children, bit1: first visited child
+  // Children are folded into their parent leaves-to-root. Bodies are in depth-first order, so the
+  // child visited last before a body p is p+1: it hands its sums over in registers (carry). Only
+  // the other children go through the parent's scratch accumulators, the first of them (highest
+  // index, bit1) by a plain store, the rest by a batched read-modify-write; no clearing pass.
+  const int* tree_flags = MI(body_tree_flags);   // bit1: highest-index child, bit2: has a child != body+1
+  bool carried = false;          // cr, A hold the sums handed over by body b+1
+  double cr[10], A[21];
   for (int b = nbody - 1; b > 0; b--) {
-    double cr[10], A[21];
     const int flags = tree_flags[b];
-    if (flags & 1) {
-      ldn(cr, crb, 10*b, 10);
-      ldn(A, ia, 21*b, 21);
-    } else {
-      ldn(cr, cinert, 10*b, 10);
-      inert_to_sym6(A, cr);
+    {
+      double ci[10];
+      ldn(ci, cinert, 10*b, 10);
+      if (carried) {
+        for (int j = 0; j < 10; j++) cr[j] += ci[j];
+        inert_add_sym6(A, ci);
+      } else {
+        for (int j = 0; j < 10; j++) cr[j] = ci[j];
+        inert_to_sym6(A, ci);
+      }
+    }
+    if (flags & 4) {
+      double pc[10], pA[21];
+      ldn(pc, crb, 10*b, 10); ldn(pA, ia, 21*b, 21);
+      for (int j = 0; j < 10; j++) cr[j] += pc[j];
+      for (int j = 0; j < 21; j++) A[j] += pA[j];
     }
     const int adr0 = body_dofadr[b], num = body_dofnum[b];
     for (int k = adr0 + num - 1; k >= adr0; k--) {
@@ -1737,12 +1772,24 @@ MJB_HD inline void inertia(Ctx& c) {
       qM[(size_t)madr*N] = Mkk;
       qLD[(size_t)diag*N] = D;
       qLDiagInv[(size_t)k*N] = invD;
+      // ancestor walk, MJB_ANC ancestors at a time: their cdofs are loaded together before any of
+      // the results is stored (one memory round trip per group instead of one per ancestor)
       int t = 1;
-      for (int i = dof_parentid[k]; i >= 0; i = dof_parentid[i], t++) {
-        double Si[6];
-        ldn(Si, cdof, 6*i, 6);
-        qM[(size_t)(madr + t)*N] = dot6(Si, buf);
-        qLD[(size_t)(diag - t)*N] = dot6(Si, U) * invD;
+      for (int i = dof_parentid[k]; i >= 0;) {
+        double Si[MJB_ANC][6];
+        int n = 0;
+#pragma unroll
+        for (int g = 0; g < MJB_ANC; g++) {
+          if (i >= 0) { ldn(Si[g], cdof, 6*i, 6); i = dof_parentid[i]; n = g + 1; }
+        }
+#pragma unroll
+        for (int g = 0; g < MJB_ANC; g++) {
+          if (g < n) {
+            qM[(size_t)(madr + t + g)*N] = dot6(Si[g], buf);
+            qLD[(size_t)(diag - t - g)*N] = dot6(Si[g], U) * invD;
+          }
+        }
+        t += n;
       }
       // IA -= U U' / D
       int e = 0;
@@ -1753,14 +1800,14 @@ MJB_HD inline void inertia(Ctx& c) {
     }
     const int p = body_parentid[b];
     if (p > 0) {
+      if (b == p + 1) {
+        carried = true;          // cr, A stay in registers for the parent, which is visited next
+        continue;
+      }
+      carried = false;
       if (flags & 2) {
-        double pc[10], pA[21];
-        ldn(pc, cinert, 10*p, 10);
-        inert_to_sym6(pA, pc);
-        for (int j = 0; j < 10; j++) pc[j] += cr[j];
-        for (int j = 0; j < 21; j++) pA[j] += A[j];
-        stn(crb, 10*p, pc, 10);
-        stn(ia, 21*p, pA, 21);
+        stn(crb, 10*p, cr, 10);
+        stn(ia, 21*p, A, 21);
       } else {
         double pc[10], pA[21];
         ldn(pc, crb, 10*p, 10); ldn(pA, ia, 21*p, 21);
@@ -1768,6 +1815,8 @@ MJB_HD inline void inertia(Ctx& c) {
         for (int j = 0; j < 21; j++) pA[j] += A[j];
         stn(crb, 10*p, pc, 10); stn(ia, 21*p, pA, 21);
       }
+    } else {
+      carried = false;
     }
   }
 }
