@@ -15,9 +15,12 @@
 
 #include <cstdio>
 
-// resident CTAs per SM each phase kernel is compiled for (register budget = 65536 / (128 * CTAS))
+// resident CTAs per SM each phase kernel is compiled for (register budget = 65536 / (threads * CTAS)).
+// Measured on B200 (profiles/README.md): the smooth kernel is fastest WITHOUT register spills at low
+// occupancy -- one 256-thread CTA per SM, 246 registers -- because spilled values miss the L1 that the
+// streamed scratch rows keep flushing (2.99 ms vs 4.0 ms at 128 registers for 2^20 humanoid states).
 #ifndef MJB_CTAS_SMOOTH
-#define MJB_CTAS_SMOOTH 4
+#define MJB_CTAS_SMOOTH 1
 #endif
 #ifndef MJB_CTAS_INERTIA
 #define MJB_CTAS_INERTIA 3
@@ -97,6 +100,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned c
   c.njmax = a.njmax;
   c.out = a.out;
   c.ncon = c.ne = c.nf = c.nl = c.nefc = c.status = 0;
+  c.sm = nullptr;
 }
 
 __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long long local) {
@@ -111,14 +115,21 @@ __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long lon
   c.qacc = a.qacc + s;
 }
 
+// The smooth kernel runs with its own CTA size (MJB_SMOOTH_THREADS, = the stride MJB_SMS of the
+// per-thread carry slots): fewer, larger CTAs per SM mean fewer copies of the model blob in shared
+// memory and therefore more L1 for the streamed scratch rows.
+constexpr int kSmoothThreads = MJB_SMS;
+
 template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, MJB_CTAS_SMOOTH) smooth_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kSmoothThreads, MJB_CTAS_SMOOTH) smooth_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * kThreads) {
+  // per-thread carry slots of the forward sweep, after the model blob
+  c.sm = reinterpret_cast<double*>(smem + (kModelInSmem ? ((a.model_bytes + 127) & ~127) : 0)) + threadIdx.x;
+  for (long long i = (long long)blockIdx.x * kSmoothThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kSmoothThreads) {
     bind_state(c, a, i);
     phase_smooth(c);
   }
@@ -388,17 +399,22 @@ size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
   return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
 }
 
+size_t smooth_smem_bytes(int model_bytes, int model_in_smem) {
+  return (model_in_smem ? (size_t)((model_bytes + 127) & ~127) : 0) +
+         sizeof(double) * MJB_SM_SLOTS * kSmoothThreads;
+}
+
 template <typename K>
 static cudaError_t launch_phase(K kernel, const LaunchArgs& args, size_t smem, int ctas_per_sm,
-                                cudaStream_t stream) {
-  int grid = (args.chunk_n + kThreads - 1) / kThreads;
+                                cudaStream_t stream, int threads = kThreads) {
+  int grid = (args.chunk_n + threads - 1) / threads;
   const int cap = kSMs * ctas_per_sm;
   if (grid > cap) grid = cap;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kernel<<<grid, kThreads, smem, stream>>>(args);
+  kernel<<<grid, threads, smem, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -409,8 +425,9 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   const bool in_smem = args.model_in_smem != 0;
   const bool want_inertia = args.out.qM || args.out.qLD || args.out.qLDiagInv;
   cudaError_t e;
-  e = in_smem ? launch_phase(smooth_kernel<true>, args, smem, 8, stream)
-              : launch_phase(smooth_kernel<false>, args, 0, 8, stream);
+  const size_t ssmem = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
+  e = in_smem ? launch_phase(smooth_kernel<true>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
+              : launch_phase(smooth_kernel<false>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads);
   if (e != cudaSuccess) return e;
   ++*launches;
   if (want_inertia) {

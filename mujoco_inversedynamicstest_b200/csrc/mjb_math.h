@@ -92,8 +92,13 @@ MJB_DI void mulMatVec3(double* res, const double* m, const double* v) {  // engi
   res[0] = t0; res[1] = t1; res[2] = t2;
 }
 
-// engine_util_spatial.c:119
-MJB_DI void quat2Vel(double* res, const double* q, double dt) {
+// engine_util_spatial.c:119 (out of line: atan2 is large and the callers are cold)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ inline
+#else
+static inline
+#endif
+void quat2Vel(double* res, const double* q, double dt) {
   double axis[3] = {q[1], q[2], q[3]};
   double sin_a_2 = normalize3(axis);
   double speed = 2 * atan2(sin_a_2, q[0]);

@@ -64,6 +64,7 @@
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
+  X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored) */
 
@@ -242,6 +243,9 @@ typedef struct mjbHdr_ {
   int32_t has_fixed_tendon_only;
   int32_t nscratch;         // doubles of scratch per state
   int32_t max_pair_contacts; // most contacts one candidate pair can yield (1, 2 or 4)
+  // constraint-row counts that depend only on the model: equality rows, friction-loss rows of
+  // dofs, friction-loss rows in total (dofs then tendons)
+  int32_t ne_rows, nf_dof_rows, nf_rows, pad_rows;
   double timestep, impratio;
   double gravity[3];
   double pad1;

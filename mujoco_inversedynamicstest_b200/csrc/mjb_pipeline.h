@@ -24,8 +24,13 @@
 
 #if defined(__CUDACC__)
 #define MJB_HD __host__ __device__
+// rarely taken, code-heavy leaf paths (pow, atan2) are kept out of line to keep the phase kernels
+// small; only functions of scalars qualify (an out-of-line call taking Ctx& would force the whole
+// context into local memory: measured +45% on the smooth kernel)
+#define MJB_COLD __host__ __device__ __noinline__
 #else
 #define MJB_HD
+#define MJB_COLD
 #endif
 
 // warp votes used to keep compaction loops warp-uniform; identity in the single-lane host build
@@ -69,6 +74,7 @@ struct Ctx {
   const mjbHdr* H;
   const int* I;         // int section of the model blob
   const double* D;      // double section of the model blob
+  double* sm;           // per-thread on-chip slots (shared memory, stride MJB_SMS): forward-sweep carry
   double* sc;           // double scratch [nscratch][NS], already offset to this state
   int* isc;             // int scratch [MJB_ISC_COUNT][NS], already offset to this state
   const double* qpos;   // already offset to this state
@@ -94,6 +100,17 @@ struct Ctx {
 #define MJB_ANC 2
 #endif
 
+// per-thread shared-memory slots of the forward sweep (parent carry): stride between slots
+#if defined(__CUDACC__)
+#ifndef MJB_SMOOTH_THREADS
+#define MJB_SMOOTH_THREADS 256
+#endif
+#define MJB_SMS MJB_SMOOTH_THREADS
+#else
+#define MJB_SMS 1
+#endif
+#define MJB_SM_SLOTS 25   // P[3] Q[4] V[6] A[6] AL[6]
+
 #define MI(name) (c.I + c.H->ioff[MJB_I_##name])
 #define MD(name) (c.D + c.H->noff[MJB_N_##name])
 #define SC(name) (c.sc + (size_t)c.H->scoff[MJB_SC_##name] * MJB_LS)
@@ -108,6 +125,25 @@ MJB_DI void ldn_(double* dst, const double* p, int first, int n, size_t stride) 
 MJB_DI void stn_(double* p, int first, const double* src, int n, size_t stride) {
   for (int k = 0; k < n; k++) p[(size_t)(first + k) * stride] = src[k];
 }
+// Stores of rows that only a LATER kernel reads (cdof, cinert, cfrc, geom poses ...): evict-first
+// (st.global.cs) so that they do not push the register-spill lines and the inputs out of L1.
+// MJB_STREAM_HINTS: 0 off, 1 those rows, 2 every store of the forward sweep.
+#ifndef MJB_STREAM_HINTS
+#define MJB_STREAM_HINTS 1
+#endif
+MJB_DI void stn_stream_(double* p, int first, const double* src, int n, size_t stride) {
+#if defined(__CUDA_ARCH__) && MJB_STREAM_HINTS
+  for (int k = 0; k < n; k++) __stcs(p + (size_t)(first + k) * stride, src[k]);
+#else
+  for (int k = 0; k < n; k++) p[(size_t)(first + k) * stride] = src[k];
+#endif
+}
+#define sts(p, first, src, n) stn_stream_(p, first, src, n, MJB_LS)
+#if MJB_STREAM_HINTS >= 2
+#define stc(p, first, src, n) stn_stream_(p, first, src, n, MJB_LS)
+#else
+#define stc(p, first, src, n) stn_(p, first, src, n, MJB_LS)
+#endif
 #define ldn(dst, p, first, n) ldn_(dst, p, first, n, MJB_LS)
 #define stn(p, first, src, n) stn_(p, first, src, n, MJB_LS)
 
@@ -132,326 +168,6 @@ MJB_DI double dot6(const double* a, const double* b) {
   double res = (a[0]*b[0] + a[2]*b[2]) + (a[1]*b[1] + a[3]*b[3]);
   res += a[4]*b[4] + a[5]*b[5];
   return res;
-}
-
-// ------------------------------------------------------------------------------------------
-// mj_checkPos / mj_checkVel / mj_checkAcc (engine_forward.c:53-102): flag, do not reset
-MJB_HD inline void check_inputs(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  for (int i = 0; i < H.nq; i++) {
-    double v = QPOS(i);
-    if (!(v == v) || v > MJB_MAXVAL || v < -MJB_MAXVAL) c.status |= kStatusBadQpos;
-  }
-  for (int i = 0; i < H.nv; i++) {
-    double v = QVEL(i), a = QACC(i);
-    if (!(v == v) || v > MJB_MAXVAL || v < -MJB_MAXVAL) c.status |= kStatusBadQvel;
-    if (!(a == a) || a > MJB_MAXVAL || a < -MJB_MAXVAL) c.status |= kStatusBadQacc;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Forward sweep: ONE root-to-leaves pass that does, per body, the work the reference spreads over
-//   mj_kinematics  (engine_core_smooth.c:38-178, mj_local2Global engine_support.c:1565)
-//   mj_comPos      (:183-270; cinert via mju_inertCom, cdof via mju_dofCom)
-//   mj_comVel      (:1833-1896)
-//   mj_rne forward (:1969-2005, flg_acc = 1)
-// so that a body's pose, joint axes, velocity and acceleration never leave registers between those
-// stages; only what later phases read is written to the per-state scratch.
-//
-// Frame of the spatial quantities. The reference expresses cdof/cvel/cacc/cinert/cfrc about the
-// centre of mass of the kinematic tree (subtree_com[body_rootid]), which is known only after a
-// full kinematics pass. Spatial algebra holds about ANY fixed world point, and qfrc_inverse, qM,
-// qLD, J*v, J'*f are independent of it, so the sweep uses the tree origin
-//     O_tree = position of the tree's root body before its joints act
-//            = qpos[0:3] of a free root, body_pos of a jointed or welded root
-// which is known when the root is entered (|x - O| stays of the order of the tree's size, like the
-// reference's com-based offsets). Bodies of one tree are contiguous in the body order, so O is
-// carried in registers; it is also stored per root body for the constraint phases.
-//
-// Carry. Bodies are in depth-first order, so a body's parent is very often the body just
-// processed: its pose/velocity/acceleration are then still in registers (P, Q, V, A, AL) and are
-// read from scratch only when the parent is an earlier body (warp-uniform test).
-//
-//   cvel      spatial velocity about O                              (contact rows, cfrc)
-//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
-//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
-//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                   (backward pass)
-// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
-
-// pose of the geoms of body b from the body's frames held in registers (mj_local2Global)
-MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* quat, const double* mat,
-                              const double* ip, const double* im) {
-  const int* body_geomadr = MI(body_geomadr);
-  const int* body_geomnum = MI(body_geomnum);
-  const int* geom_sameframe = MI(geom_sameframe);
-  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
-  const int g0 = body_geomadr[b], gn = body_geomnum[b];
-  for (int g = g0; g < g0 + gn; g++) {
-    const int sf = geom_sameframe[g];
-    double gp[3], gm[9];
-    if (sf == MJB_SAMEFRAME_BODY) {
-      gp[0] = pos[0]; gp[1] = pos[1]; gp[2] = pos[2];
-    } else if (sf == MJB_SAMEFRAME_INERTIA) {
-      gp[0] = ip[0]; gp[1] = ip[1]; gp[2] = ip[2];
-    } else {
-      mulMatVec3(gp, mat, geom_pos + 3*g);
-      gp[0] += pos[0]; gp[1] += pos[1]; gp[2] += pos[2];
-    }
-    if (sf == MJB_SAMEFRAME_NONE) {
-      double tq[4];
-      mulQuat(tq, quat, geom_quat + 4*g);
-      quat2Mat(gm, tq);
-    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
-      for (int k = 0; k < 9; k++) gm[k] = mat[k];
-    } else {
-      for (int k = 0; k < 9; k++) gm[k] = im[k];
-    }
-    stn(gxpos, 3*g, gp, 3);
-    stn(gxmat, 9*g, gm, 9);
-  }
-}
-
-MJB_HD inline void forward_sweep(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  const int nbody = H.nbody;
-  double* xpos = SC(xpos); double* xquat = SC(xquat); double* org = SC(origin);
-  double* cvel = SC(cvel); double* cal = SC(cacc_lin); double* cacc = SC(cacc);
-  double* cfrc = SC(cfrc); double* cinert = SC(cinert); double* cdof = SC(cdof);
-  const int* body_parentid = MI(body_parentid);
-  const int* body_jntadr = MI(body_jntadr);
-  const int* body_jntnum = MI(body_jntnum);
-  const int* body_dofadr = MI(body_dofadr);
-  const int* body_dofnum = MI(body_dofnum);
-  const int* body_mocapid = MI(body_mocapid);
-  const int* body_sameframe = MI(body_sameframe);
-  const int* tree_flags = MI(body_tree_flags);
-  const int* jnt_type = MI(jnt_type);
-  const int* jnt_qposadr = MI(jnt_qposadr);
-  const int* jnt_dofadr = MI(jnt_dofadr);
-  const int* dof_jntid = MI(dof_jntid);
-  const double* body_pos = MD(body_pos); const double* body_quat = MD(body_quat);
-  const double* body_ipos = MD(body_ipos); const double* body_iquat = MD(body_iquat);
-  const double* body_mass = MD(body_mass); const double* body_inertia = MD(body_inertia);
-  const double* jnt_pos = MD(jnt_pos); const double* jnt_axis = MD(jnt_axis);
-  const double* qpos0 = MD(qpos0);
-
-  // world body: identity pose, zero velocity, acceleration = -gravity (mj_rne :1979-1982)
-  double P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
-  double V[6] = {0, 0, 0, 0, 0, 0}, AL[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
-  double O[3] = {0, 0, 0};
-  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
-    A[3] = -H.gravity[0]; A[4] = -H.gravity[1]; A[5] = -H.gravity[2];
-  }
-  stn(xpos, 0, P, 3); stn(xquat, 0, Q, 4); stn(org, 0, O, 3);
-  stn(cvel, 0, V, 6); stn(cal, 0, AL, 6); stn(cacc, 0, A, 6);
-  {
-    const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    body_geoms(c, 0, P, Q, I9, P, I9);
-  }
-  int carry = 0;          // body whose P, Q, V, A, AL are in registers
-
-  for (int b = 1; b < nbody; b++) {
-    const int pid = body_parentid[b];
-    const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
-    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
-    if (pid != carry) {
-      ldn(P, xpos, 3*pid, 3); ldn(Q, xquat, 4*pid, 4);
-      ldn(V, cvel, 6*pid, 6); ldn(A, cacc, 6*pid, 6); ldn(AL, cal, 6*pid, 6);
-    }
-    double pos[3], quat[4];
-    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
-    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
-    const bool isfree = jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE;
-    bool has_ball = false;
-
-    if (isfree) {
-      const int qadr = jnt_qposadr[jntadr];
-      for (int k = 0; k < 3; k++) pos[k] = QPOS(qadr + k);
-      for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + 3 + k);
-      normalize4(quat);
-      if (pid == 0) { O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2]; stn(org, 3*b, O, 3); }
-    } else {
-      double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
-      if (body_mocapid[b] >= 0) normalize4(bquat);   // mocap pose = model pose (mj_resetData default)
-      if (pid) {
-        double pm[9];
-        quat2Mat(pm, Q);                 // == the parent's xmat (same function of the same xquat)
-        mulMatVec3(pos, pm, body_pos + 3*b);
-        pos[0] += P[0]; pos[1] += P[1]; pos[2] += P[2];
-        mulQuat(quat, Q, bquat);
-      } else {
-        for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
-        for (int k = 0; k < 4; k++) quat[k] = bquat[k];
-        O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
-        stn(org, 3*b, O, 3);
-      }
-      for (int j = 0; j < jntnum; j++) has_ball = has_ball || jnt_type[jntadr + j] == MJB_JNT_BALL;
-
-      for (int j = 0; j < jntnum; j++) {
-        const int jid = jntadr + j;
-        const int qadr = jnt_qposadr[jid];
-        const int dadr = jnt_dofadr[jid];
-        const int jtype = jnt_type[jid];
-        double ax[3], anc[3], cd[6];
-        rotVecQuat(ax, jnt_axis + 3*jid, quat);
-        rotVecQuat(anc, jnt_pos + 3*jid, quat);
-        anc[0] += pos[0]; anc[1] += pos[1]; anc[2] += pos[2];
-        const double off[3] = {O[0] - anc[0], O[1] - anc[1], O[2] - anc[2]};
-
-        if (jtype == MJB_JNT_SLIDE) {
-          const double q = QPOS(qadr) - qpos0[qadr];
-          pos[0] += ax[0]*q; pos[1] += ax[1]*q; pos[2] += ax[2]*q;
-          cd[0] = 0; cd[1] = 0; cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2];
-        } else {
-          double qloc[4];
-          if (jtype == MJB_JNT_BALL) {
-            for (int k = 0; k < 4; k++) qloc[k] = QPOS(qadr + k);
-            normalize4(qloc);
-            // cdof of a ball joint uses the body's FINAL orientation (mj_comPos :243-252): keep
-            // the anchor offset in the dof's slots until the pose is complete
-            stn(cdof, 6*dadr, off, 3);
-          } else {
-            // mju_axisAngle2Quat (engine_util_spatial.c:97)
-            const double angle = QPOS(qadr) - qpos0[qadr];
-            double sn, cs;
-            sincos(angle*0.5, &sn, &cs);
-            qloc[0] = cs;
-            qloc[1] = jnt_axis[3*jid]*sn; qloc[2] = jnt_axis[3*jid+1]*sn; qloc[3] = jnt_axis[3*jid+2]*sn;
-            cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
-            cross3(cd + 3, ax, off);
-          }
-          mulQuat(quat, quat, qloc);
-          double vec[3];
-          rotVecQuat(vec, jnt_pos + 3*jid, quat);
-          pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
-        }
-        if (jtype != MJB_JNT_BALL) {
-          stn(cdof, 6*dadr, cd, 6);
-          if (!has_ball) {
-            // mj_comVel / mj_rne for a scalar dof, fused: cdof_dot uses the velocity so far
-            double dd[6];
-            crossMotion(dd, V, cd);
-            const double qv = QVEL(dadr), qa = QACC(dadr);
-            for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
-          }
-        }
-      }
-    }
-
-    normalize4(quat);
-    double mat[9];
-    quat2Mat(mat, quat);
-    stn(xquat, 4*b, quat, 4);
-    stn(xpos, 3*b, pos, 3);
-
-    if (isfree) {
-      // translational dofs: cdof = [0, e_r], cdof_dot = 0
-      for (int r = 0; r < 3; r++) {
-        double cd[6] = {0, 0, 0, r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0};
-        stn(cdof, 6*(bda + r), cd, 6);
-        V[3 + r] += QVEL(bda + r);
-        t2[3 + r] += QACC(bda + r);
-      }
-      // rotational dofs: body axes; the anchor is the body origin, O - anchor = (O - pos)
-      const double off[3] = {O[0] - pos[0], O[1] - pos[1], O[2] - pos[2]};
-      double cd[3][6];
-      for (int r = 0; r < 3; r++) {
-        cd[r][0] = mat[r]; cd[r][1] = mat[r + 3]; cd[r][2] = mat[r + 6];
-        cross3(cd[r] + 3, cd[r], off);
-        stn(cdof, 6*(bda + 3 + r), cd[r], 6);
-      }
-      // all three use the velocity BEFORE this joint's rotation (mj_comVel :1855-1876)
-      for (int r = 0; r < 3; r++) {
-        double dd[6];
-        crossMotion(dd, V, cd[r]);
-        const double qv = QVEL(bda + 3 + r);
-        for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
-      }
-      for (int r = 0; r < 3; r++) {
-        const double qv = QVEL(bda + 3 + r), qa = QACC(bda + 3 + r);
-        for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
-      }
-    } else if (has_ball) {
-      // general path: finish the ball-joint cdofs with the final orientation, then run the dof
-      // loop of mj_comVel over the body's dofs from scratch
-      for (int j = 0; j < jntnum; j++) {
-        const int jid = jntadr + j;
-        if (jnt_type[jid] != MJB_JNT_BALL) continue;
-        const int dadr = jnt_dofadr[jid];
-        double off[3];
-        ldn(off, cdof, 6*dadr, 3);
-        for (int r = 0; r < 3; r++) {
-          double cd[6] = {mat[r], mat[r + 3], mat[r + 6], 0, 0, 0};
-          cross3(cd + 3, cd, off);
-          stn(cdof, 6*(dadr + r), cd, 6);
-        }
-      }
-      for (int j = 0; j < dofnum; j++) {
-        const int jt = jnt_type[dof_jntid[bda + j]];
-        if (jt == MJB_JNT_BALL) {
-          double cd[3][6];
-          for (int r = 0; r < 3; r++) {
-            double dd[6];
-            ldn(cd[r], cdof, 6*(bda + j + r), 6);
-            crossMotion(dd, V, cd[r]);
-            const double qv = QVEL(bda + j + r);
-            for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
-          }
-          for (int r = 0; r < 3; r++) {
-            const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
-            for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
-          }
-          j += 2;
-        } else {
-          double cd[6], dd[6];
-          ldn(cd, cdof, 6*(bda + j), 6);
-          crossMotion(dd, V, cd);
-          const double qv = QVEL(bda + j), qa = QACC(bda + j);
-          for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
-        }
-      }
-    }
-
-    for (int k = 0; k < 6; k++) { A[k] += t1[k]; A[k] += t2[k]; AL[k] += t2[k]; }
-    stn(cvel, 6*b, V, 6);
-    stn(cal, 6*b, AL, 6);
-    if (tree_flags[b] & 4) stn(cacc, 6*b, A, 6);   // read back only by a child that is not b+1
-
-    // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
-    const int sf = body_sameframe[b];
-    double ip[3], im[9];
-    if (sf == MJB_SAMEFRAME_BODY) {
-      ip[0] = pos[0]; ip[1] = pos[1]; ip[2] = pos[2];
-    } else {
-      mulMatVec3(ip, mat, body_ipos + 3*b);
-      ip[0] += pos[0]; ip[1] += pos[1]; ip[2] += pos[2];
-    }
-    if (sf == MJB_SAMEFRAME_NONE) {
-      double tq[4];
-      mulQuat(tq, quat, body_iquat + 4*b);
-      quat2Mat(im, tq);
-    } else {
-      for (int k = 0; k < 9; k++) im[k] = mat[k];
-    }
-    {
-      const double off[3] = {ip[0] - O[0], ip[1] - O[1], ip[2] - O[2]};
-      double ci[10], f[6], u1[6], u2[6];
-      inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
-      stn(cinert, 10*b, ci, 10);
-      mulInertVec(f, ci, A);
-      mulInertVec(u1, ci, V);
-      crossForce(u2, V, u1);
-      for (int k = 0; k < 6; k++) f[k] += u2[k];
-      stn(cfrc, 6*b, f, 6);
-    }
-
-    body_geoms(c, b, pos, quat, mat, ip, im);
-
-    P[0] = pos[0]; P[1] = pos[1]; P[2] = pos[2];
-    Q[0] = quat[0]; Q[1] = quat[1]; Q[2] = quat[2]; Q[3] = quat[3];
-    carry = b;
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,58 +197,14 @@ MJB_HD inline void tendon_fixed(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_passive: joint springs, dof dampers, tendon spring-dampers (engine_passive.c:57-379,436-497)
-// gravcomp, fluid, flex, callbacks and plugins are rejected at upload.
-MJB_HD inline void passive(Ctx& c) {
+// mj_passive (engine_passive.c:57-379,436-497): joint springs and dof dampers are evaluated per dof
+// inside the forward sweep (scalar_dof_forces / quat_dof_forces); this adds the tendon
+// spring-dampers. gravcomp, fluid, flex, callbacks and plugins are rejected at upload.
+MJB_HD inline void passive_tendons(Ctx& c) {
   const mjbHdr& H = *c.H;
+  if (H.disableflags & MJB_DSBL_PASSIVE) return;
   double* qp = SC(qfrc_passive);
-  const int nv = H.nv;
-  if (H.disableflags & MJB_DSBL_PASSIVE) {
-    for (int i = 0; i < nv; i++) AT(qp, i) = 0;
-    return;
-  }
-
-  // qfrc_passive = qfrc_spring + qfrc_damper, one joint at a time (every dof belongs to exactly
-  // one joint), each entry written once
-  const int* jnt_type = MI(jnt_type);
-  const int* jnt_qposadr = MI(jnt_qposadr);
   const int* jnt_dofadr = MI(jnt_dofadr);
-  const double* jnt_stiffness = MD(jnt_stiffness);
-  const double* qpos_spring = MD(qpos_spring);
-  const double* dof_damping = MD(dof_damping);
-  for (int i = 0; i < H.njnt; i++) {
-    const double k = jnt_stiffness[i];
-    int padr = jnt_qposadr[i];
-    const int dadr = jnt_dofadr[i];
-    const int jt = jnt_type[i];
-    double spring[6] = {0, 0, 0, 0, 0, 0};
-    int nd = 1, r0 = 0;
-    if (jt == MJB_JNT_FREE) {
-      nd = 6; r0 = 3;
-      if (k != 0) for (int r = 0; r < 3; r++) spring[r] = -k*(QPOS(padr + r) - qpos_spring[padr + r]);
-      padr += 3;
-    } else if (jt == MJB_JNT_BALL) {
-      nd = 3;
-    }
-    if (k != 0) {
-      if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
-        double quat[4] = {QPOS(padr), QPOS(padr+1), QPOS(padr+2), QPOS(padr+3)};
-        double dif[3];
-        normalize4(quat);
-        subQuat(dif, quat, qpos_spring + padr);
-        for (int r = 0; r < 3; r++) spring[r0 + r] = -k*dif[r];
-      } else {
-        spring[0] = -k*(QPOS(padr) - qpos_spring[padr]);
-      }
-    }
-    for (int r = 0; r < nd; r++) {
-      const double dmp = dof_damping[dadr + r];
-      double val = spring[r];
-      if (dmp != 0) val += -dmp*QVEL(dadr + r);
-      AT(qp, dadr + r) = val;
-    }
-  }
-
   if (H.ntendon) {
     const double* stiff = MD(tendon_stiffness); const double* damp = MD(tendon_damping);
     const double* ls = MD(tendon_lengthspring);
@@ -563,6 +235,16 @@ MJB_HD inline void passive(Ctx& c) {
 // constraint-row arithmetic shared by all row types
 
 // getimpedance (engine_core_constraint.c:1441-1489) on pre-clamped solimp
+// general power: a = 1/power(mid, p-1) ; y = a*power(x, p)  /  mirrored above the midpoint
+MJB_COLD inline double impedance_power(double x, double mid, double p) {
+  if (x <= mid) {
+    const double a = 1/pow(mid, p - 1);
+    return a*pow(x, p);
+  }
+  const double b = 1/pow(1 - mid, p - 1);
+  return 1 - b*pow(1 - x, p);
+}
+
 MJB_HD inline double impedance(const double* sp, double pos, double margin) {
   const double d0 = sp[MJB_SP_D0], d1 = sp[MJB_SP_D1], width = sp[MJB_SP_WIDTH];
   if (d0 == d1 || width <= MJB_MINVAL) return 0.5*(d0 + d1);
@@ -573,21 +255,17 @@ MJB_HD inline double impedance(const double* sp, double pos, double margin) {
   double y;
   if (p == 1) {
     y = x;
-  } else if (x <= mid) {
-    // a = 1/power(mid, p-1) ; y = a*power(x, p)
-    const double a = 1/(p == 2 ? mid : pow(mid, p - 1));
-    y = a*(p == 2 ? x*x : pow(x, p));
+  } else if (p == 2) {
+    y = x <= mid ? (1/mid)*(x*x) : 1 - (1/(1 - mid))*((1 - x)*(1 - x));
   } else {
-    const double b = 1/(p == 2 ? 1 - mid : pow(1 - mid, p - 1));
-    y = 1 - b*(p == 2 ? (1 - x)*(1 - x) : pow(1 - x, p));
+    y = impedance_power(x, mid, p);
   }
   return d0 + y*(d1 - d0);
 }
 
 // write one constraint row to the optional efc outputs; returns its row index
-MJB_HD inline int emit_row(Ctx& c, int type, int id, double pos, double margin, double D, double R,
-                           double vel, double aref, double force, int state, double imp) {
-  const int row = c.nefc++;
+MJB_HD inline int emit_row(Ctx& c, int row, int type, int id, double pos, double margin, double D,
+                           double R, double vel, double aref, double force, int state, double imp) {
   if (c.out.efc_int) {
     if (row < c.njmax) {
       const size_t N = (size_t)c.N;
@@ -615,7 +293,7 @@ MJB_HD inline int emit_row(Ctx& c, int type, int id, double pos, double margin, 
 //   pos, margin -> impedance ; dA = diagApprox ; vel = J*qvel ; jacc = J*qacc
 // mj_makeImpedance (engine_core_constraint.c:1494-1608), mj_referenceConstraint (:2362),
 // mj_invConstraint (engine_inverse.c:169) and mj_constraintUpdate (:2387-2457) for this row.
-MJB_HD inline double scalar_row(Ctx& c, int type, int id, const double* sp, double pos,
+MJB_HD inline double scalar_row(Ctx& c, int row, int type, int id, const double* sp, double pos,
                                 double margin, double dA, double vel, double jacc, double floss) {
   const double imp = impedance(sp, pos, margin);
   const double R = fmax(MJB_MINVAL, (1 - imp)*dA/imp);
@@ -632,7 +310,7 @@ MJB_HD inline double scalar_row(Ctx& c, int type, int id, const double* sp, doub
   } else if (type != MJB_CNSTR_EQUALITY) {
     if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
   }
-  emit_row(c, type, id, pos, margin, D, R, vel, aref, force, state, imp);
+  emit_row(c, row, type, id, pos, margin, D, R, vel, aref, force, state, imp);
   return force;
 }
 
@@ -751,7 +429,7 @@ MJB_HD inline void equality_rows(Ctx& c) {
         const double aref = -sp[MJB_SP_B]*vel[r] - sp[MJB_SP_K]*imp*cpos[r];
         const double jar = acc[r] - aref;
         f[r] = -D*jar;
-        emit_row(c, MJB_CNSTR_EQUALITY, i, cpos[r], 0, D, R, vel[r], aref, f[r], MJB_STATE_QUADRATIC, imp);
+        emit_row(c, c.ne + r, MJB_CNSTR_EQUALITY, i, cpos[r], 0, D, R, vel[r], aref, f[r], MJB_STATE_QUADRATIC, imp);
       }
       c.ne += nrow;
       double T[3] = {0, 0, 0};
@@ -799,7 +477,7 @@ MJB_HD inline void equality_rows(Ctx& c) {
         cpos = pos[0] - ref[0] - data[0];
       }
       const double vel = v[0] - deriv*v[1], acc = a[0] - deriv*a[1];
-      const double f = scalar_row(c, MJB_CNSTR_EQUALITY, i, sp, cpos, 0, en[MJB_EQN_DA_TRAN], vel, acc, 0);
+      const double f = scalar_row(c, c.ne, MJB_CNSTR_EQUALITY, i, sp, cpos, 0, en[MJB_EQN_DA_TRAN], vel, acc, 0);
       c.ne++;
       for (int j = 0; j < 1 + (id1 >= 0); j++) {
         const int id = j == 0 ? id0 : id1;
@@ -817,123 +495,549 @@ MJB_HD inline void equality_rows(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_instantiateFriction (engine_core_constraint.c:768-819) for dofs and fixed tendons
-MJB_HD inline void friction_rows(Ctx& c) {
+// Per-dof pieces of mj_passive / mj_instantiateFriction / mj_instantiateLimit, called from the
+// forward sweep while the dof's qpos/qvel/qacc are in registers. Row numbers are explicit: the
+// numbers of equality rows (ne_rows) and friction-loss rows (nf_rows, dofs first then tendons) are
+// model constants, so friction row of dof i is ne_rows + dof_frow[i] and limit rows follow at
+// ne_rows + nf_rows + (running count), in joint order like the reference.
+
+// mj_checkPos / mj_checkVel / mj_checkAcc (engine_forward.c:53-102): flag, do not reset
+MJB_DI int bad_value(double v) { return !(v == v) || v > MJB_MAXVAL || v < -MJB_MAXVAL; }
+
+MJB_HD inline bool rows_enabled(const mjbHdr& H) { return !(H.disableflags & MJB_DSBL_CONSTRAINT); }
+
+// friction-loss row of dof i (engine_core_constraint.c:768-790); returns the row's force
+MJB_HD inline double dof_friction_row(Ctx& c, int i, double qv, double qa) {
   const mjbHdr& H = *c.H;
-  if (H.disableflags & MJB_DSBL_FRICTIONLOSS) return;
-  double* qc = SC(qfrc_c);
-  const double* floss = MD(dof_frictionloss);
-  const double* iw = MD(dof_invweight0);
-  const double* sp = MD(sp_dof_friction);
-  for (int i = 0; i < H.nv; i++) {
-    if (floss[i] > 0) {
-      const double f = scalar_row(c, MJB_CNSTR_FRICTION_DOF, i, sp + MJB_SP_N*i, 0, 0, iw[i],
-                                  QVEL(i), QACC(i), floss[i]);
-      AT(qc, i) += f;
-      c.nf++;
+  const int frow = MI(dof_frow)[i];
+  if (frow < 0) return 0;
+  return scalar_row(c, H.ne_rows + frow, MJB_CNSTR_FRICTION_DOF, i, MD(sp_dof_friction) + MJB_SP_N*i,
+                    0, 0, MD(dof_invweight0)[i], qv, qa, MD(dof_frictionloss)[i]);
+}
+
+// limit rows of a slide/hinge joint (engine_core_constraint.c:851-871); returns J'f on its dof
+MJB_HD inline double joint_limit_rows(Ctx& c, int jid, int dof, double q, double qv, double qa) {
+  const mjbHdr& H = *c.H;
+  if (!MI(jnt_limited)[jid] || (H.disableflags & MJB_DSBL_LIMIT) || !rows_enabled(H)) return 0;
+  const double margin = MD(jnt_margin)[jid];
+  const double* range = MD(jnt_range) + 2*jid;
+  double acc = 0;
+  for (int side = -1; side <= 1; side += 2) {
+    const double dist = side * (range[(side + 1)/2] - q);
+    if (dist < margin) {
+      // J = -side at this dof
+      const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
+                                  MD(sp_jnt_limit) + MJB_SP_N*jid, dist, margin,
+                                  MD(dof_invweight0)[dof], -side*qv, -side*qa, 0);
+      acc += -side*f;
+      c.nl++;
     }
   }
-  if (H.ntendon) {
-    const double* tfl = MD(tendon_frictionloss);
-    const double* tiw = MD(tendon_invweight0);
-    const double* tsp = MD(sp_tendon_friction);
-    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
-    const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
-    const double* wrap_prm = MD(wrap_prm);
-    double* V = SC(ten_velocity);
-    for (int t = 0; t < H.ntendon; t++) {
-      if (tfl[t] > 0) {
+  return acc;
+}
+
+// everything a scalar (slide/hinge) dof contributes besides the rigid-body terms: input checks,
+// spring + damper -> qfrc_passive, friction-loss and limit rows -> qfrc_c
+MJB_HD inline void scalar_dof_forces(Ctx& c, int jid, int qadr, int dof, double q, double qv, double qa) {
+  const mjbHdr& H = *c.H;
+  if (bad_value(q)) c.status |= kStatusBadQpos;
+  if (bad_value(qv)) c.status |= kStatusBadQvel;
+  if (bad_value(qa)) c.status |= kStatusBadQacc;
+  double passive = 0;
+  if (!(H.disableflags & MJB_DSBL_PASSIVE)) {
+    const double k = MD(jnt_stiffness)[jid], dmp = MD(dof_damping)[dof];
+    if (k != 0) passive = -k*(q - MD(qpos_spring)[qadr]);
+    if (dmp != 0) passive += -dmp*qv;
+  }
+  AT(SC(qfrc_passive), dof) = passive;
+  double qc = 0;
+  if (rows_enabled(H)) {
+    qc = dof_friction_row(c, dof, qv, qa);
+    qc += joint_limit_rows(c, jid, dof, q, qv, qa);
+  }
+  AT(SC(qfrc_c), dof) = qc;
+}
+
+// the same for the 3 rotational dofs of a ball or free joint whose (normalised) quaternion is quat
+// (engine_passive.c:84-98, engine_core_constraint.c:875-918); free joints: ntrans = 3 translations
+// in front, handled here too
+MJB_HD inline void quat_dof_forces(Ctx& c, int jid, int qadr, int dof, int jt, const double* quat) {
+  const mjbHdr& H = *c.H;
+  const double k = MD(jnt_stiffness)[jid];
+  const bool passive_on = !(H.disableflags & MJB_DSBL_PASSIVE);
+  const double* dof_damping = MD(dof_damping);
+  double* qp = SC(qfrc_passive); double* qcs = SC(qfrc_c);
+  int padr = qadr, d = dof;
+  if (jt == MJB_JNT_FREE) {
+    for (int r = 0; r < 3; r++) {
+      const double q = QPOS(padr + r), qv = QVEL(d + r), qa = QACC(d + r);
+      if (bad_value(q)) c.status |= kStatusBadQpos;
+      if (bad_value(qv)) c.status |= kStatusBadQvel;
+      if (bad_value(qa)) c.status |= kStatusBadQacc;
+      double passive = 0;
+      if (passive_on) {
+        if (k != 0) passive = -k*(q - MD(qpos_spring)[padr + r]);
+        const double dmp = dof_damping[d + r];
+        if (dmp != 0) passive += -dmp*qv;
+      }
+      AT(qp, d + r) = passive;
+      AT(qcs, d + r) = rows_enabled(H) ? dof_friction_row(c, d + r, qv, qa) : 0.0;
+    }
+    padr += 3; d += 3;
+  }
+  double qv[3], qa[3];
+  for (int r = 0; r < 3; r++) {
+    qv[r] = QVEL(d + r); qa[r] = QACC(d + r);
+    if (bad_value(qv[r])) c.status |= kStatusBadQvel;
+    if (bad_value(qa[r])) c.status |= kStatusBadQacc;
+  }
+  for (int r = 0; r < 4; r++) if (bad_value(QPOS(padr + r))) c.status |= kStatusBadQpos;
+  double spring[3] = {0, 0, 0};
+  if (passive_on && k != 0) {
+    double dif[3];
+    subQuat(dif, quat, MD(qpos_spring) + padr);
+    for (int r = 0; r < 3; r++) spring[r] = -k*dif[r];
+  }
+  double qc[3] = {0, 0, 0};
+  if (rows_enabled(H)) {
+    for (int r = 0; r < 3; r++) qc[r] = dof_friction_row(c, d + r, qv[r], qa[r]);
+    if (jt == MJB_JNT_BALL && MI(jnt_limited)[jid] && !(H.disableflags & MJB_DSBL_LIMIT)) {
+      const double* range = MD(jnt_range) + 2*jid;
+      const double margin = MD(jnt_margin)[jid];
+      double aa[3];
+      quat2Vel(aa, quat, 1);
+      const double value = normalize3(aa);
+      const double dist = fmax(range[0], range[1]) - value;
+      if (dist < margin) {
+        // J = -angleAxis on the three dofs
+        double vel = 0, jacc = 0;
+        for (int r = 0; r < 3; r++) { vel += -aa[r]*qv[r]; jacc += -aa[r]*qa[r]; }
+        const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
+                                    MD(sp_jnt_limit) + MJB_SP_N*jid, dist, margin,
+                                    MD(dof_invweight0)[d], vel, jacc, 0);
+        for (int r = 0; r < 3; r++) qc[r] += -aa[r]*f;
+        c.nl++;
+      }
+    }
+  }
+  for (int r = 0; r < 3; r++) {
+    double passive = spring[r];
+    if (passive_on) {
+      const double dmp = dof_damping[d + r];
+      if (dmp != 0) passive += -dmp*qv[r];
+    }
+    AT(qp, d + r) = passive;
+    AT(qcs, d + r) = qc[r];
+  }
+}
+
+// friction-loss rows of fixed tendons (engine_core_constraint.c:793-816), after the dof rows
+MJB_HD inline void tendon_friction_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if ((H.disableflags & MJB_DSBL_FRICTIONLOSS) || !H.ntendon) return;
+  double* qc = SC(qfrc_c);
+  const double* tfl = MD(tendon_frictionloss);
+  const double* tiw = MD(tendon_invweight0);
+  const double* tsp = MD(sp_tendon_friction);
+  const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+  const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
+  const double* wrap_prm = MD(wrap_prm);
+  double* V = SC(ten_velocity);
+  int row = H.ne_rows + H.nf_dof_rows;
+  for (int t = 0; t < H.ntendon; t++) {
+    if (tfl[t] > 0) {
+      const int adr = tendon_adr[t], num = tendon_num[t];
+      double jacc = 0;
+      for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
+      const double f = scalar_row(c, row++, MJB_CNSTR_FRICTION_TENDON, t, tsp + MJB_SP_N*t, 0, 0, tiw[t],
+                                  AT(V, t), jacc, tfl[t]);
+      for (int j = 0; j < num; j++) AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
+    }
+  }
+}
+
+// limit rows of fixed tendons (engine_core_constraint.c:923-955), after the joint limit rows
+MJB_HD inline void tendon_limit_rows(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if ((H.disableflags & MJB_DSBL_LIMIT) || !H.ntendon) return;
+  double* qc = SC(qfrc_c);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* tendon_limited = MI(tendon_limited);
+  const double* tendon_range = MD(tendon_range);
+  const double* tendon_margin = MD(tendon_margin);
+  const double* tiw = MD(tendon_invweight0);
+  const double* tsp = MD(sp_tendon_limit);
+  const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+  const int* wrap_objid = MI(wrap_objid);
+  const double* wrap_prm = MD(wrap_prm);
+  double* L = SC(ten_length); double* V = SC(ten_velocity);
+  for (int t = 0; t < H.ntendon; t++) {
+    if (!tendon_limited[t]) continue;
+    const double value = AT(L, t), margin = tendon_margin[t];
+    for (int side = -1; side <= 1; side += 2) {
+      const double dist = side * (tendon_range[2*t + (side + 1)/2] - value);
+      if (dist < margin) {
         const int adr = tendon_adr[t], num = tendon_num[t];
         double jacc = 0;
         for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
-        const double f = scalar_row(c, MJB_CNSTR_FRICTION_TENDON, t, tsp + MJB_SP_N*t, 0, 0, tiw[t],
-                                    AT(V, t), jacc, tfl[t]);
-        for (int j = 0; j < num; j++) AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
-        c.nf++;
+        const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_TENDON, t,
+                                    tsp + MJB_SP_N*t, dist, margin, tiw[t], -side*AT(V, t), -side*jacc, 0);
+        for (int j = 0; j < num; j++) {
+          AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += -side*wrap_prm[adr + j]*f;
+        }
+        c.nl++;
       }
     }
   }
 }
 
-// mj_instantiateLimit (engine_core_constraint.c:824-959)
-MJB_HD inline void limit_rows(Ctx& c) {
+// ------------------------------------------------------------------------------------------
+// Forward sweep: ONE root-to-leaves pass that does, per body, the work the reference spreads over
+//   mj_kinematics  (engine_core_smooth.c:38-178, mj_local2Global engine_support.c:1565)
+//   mj_comPos      (:183-270; cinert via mju_inertCom, cdof via mju_dofCom)
+//   mj_comVel      (:1833-1896)
+//   mj_rne forward (:1969-2005, flg_acc = 1)
+// so that a body's pose, joint axes, velocity and acceleration never leave registers between those
+// stages; only what later phases read is written to the per-state scratch.
+//
+// Frame of the spatial quantities. The reference expresses cdof/cvel/cacc/cinert/cfrc about the
+// centre of mass of the kinematic tree (subtree_com[body_rootid]), which is known only after a
+// full kinematics pass. Spatial algebra holds about ANY fixed world point, and qfrc_inverse, qM,
+// qLD, J*v, J'*f are independent of it, so the sweep uses the tree origin
+//     O_tree = position of the tree's root body before its joints act
+//            = qpos[0:3] of a free root, body_pos of a jointed or welded root
+// which is known when the root is entered (|x - O| stays of the order of the tree's size, like the
+// reference's com-based offsets). Bodies of one tree are contiguous in the body order, so O is
+// carried in registers; it is also stored per root body for the constraint phases.
+//
+// Carry. Bodies are in depth-first order, so a body's parent is very often the body just
+// processed: its pose/velocity/acceleration are then still in registers (P, Q, V, A, AL) and are
+// read from scratch only when the parent is an earlier body (warp-uniform test).
+//
+//   cvel      spatial velocity about O                              (contact rows, cfrc)
+//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
+//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
+//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                   (backward pass)
+// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
+
+// L1 prefetch of the input rows (qpos/qvel/qacc) the joints of body b will read, issued one body
+// ahead so that the HBM latency of the state's inputs overlaps the current body's arithmetic
+MJB_DI void prefetch_line(const double* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+MJB_HD inline void prefetch_body_inputs(Ctx& c, int b) {
+  const int jntadr = MI(body_jntadr)[b], jntnum = MI(body_jntnum)[b];
+  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* jnt_dofnum = MI(jnt_dofnum_tab);
+  for (int j = jntadr; j < jntadr + jntnum; j++) {
+    const int nd = jnt_dofnum[j], qa = jnt_qposadr[j], da = jnt_dofadr[j];
+    const int nq = nd == 6 ? 7 : (nd == 3 ? 4 : 1);
+    for (int k = 0; k < nq; k++) prefetch_line(&QPOS(qa + k));
+    for (int k = 0; k < nd; k++) { prefetch_line(&QVEL(da + k)); prefetch_line(&QACC(da + k)); }
+  }
+}
+
+// pose of the geoms of body b from the body's frames held in registers (mj_local2Global)
+MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* quat, const double* mat,
+                              const double* ip, const double* im) {
+  const int* body_geomadr = MI(body_geomadr);
+  const int* body_geomnum = MI(body_geomnum);
+  const int* geom_sameframe = MI(geom_sameframe);
+  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const int g0 = body_geomadr[b], gn = body_geomnum[b];
+  for (int g = g0; g < g0 + gn; g++) {
+    const int sf = geom_sameframe[g];
+    double gp[3], gm[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      gp[0] = pos[0]; gp[1] = pos[1]; gp[2] = pos[2];
+    } else if (sf == MJB_SAMEFRAME_INERTIA) {
+      gp[0] = ip[0]; gp[1] = ip[1]; gp[2] = ip[2];
+    } else {
+      mulMatVec3(gp, mat, geom_pos + 3*g);
+      gp[0] += pos[0]; gp[1] += pos[1]; gp[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, geom_quat + 4*g);
+      quat2Mat(gm, tq);
+    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
+      for (int k = 0; k < 9; k++) gm[k] = mat[k];
+    } else {
+      for (int k = 0; k < 9; k++) gm[k] = im[k];
+    }
+    sts(gxpos, 3*g, gp, 3);
+    sts(gxmat, 9*g, gm, 9);
+  }
+}
+
+MJB_HD inline void forward_sweep(Ctx& c) {
   const mjbHdr& H = *c.H;
-  if (H.disableflags & MJB_DSBL_LIMIT) return;
-  double* qc = SC(qfrc_c);
-  const int* jnt_limited = MI(jnt_limited);
+  const int nbody = H.nbody;
+  double* xpos = SC(xpos); double* xquat = SC(xquat); double* org = SC(origin);
+  double* cvel = SC(cvel); double* cal = SC(cacc_lin); double* cacc = SC(cacc);
+  double* cfrc = SC(cfrc); double* cinert = SC(cinert); double* cdof = SC(cdof);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_jntadr = MI(body_jntadr);
+  const int* body_jntnum = MI(body_jntnum);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
+  const int* body_mocapid = MI(body_mocapid);
+  const int* body_sameframe = MI(body_sameframe);
+  const int* tree_flags = MI(body_tree_flags);
   const int* jnt_type = MI(jnt_type);
   const int* jnt_qposadr = MI(jnt_qposadr);
   const int* jnt_dofadr = MI(jnt_dofadr);
-  const double* jnt_range = MD(jnt_range);
-  const double* jnt_margin = MD(jnt_margin);
-  const double* iw = MD(dof_invweight0);
-  const double* sp = MD(sp_jnt_limit);
-  for (int i = 0; i < H.njnt; i++) {
-    if (!jnt_limited[i]) continue;
-    const double margin = jnt_margin[i];
-    const int jt = jnt_type[i];
-    const int dof = jnt_dofadr[i];
-    if (jt == MJB_JNT_SLIDE || jt == MJB_JNT_HINGE) {
-      const double value = QPOS(jnt_qposadr[i]);
-      for (int side = -1; side <= 1; side += 2) {
-        const double dist = side * (jnt_range[2*i + (side + 1)/2] - value);
-        if (dist < margin) {
-          // J = -side at this dof
-          const double f = scalar_row(c, MJB_CNSTR_LIMIT_JOINT, i, sp + MJB_SP_N*i, dist, margin,
-                                      iw[dof], -side*QVEL(dof), -side*QACC(dof), 0);
-          AT(qc, dof) += -side*f;
-          c.nl++;
-        }
-      }
-    } else if (jt == MJB_JNT_BALL) {
-      const int adr = jnt_qposadr[i];
-      double quat[4] = {QPOS(adr), QPOS(adr+1), QPOS(adr+2), QPOS(adr+3)};
-      double aa[3];
-      normalize4(quat);
-      quat2Vel(aa, quat, 1);
-      const double value = normalize3(aa);
-      const double dist = fmax(jnt_range[2*i], jnt_range[2*i+1]) - value;
-      if (dist < margin) {
-        // J = -angleAxis on the three dofs
-        double vel = 0, jacc = 0;
-        for (int r = 0; r < 3; r++) { vel += -aa[r]*QVEL(dof + r); jacc += -aa[r]*QACC(dof + r); }
-        const double f = scalar_row(c, MJB_CNSTR_LIMIT_JOINT, i, sp + MJB_SP_N*i, dist, margin,
-                                    iw[dof], vel, jacc, 0);
-        for (int r = 0; r < 3; r++) AT(qc, dof + r) += -aa[r]*f;
-        c.nl++;
-      }
-    }
-  }
+  const int* dof_jntid = MI(dof_jntid);
+  const double* body_pos = MD(body_pos); const double* body_quat = MD(body_quat);
+  const double* body_ipos = MD(body_ipos); const double* body_iquat = MD(body_iquat);
+  const double* body_mass = MD(body_mass); const double* body_inertia = MD(body_inertia);
+  const double* jnt_pos = MD(jnt_pos); const double* jnt_axis = MD(jnt_axis);
+  const double* qpos0 = MD(qpos0);
 
-  if (H.ntendon) {
-    const int* tendon_limited = MI(tendon_limited);
-    const double* tendon_range = MD(tendon_range);
-    const double* tendon_margin = MD(tendon_margin);
-    const double* tiw = MD(tendon_invweight0);
-    const double* tsp = MD(sp_tendon_limit);
-    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
-    const int* wrap_objid = MI(wrap_objid);
-    const double* wrap_prm = MD(wrap_prm);
-    double* L = SC(ten_length); double* V = SC(ten_velocity);
-    for (int t = 0; t < H.ntendon; t++) {
-      if (!tendon_limited[t]) continue;
-      const double value = AT(L, t), margin = tendon_margin[t];
-      for (int side = -1; side <= 1; side += 2) {
-        const double dist = side * (tendon_range[2*t + (side + 1)/2] - value);
-        if (dist < margin) {
-          const int adr = tendon_adr[t], num = tendon_num[t];
-          double jacc = 0;
-          for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
-          const double f = scalar_row(c, MJB_CNSTR_LIMIT_TENDON, t, tsp + MJB_SP_N*t, dist, margin,
-                                      tiw[t], -side*AT(V, t), -side*jacc, 0);
-          for (int j = 0; j < num; j++) {
-            AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += -side*wrap_prm[adr + j]*f;
+  // Carry of the body just processed, in per-thread shared-memory slots (on chip, and out of the
+  // register budget of the joint loop): 0..2 pos, 3..6 quat, 7..12 cvel, 13..18 cacc, 19..24 cacc_lin
+#define CS(k) c.sm[(k) * MJB_SMS]
+  // world body: identity pose, zero velocity, acceleration = -gravity (mj_rne :1979-1982)
+  double O[3] = {0, 0, 0};
+  {
+    double P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
+    double Z[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
+    if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+      A[3] = -H.gravity[0]; A[4] = -H.gravity[1]; A[5] = -H.gravity[2];
+    }
+    stc(xpos, 0, P, 3); stc(xquat, 0, Q, 4); stc(org, 0, O, 3);
+    stc(cvel, 0, Z, 6); stc(cal, 0, Z, 6); stc(cacc, 0, A, 6);
+    for (int k = 0; k < 3; k++) CS(k) = 0;
+    CS(3) = 1; CS(4) = 0; CS(5) = 0; CS(6) = 0;
+    for (int k = 0; k < 6; k++) { CS(7 + k) = 0; CS(13 + k) = A[k]; CS(19 + k) = 0; }
+    const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    body_geoms(c, 0, P, Q, I9, P, I9);
+  }
+  int carry = 0;          // body whose pose / velocity / acceleration are in the carry slots
+
+  if (nbody > 1) prefetch_body_inputs(c, 1);
+  for (int b = 1; b < nbody; b++) {
+    if (b + 1 < nbody) prefetch_body_inputs(c, b + 1);
+    const int pid = body_parentid[b];
+    const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
+    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
+    if (pid != carry) {
+      double t[25];
+      ldn(t, xpos, 3*pid, 3); ldn(t + 3, xquat, 4*pid, 4);
+      ldn(t + 7, cvel, 6*pid, 6); ldn(t + 13, cacc, 6*pid, 6); ldn(t + 19, cal, 6*pid, 6);
+      for (int k = 0; k < 25; k++) CS(k) = t[k];
+    }
+    double V[6];
+    for (int k = 0; k < 6; k++) V[k] = CS(7 + k);
+    double pos[3], quat[4];
+    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
+    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
+    const bool isfree = jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE;
+    bool has_ball = false;
+
+    if (isfree) {
+      const int qadr = jnt_qposadr[jntadr];
+      for (int k = 0; k < 3; k++) pos[k] = QPOS(qadr + k);
+      for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + 3 + k);
+      normalize4(quat);
+      if (pid == 0) { O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2]; stc(org, 3*b, O, 3); }
+      quat_dof_forces(c, jntadr, qadr, bda, MJB_JNT_FREE, quat);
+    } else {
+      double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
+      if (body_mocapid[b] >= 0) normalize4(bquat);   // mocap pose = model pose (mj_resetData default)
+      if (pid) {
+        double pm[9];
+        const double Q[4] = {CS(3), CS(4), CS(5), CS(6)};
+        quat2Mat(pm, Q);                 // == the parent's xmat (same function of the same xquat)
+        mulMatVec3(pos, pm, body_pos + 3*b);
+        pos[0] += CS(0); pos[1] += CS(1); pos[2] += CS(2);
+        mulQuat(quat, Q, bquat);
+      } else {
+        for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
+        for (int k = 0; k < 4; k++) quat[k] = bquat[k];
+        O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
+        stc(org, 3*b, O, 3);
+      }
+      for (int j = 0; j < jntnum; j++) has_ball = has_ball || jnt_type[jntadr + j] == MJB_JNT_BALL;
+
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        const int qadr = jnt_qposadr[jid];
+        const int dadr = jnt_dofadr[jid];
+        const int jtype = jnt_type[jid];
+        double ax[3], anc[3], cd[6];
+        rotVecQuat(ax, jnt_axis + 3*jid, quat);
+        rotVecQuat(anc, jnt_pos + 3*jid, quat);
+        anc[0] += pos[0]; anc[1] += pos[1]; anc[2] += pos[2];
+        const double off[3] = {O[0] - anc[0], O[1] - anc[1], O[2] - anc[2]};
+
+        double jq = 0, jqv = 0, jqa = 0;
+        if (jtype != MJB_JNT_BALL) { jq = QPOS(qadr); jqv = QVEL(dadr); jqa = QACC(dadr); }
+        if (jtype == MJB_JNT_SLIDE) {
+          const double q = jq - qpos0[qadr];
+          pos[0] += ax[0]*q; pos[1] += ax[1]*q; pos[2] += ax[2]*q;
+          cd[0] = 0; cd[1] = 0; cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2];
+        } else {
+          double qloc[4];
+          if (jtype == MJB_JNT_BALL) {
+            for (int k = 0; k < 4; k++) qloc[k] = QPOS(qadr + k);
+            normalize4(qloc);
+            // cdof of a ball joint uses the body's FINAL orientation (mj_comPos :243-252): keep
+            // the anchor offset in the dof's slots until the pose is complete
+            stn(cdof, 6*dadr, off, 3);
+            quat_dof_forces(c, jid, qadr, dadr, MJB_JNT_BALL, qloc);
+          } else {
+            // mju_axisAngle2Quat (engine_util_spatial.c:97)
+            const double angle = jq - qpos0[qadr];
+            double sn, cs;
+            sincos(angle*0.5, &sn, &cs);
+            qloc[0] = cs;
+            qloc[1] = jnt_axis[3*jid]*sn; qloc[2] = jnt_axis[3*jid+1]*sn; qloc[3] = jnt_axis[3*jid+2]*sn;
+            cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+            cross3(cd + 3, ax, off);
           }
-          c.nl++;
+          mulQuat(quat, quat, qloc);
+          double vec[3];
+          rotVecQuat(vec, jnt_pos + 3*jid, quat);
+          pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
+        }
+        if (jtype != MJB_JNT_BALL) {
+          sts(cdof, 6*dadr, cd, 6);
+          if (!has_ball) {
+            // mj_comVel / mj_rne for a scalar dof, fused: cdof_dot uses the velocity so far
+            double dd[6];
+            crossMotion(dd, V, cd);
+            for (int k = 0; k < 6; k++) { t1[k] += dd[k]*jqv; V[k] += cd[k]*jqv; t2[k] += cd[k]*jqa; }
+          }
+          scalar_dof_forces(c, jid, qadr, dadr, jq, jqv, jqa);
         }
       }
     }
+
+    normalize4(quat);
+    double mat[9];
+    quat2Mat(mat, quat);
+    stc(xquat, 4*b, quat, 4);
+    stc(xpos, 3*b, pos, 3);
+
+    if (isfree) {
+      // translational dofs: cdof = [0, e_r], cdof_dot = 0
+      for (int r = 0; r < 3; r++) {
+        double cd[6] = {0, 0, 0, r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0};
+        sts(cdof, 6*(bda + r), cd, 6);
+        V[3 + r] += QVEL(bda + r);
+        t2[3 + r] += QACC(bda + r);
+      }
+      // rotational dofs: body axes; the anchor is the body origin, O - anchor = (O - pos)
+      const double off[3] = {O[0] - pos[0], O[1] - pos[1], O[2] - pos[2]};
+      double cd[3][6];
+      for (int r = 0; r < 3; r++) {
+        cd[r][0] = mat[r]; cd[r][1] = mat[r + 3]; cd[r][2] = mat[r + 6];
+        cross3(cd[r] + 3, cd[r], off);
+        sts(cdof, 6*(bda + 3 + r), cd[r], 6);
+      }
+      // all three use the velocity BEFORE this joint's rotation (mj_comVel :1855-1876)
+      for (int r = 0; r < 3; r++) {
+        double dd[6];
+        crossMotion(dd, V, cd[r]);
+        const double qv = QVEL(bda + 3 + r);
+        for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+      }
+      for (int r = 0; r < 3; r++) {
+        const double qv = QVEL(bda + 3 + r), qa = QACC(bda + 3 + r);
+        for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+      }
+    } else if (has_ball) {
+      // general path: finish the ball-joint cdofs with the final orientation, then run the dof
+      // loop of mj_comVel over the body's dofs from scratch
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        if (jnt_type[jid] != MJB_JNT_BALL) continue;
+        const int dadr = jnt_dofadr[jid];
+        double off[3];
+        ldn(off, cdof, 6*dadr, 3);
+        for (int r = 0; r < 3; r++) {
+          double cd[6] = {mat[r], mat[r + 3], mat[r + 6], 0, 0, 0};
+          cross3(cd + 3, cd, off);
+          stn(cdof, 6*(dadr + r), cd, 6);
+        }
+      }
+      for (int j = 0; j < dofnum; j++) {
+        const int jt = jnt_type[dof_jntid[bda + j]];
+        if (jt == MJB_JNT_BALL) {
+          double cd[3][6];
+          for (int r = 0; r < 3; r++) {
+            double dd[6];
+            ldn(cd[r], cdof, 6*(bda + j + r), 6);
+            crossMotion(dd, V, cd[r]);
+            const double qv = QVEL(bda + j + r);
+            for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+          }
+          for (int r = 0; r < 3; r++) {
+            const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
+            for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+          }
+          j += 2;
+        } else {
+          double cd[6], dd[6];
+          ldn(cd, cdof, 6*(bda + j), 6);
+          crossMotion(dd, V, cd);
+          const double qv = QVEL(bda + j), qa = QACC(bda + j);
+          for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
+        }
+      }
+    }
+
+    double A[6], AL[6];
+    for (int k = 0; k < 6; k++) {
+      A[k] = CS(13 + k); A[k] += t1[k]; A[k] += t2[k];
+      AL[k] = CS(19 + k) + t2[k];
+      CS(7 + k) = V[k]; CS(13 + k) = A[k]; CS(19 + k) = AL[k];
+    }
+    stc(cvel, 6*b, V, 6);
+    stc(cal, 6*b, AL, 6);
+    if (tree_flags[b] & 4) stc(cacc, 6*b, A, 6);   // read back only by a child that is not b+1
+
+    // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
+    const int sf = body_sameframe[b];
+    double ip[3], im[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      ip[0] = pos[0]; ip[1] = pos[1]; ip[2] = pos[2];
+    } else {
+      mulMatVec3(ip, mat, body_ipos + 3*b);
+      ip[0] += pos[0]; ip[1] += pos[1]; ip[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, body_iquat + 4*b);
+      quat2Mat(im, tq);
+    } else {
+      for (int k = 0; k < 9; k++) im[k] = mat[k];
+    }
+    {
+      const double off[3] = {ip[0] - O[0], ip[1] - O[1], ip[2] - O[2]};
+      double ci[10], f[6], u1[6], u2[6];
+      inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
+      sts(cinert, 10*b, ci, 10);
+      mulInertVec(f, ci, A);
+      mulInertVec(u1, ci, V);
+      crossForce(u2, V, u1);
+      for (int k = 0; k < 6; k++) f[k] += u2[k];
+      sts(cfrc, 6*b, f, 6);
+    }
+
+    body_geoms(c, b, pos, quat, mat, ip, im);
+
+    CS(0) = pos[0]; CS(1) = pos[1]; CS(2) = pos[2];
+    CS(3) = quat[0]; CS(4) = quat[1]; CS(5) = quat[2]; CS(6) = quat[3];
+    carry = b;
   }
+#undef CS
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1012,7 +1116,7 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
     }
   }
   if (efc_address < 0) return;
-  c.nefc = efc_address;
+  int row = efc_address;
 
   const double* sp = cn + MJB_CN_SP;
   const double* friction = cn + MJB_CN_FRICTION;
@@ -1045,7 +1149,7 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
     double force = -D*jar;
     int state = MJB_STATE_QUADRATIC;
     if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
-    emit_row(c, MJB_CNSTR_CONTACT_FRICTIONLESS, k, con.dist, includemargin, D, R, vel[0], aref,
+    emit_row(c, row++, MJB_CNSTR_CONTACT_FRICTIONLESS, k, con.dist, includemargin, D, R, vel[0], aref,
              force, state, imp);
     fc[0] = force;
   } else if (H.cone == 0) {
@@ -1066,7 +1170,7 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
         double force = -D*jar;
         int state = MJB_STATE_QUADRATIC;
         if (jar >= 0) { force = 0; state = MJB_STATE_SATISFIED; }
-        emit_row(c, MJB_CNSTR_CONTACT_PYRAMIDAL, k, con.dist, includemargin, D, Rpy, v, aref, force,
+        emit_row(c, row++, MJB_CNSTR_CONTACT_PYRAMIDAL, k, con.dist, includemargin, D, Rpy, v, aref, force,
                  state, imp);
         fc[0] += force;
         fc[j] += sgn*fr*force;
@@ -1111,7 +1215,7 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
       state = MJB_STATE_CONE;
     }
     for (int j = 0; j < dim; j++) {
-      emit_row(c, MJB_CNSTR_CONTACT_ELLIPTIC, k, j == 0 ? con.dist : 0.0,
+      emit_row(c, row++, MJB_CNSTR_CONTACT_ELLIPTIC, k, j == 0 ? con.dist : 0.0,
                j == 0 ? includemargin : 0.0, 1/R[j], R[j], vel[j], aref[j], force[j], state, imp);
       fc[j] = force[j];
     }
@@ -1122,6 +1226,7 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
     F[a] = con.frame[a]*fc[0] + con.frame[3 + a]*fc[1] + con.frame[6 + a]*fc[2];
     T3[a] = con.frame[a]*fc[3] + con.frame[3 + a]*fc[4] + con.frame[6 + a]*fc[5];
   }
+  c.nefc = row;
 }
 
 // One detected contact handled entirely by the thread that owns the state: mj_setContact
@@ -1835,20 +1940,20 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   const mjbHdr& H = *c.H;
   c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
   c.status = 0;
-  check_inputs(c);
-  forward_sweep(c);
+  forward_sweep(c);        // incl. input checks, joint springs/dampers, dof friction and joint limit rows
   tendon_fixed(c);
-  passive(c);
+  passive_tendons(c);
   {
-    double* qc = SC(qfrc_c); double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);
-    for (int i = 0; i < H.nv; i++) AT(qc, i) = 0;
+    double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);
     for (int i = 0; i < 6*H.nbody; i++) { AT(fe, i) = 0; AT(fe1, i) = 0; }
   }
-  if (!(H.disableflags & MJB_DSBL_CONSTRAINT)) {
-    equality_rows(c);
-    friction_rows(c);
-    limit_rows(c);
+  if (rows_enabled(H)) {
+    equality_rows(c);      // rows [0, ne)
+    tendon_friction_rows(c);
+    tendon_limit_rows(c);
+    c.nf = H.nf_rows;
   }
+  c.nefc = c.ne + c.nf + c.nl;
   save_counters(c);
 }
 
@@ -1914,6 +2019,8 @@ MJB_HD inline void inverse_one_state(Ctx& c) {
 #undef SC
 #undef AT
 #undef ldn
+#undef sts
+#undef stc
 #undef stn
 #undef QPOS
 #undef QVEL

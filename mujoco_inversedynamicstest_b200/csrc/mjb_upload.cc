@@ -580,6 +580,29 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
   {
+    // static row numbering (mj_makeConstraint order: equality, dof friction, tendon friction, ...)
+    const bool rows = !(dsbl & mjDSBL_CONSTRAINT);
+    std::vector<int> frow(nv, -1);
+    int nfd = 0, nft = 0, ne_rows = 0;
+    if (rows && !(dsbl & mjDSBL_FRICTIONLOSS)) {
+      for (int i = 0; i < nv; i++) if (m->dof_frictionloss[i] > 0) frow[i] = nfd++;
+      for (int t = 0; t < m->ntendon; t++) if (m->tendon_frictionloss[t] > 0) nft++;
+    }
+    if (rows) {
+      for (int i = 0; i < neq; i++) {
+        const int* ei = eq_int.data() + (size_t)i * MJB_EQ_NI;
+        if (!ei[MJB_EQI_ACTIVE]) continue;
+        if (ei[MJB_EQI_TYPE] == mjEQ_CONNECT || ei[MJB_EQI_TYPE] == mjEQ_WELD) {
+          if (!ei[MJB_EQI_SKIP]) ne_rows += ei[MJB_EQI_TYPE] == mjEQ_CONNECT ? 3 : 6;
+        } else {
+          ne_rows++;
+        }
+      }
+    }
+    H.ne_rows = ne_rows; H.nf_dof_rows = nfd; H.nf_rows = nfd + nft;
+    pushInts(MJB_I_dof_frow, frow.data(), frow.size());
+  }
+  {
     std::vector<int> flags(m->nbody, 0), seen(m->nbody, 0);
     for (int b = m->nbody - 1; b > 0; b--) {
       const int p = m->body_parentid[b];

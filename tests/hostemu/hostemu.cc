@@ -37,6 +37,8 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
     c.H = H;
     c.I = reinterpret_cast<const int*>(blob.data() + H->int_section);
     c.D = reinterpret_cast<const double*>(blob.data() + H->num_section);
+    double carry_slots[MJB_SM_SLOTS];
+    c.sm = carry_slots;
     c.sc = scratch.data();
     c.isc = iscratch;
     c.qpos = qpos_soa + s;
