@@ -229,6 +229,7 @@ enum {
   MJB_SC_ten_velocity, // ntendon
   MJB_SC_crb,          // nbody*10  composite rigid-body inertias
   MJB_SC_ia,           // nbody*21  articulated-body inertias (symmetric 6x6, upper triangle)
+  MJB_SC_cfrc_gc,      // nbody*6   gravity-compensation wrenches (only when the model has gravcomp)
   MJB_SC_COUNT
 };
 

@@ -28,8 +28,14 @@
 // small; only functions of scalars qualify (an out-of-line call taking Ctx& would force the whole
 // context into local memory: measured +45% on the smooth kernel)
 #define MJB_COLD __host__ __device__ __noinline__
+#ifdef MJB_NARROW_NOINLINE
+#define MJB_NP __host__ __device__ __noinline__
+#else
+#define MJB_NP __host__ __device__
+#endif
 #else
 #define MJB_HD
+#define MJB_NP
 #define MJB_COLD
 #endif
 
@@ -199,7 +205,8 @@ MJB_HD inline void tendon_fixed(Ctx& c) {
 // ------------------------------------------------------------------------------------------
 // mj_passive (engine_passive.c:57-379,436-497): joint springs and dof dampers are evaluated per dof
 // inside the forward sweep (scalar_dof_forces / quat_dof_forces); this adds the tendon
-// spring-dampers. gravcomp, fluid, flex, callbacks and plugins are rejected at upload.
+// spring-dampers; gravity compensation is a body wrench handled by the sweeps. Fluid, flex,
+// callbacks and plugins are rejected at upload.
 MJB_HD inline void passive_tendons(Ctx& c) {
   const mjbHdr& H = *c.H;
   if (H.disableflags & MJB_DSBL_PASSIVE) return;
@@ -1029,6 +1036,16 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       crossForce(u2, V, u1);
       for (int k = 0; k < 6; k++) f[k] += u2[k];
       sts(cfrc, 6*b, f, 6);
+      if (H.has_gravcomp) {
+        // mj_gravcomp (engine_passive.c:381-401): force -gravity*mass*gravcomp at the body's centre
+        // of mass, kept as a wrench about O and projected on the dofs in the backward sweep
+        const double sgc = -(body_mass[b] * MD(body_gravcomp)[b]);
+        const double F[3] = {H.gravity[0]*sgc, H.gravity[1]*sgc, H.gravity[2]*sgc};
+        double wg[6];
+        cross3(wg, off, F);
+        wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
+        sts(SC(cfrc_gc), 6*b, wg, 6);
+      }
     }
 
     body_geoms(c, b, pos, quat, mat, ip, im);
@@ -1247,7 +1264,7 @@ MJB_HD inline void process_contact(Ctx& c, int ci, Con& con) {
 // ---- narrow phase: primitives of engine_collision_primitive.c -----------------------------
 
 // mjraw_PlaneSphere (:28)
-MJB_HD inline int plane_sphere(Con* con, double margin, const double* pos1, const double* mat1,
+MJB_NP inline int plane_sphere(Con* con, double margin, const double* pos1, const double* mat1,
                                const double* pos2, double radius) {
   con->frame[0] = mat1[2]; con->frame[1] = mat1[5]; con->frame[2] = mat1[8];
   double tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
@@ -1445,7 +1462,7 @@ MJB_HD inline int sphere_box(Con* con, double margin, const double* pos1, const 
 }
 
 // mjraw_SphereSphere (:250)
-MJB_HD inline int sphere_sphere(Con* con, double margin, const double* pos1, const double* mat1,
+MJB_NP inline int sphere_sphere(Con* con, double margin, const double* pos1, const double* mat1,
                                 double r1, const double* pos2, const double* mat2, double r2) {
   const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
   const double cdist_sqr = dot3(dif, dif);
@@ -1590,13 +1607,21 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
   const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
   const double margin = cn[MJB_CN_MARGIN];
+  const int func = cint[MJB_CI_FUNC];
   double pos1[3], pos2[3], mat1[9], mat2[9];
   ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
-  ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
+  if (func == MJB_FN_PLANE_SPHERE || func == MJB_FN_PLANE_CAPSULE || func == MJB_FN_SPHERE_SPHERE ||
+      func == MJB_FN_SPHERE_CAPSULE || func == MJB_FN_CAPSULE_CAPSULE) {
+    // these read only the z axis of either frame (plane normal, capsule axis): 6 loads instead of 18
+    for (int k = 0; k < 9; k++) { mat1[k] = 0; mat2[k] = 0; }
+    for (int k = 2; k < 9; k += 3) { mat1[k] = AT(gxmat, 9*g1 + k); mat2[k] = AT(gxmat, 9*g2 + k); }
+  } else {
+    ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
+  }
   const double* size1 = geom_size + 3*g1;
   const double* size2 = geom_size + 3*g2;
   int num = 0;
-  switch (cint[MJB_CI_FUNC]) {
+  switch (func) {
     case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
     case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
@@ -1731,24 +1756,35 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   // it, so its inertial force f and net constraint wrench w ('+' minus '-' side) are final: push
   // them to the parent and project them on the body's own dofs right away. Every body does its
   // loads first and its stores last (one memory round trip per body).
+  // gravity compensation (only models that have it): a third wrench carrier, projected into
+  // qfrc_passive except on joints whose gravcomp is routed through actuators (engine_passive.c:459-489)
+  const bool gcomp = H.has_gravcomp != 0;
+  double* fgc = SC(cfrc_gc);
+  const int* dof_jntid = MI(dof_jntid);
+  const int* jnt_actgravcomp = MI(jnt_actgravcomp);
   int carry_for = -1;
-  double cf[6], cw[6];
+  double cf[6], cw[6], cg[6] = {0, 0, 0, 0, 0, 0};
   for (int b = nbody - 1; b > 0; b--) {
     const int p = body_parentid[b];
     const bool push = p && b != p + 1;       // child p+1 hands over in registers (depth-first order)
-    double f[6], w[6], w1[6], pf[6], pw1[6];
+    double f[6], w[6], w1[6], pf[6], pw1[6], g[6] = {0, 0, 0, 0, 0, 0}, pg[6];
     ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
-    if (push) { ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6); }
+    if (gcomp) ldn(g, fgc, 6*b, 6);
+    if (push) {
+      ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6);
+      if (gcomp) ldn(pg, fgc, 6*p, 6);
+    }
     for (int k = 0; k < 6; k++) w[k] -= w1[k];
     if (carry_for == b) {
-      for (int k = 0; k < 6; k++) { f[k] += cf[k]; w[k] += cw[k]; }
+      for (int k = 0; k < 6; k++) { f[k] += cf[k]; w[k] += cw[k]; g[k] += cg[k]; }
     }
     const int d0 = body_dofadr[b], dn = body_dofnum[b];
     for (int i = d0; i < d0 + dn; i++) {
       double cd[6];
       ldn(cd, cdof, 6*i, 6);
       const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
-      const double passive_i = AT(qp, i);
+      double passive_i = AT(qp, i);
+      if (gcomp && !jnt_actgravcomp[dof_jntid[i]]) passive_i += dot6(cd, g);
       double res = dot6(cd, f);
       res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
       c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
@@ -1759,8 +1795,12 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       // parent's net = own '+' - own '-' + children's nets: children are folded into its '-' side
       for (int k = 0; k < 6; k++) { pf[k] += f[k]; pw1[k] -= w[k]; }
       stn(cfrc, 6*p, pf, 6); stn(fext1, 6*p, pw1, 6);
+      if (gcomp) {
+        for (int k = 0; k < 6; k++) pg[k] += g[k];
+        stn(fgc, 6*p, pg, 6);
+      }
     } else if (p) {
-      for (int k = 0; k < 6; k++) { cf[k] = f[k]; cw[k] = w[k]; }
+      for (int k = 0; k < 6; k++) { cf[k] = f[k]; cw[k] = w[k]; cg[k] = g[k]; }
       carry_for = p;
     }
   }

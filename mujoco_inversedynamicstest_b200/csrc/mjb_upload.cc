@@ -196,10 +196,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   if (!(dsbl & mjDSBL_PASSIVE) && (m->opt.density > 0 || m->opt.viscosity > 0)) {
     err = "fluid forces are not supported (opt.density / opt.viscosity > 0)"; return false;
   }
-  if (!(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
-      (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0)) {
-    err = "gravity compensation is not supported (ngravcomp > 0)"; return false;
-  }
+  // gravity compensation (engine_passive.c:381-401) runs iff this holds
+  const bool gravcomp = !(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
+      (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0);
   if (enbl & mjENBL_INVDISCRETE) { err = "mjENBL_INVDISCRETE is not supported"; return false; }
   if (m->nsensor && !(dsbl & mjDSBL_SENSOR)) {
     err = "sensors are not supported (nsensor > 0): set mjDSBL_SENSOR to run without sensordata";
@@ -550,7 +549,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.ncand = ncand;
   H.max_pair_contacts = max_pair_contacts;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
-  H.has_gravcomp = 0;
+  H.has_gravcomp = gravcomp ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 
@@ -635,6 +634,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_qfrc_passive] = nv;
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
     sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
+    sizes[MJB_SC_cfrc_gc] = gravcomp ? 6*nb : 0;
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;
@@ -657,7 +657,8 @@ const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
     "xpos", "xquat", "origin", "geom_xpos", "geom_xmat",
     "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
-    "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia"};
+    "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia",
+    "cfrc_gc"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
 

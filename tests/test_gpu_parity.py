@@ -14,7 +14,8 @@ import util
 pytestmark = pytest.mark.gpu
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
-         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic"]
+         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
+         "gravcomp"]
 
 
 def _run(mjb, name, gold, outmask):

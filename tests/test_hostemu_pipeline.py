@@ -18,7 +18,8 @@ import emu  # noqa: E402
 pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation library not buildable")
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
-         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic"]
+         "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
+         "gravcomp"]
 
 
 def _run(name):
