@@ -31,6 +31,7 @@ struct mjbData_ {
   long long kernel_launches = 0;  // phase kernels launched so far (reported by the benchmark)
   // inputs: internal SoA buffers and the views currently in use
   double *d_qpos = nullptr, *d_qvel = nullptr, *d_qacc = nullptr;
+  double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
   long long in_stride = 0;
   // AoS staging (host boundary), grown on demand
@@ -181,7 +182,10 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     setField(d, mjbF_EFC_INT, o.efc_int, 3 * d->njmax, 1);
     setField(d, mjbF_EFC_NUM, o.efc_num, 8 * d->njmax, 0);
   }
-  if (outmask & mjbOUT_INERTIA) {
+  if (H.discrete_acc) {
+    ok = ok && devAlloc(d, &d->d_qacc_discrete, (size_t)H.nv * S, "cudaMalloc(qacc_discrete)");
+  }
+  if ((outmask & mjbOUT_INERTIA) || H.discrete_acc) {   // mj_discreteAcc solves with the factors
     ok = ok && devAlloc(d, &o.qM, (size_t)H.nM * S, "cudaMalloc(qM)");
     ok = ok && devAlloc(d, &o.qLD, (size_t)H.nC * S, "cudaMalloc(qLD)");
     ok = ok && devAlloc(d, &o.qLDiagInv, (size_t)H.nv * S, "cudaMalloc(qLDiagInv)");
@@ -205,7 +209,7 @@ void mjb_deleteData(mjbData* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
-  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc);
+  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   for (int b = 0; b < 2; b++) {
     cudaFree(d->pipe_in[b]); cudaFree(d->pipe_out[b]);
@@ -269,6 +273,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.model_bytes = d->model_bytes;
   a.model_in_smem = d->model_in_smem;
   a.qpos = d->in_qpos; a.qvel = d->in_qvel; a.qacc = d->in_qacc;
+  a.qacc_discrete = d->d_qacc_discrete;
   a.scratch = d->d_scratch;
   a.iscratch = d->d_iscratch;
   a.chunk_stride = d->chunk_stride;

@@ -148,6 +148,20 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_INERTIA) inertia_kernel(Lau
   }
 }
 
+// mjENBL_INVDISCRETE: convert the discrete-time qacc with the factors the inertia kernel just wrote
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) discrete_acc_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    discrete_acc(c, a.qacc_discrete + c.s);
+  }
+}
+
 // contact scan: bounding-sphere survivors of every state as a bit mask + count
 template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a) {
@@ -425,6 +439,31 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   const bool in_smem = args.model_in_smem != 0;
   const bool want_inertia = args.out.qM || args.out.qLD || args.out.qLDiagInv;
   cudaError_t e;
+  if (args.qacc_discrete) {
+    // mjENBL_INVDISCRETE (engine_inverse.c:227-234): position stage + factorisation on the given
+    // state, qacc converted, then the whole pipeline on the converted accelerations
+    LaunchArgs pre = args;
+    pre.qacc_discrete = nullptr;
+    pre.has_contacts = 0;
+    const size_t s0 = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
+    e = in_smem ? launch_phase(smooth_kernel<true>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
+                : launch_phase(smooth_kernel<false>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads);
+    if (e != cudaSuccess) return e;
+    e = in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
+                : launch_phase(inertia_kernel<false>, pre, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    e = in_smem ? launch_phase(discrete_acc_kernel<true>, args, smem, 8, stream)
+                : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    *launches += 3;
+    LaunchArgs post = args;
+    post.qacc = args.qacc_discrete;
+    post.qacc_discrete = nullptr;
+    int n2 = 0;
+    e = launch_inverse(post, stream, &n2);
+    *launches += n2;
+    return e;
+  }
   const size_t ssmem = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
   e = in_smem ? launch_phase(smooth_kernel<true>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
               : launch_phase(smooth_kernel<false>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads);

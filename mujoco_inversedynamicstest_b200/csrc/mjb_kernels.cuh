@@ -25,6 +25,7 @@ struct LaunchArgs {
   const double* qpos;           // [nq][stride]
   const double* qvel;           // [nv][stride]
   const double* qacc;           // [nv][stride]
+  double* qacc_discrete;        // [nv][stride] continuous-time qacc (mjENBL_INVDISCRETE), or null
   double* scratch;              // [chunk_stride/32][nscratch][32]  intermediates of one chunk of states
   int* iscratch;                // [chunk_stride/32][niscratch][32]
   int nscratch, niscratch;      // slots per state: mjbHdr::nscratch, MJB_ISC_MASK + ceil(ncand/32) + 1

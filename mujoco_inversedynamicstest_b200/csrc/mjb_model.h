@@ -246,7 +246,8 @@ typedef struct mjbHdr_ {
   int32_t max_pair_contacts; // most contacts one candidate pair can yield (1, 2 or 4)
   // constraint-row counts that depend only on the model: equality rows, friction-loss rows of
   // dofs, friction-loss rows in total (dofs then tendons)
-  int32_t ne_rows, nf_dof_rows, nf_rows, pad_rows;
+  int32_t ne_rows, nf_dof_rows, nf_rows;
+  int32_t discrete_acc;     // mjENBL_INVDISCRETE with Euler and damped dofs: qacc is converted first
   double timestep, impratio;
   double gravity[3];
   double pad1;

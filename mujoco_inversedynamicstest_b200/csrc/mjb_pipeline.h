@@ -1967,6 +1967,48 @@ MJB_HD inline void inertia(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// mj_discreteAcc for the Euler integrator (engine_inverse.c:81-164): the discrete-time qacc is
+// converted to the continuous-time one the rest of mj_inverse works with,
+//     qacc' = M^-1 (M + h diag(B)) qacc = qacc + h M^-1 (B .* qacc),
+// using the L'DL factors of the inertia kernel. mj_solveLD (engine_core_smooth.c:1629-1707) on the
+// reduced row layout of qLD (row i: ancestors ascending, diagonal last). The reference forms
+// (M + hB) qacc with mj_mulM and solves; the two agree to rounding (cond(M) * eps).
+MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
+  const mjbHdr& H = *c.H;
+  const int nv = H.nv;
+  const size_t N = (size_t)c.N;
+  const int* rownnz = MI(C_rownnz); const int* rowadr = MI(C_rowadr); const int* colind = MI(C_colind);
+  const int* simplenum = MI(dof_simplenum);
+  const double* damping = MD(dof_damping);
+  const double* qLD = c.out.qLD + c.s; const double* qLDiagInv = c.out.qLDiagInv + c.s;
+  double* x = SC(qfrc_c);                 // free at this point: the smooth phase is rerun afterwards
+  for (int i = 0; i < nv; i++) AT(x, i) = H.timestep * damping[i] * QACC(i);
+  // x <- L^-T x
+  for (int i = nv - 1; i > 0; i--) {
+    if (simplenum[i]) continue;
+    const double xi = AT(x, i);
+    if (xi != 0) {
+      const int start = rowadr[i], end = start + rownnz[i] - 1;
+      for (int adr = start; adr < end; adr++) AT(x, colind[adr]) -= qLD[(size_t)adr*N] * xi;
+    }
+  }
+  // x <- D^-1 x
+  for (int i = 0; i < nv; i++) AT(x, i) *= qLDiagInv[(size_t)i*N];
+  // x <- L^-1 x
+  for (int i = 1; i < nv; i++) {
+    if (simplenum[i]) continue;
+    const int d = rownnz[i] - 1;
+    if (d > 0) {
+      const int adr = rowadr[i];
+      double acc = 0;
+      for (int k = 0; k < d; k++) acc += qLD[(size_t)(adr + k)*N] * AT(x, colind[adr + k]);
+      AT(x, i) -= acc;
+    }
+  }
+  for (int i = 0; i < nv; i++) qacc_out[(size_t)i*N] = QACC(i) + AT(x, i);
+}
+
+// ------------------------------------------------------------------------------------------
 // mj_inverseSkip(m, d, mjSTAGE_NONE, skipsensor=1) for one state (engine_inverse.c:197-261), cut
 // into four phases that run as separate kernels (each with its own register budget / occupancy)
 // and hand their intermediates over through the per-state scratch in HBM:
@@ -2043,10 +2085,16 @@ MJB_HD inline void phase_backward(Ctx& c) {
 }
 
 // all phases for one state in sequence (single-lane host build of the tests)
-MJB_HD inline void inverse_one_state(Ctx& c) {
+MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   int list[64];
   phase_smooth(c);
   if (c.out.qM || c.out.qLD || c.out.qLDiagInv) phase_inertia(c);
+  if (c.H->discrete_acc) {
+    // converted accelerations replace qacc for everything that follows (engine_inverse.c:227-252)
+    discrete_acc(c, qacc_discrete + c.s);
+    c.qacc = qacc_discrete + c.s;
+    phase_smooth(c);
+  }
   if (contacts_enabled(*c.H)) {
     contact_scan(c);
     phase_contact(c, true, list, 1, 64);

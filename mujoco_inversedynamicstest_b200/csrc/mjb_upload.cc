@@ -199,7 +199,19 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // gravity compensation (engine_passive.c:381-401) runs iff this holds
   const bool gravcomp = !(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
       (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0);
-  if (enbl & mjENBL_INVDISCRETE) { err = "mjENBL_INVDISCRETE is not supported"; return false; }
+  // mjENBL_INVDISCRETE (mj_discreteAcc, engine_inverse.c:81-164): Euler is supported; RK4 is an
+  // error in the reference too, the implicit integrators need mjd_smooth_vel
+  bool discrete = false;
+  if (enbl & mjENBL_INVDISCRETE) {
+    if (m->opt.integrator != mjINT_EULER) {
+      err = "mjENBL_INVDISCRETE is supported with the Euler integrator only (RK4 is an error in "
+            "the reference, implicit/implicitfast need mjd_smooth_vel)";
+      return false;
+    }
+    if (!(dsbl & mjDSBL_EULERDAMP)) {
+      for (int i = 0; i < m->nv; i++) discrete = discrete || m->dof_damping[i] > 0;
+    }
+  }
   if (m->nsensor && !(dsbl & mjDSBL_SENSOR)) {
     err = "sensors are not supported (nsensor > 0): set mjDSBL_SENSOR to run without sensordata";
     return false;
@@ -550,6 +562,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.max_pair_contacts = max_pair_contacts;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
+  H.discrete_acc = discrete ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 

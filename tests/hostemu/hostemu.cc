@@ -32,6 +32,7 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
   std::vector<double> scratch((size_t)H->nscratch + 1);
   std::vector<int> iscratch_v((size_t)mjb::MJB_ISC_MASK + (size_t)((H->ncand + 31) / 32) + 1);
   int* iscratch = iscratch_v.data();
+  std::vector<double> qacc_discrete(H->discrete_acc ? (size_t)H->nv * nbatch : 1);
   for (int s = 0; s < nbatch; s++) {
     mjb::Ctx c;
     c.H = H;
@@ -49,7 +50,7 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
     c.nconmax = nconmax;
     c.njmax = njmax;
     c.out = *out;
-    mjb::inverse_one_state(c);
+    mjb::inverse_one_state(c, qacc_discrete.data());
   }
   return 0;
 }

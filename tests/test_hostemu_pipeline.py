@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation libr
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
-         "gravcomp"]
+         "gravcomp", "humanoid_invdiscrete"]
 
 
 def _run(name):
@@ -102,6 +102,8 @@ def test_upload_rejections():
     with pytest.raises(RuntimeError, match="collision function"):
         emu.candidates(model)
     h = mjb.Model.from_mjb(util.golden("humanoid")[0])
-    h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE
+    h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE: Euler only
+    assert len(emu.candidates(h)) > 0
+    h.set_opt_int("integrator", 2)              # mjINT_IMPLICIT needs mjd_smooth_vel
     with pytest.raises(RuntimeError, match="INVDISCRETE"):
         emu.candidates(h)
