@@ -1461,6 +1461,174 @@ MJB_HD inline int sphere_box(Con* con, double margin, const double* pos1, const 
   return 1;
 }
 
+// mjraw_CapsuleBox (engine_collision_box.c:121-595): the capsule's segment is brought into the box
+// frame; the closest feature of the box (a face under one of the two end points, or one of the 12
+// edges against the segment) gives the first contact sphere, and the relative orientation of the
+// segment and that feature decides whether and where a second sphere is placed along the segment.
+// Both spheres then go through sphere_box. Arithmetic follows the reference expression by
+// expression (the predicates dist < bestdist etc. decide contact counts).
+MJB_HD inline int capsule_box(Con* con, double margin, const double* pos1, const double* mat1,
+                              const double* size1, const double* pos2, const double* mat2,
+                              const double* size2) {
+  const double halflength = size1[1];
+  double pos[3], axis[3], halfaxis[3];
+  {
+    const double d[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    const double a[3] = {mat1[2], mat1[5], mat1[8]};
+    for (int i = 0; i < 3; i++) {
+      pos[i] = mat2[i]*d[0] + mat2[3 + i]*d[1] + mat2[6 + i]*d[2];     // mat2' * d
+      axis[i] = mat2[i]*a[0] + mat2[3 + i]*a[1] + mat2[6 + i]*a[2];
+      halfaxis[i] = axis[i]*halflength;
+    }
+  }
+  const int axisdir = (halfaxis[0] > 0 ? 1 : 0) + (halfaxis[1] > 0 ? 2 : 0) + (halfaxis[2] > 0 ? 4 : 0);
+
+  double bestdist = margin + 2*(size1[0] + halflength + size2[0] + size2[1] + size2[2]);
+  double bestsegmentpos = 0, bestboxpos = 0, secondpos = -4;
+  int cltype = -4, clface = -1, clcorner = 0, cledge = 0;
+
+  // a face of the box under one of the segment's end points
+  for (int e = -1; e <= 1; e += 2) {
+    double q[3], orig[3];
+    int nclamp = 0, last = -1;
+    for (int j = 0; j < 3; j++) {
+      orig[j] = pos[j] + halfaxis[j]*e;
+      q[j] = orig[j];
+      if (q[j] < -size2[j]) { nclamp++; last = j; q[j] = -size2[j]; }
+      else if (q[j] > size2[j]) { nclamp++; last = j; q[j] = size2[j]; }
+    }
+    if (nclamp > 1) continue;
+    const double d[3] = {q[0] - orig[0], q[1] - orig[1], q[2] - orig[2]};
+    const double dist = dot3(d, d);
+    if (dist < bestdist) { bestdist = dist; bestsegmentpos = e; cltype = -2 + e; clface = last; }
+  }
+
+  // the 12 edges: edge j-direction through corner i (bit j of i clear), against the segment
+  for (int j = 0; j < 3; j++) {
+    for (int i = 0; i < 8; i++) {
+      if (i & (1 << j)) continue;
+      double start[3] = {(i & 1 ? 1 : -1)*size2[0], (i & 2 ? 1 : -1)*size2[1], (i & 4 ? 1 : -1)*size2[2]};
+      start[j] = 0;
+      double dif[3] = {start[0] - pos[0], start[1] - pos[1], start[2] - pos[2]};
+      const double ma = size2[j]*size2[j];
+      const double mb = -size2[j]*halfaxis[j];
+      const double mc = size1[1]*size1[1];
+      const double u = -size2[j]*dif[j];
+      const double v = dot3(halfaxis, dif);
+      const double det = ma*mc - mb*mb;
+      if (fabs(det) < MJB_MINVAL) continue;
+      const double idet = 1/det;
+      double x1 = (mc*u - mb*v)*idet;      // along the edge, -1..1
+      double x2 = (ma*v - mb*u)*idet;      // along the segment, -1..1
+      int s1 = 1, s2 = 1;                  // 1: interior, 0 / 2: clamped to the lower / upper end
+      if (x1 > 1) { x1 = 1; s1 = 2; x2 = (v - mb)*(1/mc); }
+      else if (x1 < -1) { x1 = -1; s1 = 0; x2 = (v + mb)*(1/mc); }
+      if (x2 > 1) {
+        x2 = 1; s2 = 2; x1 = (u - mb)*(1/ma);
+        if (x1 > 1) { x1 = 1; s1 = 2; } else if (x1 < -1) { x1 = -1; s1 = 0; }
+      } else if (x2 < -1) {
+        x2 = -1; s2 = 0; x1 = (u + mb)*(1/ma);
+        if (x1 > 1) { x1 = 1; s1 = 2; } else if (x1 < -1) { x1 = -1; s1 = 0; }
+      }
+      for (int k = 0; k < 3; k++) dif[k] += halfaxis[k]*(-x2);
+      dif[j] += size2[j]*x1;
+      const double d2 = dot3(dif, dif);
+      if (d2 < bestdist - MJB_MINVAL) {
+        const int code = s1*3 + s2;
+        bestdist = d2; bestsegmentpos = x2; bestboxpos = x1;
+        clcorner = i + (1 << j)*(code / 6);
+        cledge = j;
+        cltype = code;
+      }
+    }
+  }
+  if (cltype == -4) return 0;
+
+  // second sphere: how far along the segment from the first one
+  bool second = true;
+  double mul = 1;
+  if (cltype >= 0 && cltype / 3 != 1) {
+    // closest to a corner of the box
+    int c1 = axisdir ^ clcorner;
+    if (c1 == 0 || c1 == 7) {
+      second = false;                       // pointing at / away from the corner
+    } else {
+      double de, dp;
+      if (c1 == 1 || c1 == 2 || c1 == 4) {
+        mul = 1; de = 1 - bestsegmentpos; dp = 1 + bestsegmentpos;
+      } else {
+        mul = -1; c1 = 7 - c1; dp = 1 - bestsegmentpos; de = 1 + bestsegmentpos;
+      }
+      const int ax = c1 == 1 ? 0 : (c1 == 2 ? 1 : 2);
+      const int ax1 = (ax + 1) % 3, ax2 = (ax + 2) % 3;
+      if (axis[ax]*axis[ax] > 0.5) {        // along the edge
+        secondpos = de;
+        const double e1 = 2*size2[ax] / fabs(halfaxis[ax]);
+        if (e1 < secondpos) secondpos = e1;
+        secondpos *= mul;
+      } else {                              // along a face
+        secondpos = dp;
+        double e1 = 2*size2[ax1] / fabs(halfaxis[ax1]);
+        if (e1 < secondpos) secondpos = e1;
+        e1 = 2*size2[ax2] / fabs(halfaxis[ax2]);
+        if (e1 < secondpos) secondpos = e1;
+        secondpos *= -mul;
+      }
+    }
+  } else if (cltype >= 0) {
+    // closest to the interior of an edge: T configuration (no second point) or a cross
+    int c1 = (axisdir ^ clcorner) & (7 - (1 << cledge));
+    if (c1 != 1 && c1 != 2 && c1 != 4) {
+      second = false;
+    } else {
+      const int ax = cledge;
+      int ax1 = (ax + 1) % 3, ax2 = (ax + 2) % 3;
+      if (fabs(axis[ax1]) > fabs(axis[ax2])) ax1 = ax2;
+      ax2 = 3 - ax - ax1;
+      if (c1 & (1 << ax2)) { mul = 1; secondpos = 1 - bestsegmentpos; }
+      else { mul = -1; secondpos = 1 + bestsegmentpos; }
+      double e1 = 2*size2[ax2] / fabs(halfaxis[ax2]);
+      if (e1 < secondpos) secondpos = e1;
+      const double e2 = (((axisdir & (1 << ax)) != 0) == ((c1 & (1 << ax2)) != 0)) ? 1 - bestboxpos
+                                                                                  : 1 + bestboxpos;
+      e1 = size2[ax]*e2 / fabs(halfaxis[ax]);
+      if (e1 < secondpos) secondpos = e1;
+      secondpos *= mul;
+    }
+  } else {
+    // an end point above a face: walk towards the other end while still above the box
+    if (clface == -1) {
+      second = false;                       // the end point is inside the box
+    } else {
+      mul = cltype == -3 ? 1 : -1;
+      secondpos = 2;
+      const double t[3] = {pos[0] + halfaxis[0]*(-mul), pos[1] + halfaxis[1]*(-mul), pos[2] + halfaxis[2]*(-mul)};
+      for (int i = 0; i < 3; i++) {
+        if (i == clface) continue;
+        double e1 = (size2[i] - t[i]) / halfaxis[i] * mul;
+        if (e1 > 0 && e1 < secondpos) secondpos = e1;
+        e1 = (-size2[i] - t[i]) / halfaxis[i] * mul;
+        if (e1 > 0 && e1 < secondpos) secondpos = e1;
+      }
+      secondpos *= mul;
+    }
+  }
+  (void)second;   // the reference tests secondpos itself (> -3 once assigned)
+
+  double loc[3], cen[3];
+  for (int k = 0; k < 3; k++) loc[k] = pos[k] + halfaxis[k]*bestsegmentpos;
+  mulMatVec3(cen, mat2, loc);
+  cen[0] += pos2[0]; cen[1] += pos2[1]; cen[2] += pos2[2];
+  int n = sphere_box(con, margin, cen, size1, pos2, mat2, size2);
+  if (secondpos > -3) {
+    for (int k = 0; k < 3; k++) loc[k] = pos[k] + halfaxis[k]*(secondpos + bestsegmentpos);
+    mulMatVec3(cen, mat2, loc);
+    cen[0] += pos2[0]; cen[1] += pos2[1]; cen[2] += pos2[2];
+    n += sphere_box(con + n, margin, cen, size1, pos2, mat2, size2);
+  }
+  return n;
+}
+
 // mjraw_SphereSphere (:250)
 MJB_NP inline int sphere_sphere(Con* con, double margin, const double* pos1, const double* mat1,
                                 double r1, const double* pos2, const double* mat2, double r2) {
@@ -1628,6 +1796,7 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
     case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_PLANE_ELLIPSOID: num = plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_BOX: num = sphere_box(con, margin, pos1, size1, pos2, mat2, size2); break;
+    case MJB_FN_CAPSULE_BOX: num = capsule_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_SPHERE:
       num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
     case MJB_FN_SPHERE_CAPSULE:

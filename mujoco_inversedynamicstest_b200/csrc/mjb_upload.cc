@@ -84,6 +84,7 @@ int narrowphaseId(int t1, int t2) {
     case mjGEOM_CAPSULE:
       switch (t2) {
         case mjGEOM_CAPSULE: return MJB_FN_CAPSULE_CAPSULE;
+        case mjGEOM_BOX: return MJB_FN_CAPSULE_BOX;
         default: return -2;
       }
     default:
@@ -415,7 +416,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     ci[MJB_CI_G1] = g1; ci[MJB_CI_G2] = g2; ci[MJB_CI_FUNC] = fn; ci[MJB_CI_DIM] = condim;
     {
       const int per = (fn == MJB_FN_PLANE_CYLINDER || fn == MJB_FN_PLANE_BOX) ? 4
-                      : (fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE) ? 2 : 1;
+                      : (fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE ||
+                         fn == MJB_FN_CAPSULE_BOX) ? 2 : 1;
       max_pair_contacts = std::max(max_pair_contacts, per);
     }
     ci[MJB_CI_B1] = b1; ci[MJB_CI_B2] = b2;

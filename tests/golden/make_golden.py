@@ -43,6 +43,8 @@ CASES = {
     "zoo_elliptic": ("repo:tests/golden/models/zoo.xml", {"cone": 1}, 256, (0.0, 0.6), 32, 128),
     # mjENBL_INVDISCRETE with the Euler integrator (mj_discreteAcc, engine_inverse.c:81-164)
     "humanoid_invdiscrete": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 3}, 128, (0.0, 1.5), 64, 256),
+    "capsbox": ("repo:tests/golden/models/capsbox.xml", {}, 512, (0.0, 0.7), 48, 200),
+    "capsbox_elliptic": ("repo:tests/golden/models/capsbox.xml", {"cone": 1}, 256, (0.0, 0.7), 48, 200),
     "gravcomp": ("repo:tests/golden/models/gravcomp.xml", {}, 128, (0.5, 1.5), 8, 16),
 }
 
