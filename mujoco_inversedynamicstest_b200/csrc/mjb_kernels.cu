@@ -29,7 +29,7 @@
 #define MJB_CTAS_BACKWARD 4
 #endif
 #ifndef MJB_CTAS_CONTACT
-#define MJB_CTAS_CONTACT 3
+#define MJB_CTAS_CONTACT 2
 #endif
 
 namespace mjb {
@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
   off += sizeof(int) * kListCap * kThreads;
   int* wcnt = reinterpret_cast<int*>(smem + off) + warp * 128;   // [upd_rows | upd_cons | pcount | wstatus]
   off += sizeof(int) * 128 * (kThreads / 32);
+  int* hits = reinterpret_cast<int*>(smem + off) + warp * (32 * kListCap);   // (owner << 27) | candidate
+  off += sizeof(int) * 32 * kListCap * (kThreads / 32);
   off = (off + 15) & ~(size_t)15;
   PoolRec* pool = reinterpret_cast<PoolRec*>(smem + off) + (size_t)warp * pool_cap;
   int* upd_rows = wcnt; int* upd_cons = wcnt + 32; int* wstatus = wcnt + 96;
@@ -265,9 +267,12 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
     int pool_n = 0;
 
     // step 3 on the current pool
-    auto drain = [&]() {
+    // only full rounds of 32 records are processed until the warp's last call (final), so that the
+    // row arithmetic always runs with all lanes busy; the remainder moves to the pool's front
+    auto drain = [&](bool final) {
       const int* body_static = c.I + H.ioff[MJB_I_body_static];
-      for (int r0 = 0; r0 < pool_n; r0 += 32) {
+      const int nproc = final ? pool_n : (pool_n & ~31);
+      for (int r0 = 0; r0 < nproc; r0 += 32) {
         const int r = r0 + lane;
         const bool has = r < pool_n;
         int owner = 64 + lane, ci = 0, rows = 0, exclude = 0;
@@ -319,7 +324,15 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
         upd_cons[lane] = 0; upd_rows[lane] = 0;
         __syncwarp();
       }
-      pool_n = 0;
+      const int rem = pool_n - nproc;
+      if (rem > 0 && nproc > 0) {
+        PoolRec keep;
+        if (lane < rem) keep = pool[nproc + lane];
+        __syncwarp();
+        if (lane < rem) pool[lane] = keep;
+        __syncwarp();
+      }
+      pool_n = rem;
     };
 
     while (true) {
@@ -344,7 +357,9 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
       if (total == 0) break;
       __syncwarp();
 
-      // step 2: pooled narrow phase
+      // step 2a: exact hit test of every pooled survivor, all lanes busy; hits are compacted in
+      // order into the warp's hit list as (owner, candidate)
+      int nhit = 0;
       for (int j0 = 0; j0 < total; j0 += 32) {
         const int j = j0 + lane;
         const bool has = j < total;
@@ -356,10 +371,31 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
           if (t < 32 && e <= j) o = t;
         }
         const int eo = __shfl_sync(0xffffffffu, excl, o);
-        Con con[4];
-        int num = 0, ci = 0;
+        bool hit = false;
+        int ci = 0;
         if (has) {
           ci = lists[(j - eo) * kThreads + warp * 32 + o];
+          Ctx co = c;
+          bind_state(co, a, wbase + o);
+          hit = narrow_test(co, ci);
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int dst = nhit + __popc(hm & ((1u << lane) - 1u));
+          hits[dst] = (o << 27) | ci;
+        }
+        nhit += __popc(hm);
+      }
+      __syncwarp();
+
+      // step 2b: narrow phase of the hits
+      for (int j0 = 0; j0 < nhit; j0 += 32) {
+        const int j = j0 + lane;
+        const bool has = j < nhit;
+        Con con[4];
+        int num = 0, ci = 0, o = 0;
+        if (has) {
+          o = (unsigned)hits[j] >> 27; ci = hits[j] & 0x7ffffff;
           Ctx co = c;
           bind_state(co, a, wbase + o);
           num = narrow_pair(co, ci, con);
@@ -374,10 +410,10 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
         }
         pool_n += __shfl_sync(0xffffffffu, nincl, 31);
         __syncwarp();
-        if (pool_n + 32*maxper > pool_cap) drain();
+        if (pool_n + 32*maxper > pool_cap) drain(false);
       }
-      if (pool_n) drain();
     }
+    if (pool_n) drain(true);
 
     own.ncon = ncon; own.nefc = nefc;
     own.status |= wstatus[lane];
@@ -391,12 +427,13 @@ size_t contact_smem_bytes(int model_bytes, int model_in_smem, int max_pair_conta
   size_t off = model_in_smem ? (size_t)((model_bytes + 127) & ~127) : 0;
   off += sizeof(int) * kListCap * kThreads;
   off += sizeof(int) * 128 * (kThreads / 32);
+  off += sizeof(int) * 32 * kListCap * (kThreads / 32);
   off = (off + 15) & ~(size_t)15;
   off += sizeof(PoolRec) * (size_t)(32*max_pair_contacts + 32) * (kThreads / 32);
   return off;
 }
 
-template <bool kModelInSmem>
+template <bool kModelInSmem, bool kGravcomp>
 __global__ void __launch_bounds__(kThreads, MJB_CTAS_BACKWARD) backward_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
@@ -405,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_BACKWARD) backward_kernel(L
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
        i += (long long)gridDim.x * kThreads) {
     bind_state(c, a, i);
-    phase_backward(c);
+    phase_backward<kGravcomp>(c);
   }
 }
 
@@ -485,8 +522,13 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     if (e != cudaSuccess) return e;
     *launches += 2;
   }
-  e = in_smem ? launch_phase(backward_kernel<true>, args, smem, 8, stream)
-              : launch_phase(backward_kernel<false>, args, 0, 8, stream);
+  if (args.has_gravcomp) {
+    e = in_smem ? launch_phase(backward_kernel<true, true>, args, smem, 8, stream)
+                : launch_phase(backward_kernel<false, true>, args, 0, 8, stream);
+  } else {
+    e = in_smem ? launch_phase(backward_kernel<true, false>, args, smem, 8, stream)
+                : launch_phase(backward_kernel<false, false>, args, 0, 8, stream);
+  }
   if (e != cudaSuccess) return e;
   ++*launches;
   return cudaSuccess;

@@ -16,7 +16,7 @@ namespace mjb {
 // kernel walks its chunk of states with a block-stride loop
 constexpr int kThreads = 128;
 constexpr int kSMs = 148;
-constexpr int kListCap = 16;                  // per-lane survivor list of the contact kernel
+constexpr int kListCap = 32;                  // per-lane survivor list of the contact kernel
 
 struct LaunchArgs {
   const unsigned char* model;   // device blob (mjbHdr + sections)
@@ -35,6 +35,7 @@ struct LaunchArgs {
   long long stride;             // row stride of every state-indexed input/output array
   int nconmax, njmax;
   int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
+  int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
   Outputs out;
 };

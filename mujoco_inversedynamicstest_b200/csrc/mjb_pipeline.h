@@ -1811,6 +1811,86 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   return num;
 }
 
+// Exact pre-test of the narrow phase: would candidate ci yield at least one contact on this state?
+// For the sphere / capsule / plane primitives the accept decision of the reference is a single
+// distance comparison that comes before any square root, normalisation or frame construction
+// (mjraw_PlaneSphere :36, mjraw_SphereSphere :262), so the test evaluates exactly those
+// expressions and nothing else. The pooled contact kernel runs it on every bounding-sphere
+// survivor with all lanes busy and sends only the hits (about one in four for the humanoid) to
+// narrow_pair. Other pair types report true and are decided by narrow_pair itself.
+MJB_DI bool sphere_pair_hit(double margin, const double* pos1, double r1, const double* pos2, double r2) {
+  const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  const double cdist_sqr = dot3(dif, dif);
+  const double min_dist = margin + r1 + r2;
+  return !(cdist_sqr > min_dist*min_dist);
+}
+MJB_DI bool plane_sphere_hit(double margin, const double* pos1, const double* normal, const double* pos2,
+                             double radius) {
+  const double tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  return !(dot3(tmp, normal) > margin + radius);
+}
+
+MJB_HD inline bool narrow_test(Ctx& c, int ci) {
+  const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
+  const int func = cint[MJB_CI_FUNC];
+  if (!(func == MJB_FN_PLANE_SPHERE || func == MJB_FN_PLANE_CAPSULE || func == MJB_FN_SPHERE_SPHERE ||
+        func == MJB_FN_SPHERE_CAPSULE || func == MJB_FN_CAPSULE_CAPSULE)) return true;
+  const double margin = MD(cand_num)[MJB_CAND_NN*ci + MJB_CN_MARGIN];
+  const double* geom_size = MD(geom_size);
+  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
+  const double* size1 = geom_size + 3*g1;
+  const double* size2 = geom_size + 3*g2;
+  double pos1[3], pos2[3], z1[3], z2[3];
+  ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
+  for (int k = 0; k < 3; k++) { z1[k] = AT(gxmat, 9*g1 + 2 + 3*k); z2[k] = AT(gxmat, 9*g2 + 2 + 3*k); }
+  switch (func) {
+    case MJB_FN_PLANE_SPHERE:
+      return plane_sphere_hit(margin, pos1, z1, pos2, size2[0]);
+    case MJB_FN_PLANE_CAPSULE: {
+      const double seg[3] = {size2[1]*z2[0], size2[1]*z2[1], size2[1]*z2[2]};
+      double p[3] = {pos2[0] + seg[0], pos2[1] + seg[1], pos2[2] + seg[2]};
+      const bool h1 = plane_sphere_hit(margin, pos1, z1, p, size2[0]);
+      p[0] = pos2[0] - seg[0]; p[1] = pos2[1] - seg[1]; p[2] = pos2[2] - seg[2];
+      return h1 || plane_sphere_hit(margin, pos1, z1, p, size2[0]);
+    }
+    case MJB_FN_SPHERE_SPHERE:
+      return sphere_pair_hit(margin, pos1, size1[0], pos2, size2[0]);
+    case MJB_FN_SPHERE_CAPSULE: {
+      double vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+      const double x = clip(dot3(z2, vec), -size2[1], size2[1]);
+      vec[0] = z2[0]*x + pos2[0]; vec[1] = z2[1]*x + pos2[1]; vec[2] = z2[2]*x + pos2[2];
+      return sphere_pair_hit(margin, pos1, size1[0], vec, size2[0]);
+    }
+    default: {   // MJB_FN_CAPSULE_CAPSULE, the closest-point search of mjraw_CapsuleCapsule (:398)
+      const double axis1[3] = {z1[0]*size1[1], z1[1]*size1[1], z1[2]*size1[1]};
+      const double axis2[3] = {z2[0]*size2[1], z2[1]*size2[1], z2[2]*size2[1]};
+      const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+      const double ma = dot3(axis1, axis1);
+      const double mb = -dot3(axis1, axis2);
+      const double mc = dot3(axis2, axis2);
+      const double u = -dot3(axis1, dif);
+      const double v = dot3(axis2, dif);
+      const double det = ma*mc - mb*mb;
+      double vec1[3], vec2[3];
+      if (fabs(det) >= MJB_MINVAL) {
+        double x1 = (mc*u - mb*v) / det;
+        double x2 = (ma*v - mb*u) / det;
+        if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; }
+        else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+        if (x2 > 1) { x2 = 1; x1 = clip((u - mb) / ma, -1, 1); }
+        else if (x2 < -1) { x2 = -1; x1 = clip((u + mb) / ma, -1, 1); }
+        for (int k = 0; k < 3; k++) {
+          vec1[k] = axis1[k]*x1 + pos1[k];
+          vec2[k] = axis2[k]*x2 + pos2[k];
+        }
+        return sphere_pair_hit(margin, vec1, size1[0], vec2, size2[0]);
+      }
+      return true;   // parallel axes (|det| < mjMINVAL): up to four sphere tests, left to narrow_pair
+    }
+  }
+}
+
 // narrow phase of one candidate pair followed by the rows of every contact it yields
 MJB_HD inline void collide_pair(Ctx& c, int ci) {
   Con con[4];
@@ -1909,6 +1989,7 @@ MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, i
 // backward half of mj_rne(flg_acc=1) (engine_core_smooth.c:2008-2020) fused with the last loop of
 // mj_inverseSkip (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree
 // separately and projected with the same cdof, which is J'*efc_force for the point constraints.
+template <bool kGravcomp>
 MJB_HD inline void rne_and_output(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
@@ -1927,7 +2008,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   // loads first and its stores last (one memory round trip per body).
   // gravity compensation (only models that have it): a third wrench carrier, projected into
   // qfrc_passive except on joints whose gravcomp is routed through actuators (engine_passive.c:459-489)
-  const bool gcomp = H.has_gravcomp != 0;
+  constexpr bool gcomp = kGravcomp;    // compile-time: the carrier costs registers only where used
   double* fgc = SC(cfrc_gc);
   const int* dof_jntid = MI(dof_jntid);
   const int* jnt_actgravcomp = MI(jnt_actgravcomp);
@@ -2220,10 +2301,11 @@ MJB_HD inline void phase_contact(Ctx& c, bool valid, int* list, int lstride, int
   if (valid) save_counters(c);
 }
 
+template <bool kGravcomp>
 MJB_HD inline void phase_backward(Ctx& c) {
   const mjbHdr& H = *c.H;
   load_counters(c);
-  rne_and_output(c);
+  rne_and_output<kGravcomp>(c);
 
   const size_t N = (size_t)c.N;
   if (c.out.counts) {
@@ -2268,7 +2350,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
     contact_scan(c);
     phase_contact(c, true, list, 1, 64);
   }
-  phase_backward(c);
+  if (c.H->has_gravcomp) phase_backward<true>(c); else phase_backward<false>(c);
 }
 
 #undef MI

@@ -459,6 +459,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     ncand++;
   }
 
+  if (ncand >= (1 << 27)) { err = "too many candidate geom pairs (>= 2^27)"; return false; }
+
   // ---- sparse structure of qLD: row i = ancestors of dof i ascending, then i
   // (makeDofDofSparse with reduced/upper flags as used for C, engine_io.c:929-1018; mapM2C :1135)
   const int nv = m->nv;
