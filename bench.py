@@ -14,6 +14,8 @@ One "step" = one mjb_inverse pass over a resident batch of 2^20 synthetic humano
   roofline      FP64 roofline of the step's phase kernels: executed fp64 flops per state (ncu,
                 profiles/flops_per_state.json) x states / CUDA-event time vs the DFMA peak measured
                 in the same run
+  kernels       per phase kernel: live CUDA-event time (events around every launch), share of the
+                step, achieved fp64 TFLOP/s and DRAM GB/s against both peaks
   roofline_hbm  algorithmic bytes (in + out per state) / time vs MEASURED_PEAKS.json HBM copy
                 bandwidth, with the measured DRAM traffic of the step next to it
   cpu_baseline  the reference's own mj_inverse looped over the host cores with its thread pool
@@ -55,13 +57,13 @@ FLOPS_PER_STATE_FILE = os.path.join(ROOT, "profiles", "flops_per_state.json")
 
 
 def load_flops_per_state(workload):
-    """(fp64 flops per state, measured DRAM bytes per state) of the phase kernels, from ncu."""
+    """(fp64 flops per state, measured DRAM bytes per state, per-kernel records) from ncu."""
     try:
         with open(FLOPS_PER_STATE_FILE) as f:
             rec = json.load(f)[workload]
-        return float(rec["flops_per_state"]), rec.get("dram_bytes_per_state")
+        return float(rec["flops_per_state"]), rec.get("dram_bytes_per_state"), rec.get("kernels", {})
     except Exception:
-        return None, None
+        return None, None, {}
 
 
 def measured_peaks():
@@ -278,6 +280,14 @@ def main():
     if not np.isfinite(got).all():
         raise SystemExit("non-finite qfrc_inverse in the benchmark batch")
 
+    # ---------------- per-kernel times, live, CUDA events around every launch ----------------
+    pt_steps = max(3, min(args.steps, 5))
+    bd.phase_timing(True)
+    for _ in range(pt_steps):
+        bd.inverse(sync=False)
+    phase_ms = {k: v / pt_steps for k, v in bd.phase_times().items()}
+    bd.phase_timing(False)
+
     # ---------------- end-to-end through the C-ABI with host buffers ----------------
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
@@ -303,9 +313,9 @@ def main():
         peaks, peak_src = measured_peaks()
         per_gpu_rate = n * args.steps / (kernel_ms * 1e-3)
         fp64_peak = mjb.fp64_peak_tflops(local_rank)
-        fps, dram_per_state = load_flops_per_state(args.workload)
+        fps, dram_per_state, kcounts = load_flops_per_state(args.workload)
         if args.no_inertia:
-            fps, dram_per_state = None, None     # the frozen counts include the inertia kernel
+            fps, dram_per_state, kcounts = None, None, {}   # the frozen counts include the inertia kernel
         alg_bytes = 8 * (nq + 2 * nv) + 8 * nv + 4
         if not args.no_inertia:
             alg_bytes += 8 * (model.int("nM") + model.int("nC") + nv)
@@ -313,9 +323,26 @@ def main():
             "bound": "fp64", "achieved": (per_gpu_rate * fps * 1e-12) if fps else None,
             "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (per_gpu_rate * fps * 1e-12 / fp64_peak) if (fps and fp64_peak > 0) else None,
-            "traffic": None, "flops_per_state": fps,
+            "traffic": (dram_per_state * n) if dram_per_state else None,
+            "traffic_unit": "DRAM bytes per step per GPU (ncu dram__bytes_read+write, profiles/)",
+            "flops_per_state": fps,
             "kernel": "the step = smooth + inertia + contact_scan + contact + backward kernels",
             "peak_source": "DFMA probe measured in this run (mjb_fp64PeakTflops)"}
+        # per kernel: live CUDA-event time of this run x the frozen ncu counts (flops, DRAM bytes)
+        kernels = []
+        for name, ms in phase_ms.items():
+            if ms <= 0:
+                continue
+            kc = kcounts.get(name, {})
+            fl, by = kc.get("flops"), kc.get("dram_bytes")
+            kernels.append({
+                "kernel": name + "_kernel", "ms_per_step": ms,
+                "share": ms / max(sum(phase_ms.values()), 1e-12),
+                "fp64_tflops": (fl * n / (ms * 1e-3) * 1e-12) if fl else None,
+                "fp64_frac": (fl * n / (ms * 1e-3) * 1e-12 / fp64_peak) if (fl and fp64_peak > 0) else None,
+                "dram_gbs": (by * n / (ms * 1e-3) * 1e-9) if by else None,
+                "hbm_frac": (by * n / (ms * 1e-3) * 1e-9 / peaks["hbm_gbs"]) if by else None})
+        kernels.sort(key=lambda k: -k["ms_per_step"])
         roof_hbm = {
             "bound": "hbm", "achieved": per_gpu_rate * alg_bytes * 1e-9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": per_gpu_rate * alg_bytes * 1e-9 / peaks["hbm_gbs"],
@@ -338,6 +365,10 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": roof_fp64,
             "roofline_hbm": roof_hbm,
+            "kernels": kernels,
+            "kernels_note": "ms: CUDA events around every launch in this run (mjb_phaseTiming); flops "
+                            "and DRAM bytes per state: ncu counts frozen in profiles/flops_per_state.json; "
+                            "hbm_frac is MEASURED DRAM traffic / time vs the HBM copy peak",
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

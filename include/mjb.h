@@ -133,6 +133,13 @@ MJB_API const char* mjb_lastError(const mjbData* d);
 /* number of mj_inverse phase kernels this mjbData has launched so far (diagnostics / benchmark) */
 MJB_API long long mjb_kernelLaunches(const mjbData* d);
 
+/* Per-kernel timing of the phase kernels (diagnostics / benchmark): while enabled, every launch is
+ * bracketed by CUDA events on the launching stream. mjb_phaseTimes synchronises and returns the
+ * milliseconds accumulated since the last call in ms[0..n): smooth, inertia, contact_scan, contact,
+ * backward, discrete_acc. */
+MJB_API void mjb_phaseTiming(mjbData* d, int enable);
+MJB_API int mjb_phaseTimes(mjbData* d, double* ms, int n);
+
 /* wait for the stream */
 MJB_API int mjb_synchronize(mjbData* d);
 

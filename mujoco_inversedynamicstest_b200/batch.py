@@ -172,6 +172,19 @@ class BatchData:
     def kernel_launches(self):
         return int(lib().mjb_kernelLaunches(self._d))
 
+    PHASES = ("smooth", "inertia", "contact_scan", "contact", "backward", "discrete_acc")
+
+    def phase_timing(self, enable=True):
+        """Bracket every phase-kernel launch with CUDA events (mjb_phaseTiming)."""
+        lib().mjb_phaseTiming(self._d, 1 if enable else 0)
+
+    def phase_times(self):
+        """{kernel: milliseconds} accumulated since the last call (mjb_phaseTimes; synchronises)."""
+        ms = (ctypes.c_double * len(self.PHASES))()
+        if lib().mjb_phaseTimes(self._d, ms, len(self.PHASES)):
+            raise MjbError(f"mjb_phaseTimes: {lib().mjb_lastError(self._d).decode()}")
+        return dict(zip(self.PHASES, [float(x) for x in ms]))
+
     def inverse_host(self, n, qpos_ptr, qvel_ptr, qacc_ptr, out_ptr):
         """Pipelined host-to-host pass (mjb_inverseHost): pointers to HOST arrays n x nq|nv|nv and
         the n x nv output; asynchronous, call synchronize() before reading the output."""

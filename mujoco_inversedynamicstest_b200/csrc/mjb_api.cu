@@ -29,6 +29,12 @@ struct mjbData_ {
   int* d_iscratch = nullptr;      // [MJB_ISC_MASK + ceil(ncand/32)][chunk_stride]
   long long chunk_stride = 0;     // states per chunk (intermediates are allocated per chunk)
   long long kernel_launches = 0;  // phase kernels launched so far (reported by the benchmark)
+  // optional per-kernel timing (mjb_phaseTiming): event pool and (phase, begin, end) marks
+  bool phase_timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Mark { int phase; cudaEvent_t b, e; };
+  std::vector<Mark> marks;
   // inputs: internal SoA buffers and the views currently in use
   double *d_qpos = nullptr, *d_qvel = nullptr, *d_qacc = nullptr;
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
@@ -218,6 +224,7 @@ void mjb_deleteData(mjbData* d) {
     if (d->ev_comp[b]) cudaEventDestroy(d->ev_comp[b]);
     if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
   }
+  for (cudaEvent_t e : d->ev_pool) cudaEventDestroy(e);
   if (d->s_in) cudaStreamDestroy(d->s_in);
   if (d->s_out) cudaStreamDestroy(d->s_out);
   mjb::Outputs& o = d->out;
@@ -292,7 +299,22 @@ bool launchRange(mjbData* d, long long first, long long count) {
     a.chunk_start = start;
     a.chunk_n = (int)((first + count - start) < d->chunk_stride ? (first + count - start) : d->chunk_stride);
     int launches = 0;
-    if (!check(d, mjb::launch_inverse(a, d->stream, &launches), "launch mj_inverse kernels")) return false;
+    mjb::PhaseTimer timer;
+    timer.ctx = d;
+    timer.next_event = [](void* ctx) -> cudaEvent_t {
+      mjbData* dd = static_cast<mjbData*>(ctx);
+      if (dd->ev_used == dd->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        dd->ev_pool.push_back(e);
+      }
+      return dd->ev_pool[dd->ev_used++];
+    };
+    timer.mark = [](void* ctx, int phase, cudaEvent_t b, cudaEvent_t e) {
+      static_cast<mjbData*>(ctx)->marks.push_back({phase, b, e});
+    };
+    if (!check(d, mjb::launch_inverse(a, d->stream, &launches, d->phase_timing ? &timer : nullptr),
+               "launch mj_inverse kernels")) return false;
     d->kernel_launches += launches;
   }
   return true;
@@ -447,6 +469,25 @@ void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int* func) {
 const char* mjb_lastError(const mjbData* d) { return d->error.c_str(); }
 
 long long mjb_kernelLaunches(const mjbData* d) { return d->kernel_launches; }
+
+void mjb_phaseTiming(mjbData* d, int enable) {
+  d->phase_timing = enable != 0;
+  d->marks.clear();
+  d->ev_used = 0;
+}
+
+int mjb_phaseTimes(mjbData* d, double* ms, int n) {
+  cudaSetDevice(d->device);
+  if (!check(d, cudaStreamSynchronize(d->stream), "mjb_phaseTimes")) return -1;
+  for (int i = 0; i < n; i++) ms[i] = 0;
+  for (const auto& m : d->marks) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, m.b, m.e) == cudaSuccess && m.phase < n) ms[m.phase] += t;
+  }
+  d->marks.clear();
+  d->ev_used = 0;
+  return 0;
+}
 
 int mjb_synchronize(mjbData* d) {
   cudaSetDevice(d->device);

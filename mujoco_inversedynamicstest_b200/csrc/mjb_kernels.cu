@@ -469,7 +469,20 @@ static cudaError_t launch_phase(K kernel, const LaunchArgs& args, size_t smem, i
   return cudaGetLastError();
 }
 
-cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches) {
+namespace {
+struct PhaseScope {   // records begin/end events around one kernel launch when timing is on
+  const PhaseTimer* t; cudaStream_t s; int phase; cudaEvent_t b;
+  PhaseScope(const PhaseTimer* t_, cudaStream_t s_, int phase_) : t(t_), s(s_), phase(phase_), b(nullptr) {
+    if (t) { b = t->next_event(t->ctx); cudaEventRecord(b, s); }
+  }
+  ~PhaseScope() {
+    if (t) { cudaEvent_t e = t->next_event(t->ctx); cudaEventRecord(e, s); t->mark(t->ctx, phase, b, e); }
+  }
+};
+}  // namespace
+
+cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches,
+                           const PhaseTimer* timer) {
   *launches = 0;
   if (args.chunk_n <= 0) return cudaSuccess;
   const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
@@ -483,45 +496,53 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     pre.qacc_discrete = nullptr;
     pre.has_contacts = 0;
     const size_t s0 = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
+    { PhaseScope ps(timer, stream, kPhaseSmooth);
     e = in_smem ? launch_phase(smooth_kernel<true>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
-                : launch_phase(smooth_kernel<false>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads);
+                : launch_phase(smooth_kernel<false>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads); }
     if (e != cudaSuccess) return e;
+    { PhaseScope ps(timer, stream, kPhaseInertia);
     e = in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
-                : launch_phase(inertia_kernel<false>, pre, 0, 8, stream);
+                : launch_phase(inertia_kernel<false>, pre, 0, 8, stream); }
     if (e != cudaSuccess) return e;
+    { PhaseScope ps(timer, stream, kPhaseDiscrete);
     e = in_smem ? launch_phase(discrete_acc_kernel<true>, args, smem, 8, stream)
-                : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream);
+                : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream); }
     if (e != cudaSuccess) return e;
     *launches += 3;
     LaunchArgs post = args;
     post.qacc = args.qacc_discrete;
     post.qacc_discrete = nullptr;
     int n2 = 0;
-    e = launch_inverse(post, stream, &n2);
+    e = launch_inverse(post, stream, &n2, timer);
     *launches += n2;
     return e;
   }
   const size_t ssmem = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
+  { PhaseScope ps(timer, stream, kPhaseSmooth);
   e = in_smem ? launch_phase(smooth_kernel<true>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
-              : launch_phase(smooth_kernel<false>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads);
+              : launch_phase(smooth_kernel<false>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads); }
   if (e != cudaSuccess) return e;
   ++*launches;
   if (want_inertia) {
+    PhaseScope ps(timer, stream, kPhaseInertia);
     e = in_smem ? launch_phase(inertia_kernel<true>, args, smem, 8, stream)
                 : launch_phase(inertia_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }
   if (args.has_contacts) {
+    { PhaseScope ps(timer, stream, kPhaseScan);
     e = in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
-                : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream);
+                : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream); }
     if (e != cudaSuccess) return e;
     const size_t csmem = contact_smem_bytes(args.model_bytes, args.model_in_smem, args.max_pair_contacts);
+    { PhaseScope ps(timer, stream, kPhaseContact);
     e = in_smem ? launch_phase(contact_kernel<true>, args, csmem, 8, stream)
-                : launch_phase(contact_kernel<false>, args, csmem, 8, stream);
+                : launch_phase(contact_kernel<false>, args, csmem, 8, stream); }
     if (e != cudaSuccess) return e;
     *launches += 2;
   }
+  PhaseScope ps_backward(timer, stream, kPhaseBackward);
   if (args.has_gravcomp) {
     e = in_smem ? launch_phase(backward_kernel<true, true>, args, smem, 8, stream)
                 : launch_phase(backward_kernel<false, true>, args, 0, 8, stream);

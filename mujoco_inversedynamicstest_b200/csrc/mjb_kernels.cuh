@@ -40,9 +40,21 @@ struct LaunchArgs {
   Outputs out;
 };
 
+// phase ids for the optional per-kernel timing
+enum { kPhaseSmooth = 0, kPhaseInertia, kPhaseScan, kPhaseContact, kPhaseBackward, kPhaseDiscrete, kPhaseCount };
+
+// optional per-kernel timing: launch_inverse records a CUDA event before and after every phase
+// kernel on the launching stream (events come from the host-side pool below)
+struct PhaseTimer {
+  cudaEvent_t (*next_event)(void* ctx);      // returns a fresh event from the owner's pool
+  void (*mark)(void* ctx, int phase, cudaEvent_t begin, cudaEvent_t end);
+  void* ctx;
+};
+
 // launches the phase kernels (smooth, [inertia], [contact], backward) for one chunk on `stream`;
 // *launches receives the number of kernels launched
-cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches);
+cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches,
+                           const PhaseTimer* timer = nullptr);
 
 // AoS [n][rows] (host layout, as in looping mju_copy into d->qpos) <-> SoA [rows][stride]
 cudaError_t launch_aos_to_soa(const double* aos, double* soa, int n, int rows, long long stride,
