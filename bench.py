@@ -85,8 +85,22 @@ class ClockSampler:
         self.index = index
         self.samples = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
+        # NVML in-process (a sample every few ms, so even a 100 ms timed region is covered);
+        # nvidia-smi -lms as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -97,18 +111,40 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                ("sw_power_cap", 0x4))
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                flags = ["Active" if (r & b) else "Not Active" for _, b in bits]
+                self.samples.append(", ".join([str(sm), str(smax)] + flags))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
     def stop(self):
-        if not self.proc:
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
@@ -201,6 +237,11 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: route everything else written to fd 1 by libraries
+    # (NCCL version banner, ...) to stderr and keep the real stdout for the result line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -48,6 +48,14 @@ def main():
             u = units[col[k]]
             v[k] = x * UNIT.get(u, 1.0) if k.startswith(("dram__bytes", "gpu__time")) else x
             print(f"{k:88s} {r[col[k]]:>18s} {u}")
+        if "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum" not in v:
+            # `--set full` of this ncu carries the fp64 op counts only per cycle: flops per kernel are
+            # taken from the launch list instead (tools/launch_summary.py)
+            by = v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]
+            t = v["gpu__time_duration.sum"]
+            print(f"derived: {by/nstates:9.0f} DRAM B/state {by/t*1e-9:7.0f} GB/s DRAM "
+                  f"({100*by/t*1e-9/peak_gbs:4.1f}% of HBM copy peak)\n")
+            continue
         fl = (v["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] +
               v["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] +
               2 * v["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"])
@@ -56,6 +64,8 @@ def main():
         tot["flops"] += fl; tot["bytes"] += by; tot["t"] += t
         print(f"derived: {fl/nstates:9.0f} fp64 flop/state {by/nstates:9.0f} DRAM B/state {fl/t*1e-12:6.2f} TFLOP/s "
               f"({100*fl/t*1e-12/peak_tf:4.1f}% of DFMA probe) {by/t*1e-9:7.0f} GB/s DRAM ({100*by/t*1e-9/peak_gbs:4.1f}% of HBM copy peak)\n")
+    if tot["t"] == 0:
+        return
     print(f"== sum over the kernels: {tot['flops']/nstates:.0f} fp64 flop/state, {tot['bytes']/nstates:.0f} DRAM B/state, "
           f"{tot['t']*1e3:.2f} ms per chunk ({nstates/tot['t']:.3g} states/s under ncu), "
           f"{tot['flops']/tot['t']*1e-12:.2f} TFLOP/s = {100*tot['flops']/tot['t']*1e-12/peak_tf:.1f}% of the {peak_tf} TFLOP/s DFMA probe, "

@@ -1,0 +1,52 @@
+"""Refresh profiles/flops_per_state.json from an ncu launch list (tools/gpu_check.sh):
+    python tools/update_counts.py gpurun_out/l_TAG.csv [workload]"""
+import csv
+import json
+import os
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    path = sys.argv[1]
+    workload = sys.argv[2] if len(sys.argv) > 2 else "humanoid_contact_pyramidal"
+    nst = float(sys.argv[3]) if len(sys.argv) > 3 else 1048576.0
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, mi, vi, ii = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "ID"))
+    d = OrderedDict()
+    for r in rows[1:]:
+        d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(",", ""))
+    # the last bench step: every kernel between the last two smooth_kernel launches' first chunk
+    items = list(d.items())
+    last = [i for i, ((_, k), _) in enumerate(items) if "backward" in k]
+    step = items[last[-3] + 1:last[-1] + 1] if len(last) >= 3 else items[-10:]
+    K = {}
+    for (_, k), m in step:
+        name = k.split("(")[0].replace("void ", "").split("<")[0].replace("_kernel", "")
+        e = K.setdefault(name, {"flops": 0.0, "dram_bytes": 0.0, "warp_inst": 0.0})
+        e["flops"] += (m["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] +
+                       m["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] +
+                       2 * m["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]) / nst
+        e["dram_bytes"] += (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / nst
+        e["warp_inst"] += m.get("smsp__inst_executed.sum", 0.0) / nst
+    for e in K.values():
+        for k in e:
+            e[k] = round(e[k], 1)
+    out = os.path.join(ROOT, "profiles", "flops_per_state.json")
+    rec = json.load(open(out)) if os.path.exists(out) else {}
+    rec[workload] = {
+        "flops_per_state": round(sum(e["flops"] for e in K.values()), 1),
+        "dram_bytes_per_state": round(sum(e["dram_bytes"] for e in K.values()), 1),
+        "kernels": K,
+        "source": "ncu launch list of one bench step (%s): per kernel, (dadd + dmul + 2*dfma thread "
+                  "instructions) and dram__bytes_read+write, divided by the %d states of the step; "
+                  "qM/qLD/qLDiagInv outputs on" % (os.path.basename(path), int(nst))}
+    json.dump(rec, open(out, "w"), indent=1)
+    print(json.dumps(rec[workload]["kernels"]))
+
+
+if __name__ == "__main__":
+    main()
