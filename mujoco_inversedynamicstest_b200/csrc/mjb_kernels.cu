@@ -198,6 +198,11 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
 // Lanes are ~fully occupied in 2 and 3, and all memory traffic stays inside the 32 scratch
 // columns of the warp (same 256-byte lines), unlike a global sort of states.
 
+// records per warp: 32 + 64 for pairs with <= 2 contacts (the humanoid), 32 + 4*maxper otherwise
+__host__ __device__ inline int contact_pool_cap(int maxper) {
+  return 32 + (4*maxper > 64 ? 4*maxper : 64);
+}
+
 struct PoolRec {
   int owner;
   int ci;
@@ -236,8 +241,12 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
 
   // dynamic shared memory after the model blob: survivor lists, then per-warp pools and counters
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // pool of contact records per warp: 31 left over from the last full-round drain plus one round
+  // of narrow-phase output. Pairs that can yield many contacts (box-box: 24 before clean-up) get
+  // fewer lanes per round (per_round) instead of a larger pool.
   const int maxper = H.max_pair_contacts;
-  const int pool_cap = 32*maxper + 32;
+  const int pool_cap = contact_pool_cap(maxper);
+  const int per_round = (pool_cap - 32) / maxper < 32 ? (pool_cap - 32) / maxper : 32;
   size_t off = kModelInSmem ? (size_t)((a.model_bytes + 127) & ~127) : 0;
   int* lists = reinterpret_cast<int*>(smem + off);
   off += sizeof(int) * kListCap * kThreads;
@@ -389,10 +398,10 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
       __syncwarp();
 
       // step 2b: narrow phase of the hits
-      for (int j0 = 0; j0 < nhit; j0 += 32) {
+      for (int j0 = 0; j0 < nhit; j0 += per_round) {
         const int j = j0 + lane;
-        const bool has = j < nhit;
-        Con con[4];
+        const bool has = lane < per_round && j < nhit;
+        Con con[MJB_MAXCON_PAIR];
         int num = 0, ci = 0, o = 0;
         if (has) {
           o = (unsigned)hits[j] >> 27; ci = hits[j] & 0x7ffffff;
@@ -410,10 +419,12 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
         }
         pool_n += __shfl_sync(0xffffffffu, nincl, 31);
         __syncwarp();
-        if (pool_n + 32*maxper > pool_cap) drain(false);
+        if (pool_n + per_round*maxper > pool_cap) drain(false);
       }
+      // a pass ends with an empty pool: the next pass restarts at owner 0, and the row numbering
+      // of a round relies on every owner forming ONE run of consecutive records
+      if (pool_n) drain(true);
     }
-    if (pool_n) drain(true);
 
     own.ncon = ncon; own.nefc = nefc;
     own.status |= wstatus[lane];
@@ -429,7 +440,7 @@ size_t contact_smem_bytes(int model_bytes, int model_in_smem, int max_pair_conta
   off += sizeof(int) * 128 * (kThreads / 32);
   off += sizeof(int) * 32 * kListCap * (kThreads / 32);
   off = (off + 15) & ~(size_t)15;
-  off += sizeof(PoolRec) * (size_t)(32*max_pair_contacts + 32) * (kThreads / 32);
+  off += sizeof(PoolRec) * (size_t)contact_pool_cap(max_pair_contacts) * (kThreads / 32);
   return off;
 }
 

@@ -1061,6 +1061,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
 // contacts
 
 struct Con { double dist; double pos[3]; double frame[9]; };
+#define MJB_MAXCON_PAIR 24   // most contacts one geom pair can yield before clean-up (box-box)
 
 // relative spatial motion of body b2 minus body b1 at point p, from a per-body carrier array
 // (cvel or cacc_lin): lin = (lin2 + ang2 x (p - O2)) - (lin1 + ang1 x (p - O1)), ang = ang2 - ang1
@@ -1766,8 +1767,443 @@ MJB_HD inline int capsule_capsule(Con* con, double margin, const double* pos1, c
   return n1 + n2 + n3 + n4;
 }
 
+// mjc_BoxBox (engine_collision_box.c:607-1343) followed by the driver's removal of bad and repeated
+// contacts (engine_collision_driver.c:1522-1590, mju_outsideBox engine_util_misc.c:911).
+//
+// Structure of the reference: (A) separating-axis search over the 6 face normals and the 9 edge x
+// edge directions, keeping the axis of least penetration; (B) face case: the other box's closest
+// face polygon is clipped against the reference face (edge/edge intersections, reference corners
+// inside the polygon, polygon corners inside the face) and points above the margin are dropped;
+// (C) edge case: the same clipping for the quadrilateral spanned by the two closest edges of box 2,
+// projected along the separating direction. The predicates decide how many contacts a pair yields,
+// so every expression keeps the reference's operand order.
+#define MJB_BOXBOX_MAXCON 24   // 16 edge clips + 4 + 4 corner points
+
+struct BoxAxes { int i0, i1, i2; double f0, f1, f2; };
+
+// axis permutation / signs that turn face `face` (0..2: +x,+y,+z of the frame, 3..5: the negatives)
+// into the local +z direction (the reference's rotmore matrices and rotaxis / rotmatx macros)
+MJB_DI BoxAxes box_face_axes(int face) {
+  BoxAxes a = {0, 1, 2, 1, 1, 1};
+  if (face == 0) { a.i0 = 2; a.f0 = -1; a.i2 = 0; }
+  else if (face == 1) { a.i1 = 2; a.f1 = -1; a.i2 = 1; }
+  else if (face == 3) { a.i0 = 2; a.i2 = 0; a.f2 = -1; }
+  else if (face == 4) { a.i1 = 2; a.i2 = 1; a.f2 = -1; }
+  else if (face == 5) { a.f0 = -1; a.f2 = -1; }
+  return a;
+}
+MJB_DI void box_rotmore(double* m, int face) {
+  for (int k = 0; k < 9; k++) m[k] = 0;
+  if (face == 0) { m[2] = -1; m[4] = 1; m[6] = 1; }
+  else if (face == 1) { m[0] = 1; m[5] = -1; m[7] = 1; }
+  else if (face == 2) { m[0] = 1; m[4] = 1; m[8] = 1; }
+  else if (face == 3) { m[2] = 1; m[4] = 1; m[6] = -1; }
+  else if (face == 4) { m[0] = 1; m[5] = 1; m[7] = -1; }
+  else { m[0] = -1; m[4] = 1; m[8] = -1; }
+}
+MJB_DI void box_rotaxis(double* res, const double* v, const BoxAxes& a) {
+  const double r0 = v[a.i0]*a.f0, r1 = v[a.i1]*a.f1, r2 = v[a.i2]*a.f2;
+  res[0] = r0; res[1] = r1; res[2] = r2;
+}
+MJB_DI void box_rotmatx(double* res, const double* m, const BoxAxes& a) {
+  for (int k = 0; k < 3; k++) {
+    res[k] = m[3*a.i0 + k]*a.f0; res[3 + k] = m[3*a.i1 + k]*a.f1; res[6 + k] = m[3*a.i2 + k]*a.f2;
+  }
+}
+MJB_DI void mulMatTVec3(double* res, const double* m, const double* v) {  // engine_util_blas.c:179
+  const double t0 = m[0]*v[0] + m[3]*v[1] + m[6]*v[2];
+  const double t1 = m[1]*v[0] + m[4]*v[1] + m[7]*v[2];
+  const double t2 = m[2]*v[0] + m[5]*v[1] + m[8]*v[2];
+  res[0] = t0; res[1] = t1; res[2] = t2;
+}
+MJB_DI void mulMatMatT3(double* res, const double* a, const double* b) {  // engine_util_blas.c:223
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) res[3*i + j] = a[3*i]*b[3*j] + a[3*i + 1]*b[3*j + 1] + a[3*i + 2]*b[3*j + 2];
+}
+
+// clip the segment (o, o + d) of the plane z = const against the rectangle |x| <= lim[0],
+// |y| <= lim[1]: parameters c1 in [0, 1] where it crosses the four border lines (the reference's
+// "lines" loop); calls emit(c1, q, l, c2) for every crossing inside the border segment
+template <typename F>
+MJB_DI void box_clip_line(const double* line, const double* lim, F emit) {
+  for (int q = 0; q < 2; q++) {
+    const double a = line[q], b = line[3 + q], c = line[1 - q], d = line[4 - q];
+    if (fabs(b) > MJB_MINVAL) {
+      for (int j = -1; j <= 1; j += 2) {
+        const double l = lim[q]*j;
+        const double c1 = (l - a)*(1/b);
+        if (c1 < 0 || c1 > 1) continue;
+        const double c2 = c + d*c1;
+        if (fabs(c2) > lim[1 - q]) continue;
+        emit(c1, q, l, c2);
+      }
+    }
+  }
+}
+
+// mju_outsideBox (engine_util_misc.c:911) with inflate = 1.01
+MJB_DI int outside_box(const double* point, const double* pos, const double* mat, const double* size) {
+  const double inflate = 1.01;
+  double vec[3] = {point[0] - pos[0], point[1] - pos[1], point[2] - pos[2]};
+  mulMatTVec3(vec, mat, vec);
+  const double big[3] = {size[0]*inflate, size[1]*inflate, size[2]*inflate};
+  if (vec[0] > big[0] || vec[0] < -big[0] || vec[1] > big[1] || vec[1] < -big[1] ||
+      vec[2] > big[2] || vec[2] < -big[2]) return 1;
+  const double small[3] = {size[0]/inflate, size[1]/inflate, size[2]/inflate};
+  if (vec[0] < small[0] && vec[0] > -small[0] && vec[1] < small[1] && vec[1] > -small[1] &&
+      vec[2] < small[2] && vec[2] > -small[2]) return -1;
+  return 0;
+}
+
+MJB_HD inline int box_box_raw(Con* con, double margin, const double* pos1, const double* mat1,
+                              const double* size1, const double* pos2, const double* mat2,
+                              const double* size2) {
+  double pos21[3], pos12[3], rot[9], rott[9], rotabs[9], rottabs[9], plen1[3], plen2[3];
+  double points[MJB_BOXBOX_MAXCON][3], depth[MJB_BOXBOX_MAXCON];
+  double clnorm[3] = {0, 0, 0};
+  int n = 0, code = -1, cle1 = 0, cle2 = 0, in = 0;
+  const double margin2 = margin*margin;
+  {
+    double t[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+    mulMatTVec3(pos21, mat1, t);
+    t[0] = pos1[0] - pos2[0]; t[1] = pos1[1] - pos2[1]; t[2] = pos1[2] - pos2[2];
+    mulMatTVec3(pos12, mat2, t);
+  }
+  for (int i = 0; i < 3; i++)        // rot = mat1' * mat2  (engine_util_blas.c:208)
+    for (int j = 0; j < 3; j++)
+      rot[3*i + j] = mat1[i]*mat2[j] + mat1[3 + i]*mat2[3 + j] + mat1[6 + i]*mat2[6 + j];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rott[3*j + i] = rot[3*i + j];
+  for (int i = 0; i < 9; i++) { rotabs[i] = fabs(rot[i]); rottabs[i] = fabs(rott[i]); }
+  mulMatVec3(plen2, rotabs, size2);
+  mulMatTVec3(plen1, rotabs, size1);
+
+  // (A) least-penetration axis: face normals of box 1 (code 0..5) and of box 2 (6..11)
+  double penetration = margin;
+  for (int i = 0; i < 3; i++) penetration += size1[i]*3 + size2[i]*3;
+  for (int i = 0; i < 3; i++) {
+    const double c1 = -fabs(pos21[i]) + size1[i] + plen2[i];
+    const double c2 = -fabs(pos12[i]) + size2[i] + plen1[i];
+    if (c1 < -margin || c2 < -margin) return 0;
+    if (c1 < penetration) { penetration = c1; code = i + 3*(pos21[i] < 0) + 0; }
+    if (c2 < penetration) { penetration = c2; code = i + 3*(pos12[i] < 0) + 6; }
+  }
+  // edge i of box 1 x edge j of box 2 (code 12 + 3i + j)
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      double ax[3] = {0, 0, 0};
+      if (i == 0) { ax[1] = -rott[3*j + 2]; ax[2] = +rott[3*j + 1]; }
+      else if (i == 1) { ax[0] = +rott[3*j + 2]; ax[2] = -rott[3*j + 0]; }
+      else { ax[0] = -rott[3*j + 1]; ax[1] = +rott[3*j + 0]; }
+      const double c1 = normalize3(ax);
+      if (c1 < MJB_MINVAL) continue;
+      const double c2 = dot3(pos21, ax);
+      double c3 = 0;
+      for (int k = 0; k < 3; k++) if (k != i) c3 += size1[k]*fabs(ax[k]);
+      for (int k = 0; k < 3; k++) if (k != j) c3 += size2[k]*rotabs[3*i + 3 - k - j]/c1;
+      c3 -= fabs(c2);
+      if (c3 < -margin) return 0;
+      if (c3 < penetration*(1 - 1e-12)) {
+        penetration = c3;
+        cle1 = 0;
+        for (int k = 0; k < 3; k++) if (k != i) if ((ax[k] > 0) ^ (c2 < 0)) cle1 += 1 << k;
+        cle2 = 0;
+        for (int k = 0; k < 3; k++)
+          if (k != j) if ((rot[3*i + 3 - k - j] > 0) ^ (c2 < 0) ^ ((k - j + 3) % 3 == 1)) cle2 += 1 << k;
+        code = 12 + i*3 + j;
+        clnorm[0] = ax[0]; clnorm[1] = ax[1]; clnorm[2] = ax[2];
+        in = c2 < 0;
+      }
+    }
+  }
+  if (code == -1) return 0;
+
+  if (code < 12) {
+    // (B) a face of box (q2 ? 2 : 1) is the reference face, turned to local +z
+    const int q1 = code % 6, q2 = code / 6;
+    const BoxAxes A = box_face_axes(q1);
+    double rotmore[9], r[9], rt[9], p[3], tmp1[3], s[3];
+    box_rotmore(rotmore, q1);
+    if (q2) {
+      mulMatMatT3(r, rotmore, rot);
+      box_rotaxis(p, pos12, A); box_rotaxis(tmp1, size2, A);
+      s[0] = size1[0]; s[1] = size1[1]; s[2] = size1[2];
+    } else {
+      box_rotmatx(r, rot, A);
+      box_rotaxis(p, pos21, A); box_rotaxis(tmp1, size1, A);
+      s[0] = size2[0]; s[1] = size2[1]; s[2] = size2[2];
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rt[3*j + i] = r[3*i + j];
+    const double ss[3] = {fabs(tmp1[0]), fabs(tmp1[1]), fabs(tmp1[2])};
+    const double lx = ss[0], ly = ss[1], hz = ss[2];
+    p[2] -= hz;
+    int clcorner = 0;
+    for (int i = 0; i < 3; i++) if (r[6 + i] < 0) clcorner += 1 << i;
+    double pts[6][3];
+    for (int a = 0; a < 6; a++) for (int k = 0; k < 3; k++) pts[a][k] = 0;
+    for (int k = 0; k < 3; k++) pts[0][k] = p[k];
+    for (int a = 0; a < 3; a++) {
+      const double sc = s[a]*((clcorner & (1 << a)) ? 1 : -1);
+      for (int k = 0; k < 3; k++) pts[0][k] += rt[3*a + k]*sc;
+    }
+    int m = 1;
+    for (int i = 0; i < 3; i++) {
+      if (fabs(r[6 + i]) < 0.5) {
+        const double sc = s[i]*((clcorner & (1 << i)) ? -2 : 2);
+        for (int k = 0; k < 3; k++) pts[m][k] = rt[3*i + k]*sc;
+        m++;
+      }
+    }
+    for (int k = 0; k < 3; k++) {
+      pts[3][k] = pts[0][k] + pts[1][k];
+      pts[4][k] = pts[0][k] + pts[2][k];
+      pts[5][k] = pts[3][k] + pts[2][k];
+    }
+    double lines[4][6];
+    int nlines = 0;
+    auto set_line = [&](const double* o, const double* d) {
+      for (int k = 0; k < 3; k++) { lines[nlines][k] = o[k]; lines[nlines][3 + k] = d[k]; }
+      nlines++;
+    };
+    if (m > 1) set_line(pts[0], pts[1]);
+    if (m > 2) { set_line(pts[0], pts[2]); set_line(pts[3], pts[2]); set_line(pts[4], pts[1]); }
+    for (int i = 0; i < nlines; i++) {
+      const double* L = lines[i];
+      box_clip_line(L, ss, [&](double c1, int, double, double) {
+        for (int k = 0; k < 3; k++) points[n][k] = L[k] + L[3 + k]*c1;
+        n++;
+      });
+    }
+    {
+      const double a = pts[1][0], b = pts[2][0], c = pts[1][1], d = pts[2][1];
+      const double c1 = a*d - b*c;
+      if (m > 2) {
+        for (int i = 0; i < 4; i++) {
+          const double llx = i / 2 ? lx : -lx, lly = i % 2 ? ly : -ly;
+          const double x = llx - pts[0][0], y = lly - pts[0][1];
+          const double u = (x*d - y*b)*(1/c1), v = (y*a - x*c)*(1/c1);
+          if (u <= 0 || v <= 0 || u >= 1 || v >= 1) continue;
+          points[n][0] = llx; points[n][1] = lly;
+          points[n][2] = (pts[0][2] + u*pts[1][2] + v*pts[2][2]);
+          n++;
+        }
+      }
+    }
+    for (int i = 0; i < (1 << (m - 1)); i++) {
+      const double* t = pts[i == 0 ? 0 : i + 2];
+      if (i) if (t[0] <= -lx || t[0] >= lx) continue;
+      if (i) if (t[1] <= -ly || t[1] >= ly) continue;
+      for (int k = 0; k < 3; k++) points[n][k] = t[k];
+      n++;
+    }
+    const int cand = n;
+    n = 0;
+    for (int i = 0; i < cand; i++) {
+      if (points[i][2] > margin) continue;
+      for (int k = 0; k < 3; k++) points[n][k] = points[i][k];
+      depth[n] = points[n][2];
+      points[n][2] *= 0.5;
+      n++;
+    }
+    mulMatMatT3(r, q2 ? mat2 : mat1, rotmore);
+    const double* pc = q2 ? pos2 : pos1;
+    const double sg = q2 ? -1 : 1;
+    const double nrm[3] = {sg*r[2], sg*r[5], sg*r[8]};
+    for (int i = 0; i < n; i++) {
+      con[i].dist = points[i][2];        // as the reference: the halved coordinate, not depth[i]
+      points[i][2] += hz;
+      double g[3];
+      mulMatVec3(g, r, points[i]);
+      for (int k = 0; k < 3; k++) { con[i].pos[k] = g[k] + pc[k]; con[i].frame[k] = nrm[k]; con[i].frame[3 + k] = 0; }
+    }
+    (void)depth;
+    return n;
+  }
+
+  // (C) edge i of box 1 against edge j of box 2
+  code -= 12;
+  const int q1 = code / 3, q2 = code % 3;
+  int ax1 = q2 == 0 ? 1 : (q2 == 1 ? 0 : 1), ax2 = q2 == 0 ? 2 : (q2 == 1 ? 2 : 0);
+  int pax1 = q1 == 0 ? 1 : (q1 == 1 ? 0 : 1), pax2 = q1 == 0 ? 2 : (q1 == 1 ? 2 : 0);
+  if (rotabs[3*q1 + ax1] < rotabs[3*q1 + ax2]) { ax1 = ax2; ax2 = 3 - q2 - ax1; }
+  if (rottabs[3*q2 + pax1] < rottabs[3*q2 + pax2]) { pax1 = pax2; pax2 = 3 - q1 - pax1; }
+  const int clface = (cle1 & (1 << pax2)) ? pax2 : pax2 + 3;
+  const BoxAxes A = box_face_axes(clface);
+  double rotmore[9], r[9], rt[9], p[3], rnorm[3], s[3];
+  box_rotmore(rotmore, clface);
+  box_rotaxis(p, pos21, A);
+  box_rotaxis(rnorm, clnorm, A);
+  box_rotmatx(r, rot, A);
+  {
+    double t[3];
+    mulMatTVec3(t, rotmore, size1);
+    s[0] = fabs(t[0]); s[1] = fabs(t[1]); s[2] = fabs(t[2]);
+  }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rt[3*j + i] = r[3*i + j];
+  const double lx = s[0], ly = s[1], hz = s[2];
+  p[2] -= hz;
+
+  // the four end points of the two closest edges of box 2 (direction q2)
+  for (int e = 0; e < 2; e++) {
+    const double s1 = size2[ax1]*(((cle2 & (1 << ax1)) != 0) == (e == 0) ? 1 : -1);
+    const double s2 = size2[ax2]*((cle2 & (1 << ax2)) ? 1 : -1);
+    double base[3];
+    for (int k = 0; k < 3; k++) base[k] = p[k];
+    for (int k = 0; k < 3; k++) base[k] += rt[3*ax1 + k]*s1;
+    for (int k = 0; k < 3; k++) base[k] += rt[3*ax2 + k]*s2;
+    for (int k = 0; k < 3; k++) {
+      points[2*e][k] = base[k] + rt[3*q2 + k]*size2[q2];
+      points[2*e + 1][k] = base[k] + rt[3*q2 + k]*(-size2[q2]);
+    }
+  }
+  double axi[3][3], pu[4][3], ppts2[4][2], pts[3][3];
+  for (int k = 0; k < 3; k++) {
+    axi[0][k] = points[0][k];
+    axi[1][k] = points[1][k] - points[0][k];
+    axi[2][k] = points[2][k] - points[0][k];
+  }
+  if (fabs(rnorm[2]) < MJB_MINVAL) return 0;
+  const double innorm = (1/rnorm[2])*(in ? -1 : 1);
+  for (int i = 0; i < 4; i++) {
+    const double c1 = -points[i][2]*(1/rnorm[2]);
+    for (int k = 0; k < 3; k++) pu[i][k] = points[i][k];
+    for (int k = 0; k < 3; k++) points[i][k] += rnorm[k]*c1;
+    ppts2[i][0] = points[i][0]; ppts2[i][1] = points[i][1];
+  }
+  for (int k = 0; k < 3; k++) {
+    pts[0][k] = points[0][k];
+    pts[1][k] = points[1][k] - points[0][k];
+    pts[2][k] = points[2][k] - points[0][k];
+  }
+  double lines[4][6], linesu[4][6];
+  for (int k = 0; k < 3; k++) {
+    lines[0][k] = pts[0][k]; lines[0][3 + k] = pts[1][k];
+    linesu[0][k] = axi[0][k]; linesu[0][3 + k] = axi[1][k];
+    lines[1][k] = pts[0][k]; lines[1][3 + k] = pts[2][k];
+    linesu[1][k] = axi[0][k]; linesu[1][3 + k] = axi[2][k];
+    lines[2][k] = pts[0][k] + pts[1][k]; lines[2][3 + k] = pts[2][k];
+    linesu[2][k] = axi[0][k] + axi[1][k]; linesu[2][3 + k] = axi[2][k];
+    lines[3][k] = pts[0][k] + pts[2][k]; lines[3][3 + k] = pts[1][k];
+    linesu[3][k] = axi[0][k] + axi[2][k]; linesu[3][3 + k] = axi[1][k];
+  }
+  n = 0;
+  for (int i = 0; i < 4; i++) {
+    const double* LU = linesu[i];
+    box_clip_line(lines[i], s, [&](double c1, int q, double l, double c2) {
+      if ((LU[2] + LU[5]*c1)*innorm > margin) return;
+      for (int k = 0; k < 3; k++) points[n][k] = LU[k]*0.5;
+      for (int k = 0; k < 3; k++) points[n][k] += LU[3 + k]*(0.5*c1);
+      points[n][0 + q] += 0.5*l;
+      points[n][1 - q] += 0.5*c2;
+      depth[n] = points[n][2]*innorm*2;
+      n++;
+    });
+  }
+  const int nl = n;
+  {
+    const double a = pts[1][0], b = pts[2][0], c = pts[1][1], d = pts[2][1];
+    // c1 starts as the determinant of the quadrilateral's edge vectors and is REUSED below for the
+    // squared distance, exactly like the reference (:1229-1277): once a corner gets that far, the
+    // following corners are tested with the overwritten value. Kept for identical contact sets.
+    double c1 = a*d - b*c;
+    for (int i = 0; i < 4; i++) {
+      const double llx = i / 2 ? lx : -lx, lly = i % 2 ? ly : -ly;
+      const double x = llx - pts[0][0], y = lly - pts[0][1];
+      double u = (x*d - y*b)*(1/c1), v = (y*a - x*c)*(1/c1);
+      if (nl == 0) {
+        if ((u < 0 || u > 1) && (v < 0 || v > 1)) continue;
+      } else {
+        if (u < 0 || u > 1 || v < 0 || v > 1) continue;
+      }
+      if (u < 0) u = 0;
+      if (u > 1) u = 1;
+      if (v < 0) v = 0;
+      if (v > 1) v = 1;
+      double t[3];
+      for (int k = 0; k < 3; k++) t[k] = pu[0][k]*(1 - u - v);
+      for (int k = 0; k < 3; k++) t[k] += pu[1][k]*u;
+      for (int k = 0; k < 3; k++) t[k] += pu[2][k]*v;
+      points[n][0] = llx; points[n][1] = lly; points[n][2] = 0;
+      const double df[3] = {points[n][0] - t[0], points[n][1] - t[1], points[n][2] - t[2]};
+      c1 = dot3(df, df);
+      if (t[2] > 0) if (c1 > margin2) continue;
+      for (int k = 0; k < 3; k++) points[n][k] = (points[n][k] + t[k])*0.5;
+      depth[n] = sqrt(c1)*(t[2] < 0 ? -1 : 1);
+      n++;
+    }
+  }
+  const int nf = n;
+  for (int i = 0; i < 4; i++) {
+    const double x = ppts2[i][0], y = ppts2[i][1];
+    if (nl == 0) {
+      if (nf != 0) if (x < -lx || x > lx) if (y < -ly || y > ly) continue;
+    } else {
+      if (x < -lx || x > lx || y < -ly || y > ly) continue;
+    }
+    double c1 = 0;
+    for (int j = 0; j < 2; j++) {
+      if (ppts2[i][j] < -s[j]) c1 += (ppts2[i][j] + s[j])*(ppts2[i][j] + s[j]);
+      else if (ppts2[i][j] > s[j]) c1 += (ppts2[i][j] - s[j])*(ppts2[i][j] - s[j]);
+    }
+    c1 += pu[i][2]*innorm*pu[i][2]*innorm;
+    if (pu[i][2] > 0) if (c1 > margin2) continue;
+    double t[3] = {ppts2[i][0]*0.5, ppts2[i][1]*0.5, 0};
+    for (int j = 0; j < 2; j++) {
+      if (ppts2[i][j] < -s[j]) t[j] = -s[j]*0.5;
+      else if (ppts2[i][j] > s[j]) t[j] = +s[j]*0.5;
+    }
+    for (int k = 0; k < 3; k++) points[n][k] = t[k] + pu[i][k]*0.5;
+    depth[n] = sqrt(c1)*(pu[i][2] < 0 ? -1 : 1);
+    n++;
+  }
+  mulMatMatT3(r, mat1, rotmore);
+  double wn[3];
+  mulMatVec3(wn, r, rnorm);
+  const double sg = in ? -1 : 1;
+  for (int i = 0; i < n; i++) {
+    con[i].dist = depth[i];
+    points[i][2] += hz;
+    double g[3];
+    mulMatVec3(g, r, points[i]);
+    for (int k = 0; k < 3; k++) { con[i].pos[k] = g[k] + pos1[k]; con[i].frame[k] = wn[k]*sg; con[i].frame[3 + k] = 0; }
+  }
+  return n;
+}
+
+// box-box with the driver's clean-up: contacts outside one box and not inside the other are bad,
+// of two contacts at exactly the same position the earlier one is dropped
+MJB_COLD inline int box_box(Con* con, double margin, const double* pos1, const double* mat1,
+                          const double* size1, const double* pos2, const double* mat2,
+                          const double* size2) {
+  const int num = box_box_raw(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+  const double sz1[3] = {size1[0] + margin, size1[1] + margin, size1[2] + margin};
+  const double sz2[3] = {size2[0] + margin, size2[1] + margin, size2[2] + margin};
+  unsigned bad = 0;
+  for (int i = 0; i < num; i++) {
+    const int out1 = outside_box(con[i].pos, pos1, mat1, sz1);
+    const int out2 = outside_box(con[i].pos, pos2, mat2, sz2);
+    if ((out1 == 1 && out2 != -1) || (out2 == 1 && out1 != -1)) bad |= 1u << i;
+  }
+  for (int i = 0; i < num - 1; i++) {
+    if (bad & (1u << i)) continue;
+    for (int j = i + 1; j < num; j++) {
+      if (bad & (1u << j)) continue;
+      if (con[i].pos[0] == con[j].pos[0] && con[i].pos[1] == con[j].pos[1] && con[i].pos[2] == con[j].pos[2]) {
+        bad |= 1u << i;
+        break;
+      }
+    }
+  }
+  int k = 0;
+  for (int j = 0; j < num; j++) {
+    if (bad & (1u << j)) continue;
+    if (k < j) con[k] = con[j];
+    k++;
+  }
+  return k;
+}
+
 // narrow phase of candidate pair ci on the state bound to c; contact frames are completed
-// (mju_makeFrame) before returning. Returns the number of contacts (<= 4).
+// (mju_makeFrame) before returning. Returns the number of contacts (<= MJB_MAXCON_PAIR).
 MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
@@ -1797,6 +2233,7 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
     case MJB_FN_PLANE_ELLIPSOID: num = plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_BOX: num = sphere_box(con, margin, pos1, size1, pos2, mat2, size2); break;
     case MJB_FN_CAPSULE_BOX: num = capsule_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_BOX_BOX: num = box_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_SPHERE:
       num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
     case MJB_FN_SPHERE_CAPSULE:
@@ -1893,7 +2330,7 @@ MJB_HD inline bool narrow_test(Ctx& c, int ci) {
 
 // narrow phase of one candidate pair followed by the rows of every contact it yields
 MJB_HD inline void collide_pair(Ctx& c, int ci) {
-  Con con[4];
+  Con con[MJB_MAXCON_PAIR];
   const int num = narrow_pair(c, ci, con);
   for (int k = 0; k < num; k++) process_contact(c, ci, con[k]);
 }

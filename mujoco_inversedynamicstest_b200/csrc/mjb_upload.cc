@@ -87,6 +87,8 @@ int narrowphaseId(int t1, int t2) {
         case mjGEOM_BOX: return MJB_FN_CAPSULE_BOX;
         default: return -2;
       }
+    case mjGEOM_BOX:
+      return (t2 == mjGEOM_BOX) ? MJB_FN_BOX_BOX : -2;
     default:
       return -2;
   }
@@ -415,7 +417,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     double cn[MJB_CAND_NN];
     ci[MJB_CI_G1] = g1; ci[MJB_CI_G2] = g2; ci[MJB_CI_FUNC] = fn; ci[MJB_CI_DIM] = condim;
     {
-      const int per = (fn == MJB_FN_PLANE_CYLINDER || fn == MJB_FN_PLANE_BOX) ? 4
+      const int per = fn == MJB_FN_BOX_BOX ? 24   /* MJB_MAXCON_PAIR */
+                      : (fn == MJB_FN_PLANE_CYLINDER || fn == MJB_FN_PLANE_BOX) ? 4
                       : (fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE ||
                          fn == MJB_FN_CAPSULE_BOX) ? 2 : 1;
       max_pair_contacts = std::max(max_pair_contacts, per);

@@ -45,6 +45,8 @@ CASES = {
     "humanoid_invdiscrete": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 3}, 128, (0.0, 1.5), 64, 256),
     "capsbox": ("repo:tests/golden/models/capsbox.xml", {}, 512, (0.0, 0.7), 48, 200),
     "capsbox_elliptic": ("repo:tests/golden/models/capsbox.xml", {"cone": 1}, 256, (0.0, 0.7), 48, 200),
+    "boxes": ("repo:tests/golden/models/boxes.xml", {}, 1024, (0.0, 0.7), 64, 300),
+    "boxes_elliptic": ("repo:tests/golden/models/boxes.xml", {"cone": 1}, 256, (0.0, 0.7), 64, 300),
     "gravcomp": ("repo:tests/golden/models/gravcomp.xml", {}, 128, (0.5, 1.5), 8, 16),
 }
 
