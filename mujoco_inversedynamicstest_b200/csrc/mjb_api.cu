@@ -292,7 +292,8 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_contacts = d->hdr.ncand > 0 &&
                    !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
   a.max_pair_contacts = d->hdr.max_pair_contacts;
-  a.has_gravcomp = d->hdr.has_gravcomp;
+  a.has_gravcomp = d->hdr.passive_wrench;
+  a.has_spatial = d->hdr.has_spatial;
   a.out = d->out;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
   for (long long start = first; start < first + count; start += d->chunk_stride) {

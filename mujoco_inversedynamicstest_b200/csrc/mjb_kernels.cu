@@ -120,7 +120,7 @@ __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long lon
 // memory and therefore more L1 for the streamed scratch rows.
 constexpr int kSmoothThreads = MJB_SMS;
 
-template <bool kModelInSmem>
+template <bool kModelInSmem, bool kSpatial = false>
 __global__ void __launch_bounds__(kSmoothThreads, MJB_CTAS_SMOOTH) smooth_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kSmoothThreads, MJB_CTAS_SMOOTH) smooth_kernel
   for (long long i = (long long)blockIdx.x * kSmoothThreads + threadIdx.x; i < a.chunk_n;
        i += (long long)gridDim.x * kSmoothThreads) {
     bind_state(c, a, i);
-    phase_smooth(c);
+    phase_smooth<kSpatial>(c);
   }
 }
 
@@ -492,6 +492,19 @@ static cudaError_t launch_phase(K kernel, const LaunchArgs& args, size_t smem, i
 }
 
 namespace {
+// the smooth kernel instantiation that contains the spatial-tendon path walk is used only by models
+// with force-carrying spatial tendons (it needs more registers than the plain one)
+cudaError_t launch_smooth(const LaunchArgs& a, cudaStream_t stream) {
+  const size_t sm = smooth_smem_bytes(a.model_bytes, a.model_in_smem);
+  const int cap = 2 * MJB_CTAS_SMOOTH;
+  if (a.has_spatial) {
+    return a.model_in_smem ? launch_phase(smooth_kernel<true, true>, a, sm, cap, stream, kSmoothThreads)
+                           : launch_phase(smooth_kernel<false, true>, a, sm, cap, stream, kSmoothThreads);
+  }
+  return a.model_in_smem ? launch_phase(smooth_kernel<true, false>, a, sm, cap, stream, kSmoothThreads)
+                         : launch_phase(smooth_kernel<false, false>, a, sm, cap, stream, kSmoothThreads);
+}
+
 struct PhaseScope {   // records begin/end events around one kernel launch when timing is on
   const PhaseTimer* t; cudaStream_t s; int phase; cudaEvent_t b;
   PhaseScope(const PhaseTimer* t_, cudaStream_t s_, int phase_) : t(t_), s(s_), phase(phase_), b(nullptr) {
@@ -517,10 +530,8 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     LaunchArgs pre = args;
     pre.qacc_discrete = nullptr;
     pre.has_contacts = 0;
-    const size_t s0 = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
     { PhaseScope ps(timer, stream, kPhaseSmooth);
-    e = in_smem ? launch_phase(smooth_kernel<true>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
-                : launch_phase(smooth_kernel<false>, pre, s0, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads); }
+    e = launch_smooth(pre, stream); }
     if (e != cudaSuccess) return e;
     { PhaseScope ps(timer, stream, kPhaseInertia);
     e = in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
@@ -539,10 +550,8 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     *launches += n2;
     return e;
   }
-  const size_t ssmem = smooth_smem_bytes(args.model_bytes, args.model_in_smem);
   { PhaseScope ps(timer, stream, kPhaseSmooth);
-  e = in_smem ? launch_phase(smooth_kernel<true>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads)
-              : launch_phase(smooth_kernel<false>, args, ssmem, 2 * MJB_CTAS_SMOOTH, stream, kSmoothThreads); }
+  e = launch_smooth(args, stream); }
   if (e != cudaSuccess) return e;
   ++*launches;
   if (want_inertia) {

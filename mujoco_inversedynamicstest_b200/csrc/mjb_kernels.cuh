@@ -38,6 +38,7 @@ struct LaunchArgs {
   long long stride;             // row stride of every state-indexed input/output array
   int nconmax, njmax;
   int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
+  int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
   Outputs out;

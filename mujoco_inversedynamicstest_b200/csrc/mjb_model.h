@@ -39,6 +39,7 @@
   X(dof_parentid, nv)            \
   X(dof_Madr, nv)                \
   X(dof_simplenum, nv)           \
+  X(site_bodyid, nsite)          \
   X(geom_type, ngeom)            \
   X(geom_bodyid, ngeom)          \
   X(tendon_adr, ntendon)         \
@@ -52,6 +53,7 @@
   X(jnt_limited, njnt)           \
   X(jnt_actgravcomp, njnt)       \
   X(geom_sameframe, ngeom)       \
+  X(site_sameframe, nsite)       \
   X(tendon_limited, ntendon)
 
 // ---- derived integer tables (built by mjb_upload.cc)
@@ -64,6 +66,7 @@
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
+  X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored) */
@@ -94,6 +97,7 @@
   X(geom_rbound, ngeom, 1)        \
   X(geom_pos, ngeom, 3)           \
   X(geom_quat, ngeom, 4)          \
+  X(site_pos, nsite, 3)           \
   X(tendon_range, ntendon, 2)     \
   X(tendon_margin, ntendon, 1)    \
   X(tendon_stiffness, ntendon, 1) \
@@ -227,9 +231,10 @@ enum {
   MJB_SC_qfrc_passive, // nv
   MJB_SC_ten_length,   // ntendon
   MJB_SC_ten_velocity, // ntendon
+  MJB_SC_ten_acc,      // ntendon   ten_J * qacc
   MJB_SC_crb,          // nbody*10  composite rigid-body inertias
   MJB_SC_ia,           // nbody*21  articulated-body inertias (symmetric 6x6, upper triangle)
-  MJB_SC_cfrc_gc,      // nbody*6   gravity-compensation wrenches (only when the model has gravcomp)
+  MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
   MJB_SC_COUNT
 };
 
@@ -247,6 +252,8 @@ typedef struct mjbHdr_ {
   // constraint-row counts that depend only on the model: equality rows, friction-loss rows of
   // dofs, friction-loss rows in total (dofs then tendons)
   int32_t ne_rows, nf_dof_rows, nf_rows;
+  int32_t has_spatial;      // some spatial tendon carries a force (its path is walked on the device)
+  int32_t passive_wrench;   // the passive body-wrench carrier exists (gravcomp or spatial-tendon springs/dampers)
   int32_t discrete_acc;     // mjENBL_INVDISCRETE with Euler and damped dofs: qacc is converted first
   double timestep, impratio;
   double gravity[3];
@@ -276,7 +283,7 @@ enum { MJB_STATE_SATISFIED = 0, MJB_STATE_QUADRATIC, MJB_STATE_LINEARNEG, MJB_ST
        MJB_STATE_CONE };
 enum { MJB_SAMEFRAME_NONE = 0, MJB_SAMEFRAME_BODY, MJB_SAMEFRAME_INERTIA, MJB_SAMEFRAME_BODYROT,
        MJB_SAMEFRAME_INERTIAROT };
-enum { MJB_WRAP_JOINT = 1 };
+enum { MJB_WRAP_NONE = 0, MJB_WRAP_JOINT, MJB_WRAP_PULLEY, MJB_WRAP_SITE, MJB_WRAP_SPHERE, MJB_WRAP_CYLINDER };
 #define MJB_MINVAL 1E-15
 #define MJB_MINMU 1E-5
 #define MJB_MINIMP 0.0001

@@ -177,68 +177,6 @@ MJB_DI double dot6(const double* a, const double* b) {
 }
 
 // ------------------------------------------------------------------------------------------
-// fixed tendons of mj_tendon (engine_core_smooth.c:699-723) and ten_velocity = ten_J*qvel
-// (engine_forward.c:205-210); spatial tendons are rejected at upload.
-MJB_HD inline void tendon_fixed(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  if (!H.ntendon) return;
-  double* L = SC(ten_length); double* V = SC(ten_velocity);
-  const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
-  const int* wrap_objid = MI(wrap_objid); const int* wrap_type = MI(wrap_type);
-  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
-  const double* wrap_prm = MD(wrap_prm);
-  for (int t = 0; t < H.ntendon; t++) {
-    const int adr = tendon_adr[t], num = tendon_num[t];
-    double len = 0, vel = 0;
-    // spatial tendons are accepted only when they carry no force: their length is not computed
-    const bool fixed = wrap_type[adr] == MJB_WRAP_JOINT;
-    for (int j = 0; fixed && j < num; j++) {
-      const int k = wrap_objid[adr + j];
-      len += wrap_prm[adr + j] * QPOS(jnt_qposadr[k]);
-      vel += wrap_prm[adr + j] * QVEL(jnt_dofadr[k]);
-    }
-    AT(L, t) = len;
-    AT(V, t) = vel;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// mj_passive (engine_passive.c:57-379,436-497): joint springs and dof dampers are evaluated per dof
-// inside the forward sweep (scalar_dof_forces / quat_dof_forces); this adds the tendon
-// spring-dampers; gravity compensation is a body wrench handled by the sweeps. Fluid, flex,
-// callbacks and plugins are rejected at upload.
-MJB_HD inline void passive_tendons(Ctx& c) {
-  const mjbHdr& H = *c.H;
-  if (H.disableflags & MJB_DSBL_PASSIVE) return;
-  double* qp = SC(qfrc_passive);
-  const int* jnt_dofadr = MI(jnt_dofadr);
-  if (H.ntendon) {
-    const double* stiff = MD(tendon_stiffness); const double* damp = MD(tendon_damping);
-    const double* ls = MD(tendon_lengthspring);
-    const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
-    const int* wrap_objid = MI(wrap_objid);
-    const double* wrap_prm = MD(wrap_prm);
-    double* L = SC(ten_length); double* V = SC(ten_velocity);
-    for (int t = 0; t < H.ntendon; t++) {
-      const double ks = stiff[t], kd = damp[t];
-      if (ks == 0 && kd == 0) continue;
-      const double len = AT(L, t), lower = ls[2*t], upper = ls[2*t+1];
-      double fs = 0;
-      if (len > upper) fs = ks*(upper - len);
-      else if (len < lower) fs = ks*(lower - len);
-      const double fd = -kd*AT(V, t);
-      const int adr = tendon_adr[t], num = tendon_num[t];
-      for (int j = 0; j < num; j++) {
-        const int dof = jnt_dofadr[wrap_objid[adr + j]];
-        const double J = wrap_prm[adr + j];
-        // spring and damper are accumulated separately in the reference, then added
-        AT(qp, dof) += J*fs + J*fd;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // constraint-row arithmetic shared by all row types
 
 // getimpedance (engine_core_constraint.c:1441-1489) on pre-clamped solimp
@@ -358,6 +296,390 @@ MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, c
   ldn(w, fe, 6*b, 6);
   for (int k = 0; k < 3; k++) { w[k] += cr[k] + T[k]; w[3 + k] += F[k]; }
   stn(fe, 6*b, w, 6);
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatial tendons (mj_tendon, engine_core_smooth.c:726-856; mju_wrap and its 2D helpers,
+// engine_util_misc.c:34-420). The path is a sequence of sites, optionally wrapping around a sphere
+// or cylinder between two sites, with pulleys scaling the branches. The reference builds the row
+// ten_J with mj_jacDifPair for every straight segment whose end points sit on different bodies;
+// here the segment itself is handed to a callback, which turns it into J*qvel / J*qacc (relative
+// point motion along the segment) or into J'*f (opposite forces along the segment on the two
+// bodies) without forming the row.
+
+MJB_DI double norm2(const double* v) { return sqrt(v[0]*v[0] + v[1]*v[1]); }
+MJB_DI double normalize2(double* v) {                    // mju_normalize with n = 2
+  const double norm = sqrt(v[0]*v[0] + v[1]*v[1]);
+  if (norm < MJB_MINVAL) { v[0] = 1; v[1] = 0; }
+  else { const double inv = 1/norm; v[0] *= inv; v[1] *= inv; }
+  return norm;
+}
+
+// do the 2D segments p1-p2 and p3-p4 intersect (engine_util_misc.c:34)
+MJB_DI bool wrap_intersect(const double* p1, const double* p2, const double* p3, const double* p4) {
+  const double det = (p4[1]-p3[1])*(p2[0]-p1[0]) - (p4[0]-p3[0])*(p2[1]-p1[1]);
+  if (fabs(det) < MJB_MINVAL) return false;
+  const double a = ((p4[0]-p3[0])*(p1[1]-p3[1]) - (p4[1]-p3[1])*(p1[0]-p3[0])) / det;
+  const double b = ((p2[0]-p1[0])*(p1[1]-p3[1]) - (p2[1]-p1[1])*(p1[0]-p3[0])) / det;
+  return a >= 0 && a <= 1 && b >= 0 && b <= 1;
+}
+
+// arc length between two points of the circle (:54)
+MJB_DI double wrap_arc(const double* p0, const double* p1, int ind, double radius) {
+  double p0n[2] = {p0[0], p0[1]}, p1n[2] = {p1[0], p1[1]};
+  normalize2(p0n); normalize2(p1n);
+  double angle = acos(p0n[0]*p1n[0] + p0n[1]*p1n[1]);
+  const double cross = p0[1]*p1[0] - p0[0]*p1[1];
+  if ((cross > 0 && ind) || (cross < 0 && !ind)) angle = 2*MJB_PI - angle;
+  return radius*angle;
+}
+
+// 2D wrap around a circle centred at the origin (:79-153): tangent points in pnt, arc length or -1
+MJB_HD inline double wrap_circle(double* pnt, const double* end, const double* side, double radius) {
+  const double sqlen0 = end[0]*end[0] + end[1]*end[1];
+  const double sqlen1 = end[2]*end[2] + end[3]*end[3];
+  const double sqrad = radius*radius;
+  if (sqlen0 < sqrad || sqlen1 < sqrad || radius < MJB_MINVAL) return -1;
+  const double dif[2] = {end[2] - end[0], end[3] - end[1]};
+  const double dd = dif[0]*dif[0] + dif[1]*dif[1];
+  if (dd < MJB_MINVAL) return -1;
+  double a = -(dif[0]*end[0] + dif[1]*end[1])/dd;
+  if (a < 0) a = 0; else if (a > 1) a = 1;
+  double tmp[2] = {a*dif[0] + end[0], a*dif[1] + end[1]};
+  if (tmp[0]*tmp[0] + tmp[1]*tmp[1] > sqrad && (!side || side[0]*tmp[0] + side[1]*tmp[1] >= 0)) return -1;
+  double sol[2][2][2], good[2];
+  for (int i = 0; i < 2; i++) {
+    const double sqrt0 = sqrt(sqlen0 - sqrad), sqrt1 = sqrt(sqlen1 - sqrad);
+    const int sgn = i == 0 ? 1 : -1;
+    sol[i][0][0] = (end[0]*sqrad + sgn*radius*end[1]*sqrt0)/sqlen0;
+    sol[i][0][1] = (end[1]*sqrad - sgn*radius*end[0]*sqrt0)/sqlen0;
+    sol[i][1][0] = (end[2]*sqrad - sgn*radius*end[3]*sqrt1)/sqlen1;
+    sol[i][1][1] = (end[3]*sqrad + sgn*radius*end[2]*sqrt1)/sqlen1;
+    if (side) {
+      tmp[0] = sol[i][0][0] + sol[i][1][0]; tmp[1] = sol[i][0][1] + sol[i][1][1];
+      normalize2(tmp);
+      good[i] = tmp[0]*side[0] + tmp[1]*side[1];
+    } else {
+      tmp[0] = sol[i][0][0] - sol[i][1][0]; tmp[1] = sol[i][0][1] - sol[i][1][1];
+      good[i] = -(tmp[0]*tmp[0] + tmp[1]*tmp[1]);
+    }
+    if (wrap_intersect(end, sol[i][0], end + 2, sol[i][1])) good[i] = -10000;
+  }
+  const int i = good[0] > good[1] ? 0 : 1;
+  pnt[0] = sol[i][0][0]; pnt[1] = sol[i][0][1]; pnt[2] = sol[i][1][0]; pnt[3] = sol[i][1][1];
+  if (wrap_intersect(end, pnt, end + 2, pnt + 2)) return -1;
+  return wrap_arc(sol[i][0], sol[i][1], i, radius);
+}
+
+// 2D wrap on the inside of the circle (:160-283): one touching point (both pnt pairs), 0 or -1
+MJB_HD inline double wrap_inside(double* pnt, const double* end, double radius) {
+  const int maxiter = 20;
+  const double zinit = 1 - 1e-7, tolerance = 1e-6;
+  const double len0 = norm2(end), len1 = norm2(end + 2);
+  const double dif[2] = {end[2] - end[0], end[3] - end[1]};
+  const double dd = dif[0]*dif[0] + dif[1]*dif[1];
+  if (len0 <= radius || len1 <= radius || radius < MJB_MINVAL || len0 < MJB_MINVAL || len1 < MJB_MINVAL) return -1;
+  if (dd > MJB_MINVAL) {
+    const double a = -(dif[0]*end[0] + dif[1]*end[1]) / dd;
+    if (a > 0 && a < 1) {
+      const double tmp[2] = {end[0] + dif[0]*a, end[1] + dif[1]*a};
+      if (norm2(tmp) <= radius) return -1;
+    }
+  }
+  pnt[0] = 0.5*(end[0] + end[2]); pnt[1] = 0.5*(end[1] + end[3]);
+  normalize2(pnt);
+  pnt[0] *= radius; pnt[1] *= radius;
+  pnt[2] = pnt[0]; pnt[3] = pnt[1];
+  const double A = radius/len0, B = radius/len1;
+  const double cosG = (len0*len0 + len1*len1 - dd) / (2*len0*len1);
+  if (cosG < -1 + MJB_MINVAL) return -1;
+  else if (cosG > 1 - MJB_MINVAL) return 0;
+  const double G = acos(cosG);
+  double z = zinit;
+  double f = asin(A*z) + asin(B*z) - 2*asin(z) + G;
+  if (f > 0) return 0;
+  int iter;
+  for (iter = 0; iter < maxiter && fabs(f) > tolerance; iter++) {
+    const double df = A/fmax(MJB_MINVAL, sqrt(1 - z*z*A*A)) + B/fmax(MJB_MINVAL, sqrt(1 - z*z*B*B)) -
+                      2/fmax(MJB_MINVAL, sqrt(1 - z*z));
+    if (df > -MJB_MINVAL) return 0;
+    const double z1 = z - f/df;
+    if (z1 > z) return 0;
+    z = z1;
+    f = asin(A*z) + asin(B*z) - 2*asin(z) + G;
+    if (f > tolerance) return 0;
+  }
+  if (iter >= maxiter) return 0;
+  double vec[2], ang;
+  if (end[0]*end[3] - end[1]*end[2] > 0) { vec[0] = end[0]; vec[1] = end[1]; ang = asin(z) - asin(A*z); }
+  else { vec[0] = end[2]; vec[1] = end[3]; ang = asin(z) - asin(B*z); }
+  normalize2(vec);
+  pnt[0] = radius*(cos(ang)*vec[0] - sin(ang)*vec[1]);
+  pnt[1] = radius*(sin(ang)*vec[0] + cos(ang)*vec[1]);
+  pnt[2] = pnt[0]; pnt[3] = pnt[1];
+  return 0;
+}
+
+// mju_wrap (:293-420): wrap the segment x0-x1 around a sphere (cylinder = false) or a cylinder;
+// returns the arc length and the two 3D tangent points in wpnt, or -1 when the straight segment is kept
+MJB_HD inline double wrap_geom(double* wpnt, const double* x0, const double* x1, const double* xpos,
+                               const double* xmat, double radius, bool cylinder, const double* side) {
+  double p[2][3], t[3];
+  t[0] = x0[0] - xpos[0]; t[1] = x0[1] - xpos[1]; t[2] = x0[2] - xpos[2];
+  for (int i = 0; i < 3; i++) p[0][i] = xmat[i]*t[0] + xmat[3 + i]*t[1] + xmat[6 + i]*t[2];
+  t[0] = x1[0] - xpos[0]; t[1] = x1[1] - xpos[1]; t[2] = x1[2] - xpos[2];
+  for (int i = 0; i < 3; i++) p[1][i] = xmat[i]*t[0] + xmat[3 + i]*t[1] + xmat[6 + i]*t[2];
+  if (sqrt(dot3(p[0], p[0])) < MJB_MINVAL || sqrt(dot3(p[1], p[1])) < MJB_MINVAL) return -1;
+  double axis[2][3];
+  if (!cylinder) {
+    axis[0][0] = p[0][0]; axis[0][1] = p[0][1]; axis[0][2] = p[0][2];
+    normalize3(axis[0]);
+    double normal[3];
+    cross3(normal, p[0], p[1]);
+    const double nrm = normalize3(normal);
+    if (nrm < MJB_MINVAL) {
+      int i = 0;
+      if (fabs(axis[0][1]) > fabs(axis[0][0]) && fabs(axis[0][1]) > fabs(axis[0][2])) i = 1;
+      if (fabs(axis[0][2]) > fabs(axis[0][0]) && fabs(axis[0][2]) > fabs(axis[0][1])) i = 2;
+      axis[1][0] = 1; axis[1][1] = 1; axis[1][2] = 1;
+      axis[1][i] = 0;
+      cross3(normal, axis[0], axis[1]);
+      normalize3(normal);
+    }
+    cross3(axis[1], normal, axis[0]);
+    normalize3(axis[1]);
+  } else {
+    axis[0][0] = 1; axis[0][1] = 0; axis[0][2] = 0;
+    axis[1][0] = 0; axis[1][1] = 1; axis[1][2] = 0;
+  }
+  double s[3] = {0, 0, 0}, d[4], sd[2] = {0, 0};
+  d[0] = dot3(p[0], axis[0]); d[1] = dot3(p[0], axis[1]);
+  d[2] = dot3(p[1], axis[0]); d[3] = dot3(p[1], axis[1]);
+  if (side) {
+    t[0] = side[0] - xpos[0]; t[1] = side[1] - xpos[1]; t[2] = side[2] - xpos[2];
+    for (int i = 0; i < 3; i++) s[i] = xmat[i]*t[0] + xmat[3 + i]*t[1] + xmat[6 + i]*t[2];
+    sd[0] = dot3(s, axis[0]); sd[1] = dot3(s, axis[1]);
+    normalize2(sd);
+    sd[0] *= radius; sd[1] *= radius;
+  }
+  double wlen, pnt[4];
+  if (side && sqrt(dot3(s, s)) < radius) wlen = wrap_inside(pnt, d, radius);
+  else wlen = wrap_circle(pnt, d, side ? sd : (const double*)0, radius);
+  if (wlen < 0) return -1;
+  double res[6];
+  for (int i = 0; i < 2; i++) {
+    for (int k = 0; k < 3; k++) res[3*i + k] = axis[0][k]*pnt[2*i];
+    for (int k = 0; k < 3; k++) res[3*i + k] += axis[1][k]*pnt[2*i + 1];
+  }
+  if (cylinder) {
+    const double L0 = sqrt((p[0][0]-res[0])*(p[0][0]-res[0]) + (p[0][1]-res[1])*(p[0][1]-res[1]));
+    const double L1 = sqrt((p[1][0]-res[3])*(p[1][0]-res[3]) + (p[1][1]-res[4])*(p[1][1]-res[4]));
+    res[2] = p[0][2] + (p[1][2] - p[0][2])*L0 / (L0 + wlen + L1);
+    res[5] = p[0][2] + (p[1][2] - p[0][2])*(L0 + wlen) / (L0 + wlen + L1);
+    const double height = fabs(res[5] - res[2]);
+    wlen = sqrt(wlen*wlen + height*height);
+  }
+  mulMatVec3(wpnt, xmat, res);
+  mulMatVec3(wpnt + 3, xmat, res + 3);
+  for (int k = 0; k < 3; k++) { wpnt[k] += xpos[k]; wpnt[3 + k] += xpos[k]; }
+  return wlen;
+}
+
+// world position of a site (mj_local2Global for sites, engine_core_smooth.c:172-177)
+MJB_HD inline void site_world_pos(Ctx& c, int sid, double* out) {
+  const int b = MI(site_bodyid)[sid];
+  const int sf = MI(site_sameframe)[sid];
+  double bp[3], bq[4], bm[9];
+  ldn(bp, SC(xpos), 3*b, 3);
+  if (sf == MJB_SAMEFRAME_BODY) { out[0] = bp[0]; out[1] = bp[1]; out[2] = bp[2]; return; }
+  ldn(bq, SC(xquat), 4*b, 4);
+  quat2Mat(bm, bq);
+  if (sf == MJB_SAMEFRAME_INERTIA) {
+    mulMatVec3(out, bm, MD(body_ipos) + 3*b);      // == xipos of the body
+  } else {
+    mulMatVec3(out, bm, MD(site_pos) + 3*sid);
+  }
+  out[0] += bp[0]; out[1] += bp[1]; out[2] += bp[2];
+}
+
+// Walk the path of spatial tendon t (engine_core_smooth.c:726-856). Returns its length; calls
+// seg(body_a, point_a, body_b, point_b, dir, divisor) for every straight segment between different
+// bodies, dir = unit vector from a to b.
+template <typename F>
+MJB_HD inline double spatial_tendon_walk(Ctx& c, int t, F seg) {
+  const int* wrap_type = MI(wrap_type); const int* wrap_objid = MI(wrap_objid);
+  const double* wrap_prm = MD(wrap_prm);
+  const int* site_bodyid = MI(site_bodyid); const int* geom_bodyid = MI(geom_bodyid);
+  const double* geom_size = MD(geom_size);
+  const int adr = MI(tendon_adr)[t], num = MI(tendon_num)[t];
+  double divisor = 1, L = 0;
+  int j = 0;
+  while (j < num - 1) {
+    int type0 = wrap_type[adr + j], type1 = wrap_type[adr + j + 1];
+    int id0 = wrap_objid[adr + j], id1 = wrap_objid[adr + j + 1];
+    if (type0 == MJB_WRAP_PULLEY || type1 == MJB_WRAP_PULLEY) {
+      if (type0 == MJB_WRAP_PULLEY) divisor = wrap_prm[adr + j];
+      j++;
+      continue;
+    }
+    double wlen = -1, wpnt[12];
+    int wbody[4], wrapid = -1;
+    bool wrapping = false;
+    site_world_pos(c, id0, wpnt);
+    wbody[0] = site_bodyid[id0];
+    if (type1 == MJB_WRAP_SPHERE || type1 == MJB_WRAP_CYLINDER) {
+      const bool cylinder = type1 == MJB_WRAP_CYLINDER;
+      wrapping = true;
+      wrapid = id1;
+      id1 = wrap_objid[adr + j + 2];
+      const double prm = wrap_prm[adr + j + 1];
+      const int sideid = (int)(prm + (prm > 0 ? 0.5 : -0.5));      // mju_round
+      double x1[3], gp[3], gm[9], sidep[3];
+      site_world_pos(c, id1, x1);
+      ldn(gp, SC(geom_xpos), 3*wrapid, 3); ldn(gm, SC(geom_xmat), 9*wrapid, 9);
+      if (sideid >= 0) site_world_pos(c, sideid, sidep);
+      wlen = wrap_geom(wpnt + 3, wpnt, x1, gp, gm, geom_size[3*wrapid], cylinder,
+                       sideid >= 0 ? sidep : (const double*)0);
+    }
+    if (wlen < 0) {
+      site_world_pos(c, id1, wpnt + 3);
+      wbody[1] = site_bodyid[id1];
+      const double d[3] = {wpnt[0] - wpnt[3], wpnt[1] - wpnt[4], wpnt[2] - wpnt[5]};
+      L += sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]) / divisor;
+    } else {
+      site_world_pos(c, id1, wpnt + 9);
+      wbody[1] = wbody[2] = geom_bodyid[wrapid];
+      wbody[3] = site_bodyid[id1];
+      const double d0[3] = {wpnt[0] - wpnt[3], wpnt[1] - wpnt[4], wpnt[2] - wpnt[5]};
+      const double d1[3] = {wpnt[6] - wpnt[9], wpnt[7] - wpnt[10], wpnt[8] - wpnt[11]};
+      L += (sqrt(d0[0]*d0[0] + d0[1]*d0[1] + d0[2]*d0[2]) + wlen +
+            sqrt(d1[0]*d1[0] + d1[1]*d1[1] + d1[2]*d1[2])) / divisor;
+    }
+    for (int k = 0; k < (wlen < 0 ? 1 : 3); k++) {
+      if (wbody[k] != wbody[k + 1]) {
+        double dif[3] = {wpnt[3*k + 3] - wpnt[3*k], wpnt[3*k + 4] - wpnt[3*k + 1], wpnt[3*k + 5] - wpnt[3*k + 2]};
+        normalize3(dif);
+        seg(wbody[k], wpnt + 3*k, wbody[k + 1], wpnt + 3*k + 3, dif, divisor);
+      }
+    }
+    j += wrapping ? 2 : 1;
+  }
+  return L;
+}
+
+// J*qvel and J*qacc of spatial tendon t from the body carriers
+MJB_HD inline double spatial_tendon_kinematics(Ctx& c, int t, double* vel, double* acc) {
+  double v = 0, a = 0;
+  const double L = spatial_tendon_walk(c, t, [&](int ba, const double* pa, int bb, const double* pb,
+                                                 const double* dif, double divisor) {
+    double la[3], lb[3], ang[3];
+    point_motion(c, SC(cvel), ba, pa, la, ang);
+    point_motion(c, SC(cvel), bb, pb, lb, ang);
+    const double dv[3] = {lb[0] - la[0], lb[1] - la[1], lb[2] - la[2]};
+    v += dot3(dif, dv) / divisor;
+    point_motion(c, SC(cacc_lin), ba, pa, la, ang);
+    point_motion(c, SC(cacc_lin), bb, pb, lb, ang);
+    const double da[3] = {lb[0] - la[0], lb[1] - la[1], lb[2] - la[2]};
+    a += dot3(dif, da) / divisor;
+  });
+  *vel = v; *acc = a;
+  return L;
+}
+
+// wrench [ (p - O_b) x F ; F ] on body b, added (sign +1) or subtracted (-1) in a carrier array
+MJB_HD inline void add_force_to(Ctx& c, double* carrier, int b, const double* p, const double* F, double sign) {
+  if (MI(body_static)[b]) return;
+  double o[3], r[3], cr[3], w[6];
+  ldn(o, SC(origin), 3*MI(body_rootid)[b], 3);
+  r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+  cross3(cr, r, F);
+  ldn(w, carrier, 6*b, 6);
+  for (int k = 0; k < 3; k++) { w[k] += sign*cr[k]; w[3 + k] += sign*F[k]; }
+  stn(carrier, 6*b, w, 6);
+}
+
+// J'*f of spatial tendon t: constraint forces go to the constraint-wrench carrier, passive forces
+// (spring, damper) to the passive-wrench carrier that the backward sweep projects into qfrc_passive
+MJB_HD inline void spatial_tendon_apply(Ctx& c, int t, double f, bool passive) {
+  double* carrier = passive ? SC(cfrc_gc) : SC(cfrc_ext);
+  spatial_tendon_walk(c, t, [&](int ba, const double* pa, int bb, const double* pb, const double* dif,
+                                double divisor) {
+    const double s = f / divisor;
+    const double F[3] = {dif[0]*s, dif[1]*s, dif[2]*s};
+    add_force_to(c, carrier, bb, pb, F, 1.0);
+    add_force_to(c, carrier, ba, pa, F, -1.0);
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_tendon (engine_core_smooth.c:651-860) without the Jacobian rows: length, J*qvel
+// (ten_velocity, engine_forward.c:205-210) and J*qacc of every tendon. Fixed tendons: coefficients
+// on scalar joints (:699-723); spatial tendons: the path walk above.
+template <bool kSpatial>
+MJB_HD inline void tendon_kinematics(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (!H.ntendon) return;
+  double* L = SC(ten_length); double* V = SC(ten_velocity); double* A = SC(ten_acc);
+  const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+  const int* wrap_objid = MI(wrap_objid); const int* wrap_type = MI(wrap_type);
+  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* tendon_active = MI(tendon_active);
+  const double* wrap_prm = MD(wrap_prm);
+  for (int t = 0; t < H.ntendon; t++) {
+    const int adr = tendon_adr[t], num = tendon_num[t];
+    double len = 0, vel = 0, acc = 0;
+    if (wrap_type[adr] == MJB_WRAP_JOINT) {
+      for (int j = 0; j < num; j++) {
+        const int k = wrap_objid[adr + j];
+        len += wrap_prm[adr + j] * QPOS(jnt_qposadr[k]);
+        vel += wrap_prm[adr + j] * QVEL(jnt_dofadr[k]);
+        acc += wrap_prm[adr + j] * QACC(jnt_dofadr[k]);
+      }
+    } else if (kSpatial && tendon_active[t]) {
+      // a spatial tendon that carries no force is output-only in the reference too: skipped
+      // (kSpatial: the path walk is compiled only into the kernel instantiation that needs it)
+      len = spatial_tendon_kinematics(c, t, &vel, &acc);
+    }
+    AT(L, t) = len; AT(V, t) = vel; AT(A, t) = acc;
+  }
+}
+
+// J'*f of tendon t into the joint-space accumulator (fixed) or the body-wrench carriers (spatial)
+template <bool kSpatial>
+MJB_HD inline void tendon_apply(Ctx& c, int t, double f, double* qdst, bool passive) {
+  const int adr = MI(tendon_adr)[t], num = MI(tendon_num)[t];
+  if (MI(wrap_type)[adr] == MJB_WRAP_JOINT) {
+    const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
+    const double* wrap_prm = MD(wrap_prm);
+    for (int j = 0; j < num; j++) AT(qdst, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
+  } else if (kSpatial) {
+    spatial_tendon_apply(c, t, f, passive);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_passive (engine_passive.c:57-379,436-497): joint springs and dof dampers are evaluated per dof
+// inside the forward sweep (scalar_dof_forces / quat_dof_forces); this adds the tendon
+// spring-dampers; gravity compensation is a body wrench handled by the sweeps. Fluid, flex,
+// callbacks and plugins are rejected at upload.
+template <bool kSpatial>
+MJB_HD inline void passive_tendons(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if ((H.disableflags & MJB_DSBL_PASSIVE) || !H.ntendon) return;
+  const double* stiff = MD(tendon_stiffness); const double* damp = MD(tendon_damping);
+  const double* ls = MD(tendon_lengthspring);
+  double* L = SC(ten_length); double* V = SC(ten_velocity);
+  for (int t = 0; t < H.ntendon; t++) {
+    const double ks = stiff[t], kd = damp[t];
+    if (ks == 0 && kd == 0) continue;
+    const double len = AT(L, t), lower = ls[2*t], upper = ls[2*t+1];
+    double fs = 0;
+    if (len > upper) fs = ks*(upper - len);
+    else if (len < lower) fs = ks*(lower - len);
+    const double fd = -kd*AT(V, t);
+    // spring and damper are accumulated separately in the reference, then added
+    tendon_apply<kSpatial>(c, t, fs + fd, SC(qfrc_passive), true);
+  }
 }
 
 // 0.5 * vec( quat1 * (0, a) * quat )   (engine_core_constraint.c:617-635)
@@ -639,6 +961,7 @@ MJB_HD inline void quat_dof_forces(Ctx& c, int jid, int qadr, int dof, int jt, c
 }
 
 // friction-loss rows of fixed tendons (engine_core_constraint.c:793-816), after the dof rows
+template <bool kSpatial>
 MJB_HD inline void tendon_friction_rows(Ctx& c) {
   const mjbHdr& H = *c.H;
   if ((H.disableflags & MJB_DSBL_FRICTIONLOSS) || !H.ntendon) return;
@@ -649,21 +972,19 @@ MJB_HD inline void tendon_friction_rows(Ctx& c) {
   const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
   const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
   const double* wrap_prm = MD(wrap_prm);
-  double* V = SC(ten_velocity);
+  double* V = SC(ten_velocity); double* A = SC(ten_acc);
   int row = H.ne_rows + H.nf_dof_rows;
   for (int t = 0; t < H.ntendon; t++) {
     if (tfl[t] > 0) {
-      const int adr = tendon_adr[t], num = tendon_num[t];
-      double jacc = 0;
-      for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
       const double f = scalar_row(c, row++, MJB_CNSTR_FRICTION_TENDON, t, tsp + MJB_SP_N*t, 0, 0, tiw[t],
-                                  AT(V, t), jacc, tfl[t]);
-      for (int j = 0; j < num; j++) AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
+                                  AT(V, t), AT(A, t), tfl[t]);
+      tendon_apply<kSpatial>(c, t, f, qc, false);
     }
   }
 }
 
 // limit rows of fixed tendons (engine_core_constraint.c:923-955), after the joint limit rows
+template <bool kSpatial>
 MJB_HD inline void tendon_limit_rows(Ctx& c) {
   const mjbHdr& H = *c.H;
   if ((H.disableflags & MJB_DSBL_LIMIT) || !H.ntendon) return;
@@ -677,21 +998,17 @@ MJB_HD inline void tendon_limit_rows(Ctx& c) {
   const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
   const int* wrap_objid = MI(wrap_objid);
   const double* wrap_prm = MD(wrap_prm);
-  double* L = SC(ten_length); double* V = SC(ten_velocity);
+  double* L = SC(ten_length); double* V = SC(ten_velocity); double* A = SC(ten_acc);
   for (int t = 0; t < H.ntendon; t++) {
     if (!tendon_limited[t]) continue;
     const double value = AT(L, t), margin = tendon_margin[t];
     for (int side = -1; side <= 1; side += 2) {
       const double dist = side * (tendon_range[2*t + (side + 1)/2] - value);
       if (dist < margin) {
-        const int adr = tendon_adr[t], num = tendon_num[t];
-        double jacc = 0;
-        for (int j = 0; j < num; j++) jacc += wrap_prm[adr + j]*QACC(jnt_dofadr[wrap_objid[adr + j]]);
+        // J = -side * ten_J
         const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_TENDON, t,
-                                    tsp + MJB_SP_N*t, dist, margin, tiw[t], -side*AT(V, t), -side*jacc, 0);
-        for (int j = 0; j < num; j++) {
-          AT(qc, jnt_dofadr[wrap_objid[adr + j]]) += -side*wrap_prm[adr + j]*f;
-        }
+                                    tsp + MJB_SP_N*t, dist, margin, tiw[t], -side*AT(V, t), -side*AT(A, t), 0);
+        tendon_apply<kSpatial>(c, t, -side*f, qc, false);
         c.nl++;
       }
     }
@@ -1036,15 +1353,18 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       crossForce(u2, V, u1);
       for (int k = 0; k < 6; k++) f[k] += u2[k];
       sts(cfrc, 6*b, f, 6);
-      if (H.has_gravcomp) {
-        // mj_gravcomp (engine_passive.c:381-401): force -gravity*mass*gravcomp at the body's centre
-        // of mass, kept as a wrench about O and projected on the dofs in the backward sweep
-        const double sgc = -(body_mass[b] * MD(body_gravcomp)[b]);
-        const double F[3] = {H.gravity[0]*sgc, H.gravity[1]*sgc, H.gravity[2]*sgc};
-        double wg[6];
-        cross3(wg, off, F);
-        wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
-        sts(SC(cfrc_gc), 6*b, wg, 6);
+      if (H.passive_wrench) {
+        // passive-wrench carrier (projected into qfrc_passive by the backward sweep): starts with
+        // mj_gravcomp (engine_passive.c:381-401), force -gravity*mass*gravcomp at the body's centre
+        // of mass as a wrench about O; spatial-tendon springs and dampers are added later
+        double wg[6] = {0, 0, 0, 0, 0, 0};
+        if (H.has_gravcomp) {
+          const double sgc = -(body_mass[b] * MD(body_gravcomp)[b]);
+          const double F[3] = {H.gravity[0]*sgc, H.gravity[1]*sgc, H.gravity[2]*sgc};
+          cross3(wg, off, F);
+          wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
+        }
+        stn(SC(cfrc_gc), 6*b, wg, 6);
       }
     }
 
@@ -2471,7 +2791,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       ldn(cd, cdof, 6*i, 6);
       const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
       double passive_i = AT(qp, i);
-      if (gcomp && !jnt_actgravcomp[dof_jntid[i]]) passive_i += dot6(cd, g);
+      if (gcomp && !(H.has_gravcomp && jnt_actgravcomp[dof_jntid[i]])) passive_i += dot6(cd, g);
       double res = dot6(cd, f);
       res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
       c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
@@ -2705,21 +3025,22 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
 //   contact  : mj_collision + contact rows             (only when contacts are enabled)
 //   backward : mj_rne(flg_acc=1), J'f, final combine, output bookkeeping
 
+template <bool kSpatial>
 MJB_HD inline void phase_smooth(Ctx& c) {
   const mjbHdr& H = *c.H;
   c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
   c.status = 0;
   forward_sweep(c);        // incl. input checks, joint springs/dampers, dof friction and joint limit rows
-  tendon_fixed(c);
-  passive_tendons(c);
+  tendon_kinematics<kSpatial>(c);
+  passive_tendons<kSpatial>(c);
   {
     double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);
     for (int i = 0; i < 6*H.nbody; i++) { AT(fe, i) = 0; AT(fe1, i) = 0; }
   }
   if (rows_enabled(H)) {
     equality_rows(c);      // rows [0, ne)
-    tendon_friction_rows(c);
-    tendon_limit_rows(c);
+    tendon_friction_rows<kSpatial>(c);
+    tendon_limit_rows<kSpatial>(c);
     c.nf = H.nf_rows;
   }
   c.nefc = c.ne + c.nf + c.nl;
@@ -2775,19 +3096,19 @@ MJB_HD inline void phase_backward(Ctx& c) {
 // all phases for one state in sequence (single-lane host build of the tests)
 MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   int list[64];
-  phase_smooth(c);
+  phase_smooth<true>(c);
   if (c.out.qM || c.out.qLD || c.out.qLDiagInv) phase_inertia(c);
   if (c.H->discrete_acc) {
     // converted accelerations replace qacc for everything that follows (engine_inverse.c:227-252)
     discrete_acc(c, qacc_discrete + c.s);
     c.qacc = qacc_discrete + c.s;
-    phase_smooth(c);
+    phase_smooth<true>(c);
   }
   if (contacts_enabled(*c.H)) {
     contact_scan(c);
     phase_contact(c, true, list, 1, 64);
   }
-  if (c.H->has_gravcomp) phase_backward<true>(c); else phase_backward<false>(c);
+  if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
 }
 
 #undef MI

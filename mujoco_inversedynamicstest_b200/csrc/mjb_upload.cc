@@ -241,16 +241,17 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   for (int t = 0; t < m->ntendon; t++) {
     const int adr = m->tendon_adr[t];
     if (m->wrap_type[adr] != mjWRAP_JOINT) {
-      // a spatial tendon only produces outputs (ten_length, ten_J) unless one of these is set;
-      // those outputs are not computed here, its effect on qfrc_inverse would need mju_wrap
-      const bool dynamic = (m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints) ||
-                           (m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints) ||
-                           ((m->tendon_stiffness[t] != 0 || m->tendon_damping[t] != 0) && !(dsbl & mjDSBL_PASSIVE)) ||
-                           tendon_in_equality[t];
-      if (dynamic) {
-        setError(err, "spatial tendon %d has a limit / spring / damper / friction loss / equality: "
-                      "spatial tendons are only supported when they carry no force", t);
+      // spatial tendon: its path is walked on the device when it carries a force (limit, friction
+      // loss, spring, damper); couplings through equality constraints are not supported yet
+      if (tendon_in_equality[t]) {
+        setError(err, "spatial tendon %d is used by an equality constraint (not supported)", t);
         return false;
+      }
+      for (int j = 0; j < m->tendon_num[t]; j++) {
+        const int wt = m->wrap_type[adr + j];
+        if (wt != mjWRAP_SITE && wt != mjWRAP_SPHERE && wt != mjWRAP_CYLINDER && wt != mjWRAP_PULLEY) {
+          setError(err, "spatial tendon %d has an unknown wrap object type", t); return false;
+        }
       }
       continue;
     }
@@ -559,6 +560,27 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     }
   }
 
+  // tendons that carry a force; spatial ones with springs/dampers need the passive wrench carrier
+  std::vector<int> tendon_active(m->ntendon, 0);
+  bool spatial_passive = false, spatial_active = false;
+  for (int t = 0; t < m->ntendon; t++) {
+    const bool lim = m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints;
+    const bool fric = m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints;
+    const bool pas = (m->tendon_stiffness[t] != 0 || m->tendon_damping[t] != 0) && !(dsbl & mjDSBL_PASSIVE);
+    tendon_active[t] = lim || fric || pas;
+    if (pas && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_passive = true;
+    if (tendon_active[t] && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_active = true;
+  }
+  if (spatial_passive && gravcomp) {
+    for (int j = 0; j < m->njnt; j++) {
+      if (m->jnt_actgravcomp[j]) {
+        err = "spatial-tendon springs/dampers together with actuator-routed gravity compensation "
+              "(jnt_actgravcomp) are not supported";
+        return false;
+      }
+    }
+  }
+
   // ---- assemble
   mjbHdr H;
   std::memset(&H, 0, sizeof(H));
@@ -569,6 +591,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.max_pair_contacts = max_pair_contacts;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
+  H.passive_wrench = (gravcomp || spatial_passive) ? 1 : 0;
+  H.has_spatial = spatial_active ? 1 : 0;
   H.discrete_acc = discrete ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
@@ -597,6 +621,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_cand_int, cand_int.data(), cand_int.size());
   pushInts(MJB_I_eq_int, eq_int.data(), eq_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
+  pushInts(MJB_I_tendon_active, tendon_active.data(), tendon_active.size());
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
   {
     // static row numbering (mj_makeConstraint order: equality, dof friction, tendon friction, ...)
@@ -652,9 +677,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
     sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_cfrc_ext1] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
     sizes[MJB_SC_qfrc_passive] = nv;
-    sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt;
+    sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt; sizes[MJB_SC_ten_acc] = nt;
     sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
-    sizes[MJB_SC_cfrc_gc] = gravcomp ? 6*nb : 0;
+    sizes[MJB_SC_cfrc_gc] = (gravcomp || spatial_passive) ? 6*nb : 0;
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;
@@ -677,7 +702,7 @@ const char* scratchSlotName(int slot) {
   static const char* names[MJB_SC_COUNT] = {
     "xpos", "xquat", "origin", "geom_xpos", "geom_xmat",
     "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
-    "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "crb", "ia",
+    "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "ten_acc", "crb", "ia",
     "cfrc_gc"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }

@@ -47,6 +47,7 @@ CASES = {
     "capsbox_elliptic": ("repo:tests/golden/models/capsbox.xml", {"cone": 1}, 256, (0.0, 0.7), 48, 200),
     "boxes": ("repo:tests/golden/models/boxes.xml", {}, 1024, (0.0, 0.7), 64, 300),
     "boxes_elliptic": ("repo:tests/golden/models/boxes.xml", {"cone": 1}, 256, (0.0, 0.7), 64, 300),
+    "tendons": ("repo:tests/golden/models/tendons.xml", {}, 512, (0.3, 1.3), 8, 32),
     "gravcomp": ("repo:tests/golden/models/gravcomp.xml", {}, 128, (0.5, 1.5), 8, 16),
 }
 
