@@ -78,8 +78,9 @@ typedef enum mjbField_ {
 /* Validate `m`, flatten its constant tables, upload them to CUDA device `device` and allocate
  * batch buffers for up to nbatch_max states. Returns NULL and writes a message into err (if not
  * NULL) when the model uses a feature outside the supported path (convex/mesh/hfield/SDF geom
- * pairs that survive the static collision filters, flex, plugins, fluid forces, gravity
- * compensation, spatial tendons, equality constraints, sensors, INVDISCRETE) or when CUDA fails.
+ * pairs that survive the static collision filters, flex, plugins, fluid forces, sensors without
+ * mjDSBL_SENSOR, INVDISCRETE with a non-Euler integrator; full list in DESIGN.md section 5) or when
+ * CUDA fails.
  * nconmax / njmax bound the per-state contact / constraint-row OUTPUT arrays (they do not limit
  * the physics); pass 0 for defaults. */
 MJB_API mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned outmask,
@@ -101,6 +102,11 @@ MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qve
  * or a negative value on a CUDA error (message via mjb_lastError). Synchronous with respect to
  * the host only through the getters; the launch itself is asynchronous on the stream. */
 MJB_API int mjb_inverse(const mjModel* m, mjbData* d, int nbatch);
+/* mj_inverseSkip over the batch (include/mujoco/mujoco.h:137; used by src/inverse/inverse_test.cpp:93
+ * with mjSTAGE_VEL, skipsensor = 1). skipstage only permits the CPU engine to reuse earlier stages;
+ * the batched engine recomputes everything, which yields the same results. skipsensor must be 1 for
+ * models with sensors. Returns like mjb_inverse. */
+MJB_API int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int skipsensor);
 /* same, without reading back the status count (fully asynchronous) */
 MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 

@@ -169,6 +169,14 @@ class BatchData:
         self.nbatch = n
         return rc
 
+    def inverse_skip(self, skipstage=0, skipsensor=1, nbatch=None):
+        """mj_inverseSkip over the batch (mjb_inverseSkip)."""
+        n = self.nbatch if nbatch is None else int(nbatch)
+        rc = self._check(lib().mjb_inverseSkip(self.model.ptr, self._d, n, int(skipstage), int(skipsensor)),
+                         "mjb_inverseSkip")
+        self.nbatch = n
+        return rc
+
     def kernel_launches(self):
         return int(lib().mjb_kernelLaunches(self._d))
 

@@ -414,6 +414,25 @@ int mjb_inverse(const mjModel* m, mjbData* d, int nbatch) {
   return ok ? count : -1;
 }
 
+// mj_inverseSkip(m, d, skipstage, skipsensor) over the batch (include/mujoco/mujoco.h:137,
+// engine_inverse.c:197-261). skipstage tells the CPU engine which stages it may REUSE from the
+// previous call on the same mjData; the results equal a full evaluation whenever the caller kept
+// the corresponding inputs unchanged, which is the function's contract. Here every stage is
+// recomputed (one fused sweep: nothing is cached per state between calls), so the value is
+// validated and otherwise ignored. Sensors are not evaluated: skipsensor must be non-zero unless
+// the model has none (mjb_makeData refuses sensor models without mjDSBL_SENSOR).
+int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int skipsensor) {
+  if (skipstage < mjSTAGE_NONE || skipstage > mjSTAGE_VEL) {
+    d->error = "mjb_inverseSkip: skipstage must be mjSTAGE_NONE, mjSTAGE_POS or mjSTAGE_VEL";
+    return -1;
+  }
+  if (!skipsensor && m && m->nsensor > 0 && !(m->opt.disableflags & mjDSBL_SENSOR)) {
+    d->error = "mjb_inverseSkip: sensors are not evaluated (pass skipsensor = 1)";
+    return -1;
+  }
+  return mjb_inverse(m, d, nbatch);
+}
+
 int mjb_get(mjbData* d, int field, void* host_out) {
   if (field < 0 || field >= mjbF_COUNT || !d->field_ptr[field]) {
     d->error = "mjb_get: field was not requested in outmask";

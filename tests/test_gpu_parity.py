@@ -277,3 +277,16 @@ def test_pipelined_host_entry_point_matches_staged_calls():
         assert np.array_equal(a, b)
     c = bd.inverse_host_arrays(qpos[:1000], qvel[:1000], qacc[:1000])
     assert np.array_equal(a[:1000], c)
+
+
+def test_inverse_skip_equals_inverse():
+    """mj_inverseSkip(m, d, mjSTAGE_VEL, 1) as the fork's driver calls it (src/inverse/inverse_test.cpp:93):
+    with unchanged inputs it must return what mj_inverse returns."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "humanoid", True, 0)
+    full = bd.qfrc_inverse().copy()
+    for stage in (0, 1, 2):
+        assert bd.inverse_skip(skipstage=stage, skipsensor=1) == 0
+        np.testing.assert_array_equal(bd.qfrc_inverse(), full)
+    with pytest.raises(mjb.MjbError):
+        bd.inverse_skip(skipstage=7)
