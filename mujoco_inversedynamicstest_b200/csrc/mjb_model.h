@@ -67,9 +67,11 @@
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
   X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
+  X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
-                                 bit2 has a child other than body+1 (forward-sweep carry must be stored) */
+                                 bit2 has a child other than body+1 (forward-sweep carry must be stored), \
+                                 bit3 pose read by an equality constraint or a tendon site */
 
 // ---- double arrays copied 1:1 from mjModel (name, rows, cols)
 #define MJB_NUM_ARRAYS(X)         \

@@ -1073,8 +1073,15 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   const int* geom_sameframe = MI(geom_sameframe);
   const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
   double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  // what a later phase reads of this geom (upload, geom_store): nothing when it is in no candidate
+  // pair; position + z axis for plane / sphere / capsule pairs; the full frame for the other
+  // narrow-phase functions and for tendon wrapping. The debug dump stores everything.
+  const int* geom_store = MI(geom_store);
+  const bool dump = c.out.scratch_dump != nullptr;
   const int g0 = body_geomadr[b], gn = body_geomnum[b];
   for (int g = g0; g < g0 + gn; g++) {
+    const int store = dump ? 3 : geom_store[g];
+    if (!store) continue;
     const int sf = geom_sameframe[g];
     double gp[3], gm[9];
     if (sf == MJB_SAMEFRAME_BODY) {
@@ -1095,7 +1102,14 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
       for (int k = 0; k < 9; k++) gm[k] = im[k];
     }
     sts(gxpos, 3*g, gp, 3);
-    sts(gxmat, 9*g, gm, 9);
+    if (store & 2) {
+      sts(gxmat, 9*g, gm, 9);
+    } else {
+      const double z[3] = {gm[2], gm[5], gm[8]};
+      stn_stream_(gxmat, 9*g + 2, z, 1, MJB_LS);
+      stn_stream_(gxmat, 9*g + 5, z + 1, 1, MJB_LS);
+      stn_stream_(gxmat, 9*g + 8, z + 2, 1, MJB_LS);
+    }
   }
 }
 
@@ -1246,8 +1260,12 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     normalize4(quat);
     double mat[9];
     quat2Mat(mat, quat);
-    stc(xquat, 4*b, quat, 4);
-    stc(xpos, 3*b, pos, 3);
+    // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
+    // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
+    if ((tree_flags[b] & 12) || c.out.scratch_dump) {
+      stc(xquat, 4*b, quat, 4);
+      stc(xpos, 3*b, pos, 3);
+    }
 
     if (isfree) {
       // translational dofs: cdof = [0, e_r], cdof_dot = 0

@@ -654,7 +654,43 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       if (!seen[p]) { flags[b] |= 2; seen[p] = 1; }
       if (b != p + 1) flags[p] |= 4;
     }
+    // bodies whose pose is read back from scratch after the sweep
+    for (int i = 0; i < neq; i++) {
+      const int* ei = eq_int.data() + (size_t)i * MJB_EQ_NI;
+      if (ei[MJB_EQI_TYPE] == mjEQ_CONNECT || ei[MJB_EQI_TYPE] == mjEQ_WELD) {
+        flags[ei[MJB_EQI_B0]] |= 8; flags[ei[MJB_EQI_B1]] |= 8;
+      }
+    }
+    for (int t = 0; t < m->ntendon; t++) {
+      if (!tendon_active[t]) continue;
+      for (int j = 0; j < m->tendon_num[t]; j++) {
+        const int wt = m->wrap_type[m->tendon_adr[t] + j], id = m->wrap_objid[m->tendon_adr[t] + j];
+        if (wt == mjWRAP_SITE) flags[m->site_bodyid[id]] |= 8;
+        if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) {
+          const int side = (int)std::lround(m->wrap_prm[m->tendon_adr[t] + j]);
+          if (side >= 0 && side < m->nsite) flags[m->site_bodyid[side]] |= 8;
+        }
+      }
+    }
     pushInts(MJB_I_body_tree_flags, flags.data(), flags.size());
+    // geom frames a later phase reads (see body_geoms)
+    std::vector<int> geom_store(m->ngeom, 0);
+    for (int i = 0; i < ncand; i++) {
+      const int* ci = cand_int.data() + (size_t)i * MJB_CAND_NI;
+      const int fn = ci[MJB_CI_FUNC];
+      const bool light = fn == MJB_FN_PLANE_SPHERE || fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_SPHERE_SPHERE ||
+                         fn == MJB_FN_SPHERE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE;
+      geom_store[ci[MJB_CI_G1]] |= light ? 1 : 3;
+      geom_store[ci[MJB_CI_G2]] |= light ? 1 : 3;
+    }
+    for (int t = 0; t < m->ntendon; t++) {
+      if (!tendon_active[t]) continue;
+      for (int j = 0; j < m->tendon_num[t]; j++) {
+        const int wt = m->wrap_type[m->tendon_adr[t] + j];
+        if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) geom_store[m->wrap_objid[m->tendon_adr[t] + j]] |= 3;
+      }
+    }
+    pushInts(MJB_I_geom_store, geom_store.data(), geom_store.size());
   }
 #define X(name, rows, cols) pushNums(MJB_N_##name, m->name, (size_t)m->rows * (cols));
   MJB_NUM_ARRAYS(X)
