@@ -37,6 +37,13 @@ struct mjbData_ {
   std::vector<Mark> marks;
   // inputs: internal SoA buffers and the views currently in use
   double *d_qpos = nullptr, *d_qvel = nullptr, *d_qacc = nullptr;
+  // item-parallel contact phase: global lists of one chunk (null: pooled kernel only)
+  mjb::ContactQueue* d_cq = nullptr;
+  mjb::ContactItem* d_items = nullptr;
+  mjb::ItemCon* d_item_con = nullptr;
+  mjb::ContactRec* d_contacts = nullptr;
+  int* d_slot_rec = nullptr;
+  int items_cap = 0, contacts_cap = 0;
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
   long long in_stride = 0;
@@ -148,6 +155,30 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     if (chunk < 128) chunk = 128;
     d->chunk_stride = chunk;
   }
+  // Item-parallel contact lists, sized for the common case (<= 48 surviving pairs and <= 16 contacts
+  // per state on average over a chunk, at most ~4 GB); denser chunks fall back to the pooled
+  // kernel on the device. MJB_CONTACT_PATH=pooled disables the item path (A/B measurements).
+  {
+    const char* path = std::getenv("MJB_CONTACT_PATH");
+    const bool want = H.ncand > 0 && !(H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) &&
+                      !(path && !std::strcmp(path, "pooled"));
+    if (want) {
+      const long long per_items = H.ncand < 48 ? H.ncand : 48;
+      long long ni = d->chunk_stride * per_items, nc = d->chunk_stride * 16;
+      const long long budget = 4LL << 30;
+      const long long bytes = ni * (long long)(sizeof(mjb::ContactItem) + sizeof(mjb::ItemCon)) +
+                              nc * (long long)(sizeof(mjb::ContactRec) + sizeof(int));
+      if (bytes > budget) { ni = ni * budget / bytes; nc = nc * budget / bytes; }
+      if (ni > 0x7ffffff0LL) ni = 0x7ffffff0LL;
+      if (nc > 0x7ffffff0LL) nc = 0x7ffffff0LL;
+      d->items_cap = (int)ni; d->contacts_cap = (int)nc;
+      ok = ok && devAlloc(d, &d->d_cq, 1, "cudaMalloc(contact queue)");
+      ok = ok && devAlloc(d, &d->d_items, (size_t)ni, "cudaMalloc(contact items)");
+      ok = ok && devAlloc(d, &d->d_item_con, (size_t)ni, "cudaMalloc(item contacts)");
+      ok = ok && devAlloc(d, &d->d_contacts, (size_t)nc, "cudaMalloc(contact records)");
+      ok = ok && devAlloc(d, &d->d_slot_rec, (size_t)nc, "cudaMalloc(contact slots)");
+    }
+  }
   ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
   ok = ok && devAlloc(d, &d->d_iscratch, (size_t)(mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1) * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
   const size_t S = (size_t)d->stride;
@@ -215,6 +246,8 @@ void mjb_deleteData(mjbData* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
+  cudaFree(d->d_cq); cudaFree(d->d_items); cudaFree(d->d_item_con); cudaFree(d->d_contacts);
+  cudaFree(d->d_slot_rec);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   for (int b = 0; b < 2; b++) {
@@ -292,6 +325,9 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_contacts = d->hdr.ncand > 0 &&
                    !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
   a.max_pair_contacts = d->hdr.max_pair_contacts;
+  a.cq = d->d_cq; a.items = d->d_items; a.item_con = d->d_item_con; a.contacts = d->d_contacts;
+  a.items_cap = d->items_cap; a.contacts_cap = d->contacts_cap;
+  a.slot_rec = d->d_slot_rec;
   a.has_gravcomp = d->hdr.passive_wrench;
   a.has_spatial = d->hdr.has_spatial;
   a.out = d->out;

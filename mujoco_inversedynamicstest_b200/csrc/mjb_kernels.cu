@@ -235,6 +235,8 @@ template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
+  // fallback of the item-parallel path: runs only when that path overflowed its lists
+  if (a.cq && !*(volatile int*)&a.cq->overflow) return;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
   const mjbHdr& H = *c.H;
@@ -434,6 +436,265 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Item-parallel contact phase (default path). The pooled kernel above serialises the work of 32
+// states inside one warp at 8 warps per SM; here every stage is its own kernel with one thread
+// per work item and no shared-memory pools, so each runs at full occupancy with dense lanes:
+//   contact_items : state  -> its bounding-sphere survivors appended to the global item list
+//   contact_narrow: item   -> exact hit test; hits are compacted per CTA and run the narrow phase;
+//                             contacts are appended to the global contact list
+//   contact_index : state  -> walks its items in candidate order: contact index k and first efc row
+//                             of every contact (the reference's sequential numbering)
+//   contact_rows  : contact-> constraint rows; J'f kept in the record
+// and the backward kernel adds the records' wrenches to its own state in contact order.
+
+__global__ void __launch_bounds__(256) contact_items_kernel(LaunchArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nwords = (reinterpret_cast<const mjbHdr*>(a.model)->ncand + 31) >> 5;   // global read, uniform
+  for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < a.chunk_n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < a.chunk_n;
+    int* isc = a.iscratch + (((valid ? i : 0) >> 5) * a.niscratch << 5) + ((valid ? i : 0) & 31);
+    const int nsurv = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
+    const int incl = warp_incl_scan(nsurv, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const bool fits = base + total <= a.items_cap;
+    if (!fits && lane == 0) a.cq->overflow = 1;
+    const int mybase = fits ? base + incl - nsurv : -1;
+    if (valid) isc[MJB_ISC_ITEMBASE * MJB_LS] = mybase;
+    if (valid && fits && nsurv) {
+      int k = 0;
+      for (int w = 0; w < nwords; w++) {
+        unsigned bits = (unsigned)isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
+        while (bits) {
+          const int b = __ffs((int)bits) - 1;
+          bits &= bits - 1;
+          a.items[mybase + k] = ContactItem{(int)i, (w << 5) + b};
+          k++;
+        }
+      }
+    }
+  }
+}
+
+constexpr int kNarrowTiles = 4;      // tiles of 256 items tested per dense narrow-phase round
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  __shared__ int hitlist[256 * kNarrowTiles];
+  __shared__ int nhit;
+  if (*(volatile int*)&a.cq->overflow) return;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  const int lane = threadIdx.x & 31;
+  const int n = a.cq->nitems;
+  const int span = 256 * kNarrowTiles;
+  for (int tile = blockIdx.x * span; tile < n; tile += gridDim.x * span) {
+    if (threadIdx.x == 0) nhit = 0;
+    __syncthreads();
+    // exact hit test of `span` items, all lanes busy; hits are collected per CTA
+    for (int t = 0; t < kNarrowTiles; t++) {
+      const int i = tile + t * 256 + threadIdx.x;
+      bool hit = false;
+      if (i < n) {
+        const ContactItem it = a.items[i];
+        Ctx co = c;
+        bind_state(co, a, it.state);
+        hit = narrow_test(co, it.ci);
+        a.item_con[i] = ItemCon{0, 0};
+      }
+      const unsigned hm = __ballot_sync(0xffffffffu, hit);
+      int wbase = 0;
+      if (lane == 0 && hm) wbase = atomicAdd(&nhit, __popc(hm));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (hit) hitlist[wbase + __popc(hm & ((1u << lane) - 1u))] = i;
+    }
+    __syncthreads();
+    const int nh = nhit;
+    // dense narrow phase over the CTA's hits (order inside the list is irrelevant)
+    for (int h0 = 0; h0 < nh; h0 += 256) {
+      Con con[MJB_MAXCON_PAIR];
+      int num = 0, item = -1;
+      ContactItem it = {0, 0};
+      if (h0 + (int)threadIdx.x < nh) {
+        item = hitlist[h0 + threadIdx.x];
+        it = a.items[item];
+        Ctx co = c;
+        bind_state(co, a, it.state);
+        num = narrow_pair(co, it.ci, con);
+      }
+      if (__any_sync(0xffffffffu, num > 0)) {
+        const int incl = warp_incl_scan(num, lane);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&a.cq->ncontacts, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + total > a.contacts_cap) {
+          if (lane == 0) a.cq->overflow = 1;
+        } else if (num > 0) {
+          const int first = base + incl - num;
+          a.item_con[item] = ItemCon{first, num};
+          for (int k = 0; k < num; k++) {
+            ContactRec& r = a.contacts[first + k];
+            r.state = it.state; r.ci = it.ci; r.k = -1; r.efc_address = -1;
+            r.dist = con[k].dist;
+            for (int q = 0; q < 3; q++) r.pos[q] = con[k].pos[q];
+            for (int q = 0; q < 6; q++) r.frame[q] = con[k].frame[q];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) contact_index_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  if (*(volatile int*)&a.cq->overflow) return;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n; i0 += (long long)gridDim.x * kThreads) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < a.chunk_n;
+    bind_state(c, a, valid ? i : 0);
+    const int nsurv = valid ? c.isc[MJB_ISC_NSURV * MJB_LS] : 0;
+    const int ibase = valid ? c.isc[MJB_ISC_ITEMBASE * MJB_LS] : 0;
+    // contacts of this state: a contiguous slot range, allocated warp-wide (order across warps is
+    // irrelevant, inside a warp it follows the states)
+    int mine = 0;
+    for (int j = 0; j < nsurv; j++) mine += a.item_con[ibase + j].count;
+    const int incl = warp_incl_scan(mine, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(&a.cq->nslots, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int sbase = base + incl - mine;
+    if (valid) {
+      c.isc[MJB_ISC_ITEMBASE * MJB_LS] = sbase;        // from here on: first slot of the state ...
+      c.isc[MJB_ISC_NSURV * MJB_LS] = mine;            // ... and its number of contacts
+    }
+    if (!mine) continue;
+    load_counters(c);
+    int slot = sbase;
+    for (int j = 0; j < nsurv; j++) {
+      const ItemCon ic = a.item_con[ibase + j];
+      for (int q = 0; q < ic.count; q++) {
+        ContactRec& r = a.contacts[ic.base + q];
+        int exclude;
+        const int rows = contact_row_count(c, r.ci, r.dist, &exclude);
+        r.k = c.ncon++;
+        r.efc_address = rows ? c.nefc : -1 - exclude;     // < 0: no rows; exclude flag = -1 - value
+        c.nefc += rows;
+        a.slot_rec[slot++] = ic.base + q;
+      }
+    }
+    save_counters(c);
+  }
+}
+
+// One warp per 32 consecutive states: their contacts occupy one contiguous, (state, k)-ordered slot
+// range (contact_index_kernel), which the warp processes 32 slots at a time. J'f is applied to the
+// owner state's body accumulators right here; records of one round that hit the same (state, body)
+// are found with __match_any_sync and applied one after the other in slot order, so the sums are
+// conflict-free and bitwise deterministic. No other warp touches these states.
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  if (*(volatile int*)&a.cq->overflow) return;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int* cand_int = c.I + c.H->ioff[MJB_I_cand_int];
+  const int* body_static = c.I + c.H->ioff[MJB_I_body_static];
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n; i0 += (long long)gridDim.x * kThreads) {
+    const long long w0 = i0 + warp * 32;                  // first state of this warp
+    const long long i = w0 + lane;
+    const bool valid = i < a.chunk_n;
+    const int* isc = a.iscratch + (((valid ? i : 0) >> 5) * a.niscratch << 5) + ((valid ? i : 0) & 31);
+    const int mine = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
+    const int sbase = valid ? isc[MJB_ISC_ITEMBASE * MJB_LS] : 0;
+    const int incl = warp_incl_scan(mine, lane);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) continue;
+    const int slot0 = __shfl_sync(0xffffffffu, sbase, 0);  // lane 0's base = first slot of the warp
+    int wstatus = 0;
+    for (int r0 = 0; r0 < total; r0 += 32) {
+      const bool has = r0 + lane < total;
+      double F[3] = {0, 0, 0}, T3[3] = {0, 0, 0}, p[3] = {0, 0, 0};
+      int b1 = 0, b2 = 0, owner = 64 + lane;
+      bool active = false;
+      Ctx co = c;
+      if (has) {
+        const ContactRec& r = a.contacts[a.slot_rec[slot0 + r0 + lane]];
+        owner = r.state - (int)w0;
+        bind_state(co, a, r.state);
+        Con con;
+        con.dist = r.dist;
+        for (int k = 0; k < 3; k++) { con.pos[k] = r.pos[k]; p[k] = r.pos[k]; }
+        for (int k = 0; k < 6; k++) con.frame[k] = r.frame[k];
+        cross3(con.frame + 6, con.frame, con.frame + 3);          // as mju_makeFrame's last step
+        const int exclude = r.efc_address >= 0 ? 0 : -1 - r.efc_address;
+        co.status = 0;
+        contact_rows(co, r.ci, con, r.k, exclude, r.efc_address >= 0 ? r.efc_address : -1, F, T3);
+        active = r.efc_address >= 0;
+        b1 = cand_int[MJB_CAND_NI*r.ci + MJB_CI_B1]; b2 = cand_int[MJB_CAND_NI*r.ci + MJB_CI_B2];
+        if (co.status) wstatus |= co.status, atomicOr(&co.isc[MJB_ISC_STATUS * MJB_LS], co.status);
+      }
+      // J'f: records of this round that hit the same (state, body) form a group (__match_any_sync);
+      // the group's wrenches are summed in lane order with shuffles by its first lane, which then
+      // does ONE batched read-modify-write of the accumulator row (deterministic, conflict-free)
+      const int* rootid = c.I + c.H->ioff[MJB_I_body_rootid];
+#pragma unroll
+      for (int side = 0; side < 2; side++) {
+        const int body = side == 0 ? b2 : b1;
+        const bool act = has && active && !body_static[body];
+        double W[6] = {0, 0, 0, 0, 0, 0};
+        if (act) {
+          const double* org = co.sc + (size_t)c.H->scoff[MJB_SC_origin] * MJB_LS;
+          const int root = rootid[body];
+          const double rr[3] = {p[0] - org[(size_t)(3*root) * MJB_LS], p[1] - org[(size_t)(3*root + 1) * MJB_LS],
+                                p[2] - org[(size_t)(3*root + 2) * MJB_LS]};
+          double cr[3];
+          cross3(cr, rr, F);
+          for (int k = 0; k < 3; k++) { W[k] = cr[k] + T3[k]; W[3 + k] = F[k]; }
+        }
+        const unsigned key = act ? (((unsigned)owner << 20) | (unsigned)body) : (0x80000000u | lane);
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const int cnt = __popc(grp);
+        const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+        const bool leader = act && (__ffs((int)grp) - 1) == lane;
+        double sum[6] = {W[0], W[1], W[2], W[3], W[4], W[5]};
+        for (int t = 1; t < maxcnt; t++) {
+          const int src = t < cnt ? (int)__fns(grp, 0, t + 1) : lane;      // t-th further member of my group
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const double v = __shfl_sync(0xffffffffu, W[k], src);
+            if (t < cnt) sum[k] += v;
+          }
+        }
+        if (leader) {
+          double* fe = co.sc + (size_t)c.H->scoff[side == 0 ? MJB_SC_cfrc_ext : MJB_SC_cfrc_ext1] * MJB_LS;
+          double acc[6];
+          for (int k = 0; k < 6; k++) acc[k] = fe[(size_t)(6*body + k) * MJB_LS];
+          for (int k = 0; k < 6; k++) fe[(size_t)(6*body + k) * MJB_LS] = acc[k] + sum[k];
+        }
+      }
+      __syncwarp();
+    }
+    (void)wstatus;
+  }
+}
+
 size_t contact_smem_bytes(int model_bytes, int model_in_smem, int max_pair_contacts) {
   size_t off = model_in_smem ? (size_t)((model_bytes + 127) & ~127) : 0;
   off += sizeof(int) * kListCap * kThreads;
@@ -572,6 +833,28 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
 #ifndef MJB_CONTACT_MODEL_SMEM
 #define MJB_CONTACT_MODEL_SMEM 0
 #endif
+    if (args.cq) {
+      e = cudaMemsetAsync(args.cq, 0, sizeof(ContactQueue), stream);
+      if (e != cudaSuccess) return e;
+      { PhaseScope ps(timer, stream, kPhaseContact);
+        int grid = (args.chunk_n + 255) / 256;
+        if (grid > kSMs * 8) grid = kSMs * 8;
+        contact_items_kernel<<<grid, 256, 0, stream>>>(args);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // the narrow / rows kernels walk lists whose length is only known on the device: full grids
+        e = in_smem ? launch_phase(contact_narrow_kernel<true>, args, smem, 4, stream, 256)
+                    : launch_phase(contact_narrow_kernel<false>, args, 0, 4, stream, 256);
+        if (e != cudaSuccess) return e;
+        e = in_smem ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
+                    : launch_phase(contact_index_kernel<false>, args, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+        e = in_smem ? launch_phase(contact_rows_kernel<true>, args, smem, 8, stream)
+                    : launch_phase(contact_rows_kernel<false>, args, 0, 8, stream);
+        if (e != cudaSuccess) return e;
+      }
+      *launches += 4;
+    }
     const bool csm = in_smem && MJB_CONTACT_MODEL_SMEM;
     const size_t csmem = contact_smem_bytes(args.model_bytes, csm, args.max_pair_contacts);
     { PhaseScope ps(timer, stream, kPhaseContact);

@@ -21,6 +21,20 @@ constexpr int kSMs = 148;
 #endif
 constexpr int kListCap = MJB_LISTCAP;                  // per-lane survivor list of the contact kernel
 
+// Item-parallel contact phase: global lists of one chunk. Survivors of the bounding-sphere scan
+// ("items") and the contacts they yield are appended with warp-aggregated atomics; a state finds its
+// items through MJB_ISC_ITEMBASE / NSURV and an item its contacts through ItemCon, so placement
+// order does not matter. If a list would overflow, `overflow` is raised and the chunk is handled
+// by the pooled contact kernel instead (every kernel of either path checks the flag first).
+struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; };
+struct ContactItem { int state; int ci; };          // chunk-local state, candidate pair
+struct ItemCon { int base; int count; };            // the item's contacts: contacts[base .. base+count)
+struct ContactRec {
+  int state, ci, k, efc_address;                    // k: contact index in its state; efc_address or -1
+  double dist, pos[3], frame[6];                    // normal, tangent (third axis is their cross product)
+};
+
+
 struct LaunchArgs {
   const unsigned char* model;   // device blob (mjbHdr + sections)
   int model_bytes;
@@ -37,6 +51,10 @@ struct LaunchArgs {
   int chunk_n;                  // states in the chunk
   long long stride;             // row stride of every state-indexed input/output array
   int nconmax, njmax;
+  ContactQueue* cq;             // item-parallel contact path (null: pooled kernel only)
+  ContactItem* items; ItemCon* item_con; ContactRec* contacts;
+  int* slot_rec;                // slot (state's first slot + k) -> index into contacts
+  int items_cap, contacts_cap;
   int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
   int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)

@@ -155,8 +155,9 @@ MJB_DI void stn_stream_(double* p, int first, const double* src, int n, size_t s
 
 // per-state integer scratch rows: counters carried between the phase kernels
 // MJB_ISC_NSURV / MJB_ISC_MASK..: survivors of the contact scan (count, then ceil(ncand/32) words)
+// MJB_ISC_ITEMBASE: first entry of the state's survivors in the chunk's global item list (-1: none)
 enum { MJB_ISC_NCON = 0, MJB_ISC_NE, MJB_ISC_NF, MJB_ISC_NL, MJB_ISC_NEFC, MJB_ISC_STATUS,
-       MJB_ISC_NSURV, MJB_ISC_MASK, MJB_ISC_COUNT = MJB_ISC_MASK };
+       MJB_ISC_NSURV, MJB_ISC_ITEMBASE, MJB_ISC_MASK, MJB_ISC_COUNT = MJB_ISC_MASK };
 
 MJB_HD inline void save_counters(Ctx& c) {
   c.isc[MJB_ISC_NCON * MJB_LS] = c.ncon; c.isc[MJB_ISC_NE * MJB_LS] = c.ne;
