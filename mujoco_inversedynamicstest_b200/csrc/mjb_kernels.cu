@@ -673,21 +673,22 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
         const int cnt = __popc(grp);
         const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
         const bool leader = act && (__ffs((int)grp) - 1) == lane;
-        double sum[6] = {W[0], W[1], W[2], W[3], W[4], W[5]};
+        // the chain starts from the accumulator row and adds the members one by one in slot order:
+        // the same association as one read-modify-write per contact, so the bits do not depend on
+        // where a state sits in the batch (which contacts happen to share a round)
+        double* fe = co.sc + (size_t)c.H->scoff[side == 0 ? MJB_SC_cfrc_ext : MJB_SC_cfrc_ext1] * MJB_LS;
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        if (leader) for (int k = 0; k < 6; k++) acc[k] = fe[(size_t)(6*body + k) * MJB_LS];
+        for (int k = 0; k < 6; k++) acc[k] += W[k];
         for (int t = 1; t < maxcnt; t++) {
           const int src = t < cnt ? (int)__fns(grp, 0, t + 1) : lane;      // t-th further member of my group
 #pragma unroll
           for (int k = 0; k < 6; k++) {
             const double v = __shfl_sync(0xffffffffu, W[k], src);
-            if (t < cnt) sum[k] += v;
+            if (t < cnt) acc[k] += v;
           }
         }
-        if (leader) {
-          double* fe = co.sc + (size_t)c.H->scoff[side == 0 ? MJB_SC_cfrc_ext : MJB_SC_cfrc_ext1] * MJB_LS;
-          double acc[6];
-          for (int k = 0; k < 6; k++) acc[k] = fe[(size_t)(6*body + k) * MJB_LS];
-          for (int k = 0; k < 6; k++) fe[(size_t)(6*body + k) * MJB_LS] = acc[k] + sum[k];
-        }
+        if (leader) for (int k = 0; k < 6; k++) fe[(size_t)(6*body + k) * MJB_LS] = acc[k];
       }
       __syncwarp();
     }
