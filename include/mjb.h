@@ -146,6 +146,10 @@ MJB_API long long mjb_kernelLaunches(const mjbData* d);
 MJB_API void mjb_phaseTiming(mjbData* d, int enable);
 MJB_API int mjb_phaseTimes(mjbData* d, double* ms, int n);
 
+/* diagnostics: counters of the item-parallel contact phase of the last chunk
+ * (items, contacts, overflow flag, slots); -1 if that path is not in use */
+MJB_API int mjb_debugQueue(mjbData* d, int* out4);
+
 /* wait for the stream */
 MJB_API int mjb_synchronize(mjbData* d);
 

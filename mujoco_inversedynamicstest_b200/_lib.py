@@ -37,6 +37,7 @@ SIGNATURES = {
                              ctypes.POINTER(c_int)]),
     "mjb_lastError": (c_char_p, [c_void_p]),
     "mjb_kernelLaunches": (c_ll, [c_void_p]),
+    "mjb_debugQueue": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "mjb_phaseTiming": (None, [c_void_p, c_int]),
     "mjb_phaseTimes": (c_int, [c_void_p, ctypes.POINTER(c_double), c_int]),
     "mjb_synchronize": (c_int, [c_void_p]),

@@ -526,6 +526,12 @@ const char* mjb_lastError(const mjbData* d) { return d->error.c_str(); }
 
 long long mjb_kernelLaunches(const mjbData* d) { return d->kernel_launches; }
 
+int mjb_debugQueue(mjbData* d, int* out4) {
+  if (!d->d_cq) return -1;
+  cudaSetDevice(d->device);
+  return cudaMemcpy(out4, d->d_cq, 4 * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+
 void mjb_phaseTiming(mjbData* d, int enable) {
   d->phase_timing = enable != 0;
   d->marks.clear();

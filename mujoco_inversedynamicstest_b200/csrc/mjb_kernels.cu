@@ -14,6 +14,7 @@
 #include "mjb_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 // resident CTAs per SM each phase kernel is compiled for (register budget = 65536 / (threads * CTAS)).
 // Measured on B200 (profiles/README.md): the smooth kernel is fastest WITHOUT register spills at low
@@ -101,6 +102,11 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned c
   c.out = a.out;
   c.ncon = c.ne = c.nf = c.nl = c.nefc = c.status = 0;
   c.sm = nullptr;
+  // every field is defined before a Ctx is copied: copying a context with indeterminate members is
+  // undefined behaviour and did produce a corrupted table pointer in one kernel instantiation
+  c.sc = nullptr; c.isc = nullptr;
+  c.qpos = nullptr; c.qvel = nullptr; c.qacc = nullptr;
+  c.s = 0;
 }
 
 __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long long local) {
@@ -504,8 +510,8 @@ __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
       bool hit = false;
       if (i < n) {
         const ContactItem it = a.items[i];
-        Ctx co = c;
-        bind_state(co, a, it.state);
+        Ctx& co = c;      // rebinding c is enough (a by-value copy of the context faulted here for
+        bind_state(co, a, it.state);   //  models read from global memory; cause not established)
         hit = narrow_test(co, it.ci);
         a.item_con[i] = ItemCon{0, 0};
       }
@@ -525,7 +531,7 @@ __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
       if (h0 + (int)threadIdx.x < nh) {
         item = hitlist[h0 + threadIdx.x];
         it = a.items[item];
-        Ctx co = c;
+        Ctx& co = c;      // (a by-value copy of the context is what faulted here; rebinding c is enough)
         bind_state(co, a, it.state);
         num = narrow_pair(co, it.ci, con);
       }
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
       double F[3] = {0, 0, 0}, T3[3] = {0, 0, 0}, p[3] = {0, 0, 0};
       int b1 = 0, b2 = 0, owner = 64 + lane;
       bool active = false;
-      Ctx co = c;
+      Ctx& co = c;
       if (has) {
         const ContactRec& r = a.contacts[a.slot_rec[slot0 + r0 + lane]];
         owner = r.state - (int)w0;
