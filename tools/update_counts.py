@@ -26,6 +26,9 @@ def main():
     K = {}
     for (_, k), m in step:
         name = k.split("(")[0].replace("void ", "").split("<")[0].replace("_kernel", "")
+        # the contact phase = items + narrow + index + rows (+ the pooled fallback kernel)
+        if name.startswith("contact") and name != "contact_scan":
+            name = "contact"
         e = K.setdefault(name, {"flops": 0.0, "dram_bytes": 0.0, "warp_inst": 0.0})
         e["flops"] += (m["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] +
                        m["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] +
