@@ -290,3 +290,50 @@ def test_inverse_skip_equals_inverse():
         np.testing.assert_array_equal(bd.qfrc_inverse(), full)
     with pytest.raises(mjb.MjbError):
         bd.inverse_skip(skipstage=7)
+
+
+def test_item_parallel_and_pooled_contact_paths_agree():
+    """The contact phase has two implementations: item-parallel kernels over global lists (default)
+    and the warp-pooled kernel (on-device fallback when the lists overflow, MJB_CONTACT_PATH=pooled).
+    Both apply J'f per (state, body) in contact order starting from the accumulator row, so they
+    must agree bit for bit, on discrete outputs and on qfrc_inverse."""
+    import os
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    for name in ("humanoid", "humanoid_elliptic", "boxes"):
+        path, ref = util.golden(name)
+        model = mjb.Model.from_mjb(path)
+        n = 4096
+        qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+        res = {}
+        for mode in ("items", "pooled"):
+            if mode == "pooled":
+                os.environ["MJB_CONTACT_PATH"] = "pooled"
+            try:
+                bd = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_EFC, njmax=int(ref["njmax"]))
+            finally:
+                os.environ.pop("MJB_CONTACT_PATH", None)
+            bd.set_state(qpos, qvel, qacc)
+            assert bd.inverse() == 0
+            res[mode] = (bd.qfrc_inverse().copy(), bd.counts(), bd.efc())
+        np.testing.assert_array_equal(res["items"][1]["ncon"], res["pooled"][1]["ncon"])
+        np.testing.assert_array_equal(res["items"][1]["nefc"], res["pooled"][1]["nefc"])
+        np.testing.assert_array_equal(res["items"][2]["type"], res["pooled"][2]["type"])
+        np.testing.assert_array_equal(res["items"][2]["state"], res["pooled"][2]["state"])
+        np.testing.assert_array_equal(res["items"][0], res["pooled"][0], err_msg=name)
+
+
+def test_contact_list_overflow_falls_back_on_the_device():
+    """A chunk whose contacts do not fit the global lists (22 interpenetrating humanoids: ~290
+    contacts per state against 16 per state of list capacity) is handled by the pooled kernel;
+    the counters of the item path show the overflow and the results are the reference's."""
+    import ctypes
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200._lib import lib
+    model, bd, ref, nbad, _ = _run(mjb, "humanoids22", True, mjb.OUT_COUNTS)
+    out = (ctypes.c_int * 4)()
+    assert lib().mjb_debugQueue(bd._d, out) == 0
+    assert out[2] != 0, list(out)                       # overflow flag raised on the device
+    np.testing.assert_array_equal(bd.counts()["ncon"], ref["ncon"])
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
