@@ -11,13 +11,14 @@ One "step" = one mjb_inverse pass over a resident batch of 2^20 synthetic humano
   e2e     the same metric through the public C-ABI with HOST buffers: mjb_inverseHost (H2D from
           pinned memory + transposes, kernels, transpose + D2H of qfrc_inverse, pipelined in pieces
           over three streams), all inside the timed region
-  roofline      FP64 roofline of the step's phase kernels: executed fp64 flops per state (ncu,
-                profiles/flops_per_state.json) x states / CUDA-event time vs the DFMA peak measured
-                in the same run
+  roofline      HBM roofline of the step: algorithmic bytes (in + out per state) x states /
+                CUDA-event time vs MEASURED_PEAKS.json HBM copy bandwidth, with the measured DRAM
+                traffic of the step as `traffic` (the phase kernels are bound by the HBM traffic of
+                the per-state intermediates)
+  roofline_fp64 executed fp64 flops per state (ncu, profiles/flops_per_state.json) x states /
+                CUDA-event time vs the DFMA peak measured in the same run
   kernels       per phase kernel: live CUDA-event time (events around every launch), share of the
                 step, achieved fp64 TFLOP/s and DRAM GB/s against both peaks
-  roofline_hbm  algorithmic bytes (in + out per state) / time vs MEASURED_PEAKS.json HBM copy
-                bandwidth, with the measured DRAM traffic of the step next to it
   cpu_baseline  the reference's own mj_inverse looped over the host cores with its thread pool
                 (oracle/_ref), on a bounded sample of the same states
 
@@ -405,8 +406,8 @@ def main():
                     "h2d_bytes_per_step": n * (nq + 2 * nv) * 8, "d2h_bytes_per_step": n * nv * 8,
                     "steps": e2e_steps},
             "gpu_launches": gpu_launches,
-            "roofline": roof_fp64,
-            "roofline_hbm": roof_hbm,
+            "roofline": roof_hbm,
+            "roofline_fp64": roof_fp64,
             "kernels": kernels,
             "kernels_note": "ms: CUDA events around every launch in this run (mjb_phaseTiming); flops "
                             "and DRAM bytes per state: ncu counts frozen in profiles/flops_per_state.json; "
