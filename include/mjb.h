@@ -107,6 +107,15 @@ MJB_API int mjb_inverse(const mjModel* m, mjbData* d, int nbatch);
  * the batched engine recomputes everything, which yields the same results. skipsensor must be 1 for
  * models with sensors. Returns like mjb_inverse. */
 MJB_API int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int skipsensor);
+/* mjd_inverseFD over the batch (include/mujoco/mujoco.h mjd_inverseFD, src/engine/
+ * engine_derivative_fd.c:611; flg_actuation = 0, sensors not evaluated): forward-difference
+ * Jacobians of qfrc_inverse with respect to qpos (through mj_integratePos), qvel and qacc of the
+ * states last given to mjb_setState / mjb_setStateDevice. Outputs are HOST arrays, any of them may
+ * be NULL: DfDq, DfDv, DfDa nbatch x nv x nv, DmDq nbatch x nv x nM, row i = derivative with
+ * respect to coordinate i (the reference's transposed layout). 1 + 3 nv evaluations per state,
+ * generated and differenced on the device. Synchronous. */
+MJB_API int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq,
+                          mjtNum* DfDv, mjtNum* DfDa, mjtNum* DmDq);
 /* same, without reading back the status count (fully asynchronous) */
 MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 

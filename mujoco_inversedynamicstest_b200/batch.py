@@ -169,6 +169,18 @@ class BatchData:
         self.nbatch = n
         return rc
 
+    def inverse_fd(self, eps=1e-6, mass=False, nbatch=None):
+        """mjd_inverseFD over the batch (mjb_inverseFD): (DfDq, DfDv, DfDa[, DmDq]) as
+        [n, nv, nv] ([n, nv, nM]) arrays, row i = derivative w.r.t. coordinate i."""
+        n = self.nbatch if nbatch is None else int(nbatch)
+        nv, nM = self.model.int("nv"), self.model.int("nM")
+        dq, dv, da = (np.zeros((n, nv, nv)) for _ in range(3))
+        dm = np.zeros((n, nv, nM)) if mass else None
+        self._check(lib().mjb_inverseFD(self.model.ptr, self._d, n, float(eps), dq.ctypes.data,
+                                        dv.ctypes.data, da.ctypes.data,
+                                        dm.ctypes.data if mass else None), "mjb_inverseFD")
+        return (dq, dv, da, dm) if mass else (dq, dv, da)
+
     def inverse_skip(self, skipstage=0, skipsensor=1, nbatch=None):
         """mj_inverseSkip over the batch (mjb_inverseSkip)."""
         n = self.nbatch if nbatch is None else int(nbatch)

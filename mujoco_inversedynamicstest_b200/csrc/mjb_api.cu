@@ -62,6 +62,11 @@ struct mjbData_ {
   void* field_ptr[mjbF_COUNT];
   int field_rows[mjbF_COUNT];
   int field_isint[mjbF_COUNT];
+  // mjb_inverseFD: inner batch of perturbed states and the device buffer of the differences
+  mjbData* fd = nullptr;
+  int fd_tile = 0;
+  double* d_fd_out = nullptr;
+  size_t fd_out_doubles = 0;
   std::string error;
 };
 
@@ -245,6 +250,8 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
 void mjb_deleteData(mjbData* d) {
   if (!d) return;
   cudaSetDevice(d->device);
+  if (d->fd) mjb_deleteData(d->fd);
+  cudaFree(d->d_fd_out);
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
   cudaFree(d->d_cq); cudaFree(d->d_items); cudaFree(d->d_item_con); cudaFree(d->d_contacts);
   cudaFree(d->d_slot_rec);
@@ -467,6 +474,62 @@ int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int
     return -1;
   }
   return mjb_inverse(m, d, nbatch);
+}
+
+// mjd_inverseFD over the batch (src/engine/engine_derivative_fd.c:611, flg_actuation = 0, no
+// sensors): forward differences of qfrc_inverse (and of qM) with respect to qacc, qvel and qpos
+// (the latter through mj_integratePos), 1 + 3 nv evaluations per state. The perturbed states are
+// generated on the device and evaluated as one large batch by the same phase kernels.
+int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq, mjtNum* DfDv,
+                  mjtNum* DfDa, mjtNum* DmDq) {
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseFD: nbatch out of range"; return -1; }
+  if (!(eps > 0)) { d->error = "mjb_inverseFD: eps must be positive"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const mjbHdr& H = d->hdr;
+  const int nv = H.nv, nM = H.nM, nvar = 1 + 3*nv;
+  if (nbatch == 0 || nv == 0) return 0;
+  const bool want_mass = DmDq != nullptr;
+  int tile = (1 << 20) / nvar;
+  if (tile < 1) tile = 1;
+  if (tile > nbatch) tile = nbatch;
+  if (!d->fd || d->fd_tile < tile || (want_mass && !d->fd->out.qM)) {
+    if (d->fd) mjb_deleteData(d->fd);
+    char err[512];
+    d->fd = mjb_makeData(m, tile * nvar, d->device, want_mass ? mjbOUT_INERTIA : 0, 1, 1, err, sizeof(err));
+    if (!d->fd) { d->error = std::string("mjb_inverseFD: ") + err; return -1; }
+    d->fd_tile = tile;
+  }
+  mjbData* x = d->fd;
+  x->stream = d->stream;
+  const size_t need = (size_t)tile * nv * (size_t)(want_mass ? (nv > nM ? nv : nM) : nv);
+  if (need > d->fd_out_doubles) {
+    cudaFree(d->d_fd_out);
+    d->d_fd_out = nullptr; d->fd_out_doubles = 0;
+    if (!check(d, cudaMalloc((void**)&d->d_fd_out, need * sizeof(double)), "cudaMalloc(fd out)")) return -1;
+    d->fd_out_doubles = need;
+  }
+  bool ok = true;
+  for (int first = 0; first < nbatch && ok; first += tile) {
+    const int n = (nbatch - first) < tile ? (nbatch - first) : tile;
+    ok = ok && check(d, mjb::launch_fd_expand(d->d_model, d->in_qpos, d->in_qvel, d->in_qacc, d->in_stride,
+                                              first, n, eps, x->d_qpos, x->d_qvel, x->d_qacc, x->stride,
+                                              d->stream), "fd expand");
+    x->in_qpos = x->d_qpos; x->in_qvel = x->d_qvel; x->in_qacc = x->d_qacc; x->in_stride = x->stride;
+    if (ok && mjb_inverseAsync(m, x, n * nvar)) { d->error = "mjb_inverseFD: " + x->error; return -1; }
+    struct Job { mjtNum* host; const double* field; int v0; int ncol; };
+    const Job jobs[4] = {{DfDa, x->out.qfrc_inverse, 1, nv}, {DfDv, x->out.qfrc_inverse, 1 + nv, nv},
+                         {DfDq, x->out.qfrc_inverse, 1 + 2*nv, nv}, {DmDq, x->out.qM, 1 + 2*nv, nM}};
+    for (const Job& j : jobs) {
+      if (!j.host) continue;
+      ok = ok && check(d, mjb::launch_fd_diff(j.field, x->stride, n, nvar, j.v0, nv, j.ncol, eps,
+                                              d->d_fd_out, d->stream), "fd diff");
+      const size_t bytes = (size_t)n * nv * j.ncol * sizeof(double);
+      ok = ok && check(d, cudaMemcpyAsync(j.host + (size_t)first * nv * j.ncol, d->d_fd_out, bytes,
+                                          cudaMemcpyDeviceToHost, d->stream), "D2H fd");
+      ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_inverseFD");   // d_fd_out is reused
+    }
+  }
+  return ok ? 0 : -1;
 }
 
 int mjb_get(mjbData* d, int field, void* host_out) {

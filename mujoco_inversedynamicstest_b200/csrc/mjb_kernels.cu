@@ -943,6 +943,88 @@ cudaError_t launch_soa_to_aos_int(const int* soa, int* aos, int n, int rows, lon
 }
 
 // ------------------------------------------------------------------------------------------
+// finite-difference Jacobians of the inverse dynamics (mjd_inverseFD, engine_derivative_fd.c:611):
+// the perturbed states are generated on the device, evaluated as one large batch by the phase
+// kernels, and differenced on the device.
+
+__global__ void fd_expand_kernel(const unsigned char* model, const double* __restrict__ qpos,
+                                 const double* __restrict__ qvel, const double* __restrict__ qacc,
+                                 long long stride_in, long long first, int nstate, double eps,
+                                 double* xqpos, double* xqvel, double* xqacc, long long stride_out) {
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(model);
+  const int* I = reinterpret_cast<const int*>(model + H->int_section);
+  const int nq = H->nq, nv = H->nv, nvar = 1 + 3*nv;
+  const long long total = (long long)nstate * nvar;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long s = first + e / nvar;
+    const int v = (int)(e % nvar);
+    for (int k = 0; k < nq; k++) xqpos[(size_t)k * stride_out + e] = qpos[(size_t)k * stride_in + s];
+    for (int k = 0; k < nv; k++) {
+      xqvel[(size_t)k * stride_out + e] = qvel[(size_t)k * stride_in + s];
+      xqacc[(size_t)k * stride_out + e] = qacc[(size_t)k * stride_in + s];
+    }
+    if (v == 0) continue;
+    if (v <= nv) { xqacc[(size_t)(v - 1) * stride_out + e] += eps; continue; }
+    if (v <= 2*nv) { xqvel[(size_t)(v - nv - 1) * stride_out + e] += eps; continue; }
+    // mj_integratePos(m, qpos, unit vector of dof i, eps)  (engine_support.c:1518-1548)
+    const int i = v - 2*nv - 1;
+    const int j = (I + H->ioff[MJB_I_dof_jntid])[i];
+    const int jt = (I + H->ioff[MJB_I_jnt_type])[j];
+    int padr = (I + H->ioff[MJB_I_jnt_qposadr])[j];
+    int r = i - (I + H->ioff[MJB_I_jnt_dofadr])[j];
+    if (jt == MJB_JNT_HINGE || jt == MJB_JNT_SLIDE || (jt == MJB_JNT_FREE && r < 3)) {
+      xqpos[(size_t)(padr + r) * stride_out + e] += eps * 1.0;
+      continue;
+    }
+    if (jt == MJB_JNT_FREE) { padr += 3; r -= 3; }
+    // mju_quatIntegrate (engine_util_spatial.c:241): quat <- normalize(quat) * quat(axis e_r, eps)
+    double q[4], axis[3] = {0, 0, 0}, qrot[4], res[4];
+    for (int k = 0; k < 4; k++) q[k] = xqpos[(size_t)(padr + k) * stride_out + e];
+    axis[r] = 1.0;
+    const double angle = eps * normalize3(axis);
+    double sn, cs;
+    sincos(angle*0.5, &sn, &cs);
+    qrot[0] = cs; qrot[1] = axis[0]*sn; qrot[2] = axis[1]*sn; qrot[3] = axis[2]*sn;
+    normalize4(q);
+    mulQuat(res, q, qrot);
+    for (int k = 0; k < 4; k++) xqpos[(size_t)(padr + k) * stride_out + e] = res[k];
+  }
+}
+
+cudaError_t launch_fd_expand(const unsigned char* model, const double* qpos, const double* qvel,
+                             const double* qacc, long long stride_in, long long first, int nstate,
+                             double eps, double* xqpos, double* xqvel, double* xqacc,
+                             long long stride_out, cudaStream_t stream) {
+  if (nstate <= 0) return cudaSuccess;
+  fd_expand_kernel<<<kSMs * 8, 256, 0, stream>>>(model, qpos, qvel, qacc, stride_in, first, nstate, eps,
+                                                 xqpos, xqvel, xqacc, stride_out);
+  return cudaGetLastError();
+}
+
+__global__ void fd_diff_kernel(const double* __restrict__ f, long long stride, int nstate, int nvar,
+                               int v0, int nrow, int ncol, double inv_eps, double* out) {
+  const long long total = (long long)nstate * nrow * ncol;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(t % ncol);
+    const long long sr = t / ncol;
+    const int r = (int)(sr % nrow);
+    const long long s = sr / nrow;
+    const double base = f[(size_t)k * stride + s * nvar];
+    const double plus = f[(size_t)k * stride + s * nvar + v0 + r];
+    out[t] = inv_eps * (plus - base);                       // diff(), engine_derivative_fd.c:48
+  }
+}
+
+cudaError_t launch_fd_diff(const double* f, long long stride, int nstate, int nvar, int v0, int nrow,
+                           int ncol, double eps, double* out, cudaStream_t stream) {
+  if (nstate <= 0 || nrow <= 0 || ncol <= 0) return cudaSuccess;
+  fd_diff_kernel<<<kSMs * 8, 256, 0, stream>>>(f, stride, nstate, nvar, v0, nrow, ncol, 1/eps, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // number of states whose status word is non-zero (return value of mjb_inverse)
 
 __global__ void count_nonzero_kernel(const int* __restrict__ status, int n, int* counter) {

@@ -86,6 +86,17 @@ cudaError_t launch_soa_to_aos(const double* soa, double* aos, int n, int rows, l
 cudaError_t launch_soa_to_aos_int(const int* soa, int* aos, int n, int rows, long long stride,
                                   cudaStream_t stream);
 
+// mjd_inverseFD support (engine_derivative_fd.c:611): variant v of state s goes to column
+// s*(1+3nv) + v of the expanded batch: v = 0 unperturbed, 1..nv qacc[i] += eps, nv+1..2nv
+// qvel[i] += eps, 2nv+1..3nv qpos integrated by eps along dof i (mj_integratePos)
+cudaError_t launch_fd_expand(const unsigned char* model, const double* qpos, const double* qvel,
+                             const double* qacc, long long stride_in, long long first, int nstate,
+                             double eps, double* xqpos, double* xqvel, double* xqacc,
+                             long long stride_out, cudaStream_t stream);
+// out[(s*nrow + r)*ncol + k] = (f[k][s*nvar + v0 + r] - f[k][s*nvar]) / eps for r < nrow
+cudaError_t launch_fd_diff(const double* f, long long stride, int nstate, int nvar, int v0, int nrow,
+                           int ncol, double eps, double* out, cudaStream_t stream);
+
 // *counter += number of non-zero entries of status[0..n)
 cudaError_t launch_count_nonzero(const int* status, int n, int* counter, cudaStream_t stream);
 

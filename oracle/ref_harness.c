@@ -319,4 +319,22 @@ REFH_API void refh_compare_fwdinv(const mjModel* m, const double* qpos, const do
   mj_deleteData(d);
 }
 
+/* the reference's mjd_inverseFD (src/engine/engine_derivative_fd.c:611) looped over a batch, no
+ * actuation, no sensors: DfDq / DfDv / DfDa are nbatch x nv x nv (row i = derivative with respect
+ * to coordinate i), DmDq nbatch x nv x nM (may be NULL). */
+REFH_API void refh_inverse_fd_batch(const mjModel* m, long long nbatch, const double* qpos,
+                                    const double* qvel, const double* qacc, double eps,
+                                    double* DfDq, double* DfDv, double* DfDa, double* DmDq) {
+  mjData* d = mj_makeData(m);
+  const size_t nv = (size_t)m->nv, nM = (size_t)m->nM;
+  for (long long i = 0; i < nbatch; i++) {
+    mju_copy(d->qpos, qpos + i*m->nq, m->nq);
+    mju_copy(d->qvel, qvel + i*m->nv, m->nv);
+    mju_copy(d->qacc, qacc + i*m->nv, m->nv);
+    mjd_inverseFD(m, d, eps, 0, DfDq + i*nv*nv, DfDv + i*nv*nv, DfDa + i*nv*nv, NULL, NULL, NULL,
+                  DmDq ? DmDq + i*nv*nM : NULL);
+  }
+  mj_deleteData(d);
+}
+
 REFH_API int refh_sizeof_request(void) { return (int)sizeof(refhRequest); }

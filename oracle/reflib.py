@@ -157,6 +157,24 @@ class Model:
         return np.ctypeslib.as_array(p, shape=(n.value,))
 
     # ------------------------------------------------------------------ batch mj_inverse
+    def inverse_fd_batch(self, qpos, qvel, qacc, eps=1e-6, mass=False):
+        """The reference's mjd_inverseFD over a batch: (DfDq, DfDv, DfDa[, DmDq]), each
+        [nbatch, nv, nv] ([nbatch, nv, nM]); row i = derivative w.r.t. coordinate i."""
+        L = lib()
+        L.refh_inverse_fd_batch.restype = None
+        L.refh_inverse_fd_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 3 + \
+            [ctypes.c_double] + [ctypes.c_void_p] * 4
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        qacc = np.ascontiguousarray(qacc, dtype=np.float64)
+        n, nv, nM = qpos.shape[0], self.int("nv"), self.int("nM")
+        dq, dv, da = (np.zeros((n, nv, nv)) for _ in range(3))
+        dm = np.zeros((n, nv, nM)) if mass else None
+        L.refh_inverse_fd_batch(self.ptr, n, qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data, float(eps),
+                                dq.ctypes.data, dv.ctypes.data, da.ctypes.data,
+                                dm.ctypes.data if mass else None)
+        return (dq, dv, da, dm) if mass else (dq, dv, da)
+
     def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1):
         """Loop the reference's mj_inverse over the batch.
 

@@ -86,6 +86,26 @@ def make_case(name):
           f"mean nefc={out['nefc'].mean():.2f} max={out['ncon'].max()}/{out['nefc'].max()}")
 
 
+# finite-difference Jacobians of the reference (mjd_inverseFD, engine_derivative_fd.c:611) on the
+# first states of a case's stream: name -> (case whose model / state stream is used, nstate)
+FD_CASES = {"humanoid_fd": ("humanoid", 6), "zoo_fd": ("zoo", 6), "humanoid_nocontact_fd": ("humanoid_nocontact", 6)}
+FD_EPS = 1e-6
+
+
+def make_fd_case(name):
+    base, nstate = FD_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    dq, dv, da, dm = m.inverse_fd_batch(qpos, qvel, qacc, FD_EPS, mass=True)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), eps=np.array(FD_EPS), DfDq=dq, DfDv=dv, DfDa=da, DmDq=dm)
+    print(f"{name}: nv={m.int('nv')} states={nstate} max|DfDq|={np.abs(dq).max():.3g}")
+
+
 if __name__ == "__main__":
-    for case in (sys.argv[1:] or CASES):
-        make_case(case)
+    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES)):
+        (make_fd_case if case in FD_CASES else make_case)(case)

@@ -6,6 +6,8 @@ plus size-independent properties at BASELINE.json's full batch size.
 Bars (north_star): bit-exact ncon / contact geom pairs / efc_type / efc_id / counters;
 qfrc_inverse within 1e-9 relative + 1e-12 absolute.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -337,3 +339,26 @@ def test_contact_list_overflow_falls_back_on_the_device():
     np.testing.assert_array_equal(bd.counts()["ncon"], ref["ncon"])
     nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
     assert nviol == 0, (nviol, worst)
+
+
+@pytest.mark.parametrize("name", ["humanoid_fd", "zoo_fd", "humanoid_nocontact_fd"])
+def test_inverse_fd_matches_reference(name):
+    """mjb_inverseFD against the reference's mjd_inverseFD (engine_derivative_fd.c:611) on the same
+    states and eps. A forward difference amplifies the 1e-9-relative agreement of the two
+    evaluations by 1/eps, hence the tolerance: 2e-3 of the largest entry of the state's Jacobian
+    (contacts switching between the base and a perturbed state are the same in both engines)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    z = np.load(os.path.join(util.GOLDEN, name + ".npz"))
+    base = str(z["base"])
+    model = mjb.Model.from_mjb(util.golden(base)[0])
+    n = int(z["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(z["z_range"]))
+    bd = mjb.BatchData(model, n)
+    bd.set_state(qpos, qvel, qacc)
+    dq, dv, da, dm = bd.inverse_fd(eps=float(z["eps"]), mass=True)
+    for got, key in ((dq, "DfDq"), (dv, "DfDv"), (da, "DfDa"), (dm, "DmDq")):
+        ref = z[key]
+        scale = np.abs(ref).reshape(n, -1).max(axis=1)[:, None, None]
+        err = np.abs(got - ref) / np.maximum(scale, 1e-6)
+        assert err.max() < 2e-3, (key, float(err.max()))
