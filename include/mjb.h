@@ -43,7 +43,10 @@ typedef enum mjbOut_ {
   mjbOUT_CONTACT   = 1 << 2,  /* contact[].geom, dim, exclude, efc_address, dist, pos, frame          */
   mjbOUT_EFC       = 1 << 3,  /* efc_type, efc_id, efc_state, efc_pos, margin, D, R, vel, aref, force */
   mjbOUT_INERTIA   = 1 << 4,  /* qM, qLD, qLDiagInv (mj_crb, mj_factorM)                              */
-  mjbOUT_INTERNAL  = 1 << 5   /* every position/velocity-stage intermediate (xpos ... cfrc), debug    */
+  mjbOUT_INTERNAL  = 1 << 5,  /* every position/velocity-stage intermediate (xpos ... cfrc), debug    */
+  mjbOUT_RNEPOST   = 1 << 6   /* cacc, cfrc_int, cfrc_ext as left by mj_rnePostConstraint             *
+                               * (include/mujoco/mujoco.h mj_rnePostConstraint,                       *
+                               * src/engine/engine_core_smooth.c:2027-2181; mjdata.h cacc/cfrc_*)     */
 } mjbOut;
 
 /* per-state status bits, the batched form of d->warning[] (engine_forward.c:53-102,
@@ -72,6 +75,9 @@ typedef enum mjbField_ {
   mjbF_QLD,               /* double nC            (INERTIA)  */
   mjbF_QLDIAGINV,         /* double nv            (INERTIA)  */
   mjbF_INTERNAL,          /* double mjb_internalSize() (INTERNAL) */
+  mjbF_CACC,              /* double nbody*6: [angular, linear] acceleration, com frame (RNEPOST) */
+  mjbF_CFRC_INT,          /* double nbody*6: [torque, force] body <- parent, com frame (RNEPOST) */
+  mjbF_CFRC_EXT,          /* double nbody*6: [torque, force] of contacts and connect/weld rows (RNEPOST) */
   mjbF_COUNT
 } mjbField;
 

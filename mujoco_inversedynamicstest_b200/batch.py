@@ -15,13 +15,14 @@ import numpy as np
 
 from ._lib import lib
 
-OUT_QFRC, OUT_COUNTS, OUT_CONTACT, OUT_EFC, OUT_INERTIA, OUT_INTERNAL = (1 << i for i in range(6))
+OUT_QFRC, OUT_COUNTS, OUT_CONTACT, OUT_EFC, OUT_INERTIA, OUT_INTERNAL, OUT_RNEPOST = (1 << i for i in range(7))
 
 STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTRFULL = (
     1 << i for i in range(5))
 
 (F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
- F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL) = range(14)
+ F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL,
+ F_CACC, F_CFRC_INT, F_CFRC_EXT) = range(17)
 
 _INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
 _CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
@@ -272,6 +273,12 @@ class BatchData:
         out = {"type": ei[:, :, 0], "id": ei[:, :, 1], "state": ei[:, :, 2]}
         out.update({k: en[:, :, i] for i, k in enumerate(names)})
         return out
+
+    def rne_post_constraint(self):
+        """cacc, cfrc_int, cfrc_ext [nbatch, nbody, 6] as mj_rnePostConstraint leaves them
+        (src/engine/engine_core_smooth.c:2027-2181); needs OUT_RNEPOST."""
+        return {k: self.get(f).reshape(self.nbatch, -1, 6)
+                for k, f in (("cacc", F_CACC), ("cfrc_int", F_CFRC_INT), ("cfrc_ext", F_CFRC_EXT))}
 
     def internal(self, name):
         off, size = ctypes.c_int(), ctypes.c_int()

@@ -117,6 +117,19 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   std::vector<unsigned char> blob;
   std::string msg;
   if (!mjb::buildModelBlob(m, blob, msg)) return fail("mjb_makeData: " + msg);
+  if (outmask & mjbOUT_RNEPOST) {
+    // constraint forces of spatial tendons travel as body wrenches here but are not part of the
+    // reference's cfrc_ext; a massless tree has its frame origin at xipos, which is not kept
+    const mjbHdr* H0 = reinterpret_cast<const mjbHdr*>(blob.data());
+    if (H0->has_spatial) {
+      return fail("mjb_makeData: mjbOUT_RNEPOST is not available for models whose spatial tendons carry forces");
+    }
+    for (int b = 1; b < m->nbody; b++) {
+      if (m->body_parentid[b] == 0 && m->body_subtreemass[b] < mjMINVAL) {
+        return fail("mjb_makeData: mjbOUT_RNEPOST needs every kinematic tree to have mass");
+      }
+    }
+  }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -239,6 +252,16 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     ok = ok && devAlloc(d, &o.scratch_dump, (size_t)H.nscratch * S, "cudaMalloc(internal)");
     setField(d, mjbF_INTERNAL, o.scratch_dump, H.nscratch, 0);
   }
+  if (outmask & mjbOUT_RNEPOST) {
+    // mj_rnePostConstraint: cacc, cfrc_int, cfrc_ext (engine_core_smooth.c:2027-2181)
+    const size_t nb6 = 6 * (size_t)H.nbody;
+    ok = ok && devAlloc(d, &o.cacc, nb6 * S, "cudaMalloc(cacc)");
+    ok = ok && devAlloc(d, &o.cfrc_int, nb6 * S, "cudaMalloc(cfrc_int)");
+    ok = ok && devAlloc(d, &o.cfrc_ext, nb6 * S, "cudaMalloc(cfrc_ext)");
+    setField(d, mjbF_CACC, o.cacc, 6 * H.nbody, 0);
+    setField(d, mjbF_CFRC_INT, o.cfrc_int, 6 * H.nbody, 0);
+    setField(d, mjbF_CFRC_EXT, o.cfrc_ext, 6 * H.nbody, 0);
+  }
   if (!ok) {
     std::string e = d->error;
     mjb_deleteData(d);
@@ -272,6 +295,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(o.counts); cudaFree(o.status); cudaFree(o.contact_geom); cudaFree(o.contact_info);
   cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
   cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
+  cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext);
   delete d;
 }
 

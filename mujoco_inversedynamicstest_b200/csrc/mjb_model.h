@@ -237,6 +237,7 @@ enum {
   MJB_SC_crb,          // nbody*10  composite rigid-body inertias
   MJB_SC_ia,           // nbody*21  articulated-body inertias (symmetric 6x6, upper triangle)
   MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
+  MJB_SC_weld_dt,      // neq*3     weld rows: (raw rotational efc_force) - (torque J'f), for the cfrc_ext output (only models with welds)
   MJB_SC_COUNT
 };
 

@@ -74,6 +74,11 @@ struct Outputs {
   double* qLDiagInv;        // [nv][stride]
   // debug dump: every scratch slot copied out as [nscratch][stride] (null when not requested)
   double* scratch_dump;
+  // mj_rnePostConstraint (engine_core_smooth.c:2027-2181), all three or none, [nbody*6][stride],
+  // in the reference's frame (origin at subtree_com of the body's kinematic tree)
+  double* cacc;
+  double* cfrc_int;
+  double* cfrc_ext;
 };
 
 struct Ctx {
@@ -771,6 +776,12 @@ MJB_HD inline void equality_rows(Ctx& c) {
           weld_rot_map(col, quat1, quat, e);
           T[k] = col[0]*fr[0] + col[1]*fr[1] + col[2]*fr[2];
         }
+        // mj_rnePostConstraint reports the RAW rotational row forces as the weld's torque
+        // (engine_core_smooth.c:2092-2095), not J'f: keep the difference for the cfrc_ext output
+        if (c.out.cfrc_ext) {
+          const double dT[3] = {f[3] - T[0], f[4] - T[1], f[5] - T[2]};
+          stn(SC(weld_dt), 3*i, dT, 3);
+        }
       }
       add_wrench(c, b0, pos0, f, T, true);
       add_wrench(c, b1, pos1, f, T, false);
@@ -1344,7 +1355,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     }
     stc(cvel, 6*b, V, 6);
     stc(cal, 6*b, AL, 6);
-    if (tree_flags[b] & 4) stc(cacc, 6*b, A, 6);   // read back only by a child that is not b+1
+    // read back only by a child that is not b+1, or by the mj_rnePostConstraint outputs
+    if ((tree_flags[b] & 4) || c.out.cacc) stc(cacc, 6*b, A, 6);
 
     // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
     const int sf = body_sameframe[b];
@@ -2762,6 +2774,95 @@ MJB_HD inline void contact_process(Ctx& c, bool valid, int* list, int lstride, i
 }
 
 // ------------------------------------------------------------------------------------------
+// mj_rnePostConstraint (engine_core_smooth.c:2027-2181): cacc, cfrc_ext, cfrc_int per body, in
+// the reference's frame (origin at subtree_com of the body's tree). Everything it needs already
+// exists in the backward sweep: cacc from the forward sweep, the per-body constraint wrenches in
+// the two carriers (contacts, connect / weld rows; xfrc_applied is zero on this path exactly as
+// in an mjData fresh from mj_makeData), the subtree sums of the main loop. What is left is the
+// change of origin O -> C = subtree_com[root]:  motion  lin_C = lin_O + ang x d,
+//                                              force   trq_C = trq_O - d x F,   d = C - O,
+// with d = sum(mass*(xipos - O)) / sum(mass) over the tree, read from cinert[6..9] (mju_inertCom).
+
+// before the main loop (which folds the children into the carriers): per tree, d, then cacc and
+// the per-body cfrc_ext; d is left in the first three rows of the ROOT's cfrc_int output, which
+// the main loop overwrites last within the tree (bodies of a tree are contiguous, root first)
+MJB_HD inline void post_constraint_begin(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody;
+  const size_t N = (size_t)c.N;
+  const int* body_parentid = MI(body_parentid);
+  double* cinert = SC(cinert); double* cacc = SC(cacc);
+  double* fext = SC(cfrc_ext); double* fext1 = SC(cfrc_ext1);
+  for (int k = 0; k < 6; k++) {
+    double a = 0;
+    if (k >= 3 && !(H.disableflags & MJB_DSBL_GRAVITY)) a = -H.gravity[k - 3];
+    c.out.cacc[(size_t)k*N + c.s] = a;
+    c.out.cfrc_ext[(size_t)k*N + c.s] = 0;
+  }
+  int r = 1;
+  while (r < nbody) {
+    int e = r + 1;
+    while (e < nbody && body_parentid[e] != 0) e++;
+    double ms[4] = {0, 0, 0, 0};
+    for (int b = r; b < e; b++) {
+      double t[4];
+      ldn(t, cinert, 10*b + 6, 4);
+      for (int k = 0; k < 4; k++) ms[k] += t[k];
+    }
+    double d[3] = {0, 0, 0};
+    if (ms[3] >= MJB_MINVAL) { d[0] = ms[0]/ms[3]; d[1] = ms[1]/ms[3]; d[2] = ms[2]/ms[3]; }
+    for (int k = 0; k < 3; k++) c.out.cfrc_int[(size_t)(6*r + k)*N + c.s] = d[k];
+    for (int b = r; b < e; b++) {
+      double a[6], w[6], w1[6], cr[3];
+      ldn(a, cacc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
+      cross3(cr, a, d);
+      for (int k = 0; k < 3; k++) a[3 + k] += cr[k];
+      for (int k = 0; k < 6; k++) w[k] -= w1[k];
+      cross3(cr, d, w + 3);
+      for (int k = 0; k < 3; k++) w[k] -= cr[k];
+      for (int k = 0; k < 6; k++) {
+        c.out.cacc[(size_t)(6*b + k)*N + c.s] = a[k];
+        c.out.cfrc_ext[(size_t)(6*b + k)*N + c.s] = w[k];
+      }
+    }
+    r = e;
+  }
+}
+
+// after the main loop: the weld torque convention of the reference and the world body's row
+MJB_HD inline void post_constraint_end(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* body_parentid = MI(body_parentid);
+  if (H.neq && rows_enabled(H) && !(H.disableflags & MJB_DSBL_EQUALITY)) {
+    const int* eq_int = MI(eq_int);
+    for (int i = 0; i < H.neq; i++) {
+      const int* ei = eq_int + MJB_EQ_NI*i;
+      if (ei[MJB_EQI_TYPE] != 1 || !ei[MJB_EQI_ACTIVE] || ei[MJB_EQI_SKIP]) continue;
+      double dT[3];
+      ldn(dT, SC(weld_dt), 3*i, 3);
+      for (int side = 0; side < 2; side++) {
+        const int body = ei[side == 0 ? MJB_EQI_B0 : MJB_EQI_B1];
+        const double sg = side == 0 ? 1.0 : -1.0;
+        if (!body) continue;
+        for (int k = 0; k < 3; k++) c.out.cfrc_ext[(size_t)(6*body + k)*N + c.s] += sg*dT[k];
+        for (int a = body; a > 0; a = body_parentid[a]) {
+          for (int k = 0; k < 3; k++) c.out.cfrc_int[(size_t)(6*a + k)*N + c.s] -= sg*dT[k];
+        }
+      }
+    }
+  }
+  // the reference adds the trees' root rows into the world body's row as they are (:2178-2180)
+  double s0[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = H.nbody - 1; b > 0; b--) {
+    if (body_parentid[b] == 0) {
+      for (int k = 0; k < 6; k++) s0[k] += c.out.cfrc_int[(size_t)(6*b + k)*N + c.s];
+    }
+  }
+  for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)k*N + c.s] = s0[k];
+}
+
+// ------------------------------------------------------------------------------------------
 // backward half of mj_rne(flg_acc=1) (engine_core_smooth.c:2008-2020) fused with the last loop of
 // mj_inverseSkip (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree
 // separately and projected with the same cdof, which is J'*efc_force for the point constraints.
@@ -2788,6 +2889,10 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   double* fgc = SC(cfrc_gc);
   const int* dof_jntid = MI(dof_jntid);
   const int* jnt_actgravcomp = MI(jnt_actgravcomp);
+  const bool post = c.out.cfrc_int != nullptr;
+  if (post) post_constraint_begin(c);
+  int post_tree = -1;
+  double post_d[3] = {0, 0, 0};
   int carry_for = -1;
   double cf[6], cw[6], cg[6] = {0, 0, 0, 0, 0, 0};
   for (int b = nbody - 1; b > 0; b--) {
@@ -2803,6 +2908,20 @@ MJB_HD inline void rne_and_output(Ctx& c) {
     for (int k = 0; k < 6; k++) w[k] -= w1[k];
     if (carry_for == b) {
       for (int k = 0; k < 6; k++) { f[k] += cf[k]; w[k] += cw[k]; g[k] += cg[k]; }
+    }
+    if (post) {
+      // cfrc_int = sum over the subtree of (inertial force - external force), re-expressed about
+      // the tree's centre of mass; the shift was left in the root's row by post_constraint_begin
+      const int r = MI(body_rootid)[b];
+      if (r != post_tree) {
+        for (int k = 0; k < 3; k++) post_d[k] = c.out.cfrc_int[(size_t)(6*r + k)*N + c.s];
+        post_tree = r;
+      }
+      double o[6], cr[3];
+      for (int k = 0; k < 6; k++) o[k] = f[k] - w[k];
+      cross3(cr, post_d, o + 3);
+      for (int k = 0; k < 3; k++) o[k] -= cr[k];
+      for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)(6*b + k)*N + c.s] = o[k];
     }
     const int d0 = body_dofadr[b], dn = body_dofnum[b];
     for (int i = d0; i < d0 + dn; i++) {
@@ -2830,6 +2949,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       carry_for = p;
     }
   }
+  if (post) post_constraint_end(c);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -716,6 +716,11 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt; sizes[MJB_SC_ten_acc] = nt;
     sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
     sizes[MJB_SC_cfrc_gc] = (gravcomp || spatial_passive) ? 6*nb : 0;
+    {
+      bool has_weld = false;
+      for (int i = 0; i < m->neq; i++) has_weld = has_weld || m->eq_type[i] == mjEQ_WELD;
+      sizes[MJB_SC_weld_dt] = has_weld ? 3*m->neq : 0;
+    }
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;
@@ -739,7 +744,7 @@ const char* scratchSlotName(int slot) {
     "xpos", "xquat", "origin", "geom_xpos", "geom_xmat",
     "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
     "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "ten_acc", "crb", "ia",
-    "cfrc_gc"};
+    "cfrc_gc", "weld_dt"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
 

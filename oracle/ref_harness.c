@@ -213,6 +213,11 @@ typedef struct {
   int err;
 } refhChunk;
 
+/* when set, mj_rnePostConstraint runs after mj_inverse (mj_sensorAcc calls it only for models with
+ * acceleration / force / torque sensors, engine_sensor.c; cacc, cfrc_int, cfrc_ext are its outputs) */
+static int refh_post_constraint = 0;
+REFH_API void refh_set_post_constraint(int on) { refh_post_constraint = on; }
+
 static void* run_chunk(void* arg) {
   refhChunk* c = (refhChunk*)arg;
   const mjModel* m = c->m;
@@ -223,6 +228,7 @@ static void* run_chunk(void* arg) {
     mju_copy(d->qvel, c->qvel + i*m->nv, m->nv);
     mju_copy(d->qacc, c->qacc + i*m->nv, m->nv);
     mj_inverse(m, d);
+    if (refh_post_constraint) mj_rnePostConstraint(m, d);
     if (c->qfrc_inverse) mju_copy(c->qfrc_inverse + i*m->nv, d->qfrc_inverse, m->nv);
     for (int r = 0; r < c->nreq; r++) {
       if (copy_request(m, d, c->req + r, i)) c->err = 1;

@@ -205,6 +205,8 @@ class Model:
                 arr = np.zeros((n, maxrows, nc), dtype=dt)
             out[name] = arr
             reqs.append((name.encode(), arr, maxrows))
+        # cacc / cfrc_int / cfrc_ext are outputs of mj_rnePostConstraint, run after mj_inverse on request
+        L.refh_set_post_constraint(int(any(k in fields for k in ("cacc", "cfrc_int", "cfrc_ext"))))
         rq = (_Request * max(1, len(reqs)))()
         for i, (nm, arr, mr) in enumerate(reqs):
             rq[i].name = nm
@@ -227,6 +229,7 @@ class Model:
             "qfrc_bias": ("nv", 1), "qfrc_passive": ("nv", 1), "qfrc_constraint": ("nv", 1),
             "qfrc_spring": ("nv", 1), "qfrc_damper": ("nv", 1), "ten_length": ("ntendon", 1),
             "ten_velocity": ("ntendon", 1), "ten_J": ("ntendon", "nv"),
+            "cacc": ("nbody", 6), "cfrc_int": ("nbody", 6), "cfrc_ext": ("nbody", 6),
         }
         if name in known:
             r, c = known[name]

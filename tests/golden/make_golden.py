@@ -106,6 +106,29 @@ def make_fd_case(name):
     print(f"{name}: nv={m.int('nv')} states={nstate} max|DfDq|={np.abs(dq).max():.3g}")
 
 
+# mj_rnePostConstraint after mj_inverse (engine_core_smooth.c:2027-2181; what mj_sensorAcc runs for
+# accelerometer / force / torque sensors): cacc, cfrc_int, cfrc_ext on the first states of a case's
+# stream: name -> (case whose model / state stream is used, nstate)
+POST_CASES = {"humanoid_post": ("humanoid", 128), "humanoid_elliptic_post": ("humanoid_elliptic", 64),
+              "humanoids22_post": ("humanoids22", 4), "weld_post": ("weld", 64),
+              "connect_post": ("connect", 64), "zoo_post": ("zoo", 128), "capsbox_post": ("capsbox", 64),
+              "boxes_post": ("boxes", 64), "gravcomp_post": ("gravcomp", 32)}
+
+
+def make_post_case(name):
+    base, nstate = POST_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields={"cacc": None, "cfrc_int": None, "cfrc_ext": None})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), **out)
+    print(f"{name}: nbody={m.int('nbody')} states={nstate} max|cfrc_ext|={np.abs(out['cfrc_ext']).max():.3g}")
+
+
 if __name__ == "__main__":
-    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES)):
-        (make_fd_case if case in FD_CASES else make_case)(case)
+    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES)):
+        (make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else make_case)(case)

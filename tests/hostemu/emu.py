@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext"]
 
 
 class Outputs(ctypes.Structure):
@@ -40,7 +40,7 @@ def available():
     return os.path.exists(build_hostemu.LIB) or build_hostemu.include_dir() is not None
 
 
-def run(model, qpos, qvel, qacc, nconmax=64, njmax=256):
+def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -59,7 +59,10 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256):
              efc_num=np.zeros((njmax * 8, n)), qM=np.zeros((model.int("nM"), n)),
              qLD=np.zeros((model.int("nC"), n)), qLDiagInv=np.zeros((nv, n)),
              scratch_dump=np.zeros((nsc, n)))
-    o = Outputs(**{k: v.ctypes.data for k, v in a.items()})
+    if post:      # mj_rnePostConstraint outputs
+        nb = model.int("nbody")
+        a.update(cacc=np.zeros((6 * nb, n)), cfrc_int=np.zeros((6 * nb, n)), cfrc_ext=np.zeros((6 * nb, n)))
+    o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL
     err = ctypes.create_string_buffer(1000)
     qp, qv, qa = (np.ascontiguousarray(x.T, dtype=np.float64) for x in (qpos, qvel, qacc))
     if L.hostemu_inverse(model.ptr, n, qp.ctypes.data, qv.ctypes.data, qa.ctypes.data, nconmax,

@@ -93,6 +93,63 @@ def test_golden_inertia_outputs(name):
     np.testing.assert_allclose(cdof, ref["cdof"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("name", util.POST_CASES)
+def test_golden_rne_post_constraint(name):
+    """mjbOUT_RNEPOST: cacc, cfrc_int, cfrc_ext of the reference's mj_rnePostConstraint after
+    mj_inverse (engine_core_smooth.c:2027-2181), 1e-9 relative / 1e-12 absolute."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.post_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_RNEPOST)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    got = bd.rne_post_constraint()
+    for k in ("cacc", "cfrc_int", "cfrc_ext"):
+        nviol, worst = util.spatial_violations(got[k], ref[k])
+        assert nviol == 0, (k, nviol, worst)
+    # bodies that no contact or equality constraint touches carry exactly zero (single components
+    # that cancel exactly on the CPU may keep an FMA residual here, inside the tolerance above)
+    assert (got["cfrc_ext"][(ref["cfrc_ext"] == 0).all(axis=-1)] == 0).all()
+    # the extra outputs do not change qfrc_inverse by a bit
+    plain = mjb.BatchData(model, n)
+    plain.set_state(qpos, qvel, qacc)
+    plain.inverse()
+    np.testing.assert_array_equal(bd.qfrc_inverse(), plain.qfrc_inverse())
+
+
+def test_rne_post_constraint_newton_euler_balance():
+    """Size-independent property on 2^16 humanoid states: for a free-floating tree the root's
+    cfrc_int is the wrench its (force-free) free joint transmits, so it equals qfrc_inverse of the
+    free joint's dofs: force rows in world axes, torque rows in body axes about the root body's
+    frame -- here checked through the force part, which is independent of the reference point."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, _ = util.golden("humanoid")
+    model = mjb.Model.from_mjb(path)
+    n = 1 << 16
+    qpos, qvel, qacc = generate_states(model, n, z_range=(0.0, 1.5))
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_RNEPOST)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    post = bd.rne_post_constraint()
+    q = bd.qfrc_inverse()
+    f = post["cfrc_int"][:, 1, 3:6]
+    scale = np.maximum(np.abs(f).max(axis=1, keepdims=True), 1.0)
+    assert (np.abs(f - q[:, 0:3]) <= 1e-9 * scale).all()
+    # the world body's row is the sum of the trees' root rows (engine_core_smooth.c:2178-2180)
+    np.testing.assert_array_equal(post["cfrc_int"][:, 0], post["cfrc_int"][:, 1])
+    assert np.isfinite(post["cacc"]).all() and np.isfinite(post["cfrc_ext"]).all()
+
+
+def test_rne_post_constraint_refused_for_force_carrying_spatial_tendons():
+    import mujoco_inversedynamicstest_b200 as mjb
+    model = mjb.Model.from_mjb(util.golden("tendons")[0])
+    with pytest.raises(mjb.MjbError, match="RNEPOST"):
+        mjb.BatchData(model, 32, outmask=mjb.OUT_RNEPOST)
+
+
 def test_ldl_reconstructs_mass_matrix():
     """L' D L == M (test/engine/engine_core_smooth_test.cc:466-511, 1e-12 there on a small model)."""
     import mujoco_inversedynamicstest_b200 as mjb

@@ -78,6 +78,25 @@ def test_continuous_outputs(name):
     assert (np.abs(out["qfrc_constraint"] - ref["qfrc_constraint"]) <= 1e-12 + 1e-12 * cs).all()
 
 
+@pytest.mark.parametrize("name", util.POST_CASES)
+def test_rne_post_constraint_outputs(name):
+    """cacc, cfrc_int, cfrc_ext against the reference's mj_rnePostConstraint run after mj_inverse
+    (engine_core_smooth.c:2027-2181), incl. its raw-torque convention for weld rows."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.post_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200, post=True)
+    nb = model.int("nbody")
+    for k in ("cacc", "cfrc_int", "cfrc_ext"):
+        nviol, worst = util.spatial_violations(out[k].reshape(n, nb, 6), ref[k])
+        assert nviol == 0, (k, nviol, worst)
+    # bodies without contacts or equality constraints carry exactly zero external force
+    zero = ref["cfrc_ext"] == 0
+    assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
+
+
 def test_candidate_list_contains_reference_contacts_in_order():
     """Every contact the reference reports (after its broadphase/midphase) appears in the static
     candidate list, in the same relative order (engine_collision_driver.c:265-484)."""

@@ -70,3 +70,25 @@ def to_com_frame(model, xpos, xquat, origin, vec, per):
     out = vec.copy()
     out[..., 3:] += np.cross(vec[..., :3], shift)
     return out
+
+
+POST_CASES = ["humanoid_post", "humanoid_elliptic_post", "humanoids22_post", "weld_post", "connect_post",
+              "zoo_post", "capsbox_post", "boxes_post", "gravcomp_post"]
+
+
+def post_fixture(name):
+    """(path of the base case's MJB, dict with cacc / cfrc_int / cfrc_ext [n, nbody, 6] of the
+    reference's mj_rnePostConstraint, nstate, z_range) of a tests/golden/*_post.npz fixture."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in ("cacc", "cfrc_int", "cfrc_ext")},
+            int(z["nstate"]), tuple(z["z_range"]))
+
+
+def spatial_violations(got, ref, rtol=RTOL, atol=ATOL):
+    """north_star bound for per-body spatial vectors [n, nbody, 6]; like qfrc_violations_scaled the
+    relative part is taken against the largest entry of the STATE (sums of contact wrenches of
+    magnitude F carry rounding of order eps*F in every component)."""
+    d = np.abs(got - ref)
+    scale = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1)[:, None, None]
+    tol = atol + rtol * np.maximum(np.abs(ref), 1e-3 * scale)
+    return int((d > tol).sum()), float((d / tol).max()) if d.size else 0.0
