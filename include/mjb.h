@@ -78,15 +78,18 @@ typedef enum mjbField_ {
   mjbF_CACC,              /* double nbody*6: [angular, linear] acceleration, com frame (RNEPOST) */
   mjbF_CFRC_INT,          /* double nbody*6: [torque, force] body <- parent, com frame (RNEPOST) */
   mjbF_CFRC_EXT,          /* double nbody*6: [torque, force] of contacts and connect/weld rows (RNEPOST) */
+  mjbF_SENSORDATA,        /* double nsensordata: d->sensordata (models with sensors, no mask bit needed) */
   mjbF_COUNT
 } mjbField;
 
 /* Validate `m`, flatten its constant tables, upload them to CUDA device `device` and allocate
  * batch buffers for up to nbatch_max states. Returns NULL and writes a message into err (if not
  * NULL) when the model uses a feature outside the supported path (convex/mesh/hfield/SDF geom
- * pairs that survive the static collision filters, flex, plugins, fluid forces, sensors without
- * mjDSBL_SENSOR, INVDISCRETE with a non-Euler integrator; full list in DESIGN.md section 5) or when
- * CUDA fails.
+ * pairs that survive the static collision filters, flex, plugins, fluid forces, sensor types that
+ * are not evaluated on the device (touch, rays, cameras ...) without mjDSBL_SENSOR, INVDISCRETE with
+ * a non-Euler integrator; full list in DESIGN.md section 5) or when CUDA fails.
+ * Models with sensors get d->sensordata (mjbF_SENSORDATA) from mj_sensorPos / Vel / Acc
+ * (src/engine/engine_sensor.c:222,527,708) on every mjb_inverse, like mj_inverse.
  * nconmax / njmax bound the per-state contact / constraint-row OUTPUT arrays (they do not limit
  * the physics); pass 0 for defaults. */
 MJB_API mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned outmask,
@@ -110,8 +113,8 @@ MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qve
 MJB_API int mjb_inverse(const mjModel* m, mjbData* d, int nbatch);
 /* mj_inverseSkip over the batch (include/mujoco/mujoco.h:137; used by src/inverse/inverse_test.cpp:93
  * with mjSTAGE_VEL, skipsensor = 1). skipstage only permits the CPU engine to reuse earlier stages;
- * the batched engine recomputes everything, which yields the same results. skipsensor must be 1 for
- * models with sensors. Returns like mjb_inverse. */
+ * the batched engine recomputes everything, which yields the same results. skipsensor != 0 leaves
+ * sensordata untouched. Returns like mjb_inverse. */
 MJB_API int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int skipsensor);
 /* mjd_inverseFD over the batch (include/mujoco/mujoco.h mjd_inverseFD, src/engine/
  * engine_derivative_fd.c:611; flg_actuation = 0, sensors not evaluated): forward-difference

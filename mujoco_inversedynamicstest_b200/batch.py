@@ -22,7 +22,7 @@ STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTR
 
 (F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
  F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL,
- F_CACC, F_CFRC_INT, F_CFRC_EXT) = range(17)
+ F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA) = range(18)
 
 _INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
 _CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
@@ -279,6 +279,10 @@ class BatchData:
         (src/engine/engine_core_smooth.c:2027-2181); needs OUT_RNEPOST."""
         return {k: self.get(f).reshape(self.nbatch, -1, 6)
                 for k, f in (("cacc", F_CACC), ("cfrc_int", F_CFRC_INT), ("cfrc_ext", F_CFRC_EXT))}
+
+    def sensordata(self):
+        """d->sensordata [nbatch, nsensordata] (mj_sensorPos / Vel / Acc; models with sensors)."""
+        return self.get(F_SENSORDATA)
 
     def internal(self, name):
         off, size = ctypes.c_int(), ctypes.c_int()

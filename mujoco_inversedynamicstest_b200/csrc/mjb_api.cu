@@ -65,6 +65,7 @@ struct mjbData_ {
   // mjb_inverseFD: inner batch of perturbed states and the device buffer of the differences
   mjbData* fd = nullptr;
   int fd_tile = 0;
+  int skip_sensors = 0;        // mj_inverseSkip(skipsensor = 1) / inner batches of mjb_inverseFD
   double* d_fd_out = nullptr;
   size_t fd_out_doubles = 0;
   std::string error;
@@ -117,6 +118,10 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   std::vector<unsigned char> blob;
   std::string msg;
   if (!mjb::buildModelBlob(m, blob, msg)) return fail("mjb_makeData: " + msg);
+  {
+    const mjbHdr* H0 = reinterpret_cast<const mjbHdr*>(blob.data());
+    if (H0->sensor_post) outmask |= mjbOUT_RNEPOST;   // accelerometer / force / torque / frame*acc sensors
+  }
   if (outmask & mjbOUT_RNEPOST) {
     // constraint forces of spatial tendons travel as body wrenches here but are not part of the
     // reference's cfrc_ext; a massless tree has its frame origin at xipos, which is not kept
@@ -262,6 +267,12 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     setField(d, mjbF_CFRC_INT, o.cfrc_int, 6 * H.nbody, 0);
     setField(d, mjbF_CFRC_EXT, o.cfrc_ext, 6 * H.nbody, 0);
   }
+  if (H.nsensordata > 0) {
+    // sensordata is part of mj_inverse's output contract (engine_inverse.c:206-246): always produced
+    ok = ok && devAlloc(d, &o.sensordata, (size_t)H.nsensordata * S, "cudaMalloc(sensordata)");
+    ok = ok && check(d, cudaMemset(o.sensordata, 0, (size_t)H.nsensordata * S * sizeof(double)), "cudaMemset(sensordata)");
+    setField(d, mjbF_SENSORDATA, o.sensordata, H.nsensordata, 0);
+  }
   if (!ok) {
     std::string e = d->error;
     mjb_deleteData(d);
@@ -295,7 +306,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(o.counts); cudaFree(o.status); cudaFree(o.contact_geom); cudaFree(o.contact_info);
   cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
   cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
-  cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext);
+  cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext); cudaFree(o.sensordata);
   delete d;
 }
 
@@ -361,6 +372,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.slot_rec = d->d_slot_rec;
   a.has_gravcomp = d->hdr.passive_wrench;
   a.has_spatial = d->hdr.has_spatial;
+  a.skip_sensors = d->skip_sensors;
   a.out = d->out;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
   for (long long start = first; start < first + count; start += d->chunk_stride) {
@@ -486,18 +498,17 @@ int mjb_inverse(const mjModel* m, mjbData* d, int nbatch) {
 // previous call on the same mjData; the results equal a full evaluation whenever the caller kept
 // the corresponding inputs unchanged, which is the function's contract. Here every stage is
 // recomputed (one fused sweep: nothing is cached per state between calls), so the value is
-// validated and otherwise ignored. Sensors are not evaluated: skipsensor must be non-zero unless
-// the model has none (mjb_makeData refuses sensor models without mjDSBL_SENSOR).
+// validated and otherwise ignored. skipsensor != 0 leaves sensordata as the last evaluation wrote
+// it, like the reference.
 int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int skipsensor) {
   if (skipstage < mjSTAGE_NONE || skipstage > mjSTAGE_VEL) {
     d->error = "mjb_inverseSkip: skipstage must be mjSTAGE_NONE, mjSTAGE_POS or mjSTAGE_VEL";
     return -1;
   }
-  if (!skipsensor && m && m->nsensor > 0 && !(m->opt.disableflags & mjDSBL_SENSOR)) {
-    d->error = "mjb_inverseSkip: sensors are not evaluated (pass skipsensor = 1)";
-    return -1;
-  }
-  return mjb_inverse(m, d, nbatch);
+  d->skip_sensors = skipsensor != 0;
+  const int r = mjb_inverse(m, d, nbatch);
+  d->skip_sensors = 0;
+  return r;
 }
 
 // mjd_inverseFD over the batch (src/engine/engine_derivative_fd.c:611, flg_actuation = 0, no
@@ -525,6 +536,7 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
   }
   mjbData* x = d->fd;
   x->stream = d->stream;
+  x->skip_sensors = 1;            // mjd_inverseFD's sensor Jacobians are not produced
   const size_t need = (size_t)tile * nv * (size_t)(want_mass ? (nv > nM ? nv : nM) : nv);
   if (need > d->fd_out_doubles) {
     cudaFree(d->d_fd_out);

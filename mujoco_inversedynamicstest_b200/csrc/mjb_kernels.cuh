@@ -59,6 +59,7 @@ struct LaunchArgs {
   int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
+  int skip_sensors;             // mj_inverseSkip(skipsensor = 1): leave sensordata as it is
   Outputs out;
 };
 

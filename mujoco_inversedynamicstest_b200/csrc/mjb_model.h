@@ -69,6 +69,7 @@
   X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
   X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
+  X(sensor_int) /* nsensor*MJB_SEN_NI : sensors evaluated on the device, see MJB_SEN_*       */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored), \
                                  bit3 pose read by an equality constraint or a tendon site */
@@ -100,6 +101,7 @@
   X(geom_pos, ngeom, 3)           \
   X(geom_quat, ngeom, 4)          \
   X(site_pos, nsite, 3)           \
+  X(site_quat, nsite, 4)          \
   X(tendon_range, ntendon, 2)     \
   X(tendon_margin, ntendon, 1)    \
   X(tendon_stiffness, ntendon, 1) \
@@ -119,7 +121,8 @@
   X(sp_tendon_friction) /* ntendon */ \
   X(sp_eq)            /* neq     */ \
   X(eq_num)           /* neq*MJB_EQ_NN: site offsets / quaternions of site-defined constraints */ \
-  X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */
+  X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */ \
+  X(sensor_cutoff)    /* nsensor */
 
 enum {
 #define X(name, rows) MJB_I_##name,
@@ -174,6 +177,19 @@ enum {
   MJB_CN_SOLIMP = MJB_CN_SOLREF + 2,      // 5: contact.solimp as stored (unclamped)
   MJB_CAND_NN = MJB_CN_SOLIMP + 5
 };
+
+// sensor: integer columns (mjModel sensor_* arrays, include/mujoco/mjmodel.h)
+enum { MJB_SEN_TYPE = 0, MJB_SEN_DATATYPE, MJB_SEN_OBJTYPE, MJB_SEN_OBJID, MJB_SEN_REFTYPE, MJB_SEN_REFID,
+       MJB_SEN_DIM, MJB_SEN_ADR, MJB_SEN_NI };
+// mjtSensor / mjtObj / mjtDataType values restated (include/mujoco/mjmodel.h)
+enum { MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
+       MJB_SENS_TORQUE = 5, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
+       MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_FRAMEPOS = 25,
+       MJB_SENS_FRAMEQUAT = 26, MJB_SENS_FRAMEXAXIS = 27, MJB_SENS_FRAMEYAXIS = 28, MJB_SENS_FRAMEZAXIS = 29,
+       MJB_SENS_FRAMELINVEL = 30, MJB_SENS_FRAMEANGVEL = 31, MJB_SENS_FRAMELINACC = 32,
+       MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34 };
+enum { MJB_OBJ_BODY = 1, MJB_OBJ_XBODY = 2, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6 };
+enum { MJB_DATATYPE_REAL = 0, MJB_DATATYPE_POSITIVE = 1 };
 
 // equality constraint: integer columns (mj_instantiateEquality, engine_core_constraint.c:493-763)
 enum {
@@ -258,6 +274,10 @@ typedef struct mjbHdr_ {
   int32_t has_spatial;      // some spatial tendon carries a force (its path is walked on the device)
   int32_t passive_wrench;   // the passive body-wrench carrier exists (gravcomp or spatial-tendon springs/dampers)
   int32_t discrete_acc;     // mjENBL_INVDISCRETE with Euler and damped dofs: qacc is converted first
+  int32_t nsensor;          // sensors evaluated on the device (0 with mjDSBL_SENSOR), nsensordata their rows
+  int32_t nsensordata;
+  int32_t sensor_post;      // some sensor reads cacc / cfrc_int (mj_rnePostConstraint, engine_sensor.c:727-740)
+  int32_t nsite;
   double timestep, impratio;
   double gravity[3];
   double pad1;

@@ -79,6 +79,8 @@ struct Outputs {
   double* cacc;
   double* cfrc_int;
   double* cfrc_ext;
+  // sensordata [nsensordata][stride] (mj_sensorPos / Vel / Acc), null for models without sensors
+  double* sensordata;
 };
 
 struct Ctx {
@@ -1274,7 +1276,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     quat2Mat(mat, quat);
     // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
     // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
-    if ((tree_flags[b] & 12) || c.out.scratch_dump) {
+    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata) {
       stc(xquat, 4*b, quat, 4);
       stc(xpos, 3*b, pos, 3);
     }
@@ -2953,6 +2955,205 @@ MJB_HD inline void rne_and_output(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Sensors: mj_sensorPos, mj_sensorVel, mj_sensorAcc (engine_sensor.c:222-520, 527-704, 708-913) for
+// the sensor types whose inputs exist on this path (the others are refused at upload). Runs after
+// the backward sweep: body poses and cvel / cacc come from the scratch (about the tree origin O,
+// so points are offset from O instead of subtree_com), cfrc_int from the mj_rnePostConstraint
+// output (about the tree's centre of mass C = O + d).
+
+// world pose of a sensor object (get_xpos_xmat / get_xquat, engine_sensor.c:73-123; the frames
+// are the ones mj_kinematics builds with mj_local2Global, engine_core_smooth.c:159-200)
+MJB_HD inline int sensor_object(Ctx& c, int objtype, int objid, double* pos, double* quat) {
+  int body = objid;
+  const double* lpos = nullptr; const double* lquat = nullptr;
+  if (objtype == MJB_OBJ_BODY) { lpos = MD(body_ipos) + 3*objid; lquat = MD(body_iquat) + 4*objid; }
+  else if (objtype == MJB_OBJ_GEOM) {
+    body = MI(geom_bodyid)[objid]; lpos = MD(geom_pos) + 3*objid; lquat = MD(geom_quat) + 4*objid;
+  } else if (objtype == MJB_OBJ_SITE) {
+    body = MI(site_bodyid)[objid]; lpos = MD(site_pos) + 3*objid; lquat = MD(site_quat) + 4*objid;
+  }
+  double bq[4];
+  ldn(pos, SC(xpos), 3*body, 3); ldn(bq, SC(xquat), 4*body, 4);
+  if (lpos) {
+    double m[9], r[3];
+    quat2Mat(m, bq);
+    mulMatVec3(r, m, lpos);
+    pos[0] += r[0]; pos[1] += r[1]; pos[2] += r[2];
+    mulQuat(quat, bq, lquat);
+  } else {
+    for (int k = 0; k < 4; k++) quat[k] = bq[k];
+  }
+  return body;
+}
+
+// mj_objectVelocity / mj_objectAcceleration in world axes (engine_support.c:1265-1370): motion of
+// the body-fixed point `pos` from a carrier about O; acc adds the correction omega x v
+MJB_HD inline void sensor_point_motion(Ctx& c, const double* carrier, int body, const double* pos, double* res) {
+  double lin[3], ang[3];
+  point_motion(c, carrier, body, pos, lin, ang);
+  for (int k = 0; k < 3; k++) { res[k] = ang[k]; res[3 + k] = lin[k]; }
+}
+
+MJB_HD inline void sensors(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* sen = MI(sensor_int);
+  const double* cutoff = MD(sensor_cutoff);
+  const int* body_parentid = MI(body_parentid);
+  const int* rootid = MI(body_rootid);
+  for (int i = 0; i < H.nsensor; i++) {
+    const int* si = sen + MJB_SEN_NI*i;
+    const int type = si[MJB_SEN_TYPE], objtype = si[MJB_SEN_OBJTYPE], objid = si[MJB_SEN_OBJID];
+    const int reftype = si[MJB_SEN_REFTYPE], refid = si[MJB_SEN_REFID];
+    double v[4] = {0, 0, 0, 0};
+    if (type == MJB_SENS_JOINTPOS) {
+      v[0] = QPOS(MI(jnt_qposadr)[objid]);
+    } else if (type == MJB_SENS_JOINTVEL) {
+      v[0] = QVEL(MI(jnt_dofadr)[objid]);
+    } else if (type == MJB_SENS_TENDONPOS) {
+      v[0] = AT(SC(ten_length), objid);
+    } else if (type == MJB_SENS_TENDONVEL) {
+      v[0] = AT(SC(ten_velocity), objid);
+    } else if (type == MJB_SENS_BALLQUAT) {
+      const int a = MI(jnt_qposadr)[objid];
+      for (int k = 0; k < 4; k++) v[k] = QPOS(a + k);
+      normalize4(v);
+    } else if (type == MJB_SENS_BALLANGVEL) {
+      const int a = MI(jnt_dofadr)[objid];
+      for (int k = 0; k < 3; k++) v[k] = QVEL(a + k);
+    } else if (type == MJB_SENS_SUBTREECOM) {
+      // mj_comPos (engine_core_smooth.c:183-225): mass-weighted mean of xipos over the subtree,
+      // whose bodies are contiguous; mass*(xipos - O) and mass are cinert[6..9]
+      double ms[4] = {0, 0, 0, 0}, o[3];
+      int e = objid;
+      do {
+        double t[4];
+        ldn(t, SC(cinert), 10*e + 6, 4);
+        for (int k = 0; k < 4; k++) ms[k] += t[k];
+        e++;
+      } while (e < H.nbody && body_parentid[e] >= objid && objid > 0);
+      if (objid == 0) {
+        // the world's subtree is every body, each tree about its own origin
+        ms[0] = ms[1] = ms[2] = ms[3] = 0;
+        for (int b = 1; b < H.nbody; b++) {
+          double t[4];
+          ldn(t, SC(cinert), 10*b + 6, 4); ldn(o, SC(origin), 3*rootid[b], 3);
+          for (int k = 0; k < 3; k++) ms[k] += t[k] + t[3]*o[k];
+          ms[3] += t[3];
+        }
+        o[0] = o[1] = o[2] = 0;
+      } else {
+        ldn(o, SC(origin), 3*rootid[objid], 3);
+      }
+      if (ms[3] >= MJB_MINVAL) {
+        for (int k = 0; k < 3; k++) v[k] = o[k] + ms[k]/ms[3];
+      } else {
+        double q[4];
+        sensor_object(c, MJB_OBJ_BODY, objid, v, q);
+      }
+    } else if (type >= MJB_SENS_FRAMEPOS && type <= MJB_SENS_FRAMEZAXIS) {
+      double pos[3], quat[4], rpos[3], rquat[4], rmat[9];
+      sensor_object(c, objtype, objid, pos, quat);
+      if (refid >= 0) { sensor_object(c, reftype, refid, rpos, rquat); quat2Mat(rmat, rquat); }
+      if (type == MJB_SENS_FRAMEQUAT) {
+        if (refid >= 0) {
+          const double nq[4] = {rquat[0], -rquat[1], -rquat[2], -rquat[3]};
+          mulQuat(v, nq, quat);
+        } else {
+          for (int k = 0; k < 4; k++) v[k] = quat[k];
+        }
+      } else {
+        double w[3];
+        if (type == MJB_SENS_FRAMEPOS) {
+          for (int k = 0; k < 3; k++) w[k] = refid >= 0 ? pos[k] - rpos[k] : pos[k];
+        } else {
+          double m[9];
+          quat2Mat(m, quat);
+          const int off = type - MJB_SENS_FRAMEXAXIS;
+          w[0] = m[off]; w[1] = m[off + 3]; w[2] = m[off + 6];
+        }
+        if (refid >= 0) mulMatTVec3(v, rmat, w); else { v[0] = w[0]; v[1] = w[1]; v[2] = w[2]; }
+      }
+    } else if (type == MJB_SENS_VELOCIMETER || type == MJB_SENS_GYRO || type == MJB_SENS_ACCELEROMETER) {
+      // site velocity / acceleration in the site frame
+      double pos[3], quat[4], m[9], x[6], a[6];
+      const int body = sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      quat2Mat(m, quat);
+      sensor_point_motion(c, SC(cvel), body, pos, x);
+      if (type == MJB_SENS_ACCELEROMETER) {
+        double cr[3];
+        sensor_point_motion(c, SC(cacc), body, pos, a);
+        cross3(cr, x, x + 3);
+        for (int k = 0; k < 3; k++) a[3 + k] += cr[k];
+        mulMatTVec3(v, m, a + 3);
+      } else {
+        mulMatTVec3(v, m, type == MJB_SENS_GYRO ? x : x + 3);
+      }
+    } else if (type == MJB_SENS_FORCE || type == MJB_SENS_TORQUE) {
+      // cfrc_int of the site's body moved from C to the site and rotated into the site frame
+      double pos[3], quat[4], m[9], f[6], o[3], ms[4] = {0, 0, 0, 0};
+      const int body = sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      quat2Mat(m, quat);
+      const int r = rootid[body];
+      int e = r;
+      do {
+        double t[4];
+        ldn(t, SC(cinert), 10*e + 6, 4);
+        for (int k = 0; k < 4; k++) ms[k] += t[k];
+        e++;
+      } while (e < H.nbody && body_parentid[e] != 0);
+      ldn(o, SC(origin), 3*r, 3);
+      for (int k = 0; k < 6; k++) f[k] = c.out.cfrc_int[(size_t)(6*body + k)*N + c.s];
+      if (type == MJB_SENS_FORCE) {
+        mulMatTVec3(v, m, f + 3);
+      } else {
+        double dif[3], cr[3];
+        for (int k = 0; k < 3; k++) dif[k] = pos[k] - (o[k] + (ms[3] >= MJB_MINVAL ? ms[k]/ms[3] : 0.0));
+        cross3(cr, dif, f + 3);
+        for (int k = 0; k < 3; k++) f[k] -= cr[k];
+        mulMatTVec3(v, m, f);
+      }
+    } else if (type == MJB_SENS_FRAMELINVEL || type == MJB_SENS_FRAMEANGVEL) {
+      double pos[3], quat[4], x[6];
+      const int body = sensor_object(c, objtype, objid, pos, quat);
+      sensor_point_motion(c, SC(cvel), body, pos, x);
+      if (refid >= 0) {
+        // relative to a moving reference frame (engine_sensor.c:625-647)
+        double rpos[3], rquat[4], rmat[9], xr[6], rel[6], rvec[3], cr[3];
+        const int rbody = sensor_object(c, reftype, refid, rpos, rquat);
+        quat2Mat(rmat, rquat);
+        sensor_point_motion(c, SC(cvel), rbody, rpos, xr);
+        for (int k = 0; k < 6; k++) rel[k] = x[k] - xr[k];
+        for (int k = 0; k < 3; k++) rvec[k] = pos[k] - rpos[k];
+        cross3(cr, rvec, xr);
+        for (int k = 0; k < 3; k++) rel[3 + k] += cr[k];
+        mulMatTVec3(x, rmat, rel);
+        mulMatTVec3(x + 3, rmat, rel + 3);
+      }
+      for (int k = 0; k < 3; k++) v[k] = type == MJB_SENS_FRAMELINVEL ? x[3 + k] : x[k];
+    } else if (type == MJB_SENS_FRAMELINACC || type == MJB_SENS_FRAMEANGACC) {
+      double pos[3], quat[4], x[6], a[6], cr[3];
+      const int body = sensor_object(c, objtype, objid, pos, quat);
+      sensor_point_motion(c, SC(cvel), body, pos, x);
+      sensor_point_motion(c, SC(cacc), body, pos, a);
+      cross3(cr, x, x + 3);
+      for (int k = 0; k < 3; k++) v[k] = type == MJB_SENS_FRAMELINACC ? a[3 + k] + cr[k] : a[k];
+    }
+    // apply_cutoff (engine_sensor.c:40-68): real values on both sides, positive ones from above
+    const double cut = cutoff[i];
+    const int dt = si[MJB_SEN_DATATYPE];
+    for (int k = 0; k < si[MJB_SEN_DIM] && k < 4; k++) {
+      double x = v[k];
+      if (cut > 0) {
+        if (dt == MJB_DATATYPE_REAL) x = x < -cut ? -cut : (x > cut ? cut : x);
+        else if (dt == MJB_DATATYPE_POSITIVE) x = cut < x ? cut : x;
+      }
+      c.out.sensordata[(size_t)(si[MJB_SEN_ADR] + k)*N + c.s] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // mj_crb (engine_core_smooth.c:1353-1401) and mj_factorM / mj_factorI (:1470-1511) in one
 // leaves-to-root sweep.
 //
@@ -3248,6 +3449,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
     phase_contact(c, true, list, 1, 64);
   }
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
+  if (c.out.sensordata) sensors(c);
 }
 
 #undef MI

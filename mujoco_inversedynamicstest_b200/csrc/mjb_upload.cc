@@ -175,10 +175,10 @@ void contactParam(const mjModel* m, int g1, int g2, int* condim, mjtNum* gap, mj
   friction[4] = fri[2];
 }
 
-template <typename T>
-void setError(std::string& err, const char* fmt, T a) {
+template <typename... T>
+void setError(std::string& err, const char* fmt, T... a) {
   char buf[512];
-  std::snprintf(buf, sizeof(buf), fmt, a);
+  std::snprintf(buf, sizeof(buf), fmt, a...);
   err = buf;
 }
 
@@ -215,9 +215,52 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       for (int i = 0; i < m->nv; i++) discrete = discrete || m->dof_damping[i] > 0;
     }
   }
-  if (m->nsensor && !(dsbl & mjDSBL_SENSOR)) {
-    err = "sensors are not supported (nsensor > 0): set mjDSBL_SENSOR to run without sensordata";
-    return false;
+  // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
+  // whose inputs exist on this path are evaluated by the sensor kernel; the others (touch, rays,
+  // camera, geom distances, actuator quantities, limit sensors, subtree momenta, energies, clock,
+  // user / plugin) are refused unless mjDSBL_SENSOR is set.
+  const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
+  bool sensor_post = false;
+  std::vector<int> sensor_int;
+  std::vector<double> sensor_cutoff;
+  for (int i = 0; i < m->nsensor && sensors; i++) {
+    const int t = m->sensor_type[i], ot = m->sensor_objtype[i], rt = m->sensor_reftype[i];
+    const int rid = m->sensor_refid[i];
+    auto frame_obj = [](int o) { return o == mjOBJ_BODY || o == mjOBJ_XBODY || o == mjOBJ_GEOM || o == mjOBJ_SITE; };
+    bool ok = false;
+    switch (t) {
+      case mjSENS_JOINTPOS: case mjSENS_JOINTVEL: case mjSENS_BALLQUAT: case mjSENS_BALLANGVEL:
+      case mjSENS_SUBTREECOM:
+        ok = true; break;
+      case mjSENS_TENDONPOS: case mjSENS_TENDONVEL:
+        // fixed tendons only: a spatial tendon's length exists on the device only while it carries a force
+        ok = true;
+        {
+          const int tid = m->sensor_objid[i];
+          for (int j = 0; j < m->tendon_num[tid]; j++) ok = ok && m->wrap_type[m->tendon_adr[tid] + j] == mjWRAP_JOINT;
+        }
+        break;
+      case mjSENS_VELOCIMETER: case mjSENS_GYRO:
+        ok = true; break;
+      case mjSENS_ACCELEROMETER:
+        ok = true; sensor_post = true; break;
+      case mjSENS_FORCE: case mjSENS_TORQUE:
+        ok = m->site_bodyid[m->sensor_objid[i]] != 0; sensor_post = true; break;   // cfrc_int of the world body is a mixed-frame sum
+      case mjSENS_FRAMELINACC: case mjSENS_FRAMEANGACC:
+        ok = frame_obj(ot); sensor_post = true; break;
+      case mjSENS_FRAMEPOS: case mjSENS_FRAMEQUAT: case mjSENS_FRAMEXAXIS: case mjSENS_FRAMEYAXIS:
+      case mjSENS_FRAMEZAXIS: case mjSENS_FRAMELINVEL: case mjSENS_FRAMEANGVEL:
+        ok = frame_obj(ot) && (rid < 0 || frame_obj(rt)); break;
+      default: break;
+    }
+    if (!ok) {
+      setError(err, "sensor %d (mjtSensor %d) is not evaluated on the device: set mjDSBL_SENSOR or remove it", i, t);
+      return false;
+    }
+    const int rec[MJB_SEN_NI] = {t, m->sensor_datatype[i], ot, m->sensor_objid[i], rt, rid, m->sensor_dim[i],
+                                 m->sensor_adr[i]};
+    sensor_int.insert(sensor_int.end(), rec, rec + MJB_SEN_NI);
+    sensor_cutoff.push_back(m->sensor_cutoff[i]);
   }
   const bool equalities = constraints && !(dsbl & mjDSBL_EQUALITY) && m->nemax != 0;
   std::vector<char> tendon_in_equality(m->ntendon, 0);
@@ -594,6 +637,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.passive_wrench = (gravcomp || spatial_passive) ? 1 : 0;
   H.has_spatial = spatial_active ? 1 : 0;
   H.discrete_acc = discrete ? 1 : 0;
+  H.nsensor = sensors ? m->nsensor : 0;
+  H.nsensordata = sensors ? m->nsensordata : 0;
+  H.sensor_post = sensor_post ? 1 : 0;
+  H.nsite = m->nsite;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 
@@ -620,6 +667,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_mapM2C, mapM2C.data(), mapM2C.size());
   pushInts(MJB_I_cand_int, cand_int.data(), cand_int.size());
   pushInts(MJB_I_eq_int, eq_int.data(), eq_int.size());
+  pushInts(MJB_I_sensor_int, sensor_int.data(), sensor_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_tendon_active, tendon_active.data(), tendon_active.size());
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
@@ -702,6 +750,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_sp_eq, sp_eq.data(), sp_eq.size());
   pushNums(MJB_N_eq_num, eq_num.data(), eq_num.size());
   pushNums(MJB_N_cand_num, cand_num.data(), cand_num.size());
+  pushNums(MJB_N_sensor_cutoff, sensor_cutoff.data(), sensor_cutoff.size());
 
   // scratch layout
   {

@@ -229,7 +229,7 @@ class Model:
             "qfrc_bias": ("nv", 1), "qfrc_passive": ("nv", 1), "qfrc_constraint": ("nv", 1),
             "qfrc_spring": ("nv", 1), "qfrc_damper": ("nv", 1), "ten_length": ("ntendon", 1),
             "ten_velocity": ("ntendon", 1), "ten_J": ("ntendon", "nv"),
-            "cacc": ("nbody", 6), "cfrc_int": ("nbody", 6), "cfrc_ext": ("nbody", 6),
+            "sensordata": ("nsensordata", 1), "cacc": ("nbody", 6), "cfrc_int": ("nbody", 6), "cfrc_ext": ("nbody", 6),
         }
         if name in known:
             r, c = known[name]

@@ -49,6 +49,8 @@ CASES = {
     "boxes_elliptic": ("repo:tests/golden/models/boxes.xml", {"cone": 1}, 256, (0.0, 0.7), 64, 300),
     "tendons": ("repo:tests/golden/models/tendons.xml", {}, 512, (0.3, 1.3), 8, 32),
     "gravcomp": ("repo:tests/golden/models/gravcomp.xml", {}, 128, (0.5, 1.5), 8, 16),
+    # every sensor type evaluated on the device (mj_sensorPos / Vel / Acc); sensordata is dumped too
+    "sensors": ("repo:tests/golden/models/sensors.xml", {}, 256, (0.0, 0.6), 16, 96),
 }
 
 
@@ -74,6 +76,8 @@ def make_case(name):
               "efc_pos": njmax, "efc_D": njmax, "efc_aref": njmax,
               "qfrc_passive": None, "qfrc_constraint": None, "qM": None, "qLD": None,
               "qLDiagInv": None, "xpos": None, "cvel": None, "cdof": None}
+    if m.int("nsensordata") > 0:
+        fields["sensordata"] = None
     out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields)
     assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax, (
         name, out["ncon"].max(), out["nefc"].max())

@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata"]
 
 
 class Outputs(ctypes.Structure):
@@ -59,9 +59,12 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False):
              efc_num=np.zeros((njmax * 8, n)), qM=np.zeros((model.int("nM"), n)),
              qLD=np.zeros((model.int("nC"), n)), qLDiagInv=np.zeros((nv, n)),
              scratch_dump=np.zeros((nsc, n)))
-    if post:      # mj_rnePostConstraint outputs
+    has_sensors = model.int("nsensordata") > 0 and not (model.get_opt_int("disableflags") & (1 << 12))
+    if post or has_sensors:      # mj_rnePostConstraint outputs (mjb_makeData adds them for acceleration-stage sensors)
         nb = model.int("nbody")
         a.update(cacc=np.zeros((6 * nb, n)), cfrc_int=np.zeros((6 * nb, n)), cfrc_ext=np.zeros((6 * nb, n)))
+    if has_sensors:
+        a["sensordata"] = np.zeros((model.int("nsensordata"), n))
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL
     err = ctypes.create_string_buffer(1000)
     qp, qv, qa = (np.ascontiguousarray(x.T, dtype=np.float64) for x in (qpos, qvel, qacc))

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
-         "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons"]
+         "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
+         "sensors"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -117,6 +118,26 @@ def test_golden_rne_post_constraint(name):
     plain.set_state(qpos, qvel, qacc)
     plain.inverse()
     np.testing.assert_array_equal(bd.qfrc_inverse(), plain.qfrc_inverse())
+
+
+def test_golden_sensordata():
+    """sensordata of mj_inverse (mj_sensorPos / Vel / Acc) through the C-ABI, and mj_inverseSkip's
+    skipsensor."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, (qpos, qvel, qacc) = _run(mjb, "sensors", True, 0)
+    assert nbad == 0
+    got = bd.sensordata()
+    nviol, worst = util.sensor_violations(model, got, ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    # the sensors bring mj_rnePostConstraint's outputs with them
+    post = bd.rne_post_constraint()
+    assert np.isfinite(post["cfrc_int"]).all()
+    # skipsensor = 1 leaves sensordata as it is (engine_inverse.c:206-246)
+    bd.set_state(qpos[::-1].copy(), qvel[::-1].copy(), qacc[::-1].copy())
+    bd.inverse_skip(0, 1)
+    np.testing.assert_array_equal(bd.sensordata(), got)
+    bd.inverse_skip(0, 0)
+    np.testing.assert_array_equal(bd.sensordata(), got[::-1])
 
 
 def test_rne_post_constraint_newton_euler_balance():

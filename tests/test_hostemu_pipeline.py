@@ -19,7 +19,8 @@ pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation libr
 
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
-         "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons"]
+         "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
+         "sensors"]
 
 
 def _run(name):
@@ -97,6 +98,21 @@ def test_rne_post_constraint_outputs(name):
     assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
 
 
+def test_sensordata():
+    """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
+    every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml)."""
+    model, out, ref = _run("sensors")
+    nviol, worst = util.sensor_violations(model, out["sensordata"], ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    # position-stage sensors repeat the bit-identical kinematics of the CPU build
+    stage = model.array("sensor_needstage").ravel()
+    adr, dim = model.array("sensor_adr").ravel(), model.array("sensor_dim").ravel()
+    typ = model.array("sensor_type").ravel()
+    for a, d, s, t in zip(adr, dim, stage, typ):
+        if s == 1 and t != 34:      # subtreecom is a differently ordered mass-weighted sum
+            np.testing.assert_array_equal(out["sensordata"][:, a:a + d], ref["sensordata"][:, a:a + d])
+
+
 def test_candidate_list_contains_reference_contacts_in_order():
     """Every contact the reference reports (after its broadphase/midphase) appears in the static
     candidate list, in the same relative order (engine_collision_driver.c:265-484)."""
@@ -120,6 +136,14 @@ def test_upload_rejections():
     model.set_opt_int("disableflags", 0)
     with pytest.raises(RuntimeError, match="collision function"):
         emu.candidates(model)
+    # a sensor type that is not evaluated on the device is refused unless sensors are disabled
+    sm = mjb.Model.from_mjb(util.golden("sensors")[0])
+    assert len(emu.candidates(sm)) > 0
+    sm.array("sensor_type")[0] = 0              # mjSENS_TOUCH
+    with pytest.raises(RuntimeError, match="sensor 0"):
+        emu.candidates(sm)
+    sm.set_opt_int("disableflags", 1 << 12)     # mjDSBL_SENSOR
+    assert len(emu.candidates(sm)) > 0
     h = mjb.Model.from_mjb(util.golden("humanoid")[0])
     h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE: Euler only
     assert len(emu.candidates(h)) > 0

@@ -92,3 +92,21 @@ def spatial_violations(got, ref, rtol=RTOL, atol=ATOL):
     scale = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1)[:, None, None]
     tol = atol + rtol * np.maximum(np.abs(ref), 1e-3 * scale)
     return int((d > tol).sum()), float((d / tol).max()) if d.size else 0.0
+
+
+def sensor_violations(model, got, ref, rtol=RTOL, atol=ATOL):
+    """north_star bound on sensordata [n, nsensordata]: element-wise for position- and velocity-stage
+    sensors; for acceleration-stage sensors (accelerometer, force, torque, frame accelerations:
+    sums of contact / constraint forces) the relative part is taken against the largest
+    acceleration-stage reading of the STATE, as for qfrc_inverse."""
+    adr = model.array("sensor_adr").ravel()
+    dim = model.array("sensor_dim").ravel()
+    stage = model.array("sensor_needstage").ravel()
+    acc = np.zeros(ref.shape[1], dtype=bool)
+    for a, d, s in zip(adr, dim, stage):
+        acc[a:a + d] = s == 3
+    scale = np.abs(ref[:, acc]).max(axis=1, keepdims=True) if acc.any() else np.zeros((ref.shape[0], 1))
+    floor = np.where(acc[None, :], 1e-3 * scale, 0.0)
+    d = np.abs(got - ref)
+    tol = atol + rtol * np.maximum(np.abs(ref), floor)
+    return int((d > tol).sum()), float((d / tol).max()) if d.size else 0.0
