@@ -38,7 +38,7 @@ typedef struct mjbData_ mjbData;
 
 /* which optional per-state outputs mjb_inverse fills (qfrc_inverse is always produced) */
 typedef enum mjbOut_ {
-  mjbOUT_QFRC      = 1 << 0,  /* qfrc_constraint, qfrc_passive                    mjdata.h qfrc_*   */
+  mjbOUT_QFRC      = 1 << 0,  /* qfrc_constraint, qfrc_passive, qfrc_bias           mjdata.h qfrc_*   */
   mjbOUT_COUNTS    = 1 << 1,  /* ncon, ne, nf, nl, nefc                                               */
   mjbOUT_CONTACT   = 1 << 2,  /* contact[].geom, dim, exclude, efc_address, dist, pos, frame          */
   mjbOUT_EFC       = 1 << 3,  /* efc_type, efc_id, efc_state, efc_pos, margin, D, R, vel, aref, force */
@@ -79,6 +79,7 @@ typedef enum mjbField_ {
   mjbF_CFRC_INT,          /* double nbody*6: [torque, force] body <- parent, com frame (RNEPOST) */
   mjbF_CFRC_EXT,          /* double nbody*6: [torque, force] of contacts and connect/weld rows (RNEPOST) */
   mjbF_SENSORDATA,        /* double nsensordata: d->sensordata (models with sensors, no mask bit needed) */
+  mjbF_QFRC_BIAS,         /* double nv: mj_rne without accelerations, engine_forward.c:228 (QFRC) */
   mjbF_COUNT
 } mjbField;
 

@@ -22,7 +22,7 @@ STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTR
 
 (F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
  F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL,
- F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA) = range(18)
+ F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS) = range(19)
 
 _INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
 _CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}

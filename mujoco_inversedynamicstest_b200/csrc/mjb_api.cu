@@ -221,6 +221,8 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     ok = ok && devAlloc(d, &o.qfrc_passive, (size_t)H.nv * S, "cudaMalloc(qfrc_passive)");
     setField(d, mjbF_QFRC_CONSTRAINT, o.qfrc_constraint, H.nv, 0);
     setField(d, mjbF_QFRC_PASSIVE, o.qfrc_passive, H.nv, 0);
+    ok = ok && devAlloc(d, &o.qfrc_bias, (size_t)H.nv * S, "cudaMalloc(qfrc_bias)");
+    setField(d, mjbF_QFRC_BIAS, o.qfrc_bias, H.nv, 0);
   }
   if (outmask & mjbOUT_COUNTS) {
     ok = ok && devAlloc(d, &o.counts, 5 * S, "cudaMalloc(counts)");
@@ -307,6 +309,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
   cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
   cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext); cudaFree(o.sensordata);
+  cudaFree(o.qfrc_bias);
   delete d;
 }
 

@@ -81,6 +81,8 @@ struct Outputs {
   double* cfrc_ext;
   // sensordata [nsensordata][stride] (mj_sensorPos / Vel / Acc), null for models without sensors
   double* sensordata;
+  // qfrc_bias [nv][stride] = mj_rne(flg_acc = 0) (engine_forward.c:193-231), or null
+  double* qfrc_bias;
 };
 
 struct Ctx {
@@ -1358,7 +1360,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     stc(cvel, 6*b, V, 6);
     stc(cal, 6*b, AL, 6);
     // read back only by a child that is not b+1, or by the mj_rnePostConstraint outputs
-    if ((tree_flags[b] & 4) || c.out.cacc) stc(cacc, 6*b, A, 6);
+    if ((tree_flags[b] & 4) || c.out.cacc || c.out.qfrc_bias) stc(cacc, 6*b, A, 6);
 
     // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
     const int sf = body_sameframe[b];
@@ -2955,6 +2957,45 @@ MJB_HD inline void rne_and_output(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// qfrc_bias = mj_rne(m, d, 0, qfrc_bias) of mj_fwdVelocity (engine_forward.c:228,
+// engine_core_smooth.c:1969-2023): Coriolis, centrifugal and gravitational forces. The forward
+// sweep carries the full acceleration A = A_bias + sum cdof*qacc and the qacc part alone
+// (cacc_lin), so the bias acceleration is their difference and the body force
+// cinert*A_bias + cvel x* (cinert*cvel) is accumulated up the tree in a row block that is free
+// after the inertia kernel (ia) and projected on the dofs. Runs after the backward sweep.
+MJB_HD inline void bias_forces(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* body_parentid = MI(body_parentid);
+  const int* dof_bodyid = MI(dof_bodyid);
+  double* tmp = SC(ia);
+  for (int b = 1; b < H.nbody; b++) {
+    double ci[10], a[6], al[6], v[6], f[6], u1[6], u2[6];
+    ldn(ci, SC(cinert), 10*b, 10); ldn(a, SC(cacc), 6*b, 6); ldn(al, SC(cacc_lin), 6*b, 6);
+    ldn(v, SC(cvel), 6*b, 6);
+    for (int k = 0; k < 6; k++) a[k] -= al[k];
+    mulInertVec(f, ci, a);
+    mulInertVec(u1, ci, v);
+    crossForce(u2, v, u1);
+    for (int k = 0; k < 6; k++) f[k] += u2[k];
+    stn(tmp, 6*b, f, 6);
+  }
+  for (int b = H.nbody - 1; b > 0; b--) {
+    const int p = body_parentid[b];
+    if (!p) continue;
+    double f[6], pf[6];
+    ldn(f, tmp, 6*b, 6); ldn(pf, tmp, 6*p, 6);
+    for (int k = 0; k < 6; k++) pf[k] += f[k];
+    stn(tmp, 6*p, pf, 6);
+  }
+  for (int i = 0; i < H.nv; i++) {
+    double cd[6], f[6];
+    ldn(cd, SC(cdof), 6*i, 6); ldn(f, tmp, 6*dof_bodyid[i], 6);
+    c.out.qfrc_bias[(size_t)i*N + c.s] = dot6(cd, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Sensors: mj_sensorPos, mj_sensorVel, mj_sensorAcc (engine_sensor.c:222-520, 527-704, 708-913) for
 // the sensor types whose inputs exist on this path (the others are refused at upload). Runs after
 // the backward sweep: body poses and cvel / cacc come from the scratch (about the tree origin O,
@@ -3449,6 +3490,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
     phase_contact(c, true, list, 1, 64);
   }
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
+  if (c.out.qfrc_bias) bias_forces(c);
   if (c.out.sensordata) sensors(c);
 }
 

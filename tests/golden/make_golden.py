@@ -111,12 +111,14 @@ def make_fd_case(name):
 
 
 # mj_rnePostConstraint after mj_inverse (engine_core_smooth.c:2027-2181; what mj_sensorAcc runs for
-# accelerometer / force / torque sensors): cacc, cfrc_int, cfrc_ext on the first states of a case's
-# stream: name -> (case whose model / state stream is used, nstate)
+# accelerometer / force / torque sensors): cacc, cfrc_int, cfrc_ext -- and qfrc_bias of mj_fwdVelocity
+# (engine_forward.c:228) -- on the first states of a case's stream: name -> (case whose model / state stream is used, nstate)
 POST_CASES = {"humanoid_post": ("humanoid", 128), "humanoid_elliptic_post": ("humanoid_elliptic", 64),
               "humanoids22_post": ("humanoids22", 4), "weld_post": ("weld", 64),
               "connect_post": ("connect", 64), "zoo_post": ("zoo", 128), "capsbox_post": ("capsbox", 64),
-              "boxes_post": ("boxes", 64), "gravcomp_post": ("gravcomp", 32)}
+              "boxes_post": ("boxes", 64), "gravcomp_post": ("gravcomp", 32),
+              "humanoid_nocontact_post": ("humanoid_nocontact", 64), "tendons_post": ("tendons", 32),
+              "arm26_post": ("arm26", 32)}
 
 
 def make_post_case(name):
@@ -127,7 +129,8 @@ def make_post_case(name):
     for k, v in opts.items():
         m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
     qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
-    out, _ = m.inverse_batch(qpos, qvel, qacc, fields={"cacc": None, "cfrc_int": None, "cfrc_ext": None})
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields={"cacc": None, "cfrc_int": None, "cfrc_ext": None,
+                                                          "qfrc_bias": None})
     np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
                         z_range=np.array(zr), **out)
     print(f"{name}: nbody={m.int('nbody')} states={nstate} max|cfrc_ext|={np.abs(out['cfrc_ext']).max():.3g}")

@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias"]
 
 
 class Outputs(ctypes.Structure):
@@ -58,7 +58,7 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False):
              contact_num=np.zeros((nconmax * 13, n)), efc_int=np.zeros((njmax * 3, n), np.int32),
              efc_num=np.zeros((njmax * 8, n)), qM=np.zeros((model.int("nM"), n)),
              qLD=np.zeros((model.int("nC"), n)), qLDiagInv=np.zeros((nv, n)),
-             scratch_dump=np.zeros((nsc, n)))
+             scratch_dump=np.zeros((nsc, n)), qfrc_bias=np.zeros((nv, n)))
     has_sensors = model.int("nsensordata") > 0 and not (model.get_opt_int("disableflags") & (1 << 12))
     if post or has_sensors:      # mj_rnePostConstraint outputs (mjb_makeData adds them for acceleration-stage sensors)
         nb = model.int("nbody")

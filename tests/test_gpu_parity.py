@@ -120,6 +120,26 @@ def test_golden_rne_post_constraint(name):
     np.testing.assert_array_equal(bd.qfrc_inverse(), plain.qfrc_inverse())
 
 
+@pytest.mark.parametrize("name", util.BIAS_CASES)
+def test_golden_qfrc_bias(name):
+    """mjbF_QFRC_BIAS (mjbOUT_QFRC): mj_rne without accelerations, engine_forward.c:228."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.post_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_QFRC)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    nviol, worst = util.qfrc_violations(bd.get(mjb.F_QFRC_BIAS), ref["qfrc_bias"].reshape(n, -1))
+    assert nviol == 0, (nviol, worst)
+    # bias forces do not depend on the accelerations
+    bd.set_state(qpos, qvel, -2.0 * qacc)
+    bd.inverse()
+    nviol, worst = util.qfrc_violations(bd.get(mjb.F_QFRC_BIAS), ref["qfrc_bias"].reshape(n, -1))
+    assert nviol == 0, (nviol, worst)
+
+
 def test_golden_sensordata():
     """sensordata of mj_inverse (mj_sensorPos / Vel / Acc) through the C-ABI, and mj_inverseSkip's
     skipsensor."""

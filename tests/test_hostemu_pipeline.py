@@ -98,6 +98,20 @@ def test_rne_post_constraint_outputs(name):
     assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
 
 
+@pytest.mark.parametrize("name", util.BIAS_CASES)
+def test_qfrc_bias(name):
+    """qfrc_bias = mj_rne without accelerations (mj_fwdVelocity, engine_forward.c:228), strict
+    element-wise 1e-9 rel / 1e-12 abs against the reference."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.post_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200)
+    nviol, worst = util.qfrc_violations(out["qfrc_bias"], ref["qfrc_bias"].reshape(n, -1))
+    assert nviol == 0, (nviol, worst)
+
+
 def test_sensordata():
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
     every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml)."""

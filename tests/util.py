@@ -74,13 +74,15 @@ def to_com_frame(model, xpos, xquat, origin, vec, per):
 
 POST_CASES = ["humanoid_post", "humanoid_elliptic_post", "humanoids22_post", "weld_post", "connect_post",
               "zoo_post", "capsbox_post", "boxes_post", "gravcomp_post"]
+# fixtures used for qfrc_bias only (force-carrying spatial tendons: mjbOUT_RNEPOST is refused there)
+BIAS_CASES = POST_CASES + ["humanoid_nocontact_post", "tendons_post", "arm26_post"]
 
 
 def post_fixture(name):
     """(path of the base case's MJB, dict with cacc / cfrc_int / cfrc_ext [n, nbody, 6] of the
     reference's mj_rnePostConstraint, nstate, z_range) of a tests/golden/*_post.npz fixture."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in ("cacc", "cfrc_int", "cfrc_ext")},
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in ("cacc", "cfrc_int", "cfrc_ext", "qfrc_bias")},
             int(z["nstate"]), tuple(z["z_range"]))
 
 
