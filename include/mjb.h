@@ -126,6 +126,19 @@ MJB_API int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipst
  * generated and differenced on the device. Synchronous. */
 MJB_API int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq,
                           mjtNum* DfDv, mjtNum* DfDa, mjtNum* DmDq);
+/* mj_compareFwdInv over the batch (include/mujoco/mujoco.h mj_compareFwdInv, src/engine/
+ * engine_inverse.c:275-316): how well the inverse dynamics reproduce what a forward pass applied.
+ * The states last given to mjb_setState / mjb_setStateDevice carry the forward pass's qacc. HOST
+ * arrays, one row per state: qfrc_applied, qfrc_actuator nbatch x nv (either may be NULL = zero),
+ * xfrc_applied nbatch x nbody x 6 (force then torque per body, mjData layout; may be NULL; projected
+ * with J' on the device like mj_xfrcAccumulate, engine_support.c:1247-1260), qfrc_constraint
+ * nbatch x nv of the forward pass. Output fwdinv nbatch x 2 = d->solver_fwdinv:
+ *   [0] |qfrc_constraint(forward) - qfrc_constraint(inverse)|,
+ *   [1] |qfrc_applied + qfrc_actuator + J'xfrc_applied - qfrc_inverse|  (both 0 for states without
+ * constraint rows, as in the reference). Synchronous; returns 0 or a negative value on error. */
+MJB_API int mjb_compareFwdInv(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qfrc_applied,
+                              const mjtNum* qfrc_actuator, const mjtNum* xfrc_applied,
+                              const mjtNum* qfrc_constraint, mjtNum* fwdinv);
 /* same, without reading back the status count (fully asynchronous) */
 MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 

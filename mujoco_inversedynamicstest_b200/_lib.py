@@ -24,6 +24,7 @@ SIGNATURES = {
     "mjb_inverse": (c_int, [c_void_p, c_void_p, c_int]),
     "mjb_inverseAsync": (c_int, [c_void_p, c_void_p, c_int]),
     "mjb_inverseFD": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mjb_compareFwdInv": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mjb_inverseSkip": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
     "mjb_inverseHost": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mjb_get": (c_int, [c_void_p, c_int, c_void_p]),

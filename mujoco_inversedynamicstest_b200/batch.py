@@ -182,6 +182,19 @@ class BatchData:
                                         dm.ctypes.data if mass else None), "mjb_inverseFD")
         return (dq, dv, da, dm) if mass else (dq, dv, da)
 
+    def compare_fwdinv(self, qfrc_constraint, qfrc_applied=None, qfrc_actuator=None, xfrc_applied=None,
+                       nbatch=None):
+        """mj_compareFwdInv over the batch: [nbatch, 2] = solver_fwdinv of every state
+        (engine_inverse.c:275-316). The states set last carry the forward pass's qacc."""
+        n = self.nbatch if nbatch is None else int(nbatch)
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+                for a in (qfrc_applied, qfrc_actuator, xfrc_applied, qfrc_constraint)]
+        out = np.zeros((n, 2))
+        ptr = [None if a is None else ctypes.c_void_p(a.ctypes.data) for a in arrs]
+        self._check(lib().mjb_compareFwdInv(self.model.ptr, self._d, n, *ptr, ctypes.c_void_p(out.ctypes.data)),
+                    "mjb_compareFwdInv")
+        return out
+
     def inverse_skip(self, skipstage=0, skipsensor=1, nbatch=None):
         """mj_inverseSkip over the batch (mjb_inverseSkip)."""
         n = self.nbatch if nbatch is None else int(nbatch)

@@ -65,6 +65,9 @@ struct mjbData_ {
   // mjb_inverseFD: inner batch of perturbed states and the device buffer of the differences
   mjbData* fd = nullptr;
   int fd_tile = 0;
+  // mjb_compareFwdInv: forward-pass quantities (SoA) and the result, allocated on first use
+  double *d_fwd_qforce = nullptr, *d_fwd_xfrc = nullptr, *d_fwd_qc = nullptr, *d_fwdinv = nullptr;
+  bool own_qfrc_constraint = false;
   int skip_sensors = 0;        // mj_inverseSkip(skipsensor = 1) / inner batches of mjb_inverseFD
   double* d_fd_out = nullptr;
   size_t fd_out_doubles = 0;
@@ -293,6 +296,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_slot_rec);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
+  cudaFree(d->d_fwd_qforce); cudaFree(d->d_fwd_xfrc); cudaFree(d->d_fwd_qc); cudaFree(d->d_fwdinv);
   for (int b = 0; b < 2; b++) {
     cudaFree(d->pipe_in[b]); cudaFree(d->pipe_out[b]);
     if (d->ev_in[b]) cudaEventDestroy(d->ev_in[b]);
@@ -568,6 +572,64 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
       ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_inverseFD");   // d_fd_out is reused
     }
   }
+  return ok ? 0 : -1;
+}
+
+// mj_compareFwdInv over the batch (include/mujoco/mujoco.h mj_compareFwdInv, engine_inverse.c:275-316).
+// The caller ran the forward dynamics; the states given to mjb_setState carry its qacc. Host arrays,
+// row-major per state: qfrc_applied, qfrc_actuator nbatch x nv (either may be NULL = zero),
+// xfrc_applied nbatch x nbody x 6 (force, torque; may be NULL), qfrc_constraint nbatch x nv of the
+// forward pass; fwdinv out nbatch x 2. Sensors are not re-evaluated (skipsensor = 1 in the reference).
+int mjb_compareFwdInv(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qfrc_applied,
+                      const mjtNum* qfrc_actuator, const mjtNum* xfrc_applied,
+                      const mjtNum* qfrc_constraint, mjtNum* fwdinv) {
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_compareFwdInv: nbatch out of range"; return -1; }
+  if (!qfrc_constraint || !fwdinv) { d->error = "mjb_compareFwdInv: qfrc_constraint and fwdinv are required"; return -1; }
+  if (nbatch == 0) return 0;
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const mjbHdr& H = d->hdr;
+  const size_t S = (size_t)d->stride, n = (size_t)nbatch, nv = (size_t)H.nv, nb6 = 6 * (size_t)H.nbody;
+  mjb::Outputs& o = d->out;
+  bool ok = true;
+  if (!d->d_fwd_qforce) {
+    ok = ok && devAlloc(d, &d->d_fwd_qforce, nv * S, "cudaMalloc(fwd qforce)");
+    ok = ok && devAlloc(d, &d->d_fwd_xfrc, nb6 * S, "cudaMalloc(fwd xfrc)");
+    ok = ok && devAlloc(d, &d->d_fwd_qc, nv * S, "cudaMalloc(fwd qfrc_constraint)");
+    ok = ok && devAlloc(d, &d->d_fwdinv, 2 * S, "cudaMalloc(fwdinv)");
+  }
+  if (ok && !o.qfrc_constraint) {
+    ok = devAlloc(d, &o.qfrc_constraint, nv * S, "cudaMalloc(qfrc_constraint)");
+    d->own_qfrc_constraint = true;
+  }
+  if (!ok) return -1;
+  // qforce = qfrc_applied + qfrc_actuator on the host (a validation utility, not a hot path)
+  std::vector<double> qforce(n * nv, 0.0);
+  for (size_t k = 0; k < n * nv; k++) {
+    qforce[k] = (qfrc_applied ? qfrc_applied[k] : 0.0) + (qfrc_actuator ? qfrc_actuator[k] : 0.0);
+  }
+  const size_t bmax = n * (nb6 > nv ? nb6 : nv) * sizeof(double);
+  if (!ensureStage(d, bmax)) return -1;
+  struct Up { const double* host; double* dev; size_t rows; };
+  const Up ups[3] = {{qforce.data(), d->d_fwd_qforce, nv}, {qfrc_constraint, d->d_fwd_qc, nv},
+                     {xfrc_applied, d->d_fwd_xfrc, nb6}};
+  for (const Up& u : ups) {
+    if (!u.host) continue;
+    ok = ok && check(d, cudaMemcpyAsync(d->d_stage, u.host, n * u.rows * sizeof(double), cudaMemcpyHostToDevice, d->stream), "H2D fwd");
+    ok = ok && check(d, mjb::launch_aos_to_soa((const double*)d->d_stage, u.dev, nbatch, (int)u.rows, d->stride, d->stream), "transpose fwd");
+    ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_compareFwdInv");   // the staging buffer is reused
+  }
+  if (!ok) return -1;
+  o.fwd_qforce = d->d_fwd_qforce; o.fwd_qfrc_constraint = d->d_fwd_qc;
+  o.fwd_xfrc = xfrc_applied ? d->d_fwd_xfrc : nullptr;
+  o.fwdinv = d->d_fwdinv;
+  d->skip_sensors = 1;
+  const int r = mjb_inverseAsync(m, d, nbatch);
+  d->skip_sensors = 0;
+  o.fwd_qforce = nullptr; o.fwd_qfrc_constraint = nullptr; o.fwd_xfrc = nullptr; o.fwdinv = nullptr;
+  if (r) return -1;
+  ok = ok && check(d, mjb::launch_soa_to_aos(d->d_fwdinv, (double*)d->d_stage, nbatch, 2, d->stride, d->stream), "transpose fwdinv");
+  ok = ok && check(d, cudaMemcpyAsync(fwdinv, d->d_stage, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, d->stream), "D2H fwdinv");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_compareFwdInv");
   return ok ? 0 : -1;
 }
 

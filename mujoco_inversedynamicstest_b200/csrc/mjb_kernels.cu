@@ -739,6 +739,20 @@ __global__ void __launch_bounds__(kThreads, 4) bias_kernel(LaunchArgs a) {
   }
 }
 
+// mj_compareFwdInv over the chunk (only from mjb_compareFwdInv)
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) fwdinv_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    compare_fwdinv(c);
+  }
+}
+
 // sensordata of the chunk (mj_sensorPos / Vel / Acc); launched only for models with sensors, after
 // the backward kernel has left cacc / cfrc_int in the outputs
 template <bool kModelInSmem>
@@ -912,6 +926,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   if (args.out.qfrc_bias) {
     e = in_smem ? launch_phase(bias_kernel<true>, args, smem, 8, stream)
                 : launch_phase(bias_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  if (args.out.fwdinv) {
+    e = in_smem ? launch_phase(fwdinv_kernel<true>, args, smem, 8, stream)
+                : launch_phase(fwdinv_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }

@@ -83,6 +83,12 @@ struct Outputs {
   double* sensordata;
   // qfrc_bias [nv][stride] = mj_rne(flg_acc = 0) (engine_forward.c:193-231), or null
   double* qfrc_bias;
+  // mj_compareFwdInv (engine_inverse.c:275-316): quantities of the forward pass to compare with
+  // (inputs) and the two norms (output); all null outside mjb_compareFwdInv
+  const double* fwd_qforce;           // [nv][stride]      qfrc_applied + qfrc_actuator
+  const double* fwd_xfrc;             // [nbody*6][stride] xfrc_applied: force, torque per body; or null
+  const double* fwd_qfrc_constraint;  // [nv][stride]
+  double* fwdinv;                     // [2][stride]
 };
 
 struct Ctx {
@@ -1278,7 +1284,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     quat2Mat(mat, quat);
     // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
     // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
-    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata) {
+    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc) {
       stc(xquat, 4*b, quat, 4);
       stc(xpos, 3*b, pos, 3);
     }
@@ -3195,6 +3201,62 @@ MJB_HD inline void sensors(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// mj_compareFwdInv (engine_inverse.c:275-316) for one state, after the backward sweep:
+//   fwdinv[0] = | qfrc_constraint(forward) - qfrc_constraint(inverse) |
+//   fwdinv[1] = | qfrc_applied + qfrc_actuator + J'*xfrc_applied - qfrc_inverse |
+// J'*xfrc_applied (mj_xfrcAccumulate / mj_applyFT at xipos, engine_support.c:1194-1260) is formed
+// like every other J'f on this path: the wrench about the tree origin is summed up the tree (in
+// the ia rows, free by now) and projected with cdof.
+MJB_HD inline void compare_fwdinv(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* body_parentid = MI(body_parentid);
+  const int* dof_bodyid = MI(dof_bodyid);
+  const int* rootid = MI(body_rootid);
+  double* tmp = SC(ia);
+  const bool xf = c.out.fwd_xfrc != nullptr;
+  if (xf) {
+    for (int b = 1; b < H.nbody; b++) {
+      double F[3], T[3], p[3], q[4], o[3], r[3], w[6];
+      for (int k = 0; k < 3; k++) {
+        F[k] = c.out.fwd_xfrc[(size_t)(6*b + k)*N + c.s];
+        T[k] = c.out.fwd_xfrc[(size_t)(6*b + 3 + k)*N + c.s];
+      }
+      sensor_object(c, MJB_OBJ_BODY, b, p, q);
+      ldn(o, SC(origin), 3*rootid[b], 3);
+      r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
+      cross3(w, r, F);
+      for (int k = 0; k < 3; k++) { w[k] += T[k]; w[3 + k] = F[k]; }
+      stn(tmp, 6*b, w, 6);
+    }
+    for (int b = H.nbody - 1; b > 0; b--) {
+      const int p = body_parentid[b];
+      if (!p) continue;
+      double f[6], pf[6];
+      ldn(f, tmp, 6*b, 6); ldn(pf, tmp, 6*p, 6);
+      for (int k = 0; k < 6; k++) pf[k] += f[k];
+      stn(tmp, 6*p, pf, 6);
+    }
+  }
+  double s0 = 0, s1 = 0;
+  for (int i = 0; i < H.nv; i++) {
+    double qf = c.out.fwd_qforce[(size_t)i*N + c.s];
+    if (xf) {
+      double cd[6], f[6];
+      ldn(cd, SC(cdof), 6*i, 6); ldn(f, tmp, 6*dof_bodyid[i], 6);
+      qf += dot6(cd, f);
+    }
+    const double d1 = qf - c.out.qfrc_inverse[(size_t)i*N + c.s];
+    const double d0 = c.out.fwd_qfrc_constraint[(size_t)i*N + c.s] - c.out.qfrc_constraint[(size_t)i*N + c.s];
+    s0 += d0*d0; s1 += d1*d1;
+  }
+  // no constraint rows: the reference returns zeros without running the inverse (:283-286)
+  const bool none = c.isc[MJB_ISC_NEFC * MJB_LS] == 0;
+  c.out.fwdinv[c.s] = none ? 0.0 : sqrt(s0);
+  c.out.fwdinv[N + c.s] = none ? 0.0 : sqrt(s1);
+}
+
+// ------------------------------------------------------------------------------------------
 // mj_crb (engine_core_smooth.c:1353-1401) and mj_factorM / mj_factorI (:1470-1511) in one
 // leaves-to-root sweep.
 //
@@ -3492,6 +3554,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
   if (c.out.qfrc_bias) bias_forces(c);
   if (c.out.sensordata) sensors(c);
+  if (c.out.fwdinv) compare_fwdinv(c);
 }
 
 #undef MI

@@ -325,6 +325,36 @@ REFH_API void refh_compare_fwdinv(const mjModel* m, const double* qpos, const do
   mj_deleteData(d);
 }
 
+/* mj_forward + mj_compareFwdInv over a batch (engine_inverse.c:275-316): for every state the
+ * forward dynamics run on (qpos, qvel, ctrl, qfrc_applied, xfrc_applied); d->qacc is then shifted by
+ * dqacc (NULL: left as solved, so that the comparison is also exercised away from the solution),
+ * and the quantities mjb_compareFwdInv takes as inputs plus the reference's solver_fwdinv are
+ * returned. Arrays are row-major per state; ctrl / qfrc_applied / xfrc_applied / dqacc may be NULL. */
+REFH_API void refh_fwdinv_batch(const mjModel* m, long long nbatch, const double* qpos,
+                                const double* qvel, const double* ctrl, const double* qfrc_applied,
+                                const double* xfrc_applied, const double* dqacc, double* qacc,
+                                double* qfrc_actuator, double* qfrc_constraint, double* fwdinv) {
+  mjData* d = mj_makeData(m);
+  const size_t nv = (size_t)m->nv;
+  for (long long i = 0; i < nbatch; i++) {
+    mju_copy(d->qpos, qpos + i*m->nq, m->nq);
+    mju_copy(d->qvel, qvel + i*m->nv, m->nv);
+    if (ctrl) mju_copy(d->ctrl, ctrl + i*m->nu, m->nu);
+    if (qfrc_applied) mju_copy(d->qfrc_applied, qfrc_applied + i*nv, m->nv);
+    if (xfrc_applied) mju_copy(d->xfrc_applied, xfrc_applied + i*6*m->nbody, 6*m->nbody);
+    mju_zero(d->qacc_warmstart, m->nv);
+    mj_forward(m, d);
+    if (dqacc) mju_addTo(d->qacc, dqacc + i*nv, m->nv);
+    mju_copy(qacc + i*nv, d->qacc, m->nv);
+    mju_copy(qfrc_actuator + i*nv, d->qfrc_actuator, m->nv);
+    mju_copy(qfrc_constraint + i*nv, d->qfrc_constraint, m->nv);
+    mj_compareFwdInv(m, d);
+    fwdinv[2*i] = d->solver_fwdinv[0];
+    fwdinv[2*i + 1] = d->solver_fwdinv[1];
+  }
+  mj_deleteData(d);
+}
+
 /* the reference's mjd_inverseFD (src/engine/engine_derivative_fd.c:611) looped over a batch, no
  * actuation, no sensors: DfDq / DfDv / DfDa are nbatch x nv x nv (row i = derivative with respect
  * to coordinate i), DmDq nbatch x nv x nM (may be NULL). */

@@ -175,6 +175,22 @@ class Model:
                                 dm.ctypes.data if mass else None)
         return (dq, dv, da, dm) if mass else (dq, dv, da)
 
+    def fwdinv_batch(self, qpos, qvel, ctrl=None, qfrc_applied=None, xfrc_applied=None, dqacc=None):
+        """mj_forward + mj_compareFwdInv per state: dict(qacc, qfrc_actuator, qfrc_constraint [n, nv],
+        fwdinv [n, 2]); dqacc shifts qacc away from the forward solution before the comparison."""
+        L = lib()
+        L.refh_fwdinv_batch.restype = None
+        L.refh_fwdinv_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 10
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        qpos, qvel, ctrl, qfrc_applied, xfrc_applied, dqacc = map(c, (qpos, qvel, ctrl, qfrc_applied, xfrc_applied, dqacc))
+        n, nv = qpos.shape[0], self.int("nv")
+        out = {"qacc": np.zeros((n, nv)), "qfrc_actuator": np.zeros((n, nv)),
+               "qfrc_constraint": np.zeros((n, nv)), "fwdinv": np.zeros((n, 2))}
+        p = lambda a: None if a is None else a.ctypes.data
+        L.refh_fwdinv_batch(self.ptr, n, p(qpos), p(qvel), p(ctrl), p(qfrc_applied), p(xfrc_applied), p(dqacc),
+                            p(out["qacc"]), p(out["qfrc_actuator"]), p(out["qfrc_constraint"]), p(out["fwdinv"]))
+        return out
+
     def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1):
         """Loop the reference's mj_inverse over the batch.
 

@@ -136,6 +136,36 @@ def make_post_case(name):
     print(f"{name}: nbody={m.int('nbody')} states={nstate} max|cfrc_ext|={np.abs(out['cfrc_ext']).max():.3g}")
 
 
+# mj_forward + mj_compareFwdInv (engine_inverse.c:275-316) on the first states of a case's stream,
+# with random ctrl, qfrc_applied and xfrc_applied; for every second state qacc is moved away from
+# the forward solution so that the two norms are also compared where they are large
+FWDINV_CASES = {"humanoid_fwdinv": ("humanoid", 48), "zoo_fwdinv": ("zoo", 48), "weld_fwdinv": ("weld", 32),
+                "humanoid_nocontact_fwdinv": ("humanoid_nocontact", 16)}
+
+
+def make_fwdinv_case(name):
+    base, nstate = FWDINV_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    rng = np.random.RandomState(20250331)
+    nv, nu, nb = m.int("nv"), m.int("nu"), m.int("nbody")
+    ctrl = rng.uniform(-1, 1, (nstate, nu)) if nu else None
+    qfrc_applied = rng.normal(0, 1, (nstate, nv))
+    xfrc = rng.normal(0, 5, (nstate, nb, 6)) * (rng.uniform(0, 1, (nstate, nb, 1)) < 0.5)
+    xfrc[:, 0] = 0
+    dqacc = 0.1 * qacc * (np.arange(nstate) % 2)[:, None]
+    out = m.fwdinv_batch(qpos, qvel, ctrl, qfrc_applied, xfrc, dqacc)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), qfrc_applied=qfrc_applied, xfrc_applied=xfrc, **out)
+    print(f"{name}: states={nstate} fwdinv at the solution max {out['fwdinv'][0::2].max(axis=0)}, "
+          f"away from it max {out['fwdinv'][1::2].max(axis=0)}")
+
+
 if __name__ == "__main__":
-    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES)):
-        (make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else make_case)(case)
+    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES)):
+        (make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+         make_fwdinv_case if case in FWDINV_CASES else make_case)(case)

@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv"]
 
 
 class Outputs(ctypes.Structure):
@@ -40,7 +40,7 @@ def available():
     return os.path.exists(build_hostemu.LIB) or build_hostemu.include_dir() is not None
 
 
-def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False):
+def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -63,6 +63,12 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False):
     if post or has_sensors:      # mj_rnePostConstraint outputs (mjb_makeData adds them for acceleration-stage sensors)
         nb = model.int("nbody")
         a.update(cacc=np.zeros((6 * nb, n)), cfrc_int=np.zeros((6 * nb, n)), cfrc_ext=np.zeros((6 * nb, n)))
+    if fwd is not None:     # mj_compareFwdInv inputs: dict(qforce, qfrc_constraint[, xfrc]) per state
+        a["fwd_qforce"] = np.ascontiguousarray(fwd["qforce"].T, dtype=np.float64)
+        a["fwd_qfrc_constraint"] = np.ascontiguousarray(fwd["qfrc_constraint"].T, dtype=np.float64)
+        if fwd.get("xfrc") is not None:
+            a["fwd_xfrc"] = np.ascontiguousarray(fwd["xfrc"].reshape(n, -1).T, dtype=np.float64)
+        a["fwdinv"] = np.zeros((2, n))
     if has_sensors:
         a["sensordata"] = np.zeros((model.int("nsensordata"), n))
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL

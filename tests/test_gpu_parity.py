@@ -140,6 +140,29 @@ def test_golden_qfrc_bias(name):
     assert nviol == 0, (nviol, worst)
 
 
+@pytest.mark.parametrize("name", util.FWDINV_CASES)
+def test_golden_compare_fwdinv(name):
+    """mjb_compareFwdInv against the reference's mj_forward + mj_compareFwdInv."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, z = util.fwdinv_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    n = int(z["nstate"])
+    qpos, qvel, _ = generate_states(model, n, z_range=tuple(z["z_range"]))
+    bd = mjb.BatchData(model, n)
+    bd.set_state(qpos, qvel, z["qacc"])
+    got = bd.compare_fwdinv(z["qfrc_constraint"], qfrc_applied=z["qfrc_applied"],
+                            qfrc_actuator=z["qfrc_actuator"], xfrc_applied=z["xfrc_applied"])
+    nviol, worst = util.fwdinv_violations(got, z)
+    assert nviol == 0, (nviol, worst)
+    # the check leaves the plain path as it was
+    plain = mjb.BatchData(model, n)
+    plain.set_state(qpos, qvel, z["qacc"])
+    plain.inverse()
+    bd.inverse()
+    np.testing.assert_array_equal(bd.qfrc_inverse(), plain.qfrc_inverse())
+
+
 def test_golden_sensordata():
     """sensordata of mj_inverse (mj_sensorPos / Vel / Acc) through the C-ABI, and mj_inverseSkip's
     skipsensor."""

@@ -112,6 +112,24 @@ def test_qfrc_bias(name):
     assert nviol == 0, (nviol, worst)
 
 
+@pytest.mark.parametrize("name", util.FWDINV_CASES)
+def test_compare_fwdinv(name):
+    """solver_fwdinv of the reference's mj_forward + mj_compareFwdInv (engine_inverse.c:275-316), at
+    the forward solution and away from it, with ctrl, qfrc_applied and xfrc_applied in play."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, z = util.fwdinv_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    n = int(z["nstate"])
+    qpos, qvel, _ = generate_states(model, n, z_range=tuple(z["z_range"]))
+    fwd = {"qforce": z["qfrc_applied"] + z["qfrc_actuator"], "qfrc_constraint": z["qfrc_constraint"],
+           "xfrc": z["xfrc_applied"]}
+    out = emu.run(model, qpos, qvel, z["qacc"], nconmax=64, njmax=300, fwd=fwd)
+    nviol, worst = util.fwdinv_violations(out["fwdinv"], z)
+    assert nviol == 0, (nviol, worst)
+    assert z["fwdinv"][1::2].min() > 0.5          # the perturbed half is a non-trivial comparison
+
+
 def test_sensordata():
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
     every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml)."""

@@ -112,3 +112,21 @@ def sensor_violations(model, got, ref, rtol=RTOL, atol=ATOL):
     d = np.abs(got - ref)
     tol = atol + rtol * np.maximum(np.abs(ref), floor)
     return int((d > tol).sum()), float((d / tol).max()) if d.size else 0.0
+
+
+FWDINV_CASES = ["humanoid_fwdinv", "zoo_fwdinv", "weld_fwdinv", "humanoid_nocontact_fwdinv"]
+
+
+def fwdinv_fixture(name):
+    """(path of the base MJB, npz dict) of a mj_forward + mj_compareFwdInv fixture."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in z.files}
+
+
+def fwdinv_violations(got, z, rtol=RTOL, atol=ATOL):
+    """The two norms of mj_compareFwdInv are differences of force vectors of size F (the forward
+    pass's constraint forces): bound = atol + rtol * max(|ref|, F) per state."""
+    scale = np.maximum(np.abs(z["qfrc_constraint"]).max(axis=1, keepdims=True), 1.0)
+    tol = atol + rtol * np.maximum(np.abs(z["fwdinv"]), scale)
+    d = np.abs(got - z["fwdinv"])
+    return int((d > tol).sum()), float((d / tol).max())
