@@ -103,6 +103,11 @@ MJB_API void mjb_setStream(mjbData* d, void* cuda_stream);
 /* copy nbatch states from HOST arrays (nbatch x nq, nbatch x nv, nbatch x nv) to the device */
 MJB_API int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
                          const mjtNum* qacc);
+/* per-state poses of the mocap bodies, d->mocap_pos / d->mocap_quat (include/mujoco/mjdata.h; read by
+ * mj_kinematics, src/engine/engine_core_smooth.c:70-86): HOST arrays nbatch x nmocap x 3 and
+ * nbatch x nmocap x 4, used by every following mjb_inverse until replaced. NULL pointers return to
+ * the model pose (what mj_makeData / mj_resetData leave in mjData). */
+MJB_API int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* mocap_quat);
 /* adopt DEVICE structure-of-arrays inputs without a copy: (nq|nv) x stride, stride >= nbatch.
  * Pass NULL pointers to return to the internal buffers. */
 MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel,

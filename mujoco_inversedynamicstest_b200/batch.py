@@ -163,6 +163,15 @@ class BatchData:
                                              int(stride)), "mjb_setStateDevice")
         self.nbatch = int(n)
 
+    def set_mocap(self, mocap_pos=None, mocap_quat=None):
+        """Per-state mocap poses [nbatch, nmocap, 3] / [nbatch, nmocap, 4]; None: the model pose."""
+        if mocap_pos is None or mocap_quat is None:
+            self._check(lib().mjb_setMocap(self._d, 0, None, None), "mjb_setMocap")
+            return
+        p = np.ascontiguousarray(mocap_pos, dtype=np.float64)
+        q = np.ascontiguousarray(mocap_quat, dtype=np.float64)
+        self._check(lib().mjb_setMocap(self._d, p.shape[0], p.ctypes.data, q.ctypes.data), "mjb_setMocap")
+
     def inverse(self, nbatch=None, sync=True):
         n = self.nbatch if nbatch is None else int(nbatch)
         fn = lib().mjb_inverse if sync else lib().mjb_inverseAsync

@@ -68,6 +68,7 @@ struct mjbData_ {
   // mjb_compareFwdInv: forward-pass quantities (SoA) and the result, allocated on first use
   double *d_fwd_qforce = nullptr, *d_fwd_xfrc = nullptr, *d_fwd_qc = nullptr, *d_fwdinv = nullptr;
   bool own_qfrc_constraint = false;
+  double *d_mocap_pos = nullptr, *d_mocap_quat = nullptr;   // per-state mocap poses (mjb_setMocap)
   int skip_sensors = 0;        // mj_inverseSkip(skipsensor = 1) / inner batches of mjb_inverseFD
   double* d_fd_out = nullptr;
   size_t fd_out_doubles = 0;
@@ -296,6 +297,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_slot_rec);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
+  cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
   cudaFree(d->d_fwd_qforce); cudaFree(d->d_fwd_xfrc); cudaFree(d->d_fwd_qc); cudaFree(d->d_fwdinv);
   for (int b = 0; b < 2; b++) {
     cudaFree(d->pipe_in[b]); cudaFree(d->pipe_out[b]);
@@ -335,6 +337,32 @@ int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
   ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq + bv), d->d_qacc, nbatch, H.nv, d->stride, d->stream), "transpose qacc");
   d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
   return ok ? 0 : -1;
+}
+
+// d->mocap_pos / d->mocap_quat per state (HOST, nbatch x nmocap x 3 | 4); NULL returns to the model pose
+int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* mocap_quat) {
+  const mjbHdr& H = d->hdr;
+  mjb::Outputs& o = d->out;
+  if (!mocap_pos || !mocap_quat || H.nmocap == 0) { o.mocap_pos = nullptr; o.mocap_quat = nullptr; return 0; }
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setMocap: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const size_t S = (size_t)d->stride, n = (size_t)nbatch, nm = (size_t)H.nmocap;
+  bool ok = true;
+  if (!d->d_mocap_pos) {
+    ok = ok && devAlloc(d, &d->d_mocap_pos, 3 * nm * S, "cudaMalloc(mocap_pos)");
+    ok = ok && devAlloc(d, &d->d_mocap_quat, 4 * nm * S, "cudaMalloc(mocap_quat)");
+  }
+  if (!ok || !ensureStage(d, n * 7 * nm * sizeof(double))) return -1;
+  char* st = (char*)d->d_stage;
+  const size_t bp = n * 3 * nm * sizeof(double), bq = n * 4 * nm * sizeof(double);
+  ok = ok && check(d, cudaMemcpyAsync(st, mocap_pos, bp, cudaMemcpyHostToDevice, d->stream), "H2D mocap_pos");
+  ok = ok && check(d, cudaMemcpyAsync(st + bp, mocap_quat, bq, cudaMemcpyHostToDevice, d->stream), "H2D mocap_quat");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)st, d->d_mocap_pos, nbatch, (int)(3 * nm), d->stride, d->stream), "transpose mocap_pos");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bp), d->d_mocap_quat, nbatch, (int)(4 * nm), d->stride, d->stream), "transpose mocap_quat");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_setMocap");   // the staging buffer is shared with mjb_setState
+  if (!ok) return -1;
+  o.mocap_pos = d->d_mocap_pos; o.mocap_quat = d->d_mocap_quat;
+  return 0;
 }
 
 int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc,

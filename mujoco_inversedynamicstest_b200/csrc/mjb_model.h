@@ -278,6 +278,7 @@ typedef struct mjbHdr_ {
   int32_t nsensordata;
   int32_t sensor_post;      // some sensor reads cacc / cfrc_int (mj_rnePostConstraint, engine_sensor.c:727-740)
   int32_t nsite;
+  int32_t nmocap, pad0;
   double timestep, impratio;
   double gravity[3];
   double pad1;

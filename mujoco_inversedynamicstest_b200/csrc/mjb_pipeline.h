@@ -89,6 +89,10 @@ struct Outputs {
   const double* fwd_xfrc;             // [nbody*6][stride] xfrc_applied: force, torque per body; or null
   const double* fwd_qfrc_constraint;  // [nv][stride]
   double* fwdinv;                     // [2][stride]
+  // per-state mocap poses (d->mocap_pos / d->mocap_quat, INPUTS; engine_core_smooth.c:70-86), or null:
+  // mocap bodies then sit at their model pose, as after mj_resetData
+  const double* mocap_pos;            // [nmocap*3][stride]
+  const double* mocap_quat;           // [nmocap*4][stride]
 };
 
 struct Ctx {
@@ -1209,7 +1213,13 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       quat_dof_forces(c, jntadr, qadr, bda, MJB_JNT_FREE, quat);
     } else {
       double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
-      if (body_mocapid[b] >= 0) normalize4(bquat);   // mocap pose = model pose (mj_resetData default)
+      const int mid = body_mocapid[b];
+      if (mid >= 0) {                  // mocap pose: the caller's, else the model pose (mj_resetData default)
+        if (c.out.mocap_quat) {
+          for (int k = 0; k < 4; k++) bquat[k] = c.out.mocap_quat[(size_t)(4*mid + k)*(size_t)c.N + c.s];
+        }
+        normalize4(bquat);
+      }
       if (pid) {
         double pm[9];
         const double Q[4] = {CS(3), CS(4), CS(5), CS(6)};
@@ -1219,6 +1229,9 @@ MJB_HD inline void forward_sweep(Ctx& c) {
         mulQuat(quat, Q, bquat);
       } else {
         for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
+        if (mid >= 0 && c.out.mocap_pos) {
+          for (int k = 0; k < 3; k++) pos[k] = c.out.mocap_pos[(size_t)(3*mid + k)*(size_t)c.N + c.s];
+        }
         for (int k = 0; k < 4; k++) quat[k] = bquat[k];
         O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
         stc(org, 3*b, O, 3);

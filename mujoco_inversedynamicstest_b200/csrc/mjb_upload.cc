@@ -641,6 +641,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nsensordata = sensors ? m->nsensordata : 0;
   H.sensor_post = sensor_post ? 1 : 0;
   H.nsite = m->nsite;
+  H.nmocap = m->nmocap;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 

@@ -218,6 +218,11 @@ typedef struct {
 static int refh_post_constraint = 0;
 REFH_API void refh_set_post_constraint(int on) { refh_post_constraint = on; }
 
+/* per-state mocap poses for the batch loop (nbatch x nmocap x 3 | 4), NULL: model pose */
+static const double* refh_mocap_pos = NULL;
+static const double* refh_mocap_quat = NULL;
+REFH_API void refh_set_mocap(const double* pos, const double* quat) { refh_mocap_pos = pos; refh_mocap_quat = quat; }
+
 static void* run_chunk(void* arg) {
   refhChunk* c = (refhChunk*)arg;
   const mjModel* m = c->m;
@@ -227,6 +232,10 @@ static void* run_chunk(void* arg) {
     mju_copy(d->qpos, c->qpos + i*m->nq, m->nq);
     mju_copy(d->qvel, c->qvel + i*m->nv, m->nv);
     mju_copy(d->qacc, c->qacc + i*m->nv, m->nv);
+    if (refh_mocap_pos && refh_mocap_quat) {
+      mju_copy(d->mocap_pos, refh_mocap_pos + i*3*m->nmocap, 3*m->nmocap);
+      mju_copy(d->mocap_quat, refh_mocap_quat + i*4*m->nmocap, 4*m->nmocap);
+    }
     mj_inverse(m, d);
     if (refh_post_constraint) mj_rnePostConstraint(m, d);
     if (c->qfrc_inverse) mju_copy(c->qfrc_inverse + i*m->nv, d->qfrc_inverse, m->nv);

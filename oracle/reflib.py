@@ -191,7 +191,7 @@ class Model:
                             p(out["qacc"]), p(out["qfrc_actuator"]), p(out["qfrc_constraint"]), p(out["fwdinv"]))
         return out
 
-    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1):
+    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1, mocap=None):
         """Loop the reference's mj_inverse over the batch.
 
         fields: {name: maxrows} of extra mjData arrays / contact_* pseudo fields / scalar counters
@@ -223,6 +223,13 @@ class Model:
             reqs.append((name.encode(), arr, maxrows))
         # cacc / cfrc_int / cfrc_ext are outputs of mj_rnePostConstraint, run after mj_inverse on request
         L.refh_set_post_constraint(int(any(k in fields for k in ("cacc", "cfrc_int", "cfrc_ext"))))
+        L.refh_set_mocap.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        if mocap is not None:      # (mocap_pos [n, nmocap, 3], mocap_quat [n, nmocap, 4]) per state
+            mp = np.ascontiguousarray(mocap[0], dtype=np.float64)
+            mq = np.ascontiguousarray(mocap[1], dtype=np.float64)
+            L.refh_set_mocap(mp.ctypes.data, mq.ctypes.data)
+        else:
+            L.refh_set_mocap(None, None)
         rq = (_Request * max(1, len(reqs)))()
         for i, (nm, arr, mr) in enumerate(reqs):
             rq[i].name = nm
@@ -230,6 +237,7 @@ class Model:
             rq[i].maxrows = mr
         t = L.refh_inverse_batch(self.ptr, n, qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data,
                                  out["qfrc_inverse"].ctypes.data, rq, len(reqs), int(nthread))
+        L.refh_set_mocap(None, None)
         if t < 0:
             raise RuntimeError("refh_inverse_batch: unknown field requested")
         return out, t

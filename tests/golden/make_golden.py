@@ -49,6 +49,8 @@ CASES = {
     "boxes_elliptic": ("repo:tests/golden/models/boxes.xml", {"cone": 1}, 256, (0.0, 0.7), 64, 300),
     "tendons": ("repo:tests/golden/models/tendons.xml", {}, 512, (0.3, 1.3), 8, 32),
     "gravcomp": ("repo:tests/golden/models/gravcomp.xml", {}, 128, (0.5, 1.5), 8, 16),
+    # mocap bodies at their model pose (what mj_makeData leaves in mjData); moved per state: MOCAP_CASES
+    "mocap": ("repo:tests/golden/models/mocap.xml", {}, 128, (0.0, 0.6), 16, 96),
     # every sensor type evaluated on the device (mj_sensorPos / Vel / Acc); sensordata is dumped too
     "sensors": ("repo:tests/golden/models/sensors.xml", {}, 256, (0.0, 0.6), 16, 96),
 }
@@ -165,7 +167,44 @@ def make_fwdinv_case(name):
           f"away from it max {out['fwdinv'][1::2].max(axis=0)}")
 
 
+# per-state mocap poses (d->mocap_pos / mocap_quat as inputs of mj_kinematics): name -> (case, nstate)
+MOCAP_CASES = {"mocap_moved": ("mocap", 128)}
+
+
+def mocap_poses(m, nstate):
+    """Seeded per-state mocap poses around the model pose: +-0.15 m, ~+-0.5 rad, quaternions NOT normalised."""
+    rng = np.random.RandomState(20250331)
+    nb = m.int("nbody")
+    ids = [b for b in range(nb) if m.array("body_mocapid").ravel()[b] >= 0]
+    ids.sort(key=lambda b: m.array("body_mocapid").ravel()[b])
+    pos0 = m.array("body_pos").reshape(nb, 3)[ids]
+    quat0 = m.array("body_quat").reshape(nb, 4)[ids]
+    pos = pos0[None] + rng.uniform(-0.15, 0.15, (nstate, len(ids), 3))
+    quat = quat0[None] * rng.uniform(0.8, 1.3, (nstate, len(ids), 1)) + rng.uniform(-0.25, 0.25, (nstate, len(ids), 4))
+    return pos, quat
+
+
+def make_mocap_case(name):
+    base, nstate = MOCAP_CASES[name]
+    xml, opts, _, zr, nconmax, njmax = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]))
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    pos, quat = mocap_poses(m, nstate)
+    fields = {"ncon": 1, "ne": 1, "nf": 1, "nl": 1, "nefc": 1, "contact_geom": nconmax, "efc_type": njmax,
+              "efc_id": njmax, "efc_state": njmax, "efc_force": njmax, "xpos": None, "xquat": None,
+              "qfrc_constraint": None}
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields, mocap=(pos, quat))
+    assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), nconmax=np.array(nconmax), njmax=np.array(njmax),
+                        mocap_pos=pos, mocap_quat=quat,
+                        **{k: (v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v) for k, v in out.items()})
+    print(f"{name}: states={nstate} mean ncon={out['ncon'].mean():.2f} mean nefc={out['nefc'].mean():.2f}")
+
+
 if __name__ == "__main__":
-    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES)):
+    for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
+                 list(MOCAP_CASES)):
         (make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
-         make_fwdinv_case if case in FWDINV_CASES else make_case)(case)
+         make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
+         make_case)(case)

@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat"]
 
 
 class Outputs(ctypes.Structure):
@@ -40,7 +40,7 @@ def available():
     return os.path.exists(build_hostemu.LIB) or build_hostemu.include_dir() is not None
 
 
-def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None):
+def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -69,6 +69,9 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None):
         if fwd.get("xfrc") is not None:
             a["fwd_xfrc"] = np.ascontiguousarray(fwd["xfrc"].reshape(n, -1).T, dtype=np.float64)
         a["fwdinv"] = np.zeros((2, n))
+    if mocap is not None:   # (mocap_pos [n, nmocap, 3], mocap_quat [n, nmocap, 4])
+        a["mocap_pos"] = np.ascontiguousarray(mocap[0].reshape(n, -1).T, dtype=np.float64)
+        a["mocap_quat"] = np.ascontiguousarray(mocap[1].reshape(n, -1).T, dtype=np.float64)
     if has_sensors:
         a["sensordata"] = np.zeros((model.int("nsensordata"), n))
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL

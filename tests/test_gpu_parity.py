@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors"]
+         "sensors", "mocap"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -161,6 +161,36 @@ def test_golden_compare_fwdinv(name):
     plain.inverse()
     bd.inverse()
     np.testing.assert_array_equal(bd.qfrc_inverse(), plain.qfrc_inverse())
+
+
+def test_golden_per_state_mocap_poses():
+    """mjb_setMocap: per-state d->mocap_pos / d->mocap_quat (mj_kinematics, engine_core_smooth.c:70-86)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    z = np.load(os.path.join(util.GOLDEN, "mocap_moved.npz"))
+    model = mjb.Model.from_mjb(os.path.join(util.GOLDEN, "mocap.mjb.gz"))
+    n = int(z["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(z["z_range"]))
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC,
+                       nconmax=int(z["nconmax"]), njmax=int(z["njmax"]))
+    bd.set_state(qpos, qvel, qacc)
+    bd.set_mocap(z["mocap_pos"], z["mocap_quat"])
+    assert bd.inverse() == 0
+    cnt = bd.counts()
+    for k in ("ncon", "ne", "nf", "nl", "nefc"):
+        np.testing.assert_array_equal(cnt[k], z[k], err_msg=k)
+    np.testing.assert_array_equal(bd.contacts()["geom"], z["contact_geom"])
+    efc = bd.efc()
+    np.testing.assert_array_equal(efc["type"], z["efc_type"])
+    np.testing.assert_array_equal(efc["state"], z["efc_state"])
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), z["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    # back to the model pose: the plain fixture
+    _, ref = util.golden("mocap")
+    bd.set_mocap(None, None)
+    bd.inverse()
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
 
 
 def test_golden_sensordata():

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation libr
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors"]
+         "sensors", "mocap"]
 
 
 def _run(name):
@@ -128,6 +128,24 @@ def test_compare_fwdinv(name):
     nviol, worst = util.fwdinv_violations(out["fwdinv"], z)
     assert nviol == 0, (nviol, worst)
     assert z["fwdinv"][1::2].min() > 0.5          # the perturbed half is a non-trivial comparison
+
+
+def test_per_state_mocap_poses():
+    """d->mocap_pos / d->mocap_quat as per-state inputs (mj_kinematics, engine_core_smooth.c:70-86;
+    quaternions arrive unnormalised), welds / connects / contacts against the moved bodies."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    z = np.load(os.path.join(util.GOLDEN, "mocap_moved.npz"))
+    model = mjb.Model.from_mjb(os.path.join(util.GOLDEN, "mocap.mjb.gz"))
+    n = int(z["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(z["z_range"]))
+    out = emu.run(model, qpos, qvel, qacc, nconmax=int(z["nconmax"]), njmax=int(z["njmax"]),
+                  mocap=(z["mocap_pos"], z["mocap_quat"]))
+    for k in ("ncon", "ne", "nf", "nl", "nefc", "contact_geom", "efc_type", "efc_id", "efc_state"):
+        np.testing.assert_array_equal(out[k], z[k], err_msg=k)
+    np.testing.assert_array_equal(emu.slot(model, out, "xpos").reshape(n, -1, 3), z["xpos"])
+    nviol, worst = util.qfrc_violations_scaled(out["qfrc_inverse"], z["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
 
 
 def test_sensordata():
