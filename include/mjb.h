@@ -149,8 +149,11 @@ MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 
 /* host-to-host form of the loop: qpos/qvel/qacc in (nbatch x nq|nv, HOST, pinned for best speed),
  * qfrc_inverse out (nbatch x nv, HOST). The batch is pipelined in pieces over three CUDA streams
- * (H2D copy | kernels | D2H copy) so transfers overlap compute. Asynchronous: the results are valid
- * after mjb_synchronize(d). Returns 0, or a negative value on a CUDA error. */
+ * (H2D copy | kernels | D2H copy) so transfers overlap compute. The input arrays are read from the
+ * moment of the call (they must hold the states when it is made and stay unchanged until the results
+ * are there); consecutive calls overlap: the copy-in of one call runs under the kernels of the
+ * previous one. Asynchronous: the results are valid after mjb_synchronize(d) (or once the stream
+ * given to mjb_setStream has drained). Returns 0, or a negative value on a CUDA error. */
 MJB_API int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos,
                             const mjtNum* qvel, const mjtNum* qacc, mjtNum* qfrc_inverse);
 

@@ -56,6 +56,8 @@ struct mjbData_ {
   void* pipe_in[2] = {nullptr, nullptr};
   void* pipe_out[2] = {nullptr, nullptr};
   size_t pipe_piece = 0;
+  unsigned pipe_seq = 0;                 // pieces sent so far: piece k uses staging buffer k & 1, across calls
+  bool pipe_used[2] = {false, false};   // staging buffer b has been through the pipeline (its events are valid)
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_tr[2] = {nullptr, nullptr},
               ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   mjb::Outputs out;            // device SoA outputs
@@ -460,7 +462,13 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
   d->last_nbatch = nbatch;
   d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
   if (nbatch == 0) return 0;
-  const size_t piece = 131072;
+  // states per pipeline piece: large enough for the kernels to fill the GPU, small enough that the
+  // first copy-in and the last copy-out of a call stay short (MJB_HOST_PIECE overrides, for tuning)
+  size_t piece = d->pipe_piece ? d->pipe_piece : 131072;
+  if (!d->pipe_piece) {
+    const char* env = std::getenv("MJB_HOST_PIECE");
+    if (env && std::atol(env) >= 1024) piece = (size_t)std::atol(env) & ~(size_t)127;
+  }
   const size_t in_doubles = piece * (size_t)(H.nq + 2*H.nv), out_doubles = piece * (size_t)H.nv;
   bool ok = true;
   if (!d->s_in) {
@@ -477,20 +485,17 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
     d->pipe_piece = piece;
     if (!ok) return -1;
   }
-  // order the pipeline after whatever is already queued on the caller's stream
-  cudaEvent_t ev_start;
-  ok = ok && check(d, cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming), "cudaEventCreate");
-  ok = ok && check(d, cudaEventRecord(ev_start, d->stream), "cudaEventRecord");
-  ok = ok && check(d, cudaStreamWaitEvent(d->s_in, ev_start, 0), "cudaStreamWaitEvent");
-  ok = ok && check(d, cudaStreamWaitEvent(d->s_out, ev_start, 0), "cudaStreamWaitEvent");
+  // The host arrays are read from the moment of the call (like cudaMemcpy from host memory): the
+  // copy-in stream does NOT wait for the caller's stream, so the copies of this call overlap the
+  // kernels of the previous one; the staging buffers are handed over through their own events.
   int p = 0;
   for (size_t first = 0; first < (size_t)nbatch && ok; first += piece, p++) {
-    const int b = p & 1;
+    const int b = (int)(d->pipe_seq++ & 1u);
     const size_t n = ((size_t)nbatch - first) < piece ? ((size_t)nbatch - first) : piece;
     const size_t bq = n * H.nq * sizeof(double), bv = n * H.nv * sizeof(double);
     char* st = (char*)d->pipe_in[b];
     // stage 1: host -> device (waits until the transposes of piece p-2 released this buffer)
-    if (p >= 2) ok = ok && check(d, cudaStreamWaitEvent(d->s_in, d->ev_tr[b], 0), "wait tr");
+    if (d->pipe_used[b]) ok = ok && check(d, cudaStreamWaitEvent(d->s_in, d->ev_tr[b], 0), "wait tr");
     ok = ok && check(d, cudaMemcpyAsync(st, qpos + first * H.nq, bq, cudaMemcpyHostToDevice, d->s_in), "H2D qpos");
     ok = ok && check(d, cudaMemcpyAsync(st + bq, qvel + first * H.nv, bv, cudaMemcpyHostToDevice, d->s_in), "H2D qvel");
     ok = ok && check(d, cudaMemcpyAsync(st + bq + bv, qacc + first * H.nv, bv, cudaMemcpyHostToDevice, d->s_in), "H2D qacc");
@@ -502,19 +507,19 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
     ok = ok && check(d, mjb::launch_aos_to_soa((const double*)(st + bq + bv), d->d_qacc + first, (int)n, H.nv, d->stride, d->stream), "transpose qacc");
     ok = ok && check(d, cudaEventRecord(d->ev_tr[b], d->stream), "record tr");
     ok = ok && launchRange(d, (long long)first, (long long)n);
-    if (p >= 2) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[b], 0), "wait out");
+    if (d->pipe_used[b]) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[b], 0), "wait out");
     ok = ok && check(d, mjb::launch_soa_to_aos(d->out.qfrc_inverse + first, (double*)d->pipe_out[b], (int)n, H.nv, d->stride, d->stream), "transpose out");
     ok = ok && check(d, cudaEventRecord(d->ev_comp[b], d->stream), "record comp");
     // stage 3: device -> host
     ok = ok && check(d, cudaStreamWaitEvent(d->s_out, d->ev_comp[b], 0), "wait comp");
     ok = ok && check(d, cudaMemcpyAsync(qfrc_inverse + first * H.nv, d->pipe_out[b], bv, cudaMemcpyDeviceToHost, d->s_out), "D2H qfrc");
     ok = ok && check(d, cudaEventRecord(d->ev_out[b], d->s_out), "record out");
+    d->pipe_used[b] = true;
   }
   // the caller's stream completes when the last copies have landed
   for (int b = 0; b < 2 && ok; b++) {
-    if (p > b) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[(p - 1 - b) & 1], 0), "join");
+    if (d->pipe_used[b]) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[b], 0), "join");
   }
-  cudaEventDestroy(ev_start);
   return ok ? 0 : -1;
 }
 

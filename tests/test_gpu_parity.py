@@ -430,6 +430,21 @@ def test_pipelined_host_entry_point_matches_staged_calls():
         assert np.array_equal(a, b)
     c = bd.inverse_host_arrays(qpos[:1000], qvel[:1000], qacc[:1000])
     assert np.array_equal(a[:1000], c)
+    # consecutive calls overlap (the copy-in of a call runs under the kernels of the previous one):
+    # three calls on different inputs and outputs without a synchronisation in between
+    import torch
+    nv = model.int("nv")
+    sets = []
+    for k in range(3):
+        sl = slice(k * 70_001, k * 70_001 + 150_000)
+        ins = [torch.from_numpy(np.ascontiguousarray(x[sl])).pin_memory() for x in (qpos, qvel, qacc)]
+        out = torch.zeros((150_000, nv), dtype=torch.float64).pin_memory()
+        sets.append((sl, ins, out))
+    for sl, ins, out in sets:
+        bd.inverse_host(150_000, ins[0].data_ptr(), ins[1].data_ptr(), ins[2].data_ptr(), out.data_ptr())
+    bd.synchronize()
+    for sl, ins, out in sets:
+        assert np.array_equal(out.numpy(), a[sl])
 
 
 def test_inverse_skip_equals_inverse():
