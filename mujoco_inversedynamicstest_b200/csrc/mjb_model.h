@@ -83,6 +83,7 @@
   X(body_ipos, nbody, 3)          \
   X(body_iquat, nbody, 4)         \
   X(body_mass, nbody, 1)          \
+  X(body_subtreemass, nbody, 1)   \
   X(body_inertia, nbody, 3)       \
   X(body_invweight0, nbody, 2)    \
   X(body_gravcomp, nbody, 1)      \
@@ -187,7 +188,8 @@ enum { MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, 
        MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_FRAMEPOS = 25,
        MJB_SENS_FRAMEQUAT = 26, MJB_SENS_FRAMEXAXIS = 27, MJB_SENS_FRAMEYAXIS = 28, MJB_SENS_FRAMEZAXIS = 29,
        MJB_SENS_FRAMELINVEL = 30, MJB_SENS_FRAMEANGVEL = 31, MJB_SENS_FRAMELINACC = 32,
-       MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34 };
+       MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34, MJB_SENS_SUBTREELINVEL = 35,
+       MJB_SENS_SUBTREEANGMOM = 36 };
 enum { MJB_OBJ_BODY = 1, MJB_OBJ_XBODY = 2, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6 };
 enum { MJB_DATATYPE_REAL = 0, MJB_DATATYPE_POSITIVE = 1 };
 
@@ -278,7 +280,8 @@ typedef struct mjbHdr_ {
   int32_t nsensordata;
   int32_t sensor_post;      // some sensor reads cacc / cfrc_int (mj_rnePostConstraint, engine_sensor.c:727-740)
   int32_t nsite;
-  int32_t nmocap, pad0;
+  int32_t nmocap;
+  int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
   double timestep, impratio;
   double gravity[3];
   double pad1;

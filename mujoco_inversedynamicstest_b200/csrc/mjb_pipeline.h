@@ -3054,6 +3054,67 @@ MJB_HD inline void sensor_point_motion(Ctx& c, const double* carrier, int body, 
   for (int k = 0; k < 3; k++) { res[k] = ang[k]; res[3 + k] = lin[k]; }
 }
 
+// mj_subtreeVel (engine_core_smooth.c:1900-1960): subtree_linvel and subtree_angmom of every body,
+// left in the ia rows of the scratch (free after the inertia kernel), 21 doubles per body:
+// [0..5] body velocity at xipos (world axes), [6..8] subtree_linvel, [9..11] subtree_angmom,
+// [12..14] subtree_com, [15..17] xipos. Only for models with subtreelinvel / subtreeangmom sensors.
+MJB_HD inline void subtree_velocities(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody;
+  const int* body_parentid = MI(body_parentid);
+  const double* mass = MD(body_mass); const double* stm = MD(body_subtreemass);
+  const double* inertia = MD(body_inertia);
+  double* t = SC(ia);
+  for (int i = 0; i < nbody; i++) {
+    double pos[3], quat[4], m9[9], bv[6], w[21], dv[3], lw[3];
+    sensor_object(c, MJB_OBJ_BODY, i, pos, quat);
+    quat2Mat(m9, quat);
+    sensor_point_motion(c, SC(cvel), i, pos, bv);
+    mulMatTVec3(lw, m9, bv);
+    lw[0] *= inertia[3*i]; lw[1] *= inertia[3*i + 1]; lw[2] *= inertia[3*i + 2];
+    mulMatVec3(dv, m9, lw);
+    for (int k = 0; k < 6; k++) w[k] = bv[k];
+    for (int k = 0; k < 3; k++) {
+      w[6 + k] = bv[3 + k]*mass[i]; w[9 + k] = dv[k]; w[12 + k] = pos[k]*mass[i]; w[15 + k] = pos[k];
+    }
+    w[18] = w[19] = w[20] = 0;
+    stn(t, 21*i, w, 21);
+  }
+  // subtree_com (mj_comPos :194-213) and subtree_linvel: momenta up the tree, then the means
+  for (int i = nbody - 1; i >= 0; i--) {
+    double a[9];
+    ldn(a, t, 21*i + 6, 9);
+    if (i) {
+      const int p = body_parentid[i];
+      double pa[9];
+      ldn(pa, t, 21*p + 6, 9);
+      for (int k = 0; k < 3; k++) { pa[k] += a[k]; pa[6 + k] += a[6 + k]; }
+      stn(t, 21*p + 6, pa, 9);
+    }
+    const double inv = 1/fmax(MJB_MINVAL, stm[i]);
+    for (int k = 0; k < 3; k++) a[k] *= inv;
+    if (stm[i] < MJB_MINVAL) {
+      ldn(a + 6, t, 21*i + 15, 3);
+    } else {
+      for (int k = 0; k < 3; k++) a[6 + k] /= stm[i];
+    }
+    stn(t, 21*i + 6, a, 9);
+  }
+  for (int i = nbody - 1; i > 0; i--) {
+    const int p = body_parentid[i];
+    double w[21], pw[21], dx[3], dv[3], dL[3];
+    ldn(w, t, 21*i, 21); ldn(pw, t, 21*p, 21);
+    for (int k = 0; k < 3; k++) { dx[k] = w[15 + k] - w[12 + k]; dv[k] = (w[3 + k] - w[6 + k])*mass[i]; }
+    cross3(dL, dx, dv);
+    for (int k = 0; k < 3; k++) { w[9 + k] += dL[k]; pw[9 + k] += w[9 + k]; }
+    for (int k = 0; k < 3; k++) { dx[k] = w[12 + k] - pw[12 + k]; dv[k] = (w[6 + k] - pw[6 + k])*stm[i]; }
+    cross3(dL, dx, dv);
+    for (int k = 0; k < 3; k++) pw[9 + k] += dL[k];
+    stn(t, 21*i + 9, w + 9, 3);
+    stn(t, 21*p + 9, pw + 9, 3);
+  }
+}
+
 MJB_HD inline void sensors(Ctx& c) {
   const mjbHdr& H = *c.H;
   const size_t N = (size_t)c.N;
@@ -3061,6 +3122,7 @@ MJB_HD inline void sensors(Ctx& c) {
   const double* cutoff = MD(sensor_cutoff);
   const int* body_parentid = MI(body_parentid);
   const int* rootid = MI(body_rootid);
+  if (H.sensor_subtreevel) subtree_velocities(c);
   for (int i = 0; i < H.nsensor; i++) {
     const int* si = sen + MJB_SEN_NI*i;
     const int type = si[MJB_SEN_TYPE], objtype = si[MJB_SEN_OBJTYPE], objid = si[MJB_SEN_OBJID];
@@ -3081,6 +3143,10 @@ MJB_HD inline void sensors(Ctx& c) {
     } else if (type == MJB_SENS_BALLANGVEL) {
       const int a = MI(jnt_dofadr)[objid];
       for (int k = 0; k < 3; k++) v[k] = QVEL(a + k);
+    } else if (type == MJB_SENS_SUBTREELINVEL) {
+      ldn(v, SC(ia), 21*objid + 6, 3);
+    } else if (type == MJB_SENS_SUBTREEANGMOM) {
+      ldn(v, SC(ia), 21*objid + 9, 3);
     } else if (type == MJB_SENS_SUBTREECOM) {
       // mj_comPos (engine_core_smooth.c:183-225): mass-weighted mean of xipos over the subtree,
       // whose bodies are contiguous; mass*(xipos - O) and mass are cinert[6..9]

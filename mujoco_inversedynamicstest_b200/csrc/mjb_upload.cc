@@ -217,10 +217,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   }
   // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
   // whose inputs exist on this path are evaluated by the sensor kernel; the others (touch, rays,
-  // camera, geom distances, actuator quantities, limit sensors, subtree momenta, energies, clock,
-  // user / plugin) are refused unless mjDSBL_SENSOR is set.
+  // camera, geom distances, actuator quantities, limit sensors, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
-  bool sensor_post = false;
+  bool sensor_post = false, sensor_subtreevel = false;
   std::vector<int> sensor_int;
   std::vector<double> sensor_cutoff;
   for (int i = 0; i < m->nsensor && sensors; i++) {
@@ -242,6 +241,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         break;
       case mjSENS_VELOCIMETER: case mjSENS_GYRO:
         ok = true; break;
+      case mjSENS_SUBTREELINVEL: case mjSENS_SUBTREEANGMOM:
+        ok = true; sensor_subtreevel = true; break;
       case mjSENS_ACCELEROMETER:
         ok = true; sensor_post = true; break;
       case mjSENS_FORCE: case mjSENS_TORQUE:
@@ -642,6 +643,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.sensor_post = sensor_post ? 1 : 0;
   H.nsite = m->nsite;
   H.nmocap = m->nmocap;
+  H.sensor_subtreevel = sensor_subtreevel ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 
