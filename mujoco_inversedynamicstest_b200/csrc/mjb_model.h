@@ -185,7 +185,9 @@ enum { MJB_SEN_TYPE = 0, MJB_SEN_DATATYPE, MJB_SEN_OBJTYPE, MJB_SEN_OBJID, MJB_S
 // mjtSensor / mjtObj / mjtDataType values restated (include/mujoco/mjmodel.h)
 enum { MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
        MJB_SENS_TORQUE = 5, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
-       MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_FRAMEPOS = 25,
+       MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_JOINTLIMITPOS = 19,
+       MJB_SENS_JOINTLIMITVEL = 20, MJB_SENS_JOINTLIMITFRC = 21, MJB_SENS_TENDONLIMITPOS = 22,
+       MJB_SENS_TENDONLIMITVEL = 23, MJB_SENS_TENDONLIMITFRC = 24, MJB_SENS_FRAMEPOS = 25,
        MJB_SENS_FRAMEQUAT = 26, MJB_SENS_FRAMEXAXIS = 27, MJB_SENS_FRAMEYAXIS = 28, MJB_SENS_FRAMEZAXIS = 29,
        MJB_SENS_FRAMELINVEL = 30, MJB_SENS_FRAMEANGVEL = 31, MJB_SENS_FRAMELINACC = 32,
        MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34, MJB_SENS_SUBTREELINVEL = 35,

@@ -3115,6 +3115,26 @@ MJB_HD inline void subtree_velocities(Ctx& c) {
   }
 }
 
+// the first limit row of a joint / tendon as the limit sensors see it (engine_sensor.c:293-313,
+// 600-617, 837-855): value and velocity of the coordinate in, (pos - margin, vel, force) of the row
+// out; false when neither side is active. Same arithmetic as scalar_row, nothing is emitted.
+MJB_HD inline bool limit_row_readings(const double* sp, const double* range, double margin, double dA,
+                                      double value, double vel, double acc, double* out3) {
+  for (int side = -1; side <= 1; side += 2) {
+    const double dist = side * (range[(side + 1)/2] - value);
+    if (dist < margin) {
+      const double imp = impedance(sp, dist, margin);
+      const double R = fmax(MJB_MINVAL, (1 - imp)*dA/imp);
+      const double rv = -side*vel;
+      const double aref = -sp[MJB_SP_B]*rv - sp[MJB_SP_K]*imp*(dist - margin);
+      const double jar = -side*acc - aref;
+      out3[0] = dist - margin; out3[1] = rv; out3[2] = jar >= 0 ? 0.0 : -(1/R)*jar;
+      return true;
+    }
+  }
+  return false;
+}
+
 MJB_HD inline void sensors(Ctx& c) {
   const mjbHdr& H = *c.H;
   const size_t N = (size_t)c.N;
@@ -3143,6 +3163,23 @@ MJB_HD inline void sensors(Ctx& c) {
     } else if (type == MJB_SENS_BALLANGVEL) {
       const int a = MI(jnt_dofadr)[objid];
       for (int k = 0; k < 3; k++) v[k] = QVEL(a + k);
+    } else if (type >= MJB_SENS_JOINTLIMITPOS && type <= MJB_SENS_TENDONLIMITFRC) {
+      // limit sensors: the readings of the object's first limit row, 0 while the limit is inactive
+      double r3[3] = {0, 0, 0};
+      if (!(H.disableflags & MJB_DSBL_LIMIT) && rows_enabled(H)) {
+        if (type <= MJB_SENS_JOINTLIMITFRC) {
+          if (MI(jnt_limited)[objid]) {
+            const int dof = MI(jnt_dofadr)[objid];
+            limit_row_readings(MD(sp_jnt_limit) + MJB_SP_N*objid, MD(jnt_range) + 2*objid, MD(jnt_margin)[objid],
+                               MD(dof_invweight0)[dof], QPOS(MI(jnt_qposadr)[objid]), QVEL(dof), QACC(dof), r3);
+          }
+        } else if (MI(tendon_limited)[objid]) {
+          limit_row_readings(MD(sp_tendon_limit) + MJB_SP_N*objid, MD(tendon_range) + 2*objid,
+                             MD(tendon_margin)[objid], MD(tendon_invweight0)[objid], AT(SC(ten_length), objid),
+                             AT(SC(ten_velocity), objid), AT(SC(ten_acc), objid), r3);
+        }
+      }
+      v[0] = r3[(type - MJB_SENS_JOINTLIMITPOS) % 3];
     } else if (type == MJB_SENS_SUBTREELINVEL) {
       ldn(v, SC(ia), 21*objid + 6, 3);
     } else if (type == MJB_SENS_SUBTREEANGMOM) {

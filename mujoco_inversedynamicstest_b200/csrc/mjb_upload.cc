@@ -217,7 +217,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   }
   // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
   // whose inputs exist on this path are evaluated by the sensor kernel; the others (touch, rays,
-  // camera, geom distances, actuator quantities, limit sensors, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
+  // camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
   bool sensor_post = false, sensor_subtreevel = false;
   std::vector<int> sensor_int;
@@ -231,6 +231,13 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       case mjSENS_JOINTPOS: case mjSENS_JOINTVEL: case mjSENS_BALLQUAT: case mjSENS_BALLANGVEL:
       case mjSENS_SUBTREECOM:
         ok = true; break;
+      case mjSENS_JOINTLIMITPOS: case mjSENS_JOINTLIMITVEL: case mjSENS_JOINTLIMITFRC:
+        {
+          const int jt = m->jnt_type[m->sensor_objid[i]];
+          ok = jt == mjJNT_HINGE || jt == mjJNT_SLIDE;
+        }
+        break;
+      case mjSENS_TENDONLIMITPOS: case mjSENS_TENDONLIMITVEL: case mjSENS_TENDONLIMITFRC:
       case mjSENS_TENDONPOS: case mjSENS_TENDONVEL:
         // fixed tendons only: a spatial tendon's length exists on the device only while it carries a force
         ok = true;
