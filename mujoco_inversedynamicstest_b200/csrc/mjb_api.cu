@@ -52,7 +52,11 @@ struct mjbData_ {
   size_t stage_bytes = 0;
   int* d_counter = nullptr;
   // host pipeline of mjb_inverseHost: copy-in / copy-out streams, double-buffered staging, events
-  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_start = nullptr;
+  // work has been queued on the caller's stream since the last mjb_inverseHost: the pipeline's
+  // compute stream has to be ordered after it once
+  bool stream_dirty = true;
   void* pipe_in[2] = {nullptr, nullptr};
   void* pipe_out[2] = {nullptr, nullptr};
   size_t pipe_piece = 0;
@@ -174,10 +178,11 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   ok = ok && devAlloc(d, &d->d_model, (size_t)H.bytes, "cudaMalloc(model)");
   ok = ok && check(d, cudaMemcpy(d->d_model, blob.data(), (size_t)H.bytes, cudaMemcpyHostToDevice),
                    "cudaMemcpy(model)");
-  // intermediates live per chunk of states: at most 2^20 states and at most ~12 GB
+  // intermediates live per chunk of states: at most 2^20 states and at most ~16 GB (2^20 humanoid states
+  // are one chunk of 14.5 GB)
   {
     const double bytes_per_state = 8.0 * H.nscratch + 4.0 * (mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1);
-    long long chunk = (long long)(12.0e9 / bytes_per_state);
+    long long chunk = (long long)(16.0e9 / bytes_per_state);
     if (chunk > (1LL << 20)) chunk = 1LL << 20;
     if (chunk > d->stride) chunk = d->stride;
     chunk &= ~127LL;
@@ -309,6 +314,8 @@ void mjb_deleteData(mjbData* d) {
     if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
   }
   for (cudaEvent_t e : d->ev_pool) cudaEventDestroy(e);
+  if (d->s_comp) cudaStreamDestroy(d->s_comp);
+  if (d->ev_start) cudaEventDestroy(d->ev_start);
   if (d->s_in) cudaStreamDestroy(d->s_in);
   if (d->s_out) cudaStreamDestroy(d->s_out);
   mjb::Outputs& o = d->out;
@@ -321,9 +328,10 @@ void mjb_deleteData(mjbData* d) {
   delete d;
 }
 
-void mjb_setStream(mjbData* d, void* cuda_stream) { d->stream = (cudaStream_t)cuda_stream; }
+void mjb_setStream(mjbData* d, void* cuda_stream) { d->stream = (cudaStream_t)cuda_stream; d->stream_dirty = true; }
 
 int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc) {
+  d->stream_dirty = true;
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setState: nbatch out of range"; return -1; }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
   const mjbHdr& H = d->hdr;
@@ -343,6 +351,7 @@ int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
 
 // d->mocap_pos / d->mocap_quat per state (HOST, nbatch x nmocap x 3 | 4); NULL returns to the model pose
 int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* mocap_quat) {
+  d->stream_dirty = true;
   const mjbHdr& H = d->hdr;
   mjb::Outputs& o = d->out;
   if (!mocap_pos || !mocap_quat || H.nmocap == 0) { o.mocap_pos = nullptr; o.mocap_quat = nullptr; return 0; }
@@ -387,6 +396,7 @@ namespace {
 
 // launch the phase kernels for states [first, first + count) on the compute stream
 bool launchRange(mjbData* d, long long first, long long count) {
+  d->stream_dirty = true;      // mjb_inverseHost clears it again after its own launches
   mjb::LaunchArgs a;
   a.model = d->d_model;
   a.model_bytes = d->model_bytes;
@@ -464,7 +474,7 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
   if (nbatch == 0) return 0;
   // states per pipeline piece: large enough for the kernels to fill the GPU, small enough that the
   // first copy-in and the last copy-out of a call stay short (MJB_HOST_PIECE overrides, for tuning)
-  size_t piece = d->pipe_piece ? d->pipe_piece : 131072;
+  size_t piece = d->pipe_piece ? d->pipe_piece : 262144;   // measured best of 2^16 .. 2^19 (humanoid, 2^20 states)
   if (!d->pipe_piece) {
     const char* env = std::getenv("MJB_HOST_PIECE");
     if (env && std::atol(env) >= 1024) piece = (size_t)std::atol(env) & ~(size_t)127;
@@ -474,6 +484,8 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
   if (!d->s_in) {
     ok = ok && check(d, cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking), "cudaStreamCreate");
     ok = ok && check(d, cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && check(d, cudaStreamCreateWithFlags(&d->s_comp, cudaStreamNonBlocking), "cudaStreamCreate");
+    ok = ok && check(d, cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming), "cudaEventCreate");
     for (int b = 0; b < 2 && ok; b++) {
       ok = ok && check(d, cudaMalloc(&d->pipe_in[b], in_doubles * sizeof(double)), "cudaMalloc(pipe_in)");
       ok = ok && check(d, cudaMalloc(&d->pipe_out[b], out_doubles * sizeof(double)), "cudaMalloc(pipe_out)");
@@ -488,6 +500,16 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
   // The host arrays are read from the moment of the call (like cudaMemcpy from host memory): the
   // copy-in stream does NOT wait for the caller's stream, so the copies of this call overlap the
   // kernels of the previous one; the staging buffers are handed over through their own events.
+  // Transposes and kernels run on the pipeline's own compute stream, so that the kernels of this
+  // call follow those of the previous call directly; the caller's stream only joins at the end
+  // (it completes when the last results have landed) and is waited for only if something else was
+  // queued on it in between.
+  cudaStream_t user = d->stream;
+  if (d->stream_dirty) {
+    ok = ok && check(d, cudaEventRecord(d->ev_start, user), "cudaEventRecord");
+    ok = ok && check(d, cudaStreamWaitEvent(d->s_comp, d->ev_start, 0), "cudaStreamWaitEvent");
+  }
+  d->stream = d->s_comp;
   int p = 0;
   for (size_t first = 0; first < (size_t)nbatch && ok; first += piece, p++) {
     const int b = (int)(d->pipe_seq++ & 1u);
@@ -517,6 +539,8 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
     d->pipe_used[b] = true;
   }
   // the caller's stream completes when the last copies have landed
+  d->stream = user;
+  d->stream_dirty = false;
   for (int b = 0; b < 2 && ok; b++) {
     if (d->pipe_used[b]) ok = ok && check(d, cudaStreamWaitEvent(d->stream, d->ev_out[b], 0), "join");
   }
