@@ -178,11 +178,11 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   ok = ok && devAlloc(d, &d->d_model, (size_t)H.bytes, "cudaMalloc(model)");
   ok = ok && check(d, cudaMemcpy(d->d_model, blob.data(), (size_t)H.bytes, cudaMemcpyHostToDevice),
                    "cudaMemcpy(model)");
-  // intermediates live per chunk of states: at most 2^20 states and at most ~16 GB (2^20 humanoid states
-  // are one chunk of 14.5 GB)
+  // intermediates live per chunk of states: at most 2^20 states and at most ~20 GB (2^20 humanoid states
+  // are one chunk of 16.3 GB)
   {
     const double bytes_per_state = 8.0 * H.nscratch + 4.0 * (mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1);
-    long long chunk = (long long)(16.0e9 / bytes_per_state);
+    long long chunk = (long long)(20.0e9 / bytes_per_state);
     if (chunk > (1LL << 20)) chunk = 1LL << 20;
     if (chunk > d->stride) chunk = d->stride;
     chunk &= ~127LL;
