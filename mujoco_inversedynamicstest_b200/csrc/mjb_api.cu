@@ -131,6 +131,8 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   {
     const mjbHdr* H0 = reinterpret_cast<const mjbHdr*>(blob.data());
     if (H0->sensor_post) outmask |= mjbOUT_RNEPOST;   // accelerometer / force / torque / frame*acc sensors
+    // touch sensors walk the contact list and the contact rows' forces: those outputs are their input
+    if (H0->sensor_touch) outmask |= mjbOUT_COUNTS | mjbOUT_CONTACT | mjbOUT_EFC;
   }
   if (outmask & mjbOUT_RNEPOST) {
     // constraint forces of spatial tendons travel as body wrenches here but are not part of the

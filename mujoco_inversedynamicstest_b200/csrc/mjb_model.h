@@ -40,6 +40,7 @@
   X(dof_Madr, nv)                \
   X(dof_simplenum, nv)           \
   X(site_bodyid, nsite)          \
+  X(site_type, nsite)            \
   X(geom_type, ngeom)            \
   X(geom_bodyid, ngeom)          \
   X(tendon_adr, ntendon)         \
@@ -103,6 +104,7 @@
   X(geom_quat, ngeom, 4)          \
   X(site_pos, nsite, 3)           \
   X(site_quat, nsite, 4)          \
+  X(site_size, nsite, 3)          \
   X(tendon_range, ntendon, 2)     \
   X(tendon_margin, ntendon, 1)    \
   X(tendon_stiffness, ntendon, 1) \
@@ -183,7 +185,7 @@ enum {
 enum { MJB_SEN_TYPE = 0, MJB_SEN_DATATYPE, MJB_SEN_OBJTYPE, MJB_SEN_OBJID, MJB_SEN_REFTYPE, MJB_SEN_REFID,
        MJB_SEN_DIM, MJB_SEN_ADR, MJB_SEN_NI };
 // mjtSensor / mjtObj / mjtDataType values restated (include/mujoco/mjmodel.h)
-enum { MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
+enum { MJB_SENS_TOUCH = 0, MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
        MJB_SENS_TORQUE = 5, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
        MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_JOINTLIMITPOS = 19,
        MJB_SENS_JOINTLIMITVEL = 20, MJB_SENS_JOINTLIMITFRC = 21, MJB_SENS_TENDONLIMITPOS = 22,
@@ -284,6 +286,8 @@ typedef struct mjbHdr_ {
   int32_t nsite;
   int32_t nmocap;
   int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
+  int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
+  int32_t pad0;
   double timestep, impratio;
   double gravity[3];
   double pad1;

@@ -3115,6 +3115,99 @@ MJB_HD inline void subtree_velocities(Ctx& c) {
   }
 }
 
+// mju_rayGeom for the site shapes of touch sensors (engine_ray.c:37-52, 105-128, 222-440, 818-843):
+// distance along the ray pnt + x*vec to a sphere / capsule / ellipsoid / cylinder / box at
+// (pos, mat) with the given size, -1 without intersection.
+MJB_DI double ray_quad(double a, double b, double cc, double* x) {
+  double det = b*b - a*cc;
+  if (det < MJB_MINVAL) { x[0] = -1; x[1] = -1; return -1; }
+  det = sqrt(det);
+  x[0] = (-b - det)/a;
+  x[1] = (-b + det)/a;
+  return x[0] >= 0 ? x[0] : (x[1] >= 0 ? x[1] : -1.0);
+}
+MJB_DI double ray_sphere(const double* pos, double dist_sqr, const double* pnt, const double* vec) {
+  const double dif[3] = {pnt[0] - pos[0], pnt[1] - pos[1], pnt[2] - pos[2]};
+  const double a = vec[0]*vec[0] + vec[1]*vec[1] + vec[2]*vec[2];
+  const double b = vec[0]*dif[0] + vec[1]*dif[1] + vec[2]*dif[2];
+  const double cc = dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] - dist_sqr;
+  double xx[2];
+  return ray_quad(a, b, cc, xx);
+}
+MJB_HD inline double ray_geom(const double* pos, const double* mat, const double* size, const double* pnt,
+                              const double* vec, int type) {
+  if (type == MJB_GEOM_SPHERE) return ray_sphere(pos, size[0]*size[0], pnt, vec);
+  // ray_map: point and direction in the shape's frame
+  const double dif[3] = {pnt[0] - pos[0], pnt[1] - pos[1], pnt[2] - pos[2]};
+  double lp[3], lv[3], xx[2];
+  mulMatTVec3(lp, mat, dif);
+  mulMatTVec3(lv, mat, vec);
+  if (type == MJB_GEOM_ELLIPSOID) {
+    const double s[3] = {1/(size[0]*size[0]), 1/(size[1]*size[1]), 1/(size[2]*size[2])};
+    const double a = s[0]*lv[0]*lv[0] + s[1]*lv[1]*lv[1] + s[2]*lv[2]*lv[2];
+    const double b = s[0]*lv[0]*lp[0] + s[1]*lv[1]*lp[1] + s[2]*lv[2]*lp[2];
+    const double cc = s[0]*lp[0]*lp[0] + s[1]*lp[1]*lp[1] + s[2]*lp[2]*lp[2] - 1;
+    return ray_quad(a, b, cc, xx);
+  }
+  double x = -1, sol;
+  if (type == MJB_GEOM_CAPSULE) {
+    const double ssz = size[0] + size[1];
+    if (ray_sphere(pos, ssz*ssz, pnt, vec) < 0) return -1;
+    double a = lv[0]*lv[0] + lv[1]*lv[1];
+    double b = lv[0]*lp[0] + lv[1]*lp[1];
+    double cc = lp[0]*lp[0] + lp[1]*lp[1] - size[0]*size[0];
+    sol = ray_quad(a, b, cc, xx);
+    if (sol >= 0 && fabs(lp[2] + sol*lv[2]) <= size[1]) x = sol;
+    a = lv[0]*lv[0] + lv[1]*lv[1] + lv[2]*lv[2];
+    for (int cap = 1; cap >= -1; cap -= 2) {          // top cap, then bottom cap
+      const double ld[3] = {lp[0], lp[1], lp[2] - cap*size[1]};
+      b = lv[0]*ld[0] + lv[1]*ld[1] + lv[2]*ld[2];
+      cc = ld[0]*ld[0] + ld[1]*ld[1] + ld[2]*ld[2] - size[0]*size[0];
+      ray_quad(a, b, cc, xx);
+      for (int i = 0; i < 2; i++) {
+        const double z = lp[2] + xx[i]*lv[2];
+        if (xx[i] >= 0 && (cap > 0 ? z >= size[1] : z <= -size[1]) && (x < 0 || xx[i] < x)) x = xx[i];
+      }
+    }
+    return x;
+  }
+  if (type == MJB_GEOM_CYLINDER) {
+    if (ray_sphere(pos, size[0]*size[0] + size[1]*size[1], pnt, vec) < 0) return -1;
+    if (fabs(lv[2]) > MJB_MINVAL) {
+      for (int side = -1; side <= 1; side += 2) {
+        sol = (side*size[1] - lp[2])/lv[2];
+        if (sol >= 0) {
+          const double p0 = lp[0] + sol*lv[0], p1 = lp[1] + sol*lv[1];
+          if (p0*p0 + p1*p1 <= size[0]*size[0] && (x < 0 || sol < x)) x = sol;
+        }
+      }
+    }
+    const double a = lv[0]*lv[0] + lv[1]*lv[1];
+    const double b = lv[0]*lp[0] + lv[1]*lp[1];
+    const double cc = lp[0]*lp[0] + lp[1]*lp[1] - size[0]*size[0];
+    sol = ray_quad(a, b, cc, xx);
+    if (sol >= 0 && fabs(lp[2] + sol*lv[2]) <= size[1] && (x < 0 || sol < x)) x = sol;
+    return x;
+  }
+  if (type == MJB_GEOM_BOX) {
+    if (ray_sphere(pos, size[0]*size[0] + size[1]*size[1] + size[2]*size[2], pnt, vec) < 0) return -1;
+    for (int i = 0; i < 3; i++) {
+      if (fabs(lv[i]) > MJB_MINVAL) {
+        const int f0 = i == 0 ? 1 : 0, f1 = i == 2 ? 1 : 2;
+        for (int side = -1; side <= 1; side += 2) {
+          sol = (side*size[i] - lp[i])/lv[i];
+          if (sol >= 0) {
+            const double p0 = lp[f0] + sol*lv[f0], p1 = lp[f1] + sol*lv[f1];
+            if (fabs(p0) <= size[f0] && fabs(p1) <= size[f1] && (x < 0 || sol < x)) x = sol;
+          }
+        }
+      }
+    }
+    return x;
+  }
+  return -1;
+}
+
 // the first limit row of a joint / tendon as the limit sensors see it (engine_sensor.c:293-313,
 // 600-617, 837-855): value and velocity of the coordinate in, (pos - margin, vel, force) of the row
 // out; false when neither side is active. Same arithmetic as scalar_row, nothing is emitted.
@@ -3148,7 +3241,40 @@ MJB_HD inline void sensors(Ctx& c) {
     const int type = si[MJB_SEN_TYPE], objtype = si[MJB_SEN_OBJTYPE], objid = si[MJB_SEN_OBJID];
     const int reftype = si[MJB_SEN_REFTYPE], refid = si[MJB_SEN_REFID];
     double v[4] = {0, 0, 0, 0};
-    if (type == MJB_SENS_JOINTPOS) {
+    if (type == MJB_SENS_TOUCH) {
+      // sum of the normal forces of the contacts of the site's body whose normal ray meets the site
+      // volume (engine_sensor.c:750-793); mj_contactForce's normal component is the row force
+      // (frictionless, elliptic) or the sum of the pyramid's row forces (engine_support.c:1459-1490)
+      double pos[3], quat[4], m[9];
+      const int body = sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      quat2Mat(m, quat);
+      const int* geom_bodyid = MI(geom_bodyid);
+      int ncon = c.isc[MJB_ISC_NCON * MJB_LS];
+      if (ncon > c.nconmax) ncon = c.nconmax;
+      double total = 0;
+      for (int k = 0; k < ncon; k++) {
+        const int adr = c.out.contact_info[(size_t)(3*k + 2)*N + c.s];
+        if (adr < 0) continue;
+        const int b1 = geom_bodyid[c.out.contact_geom[(size_t)(2*k)*N + c.s]];
+        const int b2 = geom_bodyid[c.out.contact_geom[(size_t)(2*k + 1)*N + c.s]];
+        if (body != b1 && body != b2) continue;
+        const int dim = c.out.contact_info[(size_t)(3*k)*N + c.s];
+        const int nrow = (dim > 1 && H.cone == 0) ? 2*(dim - 1) : 1;
+        if (adr + nrow > c.njmax) continue;
+        double fn = 0;
+        for (int r = 0; r < nrow; r++) fn += c.out.efc_num[(size_t)(8*(adr + r) + 6)*N + c.s];
+        if (fn <= 0) continue;
+        double ray[3], p[3];
+        for (int j = 0; j < 3; j++) {
+          ray[j] = c.out.contact_num[(size_t)(13*k + 4 + j)*N + c.s]*fn;
+          p[j] = c.out.contact_num[(size_t)(13*k + 1 + j)*N + c.s];
+        }
+        normalize3(ray);
+        if (body == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+        if (ray_geom(pos, m, MD(site_size) + 3*objid, p, ray, MI(site_type)[objid]) >= 0) total += fn;
+      }
+      v[0] = total;
+    } else if (type == MJB_SENS_JOINTPOS) {
       v[0] = QPOS(MI(jnt_qposadr)[objid]);
     } else if (type == MJB_SENS_JOINTVEL) {
       v[0] = QVEL(MI(jnt_dofadr)[objid]);

@@ -216,10 +216,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     }
   }
   // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
-  // whose inputs exist on this path are evaluated by the sensor kernel; the others (touch, rays,
-  // camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
+  // whose inputs exist on this path are evaluated by the sensor kernel; the others (rangefinder,
+  // magnetometer, camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
-  bool sensor_post = false, sensor_subtreevel = false;
+  bool sensor_post = false, sensor_subtreevel = false, sensor_touch = false;
   std::vector<int> sensor_int;
   std::vector<double> sensor_cutoff;
   for (int i = 0; i < m->nsensor && sensors; i++) {
@@ -248,6 +248,14 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         break;
       case mjSENS_VELOCIMETER: case mjSENS_GYRO:
         ok = true; break;
+      case mjSENS_TOUCH:
+        {
+          const int st = m->site_type[m->sensor_objid[i]];
+          ok = st == mjGEOM_SPHERE || st == mjGEOM_CAPSULE || st == mjGEOM_ELLIPSOID || st == mjGEOM_CYLINDER ||
+               st == mjGEOM_BOX;
+          sensor_touch = true;
+        }
+        break;
       case mjSENS_SUBTREELINVEL: case mjSENS_SUBTREEANGMOM:
         ok = true; sensor_subtreevel = true; break;
       case mjSENS_ACCELEROMETER:
@@ -651,6 +659,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nsite = m->nsite;
   H.nmocap = m->nmocap;
   H.sensor_subtreevel = sensor_subtreevel ? 1 : 0;
+  H.sensor_touch = sensor_touch ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 

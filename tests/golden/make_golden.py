@@ -53,6 +53,9 @@ CASES = {
     "mocap": ("repo:tests/golden/models/mocap.xml", {}, 128, (0.0, 0.6), 16, 96),
     # every sensor type evaluated on the device (mj_sensorPos / Vel / Acc); sensordata is dumped too
     "sensors": ("repo:tests/golden/models/sensors.xml", {}, 256, (0.0, 0.6), 16, 96),
+    # touch sensors (contact list + contact-row forces + ray / site-volume tests), both cones
+    "touch": ("repo:tests/golden/models/touch.xml", {}, 256, (0.0, 0.35), 24, 160),
+    "touch_elliptic": ("repo:tests/golden/models/touch.xml", {"cone": 1}, 256, (0.0, 0.35), 24, 160),
 }
 
 

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap"]
+         "sensors", "mocap", "touch", "touch_elliptic"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -191,6 +191,20 @@ def test_golden_per_state_mocap_poses():
     bd.inverse()
     nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
     assert nviol == 0, (nviol, worst)
+
+
+@pytest.mark.parametrize("case", ["touch", "touch_elliptic"])
+def test_golden_touch_sensors(case):
+    """touch sensors (engine_sensor.c:750-793): site volumes of every shape, both cones; the contact and
+    efc outputs they read are switched on by mjb_makeData itself."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, case, True, 0)
+    assert nbad == 0
+    got = bd.sensordata()
+    nviol, worst = util.sensor_violations(model, got, ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    np.testing.assert_array_equal(got > 0, ref["sensordata"] > 0)
+    assert (ref["sensordata"] > 0).mean() > 0.05
 
 
 def test_golden_sensordata():

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation libr
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap"]
+         "sensors", "mocap", "touch", "touch_elliptic"]
 
 
 def _run(name):
@@ -148,10 +148,15 @@ def test_per_state_mocap_poses():
     assert nviol == 0, (nviol, worst)
 
 
-def test_sensordata():
+@pytest.mark.parametrize("case", ["sensors", "touch", "touch_elliptic"])
+def test_sensordata(case):
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
-    every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml)."""
-    model, out, ref = _run("sensors")
+    every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml;
+    touch.xml: touch sensors with site volumes of every shape, both cones)."""
+    model, out, ref = _run(case)
+    if case != "sensors":
+        # a touch reading is zero exactly where the reference's is (same contacts inside the zone)
+        np.testing.assert_array_equal(out["sensordata"] > 0, ref["sensordata"] > 0)
     nviol, worst = util.sensor_violations(model, out["sensordata"], ref["sensordata"])
     assert nviol == 0, (nviol, worst)
     # position-stage sensors repeat the bit-identical kinematics of the CPU build
@@ -189,7 +194,7 @@ def test_upload_rejections():
     # a sensor type that is not evaluated on the device is refused unless sensors are disabled
     sm = mjb.Model.from_mjb(util.golden("sensors")[0])
     assert len(emu.candidates(sm)) > 0
-    sm.array("sensor_type")[0] = 0              # mjSENS_TOUCH
+    sm.array("sensor_type")[0] = 7              # mjSENS_RANGEFINDER
     with pytest.raises(RuntimeError, match="sensor 0"):
         emu.candidates(sm)
     sm.set_opt_int("disableflags", 1 << 12)     # mjDSBL_SENSOR
