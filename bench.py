@@ -391,7 +391,8 @@ def main():
             "unit": "GB/s", "frac": per_gpu_rate * alg_bytes * 1e-9 / peaks["hbm_gbs"],
             "traffic": (dram_per_state * n) if dram_per_state else None,
             "traffic_unit": "DRAM bytes per step per GPU (ncu dram__bytes_read+write, profiles/)",
-            "bytes_per_state": alg_bytes, "peak_source": peak_src}
+            "bytes_per_state": alg_bytes, "peak_source": peak_src,
+            "kernel": "the whole step (all phase kernels; per-kernel figures under `kernels`)"}
         line = {
             "metric": "mj_inverse states/sec (humanoid, fp64)", "value": value, "unit": "states/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
