@@ -190,6 +190,19 @@ MJB_API int mjb_phaseTimes(mjbData* d, double* ms, int n);
  * (items, contacts, overflow flag, slots); -1 if that path is not in use */
 MJB_API int mjb_debugQueue(mjbData* d, int* out4);
 
+/* Model specialisation. mjb_specialize compiles the phase kernels FOR THIS MODEL (NVRTC, sm_100a; the
+ * model's tables become compile-time constants and the loops over bodies / dofs / candidate pairs are
+ * expanded) and switches this mjbData to them; the compiled module is cached on disk
+ * (<directory of libmjb.so>/jitcache or $MJB_JIT_CACHE). Results are those of the generic kernels up to
+ * floating-point contraction. Returns 0, or -1 with a message when the model is too large to expand or
+ * NVRTC / the driver API cannot be loaded -- the generic kernels then stay in use. The environment
+ * variable MJB_JIT=1 makes mjb_makeData call it for every model.
+ * mjb_precompile fills the cache without a GPU (build step); info receives "<key> compiled|cached <s>". */
+MJB_API int mjb_specialize(mjbData* d, char* err, int err_sz);
+MJB_API int mjb_specialized(const mjbData* d);
+MJB_API int mjb_specializeInfo(const mjbData* d, char* key, int key_sz, int* from_cache, double* compile_seconds);
+MJB_API int mjb_precompile(const mjModel* m, char* info, int info_sz);
+
 /* wait for the stream */
 MJB_API int mjb_synchronize(mjbData* d);
 

@@ -43,6 +43,10 @@ SIGNATURES = {
     "mjb_debugQueue": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "mjb_phaseTiming": (None, [c_void_p, c_int]),
     "mjb_phaseTimes": (c_int, [c_void_p, ctypes.POINTER(c_double), c_int]),
+    "mjb_specialize": (c_int, [c_void_p, c_char_p, c_int]),
+    "mjb_specialized": (c_int, [c_void_p]),
+    "mjb_specializeInfo": (c_int, [c_void_p, c_char_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double)]),
+    "mjb_precompile": (c_int, [c_void_p, c_char_p, c_int]),
     "mjb_synchronize": (c_int, [c_void_p]),
     "mjb_fp64PeakTflops": (c_double, [c_int]),
     "mjb_loadModel": (c_void_p, [c_char_p, c_char_p, c_int]),

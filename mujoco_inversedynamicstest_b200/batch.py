@@ -212,6 +212,22 @@ class BatchData:
         self.nbatch = n
         return rc
 
+    def specialize(self):
+        """mjb_specialize: compile (NVRTC) and switch to the kernels specialised for this model.
+        Returns a dict with the cache key, whether the cubin came from the cache and the compile time;
+        raises MjbError when the model cannot be specialised (the generic kernels stay in use)."""
+        err = ctypes.create_string_buffer(8192)
+        if lib().mjb_specialize(self._d, err, 8192):
+            raise MjbError(err.value.decode())
+        key = ctypes.create_string_buffer(64)
+        cached, secs = ctypes.c_int(), ctypes.c_double()
+        lib().mjb_specializeInfo(self._d, key, 64, ctypes.byref(cached), ctypes.byref(secs))
+        return {"key": key.value.decode(), "from_cache": bool(cached.value), "compile_seconds": secs.value}
+
+    @property
+    def specialized(self):
+        return bool(lib().mjb_specialized(self._d))
+
     def kernel_launches(self):
         return int(lib().mjb_kernelLaunches(self._d))
 

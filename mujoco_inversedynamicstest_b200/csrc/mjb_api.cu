@@ -10,6 +10,7 @@
 
 #include "../../include/mjb.h"
 #include "mjb_kernels.cuh"
+#include "mjb_jit.h"
 #include "mjb_upload.h"
 
 struct mjbData_ {
@@ -21,6 +22,9 @@ struct mjbData_ {
   int nconmax = 0, njmax = 0;
   int last_nbatch = 0;
   mjbHdr hdr;                  // host copy of the model header
+  std::vector<unsigned char> blob;   // host copy of the model blob (input of mjb_specialize)
+  mjb::SpecKernels spec;       // kernels compiled for this model (mjb_specialize), if any
+  bool spec_on = false;
   std::vector<int> cand;       // host copy of candidate (g1, g2, func)
   unsigned char* d_model = nullptr;
   int model_bytes = 0;
@@ -162,6 +166,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   d->nbatch_max = nbatch_max;
   d->stride = ((long long)nbatch_max + 31) & ~31LL;   // keep every row 256-byte aligned
   std::memcpy(&d->hdr, blob.data(), sizeof(mjbHdr));
+  d->blob = blob;
   const mjbHdr& H = d->hdr;
   d->nconmax = nconmax > 0 ? nconmax : 64;
   d->njmax = njmax > 0 ? njmax : 256;
@@ -293,13 +298,57 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     mjb_deleteData(d);
     return fail("mjb_makeData: " + e);
   }
+  // MJB_JIT=1: specialise every eligible model at creation (otherwise on request, mjb_specialize).
+  // A model that cannot be specialised keeps the generic kernels; the reason stays in mjb_lastError.
+  if (const char* jit = std::getenv("MJB_JIT")) {
+    if (jit[0] && jit[0] != '0') mjb_specialize(d, nullptr, 0);
+  }
   return d;
+}
+
+int mjb_specialize(mjbData* d, char* err, int err_sz) {
+  if (d->spec_on) return 0;
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  std::string msg;
+  if (!mjb::jitSpecialize(d->blob, d->spec, msg)) {
+    d->error = "mjb_specialize: " + msg;
+    if (err && err_sz > 0) std::snprintf(err, err_sz, "%s", d->error.c_str());
+    return -1;
+  }
+  d->spec_on = true;
+  return 0;
+}
+
+int mjb_specialized(const mjbData* d) { return d->spec_on ? 1 : 0; }
+
+int mjb_specializeInfo(const mjbData* d, char* key, int key_sz, int* from_cache, double* compile_seconds) {
+  if (!d->spec_on) return -1;
+  if (key && key_sz > 0) std::snprintf(key, key_sz, "%s", d->spec.key.c_str());
+  if (from_cache) *from_cache = d->spec.from_cache ? 1 : 0;
+  if (compile_seconds) *compile_seconds = d->spec.compile_seconds;
+  return 0;
+}
+
+int mjb_precompile(const mjModel* m, char* info, int info_sz) {
+  std::vector<unsigned char> blob;
+  std::string msg, key;
+  bool cached = false;
+  double seconds = 0;
+  if (!m || !mjb::buildModelBlob(m, blob, msg) || !mjb::jitCompileToCache(blob, key, cached, seconds, msg)) {
+    if (info && info_sz > 0) std::snprintf(info, info_sz, "%s", msg.c_str());
+    return -1;
+  }
+  if (info && info_sz > 0) {
+    std::snprintf(info, info_sz, "%s %s %.1f s", key.c_str(), cached ? "cached" : "compiled", seconds);
+  }
+  return 0;
 }
 
 void mjb_deleteData(mjbData* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   if (d->fd) mjb_deleteData(d->fd);
+  if (d->spec_on) mjb::jitUnload(d->spec);
   cudaFree(d->d_fd_out);
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
   cudaFree(d->d_cq); cudaFree(d->d_items); cudaFree(d->d_item_con); cudaFree(d->d_contacts);
@@ -442,7 +491,8 @@ bool launchRange(mjbData* d, long long first, long long count) {
     timer.mark = [](void* ctx, int phase, cudaEvent_t b, cudaEvent_t e) {
       static_cast<mjbData*>(ctx)->marks.push_back({phase, b, e});
     };
-    if (!check(d, mjb::launch_inverse(a, d->stream, &launches, d->phase_timing ? &timer : nullptr),
+    if (!check(d, mjb::launch_inverse(a, d->stream, &launches, d->phase_timing ? &timer : nullptr,
+                                      d->spec_on ? &d->spec : nullptr),
                "launch mj_inverse kernels")) return false;
     d->kernel_launches += launches;
   }

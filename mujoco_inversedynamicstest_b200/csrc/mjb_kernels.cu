@@ -12,6 +12,7 @@
 // blob is staged once per CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier)
 // and read through warp-uniform shared-memory broadcasts.
 #include "mjb_kernels.cuh"
+#include "mjb_jit.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -816,6 +817,15 @@ cudaError_t launch_smooth(const LaunchArgs& a, cudaStream_t stream) {
                          : launch_phase(smooth_kernel<false, false>, a, sm, cap, stream, kSmoothThreads);
 }
 
+// specialised kernel with the launch geometry of launch_phase
+cudaError_t launch_spec(void* fn, const LaunchArgs& args, size_t smem, int ctas_per_sm, cudaStream_t stream,
+                        int threads = kThreads) {
+  int grid = (args.chunk_n + threads - 1) / threads;
+  const int cap = kSMs * ctas_per_sm;
+  if (grid > cap) grid = cap;
+  return jitLaunch(fn, grid, threads, smem, stream, args);
+}
+
 struct PhaseScope {   // records begin/end events around one kernel launch when timing is on
   const PhaseTimer* t; cudaStream_t s; int phase; cudaEvent_t b;
   PhaseScope(const PhaseTimer* t_, cudaStream_t s_, int phase_) : t(t_), s(s_), phase(phase_), b(nullptr) {
@@ -828,12 +838,15 @@ struct PhaseScope {   // records begin/end events around one kernel launch when 
 }  // namespace
 
 cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* launches,
-                           const PhaseTimer* timer) {
+                           const PhaseTimer* timer, const SpecKernels* spec) {
   *launches = 0;
   if (args.chunk_n <= 0) return cudaSuccess;
   const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
   const bool in_smem = args.model_in_smem != 0;
   const bool want_inertia = args.out.qM || args.out.qLD || args.out.qLDiagInv;
+  const bool spec_smooth = spec && spec->smooth, spec_inertia = spec && spec->inertia;
+  const bool spec_scan = spec && spec->contact_scan, spec_backward = spec && spec->backward;
+  const size_t spec_smooth_smem = sizeof(double) * MJB_SM_SLOTS * kSmoothThreads;
   cudaError_t e;
   if (args.qacc_discrete) {
     // mjENBL_INVDISCRETE (engine_inverse.c:227-234): position stage + factorisation on the given
@@ -842,10 +855,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     pre.qacc_discrete = nullptr;
     pre.has_contacts = 0;
     { PhaseScope ps(timer, stream, kPhaseSmooth);
-    e = launch_smooth(pre, stream); }
+    e = spec_smooth ? launch_spec(spec->smooth, pre, spec_smooth_smem, 2 * MJB_CTAS_SMOOTH, stream, spec->smooth_threads)
+                    : launch_smooth(pre, stream); }
     if (e != cudaSuccess) return e;
     { PhaseScope ps(timer, stream, kPhaseInertia);
-    e = in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
+    e = spec_inertia ? launch_spec(spec->inertia, pre, 0, 8, stream)
+        : in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
                 : launch_phase(inertia_kernel<false>, pre, 0, 8, stream); }
     if (e != cudaSuccess) return e;
     { PhaseScope ps(timer, stream, kPhaseDiscrete);
@@ -857,24 +872,27 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     post.qacc = args.qacc_discrete;
     post.qacc_discrete = nullptr;
     int n2 = 0;
-    e = launch_inverse(post, stream, &n2, timer);
+    e = launch_inverse(post, stream, &n2, timer, spec);
     *launches += n2;
     return e;
   }
   { PhaseScope ps(timer, stream, kPhaseSmooth);
-  e = launch_smooth(args, stream); }
+  e = spec_smooth ? launch_spec(spec->smooth, args, spec_smooth_smem, 2 * MJB_CTAS_SMOOTH, stream, spec->smooth_threads)
+                  : launch_smooth(args, stream); }
   if (e != cudaSuccess) return e;
   ++*launches;
   if (want_inertia) {
     PhaseScope ps(timer, stream, kPhaseInertia);
-    e = in_smem ? launch_phase(inertia_kernel<true>, args, smem, 8, stream)
+    e = spec_inertia ? launch_spec(spec->inertia, args, 0, 8, stream)
+        : in_smem ? launch_phase(inertia_kernel<true>, args, smem, 8, stream)
                 : launch_phase(inertia_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }
   if (args.has_contacts) {
     { PhaseScope ps(timer, stream, kPhaseScan);
-    e = in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
+    e = spec_scan ? launch_spec(spec->contact_scan, args, 0, 8, stream)
+        : in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
                 : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream); }
     if (e != cudaSuccess) return e;
 // The contact kernel reads the model tables through L1 instead of a shared-memory copy: its lanes
@@ -914,7 +932,9 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     *launches += 2;
   }
   PhaseScope ps_backward(timer, stream, kPhaseBackward);
-  if (args.has_gravcomp) {
+  if (spec_backward) {
+    e = launch_spec(spec->backward, args, 0, 8, stream);
+  } else if (args.has_gravcomp) {
     e = in_smem ? launch_phase(backward_kernel<true, true>, args, smem, 8, stream)
                 : launch_phase(backward_kernel<false, true>, args, 0, 8, stream);
   } else {

@@ -1,0 +1,65 @@
+// Launch arguments shared by the precompiled sm_100a kernels (mjb_kernels.cu), the model-specialised
+// kernels compiled at run time (mjb_spec_kernels.cuh) and the C-ABI host code. Plain pointers and
+// sizes only; no dependency on the CUDA runtime headers, so NVRTC can compile it as is.
+#ifndef MJB_LAUNCH_H_
+#define MJB_LAUNCH_H_
+
+#include "mjb_model.h"
+#include "mjb_pipeline.h"
+
+namespace mjb {
+
+// launch geometry: 128-thread CTAs (4 warps), grids capped at a multiple of the 148 SMs; every
+// kernel walks its chunk of states with a block-stride loop
+constexpr int kThreads = 128;
+constexpr int kSMs = 148;
+#ifndef MJB_LISTCAP
+#define MJB_LISTCAP 24   // measured: 24 -> 5.16 ms, 16 -> 5.45, 32 -> 5.96 (2^20 humanoid states)
+#endif
+constexpr int kListCap = MJB_LISTCAP;                  // per-lane survivor list of the contact kernel
+
+// Item-parallel contact phase: global lists of one chunk. Survivors of the bounding-sphere scan
+// ("items") and the contacts they yield are appended with warp-aggregated atomics; a state finds its
+// items through MJB_ISC_ITEMBASE / NSURV and an item its contacts through ItemCon, so placement
+// order does not matter. If a list would overflow, `overflow` is raised and the chunk is handled
+// by the pooled contact kernel instead (every kernel of either path checks the flag first).
+struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; };
+struct ContactItem { int state; int ci; };          // chunk-local state, candidate pair
+struct ItemCon { int base; int count; };            // the item's contacts: contacts[base .. base+count)
+struct ContactRec {
+  int state, ci, k, efc_address;                    // k: contact index in its state; efc_address or -1
+  double dist, pos[3], frame[6];                    // normal, tangent (third axis is their cross product)
+};
+
+
+struct LaunchArgs {
+  const unsigned char* model;   // device blob (mjbHdr + sections)
+  int model_bytes;
+  int model_in_smem;            // 1: stage the blob into shared memory with a TMA bulk copy
+  const double* qpos;           // [nq][stride]
+  const double* qvel;           // [nv][stride]
+  const double* qacc;           // [nv][stride]
+  double* qacc_discrete;        // [nv][stride] continuous-time qacc (mjENBL_INVDISCRETE), or null
+  double* scratch;              // [chunk_stride/32][nscratch][32]  intermediates of one chunk of states
+  int* iscratch;                // [chunk_stride/32][niscratch][32]
+  int nscratch, niscratch;      // slots per state: mjbHdr::nscratch, MJB_ISC_MASK + ceil(ncand/32) + 1
+  long long chunk_stride;       // states per chunk (multiple of 32)
+  long long chunk_start;        // first state of the chunk
+  int chunk_n;                  // states in the chunk
+  long long stride;             // row stride of every state-indexed input/output array
+  int nconmax, njmax;
+  ContactQueue* cq;             // item-parallel contact path (null: pooled kernel only)
+  ContactItem* items; ItemCon* item_con; ContactRec* contacts;
+  int* slot_rec;                // slot (state's first slot + k) -> index into contacts
+  int items_cap, contacts_cap;
+  int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
+  int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
+  int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
+  int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
+  int skip_sensors;             // mj_inverseSkip(skipsensor = 1): leave sensordata as it is
+  Outputs out;
+};
+
+}  // namespace mjb
+
+#endif  // MJB_LAUNCH_H_

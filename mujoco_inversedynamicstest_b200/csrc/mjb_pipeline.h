@@ -23,7 +23,13 @@
 #include "mjb_model.h"
 
 #if defined(__CUDACC__)
+#ifdef MJB_SPECIALIZED
+// specialised build: every function that takes the per-state context is inlined, so that the
+// context stays in registers and its table pointers stay compile-time constants in the callee
+#define MJB_HD __host__ __device__ __attribute__((always_inline))
+#else
 #define MJB_HD __host__ __device__
+#endif
 // rarely taken, code-heavy leaf paths (pow, atan2) are kept out of line to keep the phase kernels
 // small; only functions of scalars qualify (an out-of-line call taking Ctx& would force the whole
 // context into local memory: measured +45% on the smooth kernel)
@@ -48,7 +54,35 @@
 #define MJB_WARP_MAX(x) (x)
 #endif
 
+// Model-specialised build (csrc/mjb_spec_kernels.h, compiled per model at mjb_makeData by NVRTC): the
+// model blob is a `__device__ const` array in the translation unit, so every table look-up whose
+// index is a compile-time constant folds to an immediate. The loops over bodies are then expanded
+// at compile time (MJB_BODY_LOOP_*: template recursion calling the loop body with a constant
+// index; the optimiser's own `#pragma unroll` gives up on bodies of this size) and the small
+// model-bounded inner loops (joints / dofs / geoms of one body, tendon terms) carry MJB_UNROLL.
+// In the generic build both are plain loops.
+#ifdef MJB_SPECIALIZED
+#define MJB_UNROLL _Pragma("unroll")
+#define MJB_BODY_LAMBDA __attribute__((always_inline))   // every expansion of a loop body is inlined
+#else
+#define MJB_UNROLL
+#define MJB_BODY_LAMBDA
+#endif
+
 namespace mjb {
+
+#ifdef MJB_SPECIALIZED
+template <int B, int E, typename F>
+MJB_DI void static_for_up(F& f) { if constexpr (B < E) { f(B); static_for_up<B + 1, E>(f); } }
+template <int B, int E, typename F>
+MJB_DI void static_for_down(F& f) { if constexpr (B > E) { f(B); static_for_down<B - 1, E>(f); } }
+// body(b) for b = first .. n-1 / b = n-1 .. first ; nspec is the compile-time value of n
+#define MJB_BODY_LOOP_UP(body, first, n, nspec) static_for_up<first, nspec>(body)
+#define MJB_BODY_LOOP_DOWN(body, first, n, nspec) static_for_down<(nspec) - 1, (first) - 1>(body)
+#else
+#define MJB_BODY_LOOP_UP(body, first, n, nspec) for (int b_ = (first); b_ < (n); b_++) body(b_)
+#define MJB_BODY_LOOP_DOWN(body, first, n, nspec) for (int b_ = (n) - 1; b_ >= (first); b_--) body(b_)
+#endif
 
 // status bits (mirrored in include/mjb.h)
 enum { kStatusBadQpos = 1, kStatusBadQvel = 2, kStatusBadQacc = 4, kStatusContactFull = 8,
@@ -645,10 +679,12 @@ MJB_HD inline void tendon_kinematics(Ctx& c) {
   const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
   const int* tendon_active = MI(tendon_active);
   const double* wrap_prm = MD(wrap_prm);
+  MJB_UNROLL
   for (int t = 0; t < H.ntendon; t++) {
     const int adr = tendon_adr[t], num = tendon_num[t];
     double len = 0, vel = 0, acc = 0;
     if (wrap_type[adr] == MJB_WRAP_JOINT) {
+      MJB_UNROLL
       for (int j = 0; j < num; j++) {
         const int k = wrap_objid[adr + j];
         len += wrap_prm[adr + j] * QPOS(jnt_qposadr[k]);
@@ -671,6 +707,7 @@ MJB_HD inline void tendon_apply(Ctx& c, int t, double f, double* qdst, bool pass
   if (MI(wrap_type)[adr] == MJB_WRAP_JOINT) {
     const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
     const double* wrap_prm = MD(wrap_prm);
+    MJB_UNROLL
     for (int j = 0; j < num; j++) AT(qdst, jnt_dofadr[wrap_objid[adr + j]]) += wrap_prm[adr + j]*f;
   } else if (kSpatial) {
     spatial_tendon_apply(c, t, f, passive);
@@ -689,6 +726,7 @@ MJB_HD inline void passive_tendons(Ctx& c) {
   const double* stiff = MD(tendon_stiffness); const double* damp = MD(tendon_damping);
   const double* ls = MD(tendon_lengthspring);
   double* L = SC(ten_length); double* V = SC(ten_velocity);
+  MJB_UNROLL
   for (int t = 0; t < H.ntendon; t++) {
     const double ks = stiff[t], kd = damp[t];
     if (ks == 0 && kd == 0) continue;
@@ -1000,6 +1038,7 @@ MJB_HD inline void tendon_friction_rows(Ctx& c) {
   const double* wrap_prm = MD(wrap_prm);
   double* V = SC(ten_velocity); double* A = SC(ten_acc);
   int row = H.ne_rows + H.nf_dof_rows;
+  MJB_UNROLL
   for (int t = 0; t < H.ntendon; t++) {
     if (tfl[t] > 0) {
       const double f = scalar_row(c, row++, MJB_CNSTR_FRICTION_TENDON, t, tsp + MJB_SP_N*t, 0, 0, tiw[t],
@@ -1025,6 +1064,7 @@ MJB_HD inline void tendon_limit_rows(Ctx& c) {
   const int* wrap_objid = MI(wrap_objid);
   const double* wrap_prm = MD(wrap_prm);
   double* L = SC(ten_length); double* V = SC(ten_velocity); double* A = SC(ten_acc);
+  MJB_UNROLL
   for (int t = 0; t < H.ntendon; t++) {
     if (!tendon_limited[t]) continue;
     const double value = AT(L, t), margin = tendon_margin[t];
@@ -1083,6 +1123,7 @@ MJB_HD inline void prefetch_body_inputs(Ctx& c, int b) {
   const int jntadr = MI(body_jntadr)[b], jntnum = MI(body_jntnum)[b];
   const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
   const int* jnt_dofnum = MI(jnt_dofnum_tab);
+  MJB_UNROLL
   for (int j = jntadr; j < jntadr + jntnum; j++) {
     const int nd = jnt_dofnum[j], qa = jnt_qposadr[j], da = jnt_dofadr[j];
     const int nq = nd == 6 ? 7 : (nd == 3 ? 4 : 1);
@@ -1105,6 +1146,7 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   const int* geom_store = MI(geom_store);
   const bool dump = c.out.scratch_dump != nullptr;
   const int g0 = body_geomadr[b], gn = body_geomnum[b];
+  MJB_UNROLL
   for (int g = g0; g < g0 + gn; g++) {
     const int store = dump ? 3 : geom_store[g];
     if (!store) continue;
@@ -1185,7 +1227,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
   int carry = 0;          // body whose pose / velocity / acceleration are in the carry slots
 
   if (nbody > 1) prefetch_body_inputs(c, 1);
-  for (int b = 1; b < nbody; b++) {
+  auto sweep_body = [&](const int b) MJB_BODY_LAMBDA {
     if (b + 1 < nbody) prefetch_body_inputs(c, b + 1);
     const int pid = body_parentid[b];
     const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
@@ -1236,8 +1278,10 @@ MJB_HD inline void forward_sweep(Ctx& c) {
         O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
         stc(org, 3*b, O, 3);
       }
+      MJB_UNROLL
       for (int j = 0; j < jntnum; j++) has_ball = has_ball || jnt_type[jntadr + j] == MJB_JNT_BALL;
 
+      MJB_UNROLL
       for (int j = 0; j < jntnum; j++) {
         const int jid = jntadr + j;
         const int qadr = jnt_qposadr[jid];
@@ -1332,6 +1376,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     } else if (has_ball) {
       // general path: finish the ball-joint cdofs with the final orientation, then run the dof
       // loop of mj_comVel over the body's dofs from scratch
+      MJB_UNROLL
       for (int j = 0; j < jntnum; j++) {
         const int jid = jntadr + j;
         if (jnt_type[jid] != MJB_JNT_BALL) continue;
@@ -1344,6 +1389,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
           stn(cdof, 6*(dadr + r), cd, 6);
         }
       }
+      MJB_UNROLL
       for (int j = 0; j < dofnum; j++) {
         const int jt = jnt_type[dof_jntid[bda + j]];
         if (jt == MJB_JNT_BALL) {
@@ -1427,7 +1473,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     CS(0) = pos[0]; CS(1) = pos[1]; CS(2) = pos[2];
     CS(3) = quat[0]; CS(4) = quat[1]; CS(5) = quat[2]; CS(6) = quat[3];
     carry = b;
-  }
+  };
+  MJB_BODY_LOOP_UP(sweep_body, 1, nbody, MJB_SPEC_NBODY);
 #undef CS
 }
 
@@ -2734,6 +2781,7 @@ MJB_HD inline int contact_scan(Ctx& c) {
   int last_g1 = -1, total = 0;
   double pos1[3] = {0, 0, 0}, nrm[3] = {0, 0, 0};
   unsigned bits = 0;
+  MJB_UNROLL
   for (int ci = 0; ci < ncand; ci++) {
     const int* cint = cand_int + MJB_CAND_NI*ci;
     const double bound = cand_num[MJB_CAND_NN*ci + MJB_CN_RBOUND];
@@ -2918,7 +2966,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   double post_d[3] = {0, 0, 0};
   int carry_for = -1;
   double cf[6], cw[6], cg[6] = {0, 0, 0, 0, 0, 0};
-  for (int b = nbody - 1; b > 0; b--) {
+  auto rne_body = [&](const int b) MJB_BODY_LAMBDA {
     const int p = body_parentid[b];
     const bool push = p && b != p + 1;       // child p+1 hands over in registers (depth-first order)
     double f[6], w[6], w1[6], pf[6], pw1[6], g[6] = {0, 0, 0, 0, 0, 0}, pg[6];
@@ -2947,6 +2995,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)(6*b + k)*N + c.s] = o[k];
     }
     const int d0 = body_dofadr[b], dn = body_dofnum[b];
+    MJB_UNROLL
     for (int i = d0; i < d0 + dn; i++) {
       double cd[6];
       ldn(cd, cdof, 6*i, 6);
@@ -2971,7 +3020,8 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       for (int k = 0; k < 6; k++) { cf[k] = f[k]; cw[k] = w[k]; cg[k] = g[k]; }
       carry_for = p;
     }
-  }
+  };
+  MJB_BODY_LOOP_DOWN(rne_body, 1, nbody, MJB_SPEC_NBODY);
   if (post) post_constraint_end(c);
 }
 
@@ -3566,7 +3616,7 @@ MJB_HD inline void inertia(Ctx& c) {
   const int* tree_flags = MI(body_tree_flags);   // bit1: highest-index child, bit2: has a child != body+1
   bool carried = false;          // cr, A hold the sums handed over by body b+1
   double cr[10], A[21];
-  for (int b = nbody - 1; b > 0; b--) {
+  auto inertia_body = [&](const int b) MJB_BODY_LAMBDA {
     const int flags = tree_flags[b];
     {
       double ci[10];
@@ -3586,6 +3636,7 @@ MJB_HD inline void inertia(Ctx& c) {
       for (int j = 0; j < 21; j++) A[j] += pA[j];
     }
     const int adr0 = body_dofadr[b], num = body_dofnum[b];
+    MJB_UNROLL
     for (int k = adr0 + num - 1; k >= adr0; k--) {
       const int madr = dof_Madr[k];
       const int diag = rowadr[k] + rownnz[k] - 1;
@@ -3639,7 +3690,7 @@ MJB_HD inline void inertia(Ctx& c) {
     if (p > 0) {
       if (b == p + 1) {
         carried = true;          // cr, A stay in registers for the parent, which is visited next
-        continue;
+        return;
       }
       carried = false;
       if (flags & 2) {
@@ -3655,7 +3706,8 @@ MJB_HD inline void inertia(Ctx& c) {
     } else {
       carried = false;
     }
-  }
+  };
+  MJB_BODY_LOOP_DOWN(inertia_body, 1, nbody, MJB_SPEC_NBODY);
 }
 
 // ------------------------------------------------------------------------------------------
