@@ -157,8 +157,10 @@ MJB_API int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch);
 MJB_API int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos,
                             const mjtNum* qvel, const mjtNum* qacc, mjtNum* qfrc_inverse);
 
-/* copy a field of the last mjb_inverse to a HOST array laid out nbatch x rows (row-major) */
+/* copy a field of the last mjb_inverse to a HOST array laid out nbatch x rows (row-major), where
+ * nbatch is the batch size of the last evaluation: mjb_lastBatch(d) */
 MJB_API int mjb_get(mjbData* d, int field, void* host_out);
+MJB_API int mjb_lastBatch(const mjbData* d);
 MJB_API int mjb_getQfrcInverse(mjbData* d, mjtNum* qfrc_inverse);
 /* DEVICE structure-of-arrays view of a field (rows x stride), valid until mjb_deleteData */
 MJB_API const void* mjb_devicePtr(mjbData* d, int field);
@@ -187,8 +189,21 @@ MJB_API void mjb_phaseTiming(mjbData* d, int enable);
 MJB_API int mjb_phaseTimes(mjbData* d, double* ms, int n);
 
 /* diagnostics: counters of the item-parallel contact phase of the last chunk
- * (items, contacts, overflow flag, slots); -1 if that path is not in use */
+ * (items, contacts, overflow flags -- bit0 item list, bit1 contact list --, slots); -1 if that path is
+ * not in use */
 MJB_API int mjb_debugQueue(mjbData* d, int* out4);
+
+/* Several devices behind one mjbData: shard g lives on devices[g] and evaluates the
+ * contiguous range [g*per, (g+1)*per) of every batch, per = ceil(nbatch / ndevice); the model is
+ * replicated on each device, there is no collective. mjb_setState / mjb_inverse / mjb_inverseAsync /
+ * mjb_inverseSkip / mjb_inverseHost / mjb_get / mjb_setMocap / mjb_synchronize / mjb_specialize work on
+ * the whole batch with the same host arrays as on one device; mjb_inverseHost drives every device from
+ * its own host thread (the reference's batched API chunks over a thread pool the same way,
+ * python/mujoco/rollout.cc:180-210). Device views (mjb_devicePtr, mjb_setStateDevice), mjb_inverseFD
+ * and mjb_compareFwdInv need a single-device mjbData. A device may be listed more than once. */
+MJB_API mjbData* mjb_makeDataMulti(const mjModel* m, int nbatch_max, const int* devices, int ndevice,
+                                   unsigned outmask, int nconmax, int njmax, char* err, int err_sz);
+MJB_API int mjb_ndevice(const mjbData* d);
 
 /* Model specialisation. mjb_specialize compiles the phase kernels FOR THIS MODEL (NVRTC, sm_100a; the
  * model's tables become compile-time constants and the loops over bodies / dofs / candidate pairs are

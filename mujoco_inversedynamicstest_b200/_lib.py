@@ -17,6 +17,9 @@ c_ll, c_uint, c_double = ctypes.c_longlong, ctypes.c_uint, ctypes.c_double
 # name -> (restype, argtypes); mirrors include/mjb.h and include/mjb_modelio.h one to one
 SIGNATURES = {
     "mjb_makeData": (c_void_p, [c_void_p, c_int, c_int, c_uint, c_int, c_int, c_char_p, c_int]),
+    "mjb_makeDataMulti": (c_void_p, [c_void_p, c_int, ctypes.POINTER(c_int), c_int, c_uint, c_int, c_int,
+                                     c_char_p, c_int]),
+    "mjb_ndevice": (c_int, [c_void_p]),
     "mjb_deleteData": (None, [c_void_p]),
     "mjb_setStream": (None, [c_void_p, c_void_p]),
     "mjb_setState": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -29,6 +32,7 @@ SIGNATURES = {
     "mjb_inverseSkip": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
     "mjb_inverseHost": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mjb_get": (c_int, [c_void_p, c_int, c_void_p]),
+    "mjb_lastBatch": (c_int, [c_void_p]),
     "mjb_getQfrcInverse": (c_int, [c_void_p, c_void_p]),
     "mjb_devicePtr": (c_void_p, [c_void_p, c_int]),
     "mjb_fieldRows": (c_int, [c_void_p, c_int]),

@@ -81,6 +81,7 @@ class Model:
         if n == 0 or not ptr.value:
             return np.zeros((nr.value, nc.value), dtype=dt)
         buf = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr.value)
+        buf._owner = self        # the view keeps the model (and with it the memory) alive
         return np.frombuffer(buf, dtype=dt).reshape(nr.value, nc.value)
 
     def get_opt_int(self, name):
@@ -99,12 +100,19 @@ class Model:
 class BatchData:
     """mjbData: the batched counterpart of mjData on one CUDA device."""
 
-    def __init__(self, model, nbatch_max, device=0, outmask=0, nconmax=0, njmax=0, stream=None):
+    def __init__(self, model, nbatch_max, device=0, outmask=0, nconmax=0, njmax=0, stream=None, devices=None):
+        """devices: list of CUDA device indices -> one mjbData sharded over them (mjb_makeDataMulti)."""
         self.model = model
         self.nq, self.nv = model.int("nq"), model.int("nv")
         err = ctypes.create_string_buffer(1024)
-        self._d = lib().mjb_makeData(model.ptr, int(nbatch_max), int(device), int(outmask),
-                                     int(nconmax), int(njmax), err, 1024)
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*[int(x) for x in devices])
+            self._d = lib().mjb_makeDataMulti(model.ptr, int(nbatch_max), arr, len(devices), int(outmask),
+                                              int(nconmax), int(njmax), err, 1024)
+            device = devices[0] if devices else 0
+        else:
+            self._d = lib().mjb_makeData(model.ptr, int(nbatch_max), int(device), int(outmask),
+                                         int(nconmax), int(njmax), err, 1024)
         if not self._d:
             raise MjbError(err.value.decode())
         self._d = ctypes.c_void_p(self._d)
@@ -272,11 +280,19 @@ class BatchData:
     def device_ptr(self, field):
         return lib().mjb_devicePtr(self._d, field)
 
+    def last_batch(self):
+        """Batch size of the last evaluation (what mjb_get copies), independent of later set_state calls."""
+        return int(lib().mjb_lastBatch(self._d))
+
     def get(self, field, out=None):
         rows = self.rows(field)
         dt = np.int32 if field in _INT_FIELDS else np.float64
+        n = self.last_batch()
         if out is None:
-            out = np.empty((self.nbatch, rows), dtype=dt)
+            out = np.empty((n, rows), dtype=dt)
+        elif (out.dtype != dt or out.size < n * rows or not out.flags["C_CONTIGUOUS"]):
+            raise MjbError(f"mjb_get: `out` must be a C-contiguous {np.dtype(dt).name} array of at least "
+                           f"{n} x {rows} elements")
         self._check(lib().mjb_get(self._d, field, out.ctypes.data), "mjb_get")
         return out
 
@@ -296,17 +312,17 @@ class BatchData:
 
     def contacts(self):
         nc = self.rows(F_CONTACT_GEOM) // 2
-        geom = self.get(F_CONTACT_GEOM).reshape(self.nbatch, nc, 2)
-        info = self.get(F_CONTACT_INFO).reshape(self.nbatch, nc, 3)
-        num = self.get(F_CONTACT_NUM).reshape(self.nbatch, nc, 13)
+        geom = self.get(F_CONTACT_GEOM).reshape(-1, nc, 2)
+        info = self.get(F_CONTACT_INFO).reshape(-1, nc, 3)
+        num = self.get(F_CONTACT_NUM).reshape(-1, nc, 13)
         return {"geom": geom, "dim": info[:, :, 0], "exclude": info[:, :, 1],
                 "efc_address": info[:, :, 2], "dist": num[:, :, 0], "pos": num[:, :, 1:4],
                 "frame": num[:, :, 4:13]}
 
     def efc(self):
         nj = self.rows(F_EFC_INT) // 3
-        ei = self.get(F_EFC_INT).reshape(self.nbatch, nj, 3)
-        en = self.get(F_EFC_NUM).reshape(self.nbatch, nj, 8)
+        ei = self.get(F_EFC_INT).reshape(-1, nj, 3)
+        en = self.get(F_EFC_NUM).reshape(-1, nj, 8)
         names = ("pos", "margin", "D", "R", "vel", "aref", "force", "diagApprox")
         out = {"type": ei[:, :, 0], "id": ei[:, :, 1], "state": ei[:, :, 2]}
         out.update({k: en[:, :, i] for i, k in enumerate(names)})
@@ -315,7 +331,7 @@ class BatchData:
     def rne_post_constraint(self):
         """cacc, cfrc_int, cfrc_ext [nbatch, nbody, 6] as mj_rnePostConstraint leaves them
         (src/engine/engine_core_smooth.c:2027-2181); needs OUT_RNEPOST."""
-        return {k: self.get(f).reshape(self.nbatch, -1, 6)
+        return {k: self.get(f).reshape(self.last_batch(), -1, 6)
                 for k, f in (("cacc", F_CACC), ("cfrc_int", F_CFRC_INT), ("cfrc_ext", F_CFRC_EXT))}
 
     def sensordata(self):

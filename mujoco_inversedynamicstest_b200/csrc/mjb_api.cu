@@ -4,9 +4,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/mjb.h"
 #include "mjb_kernels.cuh"
@@ -25,6 +27,8 @@ struct mjbData_ {
   std::vector<unsigned char> blob;   // host copy of the model blob (input of mjb_specialize)
   mjb::SpecKernels spec;       // kernels compiled for this model (mjb_specialize), if any
   bool spec_on = false;
+  bool spec_wanted = false;    // the caller asked for specialised kernels (re-specialise after a model refresh)
+  unsigned long long opt_hash = 0;   // hash of m->opt when the blob was built (mj_inverse honours m->opt per call)
   std::vector<int> cand;       // host copy of candidate (g1, g2, func)
   unsigned char* d_model = nullptr;
   int model_bytes = 0;
@@ -83,9 +87,33 @@ struct mjbData_ {
   double* d_fd_out = nullptr;
   size_t fd_out_doubles = 0;
   std::string error;
+  // multi-device front (mjb_makeDataMulti): this object owns no device memory itself; shard g is a
+  // complete mjbData on devices[g] and evaluates the contiguous range [g*per, (g+1)*per) of a batch,
+  // per = ceil(nbatch / ndevice). No collective: states are independent.
+  std::vector<mjbData*> shards;
 };
 
 namespace {
+
+unsigned long long optHash(const mjModel* m) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(&m->opt);
+  unsigned long long h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < sizeof(m->opt); i++) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
+// The reference consults global callbacks on this path (mjcb_passive engine_passive.c:497-499,
+// mjcb_contactfilter engine_collision_driver.c:1474-1478, mjcb_sensor, mjcb_control is not on it): a
+// device path cannot call back into host code, so a process whose libmujoco has one of them set is
+// refused. The symbols are looked up in the process image (present when the caller links libmujoco).
+const char* activeCallback() {
+  static const char* const names[] = {"mjcb_passive", "mjcb_contactfilter", "mjcb_sensor", nullptr};
+  for (int i = 0; names[i]; i++) {
+    void** p = reinterpret_cast<void**>(dlsym(RTLD_DEFAULT, names[i]));
+    if (p && *p) return names[i];
+  }
+  return nullptr;
+}
 
 bool check(mjbData* d, cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -118,6 +146,41 @@ void setField(mjbData* d, int f, void* p, int rows, int isint) {
 
 }  // namespace
 
+
+namespace {
+
+struct ShardRange { long long first; int n; };
+
+ShardRange shardRange(const mjbData* d, int g, int nbatch) {
+  const long long G = (long long)d->shards.size();
+  const long long per = (nbatch + G - 1) / G;
+  long long first = per * g, end = first + per;
+  if (first > nbatch) first = nbatch;
+  if (end > nbatch) end = nbatch;
+  return {first, (int)(end - first)};
+}
+
+// run fn(shard, range) for every shard, one host thread per device; returns false if any failed
+template <typename F>
+bool forShards(mjbData* d, int nbatch, bool threaded, F fn) {
+  const int G = (int)d->shards.size();
+  std::vector<int> rc(G, 0);
+  auto work = [&](int g) { rc[g] = fn(d->shards[g], shardRange(d, g, nbatch)); };
+  if (threaded && G > 1) {
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back(work, g);
+    for (auto& t : th) t.join();
+  } else {
+    for (int g = 0; g < G; g++) work(g);
+  }
+  for (int g = 0; g < G; g++) {
+    if (rc[g] < 0) { d->error = "device " + std::to_string(d->shards[g]->device) + ": " + d->shards[g]->error; return false; }
+  }
+  return true;
+}
+
+}  // namespace
+
 extern "C" {
 
 mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned outmask, int nconmax,
@@ -128,6 +191,10 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   };
   if (!m) return fail("mjb_makeData: null model");
   if (nbatch_max <= 0) return fail("mjb_makeData: nbatch_max must be positive");
+  if (const char* cb = activeCallback()) {
+    return fail(std::string("mjb_makeData: the global callback ") + cb +
+                " is set; the batched device path cannot call host callbacks");
+  }
 
   std::vector<unsigned char> blob;
   std::string msg;
@@ -167,6 +234,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   d->stride = ((long long)nbatch_max + 31) & ~31LL;   // keep every row 256-byte aligned
   std::memcpy(&d->hdr, blob.data(), sizeof(mjbHdr));
   d->blob = blob;
+  d->opt_hash = optHash(m);
   const mjbHdr& H = d->hdr;
   d->nconmax = nconmax > 0 ? nconmax : 64;
   d->njmax = njmax > 0 ? njmax : 256;
@@ -204,8 +272,11 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     const bool want = H.ncand > 0 && !(H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) &&
                       !(path && !std::strcmp(path, "pooled"));
     if (want) {
-      const long long per_items = H.ncand < 48 ? H.ncand : 48;
-      long long ni = d->chunk_stride * per_items, nc = d->chunk_stride * 16;
+      // MJB_ITEMS_PER_STATE / MJB_CONTACTS_PER_STATE override the list sizing (tests, measurements)
+      long long per_items = H.ncand < 48 ? H.ncand : 48, per_contacts = 16;
+      if (const char* env = std::getenv("MJB_ITEMS_PER_STATE")) { if (std::atol(env) > 0) per_items = std::atol(env); }
+      if (const char* env = std::getenv("MJB_CONTACTS_PER_STATE")) { if (std::atol(env) > 0) per_contacts = std::atol(env); }
+      long long ni = d->chunk_stride * per_items, nc = d->chunk_stride * per_contacts;
       const long long budget = 4LL << 30;
       const long long bytes = ni * (long long)(sizeof(mjb::ContactItem) + sizeof(mjb::ItemCon)) +
                               nc * (long long)(sizeof(mjb::ContactRec) + sizeof(int));
@@ -306,7 +377,42 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   return d;
 }
 
+mjbData* mjb_makeDataMulti(const mjModel* m, int nbatch_max, const int* devices, int ndevice, unsigned outmask,
+                           int nconmax, int njmax, char* err, int err_sz) {
+  auto fail = [&](const std::string& msg) -> mjbData* {
+    if (err && err_sz > 0) std::snprintf(err, err_sz, "%s", msg.c_str());
+    return nullptr;
+  };
+  if (!devices || ndevice <= 0) return fail("mjb_makeDataMulti: at least one device is required");
+  if (nbatch_max <= 0) return fail("mjb_makeDataMulti: nbatch_max must be positive");
+  mjbData* d = new mjbData_;
+  std::memset(&d->out, 0, sizeof(d->out));
+  for (int f = 0; f < mjbF_COUNT; f++) setField(d, f, nullptr, 0, 0);
+  d->nbatch_max = nbatch_max;
+  d->outmask = outmask;
+  const int per = (nbatch_max + ndevice - 1) / ndevice;
+  for (int g = 0; g < ndevice; g++) {
+    mjbData* sh = mjb_makeData(m, per, devices[g], outmask, nconmax, njmax, err, err_sz);
+    if (!sh) { mjb_deleteData(d); return nullptr; }
+    d->shards.push_back(sh);
+  }
+  d->device = devices[0];
+  d->hdr = d->shards[0]->hdr;
+  d->nconmax = d->shards[0]->nconmax; d->njmax = d->shards[0]->njmax;
+  for (int f = 0; f < mjbF_COUNT; f++) { d->field_rows[f] = d->shards[0]->field_rows[f]; d->field_isint[f] = d->shards[0]->field_isint[f]; }
+  return d;
+}
+
+int mjb_ndevice(const mjbData* d) { return d->shards.empty() ? 1 : (int)d->shards.size(); }
+
 int mjb_specialize(mjbData* d, char* err, int err_sz) {
+  if (!d->shards.empty()) {
+    int rc = 0;
+    for (mjbData* sh : d->shards) if (mjb_specialize(sh, err, err_sz)) rc = -1;
+    d->spec_on = rc == 0;
+    return rc;
+  }
+  d->spec_wanted = true;
   if (d->spec_on) return 0;
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
   std::string msg;
@@ -346,6 +452,11 @@ int mjb_precompile(const mjModel* m, char* info, int info_sz) {
 
 void mjb_deleteData(mjbData* d) {
   if (!d) return;
+  if (!d->shards.empty()) {
+    for (mjbData* sh : d->shards) mjb_deleteData(sh);
+    delete d;
+    return;
+  }
   cudaSetDevice(d->device);
   if (d->fd) mjb_deleteData(d->fd);
   if (d->spec_on) mjb::jitUnload(d->spec);
@@ -382,6 +493,13 @@ void mjb_deleteData(mjbData* d) {
 void mjb_setStream(mjbData* d, void* cuda_stream) { d->stream = (cudaStream_t)cuda_stream; d->stream_dirty = true; }
 
 int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc) {
+  if (!d->shards.empty()) {
+    if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setState: nbatch out of range"; return -1; }
+    const int nq = d->hdr.nq, nv = d->hdr.nv;
+    return forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) {
+      return mjb_setState(sh, r.n, qpos + r.first * nq, qvel + r.first * nv, qacc + r.first * nv);
+    }) ? 0 : -1;
+  }
   d->stream_dirty = true;
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setState: nbatch out of range"; return -1; }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
@@ -402,6 +520,13 @@ int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
 
 // d->mocap_pos / d->mocap_quat per state (HOST, nbatch x nmocap x 3 | 4); NULL returns to the model pose
 int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* mocap_quat) {
+  if (!d->shards.empty()) {
+    const int nm = d->hdr.nmocap;
+    return forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) {
+      return mjb_setMocap(sh, r.n, mocap_pos ? mocap_pos + r.first * 3 * nm : nullptr,
+                          mocap_quat ? mocap_quat + r.first * 4 * nm : nullptr);
+    }) ? 0 : -1;
+  }
   d->stream_dirty = true;
   const mjbHdr& H = d->hdr;
   mjb::Outputs& o = d->out;
@@ -429,6 +554,7 @@ int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* 
 
 int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel, const mjtNum* qacc,
                        long long stride) {
+  if (!d->shards.empty()) { d->error = "mjb_setStateDevice: not available on a multi-device mjbData (use the shard of one device)"; return -1; }
   if (!qpos || !qvel || !qacc) {
     d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
     return 0;
@@ -446,6 +572,42 @@ int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel, const
 namespace {
 
 // launch the phase kernels for states [first, first + count) on the compute stream
+// mj_inverse reads m->opt on every call; the batched path flattened the model at mjb_makeData. When
+// the caller changed m->opt in between (flags, cone, timestep, gravity ...), the blob is rebuilt and
+// uploaded again if its layout is unchanged; a change that alters the layout (e.g. contacts switched
+// on for a model uploaded without candidate pairs) is an error asking for a new mjbData.
+bool refreshModel(mjbData* d, const mjModel* m) {
+  if (!m) return true;
+  const unsigned long long h = optHash(m);
+  if (h == d->opt_hash) return true;
+  std::vector<unsigned char> blob;
+  std::string msg;
+  if (!mjb::buildModelBlob(m, blob, msg)) { d->error = "mjb_inverse: m->opt changed: " + msg; return false; }
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
+  const mjbHdr& O = d->hdr;
+  if (H->bytes != O.bytes || H->nscratch != O.nscratch || H->ncand != O.ncand || H->nsensordata != O.nsensordata ||
+      H->discrete_acc != O.discrete_acc || H->sensor_post != O.sensor_post || H->sensor_touch != O.sensor_touch ||
+      ((H->ncand > 0 && !(H->disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT))) && !d->d_cq &&
+       !(std::getenv("MJB_CONTACT_PATH")))) {
+    d->error = "mjb_inverse: m->opt changed since mjb_makeData in a way that changes the device layout; "
+               "create a new mjbData";
+    return false;
+  }
+  // kernels already queued on the stream still read the old blob: order the upload after them
+  if (!check(d, cudaStreamSynchronize(d->stream), "cudaStreamSynchronize")) return false;
+  if (!check(d, cudaMemcpy(d->d_model, blob.data(), blob.size(), cudaMemcpyHostToDevice), "cudaMemcpy(model)")) return false;
+  std::memcpy(&d->hdr, blob.data(), sizeof(mjbHdr));
+  d->blob = blob;
+  d->opt_hash = h;
+  if (d->spec_on) {           // the specialised kernels were compiled for the old options
+    mjb::jitUnload(d->spec);
+    d->spec_on = false;
+    if (d->spec_wanted && mjb_specialize(d, nullptr, 0)) d->error.clear();   // generic kernels otherwise
+  }
+  if (d->fd) { mjb_deleteData(d->fd); d->fd = nullptr; d->fd_tile = 0; }
+  return true;
+}
+
 bool launchRange(mjbData* d, long long first, long long count) {
   d->stream_dirty = true;      // mjb_inverseHost clears it again after its own launches
   mjb::LaunchArgs a;
@@ -504,9 +666,14 @@ bool launchRange(mjbData* d, long long first, long long count) {
 extern "C" {
 
 int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
-  (void)m;   // the model was flattened at mjb_makeData; kept for signature parity with mj_inverse
+  if (!d->shards.empty()) {
+    if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverse: nbatch out of range"; return -1; }
+    d->last_nbatch = nbatch;
+    return forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) { return mjb_inverseAsync(m, sh, r.n); }) ? 0 : -1;
+  }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverse: nbatch out of range"; return -1; }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  if (!refreshModel(d, m)) return -1;
   d->last_nbatch = nbatch;
   return launchRange(d, 0, nbatch) ? 0 : -1;
 }
@@ -517,9 +684,20 @@ int mjb_inverseAsync(const mjModel* m, mjbData* d, int nbatch) {
 // directions overlap the compute of neighbouring pieces. Host buffers should be pinned.
 int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos, const mjtNum* qvel,
                     const mjtNum* qacc, mjtNum* qfrc_inverse) {
-  (void)m;
+  if (!d->shards.empty()) {
+    // one host thread per device, each driving its own three-stream pipeline on its slice of the
+    // caller's arrays (python/mujoco/rollout.cc:180-210 chunks the batch over a thread pool the same way)
+    if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseHost: nbatch out of range"; return -1; }
+    d->last_nbatch = nbatch;
+    const int nq = d->hdr.nq, nv = d->hdr.nv;
+    return forShards(d, nbatch, true, [&](mjbData* sh, ShardRange r) {
+      return mjb_inverseHost(m, sh, r.n, qpos + r.first * nq, qvel + r.first * nv, qacc + r.first * nv,
+                             qfrc_inverse + r.first * nv);
+    }) ? 0 : -1;
+  }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseHost: nbatch out of range"; return -1; }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  if (!refreshModel(d, m)) return -1;
   const mjbHdr& H = d->hdr;
   d->last_nbatch = nbatch;
   d->in_qpos = d->d_qpos; d->in_qvel = d->d_qvel; d->in_qacc = d->d_qacc; d->in_stride = d->stride;
@@ -600,6 +778,21 @@ int mjb_inverseHost(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qpos
 }
 
 int mjb_inverse(const mjModel* m, mjbData* d, int nbatch) {
+  if (!d->shards.empty()) {
+    if (mjb_inverseAsync(m, d, nbatch)) return -1;       // queued on every device first, then counted
+    int total = 0;
+    const bool ok = forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) {
+      int count = 0;
+      bool k = check(sh, cudaSetDevice(sh->device), "cudaSetDevice");
+      k = k && check(sh, cudaMemsetAsync(sh->d_counter, 0, sizeof(int), sh->stream), "memset counter");
+      k = k && check(sh, mjb::launch_count_nonzero(sh->out.status, r.n, sh->d_counter, sh->stream), "count status");
+      k = k && check(sh, cudaMemcpyAsync(&count, sh->d_counter, sizeof(int), cudaMemcpyDeviceToHost, sh->stream), "D2H counter");
+      k = k && check(sh, cudaStreamSynchronize(sh->stream), "mjb_inverse");
+      total += count;
+      return k ? 0 : -1;
+    });
+    return ok ? total : -1;
+  }
   if (mjb_inverseAsync(m, d, nbatch)) return -1;
   int count = 0;
   bool ok = check(d, cudaMemsetAsync(d->d_counter, 0, sizeof(int), d->stream), "memset counter");
@@ -633,6 +826,7 @@ int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int
 // generated on the device and evaluated as one large batch by the same phase kernels.
 int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq, mjtNum* DfDv,
                   mjtNum* DfDa, mjtNum* DmDq) {
+  if (!d->shards.empty()) { d->error = "mjb_inverseFD: not available on a multi-device mjbData"; return -1; }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseFD: nbatch out of range"; return -1; }
   if (!(eps > 0)) { d->error = "mjb_inverseFD: eps must be positive"; return -1; }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
@@ -692,6 +886,7 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
 int mjb_compareFwdInv(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qfrc_applied,
                       const mjtNum* qfrc_actuator, const mjtNum* xfrc_applied,
                       const mjtNum* qfrc_constraint, mjtNum* fwdinv) {
+  if (!d->shards.empty()) { d->error = "mjb_compareFwdInv: not available on a multi-device mjbData"; return -1; }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_compareFwdInv: nbatch out of range"; return -1; }
   if (!qfrc_constraint || !fwdinv) { d->error = "mjb_compareFwdInv: qfrc_constraint and fwdinv are required"; return -1; }
   if (nbatch == 0) return 0;
@@ -743,6 +938,16 @@ int mjb_compareFwdInv(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qf
 }
 
 int mjb_get(mjbData* d, int field, void* host_out) {
+  if (!d->shards.empty()) {
+    if (field < 0 || field >= mjbF_COUNT || !d->shards[0]->field_ptr[field]) {
+      d->error = "mjb_get: field was not requested in outmask";
+      return -1;
+    }
+    const size_t row_bytes = (size_t)d->field_rows[field] * (d->field_isint[field] ? sizeof(int) : sizeof(double));
+    return forShards(d, d->last_nbatch, true, [&](mjbData* sh, ShardRange r) {
+      return r.n ? mjb_get(sh, field, (char*)host_out + (size_t)r.first * row_bytes) : 0;
+    }) ? 0 : -1;
+  }
   if (field < 0 || field >= mjbF_COUNT || !d->field_ptr[field]) {
     d->error = "mjb_get: field was not requested in outmask";
     return -1;
@@ -767,6 +972,7 @@ int mjb_get(mjbData* d, int field, void* host_out) {
 int mjb_getQfrcInverse(mjbData* d, mjtNum* qfrc_inverse) { return mjb_get(d, mjbF_QFRC_INVERSE, qfrc_inverse); }
 
 const void* mjb_devicePtr(mjbData* d, int field) {
+  if (!d->shards.empty()) return nullptr;    // per-device views: use one mjbData per device
   return (field >= 0 && field < mjbF_COUNT) ? d->field_ptr[field] : nullptr;
 }
 
@@ -797,13 +1003,24 @@ void mjb_candidate(const mjbData* d, int i, int* geom1, int* geom2, int* func) {
 
 const char* mjb_lastError(const mjbData* d) { return d->error.c_str(); }
 
-long long mjb_kernelLaunches(const mjbData* d) { return d->kernel_launches; }
+long long mjb_kernelLaunches(const mjbData* d) {
+  if (!d->shards.empty()) {
+    long long t = 0;
+    for (const mjbData* sh : d->shards) t += sh->kernel_launches;
+    return t;
+  } return d->kernel_launches; }
 
 int mjb_debugQueue(mjbData* d, int* out4) {
   if (!d->d_cq) return -1;
   cudaSetDevice(d->device);
-  return cudaMemcpy(out4, d->d_cq, 4 * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+  int q[5];
+  if (cudaMemcpy(q, d->d_cq, sizeof q, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  out4[0] = q[0]; out4[1] = q[1]; out4[3] = q[3];
+  out4[2] = (q[2] ? 1 : 0) | (q[4] ? 2 : 0);     // bit0: item list overflowed, bit1: contact list overflowed
+  return 0;
 }
+
+int mjb_lastBatch(const mjbData* d) { return d->last_nbatch; }
 
 void mjb_phaseTiming(mjbData* d, int enable) {
   d->phase_timing = enable != 0;
@@ -825,6 +1042,11 @@ int mjb_phaseTimes(mjbData* d, double* ms, int n) {
 }
 
 int mjb_synchronize(mjbData* d) {
+  if (!d->shards.empty()) {
+    int rc = 0;
+    for (mjbData* sh : d->shards) if (mjb_synchronize(sh)) rc = -1;
+    return rc;
+  }
   cudaSetDevice(d->device);
   return check(d, cudaStreamSynchronize(d->stream), "cudaStreamSynchronize") ? 0 : -1;
 }

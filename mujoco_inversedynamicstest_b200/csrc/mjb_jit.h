@@ -18,14 +18,12 @@ namespace mjb {
 
 struct SpecKernels {
   void* module = nullptr;        // CUmodule
-  void* smooth = nullptr;        // CUfunction handles (null: use the generic kernel for that phase)
-  void* inertia = nullptr;
+  // CUfunction handles. smooth / inertia: one kernel per stage (body range), launched in order;
+  // an empty list or a null handle means the generic kernel runs that phase.
+  std::vector<void*> smooth;
+  std::vector<void*> inertia;
   void* contact_scan = nullptr;
   void* backward = nullptr;
-  void* tree = nullptr;          // fused forward + inertia (+ backward) kernel, see mjb_spec_kernels.cuh
-  int smooth_threads = 0;
-  int tree_threads = 0;
-  int tree_smem = 0;
   bool from_cache = false;
   double compile_seconds = 0;
   std::string key;               // cache key (hex)
@@ -47,6 +45,9 @@ void jitUnload(SpecKernels& k);
 // launch one specialised kernel (grid x 1 x 1, threads x 1 x 1) with the launch arguments by value
 cudaError_t jitLaunch(void* fn, int grid, int threads, size_t smem, cudaStream_t stream,
                       const LaunchArgs& args);
+
+// stage boundaries the prelude was generated with (for diagnostics): "smooth 1-5 5-9 ... | inertia ..."
+std::string jitStagePlan(const std::vector<unsigned char>& blob);
 
 }  // namespace mjb
 

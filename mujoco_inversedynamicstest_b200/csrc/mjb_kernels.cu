@@ -15,6 +15,7 @@
 #include "mjb_jit.h"
 
 #include <cstdio>
+#include <vector>
 #include <cstdlib>
 
 // resident CTAs per SM each phase kernel is compiled for (register budget = 65536 / (threads * CTAS)).
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   // fallback of the item-parallel path: runs only when that path overflowed its lists
-  if (a.cq && !*(volatile int*)&a.cq->overflow) return;
+  if (a.cq && !(*(volatile int*)&a.cq->overflow | *(volatile int*)&a.cq->overflow_contacts)) return;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
   const mjbHdr& H = *c.H;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
         if (lane == 0) base = atomicAdd(&a.cq->ncontacts, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base + total > a.contacts_cap) {
-          if (lane == 0) a.cq->overflow = 1;
+          if (lane == 0) a.cq->overflow_contacts = 1;
         } else if (num > 0) {
           const int first = base + incl - num;
           a.item_con[item] = ItemCon{first, num};
@@ -565,7 +566,7 @@ template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, 4) contact_index_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
-  if (*(volatile int*)&a.cq->overflow) return;
+  if (*(volatile int*)&a.cq->overflow | *(volatile int*)&a.cq->overflow_contacts) return;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
   const int lane = threadIdx.x & 31;
@@ -617,7 +618,7 @@ template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
-  if (*(volatile int*)&a.cq->overflow) return;
+  if (*(volatile int*)&a.cq->overflow | *(volatile int*)&a.cq->overflow_contacts) return;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -817,13 +818,48 @@ cudaError_t launch_smooth(const LaunchArgs& a, cudaStream_t stream) {
                          : launch_phase(smooth_kernel<false, false>, a, sm, cap, stream, kSmoothThreads);
 }
 
-// specialised kernel with the launch geometry of launch_phase
-cudaError_t launch_spec(void* fn, const LaunchArgs& args, size_t smem, int ctas_per_sm, cudaStream_t stream,
-                        int threads = kThreads) {
-  int grid = (args.chunk_n + threads - 1) / threads;
-  const int cap = kSMs * ctas_per_sm;
-  if (grid > cap) grid = cap;
-  return jitLaunch(fn, grid, threads, smem, stream, args);
+cudaError_t generic_inertia(const LaunchArgs& a, cudaStream_t stream) {
+  const size_t smem = inverse_smem_bytes(a.model_bytes, a.model_in_smem);
+  return a.model_in_smem ? launch_phase(inertia_kernel<true>, a, smem, 8, stream)
+                         : launch_phase(inertia_kernel<false>, a, 0, 8, stream);
+}
+cudaError_t generic_scan(const LaunchArgs& a, cudaStream_t stream) {
+  const size_t smem = inverse_smem_bytes(a.model_bytes, a.model_in_smem);
+  return a.model_in_smem ? launch_phase(contact_scan_kernel<true>, a, smem, 8, stream)
+                         : launch_phase(contact_scan_kernel<false>, a, 0, 8, stream);
+}
+cudaError_t generic_backward(const LaunchArgs& a, cudaStream_t stream) {
+  const size_t smem = inverse_smem_bytes(a.model_bytes, a.model_in_smem);
+  if (a.has_gravcomp) {
+    return a.model_in_smem ? launch_phase(backward_kernel<true, true>, a, smem, 8, stream)
+                           : launch_phase(backward_kernel<false, true>, a, 0, 8, stream);
+  }
+  return a.model_in_smem ? launch_phase(backward_kernel<true, false>, a, smem, 8, stream)
+                         : launch_phase(backward_kernel<false, false>, a, 0, 8, stream);
+}
+
+// one specialised kernel over the chunk, same grid rule as launch_phase
+cudaError_t launch_spec(void* fn, const LaunchArgs& args, int ctas_per_sm, cudaStream_t stream) {
+  int grid = (args.chunk_n + kThreads - 1) / kThreads;
+  if (grid > kSMs * ctas_per_sm) grid = kSMs * ctas_per_sm;
+  return jitLaunch(fn, grid, kThreads, 0, stream, args);
+}
+
+// one phase of a chunk: the specialised kernels (one per stage, in order) when there are any, else
+// the generic kernel
+template <typename G>
+cudaError_t run_phase(const std::vector<void*>* stages, void* single, const LaunchArgs& args,
+                      cudaStream_t stream, int* launches, G generic) {
+  if (stages && !stages->empty()) {
+    for (void* fn : *stages) {
+      ++*launches;
+      cudaError_t e = launch_spec(fn, args, 8, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  ++*launches;
+  return single ? launch_spec(single, args, 8, stream) : generic(args, stream);
 }
 
 struct PhaseScope {   // records begin/end events around one kernel launch when timing is on
@@ -844,9 +880,10 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   const size_t smem = inverse_smem_bytes(args.model_bytes, args.model_in_smem);
   const bool in_smem = args.model_in_smem != 0;
   const bool want_inertia = args.out.qM || args.out.qLD || args.out.qLDiagInv;
-  const bool spec_smooth = spec && spec->smooth, spec_inertia = spec && spec->inertia;
-  const bool spec_scan = spec && spec->contact_scan, spec_backward = spec && spec->backward;
-  const size_t spec_smooth_smem = sizeof(double) * MJB_SM_SLOTS * kSmoothThreads;
+  const std::vector<void*>* const st_smooth = spec ? &spec->smooth : nullptr;
+  const std::vector<void*>* const st_inertia = spec ? &spec->inertia : nullptr;
+  void* const fn_scan = spec ? spec->contact_scan : nullptr;
+  void* const fn_backward = spec ? spec->backward : nullptr;
   cudaError_t e;
   if (args.qacc_discrete) {
     // mjENBL_INVDISCRETE (engine_inverse.c:227-234): position stage + factorisation on the given
@@ -855,19 +892,16 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     pre.qacc_discrete = nullptr;
     pre.has_contacts = 0;
     { PhaseScope ps(timer, stream, kPhaseSmooth);
-    e = spec_smooth ? launch_spec(spec->smooth, pre, spec_smooth_smem, 2 * MJB_CTAS_SMOOTH, stream, spec->smooth_threads)
-                    : launch_smooth(pre, stream); }
+    e = run_phase(st_smooth, nullptr, pre, stream, launches, launch_smooth); }
     if (e != cudaSuccess) return e;
     { PhaseScope ps(timer, stream, kPhaseInertia);
-    e = spec_inertia ? launch_spec(spec->inertia, pre, 0, 8, stream)
-        : in_smem ? launch_phase(inertia_kernel<true>, pre, smem, 8, stream)
-                : launch_phase(inertia_kernel<false>, pre, 0, 8, stream); }
+    e = run_phase(st_inertia, nullptr, pre, stream, launches, generic_inertia); }
     if (e != cudaSuccess) return e;
     { PhaseScope ps(timer, stream, kPhaseDiscrete);
     e = in_smem ? launch_phase(discrete_acc_kernel<true>, args, smem, 8, stream)
                 : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream); }
     if (e != cudaSuccess) return e;
-    *launches += 3;
+    *launches += 1;
     LaunchArgs post = args;
     post.qacc = args.qacc_discrete;
     post.qacc_discrete = nullptr;
@@ -877,23 +911,16 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     return e;
   }
   { PhaseScope ps(timer, stream, kPhaseSmooth);
-  e = spec_smooth ? launch_spec(spec->smooth, args, spec_smooth_smem, 2 * MJB_CTAS_SMOOTH, stream, spec->smooth_threads)
-                  : launch_smooth(args, stream); }
+  e = run_phase(st_smooth, nullptr, args, stream, launches, launch_smooth); }
   if (e != cudaSuccess) return e;
-  ++*launches;
   if (want_inertia) {
     PhaseScope ps(timer, stream, kPhaseInertia);
-    e = spec_inertia ? launch_spec(spec->inertia, args, 0, 8, stream)
-        : in_smem ? launch_phase(inertia_kernel<true>, args, smem, 8, stream)
-                : launch_phase(inertia_kernel<false>, args, 0, 8, stream);
+    e = run_phase(st_inertia, nullptr, args, stream, launches, generic_inertia);
     if (e != cudaSuccess) return e;
-    ++*launches;
   }
   if (args.has_contacts) {
     { PhaseScope ps(timer, stream, kPhaseScan);
-    e = spec_scan ? launch_spec(spec->contact_scan, args, 0, 8, stream)
-        : in_smem ? launch_phase(contact_scan_kernel<true>, args, smem, 8, stream)
-                : launch_phase(contact_scan_kernel<false>, args, 0, 8, stream); }
+    e = run_phase(nullptr, fn_scan, args, stream, launches, generic_scan); }
     if (e != cudaSuccess) return e;
 // The contact kernel reads the model tables through L1 instead of a shared-memory copy: its lanes
 // index the candidate tables with per-lane (non-uniform) indices anyway, and the 25 KB per CTA are
@@ -929,20 +956,11 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     e = csm ? launch_phase(contact_kernel<true>, args, csmem, 8, stream, kThreads, MJB_CTAS_CONTACT)
             : launch_phase(contact_kernel<false>, args, csmem, 8, stream, kThreads, MJB_CTAS_CONTACT); }
     if (e != cudaSuccess) return e;
-    *launches += 2;
+    *launches += 1;
   }
   PhaseScope ps_backward(timer, stream, kPhaseBackward);
-  if (spec_backward) {
-    e = launch_spec(spec->backward, args, 0, 8, stream);
-  } else if (args.has_gravcomp) {
-    e = in_smem ? launch_phase(backward_kernel<true, true>, args, smem, 8, stream)
-                : launch_phase(backward_kernel<false, true>, args, 0, 8, stream);
-  } else {
-    e = in_smem ? launch_phase(backward_kernel<true, false>, args, smem, 8, stream)
-                : launch_phase(backward_kernel<false, false>, args, 0, 8, stream);
-  }
+  e = run_phase(nullptr, fn_backward, args, stream, launches, generic_backward);
   if (e != cudaSuccess) return e;
-  ++*launches;
   if (args.out.qfrc_bias) {
     e = in_smem ? launch_phase(bias_kernel<true>, args, smem, 8, stream)
                 : launch_phase(bias_kernel<false>, args, 0, 8, stream);

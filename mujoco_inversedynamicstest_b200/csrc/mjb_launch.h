@@ -23,7 +23,10 @@ constexpr int kListCap = MJB_LISTCAP;                  // per-lane survivor list
 // items through MJB_ISC_ITEMBASE / NSURV and an item its contacts through ItemCon, so placement
 // order does not matter. If a list would overflow, `overflow` is raised and the chunk is handled
 // by the pooled contact kernel instead (every kernel of either path checks the flag first).
-struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; };
+// `overflow` is raised only by contact_items_kernel (item list full) and `overflow_contacts` only by
+// contact_narrow_kernel (contact list full), so the flag a kernel tests on entry cannot change while
+// that kernel runs: every thread of every CTA takes the same decision.
+struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; int overflow_contacts; };
 struct ContactItem { int state; int ci; };          // chunk-local state, candidate pair
 struct ItemCon { int base; int count; };            // the item's contacts: contacts[base .. base+count)
 struct ContactRec {

@@ -76,12 +76,12 @@ template <int B, int E, typename F>
 MJB_DI void static_for_up(F& f) { if constexpr (B < E) { f(B); static_for_up<B + 1, E>(f); } }
 template <int B, int E, typename F>
 MJB_DI void static_for_down(F& f) { if constexpr (B > E) { f(B); static_for_down<B - 1, E>(f); } }
-// body(b) for b = first .. n-1 / b = n-1 .. first ; nspec is the compile-time value of n
-#define MJB_BODY_LOOP_UP(body, first, n, nspec) static_for_up<first, nspec>(body)
-#define MJB_BODY_LOOP_DOWN(body, first, n, nspec) static_for_down<(nspec) - 1, (first) - 1>(body)
+// body(b) for b = lo .. hi-1 / b = hi-1 .. lo ; kLo, kHi are the compile-time values of lo, hi
+#define MJB_BODY_LOOP_UP(body, lo, hi, kLo, kHi) static_for_up<kLo, kHi>(body)
+#define MJB_BODY_LOOP_DOWN(body, lo, hi, kLo, kHi) static_for_down<(kHi) - 1, (kLo) - 1>(body)
 #else
-#define MJB_BODY_LOOP_UP(body, first, n, nspec) for (int b_ = (first); b_ < (n); b_++) body(b_)
-#define MJB_BODY_LOOP_DOWN(body, first, n, nspec) for (int b_ = (n) - 1; b_ >= (first); b_--) body(b_)
+#define MJB_BODY_LOOP_UP(body, lo, hi, kLo, kHi) for (int b_ = (lo); b_ < (hi); b_++) body(b_)
+#define MJB_BODY_LOOP_DOWN(body, lo, hi, kLo, kHi) for (int b_ = (hi) - 1; b_ >= (lo); b_--) body(b_)
 #endif
 
 // status bits (mirrored in include/mjb.h)
@@ -1181,9 +1181,18 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   }
 }
 
+// Body range [kLo, kHi) (kHi = 0: up to nbody). The generic kernels run the whole tree in one call;
+// the model-specialised build cuts the expanded sweep into stages of a few thousand instructions,
+// one kernel each, so that the code of a kernel stays resident in the instruction cache (measured:
+// ONE expanded kernel of 24 K instructions ran 1.5x slower than the generic loop although it
+// executes 2.6x fewer instructions -- every warp streams 390 KB of cold code per state). A stage
+// that does not start at body 1 reloads the tree origin and lets its first body fetch the parent
+// from scratch; a stage that does not end at the last body stores the carry of its last body.
+template <int kLo = 1, int kHi = 0>
 MJB_HD inline void forward_sweep(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
+  const int lo = kLo, hi = kHi ? kHi : nbody;
   double* xpos = SC(xpos); double* xquat = SC(xquat); double* org = SC(origin);
   double* cvel = SC(cvel); double* cal = SC(cacc_lin); double* cacc = SC(cacc);
   double* cfrc = SC(cfrc); double* cinert = SC(cinert); double* cdof = SC(cdof);
@@ -1210,7 +1219,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
 #define CS(k) c.sm[(k) * MJB_SMS]
   // world body: identity pose, zero velocity, acceleration = -gravity (mj_rne :1979-1982)
   double O[3] = {0, 0, 0};
-  {
+  int carry = 0;          // body whose pose / velocity / acceleration are in the carry slots
+  if (lo == 1) {
     double P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
     double Z[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
     if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
@@ -1223,10 +1233,12 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     for (int k = 0; k < 6; k++) { CS(7 + k) = 0; CS(13 + k) = A[k]; CS(19 + k) = 0; }
     const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     body_geoms(c, 0, P, Q, I9, P, I9);
+  } else {
+    carry = -1;
+    ldn(O, org, 3*MI(body_rootid)[lo], 3);
   }
-  int carry = 0;          // body whose pose / velocity / acceleration are in the carry slots
 
-  if (nbody > 1) prefetch_body_inputs(c, 1);
+  if (lo < nbody) prefetch_body_inputs(c, lo);
   auto sweep_body = [&](const int b) MJB_BODY_LAMBDA {
     if (b + 1 < nbody) prefetch_body_inputs(c, b + 1);
     const int pid = body_parentid[b];
@@ -1474,7 +1486,14 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     CS(3) = quat[0]; CS(4) = quat[1]; CS(5) = quat[2]; CS(6) = quat[3];
     carry = b;
   };
-  MJB_BODY_LOOP_UP(sweep_body, 1, nbody, MJB_SPEC_NBODY);
+  MJB_BODY_LOOP_UP(sweep_body, lo, hi, kLo, (kHi ? kHi : MJB_SPEC_NBODY));
+  if (hi < nbody && carry > 0) {
+    // hand-over to the next stage: everything a child may read of the last body of this one
+    double t[25];
+    for (int k = 0; k < 25; k++) t[k] = CS(k);
+    stc(xpos, 3*carry, t, 3); stc(xquat, 4*carry, t + 3, 4);
+    stc(cvel, 6*carry, t + 7, 6); stc(cacc, 6*carry, t + 13, 6); stc(cal, 6*carry, t + 19, 6);
+  }
 #undef CS
 }
 
@@ -3021,7 +3040,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
       carry_for = p;
     }
   };
-  MJB_BODY_LOOP_DOWN(rne_body, 1, nbody, MJB_SPEC_NBODY);
+  MJB_BODY_LOOP_DOWN(rne_body, 1, nbody, 1, MJB_SPEC_NBODY);
   if (post) post_constraint_end(c);
 }
 
@@ -3593,9 +3612,13 @@ MJB_DI void inert_add_sym6(double* A, const double* i) {
   A[20] += i[9];
 }
 
+// Body range [kLo, kHi) as in forward_sweep, visited downwards. At a stage boundary the register
+// hand-over from body p+1 to its parent p becomes a push through the parent's scratch accumulators.
+template <int kLo = 1, int kHi = 0>
 MJB_HD inline void inertia(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
+  const int lo = kLo, hi = kHi ? kHi : nbody;
   double* crb = SC(crb); double* ia = SC(ia); double* cinert = SC(cinert); double* cdof = SC(cdof);
   const int* body_parentid = MI(body_parentid);
   const int* body_dofadr = MI(body_dofadr);
@@ -3629,7 +3652,9 @@ MJB_HD inline void inertia(Ctx& c) {
         inert_to_sym6(A, ci);
       }
     }
-    if (flags & 4) {
+    // sums pushed through scratch: by children other than b+1, and by b+1 itself when it was the
+    // last body of the previous stage
+    if ((flags & 4) || (b + 1 == hi && hi < nbody && body_parentid[b + 1] == b)) {
       double pc[10], pA[21];
       ldn(pc, crb, 10*b, 10); ldn(pA, ia, 21*b, 21);
       for (int j = 0; j < 10; j++) cr[j] += pc[j];
@@ -3688,7 +3713,7 @@ MJB_HD inline void inertia(Ctx& c) {
     }
     const int p = body_parentid[b];
     if (p > 0) {
-      if (b == p + 1) {
+      if (b == p + 1 && b != lo) {
         carried = true;          // cr, A stay in registers for the parent, which is visited next
         return;
       }
@@ -3707,7 +3732,7 @@ MJB_HD inline void inertia(Ctx& c) {
       carried = false;
     }
   };
-  MJB_BODY_LOOP_DOWN(inertia_body, 1, nbody, MJB_SPEC_NBODY);
+  MJB_BODY_LOOP_DOWN(inertia_body, lo, hi, kLo, (kHi ? kHi : MJB_SPEC_NBODY));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -3762,12 +3787,17 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
 //   contact  : mj_collision + contact rows             (only when contacts are enabled)
 //   backward : mj_rne(flg_acc=1), J'f, final combine, output bookkeeping
 
-template <bool kSpatial>
+template <bool kSpatial, int kLo = 1, int kHi = 0>
 MJB_HD inline void phase_smooth(Ctx& c) {
   const mjbHdr& H = *c.H;
-  c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
-  c.status = 0;
-  forward_sweep(c);        // incl. input checks, joint springs/dampers, dof friction and joint limit rows
+  if (kLo == 1) {
+    c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
+    c.status = 0;
+  } else {
+    load_counters(c);      // a later stage of the sweep: running limit-row count and status bits
+  }
+  forward_sweep<kLo, kHi>(c);   // incl. input checks, joint springs/dampers, dof friction and joint limit rows
+  if (kHi != 0 && kHi < H.nbody) { save_counters(c); return; }
   tendon_kinematics<kSpatial>(c);
   passive_tendons<kSpatial>(c);
   {
@@ -3784,7 +3814,8 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   save_counters(c);
 }
 
-MJB_HD inline void phase_inertia(Ctx& c) { inertia(c); }
+template <int kLo = 1, int kHi = 0>
+MJB_HD inline void phase_inertia(Ctx& c) { inertia<kLo, kHi>(c); }
 
 MJB_HD inline bool contacts_enabled(const mjbHdr& H) {
   return !(H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) && H.ncand > 0;

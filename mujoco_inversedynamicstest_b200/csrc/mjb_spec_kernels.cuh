@@ -54,8 +54,12 @@ __device__ __forceinline__ void spec_bind(Ctx& c, const LaunchArgs& a, long long
 
 }  // namespace mjb
 
+// Stages. The expanded forward sweep and the expanded inertia sweep are cut into body ranges of a few
+// thousand instructions each (MJBS_SMOOTH_STAGES / MJBS_INERTIA_STAGES, chosen by the host from a
+// per-body cost estimate), one kernel per range, so that each kernel's code stays resident in the
+// instruction cache; stages hand over through the same scratch rows the generic kernels use.
 #ifndef MJBS_SMOOTH_CTAS
-#define MJBS_SMOOTH_CTAS 1
+#define MJBS_SMOOTH_CTAS 2
 #endif
 #ifndef MJBS_INERTIA_CTAS
 #define MJBS_INERTIA_CTAS 3
@@ -67,34 +71,45 @@ __device__ __forceinline__ void spec_bind(Ctx& c, const LaunchArgs& a, long long
 #define MJBS_SCAN_CTAS 4
 #endif
 
-// smooth: launched with MJB_SMS threads (the stride of the per-thread carry slots in shared memory)
-extern "C" __global__ void __launch_bounds__(MJB_SMS, MJBS_SMOOTH_CTAS) mjbs_smooth(mjb::LaunchArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  mjb::Ctx c;
-  mjb::spec_ctx(c, a);
-  c.sm = reinterpret_cast<double*>(smem) + threadIdx.x;
-  for (long long i = (long long)blockIdx.x * MJB_SMS + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * MJB_SMS) {
-    mjb::spec_bind(c, a, i);
-    mjb::phase_smooth<MJB_SPEC_SPATIAL != 0>(c);
-  }
-}
+#define MJBS_STATE_LOOP(i)                                                                        \
+  for (long long i = (long long)blockIdx.x * mjb::kThreads + threadIdx.x; i < a.chunk_n;          \
+       i += (long long)gridDim.x * mjb::kThreads)
 
-extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_INERTIA_CTAS) mjbs_inertia(mjb::LaunchArgs a) {
-  mjb::Ctx c;
-  mjb::spec_ctx(c, a);
-  for (long long i = (long long)blockIdx.x * mjb::kThreads + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * mjb::kThreads) {
-    mjb::spec_bind(c, a, i);
-    mjb::phase_inertia(c);
+// per-thread carry slots of the forward sweep in shared memory: stride = CTA size
+#if MJB_SMS != 128
+#error "the specialised kernels are compiled with MJB_SMOOTH_THREADS = 128 (mjb_jit.cu)"
+#endif
+
+#define MJBS_DEFINE_SMOOTH(idx, lo, hi)                                                            \
+  extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_SMOOTH_CTAS)                    \
+  mjbs_smooth_##idx(mjb::LaunchArgs a) {                                                           \
+    __shared__ double carry_slots[MJB_SM_SLOTS * mjb::kThreads];                                   \
+    mjb::Ctx c;                                                                                    \
+    mjb::spec_ctx(c, a);                                                                           \
+    c.sm = carry_slots + threadIdx.x;                                                              \
+    MJBS_STATE_LOOP(i) {                                                                           \
+      mjb::spec_bind(c, a, i);                                                                     \
+      mjb::phase_smooth<MJB_SPEC_SPATIAL != 0, lo, hi>(c);                                         \
+    }                                                                                              \
   }
-}
+MJBS_SMOOTH_STAGES(MJBS_DEFINE_SMOOTH)
+
+#define MJBS_DEFINE_INERTIA(idx, lo, hi)                                                           \
+  extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_INERTIA_CTAS)                   \
+  mjbs_inertia_##idx(mjb::LaunchArgs a) {                                                          \
+    mjb::Ctx c;                                                                                    \
+    mjb::spec_ctx(c, a);                                                                           \
+    MJBS_STATE_LOOP(i) {                                                                           \
+      mjb::spec_bind(c, a, i);                                                                     \
+      mjb::phase_inertia<lo, hi>(c);                                                               \
+    }                                                                                              \
+  }
+MJBS_INERTIA_STAGES(MJBS_DEFINE_INERTIA)
 
 extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_SCAN_CTAS) mjbs_contact_scan(mjb::LaunchArgs a) {
   mjb::Ctx c;
   mjb::spec_ctx(c, a);
-  for (long long i = (long long)blockIdx.x * mjb::kThreads + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * mjb::kThreads) {
+  MJBS_STATE_LOOP(i) {
     mjb::spec_bind(c, a, i);
     mjb::contact_scan(c);
   }
@@ -103,8 +118,7 @@ extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_SCAN_CTAS) mjbs
 extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_BACKWARD_CTAS) mjbs_backward(mjb::LaunchArgs a) {
   mjb::Ctx c;
   mjb::spec_ctx(c, a);
-  for (long long i = (long long)blockIdx.x * mjb::kThreads + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * mjb::kThreads) {
+  MJBS_STATE_LOOP(i) {
     mjb::spec_bind(c, a, i);
     mjb::phase_backward<MJB_SPEC_PASSIVE_WRENCH != 0>(c);
   }

@@ -79,6 +79,7 @@ def make_case(name):
               "contact_frame": nconmax,
               "efc_type": njmax, "efc_id": njmax, "efc_state": njmax, "efc_force": njmax,
               "efc_pos": njmax, "efc_D": njmax, "efc_aref": njmax,
+              "efc_margin": njmax, "efc_R": njmax, "efc_vel": njmax, "efc_diagApprox": njmax,
               "qfrc_passive": None, "qfrc_constraint": None, "qM": None, "qLD": None,
               "qLDiagInv": None, "xpos": None, "cvel": None, "cdof": None}
     if m.int("nsensordata") > 0:
@@ -93,6 +94,37 @@ def make_case(name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
     print(f"{name}: nv={m.int('nv')} states={nstate} mean ncon={out['ncon'].mean():.2f} "
           f"mean nefc={out['nefc'].mean():.2f} max={out['ncon'].max()}/{out['nefc'].max()}")
+
+
+# Large multi-tree scenes (BASELINE config 5) with enough states for statistics: only the discrete
+# outputs and qfrc_inverse are kept (the full dump of every contact frame would be tens of MB).
+# name -> (reference xml, nstate, z_range, nconmax, njmax)
+REDUCED_CASES = {
+    "humanoids22_256": ("model/humanoid/22_humanoids.xml", 256, (0.0, 1.5), 704, 1408),
+}
+
+
+def make_reduced_case(name):
+    xml, nstate, zr, nconmax, njmax = REDUCED_CASES[name]
+    m = reflib.Model.from_xml(reflib.reference_path(xml))
+    raw = os.path.join(HERE, name + ".mjb")
+    m.save_mjb(raw)
+    with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb",
+                                             compresslevel=9, mtime=0) as g:
+        g.write(f.read())
+    os.remove(raw)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    fields = {"ncon": 1, "ne": 1, "nf": 1, "nl": 1, "nefc": 1, "contact_geom": nconmax,
+              "efc_type": njmax, "efc_id": njmax, "efc_state": njmax}
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields, nthread=os.cpu_count() or 1)
+    assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax, (name, out["ncon"].max(), out["nefc"].max())
+    save = {"z_range": np.array(zr), "nstate": np.array(nstate), "nconmax": np.array(nconmax), "njmax": np.array(njmax)}
+    for k, v in out.items():
+        v = v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v
+        save[k] = v.astype(np.int16) if (v.dtype == np.int32 and k.startswith(("contact_", "efc_"))) else v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(f"{name}: nv={m.int('nv')} states={nstate} mean ncon={out['ncon'].mean():.1f} "
+          f"mean nefc={out['nefc'].mean():.1f} max={out['ncon'].max()}/{out['nefc'].max()}")
 
 
 # finite-difference Jacobians of the reference (mjd_inverseFD, engine_derivative_fd.c:611) on the
@@ -207,7 +239,7 @@ def make_mocap_case(name):
 
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
-                 list(MOCAP_CASES)):
-        (make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(MOCAP_CASES) + list(REDUCED_CASES)):
+        (make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

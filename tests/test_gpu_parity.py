@@ -542,3 +542,57 @@ def test_inverse_fd_matches_reference(name):
         scale = np.abs(ref).reshape(n, -1).max(axis=1)[:, None, None]
         err = np.abs(got - ref) / np.maximum(scale, 1e-6)
         assert err.max() < 2e-3, (key, float(err.max()))
+
+
+def test_contact_record_list_overflow_falls_back_on_the_device():
+    """The CONTACT list (not the item list) overflows: the survivors fit, the contacts they yield do
+    not (capacity forced to 1 contact per state with MJB_CONTACTS_PER_STATE). contact_narrow_kernel
+    raises its own flag -- which it never tests itself, so all its CTAs run to the end -- and the
+    pooled kernel produces the reference's results."""
+    import ctypes
+    import os
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200._lib import lib
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden("humanoid")
+    model = mjb.Model.from_mjb(path)
+    n = 8192
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+    os.environ["MJB_CONTACTS_PER_STATE"] = "1"
+    try:
+        small = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT, nconmax=64)
+    finally:
+        os.environ.pop("MJB_CONTACTS_PER_STATE", None)
+    full = mjb.BatchData(model, n, outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT, nconmax=64)
+    for bd in (small, full):
+        bd.set_state(qpos, qvel, qacc)
+        assert bd.inverse() == 0
+    out = (ctypes.c_int * 4)()
+    assert lib().mjb_debugQueue(small._d, out) == 0
+    assert out[2] == 2, list(out)                       # contact list overflowed, item list did not
+    assert lib().mjb_debugQueue(full._d, out) == 0 and out[2] == 0
+    np.testing.assert_array_equal(small.counts()["ncon"], full.counts()["ncon"])
+    np.testing.assert_array_equal(small.contacts()["geom"], full.contacts()["geom"])
+    np.testing.assert_array_equal(small.qfrc_inverse(), full.qfrc_inverse())
+    np.testing.assert_array_equal(small.counts()["ncon"][:256], ref["ncon"])
+
+
+def test_get_is_sized_by_the_last_evaluation():
+    """mjb_get copies the batch of the LAST evaluation; set_state afterwards must not shrink the
+    buffer the Python mirror hands to it, and an undersized `out` is refused."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden("humanoid_nocontact")
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, 1000, z_range=tuple(ref["z_range"]))
+    bd = mjb.BatchData(model, 1000)
+    bd.set_state(qpos, qvel, qacc)
+    bd.inverse()
+    first = bd.qfrc_inverse().copy()
+    bd.set_state(qpos[:10], qvel[:10], qacc[:10])
+    assert bd.last_batch() == 1000
+    again = bd.qfrc_inverse()
+    assert again.shape == (1000, model.int("nv"))
+    np.testing.assert_array_equal(first, again)
+    with pytest.raises(mjb.MjbError):
+        bd.get(mjb.F_QFRC_INVERSE, out=np.empty((10, model.int("nv"))))

@@ -10,6 +10,27 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 RTOL, ATOL = 1e-9, 1e-12
 
 
+# Fixtures whose qfrc_inverse is NOT inside the element-wise bound everywhere, with the number of
+# entries outside it and the largest ratio to the bound that the tests accept (measured values are
+# recorded in profiles/r02_parity_report.jsonl and BASELINE.md). Everything else is strict.
+#   humanoids22*: 22 interpenetrating humanoids, ~300 contacts per state; a component that is the
+#   sum of hundreds of contact terms of size F carries ~eps*F*sqrt(n) of rounding in either engine.
+#   weld: three welds holding a chain; components that cancel between large weld forces.
+# Measured in round 2 (profiles/r02_parity_report.jsonl): humanoids22 0 of 4,752 entries,
+# humanoids22_256 2 of 152,064 (worst ratio 2.8), weld 2 of 1,920 (worst 83); every other fixture 0.
+STRICT_EXCEPTIONS = {
+    "humanoids22": (4, 4.0),
+    "humanoids22_256": (16, 8.0),
+    "weld": (4, 200.0),
+}
+
+# At 2^20 live states per cone (test_live_reference_1m_states) 81-86 of 28.3 M entries (3e-6 of them)
+# sit outside the element-wise bound, worst ratio 46: components of a few 1e-3 next to contact forces
+# of 1e3-1e4 in the same state. The test allows this fraction and requires every such entry to be
+# inside the same bound taken against the largest force of its state (qfrc_violations_scaled).
+LIVE_STRICT_FRACTION = 1e-5
+
+
 def golden(name):
     """(path of the gzip'd MJB, dict of reference outputs) of a committed fixture."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -21,6 +42,19 @@ def qfrc_violations(got, ref, rtol=RTOL, atol=ATOL):
     d = np.abs(got - ref)
     tol = atol + rtol * np.abs(ref)
     return int((d > tol).sum()), float((d / tol).max()) if d.size else 0.0
+
+
+def worst_entries(got, ref, k=3, rtol=RTOL, atol=ATOL):
+    """The k entries with the largest ratio to the element-wise bound: (state, column, ref, got,
+    ratio, largest |ref| of the state) -- what a documented exception looks like."""
+    r = np.abs(got - ref) / (atol + rtol * np.abs(ref))
+    idx = np.argsort(r, axis=None)[::-1][:k]
+    out = []
+    for i in idx:
+        s, c = np.unravel_index(i, r.shape)
+        out.append({"state": int(s), "col": int(c), "ref": float(ref[s, c]), "got": float(got[s, c]),
+                    "ratio": float(r[s, c]), "state_max": float(np.abs(ref[s]).max())})
+    return out
 
 
 def qfrc_violations_scaled(got, ref, rtol=RTOL, atol=ATOL):
