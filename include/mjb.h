@@ -184,7 +184,7 @@ MJB_API long long mjb_kernelLaunches(const mjbData* d);
 /* Per-kernel timing of the phase kernels (diagnostics / benchmark): while enabled, every launch is
  * bracketed by CUDA events on the launching stream. mjb_phaseTimes synchronises and returns the
  * milliseconds accumulated since the last call in ms[0..n): smooth, inertia, contact_scan, contact,
- * backward, discrete_acc. */
+ * backward, discrete_acc, tree (the fused forward + inertia stages of a specialised model). */
 MJB_API void mjb_phaseTiming(mjbData* d, int enable);
 MJB_API int mjb_phaseTimes(mjbData* d, double* ms, int n);
 

@@ -239,7 +239,7 @@ class BatchData:
     def kernel_launches(self):
         return int(lib().mjb_kernelLaunches(self._d))
 
-    PHASES = ("smooth", "inertia", "contact_scan", "contact", "backward", "discrete_acc")
+    PHASES = ("smooth", "inertia", "contact_scan", "contact", "backward", "discrete_acc", "tree")
 
     def phase_timing(self, enable=True):
         """Bracket every phase-kernel launch with CUDA events (mjb_phaseTiming)."""

@@ -256,7 +256,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   // intermediates live per chunk of states: at most 2^20 states and at most ~20 GB (2^20 humanoid states
   // are one chunk of 16.3 GB)
   {
-    const double bytes_per_state = 8.0 * H.nscratch + 4.0 * (mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1);
+    const double bytes_per_state = 8.0 * H.nscratch + 4.0 * mjb::isc_rows(H);
     long long chunk = (long long)(20.0e9 / bytes_per_state);
     if (chunk > (1LL << 20)) chunk = 1LL << 20;
     if (chunk > d->stride) chunk = d->stride;
@@ -292,7 +292,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     }
   }
   ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
-  ok = ok && devAlloc(d, &d->d_iscratch, (size_t)(mjb::MJB_ISC_MASK + (H.ncand + 31) / 32 + 1) * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
+  ok = ok && devAlloc(d, &d->d_iscratch, (size_t)mjb::isc_rows(H) * (size_t)d->chunk_stride, "cudaMalloc(iscratch)");
   const size_t S = (size_t)d->stride;
   ok = ok && devAlloc(d, &d->d_qpos, (size_t)H.nq * S, "cudaMalloc(qpos)");
   ok = ok && devAlloc(d, &d->d_qvel, (size_t)H.nv * S, "cudaMalloc(qvel)");
@@ -445,7 +445,8 @@ int mjb_precompile(const mjModel* m, char* info, int info_sz) {
     return -1;
   }
   if (info && info_sz > 0) {
-    std::snprintf(info, info_sz, "%s %s %.1f s", key.c_str(), cached ? "cached" : "compiled", seconds);
+    std::snprintf(info, info_sz, "%s %s %.1f s [%s]", key.c_str(), cached ? "cached" : "compiled", seconds,
+                  mjb::jitStagePlan(blob).c_str());
   }
   return 0;
 }
@@ -620,7 +621,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.iscratch = d->d_iscratch;
   a.chunk_stride = d->chunk_stride;
   a.nscratch = d->hdr.nscratch;
-  a.niscratch = mjb::MJB_ISC_MASK + (d->hdr.ncand + 31) / 32 + 1;
+  a.niscratch = mjb::isc_rows(d->hdr);
   a.stride = d->stride;
   a.nconmax = d->nconmax;
   a.njmax = d->njmax;

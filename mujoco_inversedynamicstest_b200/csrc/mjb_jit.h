@@ -22,6 +22,8 @@ struct SpecKernels {
   // an empty list or a null handle means the generic kernel runs that phase.
   std::vector<void*> smooth;
   std::vector<void*> inertia;
+  std::vector<void*> tree;       // trunk-forward / fused-subtree / trunk-backward stages (phase_tree): replace
+                                 // smooth + inertia when the inertia outputs are requested
   void* contact_scan = nullptr;
   void* backward = nullptr;
   bool from_cache = false;

@@ -109,6 +109,7 @@ __device__ __forceinline__ void make_ctx(Ctx& c, const LaunchArgs& a, unsigned c
   c.sc = nullptr; c.isc = nullptr;
   c.qpos = nullptr; c.qvel = nullptr; c.qacc = nullptr;
   c.s = 0;
+  c.lci = nullptr; c.lcd = nullptr; c.lbody0 = 0; c.ldof0 = 0;
 }
 
 __device__ __forceinline__ void bind_state(Ctx& c, const LaunchArgs& a, long long local) {
@@ -686,7 +687,11 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
         // where a state sits in the batch (which contacts happen to share a round)
         double* fe = co.sc + (size_t)c.H->scoff[side == 0 ? MJB_SC_cfrc_ext : MJB_SC_cfrc_ext1] * MJB_LS;
         double acc[6] = {0, 0, 0, 0, 0, 0};
-        if (leader) for (int k = 0; k < 6; k++) acc[k] = fe[(size_t)(6*body + k) * MJB_LS];
+        // the first wrench on this (state, body, side) starts from zero: the accumulator rows are
+        // not cleared per state, their validity is the state's wrench mask (mjb_pipeline.h)
+        if (leader && wmask_test_and_set(co, body, side == 0)) {
+          for (int k = 0; k < 6; k++) acc[k] = fe[(size_t)(6*body + k) * MJB_LS];
+        }
         for (int k = 0; k < 6; k++) acc[k] += W[k];
         for (int t = 1; t < maxcnt; t++) {
           const int src = t < cnt ? (int)__fns(grp, 0, t + 1) : lane;      // t-th further member of my group
@@ -910,13 +915,20 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     *launches += n2;
     return e;
   }
-  { PhaseScope ps(timer, stream, kPhaseSmooth);
-  e = run_phase(st_smooth, nullptr, args, stream, launches, launch_smooth); }
-  if (e != cudaSuccess) return e;
-  if (want_inertia) {
-    PhaseScope ps(timer, stream, kPhaseInertia);
-    e = run_phase(st_inertia, nullptr, args, stream, launches, generic_inertia);
+  if (want_inertia && spec && !spec->tree.empty()) {
+    // specialised tree stages: forward sweep and mj_crb / mj_factorM fused per subtree (phase_tree)
+    PhaseScope ps(timer, stream, kPhaseTree);
+    e = run_phase(&spec->tree, nullptr, args, stream, launches, launch_smooth);
     if (e != cudaSuccess) return e;
+  } else {
+    { PhaseScope ps(timer, stream, kPhaseSmooth);
+    e = run_phase(st_smooth, nullptr, args, stream, launches, launch_smooth); }
+    if (e != cudaSuccess) return e;
+    if (want_inertia) {
+      PhaseScope ps(timer, stream, kPhaseInertia);
+      e = run_phase(st_inertia, nullptr, args, stream, launches, generic_inertia);
+      if (e != cudaSuccess) return e;
+    }
   }
   if (args.has_contacts) {
     { PhaseScope ps(timer, stream, kPhaseScan);

@@ -11,7 +11,7 @@
 namespace mjb {
 
 // phase ids for the optional per-kernel timing
-enum { kPhaseSmooth = 0, kPhaseInertia, kPhaseScan, kPhaseContact, kPhaseBackward, kPhaseDiscrete, kPhaseCount };
+enum { kPhaseSmooth = 0, kPhaseInertia, kPhaseScan, kPhaseContact, kPhaseBackward, kPhaseDiscrete, kPhaseTree, kPhaseCount };
 
 // optional per-kernel timing: launch_inverse records a CUDA event before and after every phase
 // kernel on the launching stream (events come from the host-side pool below)

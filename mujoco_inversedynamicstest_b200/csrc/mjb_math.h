@@ -175,6 +175,30 @@ MJB_DI void mulInertVec(double* res, const double* i, const double* v) {
   res[5] = i[7]*v[0] - i[6]*v[1] + i[9]*v[5];
 }
 
+// ---- explicitly fused variants -------------------------------------------------------------
+// libmjb is compiled WITHOUT automatic fp contraction (nvcc/NVRTC -fmad=false), like the reference
+// (its x86-64 builds have no FMA): every value that feeds a contact / limit predicate or a stiff
+// constraint row (poses, distances, frames, J*v, J*qacc) then carries exactly the reference's
+// rounding, which the row arithmetic amplifies by D*K ~ 1e6-1e8. The two leaves-to-root sweeps
+// (mj_crb + mj_factorM, mj_rne backward) only form sums that go straight into outputs, so they use
+// these fused forms: same values to a few ulp, 30 % fewer fp64 instructions, and -- being explicit
+// -- the same bits whichever compiler (nvcc, NVRTC) or kernel variant evaluates them.
+MJB_DI double dot6f(const double* a, const double* b) {
+  double r = a[0]*b[0];
+  r = fma(a[1], b[1], r); r = fma(a[2], b[2], r); r = fma(a[3], b[3], r);
+  r = fma(a[4], b[4], r); r = fma(a[5], b[5], r);
+  return r;
+}
+
+MJB_DI void mulInertVecF(double* res, const double* i, const double* v) {   // mulInertVec, fused
+  res[0] = fma(i[7], v[5], fma(-i[8], v[4], fma(i[4], v[2], fma(i[3], v[1], i[0]*v[0]))));
+  res[1] = fma(-i[6], v[5], fma(i[8], v[3], fma(i[5], v[2], fma(i[1], v[1], i[3]*v[0]))));
+  res[2] = fma(i[6], v[4], fma(-i[7], v[3], fma(i[2], v[2], fma(i[5], v[1], i[4]*v[0]))));
+  res[3] = fma(i[9], v[3], fma(-i[7], v[2], i[8]*v[1]));
+  res[4] = fma(i[9], v[4], fma(-i[8], v[0], i[6]*v[2]));
+  res[5] = fma(i[9], v[5], fma(-i[6], v[1], i[7]*v[0]));
+}
+
 // engine_util_spatial.c:526
 MJB_DI void makeFrame(double* frame) {
   normalize3(frame);

@@ -73,7 +73,8 @@
   X(sensor_int) /* nsensor*MJB_SEN_NI : sensors evaluated on the device, see MJB_SEN_*       */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored), \
-                                 bit3 pose read by an equality constraint or a tendon site */
+                                 bit3 pose read by an equality constraint or a tendon site, \
+                                 bit4 velocity carriers read by constraint rows (candidate pair, equality, tendon site) */
 
 // ---- double arrays copied 1:1 from mjModel (name, rows, cols)
 #define MJB_NUM_ARRAYS(X)         \

@@ -144,6 +144,12 @@ struct Ctx {
   int nconmax, njmax;
   Outputs out;
   int ncon, ne, nf, nl, nefc, status;
+  // Fused subtree stages of the specialised build (phase_tree): cinert of bodies >= lbody0 and cdof
+  // of dofs >= ldof0 are handed from the forward sweep to the inertia sweep of the SAME kernel in
+  // these thread-local rows (registers) instead of the scratch; null otherwise.
+  double* lci;
+  double* lcd;
+  int lbody0, ldof0;
 };
 
 // lane stride of the per-state scratch: device scratch is blocked per warp, element (slot, state i)
@@ -181,6 +187,16 @@ struct Ctx {
 MJB_DI void ldn_(double* dst, const double* p, int first, int n, size_t stride) {
   for (int k = 0; k < n; k++) dst[k] = p[(size_t)(first + k) * stride];
 }
+// rows that the running kernel only reads (written by an earlier kernel): ld.global.nc, which tells
+// the compiler that no store of this kernel can alias them, so the loads can be hoisted above the
+// output stores and repeated loads of the same row (ancestor cdofs) are merged
+MJB_DI void ldn_ro_(double* dst, const double* p, int first, int n, size_t stride) {
+#if defined(__CUDA_ARCH__)
+  for (int k = 0; k < n; k++) dst[k] = __ldg(p + (size_t)(first + k) * stride);
+#else
+  for (int k = 0; k < n; k++) dst[k] = p[(size_t)(first + k) * stride];
+#endif
+}
 MJB_DI void stn_(double* p, int first, const double* src, int n, size_t stride) {
   for (int k = 0; k < n; k++) p[(size_t)(first + k) * stride] = src[k];
 }
@@ -204,6 +220,7 @@ MJB_DI void stn_stream_(double* p, int first, const double* src, int n, size_t s
 #define stc(p, first, src, n) stn_(p, first, src, n, MJB_LS)
 #endif
 #define ldn(dst, p, first, n) ldn_(dst, p, first, n, MJB_LS)
+#define ldn_ro(dst, p, first, n) ldn_ro_(dst, p, first, n, MJB_LS)
 #define stn(p, first, src, n) stn_(p, first, src, n, MJB_LS)
 
 // per-state integer scratch rows: counters carried between the phase kernels
@@ -211,6 +228,43 @@ MJB_DI void stn_stream_(double* p, int first, const double* src, int n, size_t s
 // MJB_ISC_ITEMBASE: first entry of the state's survivors in the chunk's global item list (-1: none)
 enum { MJB_ISC_NCON = 0, MJB_ISC_NE, MJB_ISC_NF, MJB_ISC_NL, MJB_ISC_NEFC, MJB_ISC_STATUS,
        MJB_ISC_NSURV, MJB_ISC_ITEMBASE, MJB_ISC_MASK, MJB_ISC_COUNT = MJB_ISC_MASK };
+
+// Wrench-accumulator masks: the per-body constraint wrench rows cfrc_ext ('+' side) and cfrc_ext1
+// ('-' side) are NOT cleared per state; a body's row is valid only if its bit is set in the state's
+// mask (one bit per body and side, after the survivor words). The forward sweep clears the masks
+// (a few ints instead of 12*nbody doubles), whoever adds the first wrench to a body starts from zero
+// and sets the bit, and the backward sweep reads only rows whose bit is set.
+MJB_HD inline int isc_wmask_row(const mjbHdr& H) { return MJB_ISC_MASK + (H.ncand + 31) / 32 + 1; }
+MJB_HD inline int isc_wmask_words(const mjbHdr& H) { return (H.nbody + 31) / 32; }
+MJB_HD inline int isc_rows(const mjbHdr& H) { return isc_wmask_row(H) + 2 * isc_wmask_words(H); }
+
+// sets the bit of (body, side) and returns whether it was already set. Lanes of one warp may work
+// on different bodies of the SAME state (pooled / item-parallel contact kernels): atomic on device.
+MJB_HD inline bool wmask_test_and_set(Ctx& c, int body, bool positive, bool shared = true) {
+  const mjbHdr& H = *c.H;
+  int* w = c.isc + (size_t)(isc_wmask_row(H) + (positive ? 0 : isc_wmask_words(H)) + (body >> 5)) * MJB_LS;
+  const int bit = (int)(1u << (body & 31));
+#if defined(__CUDA_ARCH__)
+  if (shared) return (atomicOr(w, bit) & bit) != 0;
+  const bool was = (*w & bit) != 0;      // thread-per-state kernel: the word belongs to this thread
+  *w |= bit;
+  return was;
+#else
+  const bool was = (*w & bit) != 0;
+  *w |= bit;
+  return was;
+#endif
+}
+MJB_HD inline bool wmask_test(Ctx& c, int body, bool positive) {
+  const mjbHdr& H = *c.H;
+  const int* w = c.isc + (size_t)(isc_wmask_row(H) + (positive ? 0 : isc_wmask_words(H)) + (body >> 5)) * MJB_LS;
+  return ((*w >> (body & 31)) & 1) != 0;
+}
+MJB_HD inline void wmask_clear(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int n = 2 * isc_wmask_words(H), row = isc_wmask_row(H);
+  for (int k = 0; k < n; k++) c.isc[(size_t)(row + k) * MJB_LS] = 0;
+}
 
 MJB_HD inline void save_counters(Ctx& c) {
   c.isc[MJB_ISC_NCON * MJB_LS] = c.ncon; c.isc[MJB_ISC_NE * MJB_LS] = c.ne;
@@ -345,9 +399,10 @@ MJB_HD inline void add_wrench(Ctx& c, int b, const double* p, const double* F, c
   ldn(o, com, 3*rootid[b], 3);
   r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
   cross3(cr, r, F);
-  // one batched read-modify-write (loads first, stores last): a single memory round trip
-  double w[6];
-  ldn(w, fe, 6*b, 6);
+  // one batched read-modify-write (loads first, stores last): a single memory round trip; the
+  // first wrench on this (body, side) of the state starts from zero (wrench-accumulator masks)
+  double w[6] = {0, 0, 0, 0, 0, 0};
+  if (wmask_test_and_set(c, b, positive)) ldn(w, fe, 6*b, 6);
   for (int k = 0; k < 3; k++) { w[k] += cr[k] + T[k]; w[3 + k] += F[k]; }
   stn(fe, 6*b, w, 6);
 }
@@ -641,13 +696,16 @@ MJB_HD inline double spatial_tendon_kinematics(Ctx& c, int t, double* vel, doubl
 }
 
 // wrench [ (p - O_b) x F ; F ] on body b, added (sign +1) or subtracted (-1) in a carrier array
-MJB_HD inline void add_force_to(Ctx& c, double* carrier, int b, const double* p, const double* F, double sign) {
+// masked: the carrier is the '+' constraint-wrench accumulator, whose rows are valid only under
+// the state's wrench mask (the passive carrier is initialised for every body by the forward sweep)
+MJB_HD inline void add_force_to(Ctx& c, double* carrier, int b, const double* p, const double* F, double sign,
+                                bool masked) {
   if (MI(body_static)[b]) return;
-  double o[3], r[3], cr[3], w[6];
+  double o[3], r[3], cr[3], w[6] = {0, 0, 0, 0, 0, 0};
   ldn(o, SC(origin), 3*MI(body_rootid)[b], 3);
   r[0] = p[0] - o[0]; r[1] = p[1] - o[1]; r[2] = p[2] - o[2];
   cross3(cr, r, F);
-  ldn(w, carrier, 6*b, 6);
+  if (!masked || wmask_test_and_set(c, b, true)) ldn(w, carrier, 6*b, 6);
   for (int k = 0; k < 3; k++) { w[k] += sign*cr[k]; w[3 + k] += sign*F[k]; }
   stn(carrier, 6*b, w, 6);
 }
@@ -660,8 +718,8 @@ MJB_HD inline void spatial_tendon_apply(Ctx& c, int t, double f, bool passive) {
                                 double divisor) {
     const double s = f / divisor;
     const double F[3] = {dif[0]*s, dif[1]*s, dif[2]*s};
-    add_force_to(c, carrier, bb, pb, F, 1.0);
-    add_force_to(c, carrier, ba, pa, F, -1.0);
+    add_force_to(c, carrier, bb, pb, F, 1.0, !passive);
+    add_force_to(c, carrier, ba, pa, F, -1.0, !passive);
   });
 }
 
@@ -1188,7 +1246,14 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
 // executes 2.6x fewer instructions -- every warp streams 390 KB of cold code per state). A stage
 // that does not start at body 1 reloads the tree origin and lets its first body fetch the parent
 // from scratch; a stage that does not end at the last body stores the carry of its last body.
-template <int kLo = 1, int kHi = 0>
+// a finished cdof row: to the scratch (backward sweep, constraint rows) and, in a fused subtree
+// stage, to the thread-local rows the inertia sweep of the same kernel reads
+MJB_HD inline void store_cdof(Ctx& c, double* cdof, int dof, const double* cd) {
+  sts(cdof, 6*dof, cd, 6);
+  if (c.lcd) { for (int k = 0; k < 6; k++) c.lcd[6*(dof - c.ldof0) + k] = cd[k]; }
+}
+
+template <int kLo = 1, int kHi = 0, bool kHandOver = true>
 MJB_HD inline void forward_sweep(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
@@ -1336,7 +1401,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
           pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
         }
         if (jtype != MJB_JNT_BALL) {
-          sts(cdof, 6*dadr, cd, 6);
+          store_cdof(c, cdof, dadr, cd);
           if (!has_ball) {
             // mj_comVel / mj_rne for a scalar dof, fused: cdof_dot uses the velocity so far
             double dd[6];
@@ -1362,7 +1427,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       // translational dofs: cdof = [0, e_r], cdof_dot = 0
       for (int r = 0; r < 3; r++) {
         double cd[6] = {0, 0, 0, r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0};
-        sts(cdof, 6*(bda + r), cd, 6);
+        store_cdof(c, cdof, bda + r, cd);
         V[3 + r] += QVEL(bda + r);
         t2[3 + r] += QACC(bda + r);
       }
@@ -1372,7 +1437,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       for (int r = 0; r < 3; r++) {
         cd[r][0] = mat[r]; cd[r][1] = mat[r + 3]; cd[r][2] = mat[r + 6];
         cross3(cd[r] + 3, cd[r], off);
-        sts(cdof, 6*(bda + 3 + r), cd[r], 6);
+        store_cdof(c, cdof, bda + 3 + r, cd[r]);
       }
       // all three use the velocity BEFORE this joint's rotation (mj_comVel :1855-1876)
       for (int r = 0; r < 3; r++) {
@@ -1398,7 +1463,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
         for (int r = 0; r < 3; r++) {
           double cd[6] = {mat[r], mat[r + 3], mat[r + 6], 0, 0, 0};
           cross3(cd + 3, cd, off);
-          stn(cdof, 6*(dadr + r), cd, 6);
+          store_cdof(c, cdof, dadr + r, cd);
         }
       }
       MJB_UNROLL
@@ -1434,8 +1499,13 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       AL[k] = CS(19 + k) + t2[k];
       CS(7 + k) = V[k]; CS(13 + k) = A[k]; CS(19 + k) = AL[k];
     }
-    stc(cvel, 6*b, V, 6);
-    stc(cal, 6*b, AL, 6);
+    // read back only by a child that is not b+1 (bit 2), by constraint rows on this body (bit 4:
+    // candidate pairs, equality constraints, tendon sites), or by the optional per-body outputs
+    if ((tree_flags[b] & (4 | 16)) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.fwdinv ||
+        c.out.cacc || c.out.qfrc_bias) {
+      stc(cvel, 6*b, V, 6);
+      stc(cal, 6*b, AL, 6);
+    }
     // read back only by a child that is not b+1, or by the mj_rnePostConstraint outputs
     if ((tree_flags[b] & 4) || c.out.cacc || c.out.qfrc_bias) stc(cacc, 6*b, A, 6);
 
@@ -1459,7 +1529,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       const double off[3] = {ip[0] - O[0], ip[1] - O[1], ip[2] - O[2]};
       double ci[10], f[6], u1[6], u2[6];
       inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
-      sts(cinert, 10*b, ci, 10);
+      if (c.lci) { for (int k = 0; k < 10; k++) c.lci[10*(b - c.lbody0) + k] = ci[k]; }
+      if (!c.lci || c.out.cfrc_int || c.out.qfrc_bias || c.out.sensordata || c.out.scratch_dump) sts(cinert, 10*b, ci, 10);
       mulInertVec(f, ci, A);
       mulInertVec(u1, ci, V);
       crossForce(u2, V, u1);
@@ -1487,7 +1558,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     carry = b;
   };
   MJB_BODY_LOOP_UP(sweep_body, lo, hi, kLo, (kHi ? kHi : MJB_SPEC_NBODY));
-  if (hi < nbody && carry > 0) {
+  if (kHandOver && hi < nbody && carry > 0) {
     // hand-over to the next stage: everything a child may read of the last body of this one
     double t[25];
     for (int k = 0; k < 25; k++) t[k] = CS(k);
@@ -2903,8 +2974,10 @@ MJB_HD inline void post_constraint_begin(Ctx& c) {
     if (ms[3] >= MJB_MINVAL) { d[0] = ms[0]/ms[3]; d[1] = ms[1]/ms[3]; d[2] = ms[2]/ms[3]; }
     for (int k = 0; k < 3; k++) c.out.cfrc_int[(size_t)(6*r + k)*N + c.s] = d[k];
     for (int b = r; b < e; b++) {
-      double a[6], w[6], w1[6], cr[3];
-      ldn(a, cacc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
+      double a[6], w[6] = {0, 0, 0, 0, 0, 0}, w1[6] = {0, 0, 0, 0, 0, 0}, cr[3];
+      ldn(a, cacc, 6*b, 6);
+      if (wmask_test(c, b, true)) ldn(w, fext, 6*b, 6);
+      if (wmask_test(c, b, false)) ldn(w1, fext1, 6*b, 6);
       cross3(cr, a, d);
       for (int k = 0; k < 3; k++) a[3 + k] += cr[k];
       for (int k = 0; k < 6; k++) w[k] -= w1[k];
@@ -2984,21 +3057,32 @@ MJB_HD inline void rne_and_output(Ctx& c) {
   int post_tree = -1;
   double post_d[3] = {0, 0, 0};
   int carry_for = -1;
+  bool carry_w = false;
   double cf[6], cw[6], cg[6] = {0, 0, 0, 0, 0, 0};
   auto rne_body = [&](const int b) MJB_BODY_LAMBDA {
     const int p = body_parentid[b];
     const bool push = p && b != p + 1;       // child p+1 hands over in registers (depth-first order)
-    double f[6], w[6], w1[6], pf[6], pw1[6], g[6] = {0, 0, 0, 0, 0, 0}, pg[6];
-    ldn(f, cfrc, 6*b, 6); ldn(w, fext, 6*b, 6); ldn(w1, fext1, 6*b, 6);
+    double f[6], w[6] = {0, 0, 0, 0, 0, 0}, w1[6] = {0, 0, 0, 0, 0, 0}, pf[6];
+    double pw1[6] = {0, 0, 0, 0, 0, 0}, g[6] = {0, 0, 0, 0, 0, 0}, pg[6];
+    ldn(f, cfrc, 6*b, 6);
+    // constraint wrenches: only rows some constraint has written for this state (wrench masks);
+    // a contact-free state reads none of them
+    const bool has_w = wmask_test(c, b, true), has_w1 = wmask_test(c, b, false);
+    if (has_w) ldn_ro(w, fext, 6*b, 6);
+    if (has_w1) ldn(w1, fext1, 6*b, 6);
     if (gcomp) ldn(g, fgc, 6*b, 6);
+    bool carried_w = false;
     if (push) {
-      ldn(pf, cfrc, 6*p, 6); ldn(pw1, fext1, 6*p, 6);
+      ldn(pf, cfrc, 6*p, 6);
+      if (wmask_test(c, p, false)) ldn(pw1, fext1, 6*p, 6);
       if (gcomp) ldn(pg, fgc, 6*p, 6);
     }
     for (int k = 0; k < 6; k++) w[k] -= w1[k];
     if (carry_for == b) {
       for (int k = 0; k < 6; k++) { f[k] += cf[k]; w[k] += cw[k]; g[k] += cg[k]; }
+      carried_w = carry_w;
     }
+    const bool any_w = has_w || has_w1 || carried_w;    // this subtree carries a constraint wrench
     if (post) {
       // cfrc_int = sum over the subtree of (inertial force - external force), re-expressed about
       // the tree's centre of mass; the shift was left in the root's row by post_constraint_begin
@@ -3017,11 +3101,11 @@ MJB_HD inline void rne_and_output(Ctx& c) {
     MJB_UNROLL
     for (int i = d0; i < d0 + dn; i++) {
       double cd[6];
-      ldn(cd, cdof, 6*i, 6);
-      const double qfrc_constraint = AT(qc, i) + dot6(cd, w);
+      ldn_ro(cd, cdof, 6*i, 6);
+      const double qfrc_constraint = AT(qc, i) + dot6f(cd, w);
       double passive_i = AT(qp, i);
-      if (gcomp && !(H.has_gravcomp && jnt_actgravcomp[dof_jntid[i]])) passive_i += dot6(cd, g);
-      double res = dot6(cd, f);
+      if (gcomp && !(H.has_gravcomp && jnt_actgravcomp[dof_jntid[i]])) passive_i += dot6f(cd, g);
+      double res = dot6f(cd, f);
       res += armature[i]*QACC(i) - passive_i - qfrc_constraint;
       c.out.qfrc_inverse[(size_t)i*N + c.s] = res;
       if (c.out.qfrc_constraint) c.out.qfrc_constraint[(size_t)i*N + c.s] = qfrc_constraint;
@@ -3030,7 +3114,8 @@ MJB_HD inline void rne_and_output(Ctx& c) {
     if (push) {
       // parent's net = own '+' - own '-' + children's nets: children are folded into its '-' side
       for (int k = 0; k < 6; k++) { pf[k] += f[k]; pw1[k] -= w[k]; }
-      stn(cfrc, 6*p, pf, 6); stn(fext1, 6*p, pw1, 6);
+      stn(cfrc, 6*p, pf, 6);
+      if (any_w) { stn(fext1, 6*p, pw1, 6); wmask_test_and_set(c, p, false, false); }
       if (gcomp) {
         for (int k = 0; k < 6; k++) pg[k] += g[k];
         stn(fgc, 6*p, pg, 6);
@@ -3038,6 +3123,7 @@ MJB_HD inline void rne_and_output(Ctx& c) {
     } else if (p) {
       for (int k = 0; k < 6; k++) { cf[k] = f[k]; cw[k] = w[k]; cg[k] = g[k]; }
       carry_for = p;
+      carry_w = any_w;
     }
   };
   MJB_BODY_LOOP_DOWN(rne_body, 1, nbody, 1, MJB_SPEC_NBODY);
@@ -3584,12 +3670,16 @@ MJB_HD inline void compare_fwdinv(Ctx& c) {
 
 // y = A x for a symmetric 6x6 stored as its 21 upper-triangular entries (row-major)
 MJB_DI void sym6_mul(double* y, const double* A, const double* x) {
-  y[0] = A[0]*x[0] + A[1]*x[1] + A[2]*x[2] + A[3]*x[3] + A[4]*x[4] + A[5]*x[5];
-  y[1] = A[1]*x[0] + A[6]*x[1] + A[7]*x[2] + A[8]*x[3] + A[9]*x[4] + A[10]*x[5];
-  y[2] = A[2]*x[0] + A[7]*x[1] + A[11]*x[2] + A[12]*x[3] + A[13]*x[4] + A[14]*x[5];
-  y[3] = A[3]*x[0] + A[8]*x[1] + A[12]*x[2] + A[15]*x[3] + A[16]*x[4] + A[17]*x[5];
-  y[4] = A[4]*x[0] + A[9]*x[1] + A[13]*x[2] + A[16]*x[3] + A[18]*x[4] + A[19]*x[5];
-  y[5] = A[5]*x[0] + A[10]*x[1] + A[14]*x[2] + A[17]*x[3] + A[19]*x[4] + A[20]*x[5];
+  // explicitly fused (see mjb_math.h): used only by the inertia sweep
+#define MJB_ROW6(a0, a1, a2, a3, a4, a5) \
+  fma(A[a5], x[5], fma(A[a4], x[4], fma(A[a3], x[3], fma(A[a2], x[2], fma(A[a1], x[1], A[a0]*x[0])))))
+  y[0] = MJB_ROW6(0, 1, 2, 3, 4, 5);
+  y[1] = MJB_ROW6(1, 6, 7, 8, 9, 10);
+  y[2] = MJB_ROW6(2, 7, 11, 12, 13, 14);
+  y[3] = MJB_ROW6(3, 8, 12, 15, 16, 17);
+  y[4] = MJB_ROW6(4, 9, 13, 16, 18, 19);
+  y[5] = MJB_ROW6(5, 10, 14, 17, 19, 20);
+#undef MJB_ROW6
 }
 
 // the 10-number rigid inertia of mju_inertCom as a symmetric 6x6 (layout of mju_mulInertVec)
@@ -3643,7 +3733,8 @@ MJB_HD inline void inertia(Ctx& c) {
     const int flags = tree_flags[b];
     {
       double ci[10];
-      ldn(ci, cinert, 10*b, 10);
+      if (c.lci) { for (int j = 0; j < 10; j++) ci[j] = c.lci[10*(b - c.lbody0) + j]; }
+      else ldn_ro(ci, cinert, 10*b, 10);
       if (carried) {
         for (int j = 0; j < 10; j++) cr[j] += ci[j];
         inert_add_sym6(A, ci);
@@ -3676,11 +3767,12 @@ MJB_HD inline void inertia(Ctx& c) {
         continue;
       }
       double S[6], buf[6], U[6];
-      ldn(S, cdof, 6*k, 6);
-      mulInertVec(buf, cr, S);
+      if (c.lcd) { for (int j = 0; j < 6; j++) S[j] = c.lcd[6*(k - c.ldof0) + j]; }
+      else ldn_ro(S, cdof, 6*k, 6);
+      mulInertVecF(buf, cr, S);
       sym6_mul(U, A, S);
-      const double Mkk = armature[k] + dot6(S, buf);
-      const double D = armature[k] + dot6(S, U);
+      const double Mkk = armature[k] + dot6f(S, buf);
+      const double D = armature[k] + dot6f(S, U);
       const double invD = 1/D;
       qM[(size_t)madr*N] = Mkk;
       qLD[(size_t)diag*N] = D;
@@ -3693,13 +3785,17 @@ MJB_HD inline void inertia(Ctx& c) {
         int n = 0;
 #pragma unroll
         for (int g = 0; g < MJB_ANC; g++) {
-          if (i >= 0) { ldn(Si[g], cdof, 6*i, 6); i = dof_parentid[i]; n = g + 1; }
+          if (i >= 0) {
+            if (c.lcd && i >= c.ldof0) { for (int j = 0; j < 6; j++) Si[g][j] = c.lcd[6*(i - c.ldof0) + j]; }
+            else ldn_ro(Si[g], cdof, 6*i, 6);
+            i = dof_parentid[i]; n = g + 1;
+          }
         }
 #pragma unroll
         for (int g = 0; g < MJB_ANC; g++) {
           if (g < n) {
-            qM[(size_t)(madr + t + g)*N] = dot6(Si[g], buf);
-            qLD[(size_t)(diag - t - g)*N] = dot6(Si[g], U) * invD;
+            qM[(size_t)(madr + t + g)*N] = dot6f(Si[g], buf);
+            qLD[(size_t)(diag - t - g)*N] = dot6f(Si[g], U) * invD;
           }
         }
         t += n;
@@ -3708,7 +3804,7 @@ MJB_HD inline void inertia(Ctx& c) {
       int e = 0;
       for (int r = 0; r < 6; r++) {
         const double ur = U[r]*invD;
-        for (int q = r; q < 6; q++) A[e++] -= ur*U[q];
+        for (int q = r; q < 6; q++, e++) A[e] = fma(-ur, U[q], A[e]);
       }
     }
     const int p = body_parentid[b];
@@ -3787,6 +3883,9 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
 //   contact  : mj_collision + contact rows             (only when contacts are enabled)
 //   backward : mj_rne(flg_acc=1), J'f, final combine, output bookkeeping
 
+template <bool kSpatial>
+MJB_HD inline void smooth_tail(Ctx& c);
+
 template <bool kSpatial, int kLo = 1, int kHi = 0>
 MJB_HD inline void phase_smooth(Ctx& c) {
   const mjbHdr& H = *c.H;
@@ -3798,12 +3897,16 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   }
   forward_sweep<kLo, kHi>(c);   // incl. input checks, joint springs/dampers, dof friction and joint limit rows
   if (kHi != 0 && kHi < H.nbody) { save_counters(c); return; }
+  smooth_tail<kSpatial>(c);
+}
+
+// what follows the sweep over the last body: tendons, equality rows, the row counters
+template <bool kSpatial>
+MJB_HD inline void smooth_tail(Ctx& c) {
+  const mjbHdr& H = *c.H;
   tendon_kinematics<kSpatial>(c);
   passive_tendons<kSpatial>(c);
-  {
-    double* fe = SC(cfrc_ext); double* fe1 = SC(cfrc_ext1);
-    for (int i = 0; i < 6*H.nbody; i++) { AT(fe, i) = 0; AT(fe1, i) = 0; }
-  }
+  wmask_clear(c);          // no wrench on any body yet (the accumulator rows themselves are not cleared)
   if (rows_enabled(H)) {
     equality_rows(c);      // rows [0, ne)
     tendon_friction_rows<kSpatial>(c);
@@ -3816,6 +3919,92 @@ MJB_HD inline void phase_smooth(Ctx& c) {
 
 template <int kLo = 1, int kHi = 0>
 MJB_HD inline void phase_inertia(Ctx& c) { inertia<kLo, kHi>(c); }
+
+// Active joint-limit rows of all joints in front of body `lo`, from the inputs alone (a limit is
+// active iff dist < margin, which depends on qpos and the model only: same expressions as
+// joint_limit_rows / quat_dof_forces). The tree stages below run body ranges in an order that is
+// not the body order, while a limit row's index is its rank in body order.
+MJB_HD inline int limit_rows_before(Ctx& c, int lo) {
+  const mjbHdr& H = *c.H;
+  if ((H.disableflags & MJB_DSBL_LIMIT) || !rows_enabled(H)) return 0;
+  const int* jnt_type = MI(jnt_type); const int* jnt_limited = MI(jnt_limited);
+  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_bodyid = MI(jnt_bodyid);
+  const double* jnt_range = MD(jnt_range); const double* jnt_margin = MD(jnt_margin);
+  int n = 0;
+  MJB_UNROLL
+  for (int j = 0; j < H.njnt; j++) {
+    if (jnt_bodyid[j] >= lo || !jnt_limited[j]) continue;    // joints are ordered by body
+    const int jt = jnt_type[j], qadr = jnt_qposadr[j];
+    const double margin = jnt_margin[j];
+    if (jt == MJB_JNT_HINGE || jt == MJB_JNT_SLIDE) {
+      const double q = QPOS(qadr);
+      for (int side = -1; side <= 1; side += 2) {
+        const double dist = side * (jnt_range[2*j + (side + 1)/2] - q);
+        if (dist < margin) n++;
+      }
+    } else if (jt == MJB_JNT_BALL) {
+      double quat[4], aa[3];
+      for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + k);
+      normalize4(quat);
+      quat2Vel(aa, quat, 1);
+      const double value = normalize3(aa);
+      const double dist = fmax(jnt_range[2*j], jnt_range[2*j + 1]) - value;
+      if (dist < margin) n++;
+    }
+  }
+  return n;
+}
+
+// Tree stages of the model-specialised build (mjb_jit.cu plans them, mjb_spec_kernels.cuh launches
+// one kernel per stage). The tree is cut into a TRUNK (bodies whose subtree is too large for one
+// kernel) and complete SUBTREES:
+//   kTreeFwd   : forward sweep over a range of trunk bodies                 (runs first, ascending)
+//   kTreeFused : forward sweep over a range of complete subtrees, then mj_crb + mj_factorM over the
+//                same range while cinert / cdof of its bodies are still in registers; the composite
+//                inertias are pushed to the (trunk) parent through its scratch accumulators
+//   kTreeBwd   : mj_crb + mj_factorM over a range of trunk bodies
+// Fused and Bwd stages run in DESCENDING body order, which is the order the accumulator protocol of
+// inertia() assumes (highest-index child first). kTail adds what follows the last body of the
+// sweep (tendons, equality rows, row counters); it is attached to the stage that runs last.
+// cinert of subtree bodies is never written to HBM, and cdof / cinert are not read back from it.
+enum { kTreeFwd = 0, kTreeFused = 1, kTreeBwd = 2 };
+
+template <bool kSpatial, int kMode, int kLo, int kHi, bool kFirst, bool kTail, int kBodies, int kDof0, int kDofs>
+MJB_HD inline void phase_tree(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  double lci[kMode == kTreeFused ? 10*kBodies : 1];
+  double lcd[kMode == kTreeFused ? 6*(kDofs > 0 ? kDofs : 1) : 1];
+  if (kMode != kTreeBwd) {
+    if (kFirst) {
+      c.ncon = c.ne = c.nf = c.nl = c.nefc = 0;
+      c.status = 0;
+    } else {
+      load_counters(c);
+    }
+    // limit rows are numbered in body order: number this range's rows from the rank of its first row
+    const int total_before = c.nl;
+    const int prefix = limit_rows_before(c, kLo);
+    c.nl = prefix;
+    if (kMode == kTreeFused) {
+      c.lci = lci; c.lcd = lcd;
+      c.lbody0 = kLo; c.ldof0 = kDof0;
+      forward_sweep<kLo, kHi, false>(c);
+    } else {
+      forward_sweep<kLo, kHi, true>(c);
+    }
+    c.nl = total_before + (c.nl - prefix);
+  }
+  if (kMode != kTreeFwd) {
+    inertia<kLo, kHi>(c);
+    c.lci = nullptr; c.lcd = nullptr;
+  }
+  if (kTail) {
+    if (kMode == kTreeBwd) load_counters(c);
+    smooth_tail<kSpatial>(c);      // ends with save_counters
+  } else if (kMode != kTreeBwd) {
+    save_counters(c);
+  }
+}
 
 MJB_HD inline bool contacts_enabled(const mjbHdr& H) {
   return !(H.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT)) && H.ncand > 0;
@@ -3887,6 +4076,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
 #undef SC
 #undef AT
 #undef ldn
+#undef ldn_ro
 #undef sts
 #undef stc
 #undef stn

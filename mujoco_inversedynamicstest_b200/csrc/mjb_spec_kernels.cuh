@@ -39,6 +39,7 @@ __device__ __forceinline__ void spec_ctx(Ctx& c, const LaunchArgs& a) {
   c.sm = nullptr; c.sc = nullptr; c.isc = nullptr;
   c.qpos = nullptr; c.qvel = nullptr; c.qacc = nullptr;
   c.s = 0;
+  c.lci = nullptr; c.lcd = nullptr; c.lbody0 = 0; c.ldof0 = 0;
 }
 
 __device__ __forceinline__ void spec_bind(Ctx& c, const LaunchArgs& a, long long local) {
@@ -105,6 +106,25 @@ MJBS_SMOOTH_STAGES(MJBS_DEFINE_SMOOTH)
     }                                                                                              \
   }
 MJBS_INERTIA_STAGES(MJBS_DEFINE_INERTIA)
+
+// tree stages (trunk forward / fused subtree / trunk backward, mjb_pipeline.h phase_tree), used when
+// the inertia outputs are requested; launched in the order of the list
+#ifndef MJBS_TREE_CTAS
+#define MJBS_TREE_CTAS 2
+#endif
+#define MJBS_DEFINE_TREE(idx, mode, lo, hi, first, tail, nbodies, dof0, ndofs)                     \
+  extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_TREE_CTAS)                      \
+  mjbs_tree_##idx(mjb::LaunchArgs a) {                                                             \
+    __shared__ double carry_slots[MJB_SM_SLOTS * mjb::kThreads];                                   \
+    mjb::Ctx c;                                                                                    \
+    mjb::spec_ctx(c, a);                                                                           \
+    c.sm = carry_slots + threadIdx.x;                                                              \
+    MJBS_STATE_LOOP(i) {                                                                           \
+      mjb::spec_bind(c, a, i);                                                                     \
+      mjb::phase_tree<MJB_SPEC_SPATIAL != 0, mode, lo, hi, first, tail, nbodies, dof0, ndofs>(c);  \
+    }                                                                                              \
+  }
+MJBS_TREE_STAGES(MJBS_DEFINE_TREE)
 
 extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_SCAN_CTAS) mjbs_contact_scan(mjb::LaunchArgs a) {
   mjb::Ctx c;

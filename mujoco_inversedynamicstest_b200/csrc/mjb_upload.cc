@@ -739,6 +739,14 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         }
       }
     }
+    // bodies whose velocity / acceleration carriers (cvel, cacc_lin) a later phase reads: the two
+    // bodies of every candidate pair (contact rows) and the bodies flagged above (equality rows,
+    // tendon sites)
+    for (int i = 0; i < ncand; i++) {
+      const int* ci = cand_int.data() + (size_t)i * MJB_CAND_NI;
+      flags[ci[MJB_CI_B1]] |= 16; flags[ci[MJB_CI_B2]] |= 16;
+    }
+    for (int b = 0; b < m->nbody; b++) if (flags[b] & 8) flags[b] |= 16;
     pushInts(MJB_I_body_tree_flags, flags.data(), flags.size());
     // geom frames a later phase reads (see body_geoms)
     std::vector<int> geom_store(m->ngeom, 0);

@@ -30,7 +30,7 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
   }
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
   std::vector<double> scratch((size_t)H->nscratch + 1);
-  std::vector<int> iscratch_v((size_t)mjb::MJB_ISC_MASK + (size_t)((H->ncand + 31) / 32) + 1);
+  std::vector<int> iscratch_v((size_t)mjb::isc_rows(*H));
   int* iscratch = iscratch_v.data();
   std::vector<double> qacc_discrete(H->discrete_acc ? (size_t)H->nv * nbatch : 1);
   for (int s = 0; s < nbatch; s++) {
@@ -50,6 +50,7 @@ int hostemu_inverse(const mjModel_* m, int nbatch, const double* qpos_soa, const
     c.nconmax = nconmax;
     c.njmax = njmax;
     c.out = *out;
+    c.lci = nullptr; c.lcd = nullptr; c.lbody0 = 0; c.ldof0 = 0;
     mjb::inverse_one_state(c, qacc_discrete.data());
   }
   return 0;

@@ -18,12 +18,14 @@ BIN = os.path.join(util.ROOT, "tests", "cabi", "_bin", "dropin")
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="tests/cabi/_bin/dropin not built (python tests/cabi/build_dropin.py)")
-@pytest.mark.parametrize("name,n", [("humanoid", 2048), ("humanoid_nocontact", 512), ("zoo", 512), ("weld", 256)])
-def test_compiled_c_dropin(name, n):
+# weld: components that cancel between large weld forces (util.STRICT_EXCEPTIONS); a few entries allowed
+@pytest.mark.parametrize("name,n,allowed", [("humanoid", 2048, 0), ("humanoid_nocontact", 512, 0), ("zoo", 512, 0),
+                                            ("weld", 256, 16)])
+def test_compiled_c_dropin(name, n, allowed):
     with tempfile.NamedTemporaryFile(suffix=".mjb", delete=False) as tf:
         tf.write(gzip.open(os.path.join(util.GOLDEN, name + ".mjb.gz"), "rb").read())
     try:
-        r = subprocess.run([BIN, tf.name, str(n)], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([BIN, tf.name, str(n), str(allowed)], capture_output=True, text=True, timeout=600)
     finally:
         os.remove(tf.name)
     print(r.stdout, r.stderr)
