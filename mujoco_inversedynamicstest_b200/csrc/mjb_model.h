@@ -71,6 +71,10 @@
   X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(sensor_int) /* nsensor*MJB_SEN_NI : sensors evaluated on the device, see MJB_SEN_*       */ \
+  X(scan_int)  /* ncand*2 : compact rows of the bounding-sphere scan: geom 1 | filter kind << 28, geom 2      */ \
+  X(scan_run)  /* nrun*4  : runs of consecutive candidates with the same (tree of body 1, tree of body 2):   \
+                            first candidate, count, tree 1, tree 2 (-1: static body, never culled)           */ \
+  X(tree_int)  /* ntree*3 : kinematic trees: root body, first geom, one past the last geom                   */ \
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored), \
                                  bit3 pose read by an equality constraint or a tendon site, \
@@ -126,6 +130,8 @@
   X(sp_eq)            /* neq     */ \
   X(eq_num)           /* neq*MJB_EQ_NN: site offsets / quaternions of site-defined constraints */ \
   X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */ \
+  X(scan_bound)       /* ncand: MJB_CN_RBOUND of every candidate, contiguous (the scan reads nothing else) */ \
+  X(scan_misc)        /* 1: largest contact margin of any candidate (tree-level culling) */ \
   X(sensor_cutoff)    /* nsensor */
 
 enum {
@@ -261,6 +267,7 @@ enum {
   MJB_SC_ia,           // nbody*21  articulated-body inertias (symmetric 6x6, upper triangle)
   MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
   MJB_SC_weld_dt,      // neq*3     weld rows: (raw rotational efc_force) - (torque J'f), for the cfrc_ext output (only models with welds)
+  MJB_SC_tree_sphere,  // ntree*4   bounding sphere of every kinematic tree (tree-level broadphase; only with scan runs)
   MJB_SC_COUNT
 };
 
@@ -291,7 +298,8 @@ typedef struct mjbHdr_ {
   int32_t pad0;
   double timestep, impratio;
   double gravity[3];
-  double pad1;
+  int32_t nrun;             // runs of the candidate list for the tree-level broadphase (0: flat scan)
+  int32_t ntree;            // kinematic trees with collidable geoms
   int32_t ioff[MJB_NI];     // element offsets into the int section
   int32_t noff[MJB_NN];     // element offsets into the double section
   int32_t scoff[MJB_SC_COUNT];  // scratch slot offsets (doubles per thread)

@@ -2865,18 +2865,28 @@ MJB_HD inline void collide_pair(Ctx& c, int ci) {
 MJB_HD inline int contact_scan(Ctx& c) {
   const mjbHdr& H = *c.H;
   double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
-  const int* cand_int = MI(cand_int);
-  const double* cand_num = MD(cand_num);
+  // compact scan rows (mjb_upload.cc): geom 1 | kind << 28, geom 2, and the bound
+  const int* scan_int = MI(scan_int);
+  const double* scan_bound = MD(scan_bound);
   const int ncand = H.ncand;
   int last_g1 = -1, total = 0;
   double pos1[3] = {0, 0, 0}, nrm[3] = {0, 0, 0};
+  // survivor words are written in order; `cw` is the word being assembled in `bits`
   unsigned bits = 0;
-  MJB_UNROLL
-  for (int ci = 0; ci < ncand; ci++) {
-    const int* cint = cand_int + MJB_CAND_NI*ci;
-    const double bound = cand_num[MJB_CAND_NN*ci + MJB_CN_RBOUND];
-    const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
-    const int planeflag = cint[MJB_CI_PLANE];
+  int cw = 0;
+  auto advance_to = [&](int ci) {        // candidates up to ci are decided: flush the words in front of ci's
+    const int w = ci >> 5;
+    if (w != cw) {
+      c.isc[(size_t)(MJB_ISC_MASK + cw) * MJB_LS] = (int)bits;
+      for (int k = cw + 1; k < w; k++) c.isc[(size_t)(MJB_ISC_MASK + k) * MJB_LS] = 0;
+      bits = 0;
+      cw = w;
+    }
+  };
+  auto test = [&](int ci) {
+    const int g1k = scan_int[2*ci], g2 = scan_int[2*ci + 1];
+    const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
+    const double bound = scan_bound[ci];
     if (g1 != last_g1) {          // candidates are grouped by geom 1: keep it in registers
       ldn(pos1, gxpos, 3*g1, 3);
       if (planeflag == 1) { nrm[0] = AT(gxmat, 9*g1 + 2); nrm[1] = AT(gxmat, 9*g1 + 5); nrm[2] = AT(gxmat, 9*g1 + 8); }
@@ -2892,11 +2902,54 @@ MJB_HD inline int contact_scan(Ctx& c) {
       const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
       pass = !(dot3(dif, nrm) > bound);
     }
+    advance_to(ci);
     if (pass) { bits |= 1u << (ci & 31); total++; }
-    if ((ci & 31) == 31 || ci == ncand - 1) {
-      c.isc[(size_t)(MJB_ISC_MASK + (ci >> 5)) * MJB_LS] = (int)bits;
-      bits = 0;
+  };
+  if (H.nrun == 0) {
+    MJB_UNROLL
+    for (int ci = 0; ci < ncand; ci++) test(ci);
+  } else {
+    // tree-level broadphase: bounding sphere of every kinematic tree about its origin, over the
+    // geoms a candidate pair reads; a run of candidates between two trees is skipped when the
+    // spheres are further apart than the largest contact margin. A warp skips a run only if all of
+    // its 32 states do (uniform control flow; the others' tests fail anyway).
+    const int* tree_int = MI(tree_int); const int* geom_store = MI(geom_store);
+    const double* rbound = MD(geom_rbound);
+    double* org = SC(origin); double* ts = SC(tree_sphere);
+    const double max_margin = MD(scan_misc)[0];
+    for (int t = 0; t < H.ntree; t++) {
+      double O[3], r = 0;
+      ldn(O, org, 3*tree_int[3*t], 3);
+      for (int g = tree_int[3*t + 1]; g < tree_int[3*t + 2]; g++) {
+        if (!geom_store[g]) continue;
+        double p[3];
+        ldn(p, gxpos, 3*g, 3);
+        const double d[3] = {p[0] - O[0], p[1] - O[1], p[2] - O[2]};
+        r = fmax(r, sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]) + rbound[g]);
+      }
+      const double rec[4] = {O[0], O[1], O[2], r};
+      stn(ts, 4*t, rec, 4);
     }
+    const int* run = MI(scan_run);
+    for (int k = 0; k < H.nrun; k++) {
+      const int first = run[4*k], count = run[4*k + 1], t1 = run[4*k + 2], t2 = run[4*k + 3];
+      bool near = true;
+      if (t1 >= 0 && t2 >= 0 && t1 != t2) {
+        double a[4], b4[4];
+        ldn(a, ts, 4*t1, 4); ldn(b4, ts, 4*t2, 4);
+        const double d[3] = {a[0] - b4[0], a[1] - b4[1], a[2] - b4[2]};
+        // slack of 1e-9 relative: the skip must never be tighter than the geom-level test it replaces
+        const double reach = (a[3] + b4[3] + max_margin) * (1 + 1e-9) + 1e-12;
+        near = !(d[0]*d[0] + d[1]*d[1] + d[2]*d[2] > reach*reach);
+      }
+      if (!MJB_WARP_ANY(near)) continue;           // every candidate of the run fails: bits stay 0
+      for (int ci = first; ci < first + count; ci++) test(ci);
+    }
+  }
+  // flush the word in progress and clear the words behind it
+  if (ncand > 0) {
+    c.isc[(size_t)(MJB_ISC_MASK + cw) * MJB_LS] = (int)bits;
+    for (int k = cw + 1; k <= (ncand - 1) >> 5; k++) c.isc[(size_t)(MJB_ISC_MASK + k) * MJB_LS] = 0;
   }
   c.isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
   return total;

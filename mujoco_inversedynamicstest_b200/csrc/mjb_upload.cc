@@ -524,6 +524,62 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 
   if (ncand >= (1 << 27)) { err = "too many candidate geom pairs (>= 2^27)"; return false; }
 
+  // ---- compact tables of the bounding-sphere scan, and the tree-level broadphase
+  // The scan (mj_filterSphere per candidate) reads 16 bytes per candidate -- geom ids, filter kind,
+  // bound -- instead of the 256-byte candidate record, so that even the ~90 K candidates of the
+  // 22-humanoid scene stay resident in L2. For scenes with several kinematic trees the candidate
+  // list is cut into runs of equal (tree of body 1, tree of body 2); the scan skips a run when the
+  // bounding spheres of the two trees do not overlap (what mj_broadphase's sweep achieves with body
+  // AABBs, engine_collision_driver.c:1148-1282; conservative, so the survivors are unchanged).
+  std::vector<int> scan_int((size_t)ncand * 2), scan_run, tree_int;
+  std::vector<double> scan_bound((size_t)ncand), scan_misc(1, 0.0);
+  int nrun = 0, ntree = 0;
+  {
+    if (m->ngeom >= (1 << 28)) { err = "too many geoms"; return false; }
+    for (int i = 0; i < ncand; i++) {
+      const int* ci = cand_int.data() + (size_t)i * MJB_CAND_NI;
+      scan_int[2*i] = ci[MJB_CI_G1] | (ci[MJB_CI_PLANE] << 28);
+      scan_int[2*i + 1] = ci[MJB_CI_G2];
+      scan_bound[i] = cand_num[(size_t)i * MJB_CAND_NN + MJB_CN_RBOUND];
+      scan_misc[0] = std::max(scan_misc[0], cand_num[(size_t)i * MJB_CAND_NN + MJB_CN_MARGIN]);
+    }
+    // trees: maximal sets of moving bodies with the same root; static bodies (weldid 0) have none
+    std::vector<int> tree_of(m->nbody, -1);
+    for (int b = 1; b < m->nbody; b++) {
+      if (m->body_weldid[b] == 0) continue;
+      const int r = m->body_rootid[b];
+      if (tree_of[r] < 0) { tree_of[r] = ntree++; tree_int.push_back(r); tree_int.push_back(m->ngeom); tree_int.push_back(0); }
+      tree_of[b] = tree_of[r];
+    }
+    for (int g = 0; g < m->ngeom; g++) {
+      const int t = tree_of[m->geom_bodyid[g]];
+      if (t < 0) continue;
+      tree_int[3*t + 1] = std::min(tree_int[3*t + 1], g);
+      tree_int[3*t + 2] = std::max(tree_int[3*t + 2], g + 1);
+    }
+    for (int t = 0; t < ntree; t++) if (tree_int[3*t + 1] > tree_int[3*t + 2]) tree_int[3*t + 1] = tree_int[3*t + 2] = 0;
+    // runs are worth their bookkeeping only for multi-tree scenes with long candidate lists
+    if (ntree >= 2 && ncand >= 1024) {
+      int i = 0;
+      while (i < ncand) {
+        const int* ci = cand_int.data() + (size_t)i * MJB_CAND_NI;
+        const int t1 = tree_of[ci[MJB_CI_B1]], t2 = tree_of[ci[MJB_CI_B2]];
+        int j = i + 1;
+        while (j < ncand) {
+          const int* cj = cand_int.data() + (size_t)j * MJB_CAND_NI;
+          if (tree_of[cj[MJB_CI_B1]] != t1 || tree_of[cj[MJB_CI_B2]] != t2) break;
+          j++;
+        }
+        scan_run.push_back(i); scan_run.push_back(j - i); scan_run.push_back(t1); scan_run.push_back(t2);
+        nrun++;
+        i = j;
+      }
+    } else {
+      ntree = 0;
+      tree_int.clear();
+    }
+  }
+
   // ---- sparse structure of qLD: row i = ancestors of dof i ascending, then i
   // (makeDofDofSparse with reduced/upper flags as used for C, engine_io.c:929-1018; mapM2C :1135)
   const int nv = m->nv;
@@ -620,11 +676,27 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   }
 
   // tendons that carry a force; spatial ones with springs/dampers need the passive wrench carrier
+  // A tendon whose path touches no dof has an empty Jacobian row: mj_addConstraint drops its friction
+  // and limit rows (engine_core_constraint.c:265-330 -- dense: every entry of the row is zero,
+  // sparse: the dof chain is empty; reference models core_constraint/dofless_tendon_*.xml). That is
+  // a property of the model: spatial tendons between sites / geoms of static bodies, and (dense
+  // only) fixed tendons whose coefficients are all zero.
+  std::vector<int> tendon_empty(m->ntendon, 0);
+  for (int t = 0; t < m->ntendon; t++) {
+    bool empty = true;
+    for (int j = 0; j < m->tendon_num[t] && empty; j++) {
+      const int w = m->tendon_adr[t] + j, wt = m->wrap_type[w], id = m->wrap_objid[w];
+      if (wt == mjWRAP_JOINT) empty = !isSparseJacobian(m) && m->wrap_prm[w] == 0;
+      else if (wt == mjWRAP_SITE) empty = m->body_weldid[m->site_bodyid[id]] == 0;
+      else if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) empty = m->body_weldid[m->geom_bodyid[id]] == 0;
+    }
+    tendon_empty[t] = empty;
+  }
   std::vector<int> tendon_active(m->ntendon, 0);
   bool spatial_passive = false, spatial_active = false;
   for (int t = 0; t < m->ntendon; t++) {
-    const bool lim = m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints;
-    const bool fric = m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints;
+    const bool lim = m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints && !tendon_empty[t];
+    const bool fric = m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints && !tendon_empty[t];
     const bool pas = (m->tendon_stiffness[t] != 0 || m->tendon_damping[t] != 0) && !(dsbl & mjDSBL_PASSIVE);
     tendon_active[t] = lim || fric || pas;
     if (pas && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_passive = true;
@@ -647,6 +719,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nq = m->nq; H.nv = nv; H.nbody = m->nbody; H.njnt = m->njnt; H.ngeom = m->ngeom;
   H.ntendon = m->ntendon; H.nwrap = m->nwrap; H.neq = neq; H.nM = m->nM; H.nC = m->nC;
   H.ncand = ncand;
+  H.nrun = nrun; H.ntree = ntree;
   H.max_pair_contacts = max_pair_contacts;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
@@ -685,6 +758,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_C_colind, C_colind.data(), C_colind.size());
   pushInts(MJB_I_mapM2C, mapM2C.data(), mapM2C.size());
   pushInts(MJB_I_cand_int, cand_int.data(), cand_int.size());
+  pushInts(MJB_I_scan_int, scan_int.data(), scan_int.size());
+  pushInts(MJB_I_scan_run, scan_run.data(), scan_run.size());
+  pushInts(MJB_I_tree_int, tree_int.data(), tree_int.size());
   pushInts(MJB_I_eq_int, eq_int.data(), eq_int.size());
   pushInts(MJB_I_sensor_int, sensor_int.data(), sensor_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
@@ -697,7 +773,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     int nfd = 0, nft = 0, ne_rows = 0;
     if (rows && !(dsbl & mjDSBL_FRICTIONLOSS)) {
       for (int i = 0; i < nv; i++) if (m->dof_frictionloss[i] > 0) frow[i] = nfd++;
-      for (int t = 0; t < m->ntendon; t++) if (m->tendon_frictionloss[t] > 0) nft++;
+      for (int t = 0; t < m->ntendon; t++) if (m->tendon_frictionloss[t] > 0 && !tendon_empty[t]) nft++;
     }
     if (rows) {
       for (int i = 0; i < neq; i++) {
@@ -770,6 +846,11 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 #define X(name, rows, cols) pushNums(MJB_N_##name, m->name, (size_t)m->rows * (cols));
   MJB_NUM_ARRAYS(X)
 #undef X
+  for (int t = 0; t < m->ntendon; t++) {          // rows of empty tendons are never instantiated
+    if (!tendon_empty[t]) continue;
+    nums[H.noff[MJB_N_tendon_frictionloss] + t] = 0;
+    ints[H.ioff[MJB_I_tendon_limited] + t] = 0;
+  }
   pushNums(MJB_N_sp_jnt_limit, sp_jnt.data(), sp_jnt.size());
   pushNums(MJB_N_sp_tendon_limit, sp_tl.data(), sp_tl.size());
   pushNums(MJB_N_sp_dof_friction, sp_df.data(), sp_df.size());
@@ -777,6 +858,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_sp_eq, sp_eq.data(), sp_eq.size());
   pushNums(MJB_N_eq_num, eq_num.data(), eq_num.size());
   pushNums(MJB_N_cand_num, cand_num.data(), cand_num.size());
+  pushNums(MJB_N_scan_bound, scan_bound.data(), scan_bound.size());
+  pushNums(MJB_N_scan_misc, scan_misc.data(), scan_misc.size());
   pushNums(MJB_N_sensor_cutoff, sensor_cutoff.data(), sensor_cutoff.size());
 
   // scratch layout
@@ -797,6 +880,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       for (int i = 0; i < m->neq; i++) has_weld = has_weld || m->eq_type[i] == mjEQ_WELD;
       sizes[MJB_SC_weld_dt] = has_weld ? 3*m->neq : 0;
     }
+    sizes[MJB_SC_tree_sphere] = 4*ntree;
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;
@@ -820,7 +904,7 @@ const char* scratchSlotName(int slot) {
     "xpos", "xquat", "origin", "geom_xpos", "geom_xmat",
     "cinert", "cdof", "cvel", "cacc_lin", "cacc", "cfrc",
     "cfrc_ext", "cfrc_ext1", "qfrc_c", "qfrc_passive", "ten_length", "ten_velocity", "ten_acc", "crb", "ia",
-    "cfrc_gc", "weld_dt"};
+    "cfrc_gc", "weld_dt", "tree_sphere"};
   return (slot >= 0 && slot < MJB_SC_COUNT) ? names[slot] : nullptr;
 }
 

@@ -77,3 +77,39 @@ def generate_states(model, n, first=0, seed=SEED, z_range=(0.0, 1.5)):
         qvel[:, i] = 2 * _uniform(seed, idx, 100000 + i) - 1
         qacc[:, i] = 20 * _uniform(seed, idx, 200000 + i) - 10
     return qpos, qvel, qacc
+
+
+def near_default_states(model, n, scale=0.05, seed=SEED):
+    """State 0 = the model's default state (qpos0, zero velocity and acceleration), as the
+    reference's own tests evaluate it; states 1 .. n-1 = qpos0 perturbed by `scale` (positions and
+    scalar joints +- scale, quaternions re-normalised after a perturbation of N(0, scale)), with
+    qvel ~ U(-1, 1) and qacc ~ U(-10, 10). Used for the reference's edge-case models, whose contact
+    structure (stacked boxes, touching spheres) only exists near the default pose."""
+    nq, nv, njnt = model.int("nq"), model.int("nv"), model.int("njnt")
+    jnt_type = model.array("jnt_type").ravel()
+    jnt_qposadr = model.array("jnt_qposadr").ravel()
+    qpos0 = model.array("qpos0").ravel()
+    idx = np.arange(0, n, dtype=np.uint64)
+    qpos = np.tile(qpos0[None, :], (n, 1)) if nq else np.empty((n, 0))
+    for j in range(njnt):
+        t, a = int(jnt_type[j]), int(jnt_qposadr[j])
+        if t == 0:
+            for k in range(3):
+                qpos[:, a + k] += scale * (2 * _uniform(seed, idx, 300000 + a + k) - 1)
+            a += 3
+        if t in (0, 1):
+            q = qpos[:, a:a + 4] + scale * np.stack([_normal(seed, idx, 300000 + a + k) for k in range(4)], axis=1)
+            qpos[:, a:a + 4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        else:
+            qpos[:, a] += scale * (2 * _uniform(seed, idx, 300000 + a) - 1)
+    qvel = np.empty((n, nv))
+    qacc = np.empty((n, nv))
+    for i in range(nv):
+        qvel[:, i] = 2 * _uniform(seed, idx, 100000 + i) - 1
+        qacc[:, i] = 20 * _uniform(seed, idx, 200000 + i) - 10
+    if n and nq:
+        qpos[0] = qpos0
+    if n:
+        qvel[0] = 0
+        qacc[0] = 0
+    return qpos, qvel, qacc

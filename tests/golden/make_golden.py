@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import reflib  # noqa: E402
-from mujoco_inversedynamicstest_b200.states import generate_states  # noqa: E402
+from mujoco_inversedynamicstest_b200.states import generate_states, near_default_states  # noqa: E402
 
 DSBL_CONTACT, DSBL_EQUALITY = 1 << 4, 1 << 1
 
@@ -125,6 +125,77 @@ def make_reduced_case(name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
     print(f"{name}: nv={m.int('nv')} states={nstate} mean ncon={out['ncon'].mean():.1f} "
           f"mean nefc={out['nefc'].mean():.1f} max={out['ncon'].max()}/{out['nefc'].max()}")
+
+
+# The reference's own edge-case models (what pins results in the reference's tests), run
+# through mj_inverse at the default state (state 0, what those tests evaluate) and at perturbed
+# states around it. name -> (xml, {opt overrides}, nstate, nconmax, njmax)
+T = "test/engine/testdata/"
+DSBL_FILTERPARENT, JAC_DENSE, JAC_SPARSE = 1 << 9, 0, 1
+EDGE_CASES = {
+    # engine_collision_driver_test.cc:52-68 (pairs), :99-132 (ncon == 8), :134-203 (parent filter)
+    "ref_collisions": (T + "collisions.xml", {}, 64, 8, 32),
+    "ref_contact_count": ("repo:tests/golden/models/contact_count.xml", {}, 64, 16, 64),
+    "ref_filter_parent": ("repo:tests/golden/models/filter_parent.xml", {}, 32, 8, 32),
+    "ref_filter_parent_off": ("repo:tests/golden/models/filter_parent.xml", {"disableflags": DSBL_FILTERPARENT}, 32, 8, 32),
+    "ref_filter_parent_world": ("repo:tests/golden/models/filter_parent_world.xml", {}, 32, 8, 32),
+    "ref_midphase": (T + "collision_driver/midphase.xml", {}, 16, 256, 1024),
+    "ref_planks": (T + "collision_driver/planks.xml", {}, 8, 1536, 6144),
+    # engine_collision_box_test.cc:40-277 (bad / duplicate contact removal, deep penetration: ncon == 4)
+    "ref_boxbox_bad0": (T + "collision_box/boxbox_bad0.xml", {}, 64, 64, 256),
+    "ref_boxbox_deep": (T + "collision_box/boxbox_deep.xml", {}, 64, 16, 64),
+    "ref_boxbox_duplicate": (T + "collision_box/boxbox_duplicate.xml", {}, 64, 16, 64),
+    "ref_sphere_cylinder": (T + "collision_primitive/sphere_cylinder.xml", {}, 64, 16, 64),
+    # engine_core_constraint_test.cc:231-251 (dof-less / bilateral-margin models, dense and sparse)
+    "ref_dofless_contact": (T + "core_constraint/dofless_contact.xml", {"jacobian": JAC_DENSE}, 4, 8, 32),
+    "ref_dofless_contact_sparse": (T + "core_constraint/dofless_contact.xml", {"jacobian": JAC_SPARSE}, 4, 8, 32),
+    "ref_dofless_tendon_frictional": (T + "core_constraint/dofless_tendon_frictional.xml", {}, 4, 8, 32),
+    "ref_dofless_tendon_limited": (T + "core_constraint/dofless_tendon_limited.xml", {}, 4, 8, 32),
+    "ref_dofless_tendon_limitedmargin": (T + "core_constraint/dofless_tendon_limitedmargin.xml", {}, 4, 8, 32),
+    "ref_dofless_weld": (T + "core_constraint/dofless_weld.xml", {"jacobian": JAC_DENSE}, 32, 8, 64),
+    "ref_dofless_weld_sparse": (T + "core_constraint/dofless_weld.xml", {"jacobian": JAC_SPARSE}, 32, 8, 64),
+    "ref_joint_limited_bilateral_margin": (T + "core_constraint/joint_limited_bilateral_margin.xml", {}, 64, 8, 32),
+    "ref_tendon_limited_bilateral_margin": (T + "core_constraint/tendon_limited_bilateral_margin.xml", {}, 64, 8, 32),
+    "ref_soft_weld": (T + "core_constraint/soft_weld.xml", {}, 64, 8, 32),
+    # engine_core_smooth_test.cc:466-511 (L'DL == M on inertia.xml), tendon wrapping
+    "ref_inertia": (T + "inertia.xml", {}, 64, 16, 64),
+    "ref_tendon_wrap_cylinder": (T + "core_smooth/tendon_wrap_cylinder.xml", {}, 64, 16, 64),
+    "ref_tendon_wrap_sphere": (T + "core_smooth/tendon_wrap_sphere.xml", {}, 64, 16, 64),
+    # pipeline_test.cc:39-71: dense == sparse Jacobian semantics on the humanoid
+    "ref_humanoid_sparse": ("model/humanoid/humanoid.xml", {"jacobian": JAC_SPARSE}, 64, 64, 256),
+}
+
+
+def make_edge_case(name):
+    xml, opts, nstate, nconmax, njmax = EDGE_CASES[name]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    raw = os.path.join(HERE, name + ".mjb")
+    m.save_mjb(raw)
+    with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb",
+                                             compresslevel=9, mtime=0) as g:
+        g.write(f.read())
+    os.remove(raw)
+    if name == "ref_humanoid_sparse":
+        qpos, qvel, qacc = generate_states(m, nstate)
+    else:
+        qpos, qvel, qacc = near_default_states(m, nstate)
+    fields = {"ncon": 1, "ne": 1, "nf": 1, "nl": 1, "nefc": 1, "contact_geom": nconmax, "contact_dist": nconmax,
+              "contact_dim": nconmax, "contact_exclude": nconmax, "contact_efc_address": nconmax,
+              "efc_type": njmax, "efc_id": njmax, "efc_state": njmax, "efc_force": njmax, "efc_pos": njmax,
+              "qfrc_constraint": None, "qM": None, "qLD": None, "qLDiagInv": None}
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields)
+    assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax, (name, out["ncon"].max(), out["nefc"].max())
+    save = {"nstate": np.array(nstate), "nconmax": np.array(nconmax), "njmax": np.array(njmax),
+            "near_default": np.array(name != "ref_humanoid_sparse")}
+    for k, v in out.items():
+        v = v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v
+        save[k] = v.astype(np.int16) if (v.dtype == np.int32 and k.startswith(("contact_", "efc_"))) else v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(f"{name}: nv={m.int('nv')} ngeom={m.int('ngeom')} states={nstate} ncon at default={out['ncon'][0]} "
+          f"mean ncon={out['ncon'].mean():.2f} mean nefc={out['nefc'].mean():.2f} max={out['ncon'].max()}/{out['nefc'].max()}")
 
 
 # finite-difference Jacobians of the reference (mjd_inverseFD, engine_derivative_fd.c:611) on the
@@ -239,7 +310,7 @@ def make_mocap_case(name):
 
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
-                 list(MOCAP_CASES) + list(REDUCED_CASES)):
-        (make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES)):
+        (make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

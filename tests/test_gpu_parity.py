@@ -507,18 +507,48 @@ def test_item_parallel_and_pooled_contact_paths_agree():
 
 def test_contact_list_overflow_falls_back_on_the_device():
     """A chunk whose contacts do not fit the global lists (22 interpenetrating humanoids: ~290
-    contacts per state against 16 per state of list capacity) is handled by the pooled kernel;
-    the counters of the item path show the overflow and the results are the reference's."""
+    contacts per state against a forced capacity of 16 per state) is handled by the pooled kernel;
+    the counters of the item path show the overflow and the results are the reference's. With the
+    per-model list sizing the same scene runs on the item-parallel path (next test)."""
     import ctypes
     import mujoco_inversedynamicstest_b200 as mjb
     from mujoco_inversedynamicstest_b200._lib import lib
-    model, bd, ref, nbad, _ = _run(mjb, "humanoids22", True, mjb.OUT_COUNTS)
+    import os
+    os.environ["MJB_ITEMS_PER_STATE"] = "48"            # the sizing of a single articulated figure
+    os.environ["MJB_CONTACTS_PER_STATE"] = "16"
+    try:
+        model, bd, ref, nbad, _ = _run(mjb, "humanoids22", True, mjb.OUT_COUNTS)
+    finally:
+        os.environ.pop("MJB_ITEMS_PER_STATE", None)
+        os.environ.pop("MJB_CONTACTS_PER_STATE", None)
     out = (ctypes.c_int * 4)()
     assert lib().mjb_debugQueue(bd._d, out) == 0
     assert out[2] != 0, list(out)                       # overflow flag raised on the device
     np.testing.assert_array_equal(bd.counts()["ncon"], ref["ncon"])
     nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
     assert nviol == 0, (nviol, worst)
+
+
+def test_multi_tree_scene_runs_on_the_item_parallel_path():
+    """22 humanoids (BASELINE config 5), 256 states: the lists are sized from the geom count, so the
+    item-parallel contact kernels handle the scene (no overflow, no pooled fallback); contact lists
+    and efc ordering bit-exact against the 256-state dump."""
+    import ctypes
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200._lib import lib
+    model, bd, ref, nbad, _ = _run(mjb, "humanoids22_256", True, mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC)
+    assert nbad == 0
+    out = (ctypes.c_int * 4)()
+    assert lib().mjb_debugQueue(bd._d, out) == 0
+    assert out[2] == 0, list(out)
+    assert out[0] == int(bd.counts()["ncon"].size and out[0])   # items were appended
+    cnt = bd.counts()
+    for k in ("ncon", "ne", "nf", "nl", "nefc"):
+        np.testing.assert_array_equal(cnt[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
+    efc = bd.efc()
+    for k in ("type", "id", "state"):
+        np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
 
 
 @pytest.mark.parametrize("name", ["humanoid_fd", "zoo_fd", "humanoid_nocontact_fd"])

@@ -205,3 +205,37 @@ def test_upload_rejections():
     h.set_opt_int("integrator", 2)              # mjINT_IMPLICIT needs mjd_smooth_vel
     with pytest.raises(RuntimeError, match="INVDISCRETE"):
         emu.candidates(h)
+
+
+import edge_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", edge_cases.NAMES)
+def test_reference_edge_case_models(name):
+    """collisions.xml / ContactCount / FilterParent / collision_box / core_constraint (dof-less
+    models, dense and sparse) / inertia.xml / tendon wrapping / sparse-forced humanoid: the
+    reference's own edge-case models through the per-state pipeline, against the reference's dump
+    and against the values the reference's tests hold for the default state."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, ref = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = edge_cases.states(model, ref)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]))
+    assert (out["status"] == 0).all()
+    edge_cases.check(name, out, ref)
+    if "qM" in ref and out["qM"].size:
+        # entries that cancel to zero carry the rounding of the largest entry of the matrix
+        atol = 1e-12 * max(1.0, float(np.abs(ref["qM"]).max()))
+        np.testing.assert_allclose(out["qM"], ref["qM"], rtol=1e-9, atol=atol)
+        np.testing.assert_allclose(out["qLD"], ref["qLD"], rtol=1e-9, atol=atol)
+
+
+def test_dense_and_sparse_jacobian_give_the_same_result():
+    """pipeline_test.cc:39-71 (SparseDenseEquivalent): the humanoid with a sparse-forced Jacobian
+    yields the reference's dense results; both dumps come from the reference."""
+    _, dense = util.golden("humanoid")
+    _, sparse = util.golden("ref_humanoid_sparse")
+    n = int(sparse["nstate"])
+    np.testing.assert_array_equal(dense["ncon"][:n], sparse["ncon"])
+    np.testing.assert_array_equal(dense["nefc"][:n], sparse["nefc"])
+    np.testing.assert_allclose(dense["qfrc_inverse"][:n], sparse["qfrc_inverse"], rtol=1e-9, atol=1e-9)

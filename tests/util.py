@@ -30,7 +30,7 @@ STRICT_EXCEPTIONS = {
 # velocities here, dense Jacobian rows there -- which a stiff contact row multiplies by D*B ~ 1e6-1e8).
 # The test allows LIVE_STRICT_FRACTION of the entries outside the element-wise bound, of which at most
 # LIVE_SCALED_FRACTION may also exceed 1e-9 * max(|ref_i|, 1e-3 * max_j |ref_j|) (measured: 2-3
-# entries), and requires EVERY entry inside 1e-9 * max(|ref_i|, 1e-2 * max_j |ref_j|).
+# entries), and requires every entry to be within 1e-9 of the largest force of its state.
 LIVE_STRICT_FRACTION = 1e-5
 LIVE_SCALED_FRACTION = 1e-6
 
