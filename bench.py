@@ -46,7 +46,11 @@ WORKLOADS = {
     "humanoid_nocontact": ("humanoid_nocontact", (2.0, 3.0),
                            "humanoid.xml, mjDSBL_CONTACT"),
     "humanoids22": ("humanoids22", (0.0, 1.5), "22_humanoids.xml (nv=594)"),
+    "arm26": ("arm26", (0.0, 1.5), "tendon_arm/arm26.xml (tendons, joint limits)"),
 }
+# the other BASELINE configs, measured device-resident after the headline (N = 1): config 2, 3b, one
+# point of config 4's sweep, config 5
+OTHER_CONFIGS = ["humanoid_nocontact", "humanoid_contact_elliptic", "arm26", "humanoids22"]
 DEFAULT_WORKLOAD = "humanoid_contact_pyramidal"
 BATCH = {"humanoids22": 1 << 15}
 DEFAULT_BATCH = 1 << 20
@@ -163,6 +167,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(workload, n, world, no_inertia=False):
+    """`config` of the JSON line: the same dict in the mjb arm and in the reference arm (the
+    reference arm's bounded sample is described in its `cpu_baseline.sample`)."""
+    return {"workload": workload, "description": WORKLOADS[workload][2], "states_per_gpu": n,
+            "outputs": "qfrc_inverse" + ("" if no_inertia else "+qM+qLD+qLDiagInv"),
+            "l2": "inputs larger than L2 (hundreds of MB of states per step)",
+            "parallelism": f"batch sharded over {world} GPU(s), no collective"}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -199,6 +212,91 @@ def cpu_reference_rate(golden_name, z_range, nthread, target_seconds=10.0, first
     return n / t, n, t
 
 
+def specialise(bd, generic):
+    """Switch a batch to the kernels compiled for its model (NVRTC, cached next to libmjb.so); the
+    generic kernels stay in use when that is not possible, and the line says which ran."""
+    if generic:
+        return "generic"
+    try:
+        info = bd.specialize()
+        return "specialised (cubin %s)" % ("from cache" if info["from_cache"] else
+                                           "compiled in %.0f s" % info["compile_seconds"])
+    except Exception as exc:
+        return "generic (not specialised: %s)" % str(exc).splitlines()[0][:120]
+
+
+def device_rate(mjb, workload, local_rank, stream, generic, steps=5, warmup=3):
+    """Short device-resident measurement of another BASELINE config (same timing rules)."""
+    import torch
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    golden_name, z_range, _ = WORKLOADS[workload]
+    n = BATCH.get(workload, DEFAULT_BATCH)
+    model = mjb.Model.from_mjb(os.path.join(ROOT, "tests", "golden", golden_name + ".mjb.gz"))
+    qpos, qvel, qacc = generate_states(model, n, z_range=z_range)
+    bd = mjb.BatchData(model, n, device=local_rank, outmask=mjb.OUT_INERTIA, stream=stream.cuda_stream)
+    try:
+        mode = specialise(bd, generic)
+        bd.set_state(qpos, qvel, qacc)
+        for _ in range(warmup):
+            bd.inverse(sync=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            bd.inverse(sync=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        nq, nv = model.int("nq"), model.int("nv")
+        alg = 8 * (nq + 2 * nv) + 8 * nv + 4 + 8 * (model.int("nM") + model.int("nC") + nv)
+        return {"workload": workload, "states_per_gpu": n, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "states/s",
+                "kernel_mode": mode, "bytes_per_state": alg,
+                "hbm_gbs_algorithmic": n * alg / (ms * 1e-3) * 1e-9}
+    finally:
+        bd.close()
+
+
+def parity_sample(mjb, workload, local_rank, stream, generic, nstate=1 << 16, first=1 << 23):
+    """`parity` of the JSON line: a sample of the workload's stream that is in no committed fixture,
+    through the CUDA path and through the reference library (oracle/_ref, the checker): states whose
+    ncon / nefc / nl / nf / ne, contact geom pairs or efc_type / efc_id / efc_state differ, and
+    qfrc_inverse entries outside 1e-9 * |ref| + 1e-12 (element-wise)."""
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    golden_name, z_range, _ = WORKLOADS[workload]
+    rm = load_reference_model(golden_name)
+    model = mjb.Model.from_mjb(os.path.join(ROOT, "tests", "golden", golden_name + ".mjb.gz"))
+    nconmax, njmax = 64, 256
+    qpos, qvel, qacc = generate_states(model, nstate, first=first, z_range=z_range)
+    ref, _ = rm.inverse_batch(qpos, qvel, qacc, nthread=host_threads(), fields={
+        "ncon": 1, "nefc": 1, "nl": 1, "nf": 1, "ne": 1, "contact_geom": nconmax,
+        "efc_type": njmax, "efc_id": njmax, "efc_state": njmax})
+    bd = mjb.BatchData(model, nstate, device=local_rank, stream=stream.cuda_stream, nconmax=nconmax, njmax=njmax,
+                       outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC | mjb.OUT_INERTIA)
+    try:
+        specialise(bd, generic)
+        bd.set_state(qpos, qvel, qacc)
+        flagged = bd.inverse()
+        cnt, efc = bd.counts(), bd.efc()
+        bad = np.zeros(nstate, dtype=bool)
+        for key in ("ncon", "nefc", "nl", "nf", "ne"):
+            bad |= cnt[key] != ref[key]
+        bad |= (bd.contacts()["geom"] != ref["contact_geom"]).any(axis=(1, 2))
+        for key in ("type", "id", "state"):
+            bad |= (efc[key] != ref["efc_" + key][:, :, 0]).any(axis=1)
+        got = bd.qfrc_inverse()
+        d = np.abs(got - ref["qfrc_inverse"])
+        tol = 1e-12 + 1e-9 * np.abs(ref["qfrc_inverse"])
+        smax = np.maximum(np.abs(ref["qfrc_inverse"]).max(axis=1, keepdims=True), 1.0)
+        return {"states": nstate, "flagged": int(flagged), "discrete_mismatch": int(bad.sum()),
+                "entries": int(got.size), "strict_viol": int((d > tol).sum()),
+                "strict_worst_ratio": float((d / tol).max()),
+                "worst_error_over_state_max": float((d / smax).max()),
+                "contacts": int(ref["ncon"].sum()), "against": "oracle/_ref (reference library, live)"}
+    finally:
+        bd.close()
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU mj_inverse over the host cores (rank 0 only)."""
     if rank != 0:
@@ -221,14 +319,15 @@ def run_reference(args, rank, world):
         _, t = rm.inverse_batch(qpos, qvel, qacc, nthread=nthread)
         total += t
     value = n * args.steps / total
-    sample = f"{n} states/step x {args.steps} steps of the {args.workload} stream"
+    sample = (f"{n} states/step x {args.steps} steps of the {args.workload} stream, reference mj_inverse "
+              f"+ src/thread pool on {nthread} host threads")
     line = {
         "impl": "reference", "metric": "mj_inverse states/sec (humanoid, fp64)", "value": value,
         "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "states_per_step": n,
-                   "host_threads": nthread},
+        "config": workload_config(args.workload, args.batch or BATCH.get(args.workload, DEFAULT_BATCH),
+                                  max(world, 1), args.no_inertia),
         "cpu_baseline": {"value": value, "unit": "states/s", "cores": nthread, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,6 +352,10 @@ def main():
     ap.add_argument("--no-inertia", action="store_true",
                     help="skip the mj_crb / mj_factorM outputs (qM, qLD, qLDiagInv)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generic", action="store_true",
+                    help="generic kernels only (default: the kernels specialised for the model, mjb_specialize)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-timed lines of the other BASELINE configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mjb" else args.warmup
 
@@ -293,6 +396,7 @@ def main():
 
     stream = torch.cuda.current_stream()
     bd = mjb.BatchData(model, n, device=local_rank, outmask=outmask, stream=stream.cuda_stream)
+    kernel_mode = specialise(bd, args.generic)
 
     def barrier():
         if world > 1:
@@ -398,10 +502,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "states_per_gpu": n,
-                       "outputs": "qfrc_inverse" + ("" if args.no_inertia else "+qM+qLD+qLDiagInv"),
-                       "l2": "inputs larger than L2 (%.0f MB per step)" % (n * (nq + 2 * nv) * 8 / 1e6),
-                       "parallelism": f"batch sharded over {world} GPU(s), no collective"},
+            "config": workload_config(args.workload, n, world, args.no_inertia),
+            "kernel_mode": kernel_mode,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "states/s",
                     "h2d_bytes_per_step": n * (nq + 2 * nv) * 8, "d2h_bytes_per_step": n * nv * 8,
@@ -425,6 +527,22 @@ def main():
             except Exception as exc:  # the checker library is absent: say so, do not fake it
                 line["cpu_baseline"] = {"value": None, "unit": "states/s", "cores": 0,
                                         "kind": "reference", "sample": f"unavailable: {exc}"}
+        if world == 1 and not args.no_other_configs:
+            # not part of the timed regions above: parity of a fresh sample against the reference
+            # library, and short device-resident lines of the other BASELINE configs
+            bd.close()
+            try:
+                line["parity"] = parity_sample(mjb, args.workload, local_rank, stream, args.generic)
+            except Exception as exc:
+                line["parity"] = {"unavailable": str(exc)[:200]}
+            line["other_configs"] = []
+            for wl in OTHER_CONFIGS:
+                if wl == args.workload:
+                    continue
+                try:
+                    line["other_configs"].append(device_rate(mjb, wl, local_rank, stream, args.generic))
+                except Exception as exc:
+                    line["other_configs"].append({"workload": wl, "unavailable": str(exc)[:200]})
         print(json.dumps(line), flush=True)
 
     if world > 1:

@@ -638,6 +638,8 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_gravcomp = d->hdr.passive_wrench;
   a.has_spatial = d->hdr.has_spatial;
   a.skip_sensors = d->skip_sensors;
+  a.scan_ngeom = d->hdr.ngeom;
+  a.scan_wide = std::getenv("MJB_SCAN_FLAT") ? 0 : mjb::scan_wide_states(d->hdr.ncand, d->hdr.ngeom);
   a.out = d->out;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
   for (long long start = first; start < first + count; start += d->chunk_stride) {

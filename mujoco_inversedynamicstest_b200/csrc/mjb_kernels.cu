@@ -186,6 +186,145 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-per-state candidate scan for scenes with long candidate lists (BASELINE config 5: 22
+// humanoids, ~90 K candidate pairs, ~1,200 survivors per state).
+//
+// With one thread per state every lane walks the whole candidate list and gathers two geom
+// positions per candidate from its own scratch column: 2^15 states x 90 K candidates x 48 bytes of
+// L1/L2 sector traffic (49.5 ms, 69 % of that step). Here ONE WARP owns one state and its 32 lanes
+// test 32 consecutive candidates per step:
+//   * the state's geom positions (ngeom x 3 doubles) are staged once in shared memory, structure of
+//     arrays, so that lanes testing consecutive geoms read consecutive words;
+//   * the compact candidate rows (geom ids, filter kind, bound: 16 bytes, mjb_upload.cc) are
+//     streamed through shared memory in tiles shared by the CTA's warps (one L2 read per CTA);
+//   * a ballot over the 32 outcomes IS the survivor mask word of those candidates (kept for the
+//     pooled fallback), and its prefix popcount places the survivors, in candidate order, in the
+//     warp's buffer; the state's items are then appended to the chunk's global item list with one
+//     atomicAdd, which makes contact_items_kernel unnecessary on this path.
+// The test is mj_filterSphere's arithmetic, identical to contact_scan (mjb_pipeline.h).
+constexpr int kWideTile = 2048;     // candidate rows per shared-memory tile
+constexpr int kWideBuf = 2048;      // survivors buffered per warp before they are written out
+
+size_t scan_wide_smem_bytes(int ngeom, int states_per_cta) {
+  const size_t gp = (size_t)((ngeom + 3) & ~3);
+  return (size_t)states_per_cta * (3 * gp * sizeof(double) + kWideBuf * sizeof(int)) +
+         (size_t)kWideTile * (sizeof(double) + 2 * sizeof(int));
+}
+
+// states per CTA (= warps) of the wide scan for this model, 0 if the flat thread-per-state scan is used
+int scan_wide_states(int ncand, int ngeom) {
+  if (ncand < 4096) return 0;
+  for (int w = 8; w >= 2; w--) if (scan_wide_smem_bytes(ngeom, w) <= 200 * 1024) return w;
+  return 0;
+}
+
+__global__ void __launch_bounds__(256, 1) contact_scan_wide_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(a.model);
+  const int* I = reinterpret_cast<const int*>(a.model + H->int_section);
+  const double* D = reinterpret_cast<const double*>(a.model + H->num_section);
+  const int ngeom = H->ngeom, ncand = H->ncand;
+  const int* scan_int = I + H->ioff[MJB_I_scan_int];
+  const double* scan_bound = D + H->noff[MJB_N_scan_bound];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int gp = (ngeom + 3) & ~3;
+  double* gx_all = reinterpret_cast<double*>(smem);                         // [W][3][gp]
+  double* tile_bound = gx_all + (size_t)W * 3 * gp;                         // [kWideTile]
+  int* tile_int = reinterpret_cast<int*>(tile_bound + kWideTile);           // [2*kWideTile]
+  int* buf_all = tile_int + 2 * kWideTile;                                  // [W][kWideBuf]
+  double* gx = gx_all + (size_t)warp * 3 * gp;
+  int* buf = buf_all + (size_t)warp * kWideBuf;
+  const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_xmat];
+
+  for (long long s0 = (long long)blockIdx.x * W; s0 < a.chunk_n; s0 += (long long)gridDim.x * W) {
+    const long long s = s0 + warp;
+    const bool valid = s < a.chunk_n;
+    const long long sb = valid ? s : 0;
+    const double* sc = a.scratch + ((sb >> 5) * a.nscratch << 5) + (sb & 31);
+    int* isc = a.iscratch + ((sb >> 5) * a.niscratch << 5) + (sb & 31);
+    __syncthreads();                      // the previous round's tiles and positions are consumed
+    if (valid) {
+      for (int g = lane; g < ngeom; g += 32) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) gx[k * gp + g] = sc[(off_gxpos + 3 * g + k) * MJB_LS];
+      }
+    }
+    int total = 0;
+    bool rescan = false;
+    for (int pass = 0; pass < 2; pass++) {
+      // pass 0 buffers the survivors; pass 1 (only when some warp's buffer overflowed) writes them
+      // straight to the item list, whose range is known by then
+      int base = 0;
+      bool fits = true;
+      if (pass == 1) {
+        const bool mine = rescan;
+        if (!__syncthreads_or(mine)) break;
+        if (lane == 0 && mine) base = atomicAdd(&a.cq->nitems, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        fits = base + total <= a.items_cap;
+        if (mine && !fits && lane == 0) a.cq->overflow = 1;
+        if (mine && lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
+      }
+      int count = 0;
+      for (int t0 = 0; t0 < ncand; t0 += kWideTile) {
+        const int nt = ncand - t0 < kWideTile ? ncand - t0 : kWideTile;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+          tile_bound[i] = scan_bound[t0 + i];
+          tile_int[2 * i] = scan_int[2 * (t0 + i)];
+          tile_int[2 * i + 1] = scan_int[2 * (t0 + i) + 1];
+        }
+        __syncthreads();
+        if (!valid || (pass == 1 && !rescan)) continue;
+        for (int c0 = 0; c0 < nt; c0 += 32) {
+          const int ci = c0 + lane;
+          bool pass_test = false;
+          if (ci < nt) {
+            const int g1k = tile_int[2 * ci], g2 = tile_int[2 * ci + 1];
+            const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
+            const double bound = tile_bound[ci];
+            const double pos1[3] = {gx[g1], gx[gp + g1], gx[2 * gp + g1]};
+            const double pos2[3] = {gx[g2], gx[gp + g2], gx[2 * gp + g2]};
+            pass_test = true;
+            if (planeflag == 0) {
+              const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+              pass_test = !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
+            } else if (planeflag == 1) {
+              const double nrm[3] = {sc[(off_gxmat + 9 * g1 + 2) * MJB_LS], sc[(off_gxmat + 9 * g1 + 5) * MJB_LS],
+                                     sc[(off_gxmat + 9 * g1 + 8) * MJB_LS]};
+              const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+              pass_test = !(dot3(dif, nrm) > bound);
+            }
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, pass_test);
+          if (pass == 0 && lane == 0) isc[(size_t)(MJB_ISC_MASK + ((t0 + c0) >> 5)) * MJB_LS] = (int)m;
+          if (pass_test) {
+            const int k = count + __popc(m & ((1u << lane) - 1u));
+            if (pass == 0) { if (k < kWideBuf) buf[k] = t0 + ci; }
+            else if (fits) a.items[base + k] = ContactItem{(int)s, t0 + ci};
+          }
+          count += __popc(m);
+        }
+      }
+      if (pass == 0) {
+        total = count;
+        if (valid && lane == 0) isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
+        if (!a.cq) break;                  // pooled path only: the masks are all it needs
+        rescan = valid && total > kWideBuf;
+        if (valid && !rescan) {
+          if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          fits = base + total <= a.items_cap;
+          if (!fits && lane == 0) a.cq->overflow = 1;
+          if (lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
+          if (fits) for (int k = lane; k < total; k += 32) a.items[base + k] = ContactItem{(int)s, buf[k]};
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // contact kernel: warp-pooled narrow phase and contact rows.
 //
 // A warp owns 32 consecutive states. Work per state is very uneven (0..60 bounding-sphere
@@ -931,8 +1070,25 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     }
   }
   if (args.has_contacts) {
+    if (args.cq) {
+      e = cudaMemsetAsync(args.cq, 0, sizeof(ContactQueue), stream);
+      if (e != cudaSuccess) return e;
+    }
     { PhaseScope ps(timer, stream, kPhaseScan);
-    e = run_phase(nullptr, fn_scan, args, stream, launches, generic_scan); }
+      if (args.scan_wide > 0) {
+        // one warp per state; appends the survivors to the item list itself
+        const size_t wsm = scan_wide_smem_bytes(args.scan_ngeom, args.scan_wide);
+        e = cudaFuncSetAttribute(contact_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+        if (e != cudaSuccess) return e;
+        int grid = (args.chunk_n + args.scan_wide - 1) / args.scan_wide;
+        if (grid > kSMs) grid = kSMs;
+        contact_scan_wide_kernel<<<grid, 32 * args.scan_wide, wsm, stream>>>(args);
+        e = cudaGetLastError();
+        ++*launches;
+      } else {
+        e = run_phase(nullptr, fn_scan, args, stream, launches, generic_scan);
+      }
+    }
     if (e != cudaSuccess) return e;
 // The contact kernel reads the model tables through L1 instead of a shared-memory copy: its lanes
 // index the candidate tables with per-lane (non-uniform) indices anyway, and the 25 KB per CTA are
@@ -941,14 +1097,15 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
 #define MJB_CONTACT_MODEL_SMEM 0
 #endif
     if (args.cq) {
-      e = cudaMemsetAsync(args.cq, 0, sizeof(ContactQueue), stream);
-      if (e != cudaSuccess) return e;
       { PhaseScope ps(timer, stream, kPhaseContact);
-        int grid = (args.chunk_n + 255) / 256;
-        if (grid > kSMs * 8) grid = kSMs * 8;
-        contact_items_kernel<<<grid, 256, 0, stream>>>(args);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        if (args.scan_wide <= 0) {
+          int grid = (args.chunk_n + 255) / 256;
+          if (grid > kSMs * 8) grid = kSMs * 8;
+          contact_items_kernel<<<grid, 256, 0, stream>>>(args);
+          e = cudaGetLastError();
+          if (e != cudaSuccess) return e;
+          ++*launches;
+        }
         // the narrow / rows kernels walk lists whose length is only known on the device: full grids
         e = in_smem ? launch_phase(contact_narrow_kernel<true>, args, smem, 4, stream, 256)
                     : launch_phase(contact_narrow_kernel<false>, args, 0, 4, stream, 256);
@@ -960,7 +1117,7 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
                     : launch_phase(contact_rows_kernel<false>, args, 0, 8, stream);
         if (e != cudaSuccess) return e;
       }
-      *launches += 4;
+      *launches += 3;
     }
     const bool csm = in_smem && MJB_CONTACT_MODEL_SMEM;
     const size_t csmem = contact_smem_bytes(args.model_bytes, csm, args.max_pair_contacts);

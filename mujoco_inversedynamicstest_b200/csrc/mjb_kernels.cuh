@@ -57,6 +57,11 @@ cudaError_t dfma_peak_probe(int iters, float* ms, double* flops, cudaStream_t st
 
 size_t inverse_smem_bytes(int model_bytes, int model_in_smem);
 
+// states per CTA of the warp-per-state candidate scan for a model with `ncand` candidate pairs and
+// `ngeom` geoms; 0: the thread-per-state scan is used (short lists, or positions do not fit shared memory)
+int scan_wide_states(int ncand, int ngeom);
+size_t scan_wide_smem_bytes(int ngeom, int states_per_cta);
+
 }  // namespace mjb
 
 #endif  // MJB_KERNELS_CUH_

@@ -60,6 +60,9 @@ struct LaunchArgs {
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
   int skip_sensors;             // mj_inverseSkip(skipsensor = 1): leave sensordata as it is
+  int scan_wide;                // > 0: warp-per-state candidate scan with this many states per CTA
+                                //      (scenes with long candidate lists, mjb_kernels.cu)
+  int scan_ngeom;               // mjbHdr::ngeom (sizes the wide scan's shared memory)
   Outputs out;
 };
 
