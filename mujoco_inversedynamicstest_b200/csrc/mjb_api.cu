@@ -51,6 +51,7 @@ struct mjbData_ {
   mjb::ItemCon* d_item_con = nullptr;
   mjb::ContactRec* d_contacts = nullptr;
   int* d_slot_rec = nullptr;
+  int* d_scan_buf = nullptr;   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
   int items_cap = 0, contacts_cap = 0;
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
@@ -76,6 +77,7 @@ struct mjbData_ {
   void* field_ptr[mjbF_COUNT];
   int field_rows[mjbF_COUNT];
   int field_isint[mjbF_COUNT];
+  bool field_set[mjbF_COUNT];   // requested in outmask (a field of a model with no rows of it has no buffer)
   // mjb_inverseFD: inner batch of perturbed states and the device buffer of the differences
   mjbData* fd = nullptr;
   int fd_tile = 0;
@@ -142,6 +144,7 @@ void setField(mjbData* d, int f, void* p, int rows, int isint) {
   d->field_ptr[f] = p;
   d->field_rows[f] = rows;
   d->field_isint[f] = isint;
+  d->field_set[f] = true;
 }
 
 }  // namespace
@@ -227,7 +230,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
 
   mjbData* d = new mjbData_;
   std::memset(&d->out, 0, sizeof(d->out));
-  for (int f = 0; f < mjbF_COUNT; f++) setField(d, f, nullptr, 0, 0);
+  for (int f = 0; f < mjbF_COUNT; f++) { setField(d, f, nullptr, 0, 0); d->field_set[f] = false; }
   d->device = device;
   d->outmask = outmask;
   d->nbatch_max = nbatch_max;
@@ -293,6 +296,9 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
       ok = ok && devAlloc(d, &d->d_item_con, (size_t)ni, "cudaMalloc(item contacts)");
       ok = ok && devAlloc(d, &d->d_contacts, (size_t)nc, "cudaMalloc(contact records)");
       ok = ok && devAlloc(d, &d->d_slot_rec, (size_t)nc, "cudaMalloc(contact slots)");
+    }
+    if (H.ncand > 0 && mjb::scan_wide_states(H.ncand, H.ngeom) > 0) {
+      ok = ok && devAlloc(d, &d->d_scan_buf, (size_t)mjb::scan_wide_buf_ints(H.ncand, H.ngeom), "cudaMalloc(scan buffers)");
     }
   }
   ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
@@ -391,7 +397,7 @@ mjbData* mjb_makeDataMulti(const mjModel* m, int nbatch_max, const int* devices,
   if (nbatch_max <= 0) return fail("mjb_makeDataMulti: nbatch_max must be positive");
   mjbData* d = new mjbData_;
   std::memset(&d->out, 0, sizeof(d->out));
-  for (int f = 0; f < mjbF_COUNT; f++) setField(d, f, nullptr, 0, 0);
+  for (int f = 0; f < mjbF_COUNT; f++) { setField(d, f, nullptr, 0, 0); d->field_set[f] = false; }
   d->nbatch_max = nbatch_max;
   d->outmask = outmask;
   const int per = (nbatch_max + ndevice - 1) / ndevice;
@@ -469,6 +475,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_model); cudaFree(d->d_scratch); cudaFree(d->d_iscratch);
   cudaFree(d->d_cq); cudaFree(d->d_items); cudaFree(d->d_item_con); cudaFree(d->d_contacts);
   cudaFree(d->d_slot_rec);
+  cudaFree(d->d_scan_buf);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
@@ -632,6 +639,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_contacts = d->hdr.ncand > 0 &&
                    !(d->hdr.disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT));
   a.max_pair_contacts = d->hdr.max_pair_contacts;
+  a.simple_pairs = d->hdr.simple_pairs;
   a.cq = d->d_cq; a.items = d->d_items; a.item_con = d->d_item_con; a.contacts = d->d_contacts;
   a.items_cap = d->items_cap; a.contacts_cap = d->contacts_cap;
   a.slot_rec = d->d_slot_rec;
@@ -639,7 +647,15 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_spatial = d->hdr.has_spatial;
   a.skip_sensors = d->skip_sensors;
   a.scan_ngeom = d->hdr.ngeom;
-  a.scan_wide = std::getenv("MJB_SCAN_FLAT") ? 0 : mjb::scan_wide_states(d->hdr.ncand, d->hdr.ngeom);
+  a.scan_buf = d->d_scan_buf; a.scan_buf_cap = mjb::scan_wide_buf_cap(d->hdr.ncand);
+  a.sub_nv = d->hdr.nv; a.sub_nbody = d->hdr.nbody; a.sub_nC = d->hdr.nC;
+  {
+    // MJB_INERTIA=thread | subwarp overrides the choice (A/B measurements)
+    const char* env = std::getenv("MJB_INERTIA");
+    const bool fits = mjb::inertia_subwarp_fits(d->hdr.nv, d->hdr.nbody, d->hdr.nC);
+    a.inertia_subwarp = (fits && env && !std::strcmp(env, "subwarp")) ? 1 : 0;
+  }
+  a.scan_wide = (std::getenv("MJB_SCAN_FLAT") || !d->d_scan_buf) ? 0 : mjb::scan_wide_states(d->hdr.ncand, d->hdr.ngeom);
   a.out = d->out;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
   for (long long start = first; start < first + count; start += d->chunk_stride) {
@@ -836,6 +852,14 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
   if (!d->shards.empty()) { d->error = "mjb_inverseFD: not available on a multi-device mjbData"; return -1; }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseFD: nbatch out of range"; return -1; }
   if (!(eps > 0)) { d->error = "mjb_inverseFD: eps must be positive"; return -1; }
+  // the reference's own refusals (engine_derivative_fd.c:618-626)
+  if (m->opt.integrator == mjINT_RK4) { d->error = "mjb_inverseFD: RK4 integrator is not supported"; return -1; }
+  if (m->opt.noslip_iterations) { d->error = "mjb_inverseFD: noslip solver is not supported"; return -1; }
+  // the perturbed copies are evaluated in an inner batch that holds no per-state mocap poses
+  if (d->d_mocap_pos || d->d_mocap_quat) {
+    d->error = "mjb_inverseFD: per-state mocap poses (mjb_setMocap) are not carried into the perturbed batch";
+    return -1;
+  }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
   const mjbHdr& H = d->hdr;
   const int nv = H.nv, nM = H.nM, nvar = 1 + 3*nv;
@@ -946,7 +970,7 @@ int mjb_compareFwdInv(const mjModel* m, mjbData* d, int nbatch, const mjtNum* qf
 
 int mjb_get(mjbData* d, int field, void* host_out) {
   if (!d->shards.empty()) {
-    if (field < 0 || field >= mjbF_COUNT || !d->shards[0]->field_ptr[field]) {
+    if (field < 0 || field >= mjbF_COUNT || !d->shards[0]->field_set[field]) {
       d->error = "mjb_get: field was not requested in outmask";
       return -1;
     }
@@ -955,10 +979,11 @@ int mjb_get(mjbData* d, int field, void* host_out) {
       return r.n ? mjb_get(sh, field, (char*)host_out + (size_t)r.first * row_bytes) : 0;
     }) ? 0 : -1;
   }
-  if (field < 0 || field >= mjbF_COUNT || !d->field_ptr[field]) {
+  if (field < 0 || field >= mjbF_COUNT || !d->field_set[field]) {
     d->error = "mjb_get: field was not requested in outmask";
     return -1;
   }
+  if (!d->field_ptr[field]) return 0;       // requested, but the model has no rows of it (nv == 0 ...)
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
   const int n = d->last_nbatch, rows = d->field_rows[field];
   const size_t esz = d->field_isint[field] ? sizeof(int) : sizeof(double);

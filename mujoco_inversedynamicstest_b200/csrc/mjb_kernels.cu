@@ -157,6 +157,169 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_INERTIA) inertia_kernel(Lau
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// mj_crb + mj_factorM with a SUB-WARP of 8 lanes per state and every intermediate on chip (the
+// mapping BASELINE.json's north_star names: engine_core_smooth.c:1353-1401, :1470-1511).
+//
+// One CTA owns one warp block of the scratch (32 consecutive states) at a time: 256 threads = 32
+// states x 8 workers, the 8 workers of a state in one warp (4 states per warp). Per state the
+// kernel keeps cdof (6 nv), the composite inertias (10 nbody) and the sparse matrix (nC entries,
+// the reference's C layout: row i = ancestors ascending, self last) in shared memory, state-major
+// with odd strides so that the coalesced transfers (lane = state) and the worker accesses (8
+// entries of 4 states) spread over the banks:
+//   load   : cdof / cinert rows of the block, 256-byte lines, straight from the scratch
+//   crb    : every worker owns components of the 10-number inertias and walks the bodies leaves to
+//            root on its own (no exchange between workers)
+//   M      : worker g takes dofs g, g+8, ...: buf = crb[body] cdof_i, then one dot product per
+//            ancestor (the walk of mj_crb), written into the matrix
+//   qM out : the finished entries leave as whole 256-byte rows (legacy layout through mapM2C)
+//   L'DL   : mj_factorI's elimination in place, rows k = nv-1 .. 0 in lock step (__syncwarp), the
+//            ancestor rows of k dealt out to the 8 workers in pairs (p, na-1-p) of equal work
+//   out    : qLD / qLDiagInv as whole rows
+// HBM sees the inputs once (cinert + cdof) and the outputs once; nothing is re-read and there are
+// no accumulator pushes. Selected per model when the three arrays fit in shared memory.
+constexpr int kSubG = 8;            // workers per state
+constexpr int kSubS = 32;           // states per CTA (one warp block of the scratch)
+
+struct SubwarpLayout { int cd, cr, ws; size_t bytes; };
+SubwarpLayout subwarp_layout(int nv, int nbody, int nC) {
+  SubwarpLayout L;
+  L.cd = (6 * nv) | 1; L.cr = (10 * nbody) | 1; L.ws = nC | 1;
+  L.bytes = (size_t)kSubS * (size_t)(L.cd + L.cr + L.ws) * sizeof(double);
+  return L;
+}
+bool inertia_subwarp_fits(int nv, int nbody, int nC) {
+  return nv > 0 && subwarp_layout(nv, nbody, nC).bytes <= 220 * 1024;
+}
+
+__global__ void __launch_bounds__(kSubS * kSubG, 1) inertia_subwarp_kernel(LaunchArgs a) {
+  extern __shared__ __align__(16) double sw[];
+  const mjbHdr* H = reinterpret_cast<const mjbHdr*>(a.model);
+  const int* I = reinterpret_cast<const int*>(a.model + H->int_section);
+  const double* D = reinterpret_cast<const double*>(a.model + H->num_section);
+  const int nv = H->nv, nbody = H->nbody, nC = H->nC;
+  const int* body_parentid = I + H->ioff[MJB_I_body_parentid];
+  const int* dof_bodyid = I + H->ioff[MJB_I_dof_bodyid];
+  const int* dof_parentid = I + H->ioff[MJB_I_dof_parentid];
+  const int* dof_Madr = I + H->ioff[MJB_I_dof_Madr];
+  const int* dof_simplenum = I + H->ioff[MJB_I_dof_simplenum];
+  const int* rownnz = I + H->ioff[MJB_I_C_rownnz];
+  const int* rowadr = I + H->ioff[MJB_I_C_rowadr];
+  const int* colind = I + H->ioff[MJB_I_C_colind];
+  const int* mapM2C = I + H->ioff[MJB_I_mapM2C];
+  const double* armature = D + H->noff[MJB_N_dof_armature];
+  const double* dof_M0 = D + H->noff[MJB_N_dof_M0];
+  const int CD = (6 * nv) | 1, CR = (10 * nbody) | 1, WS = nC | 1;
+  double* cd_all = sw;
+  double* cr_all = cd_all + (size_t)kSubS * CD;
+  double* ws_all = cr_all + (size_t)kSubS * CR;
+  const int tid = threadIdx.x;
+  const int s = tid / kSubG, g = tid % kSubG;          // compute phases: state, worker
+  const int sl = tid & 31, rl = tid >> 5;              // transfer phases: state = lane, row slice
+  constexpr int kRows = kSubS * kSubG / 32;            // rows moved per pass
+  double* cd = cd_all + (size_t)s * CD;
+  double* cr = cr_all + (size_t)s * CR;
+  double* ws = ws_all + (size_t)s * WS;
+  const size_t off_cdof = (size_t)H->scoff[MJB_SC_cdof], off_cinert = (size_t)H->scoff[MJB_SC_cinert];
+  const size_t N = (size_t)a.stride;
+  const long long nblocks = (a.chunk_n + 31) >> 5;
+
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const double* sc = a.scratch + (blk * a.nscratch << 5);
+    const long long sg = a.chunk_start + (blk << 5) + sl;          // global state of the transfer lane
+    const bool live = (blk << 5) + sl < a.chunk_n;
+    // ---- load
+    for (int r = rl; r < 6 * nv; r += kRows) cd_all[(size_t)sl * CD + r] = __ldcs(sc + ((off_cdof + r) << 5) + sl);
+    for (int r = rl; r < 10 * nbody; r += kRows) cr_all[(size_t)sl * CR + r] = __ldcs(sc + ((off_cinert + r) << 5) + sl);
+    __syncthreads();
+    // ---- crb: components g and g + 8 of every body, leaves to root
+    for (int comp = g; comp < 10; comp += kSubG) {
+      for (int b = nbody - 1; b > 0; b--) {
+        const int p = body_parentid[b];
+        if (p > 0) cr[10 * p + comp] += cr[10 * b + comp];
+      }
+    }
+    __syncwarp();
+    // ---- M: the entries of rows g, g + 8, ...
+    for (int i = g; i < nv; i += kSubG) {
+      const int diag = rowadr[i] + rownnz[i] - 1;
+      if (dof_simplenum[i]) {
+        // simple body: M is diagonal and constant (engine_core_smooth.c:1375-1385); the legacy qM
+        // keeps the zero ancestor entries, which the reduced rows do not hold
+        ws[diag] = dof_M0[i];
+        const long long st = a.chunk_start + (blk << 5) + s;
+        if ((blk << 5) + s < a.chunk_n) {
+          int t = 1;
+          for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j], t++) a.out.qM[(size_t)(dof_Madr[i] + t) * N + st] = 0;
+        }
+        continue;
+      }
+      double S[6], inert[10], buf[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) S[k] = cd[6 * i + k];
+      const int b = dof_bodyid[i];
+#pragma unroll
+      for (int k = 0; k < 10; k++) inert[k] = cr[10 * b + k];
+      mulInertVecF(buf, inert, S);
+      ws[diag] = armature[i] + dot6f(S, buf);
+      int e = diag - 1;
+      for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j], e--) {
+        double Sj[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) Sj[k] = cd[6 * j + k];
+        ws[e] = dot6f(Sj, buf);
+      }
+    }
+    __syncthreads();
+    // ---- qM out (legacy layout), whole rows
+    if (live) {
+      for (int k = rl; k < nC; k += kRows) __stcs(a.out.qM + (size_t)mapM2C[k] * N + sg, ws_all[(size_t)sl * WS + k]);
+    }
+    __syncthreads();
+    // ---- L'DL in place (mj_factorI): 1/D of row k lands in the dead cdof row of the state
+    for (int k = nv - 1; k >= 0; k--) {
+      const int rk = rowadr[k], na = rownnz[k] - 1;        // ancestors of k
+      const double invD = 1 / ws[rk + na];
+      if (g == 0) cd[k] = invD;
+      if (dof_simplenum[k] || na == 0) continue;
+      // ancestor rows p (length p + 1) in pairs (p, na - 1 - p): equal work per worker
+      double tmp[2];
+      int pp[2];
+      pp[0] = g < na ? g : -1;
+      pp[1] = (na - 1 - g >= kSubG) ? na - 1 - g : -1;
+      // more than 2 * kSubG ancestors: the rows in between, dealt out round robin
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        tmp[q] = 0;
+        if (pp[q] < 0) continue;
+        const int p = pp[q];
+        tmp[q] = ws[rk + p] * invD;
+        double* ri = ws + rowadr[colind[rk + p]];
+        const double scl = -tmp[q];
+        for (int t = 0; t <= p; t++) ri[t] = fma(scl, ws[rk + t], ri[t]);
+      }
+      for (int p = kSubG + g; p < na - kSubG; p += kSubG) {      // deep chains only (na > 16)
+        const double tp = ws[rk + p] * invD;
+        double* ri = ws + rowadr[colind[rk + p]];
+        for (int t = 0; t <= p; t++) ri[t] = fma(-tp, ws[rk + t], ri[t]);
+      }
+      __syncwarp();
+      // row k itself is scaled after every worker has read its unscaled entries
+#pragma unroll
+      for (int q = 0; q < 2; q++) if (pp[q] >= 0) ws[rk + pp[q]] = tmp[q];
+      for (int p = kSubG + g; p < na - kSubG; p += kSubG) ws[rk + p] *= invD;
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- qLD, qLDiagInv out
+    if (live) {
+      for (int k = rl; k < nC; k += kRows) __stcs(a.out.qLD + (size_t)k * N + sg, ws_all[(size_t)sl * WS + k]);
+      for (int k = rl; k < nv; k += kRows) __stcs(a.out.qLDiagInv + (size_t)k * N + sg, cd_all[(size_t)sl * CD + k]);
+    }
+    __syncthreads();
+  }
+}
+
 // mjENBL_INVDISCRETE: convert the discrete-time qacc with the factors the inertia kernel just wrote
 template <bool kModelInSmem>
 __global__ void __launch_bounds__(kThreads, 4) discrete_acc_kernel(LaunchArgs a) {
@@ -192,33 +355,72 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
 // With one thread per state every lane walks the whole candidate list and gathers two geom
 // positions per candidate from its own scratch column: 2^15 states x 90 K candidates x 48 bytes of
 // L1/L2 sector traffic (49.5 ms, 69 % of that step). Here ONE WARP owns one state and its 32 lanes
-// test 32 consecutive candidates per step:
-//   * the state's geom positions (ngeom x 3 doubles) are staged once in shared memory, structure of
-//     arrays, so that lanes testing consecutive geoms read consecutive words;
-//   * the compact candidate rows (geom ids, filter kind, bound: 16 bytes, mjb_upload.cc) are
-//     streamed through shared memory in tiles shared by the CTA's warps (one L2 read per CTA);
-//   * a ballot over the 32 outcomes IS the survivor mask word of those candidates (kept for the
-//     pooled fallback), and its prefix popcount places the survivors, in candidate order, in the
-//     warp's buffer; the state's items are then appended to the chunk's global item list with one
-//     atomicAdd, which makes contact_items_kernel unnecessary on this path.
-// The test is mj_filterSphere's arithmetic, identical to contact_scan (mjb_pipeline.h).
+// test 32 consecutive candidates per step, in two stages:
+//   1. a CONSERVATIVE single-precision filter over all candidates. The state's geom positions are
+//      staged once in shared memory as floats relative to the state's first geom (structure of
+//      arrays: lanes testing consecutive geoms read consecutive words), the compact candidate rows
+//      (geom ids, filter kind: 8 bytes, mjb_upload.cc) and the bounds rounded UP to float are
+//      streamed through shared memory in tiles shared by the CTA's warps. A candidate is dropped
+//      only if its float distance exceeds the float bound by more than `slack`, which covers the
+//      rounding of the float path many times over (|coordinate| <= M after centring: error of the
+//      distance <= ~7e-7 M, slack = max(1e-4, 8e-6 M)); everything else ("maybe": the true
+//      survivors plus a 0.1 mm band, plus all plane candidates) is buffered in candidate order;
+//   2. the EXACT test -- mj_filterSphere's double-precision arithmetic, identical to contact_scan
+//      (mjb_pipeline.h) -- over the buffered candidates only, 32 at a time with all lanes busy,
+//      compacting the buffer in place.
+// The state's survivors are then appended to the chunk's global item list with one atomicAdd,
+// which makes contact_items_kernel unnecessary on this path. The fp64 pipe (64 lanes per SM and
+// clock) sees ~1.5 % of the candidates instead of all of them. The ballot of stage 1 is kept as
+// the survivor mask word of those 32 candidates for the pooled fallback, which applies the exact
+// tests itself; stage 2 clears the bits of the candidates it rejects.
 constexpr int kWideTile = 2048;     // candidate rows per shared-memory tile
-constexpr int kWideBuf = 2048;      // survivors buffered per warp before they are written out
+constexpr int kWidePlanes = 8;      // plane geoms whose normals are staged for the float filter
+constexpr int kWideCtas = 2;        // resident CTAs per SM
 
 size_t scan_wide_smem_bytes(int ngeom, int states_per_cta) {
   const size_t gp = (size_t)((ngeom + 3) & ~3);
-  return (size_t)states_per_cta * (3 * gp * sizeof(double) + kWideBuf * sizeof(int)) +
-         (size_t)kWideTile * (sizeof(double) + 2 * sizeof(int));
+  return (size_t)states_per_cta * (3 * gp + 3 * kWidePlanes) * sizeof(float) +
+         (size_t)kWideTile * (sizeof(float) + 2 * sizeof(int)) + gp;
 }
 
 // states per CTA (= warps) of the wide scan for this model, 0 if the flat thread-per-state scan is used
 int scan_wide_states(int ncand, int ngeom) {
   if (ncand < 4096) return 0;
-  for (int w = 8; w >= 2; w--) if (scan_wide_smem_bytes(ngeom, w) <= 200 * 1024) return w;
+  for (int w = 16; w >= 2; w--) if (scan_wide_smem_bytes(ngeom, w) <= (size_t)(220 * 1024) / kWideCtas) return w;
   return 0;
 }
+// per-warp buffer (ints, global memory) that carries the stage-1 candidates to stage 2, and how many
+// warps the launch has: the grid is fixed (kWideCtas CTAs per SM)
+int scan_wide_buf_cap(int ncand) { return ncand < 16384 ? ((ncand + 31) & ~31) : 16384; }
+long long scan_wide_buf_ints(int ncand, int ngeom) {
+  return (long long)kSMs * kWideCtas * scan_wide_states(ncand, ngeom) * scan_wide_buf_cap(ncand);
+}
 
-__global__ void __launch_bounds__(256, 1) contact_scan_wide_kernel(LaunchArgs a) {
+// mj_filterSphere (engine_collision_driver.c:146-163) on candidate ci of the state whose scratch
+// column is sc, in double precision (same expressions as contact_scan, mjb_pipeline.h)
+__device__ __forceinline__ bool scan_exact_test(const double* sc, size_t off_gxpos, size_t off_gxmat,
+                                                const int* scan_int, const double* scan_bound, int ci) {
+  const int g1k = scan_int[2 * ci], g2 = scan_int[2 * ci + 1];
+  const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
+  if (planeflag > 1) return true;
+  const double bound = scan_bound[ci];
+  double pos1[3], pos2[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    pos1[k] = sc[(off_gxpos + 3 * g1 + k) * MJB_LS];
+    pos2[k] = sc[(off_gxpos + 3 * g2 + k) * MJB_LS];
+  }
+  if (planeflag == 0) {
+    const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    return !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
+  }
+  const double nrm[3] = {sc[(off_gxmat + 9 * g1 + 2) * MJB_LS], sc[(off_gxmat + 9 * g1 + 5) * MJB_LS],
+                         sc[(off_gxmat + 9 * g1 + 8) * MJB_LS]};
+  const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  return !(dot3(dif, nrm) > bound);
+}
+
+__global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(a.model);
   const int* I = reinterpret_cast<const int*>(a.model + H->int_section);
@@ -226,15 +428,29 @@ __global__ void __launch_bounds__(256, 1) contact_scan_wide_kernel(LaunchArgs a)
   const int ngeom = H->ngeom, ncand = H->ncand;
   const int* scan_int = I + H->ioff[MJB_I_scan_int];
   const double* scan_bound = D + H->noff[MJB_N_scan_bound];
+  const int* geom_store = I + H->ioff[MJB_I_geom_store];
+  const int* geom_type = I + H->ioff[MJB_I_geom_type];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int gp = (ngeom + 3) & ~3;
-  double* gx_all = reinterpret_cast<double*>(smem);                         // [W][3][gp]
-  double* tile_bound = gx_all + (size_t)W * 3 * gp;                         // [kWideTile]
-  int* tile_int = reinterpret_cast<int*>(tile_bound + kWideTile);           // [2*kWideTile]
-  int* buf_all = tile_int + 2 * kWideTile;                                  // [W][kWideBuf]
-  double* gx = gx_all + (size_t)warp * 3 * gp;
-  int* buf = buf_all + (size_t)warp * kWideBuf;
+  float* gx_all = reinterpret_cast<float*>(smem);                           // [W][3][gp]
+  float* pn_all = gx_all + (size_t)W * 3 * gp;                              // [W][3][kWidePlanes] plane normals
+  float* tile_bound = pn_all + (size_t)W * 3 * kWidePlanes;                 // [kWideTile]
+  int2* tile_int = reinterpret_cast<int2*>(tile_bound + kWideTile);         // [kWideTile]
+  unsigned char* plane_id = reinterpret_cast<unsigned char*>(tile_int + kWideTile);   // [gp]: slot of a plane geom
+  float* gx = gx_all + (size_t)warp * 3 * gp;
+  float* pn = pn_all + (size_t)warp * 3 * kWidePlanes;
+  const int cap = a.scan_buf_cap;
+  int* buf = a.scan_buf + ((size_t)blockIdx.x * W + warp) * cap;            // this warp's candidate buffer
   const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_xmat];
+  const int mask_row = MJB_ISC_MASK;
+  if (threadIdx.x == 0) {
+    int np = 0;
+    for (int g = 0; g < ngeom; g++) {
+      const bool pl = geom_type[g] == MJB_GEOM_PLANE && np < kWidePlanes;
+      plane_id[g] = pl ? (unsigned char)np : (unsigned char)255;
+      np += pl;
+    }
+  }
 
   for (long long s0 = (long long)blockIdx.x * W; s0 < a.chunk_n; s0 += (long long)gridDim.x * W) {
     const long long s = s0 + warp;
@@ -243,82 +459,122 @@ __global__ void __launch_bounds__(256, 1) contact_scan_wide_kernel(LaunchArgs a)
     const double* sc = a.scratch + ((sb >> 5) * a.nscratch << 5) + (sb & 31);
     int* isc = a.iscratch + ((sb >> 5) * a.niscratch << 5) + (sb & 31);
     __syncthreads();                      // the previous round's tiles and positions are consumed
+    float slack = 1e-4f;
     if (valid) {
+      // positions relative to a stored geom (geom 1 of the first candidate), as floats
+      const int gref = scan_int[0] & 0xfffffff;
+      const double r0 = sc[(off_gxpos + 3 * gref) * MJB_LS], r1 = sc[(off_gxpos + 3 * gref + 1) * MJB_LS],
+                   r2 = sc[(off_gxpos + 3 * gref + 2) * MJB_LS];
+      float m = 0;
       for (int g = lane; g < ngeom; g += 32) {
+        // geoms outside every candidate pair are not stored by the sweep (geom_store, mjb_upload.cc)
+        const bool stored = geom_store[g] != 0;
+        const float x = stored ? (float)(sc[(off_gxpos + 3 * g) * MJB_LS] - r0) : 0.f;
+        const float y = stored ? (float)(sc[(off_gxpos + 3 * g + 1) * MJB_LS] - r1) : 0.f;
+        const float z = stored ? (float)(sc[(off_gxpos + 3 * g + 2) * MJB_LS] - r2) : 0.f;
+        gx[g] = x; gx[gp + g] = y; gx[2 * gp + g] = z;
+        m = fmaxf(m, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+        const int pid = plane_id[g];
+        if (pid < kWidePlanes && stored) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) gx[k * gp + g] = sc[(off_gxpos + 3 * g + k) * MJB_LS];
-      }
-    }
-    int total = 0;
-    bool rescan = false;
-    for (int pass = 0; pass < 2; pass++) {
-      // pass 0 buffers the survivors; pass 1 (only when some warp's buffer overflowed) writes them
-      // straight to the item list, whose range is known by then
-      int base = 0;
-      bool fits = true;
-      if (pass == 1) {
-        const bool mine = rescan;
-        if (!__syncthreads_or(mine)) break;
-        if (lane == 0 && mine) base = atomicAdd(&a.cq->nitems, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        fits = base + total <= a.items_cap;
-        if (mine && !fits && lane == 0) a.cq->overflow = 1;
-        if (mine && lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
-      }
-      int count = 0;
-      for (int t0 = 0; t0 < ncand; t0 += kWideTile) {
-        const int nt = ncand - t0 < kWideTile ? ncand - t0 : kWideTile;
-        __syncthreads();
-        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-          tile_bound[i] = scan_bound[t0 + i];
-          tile_int[2 * i] = scan_int[2 * (t0 + i)];
-          tile_int[2 * i + 1] = scan_int[2 * (t0 + i) + 1];
+          for (int k = 0; k < 3; k++) pn[k * kWidePlanes + pid] = (float)sc[(off_gxmat + 9 * g + 2 + 3 * k) * MJB_LS];
         }
-        __syncthreads();
-        if (!valid || (pass == 1 && !rescan)) continue;
-        for (int c0 = 0; c0 < nt; c0 += 32) {
-          const int ci = c0 + lane;
-          bool pass_test = false;
-          if (ci < nt) {
-            const int g1k = tile_int[2 * ci], g2 = tile_int[2 * ci + 1];
-            const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
-            const double bound = tile_bound[ci];
-            const double pos1[3] = {gx[g1], gx[gp + g1], gx[2 * gp + g1]};
-            const double pos2[3] = {gx[g2], gx[gp + g2], gx[2 * gp + g2]};
-            pass_test = true;
-            if (planeflag == 0) {
-              const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
-              pass_test = !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
-            } else if (planeflag == 1) {
-              const double nrm[3] = {sc[(off_gxmat + 9 * g1 + 2) * MJB_LS], sc[(off_gxmat + 9 * g1 + 5) * MJB_LS],
-                                     sc[(off_gxmat + 9 * g1 + 8) * MJB_LS]};
-              const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
-              pass_test = !(dot3(dif, nrm) > bound);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      slack = fmaxf(1e-4f, 8e-6f * m);
+      if (!(m < 1e30f)) slack = 3e38f;    // non-finite positions: everything goes to the exact test
+    }
+    // stage 1: conservative float filter over all candidates
+    int count = 0;
+    for (int t0 = 0; t0 < ncand; t0 += kWideTile) {
+      const int nt = ncand - t0 < kWideTile ? ncand - t0 : kWideTile;
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        tile_bound[i] = __double2float_ru(scan_bound[t0 + i]);
+        tile_int[i] = make_int2(scan_int[2 * (t0 + i)], scan_int[2 * (t0 + i) + 1]);
+      }
+      __syncthreads();
+      if (!valid) continue;
+#pragma unroll 2
+      for (int c0 = 0; c0 < nt; c0 += 32) {
+        const int ci = c0 + lane;
+        bool maybe = false;
+        if (ci < nt) {
+          const int2 gi = tile_int[ci];
+          const int g1 = gi.x & 0xfffffff, g2 = gi.y;
+          const unsigned kind = (unsigned)gi.x >> 28;
+          const float t = tile_bound[ci] + slack;
+          const float dx = gx[g1] - gx[g2], dy = gx[gp + g1] - gx[gp + g2], dz = gx[2 * gp + g1] - gx[2 * gp + g2];
+          if (kind == 0) {
+            maybe = !(dx*dx + dy*dy + dz*dz > t*t);
+          } else {
+            // plane of geom 1 against the centre of geom 2: (pos2 - pos1) . normal > bound drops it
+            const int pid = kind == 1 ? plane_id[g1] : 255;
+            maybe = true;
+            if (pid < kWidePlanes) {
+              const float dist = -(dx * pn[pid] + dy * pn[kWidePlanes + pid] + dz * pn[2 * kWidePlanes + pid]);
+              maybe = !(dist > t);
             }
           }
-          const unsigned m = __ballot_sync(0xffffffffu, pass_test);
-          if (pass == 0 && lane == 0) isc[(size_t)(MJB_ISC_MASK + ((t0 + c0) >> 5)) * MJB_LS] = (int)m;
-          if (pass_test) {
-            const int k = count + __popc(m & ((1u << lane) - 1u));
-            if (pass == 0) { if (k < kWideBuf) buf[k] = t0 + ci; }
-            else if (fits) a.items[base + k] = ContactItem{(int)s, t0 + ci};
-          }
-          count += __popc(m);
         }
+        const unsigned m = __ballot_sync(0xffffffffu, maybe);
+        if (lane == 0) isc[(size_t)(mask_row + ((t0 + c0) >> 5)) * MJB_LS] = (int)m;
+        if (maybe) {
+          const int k = count + __popc(m & ((1u << lane) - 1u));
+          if (k < cap) buf[k] = t0 + ci;
+        }
+        count += __popc(m);
       }
-      if (pass == 0) {
-        total = count;
-        if (valid && lane == 0) isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
-        if (!a.cq) break;                  // pooled path only: the masks are all it needs
-        rescan = valid && total > kWideBuf;
-        if (valid && !rescan) {
-          if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          fits = base + total <= a.items_cap;
-          if (!fits && lane == 0) a.cq->overflow = 1;
-          if (lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
-          if (fits) for (int k = lane; k < total; k += 32) a.items[base + k] = ContactItem{(int)s, buf[k]};
+    }
+    if (!valid) continue;
+    __syncwarp();
+    int total = 0, base = 0;
+    bool fits = true;
+    if (count <= cap) {
+      // stage 2: exact test of the buffered candidates, compacted in place (writes trail the reads)
+      for (int k0 = 0; k0 < count; k0 += 32) {
+        const int k = k0 + lane;
+        const int ci = k < count ? buf[k] : -1;
+        const bool ok = ci >= 0 && scan_exact_test(sc, off_gxpos, off_gxmat, scan_int, scan_bound, ci);
+        __syncwarp();
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) buf[total + __popc(m & ((1u << lane) - 1u))] = ci;
+        else if (ci >= 0) atomicAnd(&isc[(size_t)(mask_row + (ci >> 5)) * MJB_LS], ~(1 << (ci & 31)));
+        total += __popc(m);
+        __syncwarp();
+      }
+      if (lane == 0) isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
+      if (!a.cq) continue;                 // pooled path only: the masks are all it needs
+      if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      fits = base + total <= a.items_cap;
+      if (!fits && lane == 0) a.cq->overflow = 1;
+      if (lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
+      if (fits) for (int k = lane; k < total; k += 32) a.items[base + k] = ContactItem{(int)s, buf[k]};
+    } else {
+      // more candidates than the buffer holds (a very dense state): exact test of the whole list
+      // straight from the tables, first to count and fix the masks, then to write the items
+      for (int pass = 0; pass < 2; pass++) {
+        int n = 0;
+        for (int c0 = 0; c0 < ncand; c0 += 32) {
+          const int ci = c0 + lane;
+          const bool ok = ci < ncand && scan_exact_test(sc, off_gxpos, off_gxmat, scan_int, scan_bound, ci);
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (pass == 0) { if (lane == 0) isc[(size_t)(mask_row + (c0 >> 5)) * MJB_LS] = (int)m; }
+          else if (ok && fits) a.items[base + n + __popc(m & ((1u << lane) - 1u))] = ContactItem{(int)s, ci};
+          n += __popc(m);
         }
+        if (pass == 1) break;
+        total = n;
+        if (lane == 0) isc[(size_t)MJB_ISC_NSURV * MJB_LS] = total;
+        if (!a.cq) break;
+        if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        fits = base + total <= a.items_cap;
+        if (!fits && lane == 0) a.cq->overflow = 1;
+        if (lane == 0) isc[(size_t)MJB_ISC_ITEMBASE * MJB_LS] = fits ? base : -1;
+        if (!fits) break;
       }
     }
   }
@@ -631,7 +887,7 @@ __global__ void __launch_bounds__(256) contact_items_kernel(LaunchArgs a) {
 
 constexpr int kNarrowTiles = 4;      // tiles of 256 items tested per dense narrow-phase round
 
-template <bool kModelInSmem>
+template <bool kModelInSmem, bool kSimple>
 __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
@@ -667,7 +923,7 @@ __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
     const int nh = nhit;
     // dense narrow phase over the CTA's hits (order inside the list is irrelevant)
     for (int h0 = 0; h0 < nh; h0 += 256) {
-      Con con[MJB_MAXCON_PAIR];
+      Con con[kSimple ? 2 : MJB_MAXCON_PAIR];
       int num = 0, item = -1;
       ContactItem it = {0, 0};
       if (h0 + (int)threadIdx.x < nh) {
@@ -675,7 +931,7 @@ __global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
         it = a.items[item];
         Ctx& co = c;      // (a by-value copy of the context is what faulted here; rebinding c is enough)
         bind_state(co, a, it.state);
-        num = narrow_pair(co, it.ci, con);
+        num = narrow_pair<kSimple>(co, it.ci, con);
       }
       if (__any_sync(0xffffffffu, num > 0)) {
         const int incl = warp_incl_scan(num, lane);
@@ -801,17 +1057,15 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
       // J'f: records of this round that hit the same (state, body) form a group (__match_any_sync);
       // the group's wrenches are summed in lane order with shuffles by its first lane, which then
       // does ONE batched read-modify-write of the accumulator row (deterministic, conflict-free)
-      const int* rootid = c.I + c.H->ioff[MJB_I_body_rootid];
 #pragma unroll
       for (int side = 0; side < 2; side++) {
         const int body = side == 0 ? b2 : b1;
         const bool act = has && active && !body_static[body];
         double W[6] = {0, 0, 0, 0, 0, 0};
         if (act) {
-          const double* org = co.sc + (size_t)c.H->scoff[MJB_SC_origin] * MJB_LS;
-          const int root = rootid[body];
-          const double rr[3] = {p[0] - org[(size_t)(3*root) * MJB_LS], p[1] - org[(size_t)(3*root + 1) * MJB_LS],
-                                p[2] - org[(size_t)(3*root + 2) * MJB_LS]};
+          double o4[4];                 // tree origin from the body's carrier record (same line as its carriers)
+          ld_rec4(o4, crec_ptr(co, body) + 3*MJB_CREC_PART);
+          const double rr[3] = {p[0] - o4[0], p[1] - o4[1], p[2] - o4[2]};
           double cr[3];
           cross3(cr, rr, F);
           for (int k = 0; k < 3; k++) { W[k] = cr[k] + T3[k]; W[3 + k] = F[k]; }
@@ -1065,7 +1319,19 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     if (e != cudaSuccess) return e;
     if (want_inertia) {
       PhaseScope ps(timer, stream, kPhaseInertia);
-      e = run_phase(st_inertia, nullptr, args, stream, launches, generic_inertia);
+      if (args.inertia_subwarp) {
+        // 8 lanes per state, intermediates in shared memory (inertia_subwarp_kernel)
+        const size_t wsm = subwarp_layout(args.sub_nv, args.sub_nbody, args.sub_nC).bytes;
+        e = cudaFuncSetAttribute(inertia_subwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
+        if (e != cudaSuccess) return e;
+        long long grid = ((long long)args.chunk_n + 31) >> 5;
+        if (grid > kSMs) grid = kSMs;
+        inertia_subwarp_kernel<<<(int)grid, kSubS * kSubG, wsm, stream>>>(args);
+        e = cudaGetLastError();
+        ++*launches;
+      } else {
+        e = run_phase(st_inertia, nullptr, args, stream, launches, generic_inertia);
+      }
       if (e != cudaSuccess) return e;
     }
   }
@@ -1081,7 +1347,7 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
         e = cudaFuncSetAttribute(contact_scan_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
         if (e != cudaSuccess) return e;
         int grid = (args.chunk_n + args.scan_wide - 1) / args.scan_wide;
-        if (grid > kSMs) grid = kSMs;
+        if (grid > kSMs * kWideCtas) grid = kSMs * kWideCtas;     // the per-warp buffers are sized for this grid
         contact_scan_wide_kernel<<<grid, 32 * args.scan_wide, wsm, stream>>>(args);
         e = cudaGetLastError();
         ++*launches;
@@ -1107,8 +1373,13 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
           ++*launches;
         }
         // the narrow / rows kernels walk lists whose length is only known on the device: full grids
-        e = in_smem ? launch_phase(contact_narrow_kernel<true>, args, smem, 4, stream, 256)
-                    : launch_phase(contact_narrow_kernel<false>, args, 0, 4, stream, 256);
+        if (args.simple_pairs) {
+          e = in_smem ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 4, stream, 256)
+                      : launch_phase(contact_narrow_kernel<false, true>, args, 0, 4, stream, 256);
+        } else {
+          e = in_smem ? launch_phase(contact_narrow_kernel<true, false>, args, smem, 4, stream, 256)
+                      : launch_phase(contact_narrow_kernel<false, false>, args, 0, 4, stream, 256);
+        }
         if (e != cudaSuccess) return e;
         e = in_smem ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
                     : launch_phase(contact_index_kernel<false>, args, 0, 8, stream);

@@ -61,6 +61,11 @@ size_t inverse_smem_bytes(int model_bytes, int model_in_smem);
 // `ngeom` geoms; 0: the thread-per-state scan is used (short lists, or positions do not fit shared memory)
 int scan_wide_states(int ncand, int ngeom);
 size_t scan_wide_smem_bytes(int ngeom, int states_per_cta);
+int scan_wide_buf_cap(int ncand);                     // ints per warp of the stage-1 -> stage-2 buffer
+long long scan_wide_buf_ints(int ncand, int ngeom);   // ... and in total for the launch's fixed grid
+
+// the sub-warp mj_crb / mj_factorM kernel keeps cdof, crb and the sparse matrix of 32 states in shared memory
+bool inertia_subwarp_fits(int nv, int nbody, int nC);
 
 }  // namespace mjb
 

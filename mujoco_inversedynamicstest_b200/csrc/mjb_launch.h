@@ -59,9 +59,14 @@ struct LaunchArgs {
   int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
+  int simple_pairs;             // mjbHdr::simple_pairs (selects the narrow-phase kernel instantiation)
   int skip_sensors;             // mj_inverseSkip(skipsensor = 1): leave sensordata as it is
+  int inertia_subwarp;          // 1: mj_crb + mj_factorM by inertia_subwarp_kernel (8 lanes per state, on-chip intermediates)
+  int sub_nv, sub_nbody, sub_nC; //    its sizes (mjbHdr::nv, nbody, nC)
   int scan_wide;                // > 0: warp-per-state candidate scan with this many states per CTA
                                 //      (scenes with long candidate lists, mjb_kernels.cu)
+  int* scan_buf;                // per-warp candidate buffers of the wide scan (scan_wide_buf_ints), or null
+  int scan_buf_cap;             //   ints per warp
   int scan_ngeom;               // mjbHdr::ngeom (sizes the wide scan's shared memory)
   Outputs out;
 };

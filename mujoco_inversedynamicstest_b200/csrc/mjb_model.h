@@ -78,7 +78,8 @@
   X(body_tree_flags) /* nbody: bit0 has child bodies, bit1 highest-index child of its parent, \
                                  bit2 has a child other than body+1 (forward-sweep carry must be stored), \
                                  bit3 pose read by an equality constraint or a tendon site, \
-                                 bit4 velocity carriers read by constraint rows (candidate pair, equality, tendon site) */
+                                 bit4 velocity carrier rows read by constraint rows (equality, tendon site), \
+                                 bit5 body of a candidate pair: its carrier record (MJB_SC_crec) is read by contact rows */
 
 // ---- double arrays copied 1:1 from mjModel (name, rows, cols)
 #define MJB_NUM_ARRAYS(X)         \
@@ -268,6 +269,9 @@ enum {
   MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
   MJB_SC_weld_dt,      // neq*3     weld rows: (raw rotational efc_force) - (torque J'f), for the cfrc_ext output (only models with welds)
   MJB_SC_tree_sphere,  // ntree*4   bounding sphere of every kinematic tree (tree-level broadphase; only with scan runs)
+  MJB_SC_crec,         // nbody*16  contact carrier RECORDS (only with candidate pairs): 16 doubles [cvel 6 | cacc_lin 6 |
+                       //           tree origin 3 | 0] per (body, state) as four 32-byte parts, part q of lane l at
+                       //           ((16*b + 4*q)*32 + 4*l): coalesced 256-bit stores, whole-sector gathers (mjb_pipeline.h)
   MJB_SC_COUNT
 };
 
@@ -295,7 +299,7 @@ typedef struct mjbHdr_ {
   int32_t nmocap;
   int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
-  int32_t pad0;
+  int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)
   double timestep, impratio;
   double gravity[3];
   int32_t nrun;             // runs of the candidate list for the tree-level broadphase (0: flat scan)

@@ -223,6 +223,69 @@ MJB_DI void stn_stream_(double* p, int first, const double* src, int n, size_t s
 #define ldn_ro(dst, p, first, n) ldn_ro_(dst, p, first, n, MJB_LS)
 #define stn(p, first, src, n) stn_(p, first, src, n, MJB_LS)
 
+// Contact carrier records (MJB_SC_crec, mjb_model.h): 16 doubles per (body, state) as four
+// 32-byte parts; part q of the 32 states of a warp block is one contiguous KB, so the forward sweep
+// writes a record with four fully coalesced 256-bit stores and a contact row gathers it with four
+// 256-bit loads, each ONE whole sector (the row layout costs it 15 sectors of 8 useful bytes).
+// Part 0: cvel[0..3]; 1: cvel[4..5], cacc_lin[0..1]; 2: cacc_lin[2..5]; 3: tree origin, 0.
+#define MJB_CREC_PART (4 * MJB_LS)      // doubles between the parts of one record
+MJB_HD inline double* crec_ptr(Ctx& c, int b) {
+#if defined(__CUDA_ARCH__)
+  // c.sc = (256-byte aligned block base) + lane: recover the lane from the address
+  const size_t ln = ((size_t)c.sc >> 3) & 31;
+  return c.sc - ln + ((size_t)c.H->scoff[MJB_SC_crec] + 16*(size_t)b) * 32 + ln*4;
+#else
+  return c.sc + ((size_t)c.H->scoff[MJB_SC_crec] + 16*(size_t)b);
+#endif
+}
+// 256-bit global accesses exist from PTX ISA 8.8 (CUDA 12.9) on; older NVRTCs get 128-bit pairs
+#if defined(__CUDA_ARCH__) && (__CUDACC_VER_MAJOR__ > 12 || (__CUDACC_VER_MAJOR__ == 12 && __CUDACC_VER_MINOR__ >= 9))
+#define MJB_WIDE256 1
+#else
+#define MJB_WIDE256 0
+#endif
+MJB_DI void st_rec4(double* p, double a, double b, double cc, double d) {
+#if defined(__CUDA_ARCH__)
+#if MJB_WIDE256
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(cc), "d"(d) : "memory");
+#else
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" :: "l"(p + 2), "d"(cc), "d"(d) : "memory");
+#endif
+#else
+  p[0] = a; p[1] = b; p[2] = cc; p[3] = d;
+#endif
+}
+MJB_DI void ld_rec4(double* dst, const double* p) {
+#if defined(__CUDA_ARCH__)
+#if MJB_WIDE256
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(dst[0]), "=d"(dst[1]), "=d"(dst[2]), "=d"(dst[3]) : "l"(p) : "memory");
+#else
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(dst[0]), "=d"(dst[1]) : "l"(p) : "memory");
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(dst[2]), "=d"(dst[3]) : "l"(p + 2) : "memory");
+#endif
+#else
+  dst[0] = p[0]; dst[1] = p[1]; dst[2] = p[2]; dst[3] = p[3];
+#endif
+}
+MJB_HD inline void store_crec(Ctx& c, int b, const double* V, const double* AL, const double* O) {
+  double* r = crec_ptr(c, b);
+  st_rec4(r, V[0], V[1], V[2], V[3]);
+  st_rec4(r + MJB_CREC_PART, V[4], V[5], AL[0], AL[1]);
+  st_rec4(r + 2*MJB_CREC_PART, AL[2], AL[3], AL[4], AL[5]);
+  st_rec4(r + 3*MJB_CREC_PART, O[0], O[1], O[2], 0.0);
+}
+// rec[16] of body b; a body without a dof on its chain to the world has zero carriers and no record
+MJB_HD inline void load_crec(Ctx& c, int b, bool is_static, double* rec) {
+  if (is_static) {
+    for (int k = 0; k < 16; k++) rec[k] = 0;
+    return;
+  }
+  const double* r = crec_ptr(c, b);
+  ld_rec4(rec, r); ld_rec4(rec + 4, r + MJB_CREC_PART); ld_rec4(rec + 8, r + 2*MJB_CREC_PART); ld_rec4(rec + 12, r + 3*MJB_CREC_PART);
+}
+
 // per-state integer scratch rows: counters carried between the phase kernels
 // MJB_ISC_NSURV / MJB_ISC_MASK..: survivors of the contact scan (count, then ceil(ncand/32) words)
 // MJB_ISC_ITEMBASE: first entry of the state's survivors in the chunk's global item list (-1: none)
@@ -1506,6 +1569,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       stc(cvel, 6*b, V, 6);
       stc(cal, 6*b, AL, 6);
     }
+    // body of a candidate pair: the carrier record the contact rows gather (one 128-byte line)
+    if (tree_flags[b] & 32) store_crec(c, b, V, AL, O);
     // read back only by a child that is not b+1, or by the mj_rnePostConstraint outputs
     if ((tree_flags[b] & 4) || c.out.cacc || c.out.qfrc_bias) stc(cacc, 6*b, A, 6);
 
@@ -1593,6 +1658,29 @@ MJB_HD inline void rel_motion(Ctx& c, const double* carrier, int b1, int b2, con
   }
 }
 
+// the same for the two bodies of a contact, velocity and acceleration carriers at once, from their
+// carrier records (MJB_SC_crec): one 128-byte line per moving body
+MJB_HD inline void contact_rel_motion(Ctx& c, int b1, int b2, const double* p, double* vlin, double* vang,
+                                      double* alin, double* aang) {
+  const int* body_static = MI(body_static);
+  double r1[16], r2[16], r[3], c1[3], c2[3];
+  load_crec(c, b1, body_static[b1] != 0, r1);
+  load_crec(c, b2, body_static[b2] != 0, r2);
+  r[0] = p[0] - r1[12]; r[1] = p[1] - r1[13]; r[2] = p[2] - r1[14];
+  double a1[3], a2[3];
+  cross3(c1, r1, r);
+  cross3(a1, r1 + 6, r);
+  r[0] = p[0] - r2[12]; r[1] = p[1] - r2[13]; r[2] = p[2] - r2[14];
+  cross3(c2, r2, r);
+  cross3(a2, r2 + 6, r);
+  for (int k = 0; k < 3; k++) {
+    vlin[k] = (r2[3+k] + c2[k]) - (r1[3+k] + c1[k]);
+    vang[k] = r2[k] - r1[k];
+    alin[k] = (r2[9+k] + a2[k]) - (r1[9+k] + a1[k]);
+    aang[k] = r2[6+k] - r1[6+k];
+  }
+}
+
 // add the wrench (torque T about point p, force F at p) to body b2 and its opposite to body b1
 MJB_HD inline void apply_wrench(Ctx& c, int b1, int b2, const double* p, const double* F,
                                 const double* T) {
@@ -1655,16 +1743,15 @@ MJB_HD inline void contact_rows(Ctx& c, int ci, const Con& con, int k, int exclu
   const double pen = con.dist - includemargin;
 
   // relative motion in the contact frame: index 0..2 translation, 3..5 rotation
-  double lin[3], ang[3], vel[6], acc[6];
-  rel_motion(c, SC(cvel), b1, b2, con.pos, lin, ang);
+  double lin[3], ang[3], alin[3], aang[3], vel[6], acc[6];
+  contact_rel_motion(c, b1, b2, con.pos, lin, ang, alin, aang);
   for (int j = 0; j < 3; j++) {
     vel[j] = dot3(con.frame + 3*j, lin);
     vel[3 + j] = dot3(con.frame + 3*j, ang);
   }
-  rel_motion(c, SC(cacc_lin), b1, b2, con.pos, lin, ang);
   for (int j = 0; j < 3; j++) {
-    acc[j] = dot3(con.frame + 3*j, lin);
-    acc[3 + j] = dot3(con.frame + 3*j, ang);
+    acc[j] = dot3(con.frame + 3*j, alin);
+    acc[3 + j] = dot3(con.frame + 3*j, aang);
   }
 
   // force coefficients along the 6 contact-frame directions (J' f)
@@ -2715,6 +2802,10 @@ MJB_COLD inline int box_box(Con* con, double margin, const double* pos1, const d
 
 // narrow phase of candidate pair ci on the state bound to c; contact frames are completed
 // (mju_makeFrame) before returning. Returns the number of contacts (<= MJB_MAXCON_PAIR).
+// kSimple: the model's pairs are all plane / sphere / capsule against sphere / capsule (mjbHdr::simple_pairs),
+// so that at most two contacts come back and `con` can stay in registers (no dynamically indexed primitive
+// is compiled in).
+template <bool kSimple = false>
 MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
@@ -2725,7 +2816,7 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int func = cint[MJB_CI_FUNC];
   double pos1[3], pos2[3], mat1[9], mat2[9];
   ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
-  if (func == MJB_FN_PLANE_SPHERE || func == MJB_FN_PLANE_CAPSULE || func == MJB_FN_SPHERE_SPHERE ||
+  if (kSimple || func == MJB_FN_PLANE_SPHERE || func == MJB_FN_PLANE_CAPSULE || func == MJB_FN_SPHERE_SPHERE ||
       func == MJB_FN_SPHERE_CAPSULE || func == MJB_FN_CAPSULE_CAPSULE) {
     // these read only the z axis of either frame (plane normal, capsule axis): 6 loads instead of 18
     for (int k = 0; k < 9; k++) { mat1[k] = 0; mat2[k] = 0; }
@@ -2739,18 +2830,18 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   switch (func) {
     case MJB_FN_PLANE_SPHERE: num = plane_sphere(con, margin, pos1, mat1, pos2, size2[0]); break;
     case MJB_FN_PLANE_CAPSULE: num = plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2); break;
-    case MJB_FN_PLANE_CYLINDER: num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
-    case MJB_FN_PLANE_BOX: num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
-    case MJB_FN_PLANE_ELLIPSOID: num = plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2); break;
-    case MJB_FN_SPHERE_BOX: num = sphere_box(con, margin, pos1, size1, pos2, mat2, size2); break;
-    case MJB_FN_CAPSULE_BOX: num = capsule_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
-    case MJB_FN_BOX_BOX: num = box_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_CYLINDER: if (!kSimple) num = plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_BOX: if (!kSimple) num = plane_box(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_PLANE_ELLIPSOID: if (!kSimple) num = plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2); break;
+    case MJB_FN_SPHERE_BOX: if (!kSimple) num = sphere_box(con, margin, pos1, size1, pos2, mat2, size2); break;
+    case MJB_FN_CAPSULE_BOX: if (!kSimple) num = capsule_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_BOX_BOX: if (!kSimple) num = box_box(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_SPHERE:
       num = sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]); break;
     case MJB_FN_SPHERE_CAPSULE:
       num = sphere_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_SPHERE_CYLINDER:
-      num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+      if (!kSimple) num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_CAPSULE_CAPSULE:
       num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     default: break;

@@ -423,6 +423,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   std::vector<int> cand_int;
   std::vector<double> cand_num;
   int ncand = 0, max_pair_contacts = 1;
+  bool simple_pairs = true;
   for (const Candidate& cd : cands) {
     int g1 = cd.g1, g2 = cd.g2;
     const int ipair = cd.ipair;
@@ -482,6 +483,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
                       : (fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE ||
                          fn == MJB_FN_CAPSULE_BOX) ? 2 : 1;
       max_pair_contacts = std::max(max_pair_contacts, per);
+      simple_pairs = simple_pairs && (fn == MJB_FN_PLANE_SPHERE || fn == MJB_FN_PLANE_CAPSULE || fn == MJB_FN_SPHERE_SPHERE ||
+                                      fn == MJB_FN_SPHERE_CAPSULE || fn == MJB_FN_CAPSULE_CAPSULE);
     }
     ci[MJB_CI_B1] = b1; ci[MJB_CI_B2] = b2;
     // NV == 0 only arises for the sparse Jacobian's merged chain (engine_support.c:659-690)
@@ -721,6 +724,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.ncand = ncand;
   H.nrun = nrun; H.ntree = ntree;
   H.max_pair_contacts = max_pair_contacts;
+  H.simple_pairs = simple_pairs ? 1 : 0;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
   H.passive_wrench = (gravcomp || spatial_passive) ? 1 : 0;
@@ -815,12 +819,12 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         }
       }
     }
-    // bodies whose velocity / acceleration carriers (cvel, cacc_lin) a later phase reads: the two
-    // bodies of every candidate pair (contact rows) and the bodies flagged above (equality rows,
-    // tendon sites)
+    // bodies whose velocity / acceleration carriers (cvel, cacc_lin) a later phase reads: the
+    // bodies flagged above (equality rows, tendon sites) read the carrier ROWS (bit 4), the two
+    // bodies of every candidate pair (contact rows) read the carrier RECORD (bit 5, MJB_SC_crec)
     for (int i = 0; i < ncand; i++) {
       const int* ci = cand_int.data() + (size_t)i * MJB_CAND_NI;
-      flags[ci[MJB_CI_B1]] |= 16; flags[ci[MJB_CI_B2]] |= 16;
+      flags[ci[MJB_CI_B1]] |= 32; flags[ci[MJB_CI_B2]] |= 32;
     }
     for (int b = 0; b < m->nbody; b++) if (flags[b] & 8) flags[b] |= 16;
     pushInts(MJB_I_body_tree_flags, flags.data(), flags.size());
@@ -881,6 +885,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       sizes[MJB_SC_weld_dt] = has_weld ? 3*m->neq : 0;
     }
     sizes[MJB_SC_tree_sphere] = 4*ntree;
+    sizes[MJB_SC_crec] = ncand > 0 ? 16*nb : 0;
     int off = 0;
     for (int s = 0; s < MJB_SC_COUNT; s++) { H.scoff[s] = off; off += sizes[s]; }
     H.nscratch = off;

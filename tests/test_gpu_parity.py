@@ -94,6 +94,25 @@ def test_golden_inertia_outputs(name):
     np.testing.assert_allclose(cdof, ref["cdof"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["humanoid", "humanoid_nocontact", "arm26", "zoo", "weld", "capsbox", "gravcomp",
+                                  "ref_inertia", "ref_dofless_weld", "ref_humanoid_sparse", "tendons"])
+def test_subwarp_inertia_kernel(name, monkeypatch):
+    """mj_crb + mj_factorM by the sub-warp kernel (8 lanes per state, intermediates in shared
+    memory; MJB_INERTIA=subwarp selects it for A/B runs) against the reference's qM / qLD / qLDiagInv,
+    and against the thread-per-state kernel's."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    monkeypatch.setenv("MJB_INERTIA", "thread")
+    _, bd, ref, _, _ = _run(mjb, name, True, mjb.OUT_INERTIA)
+    thread = {f: bd.get(f) for f in (mjb.F_QM, mjb.F_QLD, mjb.F_QLDIAGINV)}
+    bd.close()
+    monkeypatch.setenv("MJB_INERTIA", "subwarp")
+    _, bd, ref, _, _ = _run(mjb, name, True, mjb.OUT_INERTIA)
+    for f, k in ((mjb.F_QM, "qM"), (mjb.F_QLD, "qLD"), (mjb.F_QLDIAGINV, "qLDiagInv")):
+        got = bd.get(f)
+        np.testing.assert_allclose(got, ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
+        np.testing.assert_allclose(got, thread[f], rtol=1e-10, atol=1e-13, err_msg=k + " vs thread-per-state")
+
+
 @pytest.mark.parametrize("name", util.POST_CASES)
 def test_golden_rne_post_constraint(name):
     """mjbOUT_RNEPOST: cacc, cfrc_int, cfrc_ext of the reference's mj_rnePostConstraint after
