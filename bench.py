@@ -482,7 +482,7 @@ def main():
             kc = kcounts.get(name, {})
             fl, by = kc.get("flops"), kc.get("dram_bytes")
             kernels.append({
-                "kernel": ("contact_items+narrow+index+rows kernels" if name == "contact" else name + "_kernel"),
+                "kernel": ("contact_narrow+index+rows kernels" if name == "contact" else name + "_kernel"),
                 "ms_per_step": ms,
                 "share": ms / max(sum(phase_ms.values()), 1e-12),
                 "fp64_tflops": (fl * n / (ms * 1e-3) * 1e-12) if fl else None,

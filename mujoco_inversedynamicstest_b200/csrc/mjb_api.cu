@@ -278,8 +278,9 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
       // MJB_ITEMS_PER_STATE / MJB_CONTACTS_PER_STATE override the list sizing (tests, measurements)
       // sized per model: a single articulated figure has <= 48 survivors and <= 16 contacts per state
       // on average (humanoid: 15.6 and 6.1); scenes with many geoms (22 humanoids in a pile: 1,210
-      // survivors and 322 contacts per state, 419 geoms) get lists proportional to the geom count
-      long long per_items = H.ngeom > 64 ? 4LL * H.ngeom : 48, per_contacts = H.ngeom > 64 ? H.ngeom : 16;
+      // survivors and 322 contacts per state, 419 geoms; 100 humanoids: ~4,300 contacts, 1901 geoms) get lists
+      // proportional to the geom count
+      long long per_items = H.ngeom > 64 ? 8LL * H.ngeom : 48, per_contacts = H.ngeom > 64 ? 3LL * H.ngeom : 16;
       if (per_items > H.ncand) per_items = H.ncand;
       if (const char* env = std::getenv("MJB_ITEMS_PER_STATE")) { if (std::atol(env) > 0) per_items = std::atol(env); }
       if (const char* env = std::getenv("MJB_CONTACTS_PER_STATE")) { if (std::atol(env) > 0) per_contacts = std::atol(env); }

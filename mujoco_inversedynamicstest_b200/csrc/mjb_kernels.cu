@@ -181,11 +181,13 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_INERTIA) inertia_kernel(Lau
 constexpr int kSubG = 8;            // workers per state
 constexpr int kSubS = 32;           // states per CTA (one warp block of the scratch)
 
-struct SubwarpLayout { int cd, cr, ws; size_t bytes; };
+struct SubwarpLayout { int cd, cr, ws, tab_ints; size_t bytes; };
 SubwarpLayout subwarp_layout(int nv, int nbody, int nC) {
   SubwarpLayout L;
   L.cd = (6 * nv) | 1; L.cr = (10 * nbody) | 1; L.ws = nC | 1;
-  L.bytes = (size_t)kSubS * (size_t)(L.cd + L.cr + L.ws) * sizeof(double);
+  L.tab_ints = ((nbody + 7 * nv + 3 * nC) + 1) & ~1;          // index tables, kept 8-byte aligned
+  L.bytes = (size_t)kSubS * (size_t)(L.cd + L.cr + L.ws) * sizeof(double) + (size_t)2 * nv * sizeof(double) +
+            (size_t)L.tab_ints * sizeof(int);
   return L;
 }
 bool inertia_subwarp_fits(int nv, int nbody, int nC) {
@@ -198,39 +200,71 @@ __global__ void __launch_bounds__(kSubS * kSubG, 1) inertia_subwarp_kernel(Launc
   const int* I = reinterpret_cast<const int*>(a.model + H->int_section);
   const double* D = reinterpret_cast<const double*>(a.model + H->num_section);
   const int nv = H->nv, nbody = H->nbody, nC = H->nC;
-  const int* body_parentid = I + H->ioff[MJB_I_body_parentid];
-  const int* dof_bodyid = I + H->ioff[MJB_I_dof_bodyid];
-  const int* dof_parentid = I + H->ioff[MJB_I_dof_parentid];
-  const int* dof_Madr = I + H->ioff[MJB_I_dof_Madr];
-  const int* dof_simplenum = I + H->ioff[MJB_I_dof_simplenum];
-  const int* rownnz = I + H->ioff[MJB_I_C_rownnz];
-  const int* rowadr = I + H->ioff[MJB_I_C_rowadr];
-  const int* colind = I + H->ioff[MJB_I_C_colind];
-  const int* mapM2C = I + H->ioff[MJB_I_mapM2C];
-  const double* armature = D + H->noff[MJB_N_dof_armature];
-  const double* dof_M0 = D + H->noff[MJB_N_dof_M0];
   const int CD = (6 * nv) | 1, CR = (10 * nbody) | 1, WS = nC | 1;
   double* cd_all = sw;
   double* cr_all = cd_all + (size_t)kSubS * CD;
   double* ws_all = cr_all + (size_t)kSubS * CR;
+  // the model's index tables, once per CTA, in shared memory: every look-up of the sweeps below is an
+  // LDS with at most 8 distinct addresses per warp instead of a dependent global load
+  double* armature = ws_all + (size_t)kSubS * WS;             // [nv]
+  double* dof_M0 = armature + nv;                              // [nv]
+  int* body_parentid = reinterpret_cast<int*>(dof_M0 + nv);    // [nbody]
+  int* dof_bodyid = body_parentid + nbody;                     // [nv] ...
+  int* dof_parentid = dof_bodyid + nv;
+  int* dof_Madr = dof_parentid + nv;
+  int* dof_simplenum = dof_Madr + nv;
+  int* rownnz = dof_simplenum + nv;
+  int* rowadr = rownnz + nv;
+  int* diagadr = rowadr + nv;                                  // rowadr + rownnz - 1
+  int* colind = diagadr + nv;                                  // [nC]
+  int* mapM2C = colind + nC;                                   // [nC]
+  int* ancrow = mapM2C + nC;                                   // [nC]: rowadr[colind[e]], the row a C entry's column owns
   const int tid = threadIdx.x;
+  {
+    const int* g_rownnz = I + H->ioff[MJB_I_C_rownnz];
+    const int* g_rowadr = I + H->ioff[MJB_I_C_rowadr];
+    const int* g_colind = I + H->ioff[MJB_I_C_colind];
+    for (int i = tid; i < nbody; i += blockDim.x) body_parentid[i] = (I + H->ioff[MJB_I_body_parentid])[i];
+    for (int i = tid; i < nv; i += blockDim.x) {
+      dof_bodyid[i] = (I + H->ioff[MJB_I_dof_bodyid])[i];
+      dof_parentid[i] = (I + H->ioff[MJB_I_dof_parentid])[i];
+      dof_Madr[i] = (I + H->ioff[MJB_I_dof_Madr])[i];
+      dof_simplenum[i] = (I + H->ioff[MJB_I_dof_simplenum])[i];
+      rownnz[i] = g_rownnz[i]; rowadr[i] = g_rowadr[i]; diagadr[i] = g_rowadr[i] + g_rownnz[i] - 1;
+      armature[i] = (D + H->noff[MJB_N_dof_armature])[i];
+      dof_M0[i] = (D + H->noff[MJB_N_dof_M0])[i];
+    }
+    for (int e = tid; e < nC; e += blockDim.x) {
+      colind[e] = g_colind[e];
+      mapM2C[e] = (I + H->ioff[MJB_I_mapM2C])[e];
+      ancrow[e] = g_rowadr[g_colind[e]];
+    }
+  }
   const int s = tid / kSubG, g = tid % kSubG;          // compute phases: state, worker
   const int sl = tid & 31, rl = tid >> 5;              // transfer phases: state = lane, row slice
   constexpr int kRows = kSubS * kSubG / 32;            // rows moved per pass
   double* cd = cd_all + (size_t)s * CD;
   double* cr = cr_all + (size_t)s * CR;
   double* ws = ws_all + (size_t)s * WS;
+  double* cd_t = cd_all + (size_t)sl * CD;             // transfer views: this lane's state
+  double* cr_t = cr_all + (size_t)sl * CR;
+  double* ws_t = ws_all + (size_t)sl * WS;
   const size_t off_cdof = (size_t)H->scoff[MJB_SC_cdof], off_cinert = (size_t)H->scoff[MJB_SC_cinert];
   const size_t N = (size_t)a.stride;
   const long long nblocks = (a.chunk_n + 31) >> 5;
+  const int ncd = 6 * nv, ncr = 10 * nbody;
 
   for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const double* sc = a.scratch + (blk * a.nscratch << 5);
     const long long sg = a.chunk_start + (blk << 5) + sl;          // global state of the transfer lane
     const bool live = (blk << 5) + sl < a.chunk_n;
     // ---- load
-    for (int r = rl; r < 6 * nv; r += kRows) cd_all[(size_t)sl * CD + r] = __ldcs(sc + ((off_cdof + r) << 5) + sl);
-    for (int r = rl; r < 10 * nbody; r += kRows) cr_all[(size_t)sl * CR + r] = __ldcs(sc + ((off_cinert + r) << 5) + sl);
+    {
+      const double* src = sc + (off_cdof << 5) + sl;
+      for (int r = rl; r < ncd; r += kRows) cd_t[r] = __ldcs(src + ((size_t)r << 5));
+      src = sc + (off_cinert << 5) + sl;
+      for (int r = rl; r < ncr; r += kRows) cr_t[r] = __ldcs(src + ((size_t)r << 5));
+    }
     __syncthreads();
     // ---- crb: components g and g + 8 of every body, leaves to root
     for (int comp = g; comp < 10; comp += kSubG) {
@@ -242,7 +276,7 @@ __global__ void __launch_bounds__(kSubS * kSubG, 1) inertia_subwarp_kernel(Launc
     __syncwarp();
     // ---- M: the entries of rows g, g + 8, ...
     for (int i = g; i < nv; i += kSubG) {
-      const int diag = rowadr[i] + rownnz[i] - 1;
+      const int diag = diagadr[i];
       if (dof_simplenum[i]) {
         // simple body: M is diagonal and constant (engine_core_smooth.c:1375-1385); the legacy qM
         // keeps the zero ancestor entries, which the reduced rows do not hold
@@ -255,31 +289,36 @@ __global__ void __launch_bounds__(kSubS * kSubG, 1) inertia_subwarp_kernel(Launc
         continue;
       }
       double S[6], inert[10], buf[6];
+      const double* ci = cd + 6 * i;
 #pragma unroll
-      for (int k = 0; k < 6; k++) S[k] = cd[6 * i + k];
-      const int b = dof_bodyid[i];
+      for (int k = 0; k < 6; k++) S[k] = ci[k];
+      const double* cb = cr + 10 * dof_bodyid[i];
 #pragma unroll
-      for (int k = 0; k < 10; k++) inert[k] = cr[10 * b + k];
+      for (int k = 0; k < 10; k++) inert[k] = cb[k];
       mulInertVecF(buf, inert, S);
       ws[diag] = armature[i] + dot6f(S, buf);
-      int e = diag - 1;
-      for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j], e--) {
+      double* we = ws + diag - 1;
+      for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j], we--) {
+        const double* cj = cd + 6 * j;
         double Sj[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) Sj[k] = cd[6 * j + k];
-        ws[e] = dot6f(Sj, buf);
+        for (int k = 0; k < 6; k++) Sj[k] = cj[k];
+        *we = dot6f(Sj, buf);
       }
     }
     __syncthreads();
     // ---- qM out (legacy layout), whole rows
     if (live) {
-      for (int k = rl; k < nC; k += kRows) __stcs(a.out.qM + (size_t)mapM2C[k] * N + sg, ws_all[(size_t)sl * WS + k]);
+      double* dst = a.out.qM + sg;
+      for (int k = rl; k < nC; k += kRows) __stcs(dst + (size_t)mapM2C[k] * N, ws_t[k]);
     }
     __syncthreads();
     // ---- L'DL in place (mj_factorI): 1/D of row k lands in the dead cdof row of the state
     for (int k = nv - 1; k >= 0; k--) {
-      const int rk = rowadr[k], na = rownnz[k] - 1;        // ancestors of k
-      const double invD = 1 / ws[rk + na];
+      const int na = rownnz[k] - 1;                         // ancestors of k
+      double* rowk = ws + rowadr[k];
+      const int* anck = ancrow + rowadr[k];
+      const double invD = 1 / rowk[na];
       if (g == 0) cd[k] = invD;
       if (dof_simplenum[k] || na == 0) continue;
       // ancestor rows p (length p + 1) in pairs (p, na - 1 - p): equal work per worker
@@ -287,34 +326,36 @@ __global__ void __launch_bounds__(kSubS * kSubG, 1) inertia_subwarp_kernel(Launc
       int pp[2];
       pp[0] = g < na ? g : -1;
       pp[1] = (na - 1 - g >= kSubG) ? na - 1 - g : -1;
-      // more than 2 * kSubG ancestors: the rows in between, dealt out round robin
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         tmp[q] = 0;
         if (pp[q] < 0) continue;
         const int p = pp[q];
-        tmp[q] = ws[rk + p] * invD;
-        double* ri = ws + rowadr[colind[rk + p]];
+        tmp[q] = rowk[p] * invD;
+        double* ri = ws + anck[p];
         const double scl = -tmp[q];
-        for (int t = 0; t <= p; t++) ri[t] = fma(scl, ws[rk + t], ri[t]);
+#pragma unroll 4
+        for (int t = 0; t <= p; t++) ri[t] = fma(scl, rowk[t], ri[t]);
       }
       for (int p = kSubG + g; p < na - kSubG; p += kSubG) {      // deep chains only (na > 16)
-        const double tp = ws[rk + p] * invD;
-        double* ri = ws + rowadr[colind[rk + p]];
-        for (int t = 0; t <= p; t++) ri[t] = fma(-tp, ws[rk + t], ri[t]);
+        const double tp = rowk[p] * invD;
+        double* ri = ws + anck[p];
+        for (int t = 0; t <= p; t++) ri[t] = fma(-tp, rowk[t], ri[t]);
       }
       __syncwarp();
       // row k itself is scaled after every worker has read its unscaled entries
 #pragma unroll
-      for (int q = 0; q < 2; q++) if (pp[q] >= 0) ws[rk + pp[q]] = tmp[q];
-      for (int p = kSubG + g; p < na - kSubG; p += kSubG) ws[rk + p] *= invD;
+      for (int q = 0; q < 2; q++) if (pp[q] >= 0) rowk[pp[q]] = tmp[q];
+      for (int p = kSubG + g; p < na - kSubG; p += kSubG) rowk[p] *= invD;
       __syncwarp();
     }
     __syncthreads();
     // ---- qLD, qLDiagInv out
     if (live) {
-      for (int k = rl; k < nC; k += kRows) __stcs(a.out.qLD + (size_t)k * N + sg, ws_all[(size_t)sl * WS + k]);
-      for (int k = rl; k < nv; k += kRows) __stcs(a.out.qLDiagInv + (size_t)k * N + sg, cd_all[(size_t)sl * CD + k]);
+      double* dst = a.out.qLD + sg;
+      for (int k = rl; k < nC; k += kRows) __stcs(dst + (size_t)k * N, ws_t[k]);
+      dst = a.out.qLDiagInv + sg;
+      for (int k = rl; k < nv; k += kRows) __stcs(dst + (size_t)k * N, cd_t[k]);
     }
     __syncthreads();
   }
@@ -341,10 +382,13 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
   __shared__ uint64_t mbar;
   Ctx c;
   make_ctx<kModelInSmem>(c, a, smem, &mbar);
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
-       i += (long long)gridDim.x * kThreads) {
-    bind_state(c, a, i);
-    contact_scan(c);
+  const int nwords = (c.H->ncand + 31) >> 5;
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n; i0 += (long long)gridDim.x * kThreads) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < a.chunk_n;
+    bind_state(c, a, valid ? i : 0);
+    if (valid) contact_scan(c);
+    if (a.cq) scan_append_items(a, c.isc, valid, i, nwords);     // item-parallel path: survivors -> item list
   }
 }
 
@@ -845,7 +889,8 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
 // Item-parallel contact phase (default path). The pooled kernel above serialises the work of 32
 // states inside one warp at 8 warps per SM; here every stage is its own kernel with one thread
 // per work item and no shared-memory pools, so each runs at full occupancy with dense lanes:
-//   contact_items : state  -> its bounding-sphere survivors appended to the global item list
+//   (scan tail)   : state  -> its bounding-sphere survivors appended to the global item list
+//                             (scan_append_items, mjb_launch.h; the warp-per-state scan does it itself)
 //   contact_narrow: item   -> exact hit test; hits are compacted per CTA and run the narrow phase;
 //                             contacts are appended to the global contact list
 //   contact_index : state  -> walks its items in candidate order: contact index k and first efc row
@@ -853,42 +898,13 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
 //   contact_rows  : contact-> constraint rows; J'f kept in the record
 // and the backward kernel adds the records' wrenches to its own state in contact order.
 
-__global__ void __launch_bounds__(256) contact_items_kernel(LaunchArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int nwords = (reinterpret_cast<const mjbHdr*>(a.model)->ncand + 31) >> 5;   // global read, uniform
-  for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < a.chunk_n; i0 += (long long)gridDim.x * blockDim.x) {
-    const long long i = i0 + threadIdx.x;
-    const bool valid = i < a.chunk_n;
-    int* isc = a.iscratch + (((valid ? i : 0) >> 5) * a.niscratch << 5) + ((valid ? i : 0) & 31);
-    const int nsurv = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
-    const int incl = warp_incl_scan(nsurv, lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const bool fits = base + total <= a.items_cap;
-    if (!fits && lane == 0) a.cq->overflow = 1;
-    const int mybase = fits ? base + incl - nsurv : -1;
-    if (valid) isc[MJB_ISC_ITEMBASE * MJB_LS] = mybase;
-    if (valid && fits && nsurv) {
-      int k = 0;
-      for (int w = 0; w < nwords; w++) {
-        unsigned bits = (unsigned)isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
-        while (bits) {
-          const int b = __ffs((int)bits) - 1;
-          bits &= bits - 1;
-          a.items[mybase + k] = ContactItem{(int)i, (w << 5) + b};
-          k++;
-        }
-      }
-    }
-  }
-}
-
 constexpr int kNarrowTiles = 4;      // tiles of 256 items tested per dense narrow-phase round
 
+#ifndef MJB_NARROW_SIMPLE_CTAS
+#define MJB_NARROW_SIMPLE_CTAS 3
+#endif
 template <bool kModelInSmem, bool kSimple>
-__global__ void __launch_bounds__(256, 2) contact_narrow_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : 2) contact_narrow_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   __shared__ int hitlist[256 * kNarrowTiles];
@@ -1005,12 +1021,81 @@ __global__ void __launch_bounds__(kThreads, 4) contact_index_kernel(LaunchArgs a
   }
 }
 
+// The same numbering for scenes with hundreds of items per state (22 humanoids: 1,210 items, 322
+// contacts): ONE WARP per state, 32 items at a time -- item records are read coalesced, contact
+// indices and row addresses come from warp prefix sums over the items' contact and row counts
+// instead of a 1,210-step walk by a single thread (3.2 ms per 2^15 scene states, 4 % issue-active).
+// The state's slots are its own contiguous range; contact_rows_kernel<.., true> walks it per state.
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) contact_index_wide_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  if (*(volatile int*)&a.cq->overflow | *(volatile int*)&a.cq->overflow_contacts) return;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = kThreads / 32;
+  for (long long s0 = (long long)blockIdx.x * W; s0 < a.chunk_n; s0 += (long long)gridDim.x * W) {
+    const long long s = s0 + warp;
+    if (s >= a.chunk_n) continue;                          // warp-uniform
+    bind_state(c, a, s);
+    const int nsurv = c.isc[MJB_ISC_NSURV * MJB_LS];
+    const int ibase = c.isc[MJB_ISC_ITEMBASE * MJB_LS];
+    int mine = 0;
+    for (int j0 = 0; j0 < nsurv; j0 += 32) {
+      const int j = j0 + lane;
+      if (j < nsurv) mine += a.item_con[ibase + j].count;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    int sbase = 0;
+    if (lane == 0 && mine) sbase = atomicAdd(&a.cq->nslots, mine);
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    __syncwarp();                                          // every lane has read the item range
+    if (lane == 0) {
+      c.isc[MJB_ISC_ITEMBASE * MJB_LS] = sbase;            // from here on: first slot of the state ...
+      c.isc[MJB_ISC_NSURV * MJB_LS] = mine;                // ... and its number of contacts
+    }
+    if (!mine) continue;
+    load_counters(c);
+    const int ncon0 = c.ncon;
+    int ncon = c.ncon, nefc = c.nefc;
+    for (int j0 = 0; j0 < nsurv; j0 += 32) {
+      const int j = j0 + lane;
+      ItemCon ic = {0, 0};
+      if (j < nsurv) ic = a.item_con[ibase + j];
+      int rsum = 0;
+      for (int q = 0; q < ic.count; q++) {
+        const ContactRec& r = a.contacts[ic.base + q];
+        int exclude;
+        rsum += contact_row_count(c, r.ci, r.dist, &exclude);
+      }
+      const int kincl = warp_incl_scan(ic.count, lane), rincl = warp_incl_scan(rsum, lane);
+      int k = ncon + kincl - ic.count, row = nefc + rincl - rsum;
+      for (int q = 0; q < ic.count; q++) {
+        ContactRec& r = a.contacts[ic.base + q];
+        int exclude;
+        const int rows = contact_row_count(c, r.ci, r.dist, &exclude);
+        r.k = k;
+        r.efc_address = rows ? row : -1 - exclude;       // < 0: no rows; exclude flag = -1 - value
+        a.slot_rec[sbase + (k - ncon0)] = ic.base + q;
+        k++; row += rows;
+      }
+      ncon += __shfl_sync(0xffffffffu, kincl, 31);
+      nefc += __shfl_sync(0xffffffffu, rincl, 31);
+    }
+    c.ncon = ncon; c.nefc = nefc;
+    if (lane == 0) save_counters(c);
+  }
+}
+
 // One warp per 32 consecutive states: their contacts occupy one contiguous, (state, k)-ordered slot
 // range (contact_index_kernel), which the warp processes 32 slots at a time. J'f is applied to the
 // owner state's body accumulators right here; records of one round that hit the same (state, body)
 // are found with __match_any_sync and applied one after the other in slot order, so the sums are
 // conflict-free and bitwise deterministic. No other warp touches these states.
-template <bool kModelInSmem>
+// kWarpPerState: the slots were numbered by contact_index_wide_kernel, one warp walks ONE state.
+template <bool kModelInSmem, bool kWarpPerState>
 __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
@@ -1020,17 +1105,26 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int* cand_int = c.I + c.H->ioff[MJB_I_cand_int];
   const int* body_static = c.I + c.H->ioff[MJB_I_body_static];
-  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < a.chunk_n; i0 += (long long)gridDim.x * kThreads) {
-    const long long w0 = i0 + warp * 32;                  // first state of this warp
-    const long long i = w0 + lane;
-    const bool valid = i < a.chunk_n;
-    const int* isc = a.iscratch + (((valid ? i : 0) >> 5) * a.niscratch << 5) + ((valid ? i : 0) & 31);
-    const int mine = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
-    const int sbase = valid ? isc[MJB_ISC_ITEMBASE * MJB_LS] : 0;
-    const int incl = warp_incl_scan(mine, lane);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const long long per_cta = kWarpPerState ? kThreads / 32 : kThreads;      // states per CTA and pass
+  for (long long i0 = (long long)blockIdx.x * per_cta; i0 < a.chunk_n; i0 += (long long)gridDim.x * per_cta) {
+    const long long w0 = kWarpPerState ? i0 + warp : i0 + warp * 32;      // first (only) state of this warp
+    int total, slot0;
+    if (kWarpPerState) {
+      if (w0 >= a.chunk_n) continue;                      // warp-uniform
+      const int* isc = a.iscratch + ((w0 >> 5) * a.niscratch << 5) + (w0 & 31);
+      total = isc[MJB_ISC_NSURV * MJB_LS];
+      slot0 = isc[MJB_ISC_ITEMBASE * MJB_LS];
+    } else {
+      const long long i = w0 + lane;
+      const bool valid = i < a.chunk_n;
+      const int* isc = a.iscratch + (((valid ? i : 0) >> 5) * a.niscratch << 5) + ((valid ? i : 0) & 31);
+      const int mine = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
+      const int sbase = valid ? isc[MJB_ISC_ITEMBASE * MJB_LS] : 0;
+      const int incl = warp_incl_scan(mine, lane);
+      total = __shfl_sync(0xffffffffu, incl, 31);
+      slot0 = __shfl_sync(0xffffffffu, sbase, 0);         // lane 0's base = first slot of the warp
+    }
     if (!total) continue;
-    const int slot0 = __shfl_sync(0xffffffffu, sbase, 0);  // lane 0's base = first slot of the warp
     int wstatus = 0;
     for (int r0 = 0; r0 < total; r0 += 32) {
       const bool has = r0 + lane < total;
@@ -1179,8 +1273,10 @@ size_t smooth_smem_bytes(int model_bytes, int model_in_smem) {
 
 template <typename K>
 static cudaError_t launch_phase(K kernel, const LaunchArgs& args, size_t smem, int ctas_per_sm,
-                                cudaStream_t stream, int threads = kThreads, int resident = 0) {
-  int grid = (args.chunk_n + threads - 1) / threads;
+                                cudaStream_t stream, int threads = kThreads, int resident = 0,
+                                int states_per_cta = 0) {
+  const int per = states_per_cta > 0 ? states_per_cta : threads;
+  int grid = (int)(((long long)args.chunk_n + per - 1) / per);
   const int cap = kSMs * ctas_per_sm;
   if (grid > cap) grid = cap;
   if (smem > 48 * 1024) {
@@ -1364,29 +1460,33 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
 #endif
     if (args.cq) {
       { PhaseScope ps(timer, stream, kPhaseContact);
-        if (args.scan_wide <= 0) {
-          int grid = (args.chunk_n + 255) / 256;
-          if (grid > kSMs * 8) grid = kSMs * 8;
-          contact_items_kernel<<<grid, 256, 0, stream>>>(args);
-          e = cudaGetLastError();
-          if (e != cudaSuccess) return e;
-          ++*launches;
-        }
         // the narrow / rows kernels walk lists whose length is only known on the device: full grids
         if (args.simple_pairs) {
-          e = in_smem ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 4, stream, 256)
-                      : launch_phase(contact_narrow_kernel<false, true>, args, 0, 4, stream, 256);
+          e = in_smem ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256)
+                      : launch_phase(contact_narrow_kernel<false, true>, args, 0, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256);
         } else {
           e = in_smem ? launch_phase(contact_narrow_kernel<true, false>, args, smem, 4, stream, 256)
                       : launch_phase(contact_narrow_kernel<false, false>, args, 0, 4, stream, 256);
         }
         if (e != cudaSuccess) return e;
-        e = in_smem ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
-                    : launch_phase(contact_index_kernel<false>, args, 0, 8, stream);
-        if (e != cudaSuccess) return e;
-        e = in_smem ? launch_phase(contact_rows_kernel<true>, args, smem, 8, stream)
-                    : launch_phase(contact_rows_kernel<false>, args, 0, 8, stream);
-        if (e != cudaSuccess) return e;
+        if (args.scan_wide > 0) {
+          // scenes with hundreds of items per state: one warp per state (full grids: the work per
+          // state is only known on the device)
+          const int spc = kThreads / 32;
+          e = in_smem ? launch_phase(contact_index_wide_kernel<true>, args, smem, 8, stream, kThreads, 0, spc)
+                      : launch_phase(contact_index_wide_kernel<false>, args, 0, 8, stream, kThreads, 0, spc);
+          if (e != cudaSuccess) return e;
+          e = in_smem ? launch_phase(contact_rows_kernel<true, true>, args, smem, 8, stream, kThreads, 0, spc)
+                      : launch_phase(contact_rows_kernel<false, true>, args, 0, 8, stream, kThreads, 0, spc);
+          if (e != cudaSuccess) return e;
+        } else {
+          e = in_smem ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
+                      : launch_phase(contact_index_kernel<false>, args, 0, 8, stream);
+          if (e != cudaSuccess) return e;
+          e = in_smem ? launch_phase(contact_rows_kernel<true, false>, args, smem, 8, stream)
+                      : launch_phase(contact_rows_kernel<false, false>, args, 0, 8, stream);
+          if (e != cudaSuccess) return e;
+        }
       }
       *launches += 3;
     }

@@ -23,7 +23,7 @@ constexpr int kListCap = MJB_LISTCAP;                  // per-lane survivor list
 // items through MJB_ISC_ITEMBASE / NSURV and an item its contacts through ItemCon, so placement
 // order does not matter. If a list would overflow, `overflow` is raised and the chunk is handled
 // by the pooled contact kernel instead (every kernel of either path checks the flag first).
-// `overflow` is raised only by contact_items_kernel (item list full) and `overflow_contacts` only by
+// `overflow` is raised only by the scan kernels (item list full) and `overflow_contacts` only by
 // contact_narrow_kernel (contact list full), so the flag a kernel tests on entry cannot change while
 // that kernel runs: every thread of every CTA takes the same decision.
 struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; int overflow_contacts; };
@@ -70,6 +70,43 @@ struct LaunchArgs {
   int scan_ngeom;               // mjbHdr::ngeom (sizes the wide scan's shared memory)
   Outputs out;
 };
+
+#if defined(__CUDACC__)
+// Tail of the candidate scan (thread per state): the warp appends the bounding-sphere survivors of its
+// 32 states to the chunk's global item list with ONE atomicAdd; every state gets a contiguous range
+// in candidate order (MJB_ISC_ITEMBASE, -1 if the list is full). All 32 lanes must call it.
+__device__ __forceinline__ void scan_append_items(const LaunchArgs& a, int* isc, bool valid, long long local_state,
+                                                  int nwords) {
+  const int lane = threadIdx.x & 31;
+  const int nsurv = valid ? isc[MJB_ISC_NSURV * MJB_LS] : 0;
+  int incl = nsurv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 0 && total) base = atomicAdd(&a.cq->nitems, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const bool fits = base + total <= a.items_cap;
+  if (!fits && lane == 0) a.cq->overflow = 1;
+  const int mybase = fits ? base + incl - nsurv : -1;
+  if (valid) isc[MJB_ISC_ITEMBASE * MJB_LS] = mybase;
+  if (valid && fits && nsurv) {
+    int k = 0;
+    for (int w = 0; w < nwords; w++) {
+      unsigned bits = (unsigned)isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
+      while (bits) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        a.items[mybase + k] = ContactItem{(int)local_state, (w << 5) + b};
+        k++;
+      }
+    }
+  }
+}
+#endif
 
 }  // namespace mjb
 

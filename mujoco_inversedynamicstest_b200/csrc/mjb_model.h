@@ -269,9 +269,10 @@ enum {
   MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
   MJB_SC_weld_dt,      // neq*3     weld rows: (raw rotational efc_force) - (torque J'f), for the cfrc_ext output (only models with welds)
   MJB_SC_tree_sphere,  // ntree*4   bounding sphere of every kinematic tree (tree-level broadphase; only with scan runs)
-  MJB_SC_crec,         // nbody*16  contact carrier RECORDS (only with candidate pairs): 16 doubles [cvel 6 | cacc_lin 6 |
-                       //           tree origin 3 | 0] per (body, state) as four 32-byte parts, part q of lane l at
-                       //           ((16*b + 4*q)*32 + 4*l): coalesced 256-bit stores, whole-sector gathers (mjb_pipeline.h)
+  MJB_SC_crec,         // nbody*16  contact carrier RECORDS (only with candidate pairs): unlike every other array this
+                       //           one is state-major inside the warp block -- body b, lane l at (16*b*32 + 16*l) --
+                       //           so that the 16 doubles [cvel 6 | cacc_lin 6 | tree origin 3 | 0] a contact row
+                       //           gathers for one (state, body) are ONE 128-byte line instead of 15 sectors
   MJB_SC_COUNT
 };
 

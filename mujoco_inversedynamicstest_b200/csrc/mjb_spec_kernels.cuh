@@ -129,9 +129,13 @@ MJBS_TREE_STAGES(MJBS_DEFINE_TREE)
 extern "C" __global__ void __launch_bounds__(mjb::kThreads, MJBS_SCAN_CTAS) mjbs_contact_scan(mjb::LaunchArgs a) {
   mjb::Ctx c;
   mjb::spec_ctx(c, a);
-  MJBS_STATE_LOOP(i) {
-    mjb::spec_bind(c, a, i);
-    mjb::contact_scan(c);
+  const int nwords = (c.H->ncand + 31) >> 5;
+  for (long long i0 = (long long)blockIdx.x * mjb::kThreads; i0 < a.chunk_n; i0 += (long long)gridDim.x * mjb::kThreads) {
+    const long long i = i0 + threadIdx.x;
+    const bool valid = i < a.chunk_n;
+    mjb::spec_bind(c, a, valid ? i : 0);
+    if (valid) mjb::contact_scan(c);
+    if (a.cq) mjb::scan_append_items(a, c.isc, valid, i, nwords);   // item-parallel path: survivors -> item list
   }
 }
 

@@ -101,6 +101,8 @@ def make_case(name):
 # name -> (reference xml, nstate, z_range, nconmax, njmax)
 REDUCED_CASES = {
     "humanoids22_256": ("model/humanoid/22_humanoids.xml", 256, (0.0, 1.5), 704, 1408),
+    # 100 humanoids: nv = 2700, 1901 geoms, 1.8 M candidate pairs, ~4,400 contacts per state
+    "humanoids100_4": ("model/humanoid/100_humanoids.xml", 4, (0.0, 1.5), 5632, 7168),
 }
 
 

@@ -101,16 +101,30 @@ def test_subwarp_inertia_kernel(name, monkeypatch):
     memory; MJB_INERTIA=subwarp selects it for A/B runs) against the reference's qM / qLD / qLDiagInv,
     and against the thread-per-state kernel's."""
     import mujoco_inversedynamicstest_b200 as mjb
-    monkeypatch.setenv("MJB_INERTIA", "thread")
-    _, bd, ref, _, _ = _run(mjb, name, True, mjb.OUT_INERTIA)
-    thread = {f: bd.get(f) for f in (mjb.F_QM, mjb.F_QLD, mjb.F_QLDIAGINV)}
-    bd.close()
-    monkeypatch.setenv("MJB_INERTIA", "subwarp")
-    _, bd, ref, _, _ = _run(mjb, name, True, mjb.OUT_INERTIA)
-    for f, k in ((mjb.F_QM, "qM"), (mjb.F_QLD, "qLD"), (mjb.F_QLDIAGINV, "qLDiagInv")):
-        got = bd.get(f)
-        np.testing.assert_allclose(got, ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
-        np.testing.assert_allclose(got, thread[f], rtol=1e-10, atol=1e-13, err_msg=k + " vs thread-per-state")
+    import edge_cases
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    n = int(ref["nstate"])
+    if name.startswith("ref_"):
+        qpos, qvel, qacc = edge_cases.states(model, ref)
+    else:
+        qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+    got = {}
+    for mode in ("thread", "subwarp"):
+        monkeypatch.setenv("MJB_INERTIA", mode)
+        bd = mjb.BatchData(model, n, outmask=mjb.OUT_INERTIA)
+        bd.set_state(qpos, qvel, qacc)
+        bd.inverse()
+        got[mode] = {k: bd.get(f) for f, k in ((mjb.F_QM, "qM"), (mjb.F_QLD, "qLD"), (mjb.F_QLDIAGINV, "qLDiagInv"))}
+        bd.close()
+    for k in ("qM", "qLD", "qLDiagInv"):
+        # entries that cancel to ~0 (off-diagonal terms of symmetric bodies) carry the rounding of the
+        # entries they are made of: absolute term relative to the largest entry of the array
+        atol = 1e-12 + 1e-10 * float(np.abs(ref[k]).max())
+        np.testing.assert_allclose(got["subwarp"][k], ref[k], rtol=1e-9, atol=atol, err_msg=k)
+        np.testing.assert_allclose(got["subwarp"][k], got["thread"][k], rtol=1e-9, atol=atol,
+                                   err_msg=k + " vs thread-per-state")
 
 
 @pytest.mark.parametrize("name", util.POST_CASES)
@@ -568,6 +582,28 @@ def test_multi_tree_scene_runs_on_the_item_parallel_path():
     efc = bd.efc()
     for k in ("type", "id", "state"):
         np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
+
+
+def test_hundred_humanoids_scene():
+    """model/humanoid/100_humanoids.xml of the reference (nv = 2700, 1901 geoms, 1.8 M candidate pairs,
+    ~4,300 contacts per state): counters, contact lists and efc ordering bit-exact against the
+    reference's dump, qfrc_inverse element-wise within 1e-9 * |ref| + 1e-12."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "humanoids100_4", True, mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC)
+    assert nbad == 0
+    cnt = bd.counts()
+    for k in ("ncon", "ne", "nf", "nl", "nefc"):
+        np.testing.assert_array_equal(cnt[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
+    efc = bd.efc()
+    for k in ("type", "id", "state"):
+        np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
+    # forces of 1e7 summed over thousands of contacts: the same documented allowance as humanoids22_256
+    nviol, worst = util.qfrc_violations(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    max_viol, max_ratio = util.STRICT_EXCEPTIONS["humanoids22_256"]
+    assert nviol <= max_viol and worst <= max_ratio, (nviol, worst)
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
 
 
 @pytest.mark.parametrize("name", ["humanoid_fd", "zoo_fd", "humanoid_nocontact_fd"])
