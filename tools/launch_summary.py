@@ -1,5 +1,7 @@
-"""Summarise an `ncu --csv` launch list (metrics gpu__time_duration.sum, dram__bytes_*.sum, ...)
-per kernel over the LAST bench step: python tools/launch_summary.py gpurun_out/launches.csv [nlast]"""
+"""Summarise an `ncu --csv` launch list (metrics gpu__time_duration.sum, dram__bytes_*.sum, ...) per kernel:
+    python tools/launch_summary.py gpurun_out/launches.csv [nlast [nstates [peak_tflops [peak_gbs]]]]
+nlast: use only the last `nlast` launches of the list (default: all); nstates: states every launch
+processes (default 2^20). Every figure is the AVERAGE PER LAUNCH of that kernel (n = launches seen)."""
 import csv
 import sys
 from collections import OrderedDict
@@ -13,8 +15,9 @@ def main():
     for r in rows[1:]:
         d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(",", ""))
     items = list(d.items())
-    nlast = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    items = items[-nlast:]
+    nlast = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    if nlast > 0:
+        items = items[-nlast:]
     tot = OrderedDict()
     for (_, k), m in items:
         k = k.split("(")[0].replace("void ", "")
@@ -33,16 +36,19 @@ def main():
         t["wr"] += m.get("dram__bytes_write.sum", 0) * 1e-9
         t["regs"] = int(m.get("launch__registers_per_thread", 0))
         t["issue"] += m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0)
+    for t in tot.values():          # per-launch averages
+        for key in ("ms", "rd", "wr", "fl", "inst"):
+            t[key] /= t["n"]
     total = sum(t["ms"] for t in tot.values())
     for k, t in tot.items():
         print(f"{k:28s} n={t['n']} {t['ms']:7.3f} ms ({100*t['ms']/total:4.1f}%)  dram rd {t['rd']:6.2f} wr {t['wr']:6.2f} GB"
               f"  regs {t['regs']:3d}  issue {t['issue']/t['n']:5.1f}%")
-    print(f"{'total':28s}     {total:7.3f} ms")
+    print(f"{'one launch of each':28s}     {total:7.3f} ms")
     if any(t["fl"] for t in tot.values()):
         nst = float(sys.argv[3]) if len(sys.argv) > 3 else 1048576.0
         peak_tf = float(sys.argv[4]) if len(sys.argv) > 4 else 36.6
         peak_gbs = float(sys.argv[5]) if len(sys.argv) > 5 else 6541.8
-        print(f"\nper kernel over one step of {int(nst):,} states (DFMA probe {peak_tf} TFLOP/s, HBM copy peak {peak_gbs} GB/s):")
+        print(f"\nper kernel and launch, {int(nst):,} states per launch (DFMA probe {peak_tf} TFLOP/s, HBM copy peak {peak_gbs} GB/s):")
         F = B = 0.0
         for k, t in tot.items():
             by = (t["rd"] + t["wr"]) * 1e9

@@ -19,22 +19,30 @@ def main():
     d = OrderedDict()
     for r in rows[1:]:
         d.setdefault((int(r[ii]), r[ki]), {})[r[mi]] = float(r[vi].replace(",", ""))
-    # the last bench step: every kernel between the last two smooth_kernel launches' first chunk
-    items = list(d.items())
-    last = [i for i, ((_, k), _) in enumerate(items) if "backward" in k]
-    step = items[last[-3] + 1:last[-1] + 1] if len(last) >= 3 else items[-10:]
-    K = {}
-    for (_, k), m in step:
-        name = k.split("(")[0].replace("void ", "").split("<")[0].replace("_kernel", "")
-        # the contact phase = items + narrow + index + rows (+ the pooled fallback kernel)
-        if name.startswith("contact") and name != "contact_scan":
-            name = "contact"
-        e = K.setdefault(name, {"flops": 0.0, "dram_bytes": 0.0, "warp_inst": 0.0})
+    # every distinct kernel launches once per step (one chunk): per step and group, the sum over the
+    # group's kernels of their per-launch averages over the captured launches
+    per = OrderedDict()
+    for (_, k), m in d.items():
+        e = per.setdefault(k, {"n": 0, "flops": 0.0, "dram_bytes": 0.0, "warp_inst": 0.0})
+        e["n"] += 1
         e["flops"] += (m["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] +
                        m["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] +
                        2 * m["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]) / nst
         e["dram_bytes"] += (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) / nst
         e["warp_inst"] += m.get("smsp__inst_executed.sum", 0.0) / nst
+    K = {}
+    for k, pe in per.items():
+        name = k.split("(")[0].replace("void ", "").split("<")[0].replace("_kernel", "").replace("mjb::", "")
+        if name.startswith("mjbs_"):          # model-specialised stages: mjbs_smooth_3 -> smooth
+            name = name[5:].rstrip("0123456789").rstrip("_")
+        if "soa" in name or "aos" in name or "probe" in name or "count_nonzero" in name:
+            continue                           # boundary transposes / probes are not part of the step
+        # the contact phase = narrow + index + rows (+ the pooled fallback kernel)
+        if name.startswith("contact") and name != "contact_scan":
+            name = "contact"
+        e = K.setdefault(name, {"flops": 0.0, "dram_bytes": 0.0, "warp_inst": 0.0})
+        for key in e:
+            e[key] += pe[key] / pe["n"]
     for e in K.values():
         for k in e:
             e[k] = round(e[k], 1)
