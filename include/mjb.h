@@ -80,6 +80,8 @@ typedef enum mjbField_ {
   mjbF_CFRC_EXT,          /* double nbody*6: [torque, force] of contacts and connect/weld rows (RNEPOST) */
   mjbF_SENSORDATA,        /* double nsensordata: d->sensordata (models with sensors, no mask bit needed) */
   mjbF_QFRC_BIAS,         /* double nv: mj_rne without accelerations, engine_forward.c:228 (QFRC) */
+  mjbF_ENERGY,            /* double 2: d->energy = potential, kinetic (mj_energyPos / mj_energyVel, engine_sensor.c:920,
+                             1011); produced, without a mask bit, for models with mjENBL_ENERGY -- engine_inverse.c:210-223 */
   mjbF_COUNT
 } mjbField;
 
@@ -131,6 +133,15 @@ MJB_API int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipst
  * generated and differenced on the device. Synchronous. */
 MJB_API int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq,
                           mjtNum* DfDv, mjtNum* DfDa, mjtNum* DmDq);
+/* The same with the sensor Jacobians of mjd_inverseFD (engine_derivative_fd.c:611-730): DsDq, DsDv,
+ * DsDa, each nbatch x nv x nsensordata (row i = derivative of sensordata with respect to coordinate
+ * i), any of them may be NULL; the force / mass Jacobians as in mjb_inverseFD. flg_actuation must be
+ * 0: the inverse path evaluates no actuation (the reference subtracts qfrc_actuator when it is set).
+ * With all three sensor outputs NULL the perturbed evaluations skip the sensors, as the reference
+ * does (skipsensor, :629). */
+MJB_API int mjb_inverseFDSensor(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, int flg_actuation,
+                                mjtNum* DfDq, mjtNum* DfDv, mjtNum* DfDa,
+                                mjtNum* DsDq, mjtNum* DsDv, mjtNum* DsDa, mjtNum* DmDq);
 /* mj_compareFwdInv over the batch (include/mujoco/mujoco.h mj_compareFwdInv, src/engine/
  * engine_inverse.c:275-316): how well the inverse dynamics reproduce what a forward pass applied.
  * The states last given to mjb_setState / mjb_setStateDevice carry the forward pass's qacc. HOST

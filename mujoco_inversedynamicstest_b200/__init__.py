@@ -8,7 +8,7 @@ from .batch import (BatchData, MjbError, Model, fp64_peak_tflops, OUT_QFRC, OUT_
                     OUT_EFC, OUT_INERTIA, OUT_INTERNAL, OUT_RNEPOST, F_QFRC_INVERSE, F_QFRC_CONSTRAINT,
                     F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_CONTACT_NUM,
                     F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL, F_CACC, F_CFRC_INT,
-                    F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS, STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC,
+                    F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS, F_ENERGY, STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC,
                     STATUS_CONTACTFULL, STATUS_CNSTRFULL)
 from .states import SEED, generate_states
 

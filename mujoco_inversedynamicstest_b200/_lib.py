@@ -28,6 +28,7 @@ SIGNATURES = {
     "mjb_inverse": (c_int, [c_void_p, c_void_p, c_int]),
     "mjb_inverseAsync": (c_int, [c_void_p, c_void_p, c_int]),
     "mjb_inverseFD": (c_int, [c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mjb_inverseFDSensor": (c_int, [c_void_p, c_void_p, c_int, c_double, c_int] + [c_void_p] * 7),
     "mjb_compareFwdInv": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mjb_inverseSkip": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int]),
     "mjb_inverseHost": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -22,7 +22,7 @@ STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTR
 
 (F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
  F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL,
- F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS) = range(19)
+ F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS, F_ENERGY) = range(20)
 
 _INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
 _CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
@@ -199,6 +199,18 @@ class BatchData:
                                         dm.ctypes.data if mass else None), "mjb_inverseFD")
         return (dq, dv, da, dm) if mass else (dq, dv, da)
 
+    def inverse_fd_sensor(self, eps=1e-6, nbatch=None):
+        """mjd_inverseFD with its sensor Jacobians (mjb_inverseFDSensor): (DfDq, DfDv, DfDa, DsDq, DsDv,
+        DsDa), the last three [n, nv, nsensordata]."""
+        n = self.nbatch if nbatch is None else int(nbatch)
+        nv, ns = self.model.int("nv"), self.model.int("nsensordata")
+        df = [np.zeros((n, nv, nv)) for _ in range(3)]
+        ds = [np.zeros((n, nv, ns)) for _ in range(3)]
+        self._check(lib().mjb_inverseFDSensor(self.model.ptr, self._d, n, float(eps), 0,
+                                              *(a.ctypes.data for a in df), *(a.ctypes.data for a in ds), None),
+                    "mjb_inverseFDSensor")
+        return tuple(df + ds)
+
     def compare_fwdinv(self, qfrc_constraint, qfrc_applied=None, qfrc_actuator=None, xfrc_applied=None,
                        nbatch=None):
         """mj_compareFwdInv over the batch: [nbatch, 2] = solver_fwdinv of every state
@@ -337,6 +349,10 @@ class BatchData:
     def sensordata(self):
         """d->sensordata [nbatch, nsensordata] (mj_sensorPos / Vel / Acc; models with sensors)."""
         return self.get(F_SENSORDATA)
+
+    def energy(self):
+        """d->energy (potential, kinetic) per state, for models with mjENBL_ENERGY."""
+        return self.get(F_ENERGY)
 
     def internal(self, name):
         off, size = ctypes.c_int(), ctypes.c_int()

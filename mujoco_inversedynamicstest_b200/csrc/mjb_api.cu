@@ -369,6 +369,11 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     setField(d, mjbF_CFRC_INT, o.cfrc_int, 6 * H.nbody, 0);
     setField(d, mjbF_CFRC_EXT, o.cfrc_ext, 6 * H.nbody, 0);
   }
+  if (H.enableflags & MJB_ENBL_ENERGY) {
+    // d->energy is part of mj_inverse's output contract when mjENBL_ENERGY is set (engine_inverse.c:210-223)
+    ok = ok && devAlloc(d, &o.energy, (size_t)2 * S, "cudaMalloc(energy)");
+    setField(d, mjbF_ENERGY, o.energy, 2, 0);
+  }
   if (H.nsensordata > 0) {
     // sensordata is part of mj_inverse's output contract (engine_inverse.c:206-246): always produced
     ok = ok && devAlloc(d, &o.sensordata, (size_t)H.nsensordata * S, "cudaMalloc(sensordata)");
@@ -498,7 +503,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(o.counts); cudaFree(o.status); cudaFree(o.contact_geom); cudaFree(o.contact_info);
   cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
   cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
-  cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext); cudaFree(o.sensordata);
+  cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext); cudaFree(o.sensordata); cudaFree(o.energy);
   cudaFree(o.qfrc_bias);
   delete d;
 }
@@ -850,6 +855,13 @@ int mjb_inverseSkip(const mjModel* m, mjbData* d, int nbatch, int skipstage, int
 // generated on the device and evaluated as one large batch by the same phase kernels.
 int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* DfDq, mjtNum* DfDv,
                   mjtNum* DfDa, mjtNum* DmDq) {
+  return mjb_inverseFDSensor(m, d, nbatch, eps, 0, DfDq, DfDv, DfDa, nullptr, nullptr, nullptr, DmDq);
+}
+
+int mjb_inverseFDSensor(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, int flg_actuation,
+                        mjtNum* DfDq, mjtNum* DfDv, mjtNum* DfDa,
+                        mjtNum* DsDq, mjtNum* DsDv, mjtNum* DsDa, mjtNum* DmDq) {
+  if (flg_actuation) { d->error = "mjb_inverseFD: flg_actuation is not supported (no actuation on the inverse path)"; return -1; }
   if (!d->shards.empty()) { d->error = "mjb_inverseFD: not available on a multi-device mjbData"; return -1; }
   if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_inverseFD: nbatch out of range"; return -1; }
   if (!(eps > 0)) { d->error = "mjb_inverseFD: eps must be positive"; return -1; }
@@ -863,9 +875,14 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
   }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
   const mjbHdr& H = d->hdr;
-  const int nv = H.nv, nM = H.nM, nvar = 1 + 3*nv;
+  const int nv = H.nv, nM = H.nM, nvar = 1 + 3*nv, ns = H.nsensordata;
   if (nbatch == 0 || nv == 0) return 0;
   const bool want_mass = DmDq != nullptr;
+  const bool want_sensors = (DsDq || DsDv || DsDa) && ns > 0;
+  if (want_sensors && !d->out.sensordata) {
+    d->error = "mjb_inverseFD: sensor Jacobians requested but the batch evaluates no sensors (mjDSBL_SENSOR)";
+    return -1;
+  }
   int tile = (1 << 20) / nvar;
   if (tile < 1) tile = 1;
   if (tile > nbatch) tile = nbatch;
@@ -878,8 +895,11 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
   }
   mjbData* x = d->fd;
   x->stream = d->stream;
-  x->skip_sensors = 1;            // mjd_inverseFD's sensor Jacobians are not produced
-  const size_t need = (size_t)tile * nv * (size_t)(want_mass ? (nv > nM ? nv : nM) : nv);
+  x->skip_sensors = want_sensors ? 0 : 1;      // skipsensor = !DsDq && !DsDv && !DsDa (engine_derivative_fd.c:629)
+  size_t widest = (size_t)nv;
+  if (want_mass && (size_t)nM > widest) widest = (size_t)nM;
+  if (want_sensors && (size_t)ns > widest) widest = (size_t)ns;
+  const size_t need = (size_t)tile * nv * widest;
   if (need > d->fd_out_doubles) {
     cudaFree(d->d_fd_out);
     d->d_fd_out = nullptr; d->fd_out_doubles = 0;
@@ -895,8 +915,11 @@ int mjb_inverseFD(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, mjtNum* 
     x->in_qpos = x->d_qpos; x->in_qvel = x->d_qvel; x->in_qacc = x->d_qacc; x->in_stride = x->stride;
     if (ok && mjb_inverseAsync(m, x, n * nvar)) { d->error = "mjb_inverseFD: " + x->error; return -1; }
     struct Job { mjtNum* host; const double* field; int v0; int ncol; };
-    const Job jobs[4] = {{DfDa, x->out.qfrc_inverse, 1, nv}, {DfDv, x->out.qfrc_inverse, 1 + nv, nv},
-                         {DfDq, x->out.qfrc_inverse, 1 + 2*nv, nv}, {DmDq, x->out.qM, 1 + 2*nv, nM}};
+    const Job jobs[7] = {{DfDa, x->out.qfrc_inverse, 1, nv}, {DfDv, x->out.qfrc_inverse, 1 + nv, nv},
+                         {DfDq, x->out.qfrc_inverse, 1 + 2*nv, nv}, {DmDq, x->out.qM, 1 + 2*nv, nM},
+                         {want_sensors ? DsDa : nullptr, x->out.sensordata, 1, ns},
+                         {want_sensors ? DsDv : nullptr, x->out.sensordata, 1 + nv, ns},
+                         {want_sensors ? DsDq : nullptr, x->out.sensordata, 1 + 2*nv, ns}};
     for (const Job& j : jobs) {
       if (!j.host) continue;
       ok = ok && check(d, mjb::launch_fd_diff(j.field, x->stride, n, nvar, j.v0, nv, j.ncol, eps,

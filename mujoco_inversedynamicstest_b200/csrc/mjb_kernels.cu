@@ -418,13 +418,11 @@ __global__ void __launch_bounds__(kThreads, 4) contact_scan_kernel(LaunchArgs a)
 // the survivor mask word of those 32 candidates for the pooled fallback, which applies the exact
 // tests itself; stage 2 clears the bits of the candidates it rejects.
 constexpr int kWideTile = 2048;     // candidate rows per shared-memory tile
-constexpr int kWidePlanes = 8;      // plane geoms whose normals are staged for the float filter
 constexpr int kWideCtas = 2;        // resident CTAs per SM
 
 size_t scan_wide_smem_bytes(int ngeom, int states_per_cta) {
   const size_t gp = (size_t)((ngeom + 3) & ~3);
-  return (size_t)states_per_cta * (3 * gp + 3 * kWidePlanes) * sizeof(float) +
-         (size_t)kWideTile * (sizeof(float) + 2 * sizeof(int)) + gp;
+  return (size_t)states_per_cta * gp * sizeof(float4) + (size_t)kWideTile * (sizeof(float) + 2 * sizeof(int));
 }
 
 // states per CTA (= warps) of the wide scan for this model, 0 if the flat thread-per-state scan is used
@@ -473,28 +471,17 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
   const int* scan_int = I + H->ioff[MJB_I_scan_int];
   const double* scan_bound = D + H->noff[MJB_N_scan_bound];
   const int* geom_store = I + H->ioff[MJB_I_geom_store];
-  const int* geom_type = I + H->ioff[MJB_I_geom_type];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int gp = (ngeom + 3) & ~3;
-  float* gx_all = reinterpret_cast<float*>(smem);                           // [W][3][gp]
-  float* pn_all = gx_all + (size_t)W * 3 * gp;                              // [W][3][kWidePlanes] plane normals
-  float* tile_bound = pn_all + (size_t)W * 3 * kWidePlanes;                 // [kWideTile]
+  float4* gx_all = reinterpret_cast<float4*>(smem);                         // [W][gp]: x, y, z of a geom in one 16-byte word
+  float* tile_bound = reinterpret_cast<float*>(gx_all + (size_t)W * gp);    // [kWideTile]
   int2* tile_int = reinterpret_cast<int2*>(tile_bound + kWideTile);         // [kWideTile]
-  unsigned char* plane_id = reinterpret_cast<unsigned char*>(tile_int + kWideTile);   // [gp]: slot of a plane geom
-  float* gx = gx_all + (size_t)warp * 3 * gp;
-  float* pn = pn_all + (size_t)warp * 3 * kWidePlanes;
+  float4* gx = gx_all + (size_t)warp * gp;
   const int cap = a.scan_buf_cap;
   int* buf = a.scan_buf + ((size_t)blockIdx.x * W + warp) * cap;            // this warp's candidate buffer
   const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_xmat];
   const int mask_row = MJB_ISC_MASK;
-  if (threadIdx.x == 0) {
-    int np = 0;
-    for (int g = 0; g < ngeom; g++) {
-      const bool pl = geom_type[g] == MJB_GEOM_PLANE && np < kWidePlanes;
-      plane_id[g] = pl ? (unsigned char)np : (unsigned char)255;
-      np += pl;
-    }
-  }
+  const unsigned below = (1u << lane) - 1u;
 
   for (long long s0 = (long long)blockIdx.x * W; s0 < a.chunk_n; s0 += (long long)gridDim.x * W) {
     const long long s = s0 + warp;
@@ -502,6 +489,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
     const long long sb = valid ? s : 0;
     const double* sc = a.scratch + ((sb >> 5) * a.nscratch << 5) + (sb & 31);
     int* isc = a.iscratch + ((sb >> 5) * a.niscratch << 5) + (sb & 31);
+    int* maskw = isc + (size_t)mask_row * MJB_LS;
     __syncthreads();                      // the previous round's tiles and positions are consumed
     float slack = 1e-4f;
     if (valid) {
@@ -516,61 +504,56 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
         const float x = stored ? (float)(sc[(off_gxpos + 3 * g) * MJB_LS] - r0) : 0.f;
         const float y = stored ? (float)(sc[(off_gxpos + 3 * g + 1) * MJB_LS] - r1) : 0.f;
         const float z = stored ? (float)(sc[(off_gxpos + 3 * g + 2) * MJB_LS] - r2) : 0.f;
-        gx[g] = x; gx[gp + g] = y; gx[2 * gp + g] = z;
+        gx[g] = make_float4(x, y, z, 0.f);
         m = fmaxf(m, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
-        const int pid = plane_id[g];
-        if (pid < kWidePlanes && stored) {
-#pragma unroll
-          for (int k = 0; k < 3; k++) pn[k * kWidePlanes + pid] = (float)sc[(off_gxmat + 9 * g + 2 + 3 * k) * MJB_LS];
-        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       slack = fmaxf(1e-4f, 8e-6f * m);
       if (!(m < 1e30f)) slack = 3e38f;    // non-finite positions: everything goes to the exact test
     }
-    // stage 1: conservative float filter over all candidates
+    // stage 1: conservative float filter over all candidates. Plane and unfiltered candidates carry an
+    // infinite float bound and the padding of the last tile a NaN (tile staging), so the loop is ONE
+    // comparison per candidate: no branch on the kind, no bounds check. A state with non-finite
+    // positions skips it and takes the exact path below.
     int count = 0;
+    const bool finite = slack < 1e38f;
     for (int t0 = 0; t0 < ncand; t0 += kWideTile) {
       const int nt = ncand - t0 < kWideTile ? ncand - t0 : kWideTile;
+      const int ntp = (nt + 31) & ~31;
       __syncthreads();
-      for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-        tile_bound[i] = __double2float_ru(scan_bound[t0 + i]);
-        tile_int[i] = make_int2(scan_int[2 * (t0 + i)], scan_int[2 * (t0 + i) + 1]);
+      for (int i = threadIdx.x; i < ntp; i += blockDim.x) {
+        if (i < nt) {
+          const int g1k = scan_int[2 * (t0 + i)];
+          tile_bound[i] = ((unsigned)g1k >> 28) ? __int_as_float(0x7f800000) : __double2float_ru(scan_bound[t0 + i]);
+          tile_int[i] = make_int2(g1k & 0xfffffff, scan_int[2 * (t0 + i) + 1]);
+        } else {
+          tile_bound[i] = __int_as_float(0x7fc00000);
+          tile_int[i] = make_int2(0, 0);
+        }
       }
       __syncthreads();
-      if (!valid) continue;
-#pragma unroll 2
-      for (int c0 = 0; c0 < nt; c0 += 32) {
-        const int ci = c0 + lane;
-        bool maybe = false;
-        if (ci < nt) {
-          const int2 gi = tile_int[ci];
-          const int g1 = gi.x & 0xfffffff, g2 = gi.y;
-          const unsigned kind = (unsigned)gi.x >> 28;
-          const float t = tile_bound[ci] + slack;
-          const float dx = gx[g1] - gx[g2], dy = gx[gp + g1] - gx[gp + g2], dz = gx[2 * gp + g1] - gx[2 * gp + g2];
-          if (kind == 0) {
-            maybe = !(dx*dx + dy*dy + dz*dz > t*t);
-          } else {
-            // plane of geom 1 against the centre of geom 2: (pos2 - pos1) . normal > bound drops it
-            const int pid = kind == 1 ? plane_id[g1] : 255;
-            maybe = true;
-            if (pid < kWidePlanes) {
-              const float dist = -(dx * pn[pid] + dy * pn[kWidePlanes + pid] + dz * pn[2 * kWidePlanes + pid]);
-              maybe = !(dist > t);
-            }
-          }
-        }
+      if (!valid || !finite) continue;
+      int* mw = maskw + (size_t)(t0 >> 5) * MJB_LS;
+      const int2* ti = tile_int + lane;
+      const float* tb = tile_bound + lane;
+#pragma unroll 4
+      for (int c0 = 0; c0 < ntp; c0 += 32) {
+        const int2 gi = ti[c0];
+        const float t = tb[c0] + slack;
+        const float4 p1 = gx[gi.x], p2 = gx[gi.y];
+        const float dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+        const bool maybe = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= t * t;
         const unsigned m = __ballot_sync(0xffffffffu, maybe);
-        if (lane == 0) isc[(size_t)(mask_row + ((t0 + c0) >> 5)) * MJB_LS] = (int)m;
+        if (lane == 0) mw[(size_t)(c0 >> 5) * MJB_LS] = (int)m;
         if (maybe) {
-          const int k = count + __popc(m & ((1u << lane) - 1u));
-          if (k < cap) buf[k] = t0 + ci;
+          const int k = count + __popc(m & below);
+          if (k < cap) buf[k] = t0 + c0 + lane;
         }
         count += __popc(m);
       }
     }
+    if (valid && !finite) count = cap + 1;      // everything through the exact path
     if (!valid) continue;
     __syncwarp();
     int total = 0, base = 0;
@@ -1262,6 +1245,20 @@ __global__ void __launch_bounds__(kThreads, 4) sensor_kernel(LaunchArgs a) {
   }
 }
 
+// d->energy of models with mjENBL_ENERGY (mj_energyPos / mj_energyVel)
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) energy_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    energy(c);
+  }
+}
+
 size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
   return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
 }
@@ -1510,6 +1507,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   if (args.out.fwdinv) {
     e = in_smem ? launch_phase(fwdinv_kernel<true>, args, smem, 8, stream)
                 : launch_phase(fwdinv_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  if (args.out.energy) {
+    e = in_smem ? launch_phase(energy_kernel<true>, args, smem, 8, stream)
+                : launch_phase(energy_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }

@@ -127,6 +127,8 @@ struct Outputs {
   // mocap bodies then sit at their model pose, as after mj_resetData
   const double* mocap_pos;            // [nmocap*3][stride]
   const double* mocap_quat;           // [nmocap*4][stride]
+  // d->energy [2][stride] (mj_energyPos, mj_energyVel), only for models with mjENBL_ENERGY; else null
+  double* energy;
 };
 
 struct Ctx {
@@ -1567,7 +1569,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     // read back only by a child that is not b+1 (bit 2), by constraint rows on this body (bit 4:
     // candidate pairs, equality constraints, tendon sites), or by the optional per-body outputs
     if ((tree_flags[b] & (4 | 16)) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.fwdinv ||
-        c.out.cacc || c.out.qfrc_bias) {
+        c.out.cacc || c.out.qfrc_bias || c.out.energy) {
       stc(cvel, 6*b, V, 6);
       stc(cal, 6*b, AL, 6);
     }
@@ -1597,7 +1599,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
       double ci[10], f[6], u1[6], u2[6];
       inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
       if (c.lci) { for (int k = 0; k < 10; k++) c.lci[10*(b - c.lbody0) + k] = ci[k]; }
-      if (!c.lci || c.out.cfrc_int || c.out.qfrc_bias || c.out.sensordata || c.out.scratch_dump) sts(cinert, 10*b, ci, 10);
+      if (!c.lci || c.out.cfrc_int || c.out.qfrc_bias || c.out.sensordata || c.out.scratch_dump || c.out.energy) sts(cinert, 10*b, ci, 10);
       mulInertVec(f, ci, A);
       mulInertVec(u1, ci, V);
       crossForce(u2, V, u1);
@@ -3744,6 +3746,76 @@ MJB_HD inline void sensors(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// mj_energyPos / mj_energyVel (engine_sensor.c:920-1008, 1011-1020) for models with mjENBL_ENERGY,
+// after the sweeps, from the scratch:
+//   energy[0] = -sum_b m_b g.xipos_b + joint springs + tendon springs   (flex models are refused)
+//   energy[1] = 0.5 qvel' M qvel
+// m_b (xipos_b - O) and m_b are cinert[6..9] of the body (about the tree origin O), so the gravity
+// term needs no pose; the kinetic energy is summed per body, 0.5 cvel.(cinert cvel), plus the
+// armature terms -- the same quadratic form as qvel' M qvel (M = sum_b J_b' I_b J_b + armature).
+MJB_HD inline void energy(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* rootid = MI(body_rootid);
+  double e0 = 0;
+  if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+    for (int b = 1; b < H.nbody; b++) {
+      double t[4], o[3];
+      ldn(t, SC(cinert), 10*b + 6, 4); ldn(o, SC(origin), 3*rootid[b], 3);
+      const double mx[3] = {t[0] + t[3]*o[0], t[1] + t[3]*o[1], t[2] + t[3]*o[2]};     // m * xipos
+      e0 -= dot3(H.gravity, mx);
+    }
+  }
+  if (!(H.disableflags & MJB_DSBL_PASSIVE)) {
+    const int* jnt_type = MI(jnt_type); const int* jnt_qposadr = MI(jnt_qposadr);
+    const double* stiff = MD(jnt_stiffness); const double* qs = MD(qpos_spring);
+    for (int j = 0; j < H.njnt; j++) {
+      const double k = stiff[j];
+      int padr = jnt_qposadr[j];
+      const int jt = jnt_type[j];
+      if (jt == MJB_JNT_FREE) {
+        // as the reference has it (:940-944): the first FOUR coordinates normalised as a unit, then the
+        // first three of them against the spring position
+        double q4[4] = {QPOS(padr), QPOS(padr + 1), QPOS(padr + 2), QPOS(padr + 3)};
+        normalize4(q4);
+        const double dif[3] = {q4[0] - qs[padr], q4[1] - qs[padr + 1], q4[2] - qs[padr + 2]};
+        e0 += 0.5*k*dot3(dif, dif);
+        padr += 3;
+      }
+      if (jt == MJB_JNT_FREE || jt == MJB_JNT_BALL) {
+        // mju_subQuat on the quaternion as stored (:953 passes d->qpos, not the normalised copy)
+        const double q4[4] = {QPOS(padr), QPOS(padr + 1), QPOS(padr + 2), QPOS(padr + 3)};
+        double dif[3];
+        subQuat(dif, q4, qs + padr);
+        e0 += 0.5*k*dot3(dif, dif);
+      } else {
+        const double d = QPOS(padr) - qs[padr];
+        e0 += 0.5*k*d*d;
+      }
+    }
+    const double* tstiff = MD(tendon_stiffness); const double* ls = MD(tendon_lengthspring);
+    for (int t = 0; t < H.ntendon; t++) {
+      const double length = AT(SC(ten_length), t);
+      double disp = 0;
+      if (length > ls[2*t + 1]) disp = ls[2*t + 1] - length;
+      else if (length < ls[2*t]) disp = ls[2*t] - length;
+      e0 += 0.5*tstiff[t]*disp*disp;
+    }
+  }
+  double e1 = 0;
+  for (int b = 1; b < H.nbody; b++) {
+    double ci[10], v[6], iv[6];
+    ldn(ci, SC(cinert), 10*b, 10); ldn(v, SC(cvel), 6*b, 6);
+    mulInertVec(iv, ci, v);
+    e1 += dot6(v, iv);
+  }
+  const double* arm = MD(dof_armature);
+  for (int i = 0; i < H.nv; i++) { const double qv = QVEL(i); e1 += arm[i]*qv*qv; }
+  c.out.energy[c.s] = e0;
+  c.out.energy[N + c.s] = 0.5*e1;
+}
+
+// ------------------------------------------------------------------------------------------
 // mj_compareFwdInv (engine_inverse.c:275-316) for one state, after the backward sweep:
 //   fwdinv[0] = | qfrc_constraint(forward) - qfrc_constraint(inverse) |
 //   fwdinv[1] = | qfrc_applied + qfrc_actuator + J'*xfrc_applied - qfrc_inverse |
@@ -4213,6 +4285,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   }
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
   if (c.out.qfrc_bias) bias_forces(c);
+  if (c.out.energy) energy(c);
   if (c.out.sensordata) sensors(c);
   if (c.out.fwdinv) compare_fwdinv(c);
 }

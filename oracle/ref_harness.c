@@ -93,6 +93,8 @@ REFH_API int refh_data_array(const mjModel* m, const mjData* d, const char* name
                              const void** ptr, int* nr, int* nc, int* code) {
   MJDATA_POINTERS_PREAMBLE(m)
   (void)nv;
+  /* d->energy is a member array of mjData (potential, kinetic), not one of the X-macro pointers */
+  if (!strcmp(name, "energy")) { *ptr = d->energy; *nr = 2; *nc = 1; *code = refh_code_mjtNum; return 0; }
 #define X(type, field, r, c) \
   if (!strcmp(name, #field)) { *ptr = d->field; *nr = (int)m->r; *nc = (int)(c); *code = refh_code_##type; return 0; }
   MJDATA_POINTERS
@@ -378,6 +380,23 @@ REFH_API void refh_inverse_fd_batch(const mjModel* m, long long nbatch, const do
     mju_copy(d->qacc, qacc + i*m->nv, m->nv);
     mjd_inverseFD(m, d, eps, 0, DfDq + i*nv*nv, DfDv + i*nv*nv, DfDa + i*nv*nv, NULL, NULL, NULL,
                   DmDq ? DmDq + i*nv*nM : NULL);
+  }
+  mj_deleteData(d);
+}
+
+/* the same with the sensor Jacobians DsDq / DsDv / DsDa, nbatch x nv x nsensordata each */
+REFH_API void refh_inverse_fd_sensor_batch(const mjModel* m, long long nbatch, const double* qpos,
+                                           const double* qvel, const double* qacc, double eps,
+                                           double* DfDq, double* DfDv, double* DfDa,
+                                           double* DsDq, double* DsDv, double* DsDa) {
+  mjData* d = mj_makeData(m);
+  const size_t nv = (size_t)m->nv, ns = (size_t)m->nsensordata;
+  for (long long i = 0; i < nbatch; i++) {
+    mju_copy(d->qpos, qpos + i*m->nq, m->nq);
+    mju_copy(d->qvel, qvel + i*m->nv, m->nv);
+    mju_copy(d->qacc, qacc + i*m->nv, m->nv);
+    mjd_inverseFD(m, d, eps, 0, DfDq + i*nv*nv, DfDv + i*nv*nv, DfDa + i*nv*nv,
+                  DsDq + i*nv*ns, DsDv + i*nv*ns, DsDa + i*nv*ns, NULL);
   }
   mj_deleteData(d);
 }

@@ -175,6 +175,22 @@ class Model:
                                 dm.ctypes.data if mass else None)
         return (dq, dv, da, dm) if mass else (dq, dv, da)
 
+    def inverse_fd_sensor_batch(self, qpos, qvel, qacc, eps=1e-6):
+        """mjd_inverseFD with sensor Jacobians: (DfDq, DfDv, DfDa, DsDq, DsDv, DsDa)."""
+        L = lib()
+        L.refh_inverse_fd_sensor_batch.restype = None
+        L.refh_inverse_fd_sensor_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 3 + \
+            [ctypes.c_double] + [ctypes.c_void_p] * 6
+        qpos = np.ascontiguousarray(qpos, dtype=np.float64)
+        qvel = np.ascontiguousarray(qvel, dtype=np.float64)
+        qacc = np.ascontiguousarray(qacc, dtype=np.float64)
+        n, nv, ns = qpos.shape[0], self.int("nv"), self.int("nsensordata")
+        df = [np.zeros((n, nv, nv)) for _ in range(3)]
+        ds = [np.zeros((n, nv, ns)) for _ in range(3)]
+        L.refh_inverse_fd_sensor_batch(self.ptr, n, qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data, float(eps),
+                                       *(a.ctypes.data for a in df), *(a.ctypes.data for a in ds))
+        return tuple(df + ds)
+
     def fwdinv_batch(self, qpos, qvel, ctrl=None, qfrc_applied=None, xfrc_applied=None, dqacc=None):
         """mj_forward + mj_compareFwdInv per state: dict(qacc, qfrc_actuator, qfrc_constraint [n, nv],
         fwdinv [n, 2]); dqacc shifts qacc away from the forward solution before the comparison."""
@@ -255,6 +271,8 @@ class Model:
             "ten_velocity": ("ntendon", 1), "ten_J": ("ntendon", "nv"),
             "sensordata": ("nsensordata", 1), "cacc": ("nbody", 6), "cfrc_int": ("nbody", 6), "cfrc_ext": ("nbody", 6),
         }
+        if name == "energy":        # member array of mjData: potential, kinetic
+            return 2, 1, np.float64
         if name in known:
             r, c = known[name]
             return self.int(r), (self.int(c) if isinstance(c, str) else c), np.float64

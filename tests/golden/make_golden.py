@@ -56,6 +56,10 @@ CASES = {
     # touch sensors (contact list + contact-row forces + ray / site-volume tests), both cones
     "touch": ("repo:tests/golden/models/touch.xml", {}, 256, (0.0, 0.35), 24, 160),
     "touch_elliptic": ("repo:tests/golden/models/touch.xml", {"cone": 1}, 256, (0.0, 0.35), 24, 160),
+    # mjENBL_ENERGY: d->energy from mj_energyPos / mj_energyVel inside mj_inverse (engine_inverse.c:210-223)
+    "humanoid_energy": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 1}, 128, (0.0, 1.5), 64, 256),
+    "zoo_energy": ("repo:tests/golden/models/zoo.xml", {"enableflags": 1 << 1}, 128, (0.0, 0.6), 32, 128),
+    "tendons_energy": ("repo:tests/golden/models/tendons.xml", {"enableflags": 1 << 1}, 128, (0.3, 1.3), 8, 32),
 }
 
 
@@ -84,6 +88,8 @@ def make_case(name):
               "qLDiagInv": None, "xpos": None, "cvel": None, "cdof": None}
     if m.int("nsensordata") > 0:
         fields["sensordata"] = None
+    if m.get_opt_int("enableflags") & (1 << 1):
+        fields["energy"] = None
     out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields)
     assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax, (
         name, out["ncon"].max(), out["nefc"].max())
@@ -202,7 +208,9 @@ def make_edge_case(name):
 
 # finite-difference Jacobians of the reference (mjd_inverseFD, engine_derivative_fd.c:611) on the
 # first states of a case's stream: name -> (case whose model / state stream is used, nstate)
-FD_CASES = {"humanoid_fd": ("humanoid", 6), "zoo_fd": ("zoo", 6), "humanoid_nocontact_fd": ("humanoid_nocontact", 6)}
+FD_CASES = {"humanoid_fd": ("humanoid", 6), "zoo_fd": ("zoo", 6), "humanoid_nocontact_fd": ("humanoid_nocontact", 6),
+            # with the sensor Jacobians DsDq / DsDv / DsDa (62 sensors of every stage)
+            "sensors_fd": ("sensors", 6)}
 FD_EPS = 1e-6
 
 
@@ -214,6 +222,13 @@ def make_fd_case(name):
     for k, v in opts.items():
         m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
     qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    if m.int("nsensordata") > 0:
+        dq, dv, da, sq, sv, sa = m.inverse_fd_sensor_batch(qpos, qvel, qacc, FD_EPS)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                            z_range=np.array(zr), eps=np.array(FD_EPS), DfDq=dq, DfDv=dv, DfDa=da,
+                            DsDq=sq, DsDv=sv, DsDa=sa)
+        print(f"{name}: nv={m.int('nv')} states={nstate} max|DsDq|={np.abs(sq).max():.3g} max|DsDa|={np.abs(sa).max():.3g}")
+        return
     dq, dv, da, dm = m.inverse_fd_batch(qpos, qvel, qacc, FD_EPS, mass=True)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
                         z_range=np.array(zr), eps=np.array(FD_EPS), DfDq=dq, DfDv=dv, DfDa=da, DmDq=dm)

@@ -11,7 +11,7 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat", "energy"]
 
 
 class Outputs(ctypes.Structure):
@@ -74,6 +74,8 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         a["mocap_quat"] = np.ascontiguousarray(mocap[1].reshape(n, -1).T, dtype=np.float64)
     if has_sensors:
         a["sensordata"] = np.zeros((model.int("nsensordata"), n))
+    if model.get_opt_int("enableflags") & (1 << 1):     # mjENBL_ENERGY
+        a["energy"] = np.zeros((2, n))
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL
     err = ctypes.create_string_buffer(1000)
     qp, qv, qa = (np.ascontiguousarray(x.T, dtype=np.float64) for x in (qpos, qvel, qacc))

@@ -584,6 +584,19 @@ def test_multi_tree_scene_runs_on_the_item_parallel_path():
         np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
 
 
+@pytest.mark.parametrize("name", ["humanoid_energy", "zoo_energy", "tendons_energy"])
+def test_golden_energy(name):
+    """mjENBL_ENERGY: d->energy = (potential, kinetic) as mj_inverse leaves it (mj_energyPos, mj_energyVel:
+    engine_sensor.c:920, 1011; called from engine_inverse.c:210-223), 1e-9 relative / 1e-12 absolute."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, name, True, mjb.OUT_COUNTS)
+    assert nbad == 0
+    np.testing.assert_array_equal(bd.counts()["ncon"], ref["ncon"])
+    np.testing.assert_allclose(bd.energy(), ref["energy"], rtol=1e-9, atol=1e-12)
+    nviol, worst = util.qfrc_violations(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+
+
 def test_hundred_humanoids_scene():
     """model/humanoid/100_humanoids.xml of the reference (nv = 2700, 1901 geoms, 1.8 M candidate pairs,
     ~4,300 contacts per state): counters, contact lists and efc ordering bit-exact against the
@@ -627,6 +640,28 @@ def test_inverse_fd_matches_reference(name):
         scale = np.abs(ref).reshape(n, -1).max(axis=1)[:, None, None]
         err = np.abs(got - ref) / np.maximum(scale, 1e-6)
         assert err.max() < 2e-3, (key, float(err.max()))
+
+
+def test_inverse_fd_sensor_jacobians_match_reference():
+    """mjb_inverseFDSensor: DsDq / DsDv / DsDa of mjd_inverseFD (engine_derivative_fd.c:611-730) on the
+    62-sensor fixture, together with the force Jacobians of the same call; same tolerance reading as
+    test_inverse_fd_matches_reference (2e-3 of the largest entry of the state's Jacobian)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    z = np.load(os.path.join(util.GOLDEN, "sensors_fd.npz"))
+    model = mjb.Model.from_mjb(util.golden(str(z["base"]))[0])
+    n = int(z["nstate"])
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(z["z_range"]))
+    bd = mjb.BatchData(model, n)
+    bd.set_state(qpos, qvel, qacc)
+    got = bd.inverse_fd_sensor(eps=float(z["eps"]))
+    for g, key in zip(got, ("DfDq", "DfDv", "DfDa", "DsDq", "DsDv", "DsDa")):
+        ref = z[key]
+        scale = np.abs(ref).reshape(n, -1).max(axis=1)[:, None, None]
+        err = np.abs(g - ref) / np.maximum(scale, 1e-6)
+        assert err.max() < 2e-3, (key, float(err.max()))
+    # position- and velocity-stage sensors do not depend on qacc: exact zeros, as in the reference
+    np.testing.assert_array_equal(got[5] == 0, z["DsDa"] == 0)
 
 
 def test_contact_record_list_overflow_falls_back_on_the_device():

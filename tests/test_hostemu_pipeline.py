@@ -168,6 +168,15 @@ def test_sensordata(case):
             np.testing.assert_array_equal(out["sensordata"][:, a:a + d], ref["sensordata"][:, a:a + d])
 
 
+@pytest.mark.parametrize("case", ["humanoid_energy", "zoo_energy", "tendons_energy"])
+def test_energy(case):
+    """d->energy of models with mjENBL_ENERGY (mj_energyPos / mj_energyVel inside mj_inverse,
+    engine_inverse.c:210-223) against the reference's dump."""
+    model, out, ref = _run(case)
+    np.testing.assert_allclose(out["energy"], ref["energy"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(out["ncon"], ref["ncon"])
+
+
 def test_candidate_list_contains_reference_contacts_in_order():
     """Every contact the reference reports (after its broadphase/midphase) appears in the static
     candidate list, in the same relative order (engine_collision_driver.c:265-484)."""
