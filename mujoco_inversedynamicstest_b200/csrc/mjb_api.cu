@@ -51,7 +51,8 @@ struct mjbData_ {
   mjb::ItemCon* d_item_con = nullptr;
   mjb::ContactRec* d_contacts = nullptr;
   int* d_slot_rec = nullptr;
-  int* d_scan_buf = nullptr;   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
+  int* d_scan_buf = nullptr;
+  int* d_pair_ci = nullptr;    // geom pair -> candidate index (ngeom x ngeom), long candidate lists only   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
   int items_cap = 0, contacts_cap = 0;
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
@@ -300,6 +301,24 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     }
     if (H.ncand > 0 && mjb::scan_wide_states(H.ncand, H.ngeom) > 0) {
       ok = ok && devAlloc(d, &d->d_scan_buf, (size_t)mjb::scan_wide_buf_ints(H.ncand, H.ngeom), "cudaMalloc(scan buffers)");
+      // geom pair -> candidate: the pair-organised scan needs every pair to map to at most one candidate
+      // and geom ids that fit 16 bits; MJB_SCAN=list keeps the list-driven kernel (A/B measurements)
+      const char* sm = std::getenv("MJB_SCAN");
+      if (ok && H.ngeom < 65536 && !(sm && !std::strcmp(sm, "list"))) {
+        const int* si = reinterpret_cast<const int*>(blob.data() + H.int_section) + H.ioff[MJB_I_scan_int];
+        std::vector<int> pc((size_t)H.ngeom * H.ngeom, -1);
+        bool unique = true;
+        for (int i = 0; i < H.ncand && unique; i++) {
+          const size_t g1 = (size_t)(si[2*i] & 0xfffffff), g2 = (size_t)si[2*i + 1];
+          if (g1 == g2 || pc[g1 * H.ngeom + g2] >= 0) { unique = false; break; }
+          pc[g1 * H.ngeom + g2] = i; pc[g2 * H.ngeom + g1] = i;
+        }
+        if (unique) {
+          ok = ok && devAlloc(d, &d->d_pair_ci, pc.size(), "cudaMalloc(pair table)");
+          ok = ok && check(d, cudaMemcpy(d->d_pair_ci, pc.data(), pc.size() * sizeof(int), cudaMemcpyHostToDevice),
+                           "cudaMemcpy(pair table)");
+        }
+      }
     }
   }
   ok = ok && devAlloc(d, &d->d_scratch, (size_t)H.nscratch * (size_t)d->chunk_stride, "cudaMalloc(scratch)");
@@ -482,6 +501,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_cq); cudaFree(d->d_items); cudaFree(d->d_item_con); cudaFree(d->d_contacts);
   cudaFree(d->d_slot_rec);
   cudaFree(d->d_scan_buf);
+  cudaFree(d->d_pair_ci);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
@@ -653,6 +673,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.has_spatial = d->hdr.has_spatial;
   a.skip_sensors = d->skip_sensors;
   a.scan_ngeom = d->hdr.ngeom;
+  a.pair_ci = d->d_pair_ci;
   a.scan_buf = d->d_scan_buf; a.scan_buf_cap = mjb::scan_wide_buf_cap(d->hdr.ncand);
   a.sub_nv = d->hdr.nv; a.sub_nbody = d->hdr.nbody; a.sub_nC = d->hdr.nC;
   {

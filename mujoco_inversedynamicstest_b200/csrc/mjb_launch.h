@@ -65,6 +65,7 @@ struct LaunchArgs {
   int sub_nv, sub_nbody, sub_nC; //    its sizes (mjbHdr::nv, nbody, nC)
   int scan_wide;                // > 0: warp-per-state candidate scan with this many states per CTA
                                 //      (scenes with long candidate lists, mjb_kernels.cu)
+  const int* pair_ci;           // [ngeom][ngeom] candidate index of a geom pair, -1: none (contact_scan_pairs_kernel), or null
   int* scan_buf;                // per-warp candidate buffers of the wide scan (scan_wide_buf_ints), or null
   int scan_buf_cap;             //   ints per warp
   int scan_ngeom;               // mjbHdr::ngeom (sizes the wide scan's shared memory)

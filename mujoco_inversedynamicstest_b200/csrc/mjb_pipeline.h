@@ -3949,6 +3949,24 @@ MJB_HD inline void inertia(Ctx& c) {
   double cr[10], A[21];
   auto inertia_body = [&](const int b) MJB_BODY_LAMBDA {
     const int flags = tree_flags[b];
+#if defined(__CUDA_ARCH__) && !defined(MJB_NO_INERTIA_PREFETCH)
+    // the rows the NEXT body of the sweep (b - 1) will read -- its cinert, the cdofs of its dofs and,
+    // where other children pushed into it, its accumulators -- are requested now, so that their HBM
+    // latency runs under this body's arithmetic (the kernel holds 12 warps per SM: nothing else hides it)
+    if (b - 1 >= lo && !c.lci) {
+      const int nb = b - 1;
+      for (int j = 0; j < 10; j++) prefetch_line(cinert + (size_t)(10*nb + j) * MJB_LS);
+      const int a0 = body_dofadr[nb], an = body_dofnum[nb];
+      MJB_UNROLL
+      for (int k = a0; k < a0 + an; k++) {
+        for (int j = 0; j < 6; j++) prefetch_line(cdof + (size_t)(6*k + j) * MJB_LS);
+      }
+      if (tree_flags[nb] & 4) {
+        for (int j = 0; j < 10; j++) prefetch_line(crb + (size_t)(10*nb + j) * MJB_LS);
+        for (int j = 0; j < 21; j++) prefetch_line(ia + (size_t)(21*nb + j) * MJB_LS);
+      }
+    }
+#endif
     {
       double ci[10];
       if (c.lci) { for (int j = 0; j < 10; j++) ci[j] = c.lci[10*(b - c.lbody0) + j]; }
