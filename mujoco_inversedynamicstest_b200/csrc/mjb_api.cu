@@ -50,8 +50,9 @@ struct mjbData_ {
   mjb::ContactItem* d_items = nullptr;
   mjb::ItemCon* d_item_con = nullptr;
   mjb::ContactRec* d_contacts = nullptr;
-  int* d_slot_rec = nullptr;
+  mjb::SlotRec* d_slot_rec = nullptr;
   int* d_scan_buf = nullptr;
+  int* d_cmask = nullptr;      // per-state survivor masks of the warp-per-state scans (one state's words contiguous)
   int* d_pair_ci = nullptr;    // geom pair -> candidate index (ngeom x ngeom), long candidate lists only   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
   int items_cap = 0, contacts_cap = 0;
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
@@ -288,7 +289,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
       long long ni = d->chunk_stride * per_items, nc = d->chunk_stride * per_contacts;
       const long long budget = 4LL << 30;
       const long long bytes = ni * (long long)(sizeof(mjb::ContactItem) + sizeof(mjb::ItemCon)) +
-                              nc * (long long)(sizeof(mjb::ContactRec) + sizeof(int));
+                              nc * (long long)(sizeof(mjb::ContactRec) + sizeof(mjb::SlotRec));
       if (bytes > budget) { ni = ni * budget / bytes; nc = nc * budget / bytes; }
       if (ni > 0x7ffffff0LL) ni = 0x7ffffff0LL;
       if (nc > 0x7ffffff0LL) nc = 0x7ffffff0LL;
@@ -301,6 +302,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     }
     if (H.ncand > 0 && mjb::scan_wide_states(H.ncand, H.ngeom) > 0) {
       ok = ok && devAlloc(d, &d->d_scan_buf, (size_t)mjb::scan_wide_buf_ints(H.ncand, H.ngeom), "cudaMalloc(scan buffers)");
+      ok = ok && devAlloc(d, &d->d_cmask, (size_t)d->chunk_stride * (size_t)((H.ncand + 31) / 32), "cudaMalloc(scan masks)");
       // geom pair -> candidate: the pair-organised scan needs every pair to map to at most one candidate
       // and geom ids that fit 16 bits; MJB_SCAN=list keeps the list-driven kernel (A/B measurements)
       const char* sm = std::getenv("MJB_SCAN");
@@ -502,6 +504,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_slot_rec);
   cudaFree(d->d_scan_buf);
   cudaFree(d->d_pair_ci);
+  cudaFree(d->d_cmask);
   cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
@@ -683,6 +686,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
     a.inertia_subwarp = (fits && env && !std::strcmp(env, "subwarp")) ? 1 : 0;
   }
   a.scan_wide = (std::getenv("MJB_SCAN_FLAT") || !d->d_scan_buf) ? 0 : mjb::scan_wide_states(d->hdr.ncand, d->hdr.ngeom);
+  a.cmask = a.scan_wide > 0 ? d->d_cmask : nullptr;
   a.out = d->out;
   // chunks reuse the same intermediates; kernels of consecutive chunks serialise on the stream
   for (long long start = first; start < first + count; start += d->chunk_stride) {

@@ -440,25 +440,26 @@ long long scan_wide_buf_ints(int ncand, int ngeom) {
 
 // mj_filterSphere (engine_collision_driver.c:146-163) on candidate ci of the state whose scratch
 // column is sc, in double precision (same expressions as contact_scan, mjb_pipeline.h)
-__device__ __forceinline__ bool scan_exact_test(const double* sc, size_t off_gxpos, size_t off_gxmat,
+__device__ __forceinline__ bool scan_exact_test(const double* sc, size_t off_gxpos, size_t off_gz,
                                                 const int* scan_int, const double* scan_bound, int ci) {
   const int g1k = scan_int[2 * ci], g2 = scan_int[2 * ci + 1];
   const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
   if (planeflag > 1) return true;
   const double bound = scan_bound[ci];
-  double pos1[3], pos2[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    pos1[k] = sc[(off_gxpos + 3 * g1 + k) * MJB_LS];
-    pos2[k] = sc[(off_gxpos + 3 * g2 + k) * MJB_LS];
-  }
+  // geom positions / z axes are 4-double vectors per (geom, state) (mjb_pipeline.h geom_vec): sc is
+  // the state's column (block base + lane), the vector of geom g sits at block + (off + 4 g) * 32 + 4 * lane
+  const size_t ln = ((size_t)sc >> 3) & 31;
+  const double* blk = sc - ln;
+  double p1[4], p2[4];
+  ld_rec4(p1, blk + ((off_gxpos + 4 * (size_t)g1) << 5) + 4 * ln);
+  ld_rec4(p2, blk + ((off_gxpos + 4 * (size_t)g2) << 5) + 4 * ln);
   if (planeflag == 0) {
-    const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    const double dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
     return !(dif[0]*dif[0] + dif[1]*dif[1] + dif[2]*dif[2] > bound*bound);
   }
-  const double nrm[3] = {sc[(off_gxmat + 9 * g1 + 2) * MJB_LS], sc[(off_gxmat + 9 * g1 + 5) * MJB_LS],
-                         sc[(off_gxmat + 9 * g1 + 8) * MJB_LS]};
-  const double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  double nrm[4];
+  ld_rec4(nrm, blk + ((off_gz + 4 * (size_t)g1) << 5) + 4 * ln);
+  const double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
   return !(dot3(dif, nrm) > bound);
 }
 
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
   float4* gx = gx_all + (size_t)warp * gp;
   const int cap = a.scan_buf_cap;
   int* buf = a.scan_buf + ((size_t)blockIdx.x * W + warp) * cap;            // this warp's candidate buffer
-  const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_xmat];
+  const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_zaxis];
   const int mask_row = MJB_ISC_MASK;
   const unsigned below = (1u << lane) - 1u;
 
@@ -489,21 +490,23 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
     const long long sb = valid ? s : 0;
     const double* sc = a.scratch + ((sb >> 5) * a.nscratch << 5) + (sb & 31);
     int* isc = a.iscratch + ((sb >> 5) * a.niscratch << 5) + (sb & 31);
-    int* maskw = isc + (size_t)mask_row * MJB_LS;
+    int* maskw = a.cmask + (size_t)sb * ((ncand + 31) >> 5);    // this state's survivor mask, contiguous words
     __syncthreads();                      // the previous round's tiles and positions are consumed
     float slack = 1e-4f;
     if (valid) {
       // positions relative to a stored geom (geom 1 of the first candidate), as floats
       const int gref = scan_int[0] & 0xfffffff;
-      const double r0 = sc[(off_gxpos + 3 * gref) * MJB_LS], r1 = sc[(off_gxpos + 3 * gref + 1) * MJB_LS],
-                   r2 = sc[(off_gxpos + 3 * gref + 2) * MJB_LS];
+      const double* gblk = sc - (sb & 31) + 4 * (sb & 31);     // this state's 4-double geom vectors: + (off + 4 g) * 32
+      const double r0 = gblk[(off_gxpos + 4 * gref) << 5], r1 = gblk[((off_gxpos + 4 * gref) << 5) + 1],
+                   r2 = gblk[((off_gxpos + 4 * gref) << 5) + 2];
       float m = 0;
       for (int g = lane; g < ngeom; g += 32) {
         // geoms outside every candidate pair are not stored by the sweep (geom_store, mjb_upload.cc)
         const bool stored = geom_store[g] != 0;
-        const float x = stored ? (float)(sc[(off_gxpos + 3 * g) * MJB_LS] - r0) : 0.f;
-        const float y = stored ? (float)(sc[(off_gxpos + 3 * g + 1) * MJB_LS] - r1) : 0.f;
-        const float z = stored ? (float)(sc[(off_gxpos + 3 * g + 2) * MJB_LS] - r2) : 0.f;
+        const double* gv = gblk + ((off_gxpos + 4 * (size_t)g) << 5);
+        const float x = stored ? (float)(gv[0] - r0) : 0.f;
+        const float y = stored ? (float)(gv[1] - r1) : 0.f;
+        const float z = stored ? (float)(gv[2] - r2) : 0.f;
         gx[g] = make_float4(x, y, z, 0.f);
         m = fmaxf(m, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
       }
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
       }
       __syncthreads();
       if (!valid || !finite) continue;
-      int* mw = maskw + (size_t)(t0 >> 5) * MJB_LS;
+      int* mw = maskw + (t0 >> 5);
       const int2* ti = tile_int + lane;
       const float* tb = tile_bound + lane;
 #pragma unroll 4
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
         const float dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
         const bool maybe = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= t * t;
         const unsigned m = __ballot_sync(0xffffffffu, maybe);
-        if (lane == 0) mw[(size_t)(c0 >> 5) * MJB_LS] = (int)m;
+        if (lane == 0) mw[c0 >> 5] = (int)m;
         if (maybe) {
           const int k = count + __popc(m & below);
           if (k < cap) buf[k] = t0 + c0 + lane;
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
         __syncwarp();
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (ok) buf[total + __popc(m & ((1u << lane) - 1u))] = ci;
-        else if (ci >= 0) atomicAnd(&isc[(size_t)(mask_row + (ci >> 5)) * MJB_LS], ~(1 << (ci & 31)));
+        else if (ci >= 0) atomicAnd(&maskw[ci >> 5], ~(1 << (ci & 31)));
         total += __popc(m);
         __syncwarp();
       }
@@ -588,7 +591,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
           const int ci = c0 + lane;
           const bool ok = ci < ncand && scan_exact_test(sc, off_gxpos, off_gxmat, scan_int, scan_bound, ci);
           const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (pass == 0) { if (lane == 0) isc[(size_t)(mask_row + (c0 >> 5)) * MJB_LS] = (int)m; }
+          if (pass == 0) { if (lane == 0) maskw[c0 >> 5] = (int)m; }
           else if (ok && fits) a.items[base + n + __popc(m & ((1u << lane) - 1u))] = ContactItem{(int)s, ci};
           n += __popc(m);
         }
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
   float4* gx = reinterpret_cast<float4*>(smem) + (size_t)warp * gp;         // x, y, z, bounding radius of every geom
   const int cap = a.scan_buf_cap;
   int* buf = a.scan_buf + ((size_t)blockIdx.x * W + warp) * cap;            // this warp's pair buffer
-  const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_xmat];
+  const size_t off_gxpos = (size_t)H->scoff[MJB_SC_geom_xpos], off_gxmat = (size_t)H->scoff[MJB_SC_geom_zaxis];
   const int nwords = (ncand + 31) >> 5;
   const unsigned below = (1u << lane) - 1u;
   const float kInf = __int_as_float(0x7f800000), kNaN = __int_as_float(0x7fc00000);
@@ -650,25 +653,27 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
     if (s >= a.chunk_n) continue;                     // warp-uniform; no CTA-wide barrier in this kernel
     const double* sc = a.scratch + ((s >> 5) * a.nscratch << 5) + (s & 31);
     int* isc = a.iscratch + ((s >> 5) * a.niscratch << 5) + (s & 31);
-    int* maskw = isc + (size_t)MJB_ISC_MASK * MJB_LS;
+    int* cm = a.cmask + (size_t)s * nwords;           // this state's survivor mask, contiguous words
     __syncwarp();
     // positions relative to a stored geom (geom 1 of the first candidate), as floats; radius: NaN = never
     // (geom outside every candidate pair), inf = always (no bounding radius: planes)
     const int gref = scan_int[0] & 0xfffffff;
-    const double r0 = sc[(off_gxpos + 3 * gref) * MJB_LS], r1 = sc[(off_gxpos + 3 * gref + 1) * MJB_LS],
-                 r2 = sc[(off_gxpos + 3 * gref + 2) * MJB_LS];
+    const double* gblk = sc - (s & 31) + 4 * (s & 31);       // this state's 4-double geom vectors: + (off + 4 g) * 32
+    const double r0 = gblk[(off_gxpos + 4 * gref) << 5], r1 = gblk[((off_gxpos + 4 * gref) << 5) + 1],
+                 r2 = gblk[((off_gxpos + 4 * gref) << 5) + 2];
     float m = 0;
     for (int g = lane; g < gp; g += 32) {
       const bool stored = g < ngeom && geom_store[g] != 0;
-      const float x = stored ? (float)(sc[(off_gxpos + 3 * g) * MJB_LS] - r0) : 0.f;
-      const float y = stored ? (float)(sc[(off_gxpos + 3 * g + 1) * MJB_LS] - r1) : 0.f;
-      const float z = stored ? (float)(sc[(off_gxpos + 3 * g + 2) * MJB_LS] - r2) : 0.f;
+      const double* gv = gblk + ((off_gxpos + 4 * (size_t)(g < ngeom ? g : 0)) << 5);
+      const float x = stored ? (float)(gv[0] - r0) : 0.f;
+      const float y = stored ? (float)(gv[1] - r1) : 0.f;
+      const float z = stored ? (float)(gv[2] - r2) : 0.f;
       float rb = kNaN;
       if (stored) { const double r = geom_rbound[g]; rb = r > 0 ? __double2float_ru(r) : kInf; }
       gx[g] = make_float4(x, y, z, rb);
       m = fmaxf(m, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
     }
-    for (int w = lane; w < nwords; w += 32) maskw[(size_t)w * MJB_LS] = 0;
+    for (int w = lane; w < nwords; w += 32) cm[w] = 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     const bool finite = m < 1e30f;
@@ -712,7 +717,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
           ci = a.pair_ci[(size_t)(pr >> 16) * ngeom + (pr & 0xffff)];
           ok = ci >= 0 && scan_exact_test(sc, off_gxpos, off_gxmat, scan_int, scan_bound, ci);
         }
-        if (ok) atomicOr(&maskw[(size_t)(ci >> 5) * MJB_LS], 1 << (ci & 31));
+        if (ok) atomicOr(&cm[ci >> 5], 1 << (ci & 31));
         total += __popc(__ballot_sync(0xffffffffu, ok));
       }
     } else {
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
         const int ci = c0 + lane;
         const bool ok = ci < ncand && scan_exact_test(sc, off_gxpos, off_gxmat, scan_int, scan_bound, ci);
         const unsigned mm = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) maskw[(size_t)(c0 >> 5) * MJB_LS] = (int)mm;
+        if (lane == 0) cm[c0 >> 5] = (int)mm;
         total += __popc(mm);
       }
     }
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
     for (int w0 = 0; w0 < nwords; w0 += 32) {
       const int w = w0 + lane;
       // (read at L2: the bits were set with atomics after this warp's own zeroing stores went through L1)
-      unsigned bits = w < nwords ? (unsigned)__ldcg(maskw + (size_t)w * MJB_LS) : 0u;
+      unsigned bits = w < nwords ? (unsigned)__ldcg(cm + w) : 0u;
       const int n = __popc(bits);
       int incl = n;
 #pragma unroll
@@ -857,7 +862,13 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
     if (valid) load_counters(own);
     int ncon = own.ncon, nefc = own.nefc;            // running counters of the state this lane owns
     int w = 0;
-    unsigned bits = (valid && nwords > 0) ? (unsigned)own.isc[(size_t)MJB_ISC_MASK * MJB_LS] : 0u;
+    // survivor mask of this lane's state: interleaved rows of iscratch (thread-per-state scan) or the
+    // contiguous per-state words the warp-per-state scans write
+    const int* cmw = (a.cmask && valid) ? a.cmask + (size_t)i * nwords : nullptr;
+    auto mask_word = [&](int ww) -> unsigned {
+      return cmw ? (unsigned)cmw[ww] : (unsigned)own.isc[(size_t)(MJB_ISC_MASK + ww) * MJB_LS];
+    };
+    unsigned bits = (valid && nwords > 0) ? mask_word(0) : 0u;
     int pool_n = 0;
 
     // step 3 on the current pool
@@ -936,7 +947,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
         while (cnt < kListCap) {
           while (bits == 0 && w + 1 < nwords) {
             w++;
-            bits = (unsigned)own.isc[(size_t)(MJB_ISC_MASK + w) * MJB_LS];
+            bits = mask_word(w);
           }
           if (bits == 0) break;
           const int b = __ffs((int)bits) - 1;
@@ -1062,7 +1073,7 @@ __global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : 2) con
         Ctx& co = c;      // rebinding c is enough (a by-value copy of the context faulted here for
         bind_state(co, a, it.state);   //  models read from global memory; cause not established)
         hit = narrow_test(co, it.ci);
-        a.item_con[i] = ItemCon{0, 0};
+        a.item_con[i] = ItemCon{0, 0, 0, 0};
       }
       const unsigned hm = __ballot_sync(0xffffffffu, hit);
       int wbase = 0;
@@ -1094,14 +1105,20 @@ __global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : 2) con
           if (lane == 0) a.cq->overflow_contacts = 1;
         } else if (num > 0) {
           const int first = base + incl - num;
-          a.item_con[item] = ItemCon{first, num};
+          int code[2] = {0, 0};
           for (int k = 0; k < num; k++) {
+            // rows this contact will occupy (mj_instantiateContact's counts), or -1 - exclude
+            int exclude;
+            const int rows = contact_row_count(c, it.ci, con[k].dist, &exclude);
+            const int cd = rows ? rows : -1 - exclude;
+            if (k < 2) code[k] = cd;
             ContactRec& r = a.contacts[first + k];
-            r.state = it.state; r.ci = it.ci; r.k = -1; r.efc_address = -1;
+            r.state = it.state; r.ci = it.ci; r.k = -1; r.efc_address = cd;
             r.dist = con[k].dist;
             for (int q = 0; q < 3; q++) r.pos[q] = con[k].pos[q];
             for (int q = 0; q < 6; q++) r.frame[q] = con[k].frame[q];
           }
+          a.item_con[item] = ItemCon{first, num, code[0], code[1]};
         }
       }
     }
@@ -1143,13 +1160,11 @@ __global__ void __launch_bounds__(kThreads, 4) contact_index_kernel(LaunchArgs a
     for (int j = 0; j < nsurv; j++) {
       const ItemCon ic = a.item_con[ibase + j];
       for (int q = 0; q < ic.count; q++) {
-        ContactRec& r = a.contacts[ic.base + q];
-        int exclude;
-        const int rows = contact_row_count(c, r.ci, r.dist, &exclude);
-        r.k = c.ncon++;
-        r.efc_address = rows ? c.nefc : -1 - exclude;     // < 0: no rows; exclude flag = -1 - value
+        const int cd = q == 0 ? ic.code0 : (q == 1 ? ic.code1 : a.contacts[ic.base + q].efc_address);
+        const int rows = cd > 0 ? cd : 0;
+        // first efc row, or < 0: no rows, exclude flag = -1 - value
+        a.slot_rec[slot++] = SlotRec{ic.base + q, c.ncon++, rows ? c.nefc : cd, 0};
         c.nefc += rows;
-        a.slot_rec[slot++] = ic.base + q;
       }
     }
     save_counters(c);
@@ -1197,23 +1212,17 @@ __global__ void __launch_bounds__(kThreads, 4) contact_index_wide_kernel(LaunchA
     int ncon = c.ncon, nefc = c.nefc;
     for (int j0 = 0; j0 < nsurv; j0 += 32) {
       const int j = j0 + lane;
-      ItemCon ic = {0, 0};
+      ItemCon ic = {0, 0, 0, 0};
       if (j < nsurv) ic = a.item_con[ibase + j];
+      auto code_of = [&](int q) { return q == 0 ? ic.code0 : (q == 1 ? ic.code1 : a.contacts[ic.base + q].efc_address); };
       int rsum = 0;
-      for (int q = 0; q < ic.count; q++) {
-        const ContactRec& r = a.contacts[ic.base + q];
-        int exclude;
-        rsum += contact_row_count(c, r.ci, r.dist, &exclude);
-      }
+      for (int q = 0; q < ic.count; q++) { const int cd = code_of(q); rsum += cd > 0 ? cd : 0; }
       const int kincl = warp_incl_scan(ic.count, lane), rincl = warp_incl_scan(rsum, lane);
       int k = ncon + kincl - ic.count, row = nefc + rincl - rsum;
       for (int q = 0; q < ic.count; q++) {
-        ContactRec& r = a.contacts[ic.base + q];
-        int exclude;
-        const int rows = contact_row_count(c, r.ci, r.dist, &exclude);
-        r.k = k;
-        r.efc_address = rows ? row : -1 - exclude;       // < 0: no rows; exclude flag = -1 - value
-        a.slot_rec[sbase + (k - ncon0)] = ic.base + q;
+        const int cd = code_of(q);
+        const int rows = cd > 0 ? cd : 0;
+        a.slot_rec[sbase + (k - ncon0)] = SlotRec{ic.base + q, k, rows ? row : cd, 0};
         k++; row += rows;
       }
       ncon += __shfl_sync(0xffffffffu, kincl, 31);
@@ -1268,7 +1277,8 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
       bool active = false;
       Ctx& co = c;
       if (has) {
-        const ContactRec& r = a.contacts[a.slot_rec[slot0 + r0 + lane]];
+        const SlotRec sr = a.slot_rec[slot0 + r0 + lane];
+        const ContactRec& r = a.contacts[sr.rec];
         owner = r.state - (int)w0;
         bind_state(co, a, r.state);
         Con con;
@@ -1276,10 +1286,10 @@ __global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a)
         for (int k = 0; k < 3; k++) { con.pos[k] = r.pos[k]; p[k] = r.pos[k]; }
         for (int k = 0; k < 6; k++) con.frame[k] = r.frame[k];
         cross3(con.frame + 6, con.frame, con.frame + 3);          // as mju_makeFrame's last step
-        const int exclude = r.efc_address >= 0 ? 0 : -1 - r.efc_address;
+        const int exclude = sr.efc_address >= 0 ? 0 : -1 - sr.efc_address;
         co.status = 0;
-        contact_rows(co, r.ci, con, r.k, exclude, r.efc_address >= 0 ? r.efc_address : -1, F, T3);
-        active = r.efc_address >= 0;
+        contact_rows(co, r.ci, con, sr.k, exclude, sr.efc_address >= 0 ? sr.efc_address : -1, F, T3);
+        active = sr.efc_address >= 0;
         b1 = cand_int[MJB_CAND_NI*r.ci + MJB_CI_B1]; b2 = cand_int[MJB_CAND_NI*r.ci + MJB_CI_B2];
         if (co.status) wstatus |= co.status, atomicOr(&co.isc[MJB_ISC_STATUS * MJB_LS], co.status);
       }

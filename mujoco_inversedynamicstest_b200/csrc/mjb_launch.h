@@ -28,9 +28,14 @@ constexpr int kListCap = MJB_LISTCAP;                  // per-lane survivor list
 // that kernel runs: every thread of every CTA takes the same decision.
 struct ContactQueue { int nitems; int ncontacts; int overflow; int nslots; int overflow_contacts; };
 struct ContactItem { int state; int ci; };          // chunk-local state, candidate pair
-struct ItemCon { int base; int count; };            // the item's contacts: contacts[base .. base+count)
+// the item's contacts: contacts[base .. base+count); code0 / code1: rows of its first two contacts (> 0) or
+// -1 - exclude (no rows), set by the narrow kernel so that the numbering pass need not read the contact
+// records (further contacts of an item carry their code in ContactRec::efc_address)
+struct ItemCon { int base; int count; int code0; int code1; };
+// slot (state's first slot + k) -> contact record, contact index k in its state, first efc row (or -1 - exclude)
+struct SlotRec { int rec; int k; int efc_address; int pad; };
 struct ContactRec {
-  int state, ci, k, efc_address;                    // k: contact index in its state; efc_address or -1
+  int state, ci, k, efc_address;                    // efc_address: the contact's row code (see ItemCon); k unused
   double dist, pos[3], frame[6];                    // normal, tangent (third axis is their cross product)
 };
 
@@ -53,7 +58,7 @@ struct LaunchArgs {
   int nconmax, njmax;
   ContactQueue* cq;             // item-parallel contact path (null: pooled kernel only)
   ContactItem* items; ItemCon* item_con; ContactRec* contacts;
-  int* slot_rec;                // slot (state's first slot + k) -> index into contacts
+  SlotRec* slot_rec;            // slot (state's first slot + k) -> contact record and its numbering
   int items_cap, contacts_cap;
   int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
   int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
@@ -65,6 +70,8 @@ struct LaunchArgs {
   int sub_nv, sub_nbody, sub_nC; //    its sizes (mjbHdr::nv, nbody, nC)
   int scan_wide;                // > 0: warp-per-state candidate scan with this many states per CTA
                                 //      (scenes with long candidate lists, mjb_kernels.cu)
+  int* cmask;                   // survivor masks of the warp-per-state scans, [chunk_stride][ceil(ncand/32)], one state's
+                                //   words contiguous (the thread-per-state scan keeps them interleaved in iscratch), or null
   const int* pair_ci;           // [ngeom][ngeom] candidate index of a geom pair, -1: none (contact_scan_pairs_kernel), or null
   int* scan_buf;                // per-warp candidate buffers of the wide scan (scan_wide_buf_ints), or null
   int scan_buf_cap;             //   ints per warp

@@ -249,8 +249,9 @@ enum {
   MJB_SC_xpos = 0,     // nbody*3
   MJB_SC_xquat,        // nbody*4
   MJB_SC_origin,       // nbody*3   origin of the spatial frame of a kinematic tree, stored at its ROOT body
-  MJB_SC_geom_xpos,    // ngeom*3
-  MJB_SC_geom_xmat,    // ngeom*9
+  MJB_SC_geom_xpos,    // ngeom*4   geom position as a 4-double VECTOR per (geom, state): lane l of geom g at (4*g*32 + 4*l);
+                       //           one coalesced 256-bit store per geom, one whole sector per gather (mjb_pipeline.h geom_vec)
+  MJB_SC_geom_xmat,    // ngeom*9   full frame, rows; only geoms whose pairs need more than the z axis (geom_store bit 1)
   MJB_SC_cinert,       // nbody*10
   MJB_SC_cdof,         // nv*6
   MJB_SC_cvel,         // nbody*6
@@ -269,6 +270,7 @@ enum {
   MJB_SC_cfrc_gc,      // nbody*6   passive body wrenches: gravcomp, spatial-tendon springs/dampers (only if needed)
   MJB_SC_weld_dt,      // neq*3     weld rows: (raw rotational efc_force) - (torque J'f), for the cfrc_ext output (only models with welds)
   MJB_SC_tree_sphere,  // ntree*4   bounding sphere of every kinematic tree (tree-level broadphase; only with scan runs)
+  MJB_SC_geom_zaxis,   // ngeom*4   z axis of the geom frame (plane normal, capsule axis), vector layout like geom_xpos
   MJB_SC_crec,         // nbody*16  contact carrier RECORDS (only with candidate pairs): unlike every other array this
                        //           one is state-major inside the warp block -- body b, lane l at (16*b*32 + 16*l) --
                        //           so that the 16 doubles [cvel 6 | cacc_lin 6 | tree origin 3 | 0] a contact row

@@ -280,6 +280,27 @@ MJB_HD inline void store_crec(Ctx& c, int b, const double* V, const double* AL, 
   st_rec4(r + 2*MJB_CREC_PART, AL[2], AL[3], AL[4], AL[5]);
   st_rec4(r + 3*MJB_CREC_PART, O[0], O[1], O[2], 0.0);
 }
+// Geom position / z axis as 4-double vectors per (geom, state) (MJB_SC_geom_xpos, MJB_SC_geom_zaxis): the sweep
+// writes each with one coalesced 256-bit store, the scans read them with one coalesced 256-bit load per
+// geom and the item-parallel narrow phase gathers ONE sector per vector (the row layout: three).
+MJB_HD inline double* geom_vec(Ctx& c, int slot, int g) {
+#if defined(__CUDA_ARCH__)
+  const size_t ln = ((size_t)c.sc >> 3) & 31;
+  return c.sc - ln + ((size_t)c.H->scoff[slot] + 4*(size_t)g) * 32 + ln*4;
+#else
+  return c.sc + ((size_t)c.H->scoff[slot] + 4*(size_t)g);
+#endif
+}
+MJB_HD inline void load_geom_pos(Ctx& c, int g, double* p3) {
+  double v[4];
+  ld_rec4(v, geom_vec(c, MJB_SC_geom_xpos, g));
+  p3[0] = v[0]; p3[1] = v[1]; p3[2] = v[2];
+}
+MJB_HD inline void load_geom_z(Ctx& c, int g, double* z3) {
+  double v[4];
+  ld_rec4(v, geom_vec(c, MJB_SC_geom_zaxis, g));
+  z3[0] = v[0]; z3[1] = v[1]; z3[2] = v[2];
+}
 // rec[16] of body b; a body without a dof on its chain to the world has zero carriers and no record
 MJB_HD inline void load_crec(Ctx& c, int b, bool is_static, double* rec) {
   if (is_static) {
@@ -712,7 +733,7 @@ MJB_HD inline double spatial_tendon_walk(Ctx& c, int t, F seg) {
       const int sideid = (int)(prm + (prm > 0 ? 0.5 : -0.5));      // mju_round
       double x1[3], gp[3], gm[9], sidep[3];
       site_world_pos(c, id1, x1);
-      ldn(gp, SC(geom_xpos), 3*wrapid, 3); ldn(gm, SC(geom_xmat), 9*wrapid, 9);
+      load_geom_pos(c, wrapid, gp); ldn(gm, SC(geom_xmat), 9*wrapid, 9);
       if (sideid >= 0) site_world_pos(c, sideid, sidep);
       wlen = wrap_geom(wpnt + 3, wpnt, x1, gp, gm, geom_size[3*wrapid], cylinder,
                        sideid >= 0 ? sidep : (const double*)0);
@@ -1264,7 +1285,7 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   const int* body_geomnum = MI(body_geomnum);
   const int* geom_sameframe = MI(geom_sameframe);
   const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  double* gxmat = SC(geom_xmat);
   // what a later phase reads of this geom (upload, geom_store): nothing when it is in no candidate
   // pair; position + z axis for plane / sphere / capsule pairs; the full frame for the other
   // narrow-phase functions and for tendon wrapping. The debug dump stores everything.
@@ -1294,15 +1315,9 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
     } else {
       for (int k = 0; k < 9; k++) gm[k] = im[k];
     }
-    sts(gxpos, 3*g, gp, 3);
-    if (store & 2) {
-      sts(gxmat, 9*g, gm, 9);
-    } else {
-      const double z[3] = {gm[2], gm[5], gm[8]};
-      stn_stream_(gxmat, 9*g + 2, z, 1, MJB_LS);
-      stn_stream_(gxmat, 9*g + 5, z + 1, 1, MJB_LS);
-      stn_stream_(gxmat, 9*g + 8, z + 2, 1, MJB_LS);
-    }
+    st_rec4(geom_vec(c, MJB_SC_geom_xpos, g), gp[0], gp[1], gp[2], 0.0);
+    st_rec4(geom_vec(c, MJB_SC_geom_zaxis, g), gm[2], gm[5], gm[8], 0.0);
+    if (store & 2) sts(gxmat, 9*g, gm, 9);
   }
 }
 
@@ -2814,17 +2829,19 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
   const double* geom_size = MD(geom_size);
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
+  double* gxmat = SC(geom_xmat);
   const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
   const double margin = cn[MJB_CN_MARGIN];
   const int func = cint[MJB_CI_FUNC];
   double pos1[3], pos2[3], mat1[9], mat2[9];
-  ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
+  load_geom_pos(c, g1, pos1); load_geom_pos(c, g2, pos2);
   if (kSimple || func == MJB_FN_PLANE_SPHERE || func == MJB_FN_PLANE_CAPSULE || func == MJB_FN_SPHERE_SPHERE ||
       func == MJB_FN_SPHERE_CAPSULE || func == MJB_FN_CAPSULE_CAPSULE) {
-    // these read only the z axis of either frame (plane normal, capsule axis): 6 loads instead of 18
+    // these read only the z axis of either frame (plane normal, capsule axis): one vector each
+    double z1[3], z2[3];
+    load_geom_z(c, g1, z1); load_geom_z(c, g2, z2);
     for (int k = 0; k < 9; k++) { mat1[k] = 0; mat2[k] = 0; }
-    for (int k = 2; k < 9; k += 3) { mat1[k] = AT(gxmat, 9*g1 + k); mat2[k] = AT(gxmat, 9*g2 + k); }
+    for (int k = 0; k < 3; k++) { mat1[3*k + 2] = z1[k]; mat2[3*k + 2] = z2[k]; }
   } else {
     ldn(mat1, gxmat, 9*g1, 9); ldn(mat2, gxmat, 9*g2, 9);
   }
@@ -2880,13 +2897,12 @@ MJB_HD inline bool narrow_test(Ctx& c, int ci) {
         func == MJB_FN_SPHERE_CAPSULE || func == MJB_FN_CAPSULE_CAPSULE)) return true;
   const double margin = MD(cand_num)[MJB_CAND_NN*ci + MJB_CN_MARGIN];
   const double* geom_size = MD(geom_size);
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
   const int g1 = cint[MJB_CI_G1], g2 = cint[MJB_CI_G2];
   const double* size1 = geom_size + 3*g1;
   const double* size2 = geom_size + 3*g2;
   double pos1[3], pos2[3], z1[3], z2[3];
-  ldn(pos1, gxpos, 3*g1, 3); ldn(pos2, gxpos, 3*g2, 3);
-  for (int k = 0; k < 3; k++) { z1[k] = AT(gxmat, 9*g1 + 2 + 3*k); z2[k] = AT(gxmat, 9*g2 + 2 + 3*k); }
+  load_geom_pos(c, g1, pos1); load_geom_pos(c, g2, pos2);
+  load_geom_z(c, g1, z1); load_geom_z(c, g2, z2);
   switch (func) {
     case MJB_FN_PLANE_SPHERE:
       return plane_sphere_hit(margin, pos1, z1, pos2, size2[0]);
@@ -2959,7 +2975,6 @@ MJB_HD inline void collide_pair(Ctx& c, int ci) {
 //  DRAM traffic; profiles/r01_launches_sorted_contact_experiment.csv.)
 MJB_HD inline int contact_scan(Ctx& c) {
   const mjbHdr& H = *c.H;
-  double* gxpos = SC(geom_xpos); double* gxmat = SC(geom_xmat);
   // compact scan rows (mjb_upload.cc): geom 1 | kind << 28, geom 2, and the bound
   const int* scan_int = MI(scan_int);
   const double* scan_bound = MD(scan_bound);
@@ -2983,12 +2998,12 @@ MJB_HD inline int contact_scan(Ctx& c) {
     const int g1 = g1k & 0xfffffff, planeflag = (int)((unsigned)g1k >> 28);
     const double bound = scan_bound[ci];
     if (g1 != last_g1) {          // candidates are grouped by geom 1: keep it in registers
-      ldn(pos1, gxpos, 3*g1, 3);
-      if (planeflag == 1) { nrm[0] = AT(gxmat, 9*g1 + 2); nrm[1] = AT(gxmat, 9*g1 + 5); nrm[2] = AT(gxmat, 9*g1 + 8); }
+      load_geom_pos(c, g1, pos1);
+      if (planeflag == 1) load_geom_z(c, g1, nrm);
       last_g1 = g1;
     }
     double pos2[3];
-    ldn(pos2, gxpos, 3*g2, 3);
+    load_geom_pos(c, g2, pos2);
     bool pass = true;
     if (planeflag == 0) {
       const double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
@@ -3018,7 +3033,7 @@ MJB_HD inline int contact_scan(Ctx& c) {
       for (int g = tree_int[3*t + 1]; g < tree_int[3*t + 2]; g++) {
         if (!geom_store[g]) continue;
         double p[3];
-        ldn(p, gxpos, 3*g, 3);
+        load_geom_pos(c, g, p);
         const double d[3] = {p[0] - O[0], p[1] - O[1], p[2] - O[2]};
         r = fmax(r, sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]) + rbound[g]);
       }

@@ -871,7 +871,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     const int nb = m->nbody, ng = m->ngeom, nt = m->ntendon;
     int sizes[MJB_SC_COUNT];
     sizes[MJB_SC_xpos] = 3*nb; sizes[MJB_SC_xquat] = 4*nb; sizes[MJB_SC_origin] = 3*nb;
-    sizes[MJB_SC_geom_xpos] = 3*ng; sizes[MJB_SC_geom_xmat] = 9*ng;
+    sizes[MJB_SC_geom_xpos] = 4*ng; sizes[MJB_SC_geom_xmat] = 9*ng; sizes[MJB_SC_geom_zaxis] = 4*ng;
     sizes[MJB_SC_cinert] = 10*nb; sizes[MJB_SC_cdof] = 6*nv; sizes[MJB_SC_cvel] = 6*nb;
     sizes[MJB_SC_cacc_lin] = 6*nb; sizes[MJB_SC_cacc] = 6*nb;
     sizes[MJB_SC_cfrc] = 6*nb; sizes[MJB_SC_cfrc_ext] = 6*nb; sizes[MJB_SC_cfrc_ext1] = 6*nb; sizes[MJB_SC_qfrc_c] = nv;
