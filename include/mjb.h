@@ -44,9 +44,15 @@ typedef enum mjbOut_ {
   mjbOUT_EFC       = 1 << 3,  /* efc_type, efc_id, efc_state, efc_pos, margin, D, R, vel, aref, force */
   mjbOUT_INERTIA   = 1 << 4,  /* qM, qLD, qLDiagInv (mj_crb, mj_factorM)                              */
   mjbOUT_INTERNAL  = 1 << 5,  /* every position/velocity-stage intermediate (xpos ... cfrc), debug    */
-  mjbOUT_RNEPOST   = 1 << 6   /* cacc, cfrc_int, cfrc_ext as left by mj_rnePostConstraint             *
+  mjbOUT_RNEPOST   = 1 << 6,  /* cacc, cfrc_int, cfrc_ext as left by mj_rnePostConstraint             *
                                * (include/mujoco/mujoco.h mj_rnePostConstraint,                       *
                                * src/engine/engine_core_smooth.c:2027-2181; mjdata.h cacc/cfrc_*)     */
+  mjbOUT_CAMLIGHT  = 1 << 7,  /* cam_xpos, cam_xmat, light_xpos, light_xdir as mj_camlight leaves    *
+                               * them inside mj_invPosition (engine_core_smooth.c:275-389)            */
+  mjbOUT_TRANSMISSION = 1 << 8 /* actuator_length, actuator_moment (dense nu x nv), actuator_velocity:*
+                               * mj_transmission inside mj_invPosition (engine_core_smooth.c:865-1346)*
+                               * and mj_fwdVelocity (engine_forward.c:216). Models with adhesion      *
+                               * actuators (mjTRN_BODY) are refused when this bit is set.             */
 } mjbOut;
 
 /* per-state status bits, the batched form of d->warning[] (engine_forward.c:53-102,
@@ -82,6 +88,14 @@ typedef enum mjbField_ {
   mjbF_QFRC_BIAS,         /* double nv: mj_rne without accelerations, engine_forward.c:228 (QFRC) */
   mjbF_ENERGY,            /* double 2: d->energy = potential, kinetic (mj_energyPos / mj_energyVel, engine_sensor.c:920,
                              1011); produced, without a mask bit, for models with mjENBL_ENERGY -- engine_inverse.c:210-223 */
+  mjbF_CAM_XPOS,          /* double ncam*3        (CAMLIGHT) */
+  mjbF_CAM_XMAT,          /* double ncam*9        (CAMLIGHT) */
+  mjbF_LIGHT_XPOS,        /* double nlight*3      (CAMLIGHT) */
+  mjbF_LIGHT_XDIR,        /* double nlight*3      (CAMLIGHT) */
+  mjbF_ACTUATOR_LENGTH,   /* double nu            (TRANSMISSION) */
+  mjbF_ACTUATOR_MOMENT,   /* double nu*nv, row-major dense; the reference keeps the same rows compressed
+                             (moment_rownnz / moment_rowadr / moment_colind, mjdata.h)   (TRANSMISSION) */
+  mjbF_ACTUATOR_VELOCITY, /* double nu            (TRANSMISSION) */
   mjbF_COUNT
 } mjbField;
 

@@ -15,14 +15,16 @@ import numpy as np
 
 from ._lib import lib
 
-OUT_QFRC, OUT_COUNTS, OUT_CONTACT, OUT_EFC, OUT_INERTIA, OUT_INTERNAL, OUT_RNEPOST = (1 << i for i in range(7))
+(OUT_QFRC, OUT_COUNTS, OUT_CONTACT, OUT_EFC, OUT_INERTIA, OUT_INTERNAL, OUT_RNEPOST, OUT_CAMLIGHT,
+ OUT_TRANSMISSION) = (1 << i for i in range(9))
 
 STATUS_BADQPOS, STATUS_BADQVEL, STATUS_BADQACC, STATUS_CONTACTFULL, STATUS_CNSTRFULL = (
     1 << i for i in range(5))
 
 (F_QFRC_INVERSE, F_QFRC_CONSTRAINT, F_QFRC_PASSIVE, F_COUNTS, F_STATUS, F_CONTACT_GEOM,
  F_CONTACT_INFO, F_CONTACT_NUM, F_EFC_INT, F_EFC_NUM, F_QM, F_QLD, F_QLDIAGINV, F_INTERNAL,
- F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS, F_ENERGY) = range(20)
+ F_CACC, F_CFRC_INT, F_CFRC_EXT, F_SENSORDATA, F_QFRC_BIAS, F_ENERGY, F_CAM_XPOS, F_CAM_XMAT, F_LIGHT_XPOS,
+ F_LIGHT_XDIR, F_ACTUATOR_LENGTH, F_ACTUATOR_MOMENT, F_ACTUATOR_VELOCITY) = range(27)
 
 _INT_FIELDS = {F_COUNTS, F_STATUS, F_CONTACT_GEOM, F_CONTACT_INFO, F_EFC_INT}
 _CODES = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
@@ -353,6 +355,23 @@ class BatchData:
     def energy(self):
         """d->energy (potential, kinetic) per state, for models with mjENBL_ENERGY."""
         return self.get(F_ENERGY)
+
+    def camlight(self):
+        """cam_xpos [nbatch, ncam, 3], cam_xmat [.., 9], light_xpos / light_xdir [nbatch, nlight, 3] as
+        mj_camlight leaves them (src/engine/engine_core_smooth.c:275-389); needs OUT_CAMLIGHT."""
+        n = self.last_batch()
+        return {k: self.get(f).reshape(n, -1, c) for k, f, c in (
+            ("cam_xpos", F_CAM_XPOS, 3), ("cam_xmat", F_CAM_XMAT, 9), ("light_xpos", F_LIGHT_XPOS, 3),
+            ("light_xdir", F_LIGHT_XDIR, 3))}
+
+    def transmission(self):
+        """actuator_length [nbatch, nu], actuator_moment [nbatch, nu, nv] (dense), actuator_velocity
+        [nbatch, nu] (mj_transmission, src/engine/engine_core_smooth.c:865-1346); needs OUT_TRANSMISSION."""
+        n = self.last_batch()
+        length = self.get(F_ACTUATOR_LENGTH)
+        nu = length.shape[1]
+        return {"actuator_length": length, "actuator_moment": self.get(F_ACTUATOR_MOMENT).reshape(n, nu, -1),
+                "actuator_velocity": self.get(F_ACTUATOR_VELOCITY)}
 
     def internal(self, name):
         off, size = ctypes.c_int(), ctypes.c_int()

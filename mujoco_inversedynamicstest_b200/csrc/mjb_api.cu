@@ -224,6 +224,15 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     }
   }
 
+  if (outmask & mjbOUT_TRANSMISSION) {
+    // adhesion actuators take their moment from the contact normals' Jacobians (engine_core_smooth.c:1222-1330)
+    for (int i = 0; i < m->nu; i++) {
+      if (m->actuator_trntype[i] == mjTRN_BODY) {
+        return fail("mjb_makeData: mjbOUT_TRANSMISSION is not available for models with adhesion actuators (mjTRN_BODY)");
+      }
+    }
+  }
+
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     return fail("mjb_makeData: no CUDA device available (libmjb has no CPU path)");
@@ -390,6 +399,29 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     setField(d, mjbF_CFRC_INT, o.cfrc_int, 6 * H.nbody, 0);
     setField(d, mjbF_CFRC_EXT, o.cfrc_ext, 6 * H.nbody, 0);
   }
+  if (outmask & mjbOUT_TRANSMISSION) {
+    // mj_transmission + actuator_velocity (engine_core_smooth.c:865-1346, engine_forward.c:216)
+    const size_t nu = (size_t)(H.nu > 0 ? H.nu : 1), nvv = (size_t)(H.nv > 0 ? H.nv : 1);
+    ok = ok && devAlloc(d, &o.actuator_length, nu * S, "cudaMalloc(actuator_length)");
+    ok = ok && devAlloc(d, &o.actuator_moment, nu * nvv * S, "cudaMalloc(actuator_moment)");
+    ok = ok && devAlloc(d, &o.actuator_velocity, nu * S, "cudaMalloc(actuator_velocity)");
+    setField(d, mjbF_ACTUATOR_LENGTH, o.actuator_length, H.nu, 0);
+    setField(d, mjbF_ACTUATOR_MOMENT, o.actuator_moment, H.nu * H.nv, 0);
+    setField(d, mjbF_ACTUATOR_VELOCITY, o.actuator_velocity, H.nu, 0);
+  }
+  if (outmask & mjbOUT_CAMLIGHT) {
+    // mj_camlight (engine_core_smooth.c:275-389); one slot is kept for models without cameras or lights
+    // so that the four pointers are set together
+    const size_t nc = (size_t)(H.ncam > 0 ? H.ncam : 1), nl = (size_t)(H.nlight > 0 ? H.nlight : 1);
+    ok = ok && devAlloc(d, &o.cam_xpos, 3 * nc * S, "cudaMalloc(cam_xpos)");
+    ok = ok && devAlloc(d, &o.cam_xmat, 9 * nc * S, "cudaMalloc(cam_xmat)");
+    ok = ok && devAlloc(d, &o.light_xpos, 3 * nl * S, "cudaMalloc(light_xpos)");
+    ok = ok && devAlloc(d, &o.light_xdir, 3 * nl * S, "cudaMalloc(light_xdir)");
+    setField(d, mjbF_CAM_XPOS, o.cam_xpos, 3 * H.ncam, 0);
+    setField(d, mjbF_CAM_XMAT, o.cam_xmat, 9 * H.ncam, 0);
+    setField(d, mjbF_LIGHT_XPOS, o.light_xpos, 3 * H.nlight, 0);
+    setField(d, mjbF_LIGHT_XDIR, o.light_xdir, 3 * H.nlight, 0);
+  }
   if (H.enableflags & MJB_ENBL_ENERGY) {
     // d->energy is part of mj_inverse's output contract when mjENBL_ENERGY is set (engine_inverse.c:210-223)
     ok = ok && devAlloc(d, &o.energy, (size_t)2 * S, "cudaMalloc(energy)");
@@ -527,6 +559,8 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(o.contact_num); cudaFree(o.efc_int); cudaFree(o.efc_num); cudaFree(o.qM);
   cudaFree(o.qLD); cudaFree(o.qLDiagInv); cudaFree(o.scratch_dump);
   cudaFree(o.cacc); cudaFree(o.cfrc_int); cudaFree(o.cfrc_ext); cudaFree(o.sensordata); cudaFree(o.energy);
+  cudaFree(o.cam_xpos); cudaFree(o.cam_xmat); cudaFree(o.light_xpos); cudaFree(o.light_xdir);
+  cudaFree(o.actuator_length); cudaFree(o.actuator_moment); cudaFree(o.actuator_velocity);
   cudaFree(o.qfrc_bias);
   delete d;
 }

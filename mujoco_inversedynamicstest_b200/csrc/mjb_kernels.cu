@@ -1421,6 +1421,34 @@ __global__ void __launch_bounds__(kThreads, 4) energy_kernel(LaunchArgs a) {
   }
 }
 
+// cam_xpos / cam_xmat / light_xpos / light_xdir (mj_camlight), only when mjbOUT_CAMLIGHT is requested
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) camlight_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    camlight(c);
+  }
+}
+
+// actuator_length / actuator_moment / actuator_velocity (mj_transmission), only when mjbOUT_TRANSMISSION is requested
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) transmission_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    transmission(c);
+  }
+}
+
 size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
   return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
 }
@@ -1691,6 +1719,18 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   if (args.out.sensordata && !args.skip_sensors) {
     e = in_smem ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
                 : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  if (args.out.actuator_length) {
+    e = in_smem ? launch_phase(transmission_kernel<true>, args, smem, 8, stream)
+                : launch_phase(transmission_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  if (args.out.cam_xpos) {
+    e = in_smem ? launch_phase(camlight_kernel<true>, args, smem, 8, stream)
+                : launch_phase(camlight_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }

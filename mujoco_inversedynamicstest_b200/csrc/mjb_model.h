@@ -46,7 +46,14 @@
   X(tendon_adr, ntendon)         \
   X(tendon_num, ntendon)         \
   X(wrap_type, nwrap)            \
-  X(wrap_objid, nwrap)
+  X(wrap_objid, nwrap)           \
+  X(cam_mode, ncam)              \
+  X(cam_bodyid, ncam)            \
+  X(cam_targetbodyid, ncam)      \
+  X(light_mode, nlight)          \
+  X(light_bodyid, nlight)        \
+  X(light_targetbodyid, nlight)  \
+  X(actuator_trntype, nu)
 
 // ---- byte arrays of mjModel widened to int
 #define MJB_BYTE_ARRAYS(X)       \
@@ -67,6 +74,7 @@
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
+  X(actuator_trn) /* nu*2 : actuator_trnid (object, reference / slider site) */ \
   X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
   X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
@@ -120,7 +128,19 @@
   X(tendon_invweight0, ntendon, 1)   \
   X(tendon_length0, ntendon, 1)      \
   X(eq_data, neq, 11)                \
-  X(wrap_prm, nwrap, 1)
+  X(wrap_prm, nwrap, 1)              \
+  X(cam_pos, ncam, 3)                \
+  X(cam_quat, ncam, 4)               \
+  X(cam_poscom0, ncam, 3)            \
+  X(cam_pos0, ncam, 3)               \
+  X(cam_mat0, ncam, 9)               \
+  X(light_pos, nlight, 3)            \
+  X(light_dir, nlight, 3)            \
+  X(light_poscom0, nlight, 3)        \
+  X(light_pos0, nlight, 3)           \
+  X(light_dir0, nlight, 3)           \
+  X(actuator_gear, nu, 6)            \
+  X(actuator_cranklength, nu, 1)
 
 // ---- derived double tables: pre-clamped solver parameters, MJB_SP_N doubles per record
 #define MJB_DERIVED_NUM_ARRAYS(X) \
@@ -300,6 +320,8 @@ typedef struct mjbHdr_ {
   int32_t sensor_post;      // some sensor reads cacc / cfrc_int (mj_rnePostConstraint, engine_sensor.c:727-740)
   int32_t nsite;
   int32_t nmocap;
+  int32_t ncam, nlight;     // cameras / lights (mj_camlight outputs, mjbOUT_CAMLIGHT)
+  int32_t nu;               // actuators (mj_transmission outputs, mjbOUT_TRANSMISSION)
   int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
   int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)
@@ -330,6 +352,8 @@ enum { MJB_CNSTR_EQUALITY = 0, MJB_CNSTR_FRICTION_DOF, MJB_CNSTR_FRICTION_TENDON
        MJB_CNSTR_CONTACT_PYRAMIDAL, MJB_CNSTR_CONTACT_ELLIPTIC };
 enum { MJB_STATE_SATISFIED = 0, MJB_STATE_QUADRATIC, MJB_STATE_LINEARNEG, MJB_STATE_LINEARPOS,
        MJB_STATE_CONE };
+enum { MJB_TRN_JOINT = 0, MJB_TRN_JOINTINPARENT, MJB_TRN_SLIDERCRANK, MJB_TRN_TENDON, MJB_TRN_SITE, MJB_TRN_BODY };
+enum { MJB_CAMLIGHT_FIXED = 0, MJB_CAMLIGHT_TRACK, MJB_CAMLIGHT_TRACKCOM, MJB_CAMLIGHT_TARGETBODY, MJB_CAMLIGHT_TARGETBODYCOM };
 enum { MJB_SAMEFRAME_NONE = 0, MJB_SAMEFRAME_BODY, MJB_SAMEFRAME_INERTIA, MJB_SAMEFRAME_BODYROT,
        MJB_SAMEFRAME_INERTIAROT };
 enum { MJB_WRAP_NONE = 0, MJB_WRAP_JOINT, MJB_WRAP_PULLEY, MJB_WRAP_SITE, MJB_WRAP_SPHERE, MJB_WRAP_CYLINDER };

@@ -129,6 +129,15 @@ struct Outputs {
   const double* mocap_quat;           // [nmocap*4][stride]
   // d->energy [2][stride] (mj_energyPos, mj_energyVel), only for models with mjENBL_ENERGY; else null
   double* energy;
+  // mj_camlight (engine_core_smooth.c:275-389), all four or none (mjbOUT_CAMLIGHT)
+  double* cam_xpos;                   // [ncam*3][stride]
+  double* cam_xmat;                   // [ncam*9][stride]
+  double* light_xpos;                 // [nlight*3][stride]
+  double* light_xdir;                 // [nlight*3][stride]
+  // mj_transmission + actuator_velocity of mj_fwdVelocity, all three or none (mjbOUT_TRANSMISSION)
+  double* actuator_length;            // [nu][stride]
+  double* actuator_moment;            // [nu*nv][stride], dense rows
+  double* actuator_velocity;          // [nu][stride]
 };
 
 struct Ctx {
@@ -1500,7 +1509,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     quat2Mat(mat, quat);
     // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
     // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
-    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc) {
+    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.cam_xpos || c.out.actuator_length) {
       stc(xquat, 4*b, quat, 4);
       stc(xpos, 3*b, pos, 3);
     }
@@ -3831,6 +3840,290 @@ MJB_HD inline void energy(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// mj_camlight (engine_core_smooth.c:275-389): world poses of cameras and lights from the body poses
+// of the sweep. subtree_com of every body (mj_comPos :190-213, the reference's accumulation order)
+// is rebuilt in the ia rows of the scratch (free after the inertia kernel) only when a camera or
+// light tracks or targets a subtree's centre of mass.
+MJB_HD inline void camlight_point(Ctx& c, int body, const double* lpos, double* pos, double* bq) {
+  ldn(pos, SC(xpos), 3*body, 3); ldn(bq, SC(xquat), 4*body, 4);
+  double m[9], r[3];
+  quat2Mat(m, bq);
+  mulMatVec3(r, m, lpos);
+  pos[0] = r[0] + pos[0]; pos[1] = r[1] + pos[1]; pos[2] = r[2] + pos[2];
+}
+MJB_HD inline void camlight(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int* cam_mode = MI(cam_mode); const int* light_mode = MI(light_mode);
+  bool need_com = false;
+  for (int i = 0; i < H.ncam; i++) need_com |= cam_mode[i] == MJB_CAMLIGHT_TRACKCOM || cam_mode[i] == MJB_CAMLIGHT_TARGETBODYCOM;
+  for (int i = 0; i < H.nlight; i++) need_com |= light_mode[i] == MJB_CAMLIGHT_TRACKCOM || light_mode[i] == MJB_CAMLIGHT_TARGETBODYCOM;
+  double* com = SC(ia);      // [0..2] subtree_com, [3] subtree mass, [4..6] xipos per body (stride 8)
+  if (need_com) {
+    const int* body_parentid = MI(body_parentid);
+    const double* mass = MD(body_mass);
+    const double zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < H.nbody; i++) stn(com, 8*i, zero, 8);
+    for (int i = H.nbody - 1; i >= 0; i--) {
+      double w[8], xi[3], bq[4];
+      ldn(w, com, 8*i, 8);
+      camlight_point(c, i, MD(body_ipos) + 3*i, xi, bq);
+      for (int k = 0; k < 3; k++) w[k] += xi[k]*mass[i];
+      w[3] += mass[i];
+      if (i) {
+        const int p = body_parentid[i];
+        double pw[4];
+        ldn(pw, com, 8*p, 4);
+        for (int k = 0; k < 4; k++) pw[k] += w[k];
+        stn(com, 8*p, pw, 4);
+      }
+      if (w[3] < MJB_MINVAL) {
+        for (int k = 0; k < 3; k++) w[k] = xi[k];
+      } else {
+        const double inv = 1.0/fmax(MJB_MINVAL, w[3]);
+        for (int k = 0; k < 3; k++) w[k] *= inv;
+      }
+      stn(com, 8*i, w, 4);
+    }
+  }
+  double tgt[3];
+  for (int i = 0; i < H.ncam; i++) {
+    const int id = MI(cam_bodyid)[i], id1 = MI(cam_targetbodyid)[i], mode = cam_mode[i];
+    double pos[3], bq[4], q[4], mat[9];
+    camlight_point(c, id, MD(cam_pos) + 3*i, pos, bq);
+    mulQuat(q, bq, MD(cam_quat) + 4*i);
+    quat2Mat(mat, q);
+    if (mode == MJB_CAMLIGHT_TRACK || mode == MJB_CAMLIGHT_TRACKCOM) {
+      for (int k = 0; k < 9; k++) mat[k] = MD(cam_mat0)[9*i + k];
+      if (mode == MJB_CAMLIGHT_TRACK) {
+        ldn(pos, SC(xpos), 3*id, 3);
+        for (int k = 0; k < 3; k++) pos[k] += MD(cam_pos0)[3*i + k];
+      } else {
+        ldn(pos, com, 8*id, 3);
+        for (int k = 0; k < 3; k++) pos[k] += MD(cam_poscom0)[3*i + k];
+      }
+    } else if ((mode == MJB_CAMLIGHT_TARGETBODY || mode == MJB_CAMLIGHT_TARGETBODYCOM) && id1 >= 0) {
+      if (mode == MJB_CAMLIGHT_TARGETBODY) ldn(tgt, SC(xpos), 3*id1, 3); else ldn(tgt, com, 8*id1, 3);
+      double T[9];
+      for (int k = 0; k < 3; k++) T[6 + k] = pos[k] - tgt[k];   // z axis = -viewing direction
+      normalize3(T + 6);
+      T[3] = 0; T[4] = 0; T[5] = 1;
+      cross3(T, T + 3, T + 6);
+      normalize3(T);
+      cross3(T + 3, T + 6, T);
+      normalize3(T + 3);
+      for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) mat[3*r + k] = T[3*k + r];
+    }
+    for (int k = 0; k < 3; k++) c.out.cam_xpos[(size_t)(3*i + k)*N + c.s] = pos[k];
+    for (int k = 0; k < 9; k++) c.out.cam_xmat[(size_t)(9*i + k)*N + c.s] = mat[k];
+  }
+  for (int i = 0; i < H.nlight; i++) {
+    const int id = MI(light_bodyid)[i], id1 = MI(light_targetbodyid)[i], mode = light_mode[i];
+    double pos[3], bq[4], dir[3];
+    camlight_point(c, id, MD(light_pos) + 3*i, pos, bq);
+    rotVecQuat(dir, MD(light_dir) + 3*i, bq);
+    if (mode == MJB_CAMLIGHT_TRACK || mode == MJB_CAMLIGHT_TRACKCOM) {
+      for (int k = 0; k < 3; k++) dir[k] = MD(light_dir0)[3*i + k];
+      if (mode == MJB_CAMLIGHT_TRACK) {
+        ldn(pos, SC(xpos), 3*id, 3);
+        for (int k = 0; k < 3; k++) pos[k] += MD(light_pos0)[3*i + k];
+      } else {
+        ldn(pos, com, 8*id, 3);
+        for (int k = 0; k < 3; k++) pos[k] += MD(light_poscom0)[3*i + k];
+      }
+    } else if ((mode == MJB_CAMLIGHT_TARGETBODY || mode == MJB_CAMLIGHT_TARGETBODYCOM) && id1 >= 0) {
+      if (mode == MJB_CAMLIGHT_TARGETBODY) ldn(tgt, SC(xpos), 3*id1, 3); else ldn(tgt, com, 8*id1, 3);
+      for (int k = 0; k < 3; k++) dir[k] = tgt[k] - pos[k];
+    }
+    normalize3(dir);
+    for (int k = 0; k < 3; k++) c.out.light_xpos[(size_t)(3*i + k)*N + c.s] = pos[k];
+    for (int k = 0; k < 3; k++) c.out.light_xdir[(size_t)(3*i + k)*N + c.s] = dir[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_transmission (engine_core_smooth.c:865-1346) and actuator_velocity (mj_fwdVelocity,
+// engine_forward.c:216): actuator_length [nu], actuator_moment as the DENSE nu x nv matrix the
+// reference's compressed rows (moment_rownnz / rowadr / colind) expand to, actuator_velocity [nu].
+// The Jacobians of the reference (mj_jacSite, mj_jacPointAxis, ten_J) are never formed: a moment row
+// is the projection of a wrench on the dof chain of a body,
+//   row[j] += s * ( F . (ang_j x (p - O) + lin_j) + T . ang_j ),   cdof_j = (ang_j, lin_j) about O,
+// the column of (jacp' F + jacr' T). Adhesion actuators (mjTRN_BODY) are refused in mjb_makeData.
+MJB_HD inline void trn_project(Ctx& c, double* row, int body, int stop_dof, const double* p, const double* F,
+                               const double* T, double s) {
+  const int wb = MI(body_weldid)[body];
+  if (!MI(body_dofnum)[wb]) return;
+  const int* dof_parentid = MI(dof_parentid);
+  const size_t N = (size_t)c.N;
+  double o[3];
+  ldn(o, SC(origin), 3*MI(body_rootid)[wb], 3);
+  const double r[3] = {p[0] - o[0], p[1] - o[1], p[2] - o[2]};
+  for (int j = MI(body_dofadr)[wb] + MI(body_dofnum)[wb] - 1; j >= 0 && j != stop_dof; j = dof_parentid[j]) {
+    double cd[6], jp[3], v = 0;
+    ldn(cd, SC(cdof), 6*j, 6);
+    if (F) {
+      cross3(jp, cd, r);
+      jp[0] += cd[3]; jp[1] += cd[4]; jp[2] += cd[5];
+      v = jp[0]*F[0] + jp[1]*F[1] + jp[2]*F[2];
+    }
+    if (T) v += cd[0]*T[0] + cd[1]*T[1] + cd[2]*T[2];
+    row[(size_t)j*N] += s*v;
+  }
+}
+MJB_HD inline void transmission(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const size_t N = (size_t)c.N;
+  const int nv = H.nv;
+  const int* trntype = MI(actuator_trntype); const int* trn = MI(actuator_trn);
+  const int* jnt_type = MI(jnt_type); const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* site_bodyid = MI(site_bodyid);
+  for (int i = 0; i < H.nu; i++) {
+    const int id = trn[2*i], type = trntype[i];
+    const double* gear = MD(actuator_gear) + 6*i;
+    double* row = c.out.actuator_moment + (size_t)i*nv*N + c.s;
+    for (int j = 0; j < nv; j++) row[(size_t)j*N] = 0;
+    double length = 0;
+    if (type == MJB_TRN_JOINT || type == MJB_TRN_JOINTINPARENT) {
+      const int jt = jnt_type[id], qadr = jnt_qposadr[id], dadr = jnt_dofadr[id];
+      if (jt == MJB_JNT_SLIDE || jt == MJB_JNT_HINGE) {
+        length = QPOS(qadr)*gear[0];
+        row[(size_t)dadr*N] = gear[0];
+      } else {
+        // ball: gear axis against the joint's expmap; free: the last three dofs take the rotational gear
+        const int q0 = jt == MJB_JNT_BALL ? qadr : qadr + 3;
+        const double* g = jt == MJB_JNT_BALL ? gear : gear + 3;
+        double quat[4] = {QPOS(q0), QPOS(q0 + 1), QPOS(q0 + 2), QPOS(q0 + 3)};
+        double axis[3], ga[3] = {g[0], g[1], g[2]};
+        normalize4(quat);
+        if (jt == MJB_JNT_BALL) quat2Vel(axis, quat, 1);
+        if (type == MJB_TRN_JOINTINPARENT) {
+          const double nq[4] = {quat[0], -quat[1], -quat[2], -quat[3]};
+          rotVecQuat(ga, g, nq);
+        }
+        if (jt == MJB_JNT_BALL) {
+          length = dot3(axis, ga);
+          for (int k = 0; k < 3; k++) row[(size_t)(dadr + k)*N] = ga[k];
+        } else {
+          for (int k = 0; k < 3; k++) { row[(size_t)(dadr + k)*N] = gear[k]; row[(size_t)(dadr + 3 + k)*N] = ga[k]; }
+        }
+      }
+    } else if (type == MJB_TRN_SLIDERCRANK) {
+      const int ids = trn[2*i + 1];
+      const double rod = MD(actuator_cranklength)[i];
+      double p[3], ps[3], q[4], qs[4], ms[9];
+      sensor_object(c, MJB_OBJ_SITE, id, p, q);
+      sensor_object(c, MJB_OBJ_SITE, ids, ps, qs);
+      quat2Mat(ms, qs);
+      const double axis[3] = {ms[2], ms[5], ms[8]};
+      const double vec[3] = {p[0] - ps[0], p[1] - ps[1], p[2] - ps[2]};
+      const double av = dot3(vec, axis);
+      const double det = av*av + rod*rod - dot3(vec, vec);
+      double dlda[3], dldv[3];
+      if (det <= 0) {
+        length = av;
+        for (int k = 0; k < 3; k++) { dlda[k] = vec[k]; dldv[k] = axis[k]; }
+      } else {
+        const double sdet = sqrt(det);
+        length = av - sdet;
+        for (int k = 0; k < 3; k++) {
+          dldv[k] = axis[k]*(1 - av/sdet) + vec[k]*(1/sdet);
+          dlda[k] = vec[k]*(1 - av/sdet);
+        }
+      }
+      // dl/dq = dlda . (jacr_slider x axis) + dldv . (jacp_crank - jacp_slider): the first term is the
+      // torque axis x dlda on the slider's body
+      double tq[3];
+      cross3(tq, axis, dlda);
+      trn_project(c, row, site_bodyid[id], -1, p, dldv, nullptr, gear[0]);
+      trn_project(c, row, site_bodyid[ids], -1, ps, dldv, nullptr, -gear[0]);
+      trn_project(c, row, site_bodyid[ids], -1, ps, nullptr, tq, gear[0]);
+      length *= gear[0];
+    } else if (type == MJB_TRN_TENDON) {
+      const int adr = MI(tendon_adr)[id], num = MI(tendon_num)[id];
+      if (MI(wrap_type)[adr] == MJB_WRAP_JOINT) {
+        const int* wrap_objid = MI(wrap_objid); const double* wrap_prm = MD(wrap_prm);
+        for (int j = 0; j < num; j++) {
+          const int k = wrap_objid[adr + j];
+          length += wrap_prm[adr + j]*QPOS(jnt_qposadr[k]);
+          row[(size_t)jnt_dofadr[k]*N] += wrap_prm[adr + j]*gear[0];
+        }
+        length *= gear[0];
+      } else {
+        length = gear[0]*spatial_tendon_walk(c, id, [&](int ba, const double* pa, int bb, const double* pb,
+                                                          const double* dif, double divisor) {
+          trn_project(c, row, bb, -1, pb, dif, nullptr, gear[0]/divisor);
+          trn_project(c, row, ba, -1, pa, dif, nullptr, -gear[0]/divisor);
+        });
+      }
+    } else if (type == MJB_TRN_SITE) {
+      const int refid = trn[2*i + 1];
+      double p[3], q[4], m9[9];
+      sensor_object(c, MJB_OBJ_SITE, id, p, q);
+      if (refid < 0) {
+        double w[6];
+        quat2Mat(m9, q);
+        mulMatVec3(w, m9, gear); mulMatVec3(w + 3, m9, gear + 3);
+        trn_project(c, row, site_bodyid[id], -1, p, w, w + 3, 1.0);
+      } else {
+        // difference of the two sites' Jacobians with the columns of their common ancestors cleared
+        // (:1112-1160): each chain is walked only down to the first common dof
+        const int* dof_parentid = MI(dof_parentid);
+        const int b0 = MI(body_weldid)[site_bodyid[id]], b1 = MI(body_weldid)[site_bodyid[refid]];
+        int d0 = MI(body_dofadr)[b0] + MI(body_dofnum)[b0] - 1, d1 = MI(body_dofadr)[b1] + MI(body_dofnum)[b1] - 1;
+        int common = -1;
+        if (d0 >= 0 && d1 >= 0) {
+          while (d0 != d1) {
+            if (d0 < d1) d1 = dof_parentid[d1]; else d0 = dof_parentid[d0];
+            if (d0 == -1 || d1 == -1) break;
+          }
+          if (d0 == d1) common = d0;
+        }
+        double pr[3], qr[4], mr[9], w[3];
+        sensor_object(c, MJB_OBJ_SITE, refid, pr, qr);
+        quat2Mat(mr, qr);
+        if (gear[0] != 0 || gear[1] != 0 || gear[2] != 0) {
+          double vec[3] = {p[0] - pr[0], p[1] - pr[1], p[2] - pr[2]}, lv[3];
+          mulMatTVec3(lv, mr, vec);
+          length += dot3(lv, gear);
+          mulMatVec3(w, mr, gear);
+          trn_project(c, row, site_bodyid[id], common, p, w, nullptr, 1.0);
+          trn_project(c, row, site_bodyid[refid], common, pr, w, nullptr, -1.0);
+        }
+        if (gear[3] != 0 || gear[4] != 0 || gear[5] != 0) {
+          // the reference composes the quaternions as site_quat * xquat here (:1174-1176), kept as is
+          double bq[4], sq[4], rq[4], vec[3];
+          ldn(bq, SC(xquat), 4*site_bodyid[id], 4);
+          mulQuat(sq, MD(site_quat) + 4*id, bq);
+          ldn(bq, SC(xquat), 4*site_bodyid[refid], 4);
+          mulQuat(rq, MD(site_quat) + 4*refid, bq);
+          subQuat(vec, sq, rq);
+          length += dot3(vec, gear + 3);
+          mulMatVec3(w, mr, gear + 3);
+          trn_project(c, row, site_bodyid[id], common, p, nullptr, w, 1.0);
+          trn_project(c, row, site_bodyid[refid], common, pr, nullptr, w, -1.0);
+        }
+      }
+    }
+    c.out.actuator_length[(size_t)i*N + c.s] = length;
+    // actuator_velocity = moment . qvel over the row's non-zeros, in mju_dotSparse's order (four
+    // interleaved partial sums over whole groups of four, then the tail; engine_util_sparse.h:115-157)
+    int nnz = 0;
+    for (int j = 0; j < nv; j++) nnz += row[(size_t)j*N] != 0;
+    double r4[4] = {0, 0, 0, 0}, tail = 0;
+    int k = 0;
+    const int whole = nnz & ~3;
+    for (int j = 0; j < nv; j++) {
+      const double v = row[(size_t)j*N];
+      if (v == 0) continue;
+      if (k < whole) r4[k & 3] += v*QVEL(j); else { if (k == whole) tail = (r4[0] + r4[2]) + (r4[1] + r4[3]); tail += v*QVEL(j); }
+      k++;
+    }
+    if (nnz == whole) tail = (r4[0] + r4[2]) + (r4[1] + r4[3]);
+    c.out.actuator_velocity[(size_t)i*N + c.s] = tail;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // mj_compareFwdInv (engine_inverse.c:275-316) for one state, after the backward sweep:
 //   fwdinv[0] = | qfrc_constraint(forward) - qfrc_constraint(inverse) |
 //   fwdinv[1] = | qfrc_applied + qfrc_actuator + J'*xfrc_applied - qfrc_inverse |
@@ -4321,6 +4614,8 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   if (c.out.energy) energy(c);
   if (c.out.sensordata) sensors(c);
   if (c.out.fwdinv) compare_fwdinv(c);
+  if (c.out.cam_xpos) camlight(c);
+  if (c.out.actuator_length) transmission(c);
 }
 
 #undef MI

@@ -735,6 +735,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.sensor_post = sensor_post ? 1 : 0;
   H.nsite = m->nsite;
   H.nmocap = m->nmocap;
+  H.ncam = m->ncam; H.nlight = m->nlight;
+  H.nu = m->nu;
   H.sensor_subtreevel = sensor_subtreevel ? 1 : 0;
   H.sensor_touch = sensor_touch ? 1 : 0;
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
@@ -769,6 +771,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_sensor_int, sensor_int.data(), sensor_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_tendon_active, tendon_active.data(), tendon_active.size());
+  pushInts(MJB_I_actuator_trn, m->actuator_trnid, (size_t)2 * m->nu);
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
   {
     // static row numbering (mj_makeConstraint order: equality, dof friction, tendon friction, ...)
@@ -838,8 +841,13 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       geom_store[ci[MJB_CI_G1]] |= light ? 1 : 3;
       geom_store[ci[MJB_CI_G2]] |= light ? 1 : 3;
     }
+    // tendons that drive an actuator: mj_transmission walks their path when mjbOUT_TRANSMISSION is requested
+    std::vector<int> tendon_trn(m->ntendon, 0);
+    for (int i = 0; i < m->nu; i++) {
+      if (m->actuator_trntype[i] == mjTRN_TENDON) tendon_trn[m->actuator_trnid[2*i]] = 1;
+    }
     for (int t = 0; t < m->ntendon; t++) {
-      if (!tendon_active[t]) continue;
+      if (!tendon_active[t] && !tendon_trn[t]) continue;
       for (int j = 0; j < m->tendon_num[t]; j++) {
         const int wt = m->wrap_type[m->tendon_adr[t] + j];
         if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) geom_store[m->wrap_objid[m->tendon_adr[t] + j]] |= 3;

@@ -270,6 +270,8 @@ class Model:
             "qfrc_spring": ("nv", 1), "qfrc_damper": ("nv", 1), "ten_length": ("ntendon", 1),
             "ten_velocity": ("ntendon", 1), "ten_J": ("ntendon", "nv"),
             "sensordata": ("nsensordata", 1), "cacc": ("nbody", 6), "cfrc_int": ("nbody", 6), "cfrc_ext": ("nbody", 6),
+            "cam_xpos": ("ncam", 3), "cam_xmat": ("ncam", 9), "light_xpos": ("nlight", 3), "light_xdir": ("nlight", 3),
+            "actuator_length": ("nu", 1), "actuator_velocity": ("nu", 1),
         }
         if name == "energy":        # member array of mjData: potential, kinetic
             return 2, 1, np.float64
@@ -278,6 +280,12 @@ class Model:
             return self.int(r), (self.int(c) if isinstance(c, str) else c), np.float64
         if name in _INT_EFC:
             return 0, 1, np.int32
+        if name in ("moment_rownnz", "moment_rowadr"):      # compressed rows of actuator_moment
+            return self.int("nu"), 1, np.int32
+        if name == "moment_colind":
+            return self.int("nJmom"), 1, np.int32
+        if name == "actuator_moment":
+            return self.int("nJmom"), 1, np.float64
         if name.startswith("efc_"):
             return 0, (4 if name == "efc_KBIP" else 1), np.float64
         raise KeyError(name)

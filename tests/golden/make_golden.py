@@ -60,6 +60,10 @@ CASES = {
     "humanoid_energy": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 1}, 128, (0.0, 1.5), 64, 256),
     "zoo_energy": ("repo:tests/golden/models/zoo.xml", {"enableflags": 1 << 1}, 128, (0.0, 0.6), 32, 128),
     "tendons_energy": ("repo:tests/golden/models/tendons.xml", {"enableflags": 1 << 1}, 128, (0.3, 1.3), 8, 32),
+    # cameras and lights in every mjtCamLight mode (outputs of mj_camlight: CAMLIGHT_CASES)
+    "camlight": ("repo:tests/golden/models/camlight.xml", {}, 128, (0.2, 1.2), 16, 64),
+    # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)
+    "transmission": ("repo:tests/golden/models/transmission.xml", {}, 128, (0.2, 1.2), 16, 64),
 }
 
 
@@ -325,9 +329,60 @@ def make_mocap_case(name):
     print(f"{name}: states={nstate} mean ncon={out['ncon'].mean():.2f} mean nefc={out['nefc'].mean():.2f}")
 
 
+# mj_camlight inside mj_invPosition (engine_core_smooth.c:275-389): cam_xpos, cam_xmat, light_xpos,
+# light_xdir on the first states of a case's stream: name -> (case whose model / stream is used, nstate)
+CAMLIGHT_CASES = {"camlight_cl": ("camlight", 128), "humanoid_cl": ("humanoid", 64)}
+
+
+def make_camlight_case(name):
+    base, nstate = CAMLIGHT_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields={"cam_xpos": None, "cam_xmat": None, "light_xpos": None,
+                                                          "light_xdir": None})
+    out.pop("qfrc_inverse")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), **out)
+    print(f"{name}: ncam={m.int('ncam')} nlight={m.int('nlight')} states={nstate}")
+
+
+# mj_transmission inside mj_invPosition (engine_core_smooth.c:865-1346) and actuator_velocity of
+# mj_fwdVelocity (engine_forward.c:216): actuator_length, the compressed actuator_moment expanded to the
+# dense nu x nv matrix, actuator_velocity: name -> (case whose model / stream is used, nstate)
+TRANSMISSION_CASES = {"transmission_trn": ("transmission", 128), "humanoid_trn": ("humanoid", 32),
+                      "arm26_trn": ("arm26", 64), "slider_crank_trn": ("slider_crank_nocontact", 64)}
+
+
+def make_transmission_case(name):
+    base, nstate = TRANSMISSION_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields={"actuator_length": None, "actuator_velocity": None,
+                                                          "actuator_moment": None, "moment_rownnz": None,
+                                                          "moment_rowadr": None, "moment_colind": None})
+    nu, nv = m.int("nu"), m.int("nv")
+    dense = np.zeros((nstate, nu, nv))
+    for s in range(nstate):
+        for i in range(nu):
+            adr, nnz = int(out["moment_rowadr"][s, i, 0]), int(out["moment_rownnz"][s, i, 0])
+            dense[s, i, out["moment_colind"][s, adr:adr + nnz, 0]] = out["actuator_moment"][s, adr:adr + nnz, 0]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), actuator_length=out["actuator_length"][..., 0],
+                        actuator_velocity=out["actuator_velocity"][..., 0], actuator_moment=dense)
+    print(f"{name}: nu={nu} nv={nv} states={nstate} max|moment|={np.abs(dense).max():.3g} "
+          f"mean nnz={out['moment_rownnz'].mean():.2f}")
+
+
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
-                 list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES)):
-        (make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES) + list(CAMLIGHT_CASES) +
+                 list(TRANSMISSION_CASES)):
+        (make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

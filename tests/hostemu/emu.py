@@ -11,7 +11,9 @@ import build_hostemu  # noqa: E402
 
 _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status", "contact_geom",
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
-           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat", "energy"]
+           "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat", "energy",
+           "cam_xpos", "cam_xmat", "light_xpos", "light_xdir",
+           "actuator_length", "actuator_moment", "actuator_velocity"]
 
 
 class Outputs(ctypes.Structure):
@@ -40,7 +42,8 @@ def available():
     return os.path.exists(build_hostemu.LIB) or build_hostemu.include_dir() is not None
 
 
-def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None):
+def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None, camlight=False,
+        transmission=False):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -76,6 +79,14 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         a["sensordata"] = np.zeros((model.int("nsensordata"), n))
     if model.get_opt_int("enableflags") & (1 << 1):     # mjENBL_ENERGY
         a["energy"] = np.zeros((2, n))
+    if camlight:            # mj_camlight outputs (mjbOUT_CAMLIGHT)
+        nc, nl = max(1, model.int("ncam")), max(1, model.int("nlight"))
+        a.update(cam_xpos=np.zeros((3 * nc, n)), cam_xmat=np.zeros((9 * nc, n)),
+                 light_xpos=np.zeros((3 * nl, n)), light_xdir=np.zeros((3 * nl, n)))
+    if transmission:        # mj_transmission outputs (mjbOUT_TRANSMISSION)
+        nu = max(1, model.int("nu"))
+        a.update(actuator_length=np.zeros((nu, n)), actuator_moment=np.zeros((nu * max(1, nv), n)),
+                 actuator_velocity=np.zeros((nu, n)))
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL
     err = ctypes.create_string_buffer(1000)
     qp, qv, qa = (np.ascontiguousarray(x.T, dtype=np.float64) for x in (qpos, qvel, qacc))

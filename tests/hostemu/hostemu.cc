@@ -64,6 +64,15 @@ int hostemu_nscratch(const mjModel_* m) {
   return reinterpret_cast<const mjbHdr*>(blob.data())->nscratch;
 }
 
+// size of the model blob in bytes (what a CTA stages into shared memory), or -1
+__attribute__((visibility("default")))
+int hostemu_model_bytes(const mjModel_* m) {
+  std::vector<unsigned char> blob;
+  std::string msg;
+  if (!mjb::buildModelBlob(m, blob, msg)) return -1;
+  return (int)blob.size();
+}
+
 __attribute__((visibility("default")))
 int hostemu_slot(const mjModel_* m, const char* name, int* offset, int* size) {
   std::vector<unsigned char> blob;

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic"]
+         "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -582,6 +582,51 @@ def test_multi_tree_scene_runs_on_the_item_parallel_path():
     efc = bd.efc()
     for k in ("type", "id", "state"):
         np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
+
+
+def _run_fixture(mjb, path, n, zr, outmask):
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    bd = mjb.BatchData(model, n, outmask=outmask)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    return model, bd
+
+
+@pytest.mark.parametrize("name", ["camlight_cl", "humanoid_cl"])
+def test_golden_camlight(name):
+    """mjbOUT_CAMLIGHT: cam_xpos / cam_xmat / light_xpos / light_xdir as mj_camlight leaves them inside
+    mj_invPosition (engine_core_smooth.c:275-389), every mjtCamLight mode, 1e-9 relative / 1e-12 absolute."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, ref, n, zr = util.camlight_fixture(name)
+    model, bd = _run_fixture(mjb, path, n, zr, mjb.OUT_CAMLIGHT)
+    got = bd.camlight()
+    for k in ("cam_xpos", "cam_xmat", "light_xpos", "light_xdir"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["transmission_trn", "humanoid_trn", "arm26_trn", "slider_crank_trn"])
+def test_golden_transmission(name):
+    """mjbOUT_TRANSMISSION: actuator_length, actuator_moment (dense) and actuator_velocity as mj_transmission
+    and mj_fwdVelocity leave them inside mj_inverse (engine_core_smooth.c:865-1346, engine_forward.c:216);
+    joint / jointinparent / slider-crank / tendon / site transmissions, 1e-9 relative / 1e-12 absolute."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, ref, n, zr = util.transmission_fixture(name)
+    model, bd = _run_fixture(mjb, path, n, zr, mjb.OUT_TRANSMISSION)
+    got = bd.transmission()
+    np.testing.assert_allclose(got["actuator_length"], ref["actuator_length"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["actuator_moment"], ref["actuator_moment"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["actuator_velocity"], ref["actuator_velocity"], rtol=1e-9, atol=1e-11)
+
+
+def test_outputs_only_rows_leave_qfrc_inverse_unchanged():
+    """Requesting the output-only rows (camlight, transmission) does not change qfrc_inverse."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "humanoid", True, mjb.OUT_CAMLIGHT | mjb.OUT_TRANSMISSION)
+    assert nbad == 0
+    nviol, worst = util.qfrc_violations(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
 
 
 @pytest.mark.parametrize("name", ["humanoid_energy", "zoo_energy", "tendons_energy"])

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.skipif(not emu.available(), reason="host emulation libr
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic"]
+         "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission"]
 
 
 def _run(name):
@@ -166,6 +166,40 @@ def test_sensordata(case):
     for a, d, s, t in zip(adr, dim, stage, typ):
         if s == 1 and t != 34:      # subtreecom is a differently ordered mass-weighted sum
             np.testing.assert_array_equal(out["sensordata"][:, a:a + d], ref["sensordata"][:, a:a + d])
+
+
+@pytest.mark.parametrize("name", ["camlight_cl", "humanoid_cl"])
+def test_camlight(name):
+    """cam_xpos / cam_xmat / light_xpos / light_xdir as mj_camlight leaves them inside mj_invPosition
+    (engine_core_smooth.c:275-389), every mjtCamLight mode; bit-identical in the CPU build."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.camlight_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    out = emu.run(model, qpos, qvel, qacc, camlight=True)
+    for k in ("cam_xpos", "cam_xmat", "light_xpos", "light_xdir"):
+        np.testing.assert_array_equal(out[k].reshape(ref[k].shape), ref[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["transmission_trn", "humanoid_trn", "arm26_trn", "slider_crank_trn"])
+def test_transmission(name):
+    """actuator_length / actuator_moment (dense) / actuator_velocity as mj_transmission and mj_fwdVelocity
+    leave them inside mj_inverse (engine_core_smooth.c:865-1346, engine_forward.c:216): every
+    transmission type but the adhesion one, against the reference's compressed rows expanded."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.transmission_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    out = emu.run(model, qpos, qvel, qacc, transmission=True)
+    nu, nv = model.int("nu"), model.int("nv")
+    np.testing.assert_allclose(out["actuator_length"], ref["actuator_length"], rtol=1e-12, atol=1e-14)
+    mom = out["actuator_moment"].reshape(n, nu, nv)
+    np.testing.assert_allclose(mom, ref["actuator_moment"], rtol=1e-9, atol=1e-12)
+    if name == "humanoid_trn":      # joint transmissions: the rows' structural zeros are exact zeros
+        assert (mom[ref["actuator_moment"] == 0] == 0).all()
+    np.testing.assert_allclose(out["actuator_velocity"], ref["actuator_velocity"], rtol=1e-9, atol=1e-11)
 
 
 @pytest.mark.parametrize("case", ["humanoid_energy", "zoo_energy", "tendons_energy"])

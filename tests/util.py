@@ -124,6 +124,24 @@ def post_fixture(name):
             int(z["nstate"]), tuple(z["z_range"]))
 
 
+def camlight_fixture(name):
+    """(path of the base case's MJB, dict with cam_xpos / cam_xmat / light_xpos / light_xdir of the
+    reference's mj_camlight, nstate, z_range) of a tests/golden/*_cl.npz fixture."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"),
+            {k: z[k] for k in ("cam_xpos", "cam_xmat", "light_xpos", "light_xdir")},
+            int(z["nstate"]), tuple(z["z_range"]))
+
+
+def transmission_fixture(name):
+    """(path of the base case's MJB, dict with actuator_length [n, nu], actuator_moment [n, nu, nv] (dense),
+    actuator_velocity [n, nu] of the reference, nstate, z_range) of a tests/golden/*_trn.npz fixture."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"),
+            {k: z[k] for k in ("actuator_length", "actuator_moment", "actuator_velocity")},
+            int(z["nstate"]), tuple(z["z_range"]))
+
+
 def spatial_violations(got, ref, rtol=RTOL, atol=ATOL):
     """north_star bound for per-body spatial vectors [n, nbody, 6]; like qfrc_violations_scaled the
     relative part is taken against the largest entry of the STATE (sums of contact wrenches of
