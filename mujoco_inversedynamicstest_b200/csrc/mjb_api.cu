@@ -209,6 +209,8 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     if (H0->sensor_post) outmask |= mjbOUT_RNEPOST;   // accelerometer / force / torque / frame*acc sensors
     // touch sensors walk the contact list and the contact rows' forces: those outputs are their input
     if (H0->sensor_touch) outmask |= mjbOUT_COUNTS | mjbOUT_CONTACT | mjbOUT_EFC;
+    if (H0->sensor_cam) outmask |= mjbOUT_CAMLIGHT;           // camprojection sensors read the camera poses
+    if (H0->sensor_trn) outmask |= mjbOUT_TRANSMISSION;       // actuatorpos / actuatorvel sensors
   }
   if (outmask & mjbOUT_RNEPOST) {
     // constraint forces of spatial tendons travel as body wrenches here but are not part of the
@@ -422,7 +424,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     setField(d, mjbF_LIGHT_XPOS, o.light_xpos, 3 * H.nlight, 0);
     setField(d, mjbF_LIGHT_XDIR, o.light_xdir, 3 * H.nlight, 0);
   }
-  if (H.enableflags & MJB_ENBL_ENERGY) {
+  if ((H.enableflags & MJB_ENBL_ENERGY) || H.sensor_energy) {
     // d->energy is part of mj_inverse's output contract when mjENBL_ENERGY is set (engine_inverse.c:210-223)
     ok = ok && devAlloc(d, &o.energy, (size_t)2 * S, "cudaMalloc(energy)");
     setField(d, mjbF_ENERGY, o.energy, 2, 0);

@@ -1716,12 +1716,6 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     if (e != cudaSuccess) return e;
     ++*launches;
   }
-  if (args.out.sensordata && !args.skip_sensors) {
-    e = in_smem ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
-                : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
-    if (e != cudaSuccess) return e;
-    ++*launches;
-  }
   if (args.out.actuator_length) {
     e = in_smem ? launch_phase(transmission_kernel<true>, args, smem, 8, stream)
                 : launch_phase(transmission_kernel<false>, args, 0, 8, stream);
@@ -1731,6 +1725,13 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   if (args.out.cam_xpos) {
     e = in_smem ? launch_phase(camlight_kernel<true>, args, smem, 8, stream)
                 : launch_phase(camlight_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  // sensors last: they read the energies, the camera poses and the transmission outputs
+  if (args.out.sensordata && !args.skip_sensors) {
+    e = in_smem ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
+                : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }

@@ -153,7 +153,8 @@
   X(cand_num)         /* ncand*MJB_CAND_NN, see MJB_CN_* */ \
   X(scan_bound)       /* ncand: MJB_CN_RBOUND of every candidate, contiguous (the scan reads nothing else) */ \
   X(scan_misc)        /* 1: largest contact margin of any candidate (tree-level culling) */ \
-  X(sensor_cutoff)    /* nsensor */
+  X(sensor_cutoff)    /* nsensor */ \
+  X(cam_proj)         /* ncam*4: fx, fy, half width, half height in pixels (cam_project, engine_sensor.c:126-215) */
 
 enum {
 #define X(name, rows) MJB_I_##name,
@@ -214,14 +215,14 @@ enum { MJB_SEN_TYPE = 0, MJB_SEN_DATATYPE, MJB_SEN_OBJTYPE, MJB_SEN_OBJID, MJB_S
        MJB_SEN_DIM, MJB_SEN_ADR, MJB_SEN_NI };
 // mjtSensor / mjtObj / mjtDataType values restated (include/mujoco/mjmodel.h)
 enum { MJB_SENS_TOUCH = 0, MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
-       MJB_SENS_TORQUE = 5, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
-       MJB_SENS_TENDONVEL = 12, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_JOINTLIMITPOS = 19,
+       MJB_SENS_TORQUE = 5, MJB_SENS_MAGNETOMETER = 6, MJB_SENS_CAMPROJECTION = 8, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
+       MJB_SENS_TENDONVEL = 12, MJB_SENS_ACTUATORPOS = 13, MJB_SENS_ACTUATORVEL = 14, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_JOINTLIMITPOS = 19,
        MJB_SENS_JOINTLIMITVEL = 20, MJB_SENS_JOINTLIMITFRC = 21, MJB_SENS_TENDONLIMITPOS = 22,
        MJB_SENS_TENDONLIMITVEL = 23, MJB_SENS_TENDONLIMITFRC = 24, MJB_SENS_FRAMEPOS = 25,
        MJB_SENS_FRAMEQUAT = 26, MJB_SENS_FRAMEXAXIS = 27, MJB_SENS_FRAMEYAXIS = 28, MJB_SENS_FRAMEZAXIS = 29,
        MJB_SENS_FRAMELINVEL = 30, MJB_SENS_FRAMEANGVEL = 31, MJB_SENS_FRAMELINACC = 32,
        MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34, MJB_SENS_SUBTREELINVEL = 35,
-       MJB_SENS_SUBTREEANGMOM = 36 };
+       MJB_SENS_SUBTREEANGMOM = 36, MJB_SENS_E_POTENTIAL = 40, MJB_SENS_E_KINETIC = 41, MJB_SENS_CLOCK = 42 };
 enum { MJB_OBJ_BODY = 1, MJB_OBJ_XBODY = 2, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6 };
 enum { MJB_DATATYPE_REAL = 0, MJB_DATATYPE_POSITIVE = 1 };
 
@@ -323,10 +324,14 @@ typedef struct mjbHdr_ {
   int32_t ncam, nlight;     // cameras / lights (mj_camlight outputs, mjbOUT_CAMLIGHT)
   int32_t nu;               // actuators (mj_transmission outputs, mjbOUT_TRANSMISSION)
   int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
+  int32_t sensor_cam;        // some camprojection sensor reads cam_xpos / cam_xmat (mj_camlight runs for it)
+  int32_t sensor_trn;        // some actuatorpos / actuatorvel sensor reads mj_transmission's outputs
+  int32_t sensor_energy;     // some potential / kinetic energy sensor (mj_energyPos / mj_energyVel run for it)
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
   int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)
   double timestep, impratio;
   double gravity[3];
+  double magnetic[3];        // opt.magnetic (magnetometer sensors)
   int32_t nrun;             // runs of the candidate list for the tree-level broadphase (0: flat scan)
   int32_t ntree;            // kinematic trees with collidable geoms
   int32_t ioff[MJB_NI];     // element offsets into the int section

@@ -3555,6 +3555,30 @@ MJB_HD inline bool limit_row_readings(const double* sp, const double* range, dou
   return false;
 }
 
+// cam_project (engine_sensor.c:126-215): pixel coordinates of a world point, through the product of
+// the image, focal, rotation and translation matrices accumulated in the reference's loop order
+MJB_HD inline void cam_project(double* px, const double* target, const double* cam_xpos, const double* cam_xmat,
+                               const double* prj) {
+  double translation[4][4] = {{1, 0, 0, -cam_xpos[0]}, {0, 1, 0, -cam_xpos[1]}, {0, 0, 1, -cam_xpos[2]}, {0, 0, 0, 1}};
+  double rotation[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 1}};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rotation[i][j] = cam_xmat[j*3 + i];
+  const double focal[3][4] = {{-prj[0], 0, 0, 0}, {0, prj[1], 0, 0}, {0, 0, 1.0, 0}};
+  const double image[3][3] = {{1, 0, prj[2]}, {0, 1, prj[3]}, {0, 0, 1}};
+  double proj[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < 4; k++)
+        for (int l = 0; l < 4; l++)
+          for (int n = 0; n < 4; n++) proj[i][n] += image[i][j] * focal[j][k] * rotation[k][l] * translation[l][n];
+  const double hom[4] = {target[0], target[1], target[2], 1};
+  double pix[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) pix[i] += proj[i][j] * hom[j];
+  double denom = pix[2];
+  if (fabs(denom) < MJB_MINVAL) denom = denom < 0 ? fmin(denom, -MJB_MINVAL) : fmax(denom, MJB_MINVAL);
+  px[0] = pix[0] / denom;
+  px[1] = pix[1] / denom;
+}
+
 MJB_HD inline void sensors(Ctx& c) {
   const mjbHdr& H = *c.H;
   const size_t N = (size_t)c.N;
@@ -3601,6 +3625,30 @@ MJB_HD inline void sensors(Ctx& c) {
         if (ray_geom(pos, m, MD(site_size) + 3*objid, p, ray, MI(site_type)[objid]) >= 0) total += fn;
       }
       v[0] = total;
+    } else if (type == MJB_SENS_MAGNETOMETER) {
+      // opt.magnetic in the site frame (engine_sensor.c:254-257)
+      double pos[3], quat[4], m[9];
+      sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      quat2Mat(m, quat);
+      mulMatTVec3(v, m, H.magnetic);
+    } else if (type == MJB_SENS_CAMPROJECTION) {
+      // site position in the image of camera refid (engine_sensor.c:259-264); the camera pose is
+      // mj_camlight's output (mjb_makeData adds mjbOUT_CAMLIGHT for these sensors)
+      double pos[3], quat[4], cp[3], cm[9];
+      sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      for (int k = 0; k < 3; k++) cp[k] = c.out.cam_xpos[(size_t)(3*refid + k)*N + c.s];
+      for (int k = 0; k < 9; k++) cm[k] = c.out.cam_xmat[(size_t)(9*refid + k)*N + c.s];
+      cam_project(v, pos, cp, cm, MD(cam_proj) + 4*refid);
+    } else if (type == MJB_SENS_ACTUATORPOS) {
+      v[0] = c.out.actuator_length[(size_t)objid*N + c.s];
+    } else if (type == MJB_SENS_ACTUATORVEL) {
+      v[0] = c.out.actuator_velocity[(size_t)objid*N + c.s];
+    } else if (type == MJB_SENS_E_POTENTIAL) {
+      v[0] = c.out.energy[c.s];
+    } else if (type == MJB_SENS_E_KINETIC) {
+      v[0] = c.out.energy[N + c.s];
+    } else if (type == MJB_SENS_CLOCK) {
+      v[0] = 0;       // d->time is not part of the batched state: 0, as after mj_resetData
     } else if (type == MJB_SENS_JOINTPOS) {
       v[0] = QPOS(MI(jnt_qposadr)[objid]);
     } else if (type == MJB_SENS_JOINTVEL) {
@@ -4612,10 +4660,10 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
   if (c.out.qfrc_bias) bias_forces(c);
   if (c.out.energy) energy(c);
-  if (c.out.sensordata) sensors(c);
-  if (c.out.fwdinv) compare_fwdinv(c);
   if (c.out.cam_xpos) camlight(c);
   if (c.out.actuator_length) transmission(c);
+  if (c.out.sensordata) sensors(c);
+  if (c.out.fwdinv) compare_fwdinv(c);
 }
 
 #undef MI

@@ -220,6 +220,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // magnetometer, camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
   bool sensor_post = false, sensor_subtreevel = false, sensor_touch = false;
+  bool sensor_cam = false, sensor_trn = false, sensor_energy = false;
   std::vector<int> sensor_int;
   std::vector<double> sensor_cutoff;
   for (int i = 0; i < m->nsensor && sensors; i++) {
@@ -246,8 +247,16 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
           for (int j = 0; j < m->tendon_num[tid]; j++) ok = ok && m->wrap_type[m->tendon_adr[tid] + j] == mjWRAP_JOINT;
         }
         break;
-      case mjSENS_VELOCIMETER: case mjSENS_GYRO:
+      case mjSENS_VELOCIMETER: case mjSENS_GYRO: case mjSENS_MAGNETOMETER:
         ok = true; break;
+      case mjSENS_CLOCK:          // d->time is not a batched input: 0, as after mj_resetData
+        ok = true; break;
+      case mjSENS_CAMPROJECTION:
+        ok = true; sensor_cam = true; break;
+      case mjSENS_ACTUATORPOS: case mjSENS_ACTUATORVEL:
+        ok = m->actuator_trntype[m->sensor_objid[i]] != mjTRN_BODY; sensor_trn = true; break;
+      case mjSENS_E_POTENTIAL: case mjSENS_E_KINETIC:
+        ok = true; sensor_energy = true; break;
       case mjSENS_TOUCH:
         {
           const int st = m->site_type[m->sensor_objid[i]];
@@ -739,6 +748,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nu = m->nu;
   H.sensor_subtreevel = sensor_subtreevel ? 1 : 0;
   H.sensor_touch = sensor_touch ? 1 : 0;
+  H.sensor_cam = sensor_cam ? 1 : 0; H.sensor_trn = sensor_trn ? 1 : 0; H.sensor_energy = sensor_energy ? 1 : 0;
+  for (int i = 0; i < 3; i++) H.magnetic[i] = m->opt.magnetic[i];
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
 
@@ -873,6 +884,26 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_scan_bound, scan_bound.data(), scan_bound.size());
   pushNums(MJB_N_scan_misc, scan_misc.data(), scan_misc.size());
   pushNums(MJB_N_sensor_cutoff, sensor_cutoff.data(), sensor_cutoff.size());
+  {
+    // focal lengths in pixels exactly as cam_project forms them (engine_sensor.c:155-160: float
+    // arithmetic for the intrinsic form, the host's tan for the field-of-view form)
+    std::vector<double> cam_proj((size_t)4 * m->ncam);
+    for (int i = 0; i < m->ncam; i++) {
+      const float* cam_intrinsic = m->cam_intrinsic + 4*i;
+      const float* cam_sensorsize = m->cam_sensorsize + 2*i;
+      const int* cam_res = m->cam_resolution + 2*i;
+      mjtNum fx, fy;
+      if (cam_sensorsize[0] && cam_sensorsize[1]) {
+        fx = cam_intrinsic[0] / cam_sensorsize[0] * cam_res[0];
+        fy = cam_intrinsic[1] / cam_sensorsize[1] * cam_res[1];
+      } else {
+        fx = fy = .5 / std::tan(m->cam_fovy[i] * mjPI / 360.) * cam_res[1];
+      }
+      cam_proj[4*i] = fx; cam_proj[4*i + 1] = fy;
+      cam_proj[4*i + 2] = (mjtNum)cam_res[0] / 2.0; cam_proj[4*i + 3] = (mjtNum)cam_res[1] / 2.0;
+    }
+    pushNums(MJB_N_cam_proj, cam_proj.data(), cam_proj.size());
+  }
 
   // scratch layout
   {

@@ -62,6 +62,8 @@ CASES = {
     "tendons_energy": ("repo:tests/golden/models/tendons.xml", {"enableflags": 1 << 1}, 128, (0.3, 1.3), 8, 32),
     # cameras and lights in every mjtCamLight mode (outputs of mj_camlight: CAMLIGHT_CASES)
     "camlight": ("repo:tests/golden/models/camlight.xml", {}, 128, (0.2, 1.2), 16, 64),
+    # sensors that read mj_camlight / mj_transmission outputs, magnetometer, clock
+    "sensors2": ("repo:tests/golden/models/sensors2.xml", {}, 256, (0.2, 1.2), 16, 64),
     # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)
     "transmission": ("repo:tests/golden/models/transmission.xml", {}, 128, (0.2, 1.2), 16, 64),
 }

@@ -77,8 +77,12 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         a["mocap_quat"] = np.ascontiguousarray(mocap[1].reshape(n, -1).T, dtype=np.float64)
     if has_sensors:
         a["sensordata"] = np.zeros((model.int("nsensordata"), n))
-    if model.get_opt_int("enableflags") & (1 << 1):     # mjENBL_ENERGY
+    stypes = set(model.array("sensor_type").ravel().tolist()) if has_sensors else set()
+    if (model.get_opt_int("enableflags") & (1 << 1)) or (stypes & {40, 41}):     # mjENBL_ENERGY / energy sensors
         a["energy"] = np.zeros((2, n))
+    # what mjb_makeData adds for sensors that read mj_camlight / mj_transmission outputs
+    camlight = camlight or 8 in stypes
+    transmission = transmission or bool(stypes & {13, 14})
     if camlight:            # mj_camlight outputs (mjbOUT_CAMLIGHT)
         nc, nl = max(1, model.int("ncam")), max(1, model.int("nlight"))
         a.update(cam_xpos=np.zeros((3 * nc, n)), cam_xmat=np.zeros((9 * nc, n)),

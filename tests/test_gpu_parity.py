@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission"]
+         "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -258,6 +258,20 @@ def test_golden_sensordata():
     np.testing.assert_array_equal(bd.sensordata(), got)
     bd.inverse_skip(0, 0)
     np.testing.assert_array_equal(bd.sensordata(), got[::-1])
+
+
+def test_golden_sensordata_camlight_transmission_energy():
+    """Sensors that read other output-only stages: camprojection (mj_camlight poses, cam_project:
+    engine_sensor.c:126-215), actuatorpos / actuatorvel (mj_transmission), e_potential / e_kinetic
+    (mj_energyPos / mj_energyVel), magnetometer, clock; mjb_makeData adds the stages they need."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "sensors2", True, 0)
+    assert nbad == 0
+    nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    # the stages came with the sensors
+    assert np.isfinite(bd.camlight()["cam_xmat"]).all()
+    assert np.isfinite(bd.transmission()["actuator_moment"]).all()
 
 
 def test_rne_post_constraint_newton_euler_balance():
