@@ -755,11 +755,24 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 
   std::vector<int> ints;
   std::vector<double> nums;
+  // Every table starts on a 16-byte boundary; the tables whose records the contact kernels gather
+  // per candidate / per item (32-byte integer records, scan rows) start on a 128-byte line, so that
+  // the sector alignment of a record does not depend on which other tables a model happens to have
+  // (both sections start on 128-byte boundaries of the blob, see below).
+  auto hotInt = [](int id) {
+    return id == MJB_I_cand_int || id == MJB_I_scan_int || id == MJB_I_scan_run || id == MJB_I_eq_int ||
+           id == MJB_I_tree_int || id == MJB_I_sensor_int;
+  };
+  auto hotNum = [](int id) { return id == MJB_N_cand_num || id == MJB_N_scan_bound || id == MJB_N_eq_num; };
   auto pushInts = [&](int id, const int* src, size_t n) {
+    const size_t al = hotInt(id) ? 32 : 4;
+    ints.resize((ints.size() + al - 1) / al * al, 0);
     H.ioff[id] = (int)ints.size();
     ints.insert(ints.end(), src, src + n);
   };
   auto pushNums = [&](int id, const double* src, size_t n) {
+    const size_t al = hotNum(id) ? 16 : 2;
+    nums.resize((nums.size() + al - 1) / al * al, 0.0);
     H.noff[id] = (int)nums.size();
     nums.insert(nums.end(), src, src + n);
   };
@@ -930,8 +943,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     H.nscratch = off;
   }
 
-  const size_t hdr_bytes = (sizeof(mjbHdr) + 15) & ~(size_t)15;
-  const size_t int_bytes = (ints.size()*sizeof(int) + 15) & ~(size_t)15;
+  const size_t hdr_bytes = (sizeof(mjbHdr) + 127) & ~(size_t)127;
+  const size_t int_bytes = (ints.size()*sizeof(int) + 127) & ~(size_t)127;
   const size_t num_bytes = (nums.size()*sizeof(double) + 15) & ~(size_t)15;
   H.int_section = (int)hdr_bytes;
   H.num_section = (int)(hdr_bytes + int_bytes);
