@@ -211,6 +211,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     if (H0->sensor_touch) outmask |= mjbOUT_COUNTS | mjbOUT_CONTACT | mjbOUT_EFC;
     if (H0->sensor_cam) outmask |= mjbOUT_CAMLIGHT;           // camprojection sensors read the camera poses
     if (H0->sensor_trn) outmask |= mjbOUT_TRANSMISSION;       // actuatorpos / actuatorvel sensors
+    if (H0->discrete_trn) outmask |= mjbOUT_TRANSMISSION;     // implicitfast mj_discreteAcc reads the moment rows
   }
   if (outmask & mjbOUT_RNEPOST) {
     // constraint forces of spatial tendons travel as body wrenches here but are not part of the

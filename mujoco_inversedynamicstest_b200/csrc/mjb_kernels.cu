@@ -1578,6 +1578,13 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     { PhaseScope ps(timer, stream, kPhaseInertia);
     e = run_phase(st_inertia, nullptr, pre, stream, launches, generic_inertia); }
     if (e != cudaSuccess) return e;
+    if (args.out.actuator_length) {
+      // implicitfast with velocity-biased actuators: mjd_actuator_vel reads actuator_moment
+      e = in_smem ? launch_phase(transmission_kernel<true>, pre, smem, 8, stream)
+                  : launch_phase(transmission_kernel<false>, pre, 0, 8, stream);
+      if (e != cudaSuccess) return e;
+      *launches += 1;
+    }
     { PhaseScope ps(timer, stream, kPhaseDiscrete);
     e = in_smem ? launch_phase(discrete_acc_kernel<true>, args, smem, 8, stream)
                 : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream); }

@@ -154,6 +154,7 @@
   X(scan_bound)       /* ncand: MJB_CN_RBOUND of every candidate, contiguous (the scan reads nothing else) */ \
   X(scan_misc)        /* 1: largest contact margin of any candidate (tree-level culling) */ \
   X(sensor_cutoff)    /* nsensor */ \
+  X(act_biasvel)      /* nu: d force / d velocity of the actuator's affine bias (implicitfast mjENBL_INVDISCRETE) */ \
   X(cam_proj)         /* ncam*4: fx, fy, half width, half height in pixels (cam_project, engine_sensor.c:126-215) */
 
 enum {
@@ -315,7 +316,8 @@ typedef struct mjbHdr_ {
   int32_t ne_rows, nf_dof_rows, nf_rows;
   int32_t has_spatial;      // some spatial tendon carries a force (its path is walked on the device)
   int32_t passive_wrench;   // the passive body-wrench carrier exists (gravcomp or spatial-tendon springs/dampers)
-  int32_t discrete_acc;     // mjENBL_INVDISCRETE with Euler and damped dofs: qacc is converted first
+  int32_t discrete_acc;     // mjENBL_INVDISCRETE: qacc is converted first; 1 Euler with damped dofs, 2 implicitfast
+  int32_t discrete_trn;     // implicitfast with velocity-biased actuators: the conversion reads actuator_moment
   int32_t nsensor;          // sensors evaluated on the device (0 with mjDSBL_SENSOR), nsensordata their rows
   int32_t nsensordata;
   int32_t sensor_post;      // some sensor reads cacc / cfrc_int (mj_rnePostConstraint, engine_sensor.c:727-740)

@@ -4439,7 +4439,59 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
   const double* damping = MD(dof_damping);
   const double* qLD = c.out.qLD + c.s; const double* qLDiagInv = c.out.qLDiagInv + c.s;
   double* x = SC(qfrc_c);                 // free at this point: the smooth phase is rerun afterwards
-  for (int i = 0; i < nv; i++) AT(x, i) = H.timestep * damping[i] * QACC(i);
+  const bool fast = H.discrete_acc == 2;
+  // x = -h * qDeriv * qacc. Euler: qDeriv = -diag(damping) (engine_inverse.c:111-116). implicitfast
+  // (:133-152): qDeriv = sum_actuators bias_vel * m'm  -  diag(damping)  -  sum_tendons damping * J'J
+  // (mjd_actuator_vel, mjd_passive_vel) on M's sparsity pattern, i.e. an entry (a, b) of a product
+  // J'J exists only when one of the two dofs is an ancestor of the other (or a == b)
+  const bool damp = !fast || !(H.disableflags & MJB_DSBL_PASSIVE);
+  for (int i = 0; i < nv; i++) AT(x, i) = damp ? H.timestep * damping[i] * QACC(i) : 0.0;
+  if (fast) {
+    const int* dof_parentid = MI(dof_parentid);
+    // mj_mulM multiplies with the modified M (engine_support.c:966-1020): the off-diagonal entries of
+    // a "simple" dof's row are not visited
+    auto related = [&](int a, int b) {
+      int lo = a < b ? a : b, hi = a < b ? b : a;
+      if (hi != lo && simplenum[hi]) return false;
+      while (hi > lo) hi = dof_parentid[hi];
+      return hi == lo;
+    };
+    if (!(H.disableflags & MJB_DSBL_PASSIVE)) {
+      const int* tendon_adr = MI(tendon_adr); const int* tendon_num = MI(tendon_num);
+      const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
+      const double* wrap_prm = MD(wrap_prm); const double* tdamp = MD(tendon_damping);
+      for (int t = 0; t < H.ntendon; t++) {
+        if (!(tdamp[t] > 0)) continue;
+        const int adr = tendon_adr[t], num = tendon_num[t];
+        for (int k = 0; k < num; k++) {
+          const int a = jnt_dofadr[wrap_objid[adr + k]];
+          double s = 0;
+          for (int l = 0; l < num; l++) {
+            const int b = jnt_dofadr[wrap_objid[adr + l]];
+            if (related(a, b)) s += wrap_prm[adr + l] * QACC(b);
+          }
+          AT(x, a) += H.timestep * tdamp[t] * wrap_prm[adr + k] * s;
+        }
+      }
+    }
+    if (H.discrete_trn) {
+      const double* bv = MD(act_biasvel);
+      for (int u = 0; u < H.nu; u++) {
+        if (bv[u] == 0) continue;
+        const double* row = c.out.actuator_moment + (size_t)u*nv*N + c.s;
+        for (int a = 0; a < nv; a++) {
+          const double ra = row[(size_t)a*N];
+          if (ra == 0) continue;
+          double s = 0;
+          for (int b = 0; b < nv; b++) {
+            const double rb = row[(size_t)b*N];
+            if (rb != 0 && related(a, b)) s += rb * QACC(b);
+          }
+          AT(x, a) -= H.timestep * bv[u] * ra * s;
+        }
+      }
+    }
+  }
   // x <- L^-T x
   for (int i = nv - 1; i > 0; i--) {
     if (simplenum[i]) continue;
@@ -4649,6 +4701,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   if (c.out.qM || c.out.qLD || c.out.qLDiagInv) phase_inertia(c);
   if (c.H->discrete_acc) {
     // converted accelerations replace qacc for everything that follows (engine_inverse.c:227-252)
+    if (c.H->discrete_trn) transmission(c);
     discrete_acc(c, qacc_discrete + c.s);
     c.qacc = qacc_discrete + c.s;
     phase_smooth<true>(c);

@@ -202,17 +202,57 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // gravity compensation (engine_passive.c:381-401) runs iff this holds
   const bool gravcomp = !(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
       (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0);
-  // mjENBL_INVDISCRETE (mj_discreteAcc, engine_inverse.c:81-164): Euler is supported; RK4 is an
-  // error in the reference too, the implicit integrators need mjd_smooth_vel
-  bool discrete = false;
+  // mjENBL_INVDISCRETE (mj_discreteAcc, engine_inverse.c:81-164): Euler (1) and implicitfast (2) are
+  // supported; RK4 is an error in the reference too; implicit needs the Coriolis derivative mjd_rne_vel
+  int discrete = 0;
+  std::vector<double> act_biasvel(m->nu, 0.0);     // d force / d velocity of every actuator (mjd_actuator_vel)
+  bool discrete_trn = false;
   if (enbl & mjENBL_INVDISCRETE) {
-    if (m->opt.integrator != mjINT_EULER) {
-      err = "mjENBL_INVDISCRETE is supported with the Euler integrator only (RK4 is an error in "
-            "the reference, implicit/implicitfast need mjd_smooth_vel)";
+    if (m->opt.integrator == mjINT_RK4) {
+      err = "mjENBL_INVDISCRETE: discrete inverse dynamics is not supported by RK4 (an error in the reference too)";
       return false;
     }
-    if (!(dsbl & mjDSBL_EULERDAMP)) {
-      for (int i = 0; i < m->nv; i++) discrete = discrete || m->dof_damping[i] > 0;
+    if (m->opt.integrator == mjINT_IMPLICIT) {
+      err = "mjENBL_INVDISCRETE is supported with the Euler and implicitfast integrators (implicit needs mjd_rne_vel)";
+      return false;
+    }
+    if (m->opt.integrator == mjINT_EULER) {
+      if (!(dsbl & mjDSBL_EULERDAMP)) {
+        for (int i = 0; i < m->nv; i++) discrete = (discrete || m->dof_damping[i] > 0) ? 1 : 0;
+      }
+    } else {
+      // implicitfast: qfrc = (M - h*qDeriv) qacc with qDeriv = mjd_actuator_vel + mjd_passive_vel
+      // (engine_derivative.c:812-872, 1432-1505) restricted to M's sparsity
+      discrete = 2;
+      if (!(dsbl & mjDSBL_ACTUATION)) {
+        for (int i = 0; i < m->nu; i++) {
+          const int group = m->actuator_group[i];
+          if (group >= 0 && group <= 30 && (m->opt.disableactuator & (1 << group))) continue;
+          double gain_vel = 0;
+          if (m->actuator_gaintype[i] == mjGAIN_AFFINE) gain_vel = m->actuator_gainprm[mjNGAIN*i + 2];
+          if (m->actuator_gaintype[i] == mjGAIN_MUSCLE || gain_vel != 0) {
+            setError(err, "mjENBL_INVDISCRETE with implicitfast: actuator %d has a velocity-dependent gain "
+                     "(needs ctrl / act, which are not inputs of the batched inverse)", i);
+            return false;
+          }
+          if (m->actuator_biastype[i] == mjBIAS_AFFINE) act_biasvel[i] = m->actuator_biasprm[mjNBIAS*i + 2];
+          if (act_biasvel[i] != 0) {
+            if (m->actuator_trntype[i] == mjTRN_BODY) {
+              setError(err, "mjENBL_INVDISCRETE with implicitfast: adhesion actuator %d has a velocity bias", i);
+              return false;
+            }
+            discrete_trn = true;
+          }
+        }
+      }
+      if (!(dsbl & mjDSBL_PASSIVE)) {
+        for (int t = 0; t < m->ntendon; t++) {
+          if (m->tendon_damping[t] > 0 && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) {
+            setError(err, "mjENBL_INVDISCRETE with implicitfast: damped spatial tendon %d (its Jacobian row is not formed)", t);
+            return false;
+          }
+        }
+      }
     }
   }
   // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
@@ -738,7 +778,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.has_gravcomp = gravcomp ? 1 : 0;
   H.passive_wrench = (gravcomp || spatial_passive) ? 1 : 0;
   H.has_spatial = spatial_active ? 1 : 0;
-  H.discrete_acc = discrete ? 1 : 0;
+  H.discrete_acc = discrete;
+  H.discrete_trn = discrete_trn ? 1 : 0;
   H.nsensor = sensors ? m->nsensor : 0;
   H.nsensordata = sensors ? m->nsensordata : 0;
   H.sensor_post = sensor_post ? 1 : 0;
@@ -897,6 +938,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_scan_bound, scan_bound.data(), scan_bound.size());
   pushNums(MJB_N_scan_misc, scan_misc.data(), scan_misc.size());
   pushNums(MJB_N_sensor_cutoff, sensor_cutoff.data(), sensor_cutoff.size());
+  pushNums(MJB_N_act_biasvel, act_biasvel.data(), act_biasvel.size());
   {
     // focal lengths in pixels exactly as cam_project forms them (engine_sensor.c:155-160: float
     // arithmetic for the intrinsic form, the host's tan for the field-of-view form)

@@ -62,6 +62,10 @@ CASES = {
     "tendons_energy": ("repo:tests/golden/models/tendons.xml", {"enableflags": 1 << 1}, 128, (0.3, 1.3), 8, 32),
     # cameras and lights in every mjtCamLight mode (outputs of mj_camlight: CAMLIGHT_CASES)
     "camlight": ("repo:tests/golden/models/camlight.xml", {}, 128, (0.2, 1.2), 16, 64),
+    # mjENBL_INVDISCRETE with the implicitfast integrator (mj_discreteAcc + mjd_actuator_vel / mjd_passive_vel)
+    "humanoid_invdiscrete_fast": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 3, "integrator": 3}, 128,
+                                  (0.0, 1.5), 64, 256),
+    "implicitfast": ("repo:tests/golden/models/implicitfast.xml", {}, 128, (0.2, 1.2), 16, 64),
     # sensors that read mj_camlight / mj_transmission outputs, magnetometer, clock
     "sensors2": ("repo:tests/golden/models/sensors2.xml", {}, 256, (0.2, 1.2), 16, 64),
     # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)
