@@ -316,7 +316,7 @@ typedef struct mjbHdr_ {
   int32_t ne_rows, nf_dof_rows, nf_rows;
   int32_t has_spatial;      // some spatial tendon carries a force (its path is walked on the device)
   int32_t passive_wrench;   // the passive body-wrench carrier exists (gravcomp or spatial-tendon springs/dampers)
-  int32_t discrete_acc;     // mjENBL_INVDISCRETE: qacc is converted first; 1 Euler with damped dofs, 2 implicitfast
+  int32_t discrete_acc;     // mjENBL_INVDISCRETE: qacc is converted first; 1 Euler with damped dofs, 2 implicitfast, 3 implicit
   int32_t discrete_trn;     // implicitfast with velocity-biased actuators: the conversion reads actuator_moment
   int32_t nsensor;          // sensors evaluated on the device (0 with mjDSBL_SENSOR), nsensordata their rows
   int32_t nsensordata;

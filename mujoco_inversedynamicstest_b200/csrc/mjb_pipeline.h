@@ -4424,12 +4424,80 @@ MJB_HD inline void inertia(Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_discreteAcc for the Euler integrator (engine_inverse.c:81-164): the discrete-time qacc is
-// converted to the continuous-time one the rest of mj_inverse works with,
+// mj_discreteAcc (engine_inverse.c:81-164): the discrete-time qacc is converted to the
+// continuous-time one the rest of mj_inverse works with. Euler:
 //     qacc' = M^-1 (M + h diag(B)) qacc = qacc + h M^-1 (B .* qacc),
+// implicitfast / implicit: qacc' = qacc - h M^-1 (qDeriv qacc) with the analytic qDeriv (below),
 // using the L'DL factors of the inertia kernel. mj_solveLD (engine_core_smooth.c:1629-1707) on the
 // reduced row layout of qLD (row i: ancestors ascending, diagonal last). The reference forms
 // (M + hB) qacc with mj_mulM and solves; the two agree to rounding (cond(M) * eps).
+// Gravity-free bias force of the velocity field w = sv*qvel + sa*qacc: mj_comVel + mj_rne(flg_acc = 0)
+// (engine_core_smooth.c:1833-1895, 1969-2023) restated on the cdof / cinert rows of the scratch, with
+// the per-body cvel, cacc and force in the ia rows (18 of the 21 doubles per body). The result is
+// ADDED to dst with the factor scale. The function is exactly quadratic in w, which is what the
+// implicit integrator's mjd_rne_vel term is built from (discrete_acc below).
+MJB_HD inline void coriolis_add(Ctx& c, double sv, double sa, double scale, double* dst) {
+  const mjbHdr& H = *c.H;
+  const int* body_parentid = MI(body_parentid); const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum); const int* dof_jntid = MI(dof_jntid); const int* jnt_type = MI(jnt_type);
+  const int* dof_bodyid = MI(dof_bodyid);
+  double* t = SC(ia);
+  const double zero[18] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  stn(t, 0, zero, 18);
+  for (int i = 1; i < H.nbody; i++) {
+    double w[18], ci[10], tmp[6], tmp1[6];
+    ldn(w, t, 18*body_parentid[i], 12);
+    double* cvel = w; double* cacc = w + 6; double* f = w + 12;
+    const int bda = body_dofadr[i], dofnum = body_dofnum[i];
+    for (int j = 0; j < dofnum; j++) {
+      const int jt = jnt_type[dof_jntid[bda + j]];
+      int first = j, count = 1;
+      if (jt == MJB_JNT_FREE) {
+        // translational dofs: no cdof_dot, the velocity is added first
+        for (int k = 0; k < 3; k++) {
+          double cd[6];
+          ldn(cd, SC(cdof), 6*(bda + k), 6);
+          const double wj = sv*QVEL(bda + k) + sa*QACC(bda + k);
+          for (int r = 0; r < 6; r++) cvel[r] += cd[r]*wj;
+        }
+        first = j + 3; count = 3;
+      } else if (jt == MJB_JNT_BALL) {
+        count = 3;
+      }
+      // cdof_dot of the group from the velocity before the group, then the group's velocity
+      double add[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < count; k++) {
+        double cd[6], cdd[6];
+        ldn(cd, SC(cdof), 6*(bda + first + k), 6);
+        const double wj = sv*QVEL(bda + first + k) + sa*QACC(bda + first + k);
+        crossMotion(cdd, cvel, cd);
+        for (int r = 0; r < 6; r++) { cacc[r] += cdd[r]*wj; add[r] += cd[r]*wj; }
+      }
+      for (int r = 0; r < 6; r++) cvel[r] += add[r];
+      j = first + count - 1;
+    }
+    ldn(ci, SC(cinert), 10*i, 10);
+    mulInertVec(f, ci, cacc);
+    mulInertVec(tmp, ci, cvel);
+    crossForce(tmp1, cvel, tmp);
+    for (int r = 0; r < 6; r++) f[r] += tmp1[r];
+    stn(t, 18*i, w, 18);
+  }
+  for (int i = H.nbody - 1; i > 0; i--) {
+    const int p = body_parentid[i];
+    if (!p) continue;
+    double f[6], pf[6];
+    ldn(f, t, 18*i + 12, 6); ldn(pf, t, 18*p + 12, 6);
+    for (int r = 0; r < 6; r++) pf[r] += f[r];
+    stn(t, 18*p + 12, pf, 6);
+  }
+  for (int j = 0; j < H.nv; j++) {
+    double cd[6], f[6];
+    ldn(cd, SC(cdof), 6*j, 6); ldn(f, t, 18*dof_bodyid[j] + 12, 6);
+    AT(dst, j) += scale*dot6(cd, f);
+  }
+}
+
 MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
   const mjbHdr& H = *c.H;
   const int nv = H.nv;
@@ -4439,7 +4507,8 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
   const double* damping = MD(dof_damping);
   const double* qLD = c.out.qLD + c.s; const double* qLDiagInv = c.out.qLDiagInv + c.s;
   double* x = SC(qfrc_c);                 // free at this point: the smooth phase is rerun afterwards
-  const bool fast = H.discrete_acc == 2;
+  const bool fast = H.discrete_acc >= 2;        // implicitfast (2) or implicit (3)
+  const bool full = H.discrete_acc == 3;
   // x = -h * qDeriv * qacc. Euler: qDeriv = -diag(damping) (engine_inverse.c:111-116). implicitfast
   // (:133-152): qDeriv = sum_actuators bias_vel * m'm  -  diag(damping)  -  sum_tendons damping * J'J
   // (mjd_actuator_vel, mjd_passive_vel) on M's sparsity pattern, i.e. an entry (a, b) of a product
@@ -4452,7 +4521,7 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
     // a "simple" dof's row are not visited
     auto related = [&](int a, int b) {
       int lo = a < b ? a : b, hi = a < b ? b : a;
-      if (hi != lo && simplenum[hi]) return false;
+      if (!full && hi != lo && simplenum[hi]) return false;
       while (hi > lo) hi = dof_parentid[hi];
       return hi == lo;
     };
@@ -4473,6 +4542,18 @@ MJB_HD inline void discrete_acc(Ctx& c, double* qacc_out) {
           AT(x, a) += H.timestep * tdamp[t] * wrap_prm[adr + k] * s;
         }
       }
+    }
+    if (full) {
+      // implicit (engine_inverse.c:120-131): qDeriv also carries -d qfrc_bias / d qvel (mjd_rne_vel,
+      // engine_derivative.c:604-686) and the product runs over the full dof-dof pattern. The bias force
+      // c(v) is exactly quadratic in v, so its derivative along qacc is the polarisation
+      //   (dc/dv) a = c(v + a) - c(v) - c(a)      (gravity excluded: constant in v)
+      double* r = SC(qfrc_passive);        // free here as well: recomputed by the second smooth pass
+      for (int i = 0; i < nv; i++) AT(r, i) = 0;
+      coriolis_add(c, 1.0, 1.0, 1.0, r);
+      coriolis_add(c, 1.0, 0.0, -1.0, r);
+      coriolis_add(c, 0.0, 1.0, -1.0, r);
+      for (int i = 0; i < nv; i++) AT(x, i) += H.timestep * AT(r, i);
     }
     if (H.discrete_trn) {
       const double* bv = MD(act_biasvel);

@@ -202,8 +202,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // gravity compensation (engine_passive.c:381-401) runs iff this holds
   const bool gravcomp = !(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
       (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0);
-  // mjENBL_INVDISCRETE (mj_discreteAcc, engine_inverse.c:81-164): Euler (1) and implicitfast (2) are
-  // supported; RK4 is an error in the reference too; implicit needs the Coriolis derivative mjd_rne_vel
+  // mjENBL_INVDISCRETE (mj_discreteAcc, engine_inverse.c:81-164): Euler (1), implicitfast (2) and
+  // implicit (3); RK4 is an error in the reference too
   int discrete = 0;
   std::vector<double> act_biasvel(m->nu, 0.0);     // d force / d velocity of every actuator (mjd_actuator_vel)
   bool discrete_trn = false;
@@ -212,18 +212,14 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       err = "mjENBL_INVDISCRETE: discrete inverse dynamics is not supported by RK4 (an error in the reference too)";
       return false;
     }
-    if (m->opt.integrator == mjINT_IMPLICIT) {
-      err = "mjENBL_INVDISCRETE is supported with the Euler and implicitfast integrators (implicit needs mjd_rne_vel)";
-      return false;
-    }
     if (m->opt.integrator == mjINT_EULER) {
       if (!(dsbl & mjDSBL_EULERDAMP)) {
         for (int i = 0; i < m->nv; i++) discrete = (discrete || m->dof_damping[i] > 0) ? 1 : 0;
       }
     } else {
       // implicitfast: qfrc = (M - h*qDeriv) qacc with qDeriv = mjd_actuator_vel + mjd_passive_vel
-      // (engine_derivative.c:812-872, 1432-1505) restricted to M's sparsity
-      discrete = 2;
+      // (engine_derivative.c:812-872, 1432-1505) restricted to M's sparsity; implicit adds mjd_rne_vel
+      discrete = m->opt.integrator == mjINT_IMPLICIT ? 3 : 2;
       if (!(dsbl & mjDSBL_ACTUATION)) {
         for (int i = 0; i < m->nu; i++) {
           const int group = m->actuator_group[i];
@@ -231,14 +227,14 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
           double gain_vel = 0;
           if (m->actuator_gaintype[i] == mjGAIN_AFFINE) gain_vel = m->actuator_gainprm[mjNGAIN*i + 2];
           if (m->actuator_gaintype[i] == mjGAIN_MUSCLE || gain_vel != 0) {
-            setError(err, "mjENBL_INVDISCRETE with implicitfast: actuator %d has a velocity-dependent gain "
+            setError(err, "mjENBL_INVDISCRETE with implicit / implicitfast: actuator %d has a velocity-dependent gain "
                      "(needs ctrl / act, which are not inputs of the batched inverse)", i);
             return false;
           }
           if (m->actuator_biastype[i] == mjBIAS_AFFINE) act_biasvel[i] = m->actuator_biasprm[mjNBIAS*i + 2];
           if (act_biasvel[i] != 0) {
             if (m->actuator_trntype[i] == mjTRN_BODY) {
-              setError(err, "mjENBL_INVDISCRETE with implicitfast: adhesion actuator %d has a velocity bias", i);
+              setError(err, "mjENBL_INVDISCRETE with implicit / implicitfast: adhesion actuator %d has a velocity bias", i);
               return false;
             }
             discrete_trn = true;
@@ -248,7 +244,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       if (!(dsbl & mjDSBL_PASSIVE)) {
         for (int t = 0; t < m->ntendon; t++) {
           if (m->tendon_damping[t] > 0 && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) {
-            setError(err, "mjENBL_INVDISCRETE with implicitfast: damped spatial tendon %d (its Jacobian row is not formed)", t);
+            setError(err, "mjENBL_INVDISCRETE with implicit / implicitfast: damped spatial tendon %d (its Jacobian row is not formed)", t);
             return false;
           }
         }

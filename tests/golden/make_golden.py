@@ -66,6 +66,10 @@ CASES = {
     "humanoid_invdiscrete_fast": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 3, "integrator": 3}, 128,
                                   (0.0, 1.5), 64, 256),
     "implicitfast": ("repo:tests/golden/models/implicitfast.xml", {}, 128, (0.2, 1.2), 16, 64),
+    # ... and with the implicit integrator (adds mjd_rne_vel, the full dof-dof pattern)
+    "humanoid_invdiscrete_implicit": ("model/humanoid/humanoid.xml", {"enableflags": 1 << 3, "integrator": 2}, 128,
+                                      (0.0, 1.5), 64, 256),
+    "implicit": ("repo:tests/golden/models/implicitfast.xml", {"integrator": 2}, 128, (0.2, 1.2), 16, 64),
     # sensors that read mj_camlight / mj_transmission outputs, magnetometer, clock
     "sensors2": ("repo:tests/golden/models/sensors2.xml", {}, 256, (0.2, 1.2), 16, 64),
     # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)

@@ -85,7 +85,7 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
     transmission = transmission or bool(stypes & {13, 14})
     # implicitfast mjENBL_INVDISCRETE with velocity-biased actuators reads the moment rows
     transmission = transmission or bool((model.get_opt_int("enableflags") & (1 << 3)) and
-                                        model.get_opt_int("integrator") == 3 and model.int("nu") > 0)
+                                        model.get_opt_int("integrator") in (2, 3) and model.int("nu") > 0)
     if camlight:            # mj_camlight outputs (mjbOUT_CAMLIGHT)
         nc, nl = max(1, model.int("ncam")), max(1, model.int("nlight"))
         a.update(cam_xpos=np.zeros((3 * nc, n)), cam_xmat=np.zeros((9 * nc, n)),

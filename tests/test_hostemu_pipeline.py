@@ -21,7 +21,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
-         "humanoid_invdiscrete_fast", "implicitfast"]
+         "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit"]
 
 
 def _run(name):
