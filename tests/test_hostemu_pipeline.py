@@ -244,10 +244,18 @@ def test_upload_rejections():
     sm.set_opt_int("disableflags", 1 << 12)     # mjDSBL_SENSOR
     assert len(emu.candidates(sm)) > 0
     h = mjb.Model.from_mjb(util.golden("humanoid")[0])
-    h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE: Euler only
-    assert len(emu.candidates(h)) > 0
-    h.set_opt_int("integrator", 2)              # mjINT_IMPLICIT needs mjd_smooth_vel
+    h.set_opt_int("enableflags", 1 << 3)        # mjENBL_INVDISCRETE: Euler, implicit, implicitfast
+    for integrator in (0, 2, 3):
+        h.set_opt_int("integrator", integrator)
+        assert len(emu.candidates(h)) > 0
+    h.set_opt_int("integrator", 1)              # RK4: an error in the reference too (engine_inverse.c:91-94)
     with pytest.raises(RuntimeError, match="INVDISCRETE"):
+        emu.candidates(h)
+    # velocity-dependent gains need ctrl / act, which are not inputs of the batched inverse
+    h.set_opt_int("integrator", 3)
+    h.array("actuator_gaintype")[0] = 1         # mjGAIN_AFFINE
+    h.array("actuator_gainprm").reshape(-1, 10)[0, 2] = -0.5
+    with pytest.raises(RuntimeError, match="velocity-dependent gain"):
         emu.candidates(h)
 
 
