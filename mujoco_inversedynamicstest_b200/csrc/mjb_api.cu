@@ -265,8 +265,8 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   }
 
   bool ok = check(d, cudaSetDevice(device), "cudaSetDevice");
-  d->model_bytes = H.bytes;
-  d->model_in_smem = H.bytes <= 64*1024;
+  d->model_bytes = H.staged_bytes;      // what the kernels stage; the whole blob (H.bytes) is on the device
+  d->model_in_smem = H.staged_bytes <= 64*1024;
   ok = ok && devAlloc(d, &d->d_model, (size_t)H.bytes, "cudaMalloc(model)");
   ok = ok && check(d, cudaMemcpy(d->d_model, blob.data(), (size_t)H.bytes, cudaMemcpyHostToDevice),
                    "cudaMemcpy(model)");
@@ -663,7 +663,9 @@ bool refreshModel(mjbData* d, const mjModel* m) {
   if (!mjb::buildModelBlob(m, blob, msg)) { d->error = "mjb_inverse: m->opt changed: " + msg; return false; }
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
   const mjbHdr& O = d->hdr;
-  if (H->bytes != O.bytes || H->nscratch != O.nscratch || H->ncand != O.ncand || H->nsensordata != O.nsensordata ||
+  if (H->bytes != O.bytes || H->staged_bytes != O.staged_bytes || H->discrete_trn != O.discrete_trn ||
+      H->sensor_cam != O.sensor_cam || H->sensor_trn != O.sensor_trn || H->sensor_energy != O.sensor_energy ||
+      H->nscratch != O.nscratch || H->ncand != O.ncand || H->nsensordata != O.nsensordata ||
       H->discrete_acc != O.discrete_acc || H->sensor_post != O.sensor_post || H->sensor_touch != O.sensor_touch ||
       ((H->ncand > 0 && !(H->disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT))) && !d->d_cq &&
        !(std::getenv("MJB_CONTACT_PATH")))) {
@@ -692,6 +694,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.model = d->d_model;
   a.model_bytes = d->model_bytes;
   a.model_in_smem = d->model_in_smem;
+  a.sensor_cold = d->hdr.sensor_cam;
   a.qpos = d->in_qpos; a.qvel = d->in_qvel; a.qacc = d->in_qacc;
   a.qacc_discrete = d->d_qacc_discrete;
   a.scratch = d->d_scratch;

@@ -1580,14 +1580,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     if (e != cudaSuccess) return e;
     if (args.out.actuator_length) {
       // implicitfast with velocity-biased actuators: mjd_actuator_vel reads actuator_moment
-      e = in_smem ? launch_phase(transmission_kernel<true>, pre, smem, 8, stream)
-                  : launch_phase(transmission_kernel<false>, pre, 0, 8, stream);
+      e = launch_phase(transmission_kernel<false>, pre, 0, 8, stream);
       if (e != cudaSuccess) return e;
       *launches += 1;
     }
     { PhaseScope ps(timer, stream, kPhaseDiscrete);
-    e = in_smem ? launch_phase(discrete_acc_kernel<true>, args, smem, 8, stream)
-                : launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream); }
+    e = launch_phase(discrete_acc_kernel<false>, args, 0, 8, stream); }     // reads a cold table (act_biasvel)
     if (e != cudaSuccess) return e;
     *launches += 1;
     LaunchArgs post = args;
@@ -1724,21 +1722,20 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     ++*launches;
   }
   if (args.out.actuator_length) {
-    e = in_smem ? launch_phase(transmission_kernel<true>, args, smem, 8, stream)
-                : launch_phase(transmission_kernel<false>, args, 0, 8, stream);
+    // the actuator / camera / light tables are not in the staged part of the blob: model from global memory
+    e = launch_phase(transmission_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }
   if (args.out.cam_xpos) {
-    e = in_smem ? launch_phase(camlight_kernel<true>, args, smem, 8, stream)
-                : launch_phase(camlight_kernel<false>, args, 0, 8, stream);
+    e = launch_phase(camlight_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }
   // sensors last: they read the energies, the camera poses and the transmission outputs
   if (args.out.sensordata && !args.skip_sensors) {
-    e = in_smem ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
-                : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
+    e = (in_smem && !args.sensor_cold) ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
+                                       : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;
   }

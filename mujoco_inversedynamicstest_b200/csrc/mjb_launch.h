@@ -42,7 +42,8 @@ struct ContactRec {
 
 struct LaunchArgs {
   const unsigned char* model;   // device blob (mjbHdr + sections)
-  int model_bytes;
+  int model_bytes;              // the staged part of the blob (mjbHdr.staged_bytes)
+  int sensor_cold;              // the sensor kernel reads tables behind the staged part (cam_project): model from global memory
   int model_in_smem;            // 1: stage the blob into shared memory with a TMA bulk copy
   const double* qpos;           // [nq][stride]
   const double* qvel;           // [nv][stride]

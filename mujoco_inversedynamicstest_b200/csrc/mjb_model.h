@@ -303,6 +303,8 @@ enum {
 typedef struct mjbHdr_ {
   uint32_t magic;
   int32_t bytes;            // total blob size (multiple of 16)
+  int32_t staged_bytes;     // leading part of the blob a CTA stages into shared memory (everything but the tables
+                            // of the output-only kernels: mj_camlight, mj_transmission, implicit mj_discreteAcc)
   // sizes (reference names)
   int32_t nq, nv, nbody, njnt, ngeom, ntendon, nwrap, neq, nM, nC;
   int32_t ncand;            // candidate geom pairs

@@ -793,7 +793,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   std::vector<int> ints;
   std::vector<double> nums;
   // Every table starts on a 16-byte boundary; the tables whose records the contact kernels gather
-  // per candidate / per item (32-byte integer records, scan rows) start on a 128-byte line, so that
+  // per candidate / per item (32-byte integer records, scan rows) start on a 32-byte sector, so that
   // the sector alignment of a record does not depend on which other tables a model happens to have
   // (both sections start on 128-byte boundaries of the blob, see below).
   auto hotInt = [](int id) {
@@ -801,14 +801,46 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
            id == MJB_I_tree_int || id == MJB_I_sensor_int;
   };
   auto hotNum = [](int id) { return id == MJB_N_cand_num || id == MJB_N_scan_bound || id == MJB_N_eq_num; };
+  // Tables read only by the output-only kernels (mj_camlight, mj_transmission, the implicit
+  // mj_discreteAcc, cam_project) live behind the part of the blob a CTA stages into shared memory:
+  // the phase kernels' shared-memory footprint, and with it their occupancy, does not pay for them.
+  // Their offsets are, like every other, relative to the section starts (cold_int / cold_num below).
+  auto coldInt = [](int id) {
+    return id == MJB_I_cam_mode || id == MJB_I_cam_bodyid || id == MJB_I_cam_targetbodyid ||
+           id == MJB_I_light_mode || id == MJB_I_light_bodyid || id == MJB_I_light_targetbodyid ||
+           id == MJB_I_actuator_trntype || id == MJB_I_actuator_trn;
+  };
+  auto coldNum = [](int id) {
+    return id == MJB_N_cam_pos || id == MJB_N_cam_quat || id == MJB_N_cam_poscom0 || id == MJB_N_cam_pos0 ||
+           id == MJB_N_cam_mat0 || id == MJB_N_light_pos || id == MJB_N_light_dir || id == MJB_N_light_poscom0 ||
+           id == MJB_N_light_pos0 || id == MJB_N_light_dir0 || id == MJB_N_actuator_gear ||
+           id == MJB_N_actuator_cranklength || id == MJB_N_act_biasvel || id == MJB_N_cam_proj;
+  };
+  std::vector<int> cold_ints;
+  std::vector<double> cold_nums;
+  std::vector<int> cold_int_ids, cold_num_ids;
   auto pushInts = [&](int id, const int* src, size_t n) {
-    const size_t al = hotInt(id) ? 32 : 4;
+    if (coldInt(id)) {
+      cold_ints.resize((cold_ints.size() + 3) / 4 * 4, 0);
+      H.ioff[id] = (int)cold_ints.size();          // rebased once the hot part is complete
+      cold_ints.insert(cold_ints.end(), src, src + n);
+      cold_int_ids.push_back(id);
+      return;
+    }
+    const size_t al = hotInt(id) ? 8 : 4;
     ints.resize((ints.size() + al - 1) / al * al, 0);
     H.ioff[id] = (int)ints.size();
     ints.insert(ints.end(), src, src + n);
   };
   auto pushNums = [&](int id, const double* src, size_t n) {
-    const size_t al = hotNum(id) ? 16 : 2;
+    if (coldNum(id)) {
+      cold_nums.resize((cold_nums.size() + 1) / 2 * 2, 0.0);
+      H.noff[id] = (int)cold_nums.size();
+      cold_nums.insert(cold_nums.end(), src, src + n);
+      cold_num_ids.push_back(id);
+      return;
+    }
+    const size_t al = hotNum(id) ? 4 : 2;
     nums.resize((nums.size() + al - 1) / al * al, 0.0);
     H.noff[id] = (int)nums.size();
     nums.insert(nums.end(), src, src + n);
@@ -983,14 +1015,22 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
 
   const size_t hdr_bytes = (sizeof(mjbHdr) + 127) & ~(size_t)127;
   const size_t int_bytes = (ints.size()*sizeof(int) + 127) & ~(size_t)127;
-  const size_t num_bytes = (nums.size()*sizeof(double) + 15) & ~(size_t)15;
+  const size_t num_bytes = (nums.size()*sizeof(double) + 127) & ~(size_t)127;
+  const size_t cold_int_bytes = (cold_ints.size()*sizeof(int) + 127) & ~(size_t)127;
+  const size_t cold_num_bytes = (cold_nums.size()*sizeof(double) + 15) & ~(size_t)15;
   H.int_section = (int)hdr_bytes;
   H.num_section = (int)(hdr_bytes + int_bytes);
-  H.bytes = (int)(hdr_bytes + int_bytes + num_bytes);
+  H.staged_bytes = (int)(hdr_bytes + int_bytes + num_bytes);
+  const size_t cold_int_start = (size_t)H.staged_bytes, cold_num_start = cold_int_start + cold_int_bytes;
+  for (int id : cold_int_ids) H.ioff[id] += (int)((cold_int_start - (size_t)H.int_section) / sizeof(int));
+  for (int id : cold_num_ids) H.noff[id] += (int)((cold_num_start - (size_t)H.num_section) / sizeof(double));
+  H.bytes = (int)(cold_num_start + cold_num_bytes);
   blob.assign((size_t)H.bytes, 0);
   std::memcpy(blob.data(), &H, sizeof(H));
   if (!ints.empty()) std::memcpy(blob.data() + H.int_section, ints.data(), ints.size()*sizeof(int));
   if (!nums.empty()) std::memcpy(blob.data() + H.num_section, nums.data(), nums.size()*sizeof(double));
+  if (!cold_ints.empty()) std::memcpy(blob.data() + cold_int_start, cold_ints.data(), cold_ints.size()*sizeof(int));
+  if (!cold_nums.empty()) std::memcpy(blob.data() + cold_num_start, cold_nums.data(), cold_nums.size()*sizeof(double));
   return true;
 }
 
