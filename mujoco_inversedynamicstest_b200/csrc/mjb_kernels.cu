@@ -31,6 +31,9 @@
 #ifndef MJB_CTAS_BACKWARD
 #define MJB_CTAS_BACKWARD 4
 #endif
+#ifndef MJB_ROWS_CTAS
+#define MJB_ROWS_CTAS 4
+#endif
 #ifndef MJB_CTAS_CONTACT
 #define MJB_CTAS_CONTACT 2
 #endif
@@ -1240,7 +1243,7 @@ __global__ void __launch_bounds__(kThreads, 4) contact_index_wide_kernel(LaunchA
 // conflict-free and bitwise deterministic. No other warp touches these states.
 // kWarpPerState: the slots were numbered by contact_index_wide_kernel, one warp walks ONE state.
 template <bool kModelInSmem, bool kWarpPerState>
-__global__ void __launch_bounds__(kThreads, 4) contact_rows_kernel(LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, MJB_ROWS_CTAS) contact_rows_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   if (*(volatile int*)&a.cq->overflow | *(volatile int*)&a.cq->overflow_contacts) return;
@@ -1655,6 +1658,20 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
 // The contact kernel reads the model tables through L1 instead of a shared-memory copy: its lanes
 // index the candidate tables with per-lane (non-uniform) indices anyway, and the 25 KB per CTA are
 // worth more as L1 for the scattered scratch accesses (measured 5.54 vs 5.96 ms per 2^20 states).
+// Item-path kernels read the model from global memory (through L1) instead of a staged copy: a 57 KB
+// copy per CTA caps every kernel at four CTAs per SM. Measured on the humanoid (profiles/r02_*): the
+// numbering kernel, which reads no model table at all, 0.39 -> 0.19 ms (warps active 17 % -> 69 %);
+// the rows kernel 1.09 -> 1.05 ms; the narrow kernel 1.31 -> 1.30 ms. A fifth resident CTA for the
+// rows kernel (96 registers, spills) costs more than it gives: 1.29 ms.
+#ifndef MJB_INDEX_GLOBAL
+#define MJB_INDEX_GLOBAL 1
+#endif
+#ifndef MJB_ROWS_GLOBAL
+#define MJB_ROWS_GLOBAL 1
+#endif
+#ifndef MJB_NARROW_GLOBAL
+#define MJB_NARROW_GLOBAL 1
+#endif
 #ifndef MJB_CONTACT_MODEL_SMEM
 #define MJB_CONTACT_MODEL_SMEM 0
 #endif
@@ -1664,7 +1681,7 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
         // (the grid follows the ITEM list, not the states: a 22-humanoid scene has 1,200 items per state,
         // and a grid of chunk_n / 256 CTAs left most of the chip idle -- one CTA per state, capped)
         if (args.simple_pairs) {
-          e = in_smem ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256, 0, 1)
+          e = (in_smem && !MJB_NARROW_GLOBAL) ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256, 0, 1)
                       : launch_phase(contact_narrow_kernel<false, true>, args, 0, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256, 0, 1);
         } else {
           e = in_smem ? launch_phase(contact_narrow_kernel<true, false>, args, smem, 4, stream, 256, 0, 1)
@@ -1682,11 +1699,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
                       : launch_phase(contact_rows_kernel<false, true>, args, 0, 8, stream, kThreads, 0, spc);
           if (e != cudaSuccess) return e;
         } else {
-          e = in_smem ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
-                      : launch_phase(contact_index_kernel<false>, args, 0, 8, stream);
+          // the numbering kernel reads no model table: no staging, occupancy bounded by registers only
+          e = (in_smem && !MJB_INDEX_GLOBAL) ? launch_phase(contact_index_kernel<true>, args, smem, 8, stream)
+                                             : launch_phase(contact_index_kernel<false>, args, 0, MJB_INDEX_GLOBAL ? 12 : 8, stream);
           if (e != cudaSuccess) return e;
-          e = in_smem ? launch_phase(contact_rows_kernel<true, false>, args, smem, 8, stream)
-                      : launch_phase(contact_rows_kernel<false, false>, args, 0, 8, stream);
+          e = (in_smem && !MJB_ROWS_GLOBAL) ? launch_phase(contact_rows_kernel<true, false>, args, smem, 8, stream)
+                                            : launch_phase(contact_rows_kernel<false, false>, args, 0, 8, stream);
           if (e != cudaSuccess) return e;
         }
       }
