@@ -209,7 +209,7 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
     if (H0->sensor_post) outmask |= mjbOUT_RNEPOST;   // accelerometer / force / torque / frame*acc sensors
     // touch sensors walk the contact list and the contact rows' forces: those outputs are their input
     if (H0->sensor_touch) outmask |= mjbOUT_COUNTS | mjbOUT_CONTACT | mjbOUT_EFC;
-    if (H0->sensor_cam) outmask |= mjbOUT_CAMLIGHT;           // camprojection sensors read the camera poses
+    if (H0->sensor_camlight) outmask |= mjbOUT_CAMLIGHT;           // camprojection sensors read the camera poses
     if (H0->sensor_trn) outmask |= mjbOUT_TRANSMISSION;       // actuatorpos / actuatorvel sensors
     if (H0->discrete_trn) outmask |= mjbOUT_TRANSMISSION;     // implicitfast mj_discreteAcc reads the moment rows
   }
@@ -664,7 +664,7 @@ bool refreshModel(mjbData* d, const mjModel* m) {
   const mjbHdr* H = reinterpret_cast<const mjbHdr*>(blob.data());
   const mjbHdr& O = d->hdr;
   if (H->bytes != O.bytes || H->staged_bytes != O.staged_bytes || H->discrete_trn != O.discrete_trn ||
-      H->sensor_cam != O.sensor_cam || H->sensor_trn != O.sensor_trn || H->sensor_energy != O.sensor_energy ||
+      H->sensor_cam != O.sensor_cam || H->sensor_camlight != O.sensor_camlight || H->sensor_trn != O.sensor_trn || H->sensor_energy != O.sensor_energy ||
       H->nscratch != O.nscratch || H->ncand != O.ncand || H->nsensordata != O.nsensordata ||
       H->discrete_acc != O.discrete_acc || H->sensor_post != O.sensor_post || H->sensor_touch != O.sensor_touch ||
       ((H->ncand > 0 && !(H->disableflags & (MJB_DSBL_CONSTRAINT | MJB_DSBL_CONTACT))) && !d->d_cq &&

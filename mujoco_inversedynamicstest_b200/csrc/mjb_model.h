@@ -74,6 +74,7 @@
   X(eq_int)    /* neq*MJB_EQ_NI : equality constraints, see MJB_EQI_*           */ \
   X(body_static) /* nbody: 1 if no dof on the chain to the world (jac == 0)     */ \
   X(jnt_dofnum_tab) /* njnt : dofs of this joint                                */ \
+  X(ray_geom) /* ngeom (empty without rangefinder sensors): 1 if mj_ray tests the geom (visible: ray_eliminate) */ \
   X(actuator_trn) /* nu*2 : actuator_trnid (object, reference / slider site) */ \
   X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
   X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
@@ -216,7 +217,7 @@ enum { MJB_SEN_TYPE = 0, MJB_SEN_DATATYPE, MJB_SEN_OBJTYPE, MJB_SEN_OBJID, MJB_S
        MJB_SEN_DIM, MJB_SEN_ADR, MJB_SEN_NI };
 // mjtSensor / mjtObj / mjtDataType values restated (include/mujoco/mjmodel.h)
 enum { MJB_SENS_TOUCH = 0, MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2, MJB_SENS_GYRO = 3, MJB_SENS_FORCE = 4,
-       MJB_SENS_TORQUE = 5, MJB_SENS_MAGNETOMETER = 6, MJB_SENS_CAMPROJECTION = 8, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
+       MJB_SENS_TORQUE = 5, MJB_SENS_MAGNETOMETER = 6, MJB_SENS_RANGEFINDER = 7, MJB_SENS_CAMPROJECTION = 8, MJB_SENS_JOINTPOS = 9, MJB_SENS_JOINTVEL = 10, MJB_SENS_TENDONPOS = 11,
        MJB_SENS_TENDONVEL = 12, MJB_SENS_ACTUATORPOS = 13, MJB_SENS_ACTUATORVEL = 14, MJB_SENS_BALLQUAT = 17, MJB_SENS_BALLANGVEL = 18, MJB_SENS_JOINTLIMITPOS = 19,
        MJB_SENS_JOINTLIMITVEL = 20, MJB_SENS_JOINTLIMITFRC = 21, MJB_SENS_TENDONLIMITPOS = 22,
        MJB_SENS_TENDONLIMITVEL = 23, MJB_SENS_TENDONLIMITFRC = 24, MJB_SENS_FRAMEPOS = 25,
@@ -328,7 +329,8 @@ typedef struct mjbHdr_ {
   int32_t ncam, nlight;     // cameras / lights (mj_camlight outputs, mjbOUT_CAMLIGHT)
   int32_t nu;               // actuators (mj_transmission outputs, mjbOUT_TRANSMISSION)
   int32_t sensor_subtreevel; // some sensor reads subtree_linvel / subtree_angmom (mj_subtreeVel)
-  int32_t sensor_cam;        // some camprojection sensor reads cam_xpos / cam_xmat (mj_camlight runs for it)
+  int32_t sensor_cam;        // the sensor kernel reads tables behind the staged part of the blob (cam_proj, ray_geom)
+  int32_t sensor_camlight;   // some camprojection sensor reads cam_xpos / cam_xmat (mj_camlight runs for it)
   int32_t sensor_trn;        // some actuatorpos / actuatorvel sensor reads mj_transmission's outputs
   int32_t sensor_energy;     // some potential / kinetic energy sensor (mj_energyPos / mj_energyVel run for it)
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces

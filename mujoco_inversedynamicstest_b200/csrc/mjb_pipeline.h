@@ -3469,6 +3469,14 @@ MJB_HD inline double ray_geom(const double* pos, const double* mat, const double
   double lp[3], lv[3], xx[2];
   mulMatTVec3(lp, mat, dif);
   mulMatTVec3(lv, mat, vec);
+  if (type == MJB_GEOM_PLANE) {
+    // ray_plane (engine_ray.c:191-217): front face only, inside the rendered rectangle when it has one
+    if (lv[2] > -MJB_MINVAL) return -1;
+    const double xp = -lp[2]/lv[2];
+    if (xp < 0) return -1;
+    const double p0 = lp[0] + xp*lv[0], p1 = lp[1] + xp*lv[1];
+    return ((size[0] <= 0 || fabs(p0) <= size[0]) && (size[1] <= 0 || fabs(p1) <= size[1])) ? xp : -1.0;
+  }
   if (type == MJB_GEOM_ELLIPSOID) {
     const double s[3] = {1/(size[0]*size[0]), 1/(size[1]*size[1]), 1/(size[2]*size[2])};
     const double a = s[0]*lv[0]*lv[0] + s[1]*lv[1]*lv[1] + s[2]*lv[2]*lv[2];
@@ -3631,6 +3639,24 @@ MJB_HD inline void sensors(Ctx& c) {
       sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
       quat2Mat(m, quat);
       mulMatTVec3(v, m, H.magnetic);
+    } else if (type == MJB_SENS_RANGEFINDER) {
+      // mj_ray from the site along its z axis over every geom that is not eliminated (engine_sensor.c:266-275,
+      // engine_ray.c:69-100, 1145-1185: the site's own body, invisible geoms -- the static part of the
+      // test is the ray_geom table); geom frames are rebuilt from the body poses (mj_local2Global)
+      double pos[3], quat[4], m[9], gp[3], gq[4], gm[9];
+      const int body = sensor_object(c, MJB_OBJ_SITE, objid, pos, quat);
+      quat2Mat(m, quat);
+      const double rvec[3] = {m[2], m[5], m[8]};
+      const int* ray_ok = MI(ray_geom); const int* geom_bodyid = MI(geom_bodyid); const int* geom_type = MI(geom_type);
+      double dist = -1;
+      for (int g = 0; g < H.ngeom; g++) {
+        if (!ray_ok[g] || geom_bodyid[g] == body) continue;
+        sensor_object(c, MJB_OBJ_GEOM, g, gp, gq);
+        quat2Mat(gm, gq);
+        const double nd = ray_geom(gp, gm, MD(geom_size) + 3*g, pos, rvec, geom_type[g]);
+        if (nd >= 0 && (nd < dist || dist < 0)) dist = nd;
+      }
+      v[0] = dist;
     } else if (type == MJB_SENS_CAMPROJECTION) {
       // site position in the image of camera refid (engine_sensor.c:259-264); the camera pose is
       // mj_camlight's output (mjb_makeData adds mjbOUT_CAMLIGHT for these sensors)

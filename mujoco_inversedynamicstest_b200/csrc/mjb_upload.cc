@@ -256,7 +256,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // magnetometer, camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
   bool sensor_post = false, sensor_subtreevel = false, sensor_touch = false;
-  bool sensor_cam = false, sensor_trn = false, sensor_energy = false;
+  bool sensor_cam = false, sensor_trn = false, sensor_energy = false, sensor_ray = false;
   std::vector<int> sensor_int;
   std::vector<double> sensor_cutoff;
   for (int i = 0; i < m->nsensor && sensors; i++) {
@@ -289,6 +289,17 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         ok = true; break;
       case mjSENS_CAMPROJECTION:
         ok = true; sensor_cam = true; break;
+      case mjSENS_RANGEFINDER:
+        // mj_ray over the primitive geoms; height fields, meshes and SDFs in the ray's way are not restated
+        ok = true;
+        for (int g = 0; g < m->ngeom; g++) {
+          const bool invisible = m->geom_matid[g] < 0 ? m->geom_rgba[4*g + 3] == 0
+                                                      : m->mat_rgba[4*m->geom_matid[g] + 3] == 0;
+          const int gt = m->geom_type[g];
+          if (!invisible && (gt == mjGEOM_HFIELD || gt == mjGEOM_MESH || gt == mjGEOM_SDF)) ok = false;
+        }
+        sensor_ray = true;
+        break;
       case mjSENS_ACTUATORPOS: case mjSENS_ACTUATORVEL:
         ok = m->actuator_trntype[m->sensor_objid[i]] != mjTRN_BODY; sensor_trn = true; break;
       case mjSENS_E_POTENTIAL: case mjSENS_E_KINETIC:
@@ -785,7 +796,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nu = m->nu;
   H.sensor_subtreevel = sensor_subtreevel ? 1 : 0;
   H.sensor_touch = sensor_touch ? 1 : 0;
-  H.sensor_cam = sensor_cam ? 1 : 0; H.sensor_trn = sensor_trn ? 1 : 0; H.sensor_energy = sensor_energy ? 1 : 0;
+  H.sensor_cam = (sensor_cam || sensor_ray) ? 1 : 0;     // both read tables behind the staged part of the blob
+  H.sensor_camlight = sensor_cam ? 1 : 0; H.sensor_trn = sensor_trn ? 1 : 0; H.sensor_energy = sensor_energy ? 1 : 0;
   for (int i = 0; i < 3; i++) H.magnetic[i] = m->opt.magnetic[i];
   H.timestep = m->opt.timestep; H.impratio = m->opt.impratio;
   for (int i = 0; i < 3; i++) H.gravity[i] = m->opt.gravity[i];
@@ -808,7 +820,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   auto coldInt = [](int id) {
     return id == MJB_I_cam_mode || id == MJB_I_cam_bodyid || id == MJB_I_cam_targetbodyid ||
            id == MJB_I_light_mode || id == MJB_I_light_bodyid || id == MJB_I_light_targetbodyid ||
-           id == MJB_I_actuator_trntype || id == MJB_I_actuator_trn;
+           id == MJB_I_actuator_trntype || id == MJB_I_actuator_trn || id == MJB_I_ray_geom;
   };
   auto coldNum = [](int id) {
     return id == MJB_N_cam_pos || id == MJB_N_cam_quat || id == MJB_N_cam_poscom0 || id == MJB_N_cam_pos0 ||
@@ -865,6 +877,15 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_tendon_active, tendon_active.data(), tendon_active.size());
   pushInts(MJB_I_actuator_trn, m->actuator_trnid, (size_t)2 * m->nu);
+  {
+    // rangefinder sensors: the state-independent part of ray_eliminate (engine_ray.c:69-100; flg_static = 1,
+    // no geom groups: only invisible geoms are skipped, the site's own body is tested per sensor)
+    std::vector<int> ray_geom(sensor_ray ? m->ngeom : 0, 1);
+    for (size_t g = 0; g < ray_geom.size(); g++) {
+      ray_geom[g] = m->geom_matid[g] < 0 ? m->geom_rgba[4*g + 3] != 0 : m->mat_rgba[4*m->geom_matid[g] + 3] != 0;
+    }
+    pushInts(MJB_I_ray_geom, ray_geom.data(), ray_geom.size());
+  }
   pushInts(MJB_I_jnt_dofnum_tab, jnt_dofnum.data(), jnt_dofnum.size());
   {
     // static row numbering (mj_makeConstraint order: equality, dof friction, tendon friction, ...)
