@@ -3679,10 +3679,15 @@ MJB_HD inline void sensors(Ctx& c) {
       v[0] = QPOS(MI(jnt_qposadr)[objid]);
     } else if (type == MJB_SENS_JOINTVEL) {
       v[0] = QVEL(MI(jnt_dofadr)[objid]);
-    } else if (type == MJB_SENS_TENDONPOS) {
-      v[0] = AT(SC(ten_length), objid);
-    } else if (type == MJB_SENS_TENDONVEL) {
-      v[0] = AT(SC(ten_velocity), objid);
+    } else if (type == MJB_SENS_TENDONPOS || type == MJB_SENS_TENDONVEL) {
+      if (MI(wrap_type)[MI(tendon_adr)[objid]] != MJB_WRAP_JOINT && !MI(tendon_active)[objid]) {
+        // a spatial tendon that carries no force is not walked by the smooth phase: walk it here
+        double vel, acc;
+        const double len = spatial_tendon_kinematics(c, objid, &vel, &acc);
+        v[0] = type == MJB_SENS_TENDONPOS ? len : vel;
+      } else {
+        v[0] = type == MJB_SENS_TENDONPOS ? AT(SC(ten_length), objid) : AT(SC(ten_velocity), objid);
+      }
     } else if (type == MJB_SENS_BALLQUAT) {
       const int a = MI(jnt_qposadr)[objid];
       for (int k = 0; k < 4; k++) v[k] = QPOS(a + k);

@@ -274,9 +274,12 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
           ok = jt == mjJNT_HINGE || jt == mjJNT_SLIDE;
         }
         break;
-      case mjSENS_TENDONLIMITPOS: case mjSENS_TENDONLIMITVEL: case mjSENS_TENDONLIMITFRC:
       case mjSENS_TENDONPOS: case mjSENS_TENDONVEL:
-        // fixed tendons only: a spatial tendon's length exists on the device only while it carries a force
+        // fixed or spatial: the sensor kernel walks the path of a spatial tendon that carries no force itself
+        ok = true;
+        break;
+      case mjSENS_TENDONLIMITPOS: case mjSENS_TENDONLIMITVEL: case mjSENS_TENDONLIMITFRC:
+        // fixed tendons only
         ok = true;
         {
           const int tid = m->sensor_objid[i];
@@ -959,6 +962,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     std::vector<int> tendon_trn(m->ntendon, 0);
     for (int i = 0; i < m->nu; i++) {
       if (m->actuator_trntype[i] == mjTRN_TENDON) tendon_trn[m->actuator_trnid[2*i]] = 1;
+    }
+    // ... or are read by a tendonpos / tendonvel sensor
+    for (int i = 0; i < m->nsensor && sensors; i++) {
+      if (m->sensor_type[i] == mjSENS_TENDONPOS || m->sensor_type[i] == mjSENS_TENDONVEL) tendon_trn[m->sensor_objid[i]] = 1;
     }
     for (int t = 0; t < m->ntendon; t++) {
       if (!tendon_active[t] && !tendon_trn[t]) continue;
