@@ -124,6 +124,12 @@ MJB_API int mjb_setState(mjbData* d, int nbatch, const mjtNum* qpos, const mjtNu
  * nbatch x nmocap x 4, used by every following mjb_inverse until replaced. NULL pointers return to
  * the model pose (what mj_makeData / mj_resetData leave in mjData). */
 MJB_API int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* mocap_quat);
+/* per-state d->xfrc_applied (include/mujoco/mjdata.h): HOST array nbatch x nbody x 6, (force, torque) per
+ * body in world axes at the body's centre of mass, used by every following mjb_inverse until replaced;
+ * NULL returns to zero. mj_inverse ignores applied wrenches in qfrc_inverse; they enter the
+ * mj_rnePostConstraint outputs cfrc_ext / cfrc_int (src/engine/engine_core_smooth.c:2039-2049) and the
+ * force / torque sensors that read cfrc_int. Needs mjbOUT_RNEPOST (or such sensors) to have any effect. */
+MJB_API int mjb_setXfrcApplied(mjbData* d, int nbatch, const mjtNum* xfrc_applied);
 /* adopt DEVICE structure-of-arrays inputs without a copy: (nq|nv) x stride, stride >= nbatch.
  * Pass NULL pointers to return to the internal buffers. */
 MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel,

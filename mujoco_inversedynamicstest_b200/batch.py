@@ -173,6 +173,15 @@ class BatchData:
                                              int(stride)), "mjb_setStateDevice")
         self.nbatch = int(n)
 
+    def set_xfrc_applied(self, xfrc_applied):
+        """Per-state d->xfrc_applied [nbatch, nbody, 6] (force, torque per body); None returns to zero.
+        Enters cfrc_ext / cfrc_int of mj_rnePostConstraint (OUT_RNEPOST), not qfrc_inverse."""
+        if xfrc_applied is None:
+            self._check(lib().mjb_setXfrcApplied(self._d, 0, None), "mjb_setXfrcApplied")
+            return
+        x = np.ascontiguousarray(xfrc_applied, dtype=np.float64)
+        self._check(lib().mjb_setXfrcApplied(self._d, x.shape[0], x.ctypes.data), "mjb_setXfrcApplied")
+
     def set_mocap(self, mocap_pos=None, mocap_quat=None):
         """Per-state mocap poses [nbatch, nmocap, 3] / [nbatch, nmocap, 4]; None: the model pose."""
         if mocap_pos is None or mocap_quat is None:

@@ -55,6 +55,7 @@ struct mjbData_ {
   int* d_cmask = nullptr;      // per-state survivor masks of the warp-per-state scans (one state's words contiguous)
   int* d_pair_ci = nullptr;    // geom pair -> candidate index (ngeom x ngeom), long candidate lists only   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
   int items_cap = 0, contacts_cap = 0;
+  double* d_xfrc_applied = nullptr;    // per-state d->xfrc_applied [nbody*6][stride] (mjb_setXfrcApplied)
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
   long long in_stride = 0;
@@ -540,7 +541,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_scan_buf);
   cudaFree(d->d_pair_ci);
   cudaFree(d->d_cmask);
-  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete);
+  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete); cudaFree(d->d_xfrc_applied);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
   cudaFree(d->d_fwd_qforce); cudaFree(d->d_fwd_xfrc); cudaFree(d->d_fwd_qc); cudaFree(d->d_fwdinv);
@@ -627,6 +628,31 @@ int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const mjtNum* 
   ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_setMocap");   // the staging buffer is shared with mjb_setState
   if (!ok) return -1;
   o.mocap_pos = d->d_mocap_pos; o.mocap_quat = d->d_mocap_quat;
+  return 0;
+}
+
+int mjb_setXfrcApplied(mjbData* d, int nbatch, const mjtNum* xfrc_applied) {
+  if (!d->shards.empty()) {
+    const int nb = d->hdr.nbody;
+    return forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) {
+      return mjb_setXfrcApplied(sh, r.n, xfrc_applied ? xfrc_applied + r.first * 6 * nb : nullptr);
+    }) ? 0 : -1;
+  }
+  d->stream_dirty = true;
+  const mjbHdr& H = d->hdr;
+  mjb::Outputs& o = d->out;
+  if (!xfrc_applied) { o.xfrc_applied = nullptr; return 0; }
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setXfrcApplied: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const size_t S = (size_t)d->stride, n = (size_t)nbatch, rows = 6 * (size_t)H.nbody;
+  bool ok = true;
+  if (!d->d_xfrc_applied) ok = ok && devAlloc(d, &d->d_xfrc_applied, rows * S, "cudaMalloc(xfrc_applied)");
+  if (!ok || !ensureStage(d, n * rows * sizeof(double))) return -1;
+  ok = ok && check(d, cudaMemcpyAsync(d->d_stage, xfrc_applied, n * rows * sizeof(double), cudaMemcpyHostToDevice, d->stream), "H2D xfrc_applied");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)d->d_stage, d->d_xfrc_applied, nbatch, (int)rows, d->stride, d->stream), "transpose xfrc_applied");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_setXfrcApplied");   // the staging buffer is shared with mjb_setState
+  if (!ok) return -1;
+  o.xfrc_applied = d->d_xfrc_applied;
   return 0;
 }
 

@@ -1452,6 +1452,20 @@ __global__ void __launch_bounds__(kThreads, 4) transmission_kernel(LaunchArgs a)
   }
 }
 
+// d->xfrc_applied folded into cfrc_ext / cfrc_int (mj_rnePostConstraint), only when the caller has set it
+template <bool kModelInSmem>
+__global__ void __launch_bounds__(kThreads, 4) post_xfrc_kernel(LaunchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  Ctx c;
+  make_ctx<kModelInSmem>(c, a, smem, &mbar);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
+       i += (long long)gridDim.x * kThreads) {
+    bind_state(c, a, i);
+    post_xfrc(c);
+  }
+}
+
 size_t inverse_smem_bytes(int model_bytes, int model_in_smem) {
   return model_in_smem ? static_cast<size_t>(model_bytes) : 0;
 }
@@ -1721,6 +1735,12 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   PhaseScope ps_backward(timer, stream, kPhaseBackward);
   e = run_phase(nullptr, fn_backward, args, stream, launches, generic_backward);
   if (e != cudaSuccess) return e;
+  if (args.out.xfrc_applied && args.out.cfrc_ext) {
+    e = in_smem ? launch_phase(post_xfrc_kernel<true>, args, smem, 8, stream)
+                : launch_phase(post_xfrc_kernel<false>, args, 0, 8, stream);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
   if (args.out.qfrc_bias) {
     e = in_smem ? launch_phase(bias_kernel<true>, args, smem, 8, stream)
                 : launch_phase(bias_kernel<false>, args, 0, 8, stream);

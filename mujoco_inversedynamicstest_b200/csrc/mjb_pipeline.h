@@ -138,6 +138,9 @@ struct Outputs {
   double* actuator_length;            // [nu][stride]
   double* actuator_moment;            // [nu*nv][stride], dense rows
   double* actuator_velocity;          // [nu][stride]
+  // d->xfrc_applied per state (INPUT; mjb_setXfrcApplied): [nbody*6][stride], force then torque per body.
+  // mj_inverse itself ignores it; mj_rnePostConstraint adds it to cfrc_ext (engine_core_smooth.c:2039-2049)
+  const double* xfrc_applied;
 };
 
 struct Ctx {
@@ -3197,6 +3200,69 @@ MJB_HD inline void post_constraint_end(Ctx& c) {
   for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)k*N + c.s] = s0[k];
 }
 
+// d->xfrc_applied in the mj_rnePostConstraint outputs (engine_core_smooth.c:2039-2049, 2171-2181), as a
+// pass of its own after the backward sweep (only when the caller has set per-state applied wrenches):
+// X_b = the body's applied (force, torque) at xipos re-expressed about the tree's centre of mass;
+//   cfrc_ext[b] += X_b,   cfrc_int[b] -= sum of X over the subtree of b,
+// and the world body's row, the plain sum of the root rows, loses the roots' sums. The subtree sums
+// live in the ia rows of the scratch (free after the inertia kernel).
+MJB_HD inline int sensor_object(Ctx& c, int objtype, int objid, double* pos, double* quat);   // defined with the sensors
+MJB_HD inline void post_xfrc(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody;
+  const size_t N = (size_t)c.N;
+  const int* body_parentid = MI(body_parentid); const int* rootid = MI(body_rootid);
+  double* t = SC(ia);
+  const double zero[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nbody; b++) stn(t, 6*b, zero, 6);
+  double world[6] = {0, 0, 0, 0, 0, 0};
+  int tree = -1;
+  double com[3] = {0, 0, 0};
+  for (int b = nbody - 1; b > 0; b--) {
+    double x[6], X[6] = {0, 0, 0, 0, 0, 0}, acc[6];
+    bool any = false;
+    for (int k = 0; k < 6; k++) { x[k] = c.out.xfrc_applied[(size_t)(6*b + k)*N + c.s]; any = any || x[k] != 0; }
+    if (any) {
+      const int r = rootid[b];
+      if (r != tree) {
+        // subtree_com of the tree's root = O + sum m (xipos - O) / sum m, from cinert[6..9]
+        double ms[4] = {0, 0, 0, 0}, o[3];
+        int e = r;
+        do {
+          double q[4];
+          ldn(q, SC(cinert), 10*e + 6, 4);
+          for (int k = 0; k < 4; k++) ms[k] += q[k];
+          e++;
+        } while (e < nbody && body_parentid[e] != 0);
+        ldn(o, SC(origin), 3*r, 3);
+        for (int k = 0; k < 3; k++) com[k] = o[k] + (ms[3] >= MJB_MINVAL ? ms[k]/ms[3] : 0.0);
+        tree = r;
+      }
+      double xi[3], q4[4], cr[3];
+      sensor_object(c, MJB_OBJ_BODY, b, xi, q4);
+      const double dif[3] = {com[0] - xi[0], com[1] - xi[1], com[2] - xi[2]};
+      cross3(cr, dif, x);                                    // (newpos - oldpos) x force
+      for (int k = 0; k < 3; k++) { X[k] = x[3 + k] - cr[k]; X[3 + k] = x[k]; }
+      for (int k = 0; k < 6; k++) c.out.cfrc_ext[(size_t)(6*b + k)*N + c.s] += X[k];
+    }
+    ldn(acc, t, 6*b, 6);
+    bool nz = any;
+    for (int k = 0; k < 6; k++) { acc[k] += X[k]; nz = nz || acc[k] != 0; }
+    if (!nz) continue;
+    for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)(6*b + k)*N + c.s] -= acc[k];
+    const int p = body_parentid[b];
+    if (p) {
+      double pa[6];
+      ldn(pa, t, 6*p, 6);
+      for (int k = 0; k < 6; k++) pa[k] += acc[k];
+      stn(t, 6*p, pa, 6);
+    } else {
+      for (int k = 0; k < 6; k++) world[k] += acc[k];
+    }
+  }
+  for (int k = 0; k < 6; k++) c.out.cfrc_int[(size_t)k*N + c.s] -= world[k];
+}
+
 // ------------------------------------------------------------------------------------------
 // backward half of mj_rne(flg_acc=1) (engine_core_smooth.c:2008-2020) fused with the last loop of
 // mj_inverseSkip (engine_inverse.c:249-252). Constraint wrenches are accumulated up the tree
@@ -4823,6 +4889,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
     phase_contact(c, true, list, 1, 64);
   }
   if (c.H->passive_wrench) phase_backward<true>(c); else phase_backward<false>(c);
+  if (c.out.xfrc_applied && c.out.cfrc_ext) post_xfrc(c);
   if (c.out.qfrc_bias) bias_forces(c);
   if (c.out.energy) energy(c);
   if (c.out.cam_xpos) camlight(c);

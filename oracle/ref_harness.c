@@ -224,6 +224,9 @@ REFH_API void refh_set_post_constraint(int on) { refh_post_constraint = on; }
 static const double* refh_mocap_pos = NULL;
 static const double* refh_mocap_quat = NULL;
 REFH_API void refh_set_mocap(const double* pos, const double* quat) { refh_mocap_pos = pos; refh_mocap_quat = quat; }
+/* per-state d->xfrc_applied for the batch loop (nbatch x nbody x 6), NULL: zero */
+static const double* refh_xfrc = NULL;
+REFH_API void refh_set_xfrc(const double* xfrc) { refh_xfrc = xfrc; }
 
 static void* run_chunk(void* arg) {
   refhChunk* c = (refhChunk*)arg;
@@ -238,6 +241,7 @@ static void* run_chunk(void* arg) {
       mju_copy(d->mocap_pos, refh_mocap_pos + i*3*m->nmocap, 3*m->nmocap);
       mju_copy(d->mocap_quat, refh_mocap_quat + i*4*m->nmocap, 4*m->nmocap);
     }
+    if (refh_xfrc) mju_copy(d->xfrc_applied, refh_xfrc + (size_t)i*6*m->nbody, 6*m->nbody);
     mj_inverse(m, d);
     if (refh_post_constraint) mj_rnePostConstraint(m, d);
     if (c->qfrc_inverse) mju_copy(c->qfrc_inverse + i*m->nv, d->qfrc_inverse, m->nv);

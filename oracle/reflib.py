@@ -207,7 +207,7 @@ class Model:
                             p(out["qacc"]), p(out["qfrc_actuator"]), p(out["qfrc_constraint"]), p(out["fwdinv"]))
         return out
 
-    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1, mocap=None):
+    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1, mocap=None, xfrc=None):
         """Loop the reference's mj_inverse over the batch.
 
         fields: {name: maxrows} of extra mjData arrays / contact_* pseudo fields / scalar counters
@@ -246,6 +246,13 @@ class Model:
             L.refh_set_mocap(mp.ctypes.data, mq.ctypes.data)
         else:
             L.refh_set_mocap(None, None)
+        L.refh_set_xfrc.argtypes = [ctypes.c_void_p]
+        xf = None
+        if xfrc is not None:       # d->xfrc_applied per state [n, nbody, 6] (read by mj_rnePostConstraint)
+            xf = np.ascontiguousarray(xfrc, dtype=np.float64)
+            L.refh_set_xfrc(xf.ctypes.data)
+        else:
+            L.refh_set_xfrc(None)
         rq = (_Request * max(1, len(reqs)))()
         for i, (nm, arr, mr) in enumerate(reqs):
             rq[i].name = nm
@@ -254,6 +261,7 @@ class Model:
         t = L.refh_inverse_batch(self.ptr, n, qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data,
                                  out["qfrc_inverse"].ctypes.data, rq, len(reqs), int(nthread))
         L.refh_set_mocap(None, None)
+        L.refh_set_xfrc(None)
         if t < 0:
             raise RuntimeError("refh_inverse_batch: unknown field requested")
         return out, t

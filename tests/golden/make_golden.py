@@ -389,10 +389,43 @@ def make_transmission_case(name):
           f"mean nnz={out['moment_rownnz'].mean():.2f}")
 
 
+# per-state d->xfrc_applied in the mj_rnePostConstraint outputs (engine_core_smooth.c:2039-2049) and in the
+# force / torque sensors that read cfrc_int: name -> (case whose model / state stream is used, nstate)
+XFRC_CASES = {"humanoid_xfrc": ("humanoid", 64), "sensors_xfrc": ("sensors", 64), "weld_xfrc": ("weld", 32),
+              "humanoids22_xfrc": ("humanoids22", 4)}
+
+
+def xfrc_samples(m, nstate):
+    """Seeded applied wrenches [nstate, nbody, 6]: about half of the bodies loaded, the world body never."""
+    rng = np.random.RandomState(20250331)
+    nb = m.int("nbody")
+    x = rng.normal(0, 5, (nstate, nb, 6)) * (rng.uniform(0, 1, (nstate, nb, 1)) < 0.5)
+    x[:, 0] = 0
+    return x
+
+
+def make_xfrc_case(name):
+    base, nstate = XFRC_CASES[name]
+    xml, opts, _, zr, _, _ = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    fields = {"cacc": None, "cfrc_int": None, "cfrc_ext": None}
+    if m.int("nsensordata") > 0:
+        fields["sensordata"] = None
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields, xfrc=xfrc_samples(m, nstate))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), **{k: (v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v)
+                                                 for k, v in out.items()})
+    print(f"{name}: nbody={m.int('nbody')} states={nstate} max|cfrc_ext|={np.abs(out['cfrc_ext']).max():.3g}")
+
+
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
                  list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES) + list(CAMLIGHT_CASES) +
-                 list(TRANSMISSION_CASES)):
-        (make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(TRANSMISSION_CASES) + list(XFRC_CASES)):
+        (make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

@@ -13,7 +13,7 @@ _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status"
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
            "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat", "energy",
            "cam_xpos", "cam_xmat", "light_xpos", "light_xdir",
-           "actuator_length", "actuator_moment", "actuator_velocity"]
+           "actuator_length", "actuator_moment", "actuator_velocity", "xfrc_applied"]
 
 
 class Outputs(ctypes.Structure):
@@ -43,7 +43,7 @@ def available():
 
 
 def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None, camlight=False,
-        transmission=False):
+        transmission=False, xfrc=None):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -72,6 +72,8 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         if fwd.get("xfrc") is not None:
             a["fwd_xfrc"] = np.ascontiguousarray(fwd["xfrc"].reshape(n, -1).T, dtype=np.float64)
         a["fwdinv"] = np.zeros((2, n))
+    if xfrc is not None:    # d->xfrc_applied per state [n, nbody, 6]
+        a["xfrc_applied"] = np.ascontiguousarray(xfrc.reshape(n, -1).T, dtype=np.float64)
     if mocap is not None:   # (mocap_pos [n, nmocap, 3], mocap_quat [n, nmocap, 4])
         a["mocap_pos"] = np.ascontiguousarray(mocap[0].reshape(n, -1).T, dtype=np.float64)
         a["mocap_quat"] = np.ascontiguousarray(mocap[1].reshape(n, -1).T, dtype=np.float64)

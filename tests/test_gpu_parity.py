@@ -275,6 +275,34 @@ def test_golden_sensordata_camlight_transmission_energy():
     assert np.isfinite(bd.transmission()["actuator_moment"]).all()
 
 
+@pytest.mark.parametrize("name", util.XFRC_CASES)
+def test_golden_rne_post_constraint_with_xfrc_applied(name):
+    """mjb_setXfrcApplied: per-state d->xfrc_applied enters cfrc_ext / cfrc_int of mj_rnePostConstraint
+    (engine_core_smooth.c:2039-2049) and the force / torque sensors, not qfrc_inverse."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.xfrc_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_RNEPOST, nconmax=704, njmax=1408)
+    bd.set_state(qpos, qvel, qacc)
+    bd.set_xfrc_applied(util.xfrc_samples(model, n))
+    assert bd.inverse() == 0
+    post = bd.rne_post_constraint()
+    for k in ("cacc", "cfrc_int", "cfrc_ext"):
+        nviol, worst = util.spatial_violations(post[k], ref[k])
+        assert nviol == 0, (k, nviol, worst)
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    if "sensordata" in ref:
+        nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"])
+        assert nviol == 0, (nviol, worst)
+    with_x = post["cfrc_ext"].copy()
+    bd.set_xfrc_applied(None)                 # back to zero applied wrenches
+    assert bd.inverse() == 0
+    assert np.abs(bd.rne_post_constraint()["cfrc_ext"] - with_x).max() > 1
+
+
 def test_rne_post_constraint_newton_euler_balance():
     """Size-independent property on 2^16 humanoid states: for a free-floating tree the root's
     cfrc_int is the wrench its (force-free) free joint transmits, so it equals qfrc_inverse of the

@@ -99,6 +99,31 @@ def test_rne_post_constraint_outputs(name):
     assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
 
 
+@pytest.mark.parametrize("name", util.XFRC_CASES)
+def test_rne_post_constraint_with_xfrc_applied(name):
+    """Per-state d->xfrc_applied enters cfrc_ext / cfrc_int (engine_core_smooth.c:2039-2049) and the force /
+    torque sensors, not qfrc_inverse; against the reference's mj_inverse + mj_rnePostConstraint."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.xfrc_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    x = util.xfrc_samples(model, n)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200, post=True, xfrc=x)
+    nb = model.int("nbody")
+    for k in ("cacc", "cfrc_int", "cfrc_ext"):
+        nviol, worst = util.spatial_violations(out[k].reshape(n, nb, 6), ref[k])
+        assert nviol == 0, (k, nviol, worst)
+    nviol, worst = util.qfrc_violations_scaled(out["qfrc_inverse"], ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    if "sensordata" in ref:
+        nviol, worst = util.sensor_violations(model, out["sensordata"], ref["sensordata"])
+        assert nviol == 0, (nviol, worst)
+    # and the applied wrenches do change the outputs
+    plain = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200, post=True)
+    assert np.abs(plain["cfrc_ext"] - out["cfrc_ext"]).max() > 1
+
+
 @pytest.mark.parametrize("name", util.BIAS_CASES)
 def test_qfrc_bias(name):
     """qfrc_bias = mj_rne without accelerations (mj_fwdVelocity, engine_forward.c:228), strict

@@ -133,6 +133,26 @@ def camlight_fixture(name):
             int(z["nstate"]), tuple(z["z_range"]))
 
 
+XFRC_CASES = ["humanoid_xfrc", "sensors_xfrc", "weld_xfrc", "humanoids22_xfrc"]
+
+
+def xfrc_samples(model, nstate):
+    """The seeded applied wrenches of tests/golden/make_golden.py::xfrc_samples."""
+    rng = np.random.RandomState(20250331)
+    nb = model.int("nbody")
+    x = rng.normal(0, 5, (nstate, nb, 6)) * (rng.uniform(0, 1, (nstate, nb, 1)) < 0.5)
+    x[:, 0] = 0
+    return x
+
+
+def xfrc_fixture(name):
+    """(path of the base case's MJB, npz dict with cacc / cfrc_int / cfrc_ext [/ sensordata], nstate, z_range)
+    of a tests/golden/*_xfrc.npz fixture (mj_rnePostConstraint with per-state xfrc_applied)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in z.files},
+            int(z["nstate"]), tuple(z["z_range"]))
+
+
 def transmission_fixture(name):
     """(path of the base case's MJB, dict with actuator_length [n, nu], actuator_moment [n, nu, nv] (dense),
     actuator_velocity [n, nu] of the reference, nstate, z_range) of a tests/golden/*_trn.npz fixture."""
