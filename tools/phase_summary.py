@@ -30,7 +30,10 @@ def main():
     rep, nstates = sys.argv[1], float(sys.argv[2])
     peak_tf = float(sys.argv[3]) if len(sys.argv) > 3 else 36.6
     peak_gbs = float(sys.argv[4]) if len(sys.argv) > 4 else 6541.8
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.csv
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
