@@ -1512,7 +1512,8 @@ MJB_HD inline void forward_sweep(Ctx& c) {
     quat2Mat(mat, quat);
     // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
     // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
-    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.cam_xpos || c.out.actuator_length) {
+    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.cam_xpos || c.out.actuator_length ||
+        c.out.xfrc_applied) {
       stc(xquat, 4*b, quat, 4);
       stc(xpos, 3*b, pos, 3);
     }

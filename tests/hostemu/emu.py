@@ -43,7 +43,7 @@ def available():
 
 
 def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None, camlight=False,
-        transmission=False, xfrc=None):
+        transmission=False, xfrc=None, dump=True):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -96,6 +96,8 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         nu = max(1, model.int("nu"))
         a.update(actuator_length=np.zeros((nu, n)), actuator_moment=np.zeros((nu * max(1, nv), n)),
                  actuator_velocity=np.zeros((nu, n)))
+    if not dump:            # like the product: rows of the scratch are stored only where a later stage reads them
+        del a["scratch_dump"]
     o = Outputs(**{k: v.ctypes.data for k, v in a.items()})   # absent members stay NULL
     err = ctypes.create_string_buffer(1000)
     qp, qv, qa = (np.ascontiguousarray(x.T, dtype=np.float64) for x in (qpos, qvel, qacc))

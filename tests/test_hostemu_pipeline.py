@@ -99,6 +99,25 @@ def test_rne_post_constraint_outputs(name):
     assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
 
 
+@pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld",
+                                  "humanoid_invdiscrete", "mocap"])
+def test_outputs_do_not_depend_on_the_debug_dump(name):
+    """The product stores a scratch row only where a later stage reads it; the debug dump (mjbOUT_INTERNAL,
+    used by the other tests of this file) stores everything. Same results either way, bit for bit."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    n = min(32, int(ref["nstate"]))
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(ref["z_range"]))
+    kw = dict(nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]))
+    a = emu.run(model, qpos, qvel, qacc, **kw)
+    b = emu.run(model, qpos, qvel, qacc, dump=False, **kw)
+    for k in b:
+        if k != "scratch_dump":
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
 @pytest.mark.parametrize("name", util.XFRC_CASES)
 def test_rne_post_constraint_with_xfrc_applied(name):
     """Per-state d->xfrc_applied enters cfrc_ext / cfrc_int (engine_core_smooth.c:2039-2049) and the force /
@@ -109,7 +128,7 @@ def test_rne_post_constraint_with_xfrc_applied(name):
     model = mjb.Model.from_mjb(path)
     qpos, qvel, qacc = generate_states(model, n, z_range=zr)
     x = util.xfrc_samples(model, n)
-    out = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200, post=True, xfrc=x)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=640, njmax=1200, post=True, xfrc=x, dump=False)
     nb = model.int("nbody")
     for k in ("cacc", "cfrc_int", "cfrc_ext"):
         nviol, worst = util.spatial_violations(out[k].reshape(n, nb, 6), ref[k])
@@ -203,7 +222,7 @@ def test_camlight(name):
     path, ref, n, zr = util.camlight_fixture(name)
     model = mjb.Model.from_mjb(path)
     qpos, qvel, qacc = generate_states(model, n, z_range=zr)
-    out = emu.run(model, qpos, qvel, qacc, camlight=True)
+    out = emu.run(model, qpos, qvel, qacc, camlight=True, dump=False)
     for k in ("cam_xpos", "cam_xmat", "light_xpos", "light_xdir"):
         np.testing.assert_array_equal(out[k].reshape(ref[k].shape), ref[k], err_msg=k)
 
@@ -218,7 +237,7 @@ def test_transmission(name):
     path, ref, n, zr = util.transmission_fixture(name)
     model = mjb.Model.from_mjb(path)
     qpos, qvel, qacc = generate_states(model, n, z_range=zr)
-    out = emu.run(model, qpos, qvel, qacc, transmission=True)
+    out = emu.run(model, qpos, qvel, qacc, transmission=True, dump=False)
     nu, nv = model.int("nu"), model.int("nv")
     np.testing.assert_allclose(out["actuator_length"], ref["actuator_length"], rtol=1e-12, atol=1e-14)
     mom = out["actuator_moment"].reshape(n, nu, nv)
