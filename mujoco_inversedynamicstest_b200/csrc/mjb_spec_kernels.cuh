@@ -59,9 +59,9 @@ __device__ __forceinline__ void spec_bind(Ctx& c, const LaunchArgs& a, long long
 // thousand instructions each (MJBS_SMOOTH_STAGES / MJBS_INERTIA_STAGES, chosen by the host from a
 // per-body cost estimate), one kernel per range, so that each kernel's code stays resident in the
 // instruction cache; stages hand over through the same scratch rows the generic kernels use.
-// measured on the humanoid (profiles/, GPU call X): 3 resident CTAs 2.66 ms, 2 or 1: 2.75 ms
+// measured on the humanoid (GPU calls X, Y): resident CTAs 1 or 2: 2.75 ms, 3: 2.66 ms, 4: 2.62 ms
 #ifndef MJBS_SMOOTH_CTAS
-#define MJBS_SMOOTH_CTAS 3
+#define MJBS_SMOOTH_CTAS 4
 #endif
 #ifndef MJBS_INERTIA_CTAS
 #define MJBS_INERTIA_CTAS 3

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Fill the model-specialisation cache (mjb_precompile: NVRTC, no GPU needed) for committed models.
 
-    python tools/precompile.py [name ...]        # names of tests/golden/*.mjb.gz; default: all
+    python tools/precompile.py [--torch] [name ...]        # names of tests/golden/*.mjb.gz; default: all
+
+--torch: import torch first. A process that has torch loaded resolves libnvrtc to the copy bundled with
+torch (another NVRTC version, hence another cache key) -- bench.py is such a process, the tests are not.
 """
 import ctypes
 import glob
@@ -14,6 +17,8 @@ sys.path.insert(0, ROOT)
 
 
 def one(name):
+    if os.environ.get("MJB_PRECOMPILE_TORCH"):
+        import torch  # noqa: F401
     import mujoco_inversedynamicstest_b200 as mjb
     from mujoco_inversedynamicstest_b200._lib import lib
     m = mjb.Model.from_mjb(os.path.join(ROOT, "tests", "golden", name + ".mjb.gz"))
@@ -23,6 +28,9 @@ def one(name):
 
 
 def main(names):
+    if "--torch" in names:
+        names = [n for n in names if n != "--torch"]
+        os.environ["MJB_PRECOMPILE_TORCH"] = "1"
     if not names:
         names = sorted(os.path.basename(p)[:-7] for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.mjb.gz")))
     bad = 0
