@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_wide_kernel(Launc
       float m = 0;
       for (int g = lane; g < ngeom; g += 32) {
         // geoms outside every candidate pair are not stored by the sweep (geom_store, mjb_upload.cc)
-        const bool stored = geom_store[g] != 0;
+        const bool stored = (geom_store[g] & 3) != 0;
         const double* gv = gblk + ((off_gxpos + 4 * (size_t)g) << 5);
         const float x = stored ? (float)(gv[0] - r0) : 0.f;
         const float y = stored ? (float)(gv[1] - r1) : 0.f;
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(512, kWideCtas) contact_scan_pairs_kernel(Laun
                  r2 = gblk[((off_gxpos + 4 * gref) << 5) + 2];
     float m = 0;
     for (int g = lane; g < gp; g += 32) {
-      const bool stored = g < ngeom && geom_store[g] != 0;
+      const bool stored = g < ngeom && (geom_store[g] & 3) != 0;
       const double* gv = gblk + ((off_gxpos + 4 * (size_t)(g < ngeom ? g : 0)) << 5);
       const float x = stored ? (float)(gv[0] - r0) : 0.f;
       const float y = stored ? (float)(gv[1] - r1) : 0.f;

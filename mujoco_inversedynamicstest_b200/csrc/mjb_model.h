@@ -77,7 +77,7 @@
   X(ray_geom) /* ngeom (empty without rangefinder sensors): 1 if mj_ray tests the geom (visible: ray_eliminate) */ \
   X(actuator_trn) /* nu*2 : actuator_trnid (object, reference / slider site) */ \
   X(tendon_active) /* ntendon: 1 if the tendon carries a force (limit, friction loss, spring, damper) */ \
-  X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame */ \
+  X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame, bit2 full frame in runs with transmission / sensor outputs only */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(sensor_int) /* nsensor*MJB_SEN_NI : sensors evaluated on the device, see MJB_SEN_*       */ \
   X(scan_int)  /* ncand*2 : compact rows of the bounding-sphere scan: geom 1 | filter kind << 28, geom 2      */ \

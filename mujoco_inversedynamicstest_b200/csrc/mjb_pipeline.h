@@ -1306,7 +1306,8 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   const int g0 = body_geomadr[b], gn = body_geomnum[b];
   MJB_UNROLL
   for (int g = g0; g < g0 + gn; g++) {
-    const int store = dump ? 3 : geom_store[g];
+    int store = dump ? 3 : geom_store[g];
+    if (store & 4) store = (c.out.actuator_length || c.out.sensordata) ? 3 : (store & 3);
     if (!store) continue;
     const int sf = geom_sameframe[g];
     double gp[3], gm[9];
@@ -3044,7 +3045,7 @@ MJB_HD inline int contact_scan(Ctx& c) {
       double O[3], r = 0;
       ldn(O, org, 3*tree_int[3*t], 3);
       for (int g = tree_int[3*t + 1]; g < tree_int[3*t + 2]; g++) {
-        if (!geom_store[g]) continue;
+        if (!(geom_store[g] & 3)) continue;     // bit 2 alone: kept only in runs with transmission / sensor outputs
         double p[3];
         load_geom_pos(c, g, p);
         const double d[3] = {p[0] - O[0], p[1] - O[1], p[2] - O[2]};

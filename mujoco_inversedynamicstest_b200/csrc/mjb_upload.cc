@@ -971,7 +971,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       if (!tendon_active[t] && !tendon_trn[t]) continue;
       for (int j = 0; j < m->tendon_num[t]; j++) {
         const int wt = m->wrap_type[m->tendon_adr[t] + j];
-        if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) geom_store[m->wrap_objid[m->tendon_adr[t] + j]] |= 3;
+        // bit 2: only the output-only stages (mj_transmission, tendon sensors) walk this tendon -- the frame is
+        // kept only in runs that produce those outputs
+        if (wt == mjWRAP_SPHERE || wt == mjWRAP_CYLINDER) geom_store[m->wrap_objid[m->tendon_adr[t] + j]] |= tendon_active[t] ? 3 : 4;
       }
     }
     pushInts(MJB_I_geom_store, geom_store.data(), geom_store.size());

@@ -99,7 +99,7 @@ def test_rne_post_constraint_outputs(name):
     assert (out["cfrc_ext"].reshape(n, nb, 6)[zero] == 0).all()
 
 
-@pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld",
+@pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld", "arm26", "transmission",
                                   "humanoid_invdiscrete", "mocap"])
 def test_outputs_do_not_depend_on_the_debug_dump(name):
     """The product stores a scratch row only where a later stage reads it; the debug dump (mjbOUT_INTERNAL,
