@@ -60,8 +60,9 @@ __device__ __forceinline__ void spec_bind(Ctx& c, const LaunchArgs& a, long long
 // per-body cost estimate), one kernel per range, so that each kernel's code stays resident in the
 // instruction cache; stages hand over through the same scratch rows the generic kernels use.
 // measured on the humanoid (GPU calls X, Y): resident CTAs 1 or 2: 2.75 ms, 3: 2.66 ms, 4: 2.62 ms
+// (arm26, 3 bodies: 0.517 ms with 2, 0.548 ms with 4 -- small models keep 2)
 #ifndef MJBS_SMOOTH_CTAS
-#define MJBS_SMOOTH_CTAS 4
+#define MJBS_SMOOTH_CTAS (MJB_SPEC_NBODY >= 8 ? 4 : 2)
 #endif
 #ifndef MJBS_INERTIA_CTAS
 #define MJBS_INERTIA_CTAS 3
