@@ -51,8 +51,8 @@ typedef enum mjbOut_ {
                                * them inside mj_invPosition (engine_core_smooth.c:275-389)            */
   mjbOUT_TRANSMISSION = 1 << 8 /* actuator_length, actuator_moment (dense nu x nv), actuator_velocity:*
                                * mj_transmission inside mj_invPosition (engine_core_smooth.c:865-1346)*
-                               * and mj_fwdVelocity (engine_forward.c:216). Models with adhesion      *
-                               * actuators (mjTRN_BODY) are refused when this bit is set.             */
+                               * and mj_fwdVelocity (engine_forward.c:216). Adhesion actuators        *
+                               * (mjTRN_BODY) read the contact list: COUNTS and CONTACT come with it. */
 } mjbOut;
 
 /* per-state status bits, the batched form of d->warning[] (engine_forward.c:53-102,

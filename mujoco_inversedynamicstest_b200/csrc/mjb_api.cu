@@ -229,11 +229,10 @@ mjbData* mjb_makeData(const mjModel* m, int nbatch_max, int device, unsigned out
   }
 
   if (outmask & mjbOUT_TRANSMISSION) {
-    // adhesion actuators take their moment from the contact normals' Jacobians (engine_core_smooth.c:1222-1330)
+    // adhesion actuators take their moment from the contact normals (engine_core_smooth.c:1222-1330): the
+    // contact list is an input of the transmission stage
     for (int i = 0; i < m->nu; i++) {
-      if (m->actuator_trntype[i] == mjTRN_BODY) {
-        return fail("mjb_makeData: mjbOUT_TRANSMISSION is not available for models with adhesion actuators (mjTRN_BODY)");
-      }
+      if (m->actuator_trntype[i] == mjTRN_BODY) outmask |= mjbOUT_COUNTS | mjbOUT_CONTACT;
     }
   }
 
@@ -962,6 +961,10 @@ int mjb_inverseFDSensor(const mjModel* m, mjbData* d, int nbatch, mjtNum eps, in
   // the perturbed copies are evaluated in an inner batch that holds no per-state mocap poses
   if (d->d_mocap_pos || d->d_mocap_quat) {
     d->error = "mjb_inverseFD: per-state mocap poses (mjb_setMocap) are not carried into the perturbed batch";
+    return -1;
+  }
+  if (d->out.xfrc_applied && (DsDq || DsDv || DsDa)) {
+    d->error = "mjb_inverseFD: per-state applied wrenches (mjb_setXfrcApplied) are not carried into the perturbed batch";
     return -1;
   }
   if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;

@@ -4095,7 +4095,7 @@ MJB_HD inline void camlight(Ctx& c) {
 // The Jacobians of the reference (mj_jacSite, mj_jacPointAxis, ten_J) are never formed: a moment row
 // is the projection of a wrench on the dof chain of a body,
 //   row[j] += s * ( F . (ang_j x (p - O) + lin_j) + T . ang_j ),   cdof_j = (ang_j, lin_j) about O,
-// the column of (jacp' F + jacr' T). Adhesion actuators (mjTRN_BODY) are refused in mjb_makeData.
+// the column of (jacp' F + jacr' T).
 MJB_HD inline void trn_project(Ctx& c, double* row, int body, int stop_dof, const double* p, const double* F,
                                const double* T, double s) {
   const int wb = MI(body_weldid)[body];
@@ -4249,6 +4249,34 @@ MJB_HD inline void transmission(Ctx& c) {
           trn_project(c, row, site_bodyid[id], common, p, nullptr, w, 1.0);
           trn_project(c, row, site_bodyid[refid], common, pr, nullptr, w, -1.0);
         }
+      }
+    } else if (type == MJB_TRN_BODY) {
+      // adhesion (:1222-1330): minus the mean over the body's contacts (active, or excluded in the gap) of
+      // the contact normal's Jacobian row, normal . (jacp(body 2) - jacp(body 1)) at the contact point. For
+      // active contacts the reference forms it from the efc rows (the normal row, or the pyramid's rows
+      // with equal weights, whose tangential parts cancel); the contact list is this stage's input here
+      // (mjb_makeData switches the contact outputs on for models with such actuators)
+      const int* geom_bodyid = MI(geom_bodyid);
+      const int ncon = c.out.counts[c.s];
+      int counter = 0;
+      for (int k = 0; k < ncon && k < c.nconmax; k++) {
+        const int b1 = geom_bodyid[c.out.contact_geom[(size_t)(2*k)*N + c.s]];
+        const int b2 = geom_bodyid[c.out.contact_geom[(size_t)(2*k + 1)*N + c.s]];
+        if (b1 != id && b2 != id) continue;
+        const int excl = c.out.contact_info[(size_t)(3*k + 1)*N + c.s];
+        if (excl != 0 && excl != 1) continue;
+        counter++;
+        double pos[3], nrm[3];
+        for (int j = 0; j < 3; j++) {
+          pos[j] = c.out.contact_num[(size_t)(13*k + 1 + j)*N + c.s];
+          nrm[j] = c.out.contact_num[(size_t)(13*k + 4 + j)*N + c.s];
+        }
+        trn_project(c, row, b2, -1, pos, nrm, nullptr, 1.0);
+        trn_project(c, row, b1, -1, pos, nrm, nullptr, -1.0);
+      }
+      if (counter) {
+        const double sc = -1.0/counter;
+        for (int j = 0; j < nv; j++) row[(size_t)j*N] *= sc;
       }
     }
     c.out.actuator_length[(size_t)i*N + c.s] = length;

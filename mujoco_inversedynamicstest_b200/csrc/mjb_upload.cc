@@ -304,7 +304,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         sensor_ray = true;
         break;
       case mjSENS_ACTUATORPOS: case mjSENS_ACTUATORVEL:
-        ok = m->actuator_trntype[m->sensor_objid[i]] != mjTRN_BODY; sensor_trn = true; break;
+        ok = true; sensor_trn = true; break;
       case mjSENS_E_POTENTIAL: case mjSENS_E_KINETIC:
         ok = true; sensor_energy = true; break;
       case mjSENS_TOUCH:

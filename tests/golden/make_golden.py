@@ -72,6 +72,9 @@ CASES = {
     "implicit": ("repo:tests/golden/models/implicitfast.xml", {"integrator": 2}, 128, (0.2, 1.2), 16, 64),
     # sensors that read mj_camlight / mj_transmission outputs, magnetometer, clock
     "sensors2": ("repo:tests/golden/models/sensors2.xml", {}, 256, (0.2, 1.2), 16, 64),
+    # adhesion actuators (mjTRN_BODY): moments from the contact normals, both cones
+    "adhesion": ("repo:tests/golden/models/adhesion.xml", {}, 256, (0.0, 0.3), 48, 200),
+    "adhesion_elliptic": ("repo:tests/golden/models/adhesion.xml", {"cone": 1}, 128, (0.0, 0.3), 48, 200),
     # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)
     "transmission": ("repo:tests/golden/models/transmission.xml", {}, 128, (0.2, 1.2), 16, 64),
 }
@@ -362,7 +365,8 @@ def make_camlight_case(name):
 # mj_fwdVelocity (engine_forward.c:216): actuator_length, the compressed actuator_moment expanded to the
 # dense nu x nv matrix, actuator_velocity: name -> (case whose model / stream is used, nstate)
 TRANSMISSION_CASES = {"transmission_trn": ("transmission", 128), "humanoid_trn": ("humanoid", 32),
-                      "arm26_trn": ("arm26", 64), "slider_crank_trn": ("slider_crank_nocontact", 64)}
+                      "arm26_trn": ("arm26", 64), "slider_crank_trn": ("slider_crank_nocontact", 64),
+                      "adhesion_trn": ("adhesion", 256), "adhesion_elliptic_trn": ("adhesion_elliptic", 128)}
 
 
 def make_transmission_case(name):

@@ -21,7 +21,8 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
-         "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit"]
+         "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
+         "adhesion_elliptic"]
 
 
 def _run(name):
@@ -227,7 +228,8 @@ def test_camlight(name):
         np.testing.assert_array_equal(out[k].reshape(ref[k].shape), ref[k], err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["transmission_trn", "humanoid_trn", "arm26_trn", "slider_crank_trn"])
+@pytest.mark.parametrize("name", ["transmission_trn", "humanoid_trn", "arm26_trn", "slider_crank_trn", "adhesion_trn",
+                                  "adhesion_elliptic_trn"])
 def test_transmission(name):
     """actuator_length / actuator_moment (dense) / actuator_velocity as mj_transmission and mj_fwdVelocity
     leave them inside mj_inverse (engine_core_smooth.c:865-1346, engine_forward.c:216): every
