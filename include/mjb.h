@@ -130,6 +130,11 @@ MJB_API int mjb_setMocap(mjbData* d, int nbatch, const mjtNum* mocap_pos, const 
  * mj_rnePostConstraint outputs cfrc_ext / cfrc_int (src/engine/engine_core_smooth.c:2039-2049) and the
  * force / torque sensors that read cfrc_int. Needs mjbOUT_RNEPOST (or such sensors) to have any effect. */
 MJB_API int mjb_setXfrcApplied(mjbData* d, int nbatch, const mjtNum* xfrc_applied);
+/* per-state d->eq_active (include/mujoco/mjdata.h; read by mj_instantiateEquality,
+ * src/engine/engine_core_constraint.c:493-763): HOST array nbatch x neq of mjtByte, used by every following
+ * mjb_inverse until replaced; NULL returns to the model's eq_active0 (what mj_makeData / mj_resetData
+ * leave in mjData). Row numbers of everything after the equality block follow per state. */
+MJB_API int mjb_setEqActive(mjbData* d, int nbatch, const unsigned char* eq_active);
 /* adopt DEVICE structure-of-arrays inputs without a copy: (nq|nv) x stride, stride >= nbatch.
  * Pass NULL pointers to return to the internal buffers. */
 MJB_API int mjb_setStateDevice(mjbData* d, const mjtNum* qpos, const mjtNum* qvel,

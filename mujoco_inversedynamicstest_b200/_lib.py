@@ -25,6 +25,7 @@ SIGNATURES = {
     "mjb_setState": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mjb_setMocap": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "mjb_setXfrcApplied": (c_int, [c_void_p, c_int, c_void_p]),
+    "mjb_setEqActive": (c_int, [c_void_p, c_int, c_void_p]),
     "mjb_setStateDevice": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll]),
     "mjb_inverse": (c_int, [c_void_p, c_void_p, c_int]),
     "mjb_inverseAsync": (c_int, [c_void_p, c_void_p, c_int]),

@@ -182,6 +182,14 @@ class BatchData:
         x = np.ascontiguousarray(xfrc_applied, dtype=np.float64)
         self._check(lib().mjb_setXfrcApplied(self._d, x.shape[0], x.ctypes.data), "mjb_setXfrcApplied")
 
+    def set_eq_active(self, eq_active):
+        """Per-state d->eq_active [nbatch, neq] (0 / 1); None returns to the model's eq_active0."""
+        if eq_active is None:
+            self._check(lib().mjb_setEqActive(self._d, 0, None), "mjb_setEqActive")
+            return
+        e = np.ascontiguousarray(eq_active, dtype=np.uint8)
+        self._check(lib().mjb_setEqActive(self._d, e.shape[0], e.ctypes.data), "mjb_setEqActive")
+
     def set_mocap(self, mocap_pos=None, mocap_quat=None):
         """Per-state mocap poses [nbatch, nmocap, 3] / [nbatch, nmocap, 4]; None: the model pose."""
         if mocap_pos is None or mocap_quat is None:

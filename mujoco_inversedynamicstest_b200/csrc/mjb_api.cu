@@ -55,6 +55,7 @@ struct mjbData_ {
   int* d_cmask = nullptr;      // per-state survivor masks of the warp-per-state scans (one state's words contiguous)
   int* d_pair_ci = nullptr;    // geom pair -> candidate index (ngeom x ngeom), long candidate lists only   // per-warp candidate buffers of the warp-per-state scan (long candidate lists)
   int items_cap = 0, contacts_cap = 0;
+  double* d_eq_active = nullptr;       // per-state d->eq_active [neq][stride] as 0 / 1 (mjb_setEqActive)
   double* d_xfrc_applied = nullptr;    // per-state d->xfrc_applied [nbody*6][stride] (mjb_setXfrcApplied)
   double* d_qacc_discrete = nullptr;   // continuous-time qacc when mjENBL_INVDISCRETE converts it
   const double *in_qpos = nullptr, *in_qvel = nullptr, *in_qacc = nullptr;
@@ -540,7 +541,7 @@ void mjb_deleteData(mjbData* d) {
   cudaFree(d->d_scan_buf);
   cudaFree(d->d_pair_ci);
   cudaFree(d->d_cmask);
-  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete); cudaFree(d->d_xfrc_applied);
+  cudaFree(d->d_qpos); cudaFree(d->d_qvel); cudaFree(d->d_qacc); cudaFree(d->d_qacc_discrete); cudaFree(d->d_xfrc_applied); cudaFree(d->d_eq_active);
   cudaFree(d->d_stage); cudaFree(d->d_counter);
   cudaFree(d->d_mocap_pos); cudaFree(d->d_mocap_quat);
   cudaFree(d->d_fwd_qforce); cudaFree(d->d_fwd_xfrc); cudaFree(d->d_fwd_qc); cudaFree(d->d_fwdinv);
@@ -652,6 +653,33 @@ int mjb_setXfrcApplied(mjbData* d, int nbatch, const mjtNum* xfrc_applied) {
   ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_setXfrcApplied");   // the staging buffer is shared with mjb_setState
   if (!ok) return -1;
   o.xfrc_applied = d->d_xfrc_applied;
+  return 0;
+}
+
+int mjb_setEqActive(mjbData* d, int nbatch, const unsigned char* eq_active) {
+  if (!d->shards.empty()) {
+    const int ne = d->hdr.neq;
+    return forShards(d, nbatch, false, [&](mjbData* sh, ShardRange r) {
+      return mjb_setEqActive(sh, r.n, eq_active ? eq_active + r.first * ne : nullptr);
+    }) ? 0 : -1;
+  }
+  d->stream_dirty = true;
+  const mjbHdr& H = d->hdr;
+  mjb::Outputs& o = d->out;
+  if (!eq_active || H.neq == 0) { o.eq_active = nullptr; return 0; }
+  if (nbatch < 0 || nbatch > d->nbatch_max) { d->error = "mjb_setEqActive: nbatch out of range"; return -1; }
+  if (!check(d, cudaSetDevice(d->device), "cudaSetDevice")) return -1;
+  const size_t S = (size_t)d->stride, n = (size_t)nbatch, rows = (size_t)H.neq;
+  bool ok = true;
+  if (!d->d_eq_active) ok = ok && devAlloc(d, &d->d_eq_active, rows * S, "cudaMalloc(eq_active)");
+  if (!ok || !ensureStage(d, n * rows * sizeof(double))) return -1;
+  std::vector<double> flags(n * rows);                     // mjtByte -> 0 / 1 as doubles (the transposes are fp64)
+  for (size_t k = 0; k < flags.size(); k++) flags[k] = eq_active[k] ? 1.0 : 0.0;
+  ok = ok && check(d, cudaMemcpy(d->d_stage, flags.data(), flags.size() * sizeof(double), cudaMemcpyHostToDevice), "H2D eq_active");
+  ok = ok && check(d, mjb::launch_aos_to_soa((const double*)d->d_stage, d->d_eq_active, nbatch, (int)rows, d->stride, d->stream), "transpose eq_active");
+  ok = ok && check(d, cudaStreamSynchronize(d->stream), "mjb_setEqActive");
+  if (!ok) return -1;
+  o.eq_active = d->d_eq_active;
   return 0;
 }
 

@@ -141,6 +141,8 @@ struct Outputs {
   // d->xfrc_applied per state (INPUT; mjb_setXfrcApplied): [nbody*6][stride], force then torque per body.
   // mj_inverse itself ignores it; mj_rnePostConstraint adds it to cfrc_ext (engine_core_smooth.c:2039-2049)
   const double* xfrc_applied;
+  // d->eq_active per state (INPUT; mjb_setEqActive): [neq][stride], 0 / 1 as doubles; null: the model's eq_active0
+  const double* eq_active;
 };
 
 struct Ctx {
@@ -909,6 +911,29 @@ MJB_DI void weld_rot_map(double* res, const double* quat1, const double* quat, c
   res[0] = 0.5*q3[1]; res[1] = 0.5*q3[2]; res[2] = 0.5*q3[3];
 }
 
+// Equality constraint i enabled for this state: d->eq_active[i] when the caller has set per-state flags
+// (mjb_setEqActive), else the model's eq_active0 (what mj_makeData / mj_resetData leave in mjData).
+MJB_HD inline bool eq_enabled(Ctx& c, const int* ei, int i) {
+  return c.out.eq_active ? c.out.eq_active[(size_t)i*(size_t)c.N + c.s] != 0 : ei[MJB_EQI_ACTIVE] != 0;
+}
+// Number of equality rows of this state = first friction-loss row (mj_makeConstraint order). A model
+// constant (H.ne_rows, folded into the specialised kernels) unless per-state flags are set.
+MJB_HD inline int ne_base(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  if (H.neq == 0 || !c.out.eq_active) return H.ne_rows;
+  if ((H.disableflags & (MJB_DSBL_EQUALITY | MJB_DSBL_CONSTRAINT))) return 0;
+  const int* eq_int = MI(eq_int);
+  int n = 0;
+  for (int i = 0; i < H.neq; i++) {
+    const int* ei = eq_int + MJB_EQ_NI*i;
+    if (!eq_enabled(c, ei, i)) continue;
+    const int type = ei[MJB_EQI_TYPE];
+    if (type == 0 || type == 1) { if (!ei[MJB_EQI_SKIP]) n += type == 0 ? 3 : 6; }
+    else n++;
+  }
+  return n;
+}
+
 MJB_HD inline void equality_rows(Ctx& c) {
   const mjbHdr& H = *c.H;
   if (H.neq == 0 || (H.disableflags & MJB_DSBL_EQUALITY)) return;
@@ -922,7 +947,7 @@ MJB_HD inline void equality_rows(Ctx& c) {
     const int* ei = eq_int + MJB_EQ_NI*i;
     const double* en = eq_num + MJB_EQ_NN*i;
     const double* sp = sp_eq + MJB_SP_N*i;
-    if (!ei[MJB_EQI_ACTIVE]) continue;
+    if (!eq_enabled(c, ei, i)) continue;
     const int type = ei[MJB_EQI_TYPE];
     if (type == 0 || type == 1) {
       if (ei[MJB_EQI_SKIP]) continue;
@@ -1062,7 +1087,7 @@ MJB_HD inline double dof_friction_row(Ctx& c, int i, double qv, double qa) {
   const mjbHdr& H = *c.H;
   const int frow = MI(dof_frow)[i];
   if (frow < 0) return 0;
-  return scalar_row(c, H.ne_rows + frow, MJB_CNSTR_FRICTION_DOF, i, MD(sp_dof_friction) + MJB_SP_N*i,
+  return scalar_row(c, ne_base(c) + frow, MJB_CNSTR_FRICTION_DOF, i, MD(sp_dof_friction) + MJB_SP_N*i,
                     0, 0, MD(dof_invweight0)[i], qv, qa, MD(dof_frictionloss)[i]);
 }
 
@@ -1077,7 +1102,7 @@ MJB_HD inline double joint_limit_rows(Ctx& c, int jid, int dof, double q, double
     const double dist = side * (range[(side + 1)/2] - q);
     if (dist < margin) {
       // J = -side at this dof
-      const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
+      const double f = scalar_row(c, ne_base(c) + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
                                   MD(sp_jnt_limit) + MJB_SP_N*jid, dist, margin,
                                   MD(dof_invweight0)[dof], -side*qv, -side*qa, 0);
       acc += -side*f;
@@ -1163,7 +1188,7 @@ MJB_HD inline void quat_dof_forces(Ctx& c, int jid, int qadr, int dof, int jt, c
         // J = -angleAxis on the three dofs
         double vel = 0, jacc = 0;
         for (int r = 0; r < 3; r++) { vel += -aa[r]*qv[r]; jacc += -aa[r]*qa[r]; }
-        const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
+        const double f = scalar_row(c, ne_base(c) + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_JOINT, jid,
                                     MD(sp_jnt_limit) + MJB_SP_N*jid, dist, margin,
                                     MD(dof_invweight0)[d], vel, jacc, 0);
         for (int r = 0; r < 3; r++) qc[r] += -aa[r]*f;
@@ -1195,7 +1220,7 @@ MJB_HD inline void tendon_friction_rows(Ctx& c) {
   const int* wrap_objid = MI(wrap_objid); const int* jnt_dofadr = MI(jnt_dofadr);
   const double* wrap_prm = MD(wrap_prm);
   double* V = SC(ten_velocity); double* A = SC(ten_acc);
-  int row = H.ne_rows + H.nf_dof_rows;
+  int row = ne_base(c) + H.nf_dof_rows;
   MJB_UNROLL
   for (int t = 0; t < H.ntendon; t++) {
     if (tfl[t] > 0) {
@@ -1230,7 +1255,7 @@ MJB_HD inline void tendon_limit_rows(Ctx& c) {
       const double dist = side * (tendon_range[2*t + (side + 1)/2] - value);
       if (dist < margin) {
         // J = -side * ten_J
-        const double f = scalar_row(c, H.ne_rows + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_TENDON, t,
+        const double f = scalar_row(c, ne_base(c) + H.nf_rows + c.nl, MJB_CNSTR_LIMIT_TENDON, t,
                                     tsp + MJB_SP_N*t, dist, margin, tiw[t], -side*AT(V, t), -side*AT(A, t), 0);
         tendon_apply<kSpatial>(c, t, -side*f, qc, false);
         c.nl++;
@@ -3178,7 +3203,7 @@ MJB_HD inline void post_constraint_end(Ctx& c) {
     const int* eq_int = MI(eq_int);
     for (int i = 0; i < H.neq; i++) {
       const int* ei = eq_int + MJB_EQ_NI*i;
-      if (ei[MJB_EQI_TYPE] != 1 || !ei[MJB_EQI_ACTIVE] || ei[MJB_EQI_SKIP]) continue;
+      if (ei[MJB_EQI_TYPE] != 1 || !eq_enabled(c, ei, i) || ei[MJB_EQI_SKIP]) continue;
       double dT[3];
       ldn(dT, SC(weld_dt), 3*i, 3);
       for (int side = 0; side < 2; side++) {

@@ -227,6 +227,9 @@ REFH_API void refh_set_mocap(const double* pos, const double* quat) { refh_mocap
 /* per-state d->xfrc_applied for the batch loop (nbatch x nbody x 6), NULL: zero */
 static const double* refh_xfrc = NULL;
 REFH_API void refh_set_xfrc(const double* xfrc) { refh_xfrc = xfrc; }
+/* per-state d->eq_active for the batch loop (nbatch x neq bytes), NULL: eq_active0 */
+static const unsigned char* refh_eq_active = NULL;
+REFH_API void refh_set_eq_active(const unsigned char* a) { refh_eq_active = a; }
 
 static void* run_chunk(void* arg) {
   refhChunk* c = (refhChunk*)arg;
@@ -242,6 +245,7 @@ static void* run_chunk(void* arg) {
       mju_copy(d->mocap_quat, refh_mocap_quat + i*4*m->nmocap, 4*m->nmocap);
     }
     if (refh_xfrc) mju_copy(d->xfrc_applied, refh_xfrc + (size_t)i*6*m->nbody, 6*m->nbody);
+    if (refh_eq_active) memcpy(d->eq_active, refh_eq_active + (size_t)i*m->neq, (size_t)m->neq);
     mj_inverse(m, d);
     if (refh_post_constraint) mj_rnePostConstraint(m, d);
     if (c->qfrc_inverse) mju_copy(c->qfrc_inverse + i*m->nv, d->qfrc_inverse, m->nv);

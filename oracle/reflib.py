@@ -207,7 +207,7 @@ class Model:
                             p(out["qacc"]), p(out["qfrc_actuator"]), p(out["qfrc_constraint"]), p(out["fwdinv"]))
         return out
 
-    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1, mocap=None, xfrc=None):
+    def inverse_batch(self, qpos, qvel, qacc, fields=None, nthread=1, mocap=None, xfrc=None, eq_active=None):
         """Loop the reference's mj_inverse over the batch.
 
         fields: {name: maxrows} of extra mjData arrays / contact_* pseudo fields / scalar counters
@@ -253,6 +253,13 @@ class Model:
             L.refh_set_xfrc(xf.ctypes.data)
         else:
             L.refh_set_xfrc(None)
+        L.refh_set_eq_active.argtypes = [ctypes.c_void_p]
+        ea = None
+        if eq_active is not None:  # d->eq_active per state [n, neq] bytes
+            ea = np.ascontiguousarray(eq_active, dtype=np.uint8)
+            L.refh_set_eq_active(ea.ctypes.data)
+        else:
+            L.refh_set_eq_active(None)
         rq = (_Request * max(1, len(reqs)))()
         for i, (nm, arr, mr) in enumerate(reqs):
             rq[i].name = nm
@@ -262,6 +269,7 @@ class Model:
                                  out["qfrc_inverse"].ctypes.data, rq, len(reqs), int(nthread))
         L.refh_set_mocap(None, None)
         L.refh_set_xfrc(None)
+        L.refh_set_eq_active(None)
         if t < 0:
             raise RuntimeError("refh_inverse_batch: unknown field requested")
         return out, t

@@ -426,10 +426,44 @@ def make_xfrc_case(name):
     print(f"{name}: nbody={m.int('nbody')} states={nstate} max|cfrc_ext|={np.abs(out['cfrc_ext']).max():.3g}")
 
 
+# per-state d->eq_active (mj_instantiateEquality skips inactive constraints; every later row moves up):
+# name -> (case whose model / state stream is used, nstate)
+EQACTIVE_CASES = {"zoo_eqactive": ("zoo", 128), "weld_eqactive": ("weld", 64), "connect_eqactive": ("connect", 64),
+                  "mocap_eqactive": ("mocap", 64)}
+
+
+def eq_active_samples(m, nstate):
+    """Seeded per-state flags [nstate, neq]: each constraint on with probability 0.6; state 0 all off, state 1 all on."""
+    rng = np.random.RandomState(20250331)
+    e = (rng.uniform(0, 1, (nstate, m.int("neq"))) < 0.6).astype(np.uint8)
+    e[0] = 0
+    e[1] = 1
+    return e
+
+
+def make_eqactive_case(name):
+    base, nstate = EQACTIVE_CASES[name]
+    xml, opts, _, zr, nconmax, njmax = CASES[base]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:")
+                              else reflib.reference_path(xml))
+    for k, v in opts.items():
+        m.set_opt_int(k, m.get_opt_int(k) | v if k == "disableflags" else v)
+    qpos, qvel, qacc = generate_states(m, nstate, z_range=zr)
+    fields = {"ncon": 1, "ne": 1, "nf": 1, "nl": 1, "nefc": 1, "contact_geom": nconmax, "contact_efc_address": nconmax,
+              "efc_type": njmax, "efc_id": njmax, "efc_state": njmax, "efc_force": njmax, "efc_pos": njmax,
+              "qfrc_constraint": None, "cacc": None, "cfrc_int": None, "cfrc_ext": None}
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields, eq_active=eq_active_samples(m, nstate))
+    assert out["ncon"].max() <= nconmax and out["nefc"].max() <= njmax
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), base=np.array(base), nstate=np.array(nstate),
+                        z_range=np.array(zr), nconmax=np.array(nconmax), njmax=np.array(njmax),
+                        **{k: (v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v) for k, v in out.items()})
+    print(f"{name}: neq={m.int('neq')} states={nstate} ne min/mean/max={out['ne'].min()}/{out['ne'].mean():.2f}/{out['ne'].max()}")
+
+
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
                  list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES) + list(CAMLIGHT_CASES) +
-                 list(TRANSMISSION_CASES) + list(XFRC_CASES)):
-        (make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(TRANSMISSION_CASES) + list(XFRC_CASES) + list(EQACTIVE_CASES)):
+        (make_eqactive_case if case in EQACTIVE_CASES else make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

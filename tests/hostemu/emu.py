@@ -13,7 +13,7 @@ _FIELDS = ["qfrc_inverse", "qfrc_constraint", "qfrc_passive", "counts", "status"
            "contact_info", "contact_num", "efc_int", "efc_num", "qM", "qLD", "qLDiagInv",
            "scratch_dump", "cacc", "cfrc_int", "cfrc_ext", "sensordata", "qfrc_bias", "fwd_qforce", "fwd_xfrc", "fwd_qfrc_constraint", "fwdinv", "mocap_pos", "mocap_quat", "energy",
            "cam_xpos", "cam_xmat", "light_xpos", "light_xdir",
-           "actuator_length", "actuator_moment", "actuator_velocity", "xfrc_applied"]
+           "actuator_length", "actuator_moment", "actuator_velocity", "xfrc_applied", "eq_active"]
 
 
 class Outputs(ctypes.Structure):
@@ -43,7 +43,7 @@ def available():
 
 
 def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mocap=None, camlight=False,
-        transmission=False, xfrc=None, dump=True):
+        transmission=False, xfrc=None, dump=True, eq_active=None):
     """model: object with .ptr (mjModel*) and .int(). Returns dict of arrays shaped like the
     Python host mirror's getters ([n, rows])."""
     L = lib()
@@ -72,6 +72,8 @@ def run(model, qpos, qvel, qacc, nconmax=64, njmax=256, post=False, fwd=None, mo
         if fwd.get("xfrc") is not None:
             a["fwd_xfrc"] = np.ascontiguousarray(fwd["xfrc"].reshape(n, -1).T, dtype=np.float64)
         a["fwdinv"] = np.zeros((2, n))
+    if eq_active is not None and model.int("neq") > 0:   # d->eq_active per state [n, neq]
+        a["eq_active"] = np.ascontiguousarray((np.asarray(eq_active) != 0).astype(np.float64).T)
     if xfrc is not None:    # d->xfrc_applied per state [n, nbody, 6]
         a["xfrc_applied"] = np.ascontiguousarray(xfrc.reshape(n, -1).T, dtype=np.float64)
     if mocap is not None:   # (mocap_pos [n, nmocap, 3], mocap_quat [n, nmocap, 4])

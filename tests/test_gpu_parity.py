@@ -276,6 +276,39 @@ def test_golden_sensordata_camlight_transmission_energy():
     assert np.isfinite(bd.transmission()["actuator_moment"]).all()
 
 
+@pytest.mark.parametrize("name", util.EQACTIVE_CASES)
+def test_golden_per_state_eq_active(name):
+    """mjb_setEqActive: per-state d->eq_active (mj_instantiateEquality skips inactive constraints,
+    engine_core_constraint.c:493-763; every later row moves up). Discrete outputs bit-identical, forces to
+    rounding against the reference; NULL returns to eq_active0."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.eqactive_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_QFRC | mjb.OUT_COUNTS | mjb.OUT_CONTACT | mjb.OUT_EFC,
+                       nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]))
+    bd.set_state(qpos, qvel, qacc)
+    bd.set_eq_active(util.eq_active_samples(model, n))
+    assert bd.inverse() == 0
+    cnt = bd.counts()
+    for k in ("ncon", "ne", "nf", "nl", "nefc"):
+        np.testing.assert_array_equal(cnt[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
+    np.testing.assert_array_equal(bd.contacts()["efc_address"], ref["contact_efc_address"])
+    efc = bd.efc()
+    for k in ("type", "id", "state"):
+        np.testing.assert_array_equal(efc[k], ref["efc_" + k], err_msg=k)
+    scale = max(1.0, np.abs(ref["efc_force"]).max())
+    np.testing.assert_allclose(efc["force"], ref["efc_force"], rtol=1e-9, atol=1e-13 * scale)
+    nviol, worst = util.qfrc_violations_scaled(bd.qfrc_inverse(), ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    ne_set = cnt["ne"].copy()
+    bd.set_eq_active(None)                    # back to the model's eq_active0
+    assert bd.inverse() == 0
+    assert (bd.counts()["ne"] >= ne_set).all() and (bd.counts()["ne"] > ne_set).any()
+
+
 @pytest.mark.parametrize("name", util.XFRC_CASES)
 def test_golden_rne_post_constraint_with_xfrc_applied(name):
     """mjb_setXfrcApplied: per-state d->xfrc_applied enters cfrc_ext / cfrc_int of mj_rnePostConstraint

@@ -119,6 +119,33 @@ def test_outputs_do_not_depend_on_the_debug_dump(name):
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
+@pytest.mark.parametrize("name", util.EQACTIVE_CASES)
+def test_per_state_eq_active(name):
+    """Per-state d->eq_active: inactive equality constraints emit no rows and every later row (friction loss,
+    limits, contacts) moves up; discrete outputs bit-identical, forces to rounding, against the reference."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref, n, zr = util.eqactive_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, n, z_range=zr)
+    ea = util.eq_active_samples(model, n)
+    weld_post = name != "mocap_eqactive"      # mocap.xml has a massless tree: no mjbOUT_RNEPOST
+    out = emu.run(model, qpos, qvel, qacc, nconmax=int(ref["nconmax"]), njmax=int(ref["njmax"]), post=weld_post,
+                  eq_active=ea, dump=False)
+    for k in ("ncon", "ne", "nf", "nl", "nefc", "contact_geom", "contact_efc_address", "efc_type", "efc_id", "efc_state"):
+        np.testing.assert_array_equal(out[k], ref[k], err_msg=k)
+    assert ref["ne"].min() == 0 and ref["ne"].max() > 0
+    nviol, worst = util.qfrc_violations_scaled(out["qfrc_inverse"], ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    scale = max(1.0, np.abs(ref["efc_force"]).max())
+    np.testing.assert_allclose(out["efc_force"], ref["efc_force"], rtol=1e-9, atol=1e-13 * scale)
+    if weld_post:
+        nb = model.int("nbody")
+        for k in ("cacc", "cfrc_int", "cfrc_ext"):
+            nviol, worst = util.spatial_violations(out[k].reshape(n, nb, 6), ref[k])
+            assert nviol == 0, (k, nviol, worst)
+
+
 @pytest.mark.parametrize("name", util.XFRC_CASES)
 def test_rne_post_constraint_with_xfrc_applied(name):
     """Per-state d->xfrc_applied enters cfrc_ext / cfrc_int (engine_core_smooth.c:2039-2049) and the force /

@@ -153,6 +153,26 @@ def xfrc_fixture(name):
             int(z["nstate"]), tuple(z["z_range"]))
 
 
+EQACTIVE_CASES = ["zoo_eqactive", "weld_eqactive", "connect_eqactive", "mocap_eqactive"]
+
+
+def eq_active_samples(model, nstate):
+    """The seeded per-state flags of tests/golden/make_golden.py::eq_active_samples."""
+    rng = np.random.RandomState(20250331)
+    e = (rng.uniform(0, 1, (nstate, model.int("neq"))) < 0.6).astype(np.uint8)
+    e[0] = 0
+    e[1] = 1
+    return e
+
+
+def eqactive_fixture(name):
+    """(path of the base case's MJB, npz dict, nstate, z_range) of a tests/golden/*_eqactive.npz fixture
+    (mj_inverse + mj_rnePostConstraint with per-state d->eq_active)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return (os.path.join(GOLDEN, str(z["base"]) + ".mjb.gz"), {k: z[k] for k in z.files},
+            int(z["nstate"]), tuple(z["z_range"]))
+
+
 def transmission_fixture(name):
     """(path of the base case's MJB, dict with actuator_length [n, nu], actuator_moment [n, nu, nv] (dense),
     actuator_velocity [n, nu] of the reference, nstate, z_range) of a tests/golden/*_trn.npz fixture."""
