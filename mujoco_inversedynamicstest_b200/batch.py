@@ -377,17 +377,18 @@ class BatchData:
         """cam_xpos [nbatch, ncam, 3], cam_xmat [.., 9], light_xpos / light_xdir [nbatch, nlight, 3] as
         mj_camlight leaves them (src/engine/engine_core_smooth.c:275-389); needs OUT_CAMLIGHT."""
         n = self.last_batch()
-        return {k: self.get(f).reshape(n, -1, c) for k, f, c in (
-            ("cam_xpos", F_CAM_XPOS, 3), ("cam_xmat", F_CAM_XMAT, 9), ("light_xpos", F_LIGHT_XPOS, 3),
-            ("light_xdir", F_LIGHT_XDIR, 3))}
+        ncam, nlight = self.model.int("ncam"), self.model.int("nlight")
+        return {k: self.get(f).reshape(n, cnt, c) for k, f, cnt, c in (
+            ("cam_xpos", F_CAM_XPOS, ncam, 3), ("cam_xmat", F_CAM_XMAT, ncam, 9),
+            ("light_xpos", F_LIGHT_XPOS, nlight, 3), ("light_xdir", F_LIGHT_XDIR, nlight, 3))}
 
     def transmission(self):
         """actuator_length [nbatch, nu], actuator_moment [nbatch, nu, nv] (dense), actuator_velocity
         [nbatch, nu] (mj_transmission, src/engine/engine_core_smooth.c:865-1346); needs OUT_TRANSMISSION."""
         n = self.last_batch()
-        length = self.get(F_ACTUATOR_LENGTH)
-        nu = length.shape[1]
-        return {"actuator_length": length, "actuator_moment": self.get(F_ACTUATOR_MOMENT).reshape(n, nu, -1),
+        nu = self.model.int("nu")
+        return {"actuator_length": self.get(F_ACTUATOR_LENGTH),
+                "actuator_moment": self.get(F_ACTUATOR_MOMENT).reshape(n, nu, self.nv),
                 "actuator_velocity": self.get(F_ACTUATOR_VELOCITY)}
 
     def internal(self, name):
