@@ -1,0 +1,435 @@
+// Part of the per-state mj_inverse pipeline (mjb_pipeline.h includes it inside namespace mjb, after the
+// context and accessor macros; not a stand-alone header).
+// The fused forward sweep (mj_kinematics, mj_comPos, mj_comVel, forward half of mj_rne, per-dof rows, geom frames, carrier records).
+#ifndef MJB_SWEEP_H_
+#define MJB_SWEEP_H_
+
+// ------------------------------------------------------------------------------------------
+// Forward sweep: ONE root-to-leaves pass that does, per body, the work the reference spreads over
+//   mj_kinematics  (engine_core_smooth.c:38-178, mj_local2Global engine_support.c:1565)
+//   mj_comPos      (:183-270; cinert via mju_inertCom, cdof via mju_dofCom)
+//   mj_comVel      (:1833-1896)
+//   mj_rne forward (:1969-2005, flg_acc = 1)
+// so that a body's pose, joint axes, velocity and acceleration never leave registers between those
+// stages; only what later phases read is written to the per-state scratch.
+//
+// Frame of the spatial quantities. The reference expresses cdof/cvel/cacc/cinert/cfrc about the
+// centre of mass of the kinematic tree (subtree_com[body_rootid]), which is known only after a
+// full kinematics pass. Spatial algebra holds about ANY fixed world point, and qfrc_inverse, qM,
+// qLD, J*v, J'*f are independent of it, so the sweep uses the tree origin
+//     O_tree = position of the tree's root body before its joints act
+//            = qpos[0:3] of a free root, body_pos of a jointed or welded root
+// which is known when the root is entered (|x - O| stays of the order of the tree's size, like the
+// reference's com-based offsets). Bodies of one tree are contiguous in the body order, so O is
+// carried in registers; it is also stored per root body for the constraint phases.
+//
+// Carry. Bodies are in depth-first order, so a body's parent is very often the body just
+// processed: its pose/velocity/acceleration are then still in registers (P, Q, V, A, AL) and are
+// read from scratch only when the parent is an earlier body (warp-uniform test).
+//
+//   cvel      spatial velocity about O                              (contact rows, cfrc)
+//   cacc_lin  sum of cdof*qacc along the dof chain = carrier of J*qacc for point constraints
+//   cacc      rne acceleration incl. -gravity and the cdof_dot*qvel bias (children only)
+//   cfrc      cinert*cacc + cvel x* (cinert*cvel)                   (backward pass)
+// cdof_dot = cvel x cdof lives only in registers (the reference stores it for its second sweep).
+
+// L1 prefetch of the input rows (qpos/qvel/qacc) the joints of body b will read, issued one body
+// ahead so that the HBM latency of the state's inputs overlaps the current body's arithmetic
+MJB_DI void prefetch_line(const double* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+MJB_HD inline void prefetch_body_inputs(Ctx& c, int b) {
+  const int jntadr = MI(body_jntadr)[b], jntnum = MI(body_jntnum)[b];
+  const int* jnt_qposadr = MI(jnt_qposadr); const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* jnt_dofnum = MI(jnt_dofnum_tab);
+  MJB_UNROLL
+  for (int j = jntadr; j < jntadr + jntnum; j++) {
+    const int nd = jnt_dofnum[j], qa = jnt_qposadr[j], da = jnt_dofadr[j];
+    const int nq = nd == 6 ? 7 : (nd == 3 ? 4 : 1);
+    for (int k = 0; k < nq; k++) prefetch_line(&QPOS(qa + k));
+    for (int k = 0; k < nd; k++) { prefetch_line(&QVEL(da + k)); prefetch_line(&QACC(da + k)); }
+  }
+}
+
+// pose of the geoms of body b from the body's frames held in registers (mj_local2Global)
+MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* quat, const double* mat,
+                              const double* ip, const double* im) {
+  const int* body_geomadr = MI(body_geomadr);
+  const int* body_geomnum = MI(body_geomnum);
+  const int* geom_sameframe = MI(geom_sameframe);
+  const double* geom_pos = MD(geom_pos); const double* geom_quat = MD(geom_quat);
+  double* gxmat = SC(geom_xmat);
+  // what a later phase reads of this geom (upload, geom_store): nothing when it is in no candidate
+  // pair; position + z axis for plane / sphere / capsule pairs; the full frame for the other
+  // narrow-phase functions and for tendon wrapping. The debug dump stores everything.
+  const int* geom_store = MI(geom_store);
+  const bool dump = c.out.scratch_dump != nullptr;
+  const int g0 = body_geomadr[b], gn = body_geomnum[b];
+  MJB_UNROLL
+  for (int g = g0; g < g0 + gn; g++) {
+    int store = dump ? 3 : geom_store[g];
+    if (store & 4) store = (c.out.actuator_length || c.out.sensordata) ? 3 : (store & 3);
+    if (!store) continue;
+    const int sf = geom_sameframe[g];
+    double gp[3], gm[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      gp[0] = pos[0]; gp[1] = pos[1]; gp[2] = pos[2];
+    } else if (sf == MJB_SAMEFRAME_INERTIA) {
+      gp[0] = ip[0]; gp[1] = ip[1]; gp[2] = ip[2];
+    } else {
+      mulMatVec3(gp, mat, geom_pos + 3*g);
+      gp[0] += pos[0]; gp[1] += pos[1]; gp[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, geom_quat + 4*g);
+      quat2Mat(gm, tq);
+    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
+      for (int k = 0; k < 9; k++) gm[k] = mat[k];
+    } else {
+      for (int k = 0; k < 9; k++) gm[k] = im[k];
+    }
+    st_rec4(geom_vec(c, MJB_SC_geom_xpos, g), gp[0], gp[1], gp[2], 0.0);
+    st_rec4(geom_vec(c, MJB_SC_geom_zaxis, g), gm[2], gm[5], gm[8], 0.0);
+    if (store & 2) sts(gxmat, 9*g, gm, 9);
+  }
+}
+
+// Body range [kLo, kHi) (kHi = 0: up to nbody). The generic kernels run the whole tree in one call;
+// the model-specialised build cuts the expanded sweep into stages of a few thousand instructions,
+// one kernel each, so that the code of a kernel stays resident in the instruction cache (measured:
+// ONE expanded kernel of 24 K instructions ran 1.5x slower than the generic loop although it
+// executes 2.6x fewer instructions -- every warp streams 390 KB of cold code per state). A stage
+// that does not start at body 1 reloads the tree origin and lets its first body fetch the parent
+// from scratch; a stage that does not end at the last body stores the carry of its last body.
+// a finished cdof row: to the scratch (backward sweep, constraint rows) and, in a fused subtree
+// stage, to the thread-local rows the inertia sweep of the same kernel reads
+MJB_HD inline void store_cdof(Ctx& c, double* cdof, int dof, const double* cd) {
+  sts(cdof, 6*dof, cd, 6);
+  if (c.lcd) { for (int k = 0; k < 6; k++) c.lcd[6*(dof - c.ldof0) + k] = cd[k]; }
+}
+
+template <int kLo = 1, int kHi = 0, bool kHandOver = true>
+MJB_HD inline void forward_sweep(Ctx& c) {
+  const mjbHdr& H = *c.H;
+  const int nbody = H.nbody;
+  const int lo = kLo, hi = kHi ? kHi : nbody;
+  double* xpos = SC(xpos); double* xquat = SC(xquat); double* org = SC(origin);
+  double* cvel = SC(cvel); double* cal = SC(cacc_lin); double* cacc = SC(cacc);
+  double* cfrc = SC(cfrc); double* cinert = SC(cinert); double* cdof = SC(cdof);
+  const int* body_parentid = MI(body_parentid);
+  const int* body_jntadr = MI(body_jntadr);
+  const int* body_jntnum = MI(body_jntnum);
+  const int* body_dofadr = MI(body_dofadr);
+  const int* body_dofnum = MI(body_dofnum);
+  const int* body_mocapid = MI(body_mocapid);
+  const int* body_sameframe = MI(body_sameframe);
+  const int* tree_flags = MI(body_tree_flags);
+  const int* jnt_type = MI(jnt_type);
+  const int* jnt_qposadr = MI(jnt_qposadr);
+  const int* jnt_dofadr = MI(jnt_dofadr);
+  const int* dof_jntid = MI(dof_jntid);
+  const double* body_pos = MD(body_pos); const double* body_quat = MD(body_quat);
+  const double* body_ipos = MD(body_ipos); const double* body_iquat = MD(body_iquat);
+  const double* body_mass = MD(body_mass); const double* body_inertia = MD(body_inertia);
+  const double* jnt_pos = MD(jnt_pos); const double* jnt_axis = MD(jnt_axis);
+  const double* qpos0 = MD(qpos0);
+
+  // Carry of the body just processed, in per-thread shared-memory slots (on chip, and out of the
+  // register budget of the joint loop): 0..2 pos, 3..6 quat, 7..12 cvel, 13..18 cacc, 19..24 cacc_lin
+#define CS(k) c.sm[(k) * MJB_SMS]
+  // world body: identity pose, zero velocity, acceleration = -gravity (mj_rne :1979-1982)
+  double O[3] = {0, 0, 0};
+  int carry = 0;          // body whose pose / velocity / acceleration are in the carry slots
+  if (lo == 1) {
+    double P[3] = {0, 0, 0}, Q[4] = {1, 0, 0, 0};
+    double Z[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
+    if (!(H.disableflags & MJB_DSBL_GRAVITY)) {
+      A[3] = -H.gravity[0]; A[4] = -H.gravity[1]; A[5] = -H.gravity[2];
+    }
+    stc(xpos, 0, P, 3); stc(xquat, 0, Q, 4); stc(org, 0, O, 3);
+    stc(cvel, 0, Z, 6); stc(cal, 0, Z, 6); stc(cacc, 0, A, 6);
+    for (int k = 0; k < 3; k++) CS(k) = 0;
+    CS(3) = 1; CS(4) = 0; CS(5) = 0; CS(6) = 0;
+    for (int k = 0; k < 6; k++) { CS(7 + k) = 0; CS(13 + k) = A[k]; CS(19 + k) = 0; }
+    const double I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    body_geoms(c, 0, P, Q, I9, P, I9);
+  } else {
+    carry = -1;
+    ldn(O, org, 3*MI(body_rootid)[lo], 3);
+  }
+
+  if (lo < nbody) prefetch_body_inputs(c, lo);
+  auto sweep_body = [&](const int b) MJB_BODY_LAMBDA {
+    if (b + 1 < nbody) prefetch_body_inputs(c, b + 1);
+    const int pid = body_parentid[b];
+    const int jntadr = body_jntadr[b], jntnum = body_jntnum[b];
+    const int bda = body_dofadr[b], dofnum = body_dofnum[b];
+    if (pid != carry) {
+      double t[25];
+      ldn(t, xpos, 3*pid, 3); ldn(t + 3, xquat, 4*pid, 4);
+      ldn(t + 7, cvel, 6*pid, 6); ldn(t + 13, cacc, 6*pid, 6); ldn(t + 19, cal, 6*pid, 6);
+      for (int k = 0; k < 25; k++) CS(k) = t[k];
+    }
+    double V[6];
+    for (int k = 0; k < 6; k++) V[k] = CS(7 + k);
+    double pos[3], quat[4];
+    double t1[6] = {0, 0, 0, 0, 0, 0};   // cdof_dot' * qvel   (mju_mulDofVec, row by row)
+    double t2[6] = {0, 0, 0, 0, 0, 0};   // cdof' * qacc
+    const bool isfree = jntnum == 1 && jnt_type[jntadr] == MJB_JNT_FREE;
+    bool has_ball = false;
+
+    if (isfree) {
+      const int qadr = jnt_qposadr[jntadr];
+      for (int k = 0; k < 3; k++) pos[k] = QPOS(qadr + k);
+      for (int k = 0; k < 4; k++) quat[k] = QPOS(qadr + 3 + k);
+      normalize4(quat);
+      if (pid == 0) { O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2]; stc(org, 3*b, O, 3); }
+      quat_dof_forces(c, jntadr, qadr, bda, MJB_JNT_FREE, quat);
+    } else {
+      double bquat[4] = {body_quat[4*b], body_quat[4*b+1], body_quat[4*b+2], body_quat[4*b+3]};
+      const int mid = body_mocapid[b];
+      if (mid >= 0) {                  // mocap pose: the caller's, else the model pose (mj_resetData default)
+        if (c.out.mocap_quat) {
+          for (int k = 0; k < 4; k++) bquat[k] = c.out.mocap_quat[(size_t)(4*mid + k)*(size_t)c.N + c.s];
+        }
+        normalize4(bquat);
+      }
+      if (pid) {
+        double pm[9];
+        const double Q[4] = {CS(3), CS(4), CS(5), CS(6)};
+        quat2Mat(pm, Q);                 // == the parent's xmat (same function of the same xquat)
+        mulMatVec3(pos, pm, body_pos + 3*b);
+        pos[0] += CS(0); pos[1] += CS(1); pos[2] += CS(2);
+        mulQuat(quat, Q, bquat);
+      } else {
+        for (int k = 0; k < 3; k++) pos[k] = body_pos[3*b + k];
+        if (mid >= 0 && c.out.mocap_pos) {
+          for (int k = 0; k < 3; k++) pos[k] = c.out.mocap_pos[(size_t)(3*mid + k)*(size_t)c.N + c.s];
+        }
+        for (int k = 0; k < 4; k++) quat[k] = bquat[k];
+        O[0] = pos[0]; O[1] = pos[1]; O[2] = pos[2];
+        stc(org, 3*b, O, 3);
+      }
+      MJB_UNROLL
+      for (int j = 0; j < jntnum; j++) has_ball = has_ball || jnt_type[jntadr + j] == MJB_JNT_BALL;
+
+      MJB_UNROLL
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        const int qadr = jnt_qposadr[jid];
+        const int dadr = jnt_dofadr[jid];
+        const int jtype = jnt_type[jid];
+        double ax[3], anc[3], cd[6];
+        rotVecQuat(ax, jnt_axis + 3*jid, quat);
+        rotVecQuat(anc, jnt_pos + 3*jid, quat);
+        anc[0] += pos[0]; anc[1] += pos[1]; anc[2] += pos[2];
+        const double off[3] = {O[0] - anc[0], O[1] - anc[1], O[2] - anc[2]};
+
+        double jq = 0, jqv = 0, jqa = 0;
+        if (jtype != MJB_JNT_BALL) { jq = QPOS(qadr); jqv = QVEL(dadr); jqa = QACC(dadr); }
+        if (jtype == MJB_JNT_SLIDE) {
+          const double q = jq - qpos0[qadr];
+          pos[0] += ax[0]*q; pos[1] += ax[1]*q; pos[2] += ax[2]*q;
+          cd[0] = 0; cd[1] = 0; cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2];
+        } else {
+          double qloc[4];
+          if (jtype == MJB_JNT_BALL) {
+            for (int k = 0; k < 4; k++) qloc[k] = QPOS(qadr + k);
+            normalize4(qloc);
+            // cdof of a ball joint uses the body's FINAL orientation (mj_comPos :243-252): keep
+            // the anchor offset in the dof's slots until the pose is complete
+            stn(cdof, 6*dadr, off, 3);
+            quat_dof_forces(c, jid, qadr, dadr, MJB_JNT_BALL, qloc);
+          } else {
+            // mju_axisAngle2Quat (engine_util_spatial.c:97)
+            const double angle = jq - qpos0[qadr];
+            double sn, cs;
+            sincos(angle*0.5, &sn, &cs);
+            qloc[0] = cs;
+            qloc[1] = jnt_axis[3*jid]*sn; qloc[2] = jnt_axis[3*jid+1]*sn; qloc[3] = jnt_axis[3*jid+2]*sn;
+            cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+            cross3(cd + 3, ax, off);
+          }
+          mulQuat(quat, quat, qloc);
+          double vec[3];
+          rotVecQuat(vec, jnt_pos + 3*jid, quat);
+          pos[0] = anc[0] - vec[0]; pos[1] = anc[1] - vec[1]; pos[2] = anc[2] - vec[2];
+        }
+        if (jtype != MJB_JNT_BALL) {
+          store_cdof(c, cdof, dadr, cd);
+          if (!has_ball) {
+            // mj_comVel / mj_rne for a scalar dof, fused: cdof_dot uses the velocity so far
+            double dd[6];
+            crossMotion(dd, V, cd);
+            for (int k = 0; k < 6; k++) { t1[k] += dd[k]*jqv; V[k] += cd[k]*jqv; t2[k] += cd[k]*jqa; }
+          }
+          scalar_dof_forces(c, jid, qadr, dadr, jq, jqv, jqa);
+        }
+      }
+    }
+
+    normalize4(quat);
+    double mat[9];
+    quat2Mat(mat, quat);
+    // the pose goes to scratch only where a later consumer reads it: a child that is not b+1
+    // (bit 2), an equality constraint or a tendon site on this body (bit 3), or the debug dump
+    if ((tree_flags[b] & 12) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.cam_xpos || c.out.actuator_length ||
+        c.out.xfrc_applied) {
+      stc(xquat, 4*b, quat, 4);
+      stc(xpos, 3*b, pos, 3);
+    }
+
+    if (isfree) {
+      // translational dofs: cdof = [0, e_r], cdof_dot = 0
+      for (int r = 0; r < 3; r++) {
+        double cd[6] = {0, 0, 0, r == 0 ? 1.0 : 0.0, r == 1 ? 1.0 : 0.0, r == 2 ? 1.0 : 0.0};
+        store_cdof(c, cdof, bda + r, cd);
+        V[3 + r] += QVEL(bda + r);
+        t2[3 + r] += QACC(bda + r);
+      }
+      // rotational dofs: body axes; the anchor is the body origin, O - anchor = (O - pos)
+      const double off[3] = {O[0] - pos[0], O[1] - pos[1], O[2] - pos[2]};
+      double cd[3][6];
+      for (int r = 0; r < 3; r++) {
+        cd[r][0] = mat[r]; cd[r][1] = mat[r + 3]; cd[r][2] = mat[r + 6];
+        cross3(cd[r] + 3, cd[r], off);
+        store_cdof(c, cdof, bda + 3 + r, cd[r]);
+      }
+      // all three use the velocity BEFORE this joint's rotation (mj_comVel :1855-1876)
+      for (int r = 0; r < 3; r++) {
+        double dd[6];
+        crossMotion(dd, V, cd[r]);
+        const double qv = QVEL(bda + 3 + r);
+        for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+      }
+      for (int r = 0; r < 3; r++) {
+        const double qv = QVEL(bda + 3 + r), qa = QACC(bda + 3 + r);
+        for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+      }
+    } else if (has_ball) {
+      // general path: finish the ball-joint cdofs with the final orientation, then run the dof
+      // loop of mj_comVel over the body's dofs from scratch
+      MJB_UNROLL
+      for (int j = 0; j < jntnum; j++) {
+        const int jid = jntadr + j;
+        if (jnt_type[jid] != MJB_JNT_BALL) continue;
+        const int dadr = jnt_dofadr[jid];
+        double off[3];
+        ldn(off, cdof, 6*dadr, 3);
+        for (int r = 0; r < 3; r++) {
+          double cd[6] = {mat[r], mat[r + 3], mat[r + 6], 0, 0, 0};
+          cross3(cd + 3, cd, off);
+          store_cdof(c, cdof, dadr + r, cd);
+        }
+      }
+      MJB_UNROLL
+      for (int j = 0; j < dofnum; j++) {
+        const int jt = jnt_type[dof_jntid[bda + j]];
+        if (jt == MJB_JNT_BALL) {
+          double cd[3][6];
+          for (int r = 0; r < 3; r++) {
+            double dd[6];
+            ldn(cd[r], cdof, 6*(bda + j + r), 6);
+            crossMotion(dd, V, cd[r]);
+            const double qv = QVEL(bda + j + r);
+            for (int k = 0; k < 6; k++) t1[k] += dd[k]*qv;
+          }
+          for (int r = 0; r < 3; r++) {
+            const double qv = QVEL(bda + j + r), qa = QACC(bda + j + r);
+            for (int k = 0; k < 6; k++) { V[k] += cd[r][k]*qv; t2[k] += cd[r][k]*qa; }
+          }
+          j += 2;
+        } else {
+          double cd[6], dd[6];
+          ldn(cd, cdof, 6*(bda + j), 6);
+          crossMotion(dd, V, cd);
+          const double qv = QVEL(bda + j), qa = QACC(bda + j);
+          for (int k = 0; k < 6; k++) { t1[k] += dd[k]*qv; V[k] += cd[k]*qv; t2[k] += cd[k]*qa; }
+        }
+      }
+    }
+
+    double A[6], AL[6];
+    for (int k = 0; k < 6; k++) {
+      A[k] = CS(13 + k); A[k] += t1[k]; A[k] += t2[k];
+      AL[k] = CS(19 + k) + t2[k];
+      CS(7 + k) = V[k]; CS(13 + k) = A[k]; CS(19 + k) = AL[k];
+    }
+    // read back only by a child that is not b+1 (bit 2), by constraint rows on this body (bit 4:
+    // candidate pairs, equality constraints, tendon sites), or by the optional per-body outputs
+    if ((tree_flags[b] & (4 | 16)) || c.out.scratch_dump || c.out.sensordata || c.out.fwd_xfrc || c.out.fwdinv ||
+        c.out.cacc || c.out.qfrc_bias || c.out.energy) {
+      stc(cvel, 6*b, V, 6);
+      stc(cal, 6*b, AL, 6);
+    }
+    // body of a candidate pair: the carrier record the contact rows gather (one 128-byte line)
+    if (tree_flags[b] & 32) store_crec(c, b, V, AL, O);
+    // read back only by a child that is not b+1, or by the mj_rnePostConstraint outputs
+    if ((tree_flags[b] & 4) || c.out.cacc || c.out.qfrc_bias) stc(cacc, 6*b, A, 6);
+
+    // inertial frame (mj_kinematics :159-165), cinert (mju_inertCom) and the rne body force
+    const int sf = body_sameframe[b];
+    double ip[3], im[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      ip[0] = pos[0]; ip[1] = pos[1]; ip[2] = pos[2];
+    } else {
+      mulMatVec3(ip, mat, body_ipos + 3*b);
+      ip[0] += pos[0]; ip[1] += pos[1]; ip[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, body_iquat + 4*b);
+      quat2Mat(im, tq);
+    } else {
+      for (int k = 0; k < 9; k++) im[k] = mat[k];
+    }
+    {
+      const double off[3] = {ip[0] - O[0], ip[1] - O[1], ip[2] - O[2]};
+      double ci[10], f[6], u1[6], u2[6];
+      inertCom(ci, body_inertia + 3*b, im, off, body_mass[b]);
+      if (c.lci) { for (int k = 0; k < 10; k++) c.lci[10*(b - c.lbody0) + k] = ci[k]; }
+      if (!c.lci || c.out.cfrc_int || c.out.qfrc_bias || c.out.sensordata || c.out.scratch_dump || c.out.energy) sts(cinert, 10*b, ci, 10);
+      mulInertVec(f, ci, A);
+      mulInertVec(u1, ci, V);
+      crossForce(u2, V, u1);
+      for (int k = 0; k < 6; k++) f[k] += u2[k];
+      sts(cfrc, 6*b, f, 6);
+      if (H.passive_wrench) {
+        // passive-wrench carrier (projected into qfrc_passive by the backward sweep): starts with
+        // mj_gravcomp (engine_passive.c:381-401), force -gravity*mass*gravcomp at the body's centre
+        // of mass as a wrench about O; spatial-tendon springs and dampers are added later
+        double wg[6] = {0, 0, 0, 0, 0, 0};
+        if (H.has_gravcomp) {
+          const double sgc = -(body_mass[b] * MD(body_gravcomp)[b]);
+          const double F[3] = {H.gravity[0]*sgc, H.gravity[1]*sgc, H.gravity[2]*sgc};
+          cross3(wg, off, F);
+          wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
+        }
+        stn(SC(cfrc_gc), 6*b, wg, 6);
+      }
+    }
+
+    body_geoms(c, b, pos, quat, mat, ip, im);
+
+    CS(0) = pos[0]; CS(1) = pos[1]; CS(2) = pos[2];
+    CS(3) = quat[0]; CS(4) = quat[1]; CS(5) = quat[2]; CS(6) = quat[3];
+    carry = b;
+  };
+  MJB_BODY_LOOP_UP(sweep_body, lo, hi, kLo, (kHi ? kHi : MJB_SPEC_NBODY));
+  if (kHandOver && hi < nbody && carry > 0) {
+    // hand-over to the next stage: everything a child may read of the last body of this one
+    double t[25];
+    for (int k = 0; k < 25; k++) t[k] = CS(k);
+    stc(xpos, 3*carry, t, 3); stc(xquat, 4*carry, t + 3, 4);
+    stc(cvel, 6*carry, t + 7, 6); stc(cacc, 6*carry, t + 13, 6); stc(cal, 6*carry, t + 19, 6);
+  }
+#undef CS
+}
+
+
+#endif  // MJB_SWEEP_H_

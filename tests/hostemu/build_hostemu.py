@@ -19,7 +19,7 @@ def include_dir():
 def build(force=False):
     inc = include_dir()
     srcs = [os.path.join(HERE, "hostemu.cc"), os.path.join(CSRC, "mjb_upload.cc")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("mjb_pipeline.h", "mjb_math.h", "mjb_model.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
     if os.path.exists(LIB) and not force:
         if inc is None or os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
             return LIB
