@@ -344,6 +344,21 @@ REFH_API void refh_compare_fwdinv(const mjModel* m, const double* qpos, const do
   mj_deleteData(d);
 }
 
+/* Settle a model the way the reference's rne_post tests do (test/engine/engine_core_smooth_test.cc:160-240:
+ * mj_step x nstep from the default state), then mj_forward: the state (qpos, qvel, qacc) and the
+ * reference's sensordata at it. Used to restate those known-answer tests on the inverse path. */
+REFH_API void refh_settle(const mjModel* m, int nstep, double* qpos, double* qvel, double* qacc,
+                          double* sensordata) {
+  mjData* d = mj_makeData(m);
+  for (int i = 0; i < nstep; i++) mj_step(m, d);
+  mj_forward(m, d);
+  mju_copy(qpos, d->qpos, m->nq);
+  mju_copy(qvel, d->qvel, m->nv);
+  mju_copy(qacc, d->qacc, m->nv);
+  if (sensordata) mju_copy(sensordata, d->sensordata, m->nsensordata);
+  mj_deleteData(d);
+}
+
 /* mj_forward + mj_compareFwdInv over a batch (engine_inverse.c:275-316): for every state the
  * forward dynamics run on (qpos, qvel, ctrl, qfrc_applied, xfrc_applied); d->qacc is then shifted by
  * dqacc (NULL: left as solved, so that the comparison is also exercised away from the solution),

@@ -316,6 +316,16 @@ class Model:
                                   qacc.ctypes.data, out.ctypes.data)
         return out
 
+    def settle(self, nstep):
+        """mj_step x nstep from the default state, then mj_forward: (qpos, qvel, qacc, sensordata)."""
+        L = lib()
+        L.refh_settle.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
+        L.refh_settle.restype = None
+        qpos, qvel, qacc = np.zeros(self.int("nq")), np.zeros(self.int("nv")), np.zeros(self.int("nv"))
+        sd = np.zeros(max(1, self.int("nsensordata")))
+        L.refh_settle(self.ptr, int(nstep), qpos.ctypes.data, qvel.ctypes.data, qacc.ctypes.data, sd.ctypes.data)
+        return qpos, qvel, qacc, sd[:self.int("nsensordata")]
+
     def compare_fwdinv(self, qpos, qvel, ctrl=None, nstep=0):
         qpos = np.ascontiguousarray(qpos, dtype=np.float64)
         qvel = np.ascontiguousarray(qvel, dtype=np.float64)

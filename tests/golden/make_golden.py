@@ -460,10 +460,62 @@ def make_eqactive_case(name):
     print(f"{name}: neq={m.int('neq')} states={nstate} ne min/mean/max={out['ne'].min()}/{out['ne'].mean():.2f}/{out['ne'].max()}")
 
 
+# Known-answer tests the reference itself holds, restated on the inverse path: the model is settled /
+# evaluated by the reference as its test does, the state (qpos, qvel, qacc) is kept, and the EXPECTED values are the
+# ones written in the reference's test or model file -- not an output of the reference.
+#   rne_post/*: test/engine/engine_core_smooth_test.cc:160-300 (1000 steps, force / torque sensors == sensor_user, 1e-6)
+#   the others: tests/golden/models/ref_*.xml (each cites its test)
+RNE_POST_DIR = "test/engine/testdata/core_smooth/rne_post/"
+KNOWN_ANSWER_CASES = {
+    **{"ka_connect_" + n: (RNE_POST_DIR + "connect/" + n + ".xml", 1000, "sensor_user", 1e-6)
+       for n in ("force_free", "force_slide", "force_slide_rotated", "multiple_constraints", "torque_free")},
+    **{"ka_weld_" + n: (RNE_POST_DIR + "weld/" + n + ".xml", 1000, "sensor_user", 1e-6)
+       for n in ("force_free", "force_free_rotated", "force_torque_free", "force_torque_free_rotated",
+                 "force_torque_free_rotated_tendon", "tfratio0_force_free", "tfratio0_force_slide",
+                 "tfratio0_force_slide_rotated", "tfratio0_multiple_constraints", "tfratio0_torque_free")},
+    # engine_sensor_test.cc:428-455: 2*3*5 at the default state, 7*3*5 at qpos[2] = 7 (EXPECT_EQ)
+    "ka_potential_energy": ("repo:tests/golden/models/ref_sensor_potential_energy.xml", 0, [[30.0], [105.0]], 0.0),
+    # engine_sensor_test.cc:400-426: data->energy[0] == 2*3*5 with mjENBL_ENERGY (EXPECT_EQ)
+    "ka_enable_energy": ("repo:tests/golden/models/ref_sensor_enable_energy.xml", 0, "energy0=30", 0.0),
+    # engine_sensor_test.cc:595-634: pixels within 1e-4
+    "ka_camprojection": ("repo:tests/golden/models/ref_sensor_camprojection.xml", 0,
+                         [[0.0, 0.0, 1920.0, 1200.0, 960.0, 600.0]], 1e-4),
+    # engine_ray_test.cc:79-165 (0.9 / 2.9, EXPECT_FLOAT_EQ) through rangefinder sites
+    "ka_ray": ("repo:tests/golden/models/ref_ray.xml", 0, [[2.9, 0.9, 0.9]], 1e-6),
+}
+
+
+def make_known_answer_case(name):
+    xml, nstep, expected, tol = KNOWN_ANSWER_CASES[name]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:") else reflib.reference_path(xml))
+    raw = os.path.join(HERE, name + ".mjb")
+    m.save_mjb(raw)
+    with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb", compresslevel=9, mtime=0) as g:
+        g.write(f.read())
+    os.remove(raw)
+    qpos, qvel, qacc, sd = m.settle(nstep)
+    qpos, qvel, qacc = qpos[None], qvel[None], qacc[None]
+    if name == "ka_potential_energy":           # second state of the reference's test: the body lifted to z = 7
+        q2 = qpos.copy(); q2[0, 2] = 7
+        qpos, qvel, qacc = np.vstack([qpos, q2]), np.vstack([qvel, qvel]), np.vstack([qacc, qacc])
+    save = {"qpos": qpos, "qvel": qvel, "qacc": qacc, "tol": np.array(tol), "ref_sensordata": sd}
+    if expected == "sensor_user":
+        ns, nus = m.int("nsensor"), m.int("nuser_sensor")
+        save["expected"] = m.array("sensor_user").reshape(ns, nus)[:, :3].copy()[None]    # [1, nsensor, 3]
+        save["sensor_adr"] = m.array("sensor_adr").ravel().copy()
+    elif isinstance(expected, str):
+        save["expected_energy0"] = np.array(30.0)
+    else:
+        save["expected"] = np.array(expected)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(f"{name}: nq={m.int('nq')} nv={m.int('nv')} nsensordata={m.int('nsensordata')} reference reads {np.round(sd, 6)}")
+
+
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
                  list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES) + list(CAMLIGHT_CASES) +
-                 list(TRANSMISSION_CASES) + list(XFRC_CASES) + list(EQACTIVE_CASES)):
-        (make_eqactive_case if case in EQACTIVE_CASES else make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(TRANSMISSION_CASES) + list(XFRC_CASES) + list(EQACTIVE_CASES) +
+                 list(KNOWN_ANSWER_CASES)):
+        (make_known_answer_case if case in KNOWN_ANSWER_CASES else make_eqactive_case if case in EQACTIVE_CASES else make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

@@ -276,6 +276,24 @@ def test_golden_sensordata_camlight_transmission_energy():
     assert np.isfinite(bd.transmission()["actuator_moment"]).all()
 
 
+@pytest.mark.parametrize("name", util.KNOWN_ANSWER_CASES)
+def test_reference_known_answers(name):
+    """Known-answer tests the reference holds, restated through the C-ABI: force / torque sensor readings of
+    bodies hanging on connect / weld constraints against the values written in the reference's model files
+    (test/engine/engine_core_smooth_test.cc:160-300), potential energy (engine_sensor_test.cc:400-455), camera
+    projection (:595-634), ray distances (engine_ray_test.cc:79-165)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, z = util.known_answer_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    n = z["qpos"].shape[0]
+    bd = mjb.BatchData(model, n)
+    bd.set_state(z["qpos"], z["qvel"], z["qacc"])
+    assert bd.inverse() == 0
+    sensordata = bd.sensordata() if model.int("nsensordata") > 0 else None
+    energy = bd.energy() if name == "ka_enable_energy" else None
+    util.check_known_answer(name, z, sensordata, energy)
+
+
 @pytest.mark.parametrize("name", util.EQACTIVE_CASES)
 def test_golden_per_state_eq_active(name):
     """mjb_setEqActive: per-state d->eq_active (mj_instantiateEquality skips inactive constraints,

@@ -119,6 +119,20 @@ def test_outputs_do_not_depend_on_the_debug_dump(name):
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
+@pytest.mark.parametrize("name", util.KNOWN_ANSWER_CASES)
+def test_reference_known_answers(name):
+    """Known-answer tests the reference holds, restated on the inverse path: force / torque sensors of bodies
+    hanging on connect / weld constraints equal the values written in the model files
+    (test/engine/engine_core_smooth_test.cc:160-300, 1e-6), potential energy (engine_sensor_test.cc:400-455,
+    exact), camera projection (:595-634, 1e-4), ray distances (engine_ray_test.cc:79-165)."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, z = util.known_answer_fixture(name)
+    model = mjb.Model.from_mjb(path)
+    out = emu.run(model, z["qpos"], z["qvel"], z["qacc"], nconmax=16, njmax=64, post=name.startswith(("ka_connect", "ka_weld")),
+                  dump=False)
+    util.check_known_answer(name, z, out.get("sensordata"), out.get("energy"))
+
+
 @pytest.mark.parametrize("name", util.EQACTIVE_CASES)
 def test_per_state_eq_active(name):
     """Per-state d->eq_active: inactive equality constraints emit no rows and every later row (friction loss,

@@ -173,6 +173,40 @@ def eqactive_fixture(name):
             int(z["nstate"]), tuple(z["z_range"]))
 
 
+KNOWN_ANSWER_CASES = (["ka_connect_" + n for n in ("force_free", "force_slide", "force_slide_rotated",
+                                                     "multiple_constraints", "torque_free")] +
+                      ["ka_weld_" + n for n in ("force_free", "force_free_rotated", "force_torque_free",
+                                                "force_torque_free_rotated", "force_torque_free_rotated_tendon",
+                                                "tfratio0_force_free", "tfratio0_force_slide",
+                                                "tfratio0_force_slide_rotated", "tfratio0_multiple_constraints",
+                                                "tfratio0_torque_free")] +
+                      ["ka_potential_energy", "ka_enable_energy", "ka_camprojection", "ka_ray"])
+
+
+def known_answer_fixture(name):
+    """(path of the MJB, npz dict) of a tests/golden/ka_*.npz fixture: a state produced the way a test of the
+    reference produces it, and the EXPECTED values that test (or its model file) holds."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return os.path.join(GOLDEN, name + ".mjb.gz"), {k: z[k] for k in z.files}
+
+
+def check_known_answer(name, z, sensordata, energy=None):
+    """Compare with the reference-held values (not with an output of the reference)."""
+    tol = float(z["tol"])
+    if "expected_energy0" in z:
+        assert energy is not None and (energy[:, 0] == float(z["expected_energy0"])).all(), (name, energy)
+        return
+    exp = z["expected"]
+    if "sensor_adr" in z:            # three leading components of every sensor against its sensor_user
+        got = np.stack([sensordata[:, a:a + 3] for a in z["sensor_adr"]], axis=1)
+    else:
+        got = sensordata
+    if tol == 0.0:
+        np.testing.assert_array_equal(got, exp, err_msg=name)
+    else:
+        assert np.abs(got - exp).max() <= tol * max(1.0, np.abs(exp).max() if name == "ka_ray" else 1.0), (name, got, exp)
+
+
 def transmission_fixture(name):
     """(path of the base case's MJB, dict with actuator_length [n, nu], actuator_moment [n, nu, nv] (dense),
     actuator_velocity [n, nu] of the reference, nstate, z_range) of a tests/golden/*_trn.npz fixture."""
