@@ -480,6 +480,12 @@ KNOWN_ANSWER_CASES = {
     # engine_sensor_test.cc:595-634: pixels within 1e-4
     "ka_camprojection": ("repo:tests/golden/models/ref_sensor_camprojection.xml", 0,
                          [[0.0, 0.0, 1920.0, 1200.0, 960.0, 600.0]], 1e-4),
+    # engine_sensor_test.cc:221-322 (hand-picked velocities, DoubleNear(1e-14)); the third element sets qvel
+    "ka_framevel_linear": ("repo:tests/golden/models/ref_sensor_framevel_linear.xml", [2 ** 0.5, 1.0],
+                           [[-(0.5 ** 0.5), 0.5 ** 0.5, 0.0]], 1e-14),
+    "ka_framevel_angfixed": ("repo:tests/golden/models/ref_sensor_framevel_angfixed.xml", [1.0], [[0.0, 0.0, 0.0]], 1e-14),
+    "ka_framevel_angopposing": ("repo:tests/golden/models/ref_sensor_framevel_angopposing.xml", [-1.0, 1.0],
+                                [[0.0, 2.0, 0.0]], 1e-14),
     # engine_ray_test.cc:79-165 (0.9 / 2.9, EXPECT_FLOAT_EQ) through rangefinder sites
     "ka_ray": ("repo:tests/golden/models/ref_ray.xml", 0, [[2.9, 0.9, 0.9]], 1e-6),
 }
@@ -493,7 +499,13 @@ def make_known_answer_case(name):
     with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb", compresslevel=9, mtime=0) as g:
         g.write(f.read())
     os.remove(raw)
-    qpos, qvel, qacc, sd = m.settle(nstep)
+    set_qvel = nstep if isinstance(nstep, list) else None      # a list in place of the step count: qvel of the test
+    qpos, qvel, qacc, sd = m.settle(0 if set_qvel else nstep)
+    if set_qvel:
+        qvel = np.array(set_qvel)
+        qacc = np.zeros_like(qvel)      # velocity-stage sensors do not read it
+        out, _ = m.inverse_batch(qpos[None], qvel[None], qacc[None], fields={"sensordata": None})
+        sd = out["sensordata"][0, :, 0]
     qpos, qvel, qacc = qpos[None], qvel[None], qacc[None]
     if name == "ka_potential_energy":           # second state of the reference's test: the body lifted to z = 7
         q2 = qpos.copy(); q2[0, 2] = 7

@@ -180,7 +180,8 @@ KNOWN_ANSWER_CASES = (["ka_connect_" + n for n in ("force_free", "force_slide", 
                                                 "tfratio0_force_free", "tfratio0_force_slide",
                                                 "tfratio0_force_slide_rotated", "tfratio0_multiple_constraints",
                                                 "tfratio0_torque_free")] +
-                      ["ka_potential_energy", "ka_enable_energy", "ka_camprojection", "ka_ray"])
+                      ["ka_potential_energy", "ka_enable_energy", "ka_camprojection", "ka_ray", "ka_framevel_linear",
+                       "ka_framevel_angfixed", "ka_framevel_angopposing"])
 
 
 def known_answer_fixture(name):
