@@ -156,7 +156,11 @@
   X(scan_misc)        /* 1: largest contact margin of any candidate (tree-level culling) */ \
   X(sensor_cutoff)    /* nsensor */ \
   X(act_biasvel)      /* nu: d force / d velocity of the actuator's affine bias (implicitfast mjENBL_INVDISCRETE) */ \
-  X(cam_proj)         /* ncam*4: fx, fy, half width, half height in pixels (cam_project, engine_sensor.c:126-215) */
+  X(cam_proj)         /* ncam*4: fx, fy, half width, half height in pixels (cam_project, engine_sensor.c:126-215) */ \
+  X(fluid_body)       /* nbody*4 (empty without fluid forces): model kind MJB_FLUID_* and the three sides of the \
+                         equivalent inertia box (mj_inertiaBoxFluidModel, engine_passive.c:527-537) */ \
+  X(fluid_geom)       /* ngeom*MJB_FLUID_NG (empty unless some geom uses the ellipsoid model): geom_fluid's 12 \
+                         coefficients, then the semi-axes of mju_geomSemiAxes (engine_util_misc.c:425) */
 
 enum {
 #define X(name, rows) MJB_I_##name,
@@ -334,10 +338,14 @@ typedef struct mjbHdr_ {
   int32_t sensor_trn;        // some actuatorpos / actuatorvel sensor reads mj_transmission's outputs
   int32_t sensor_energy;     // some potential / kinetic energy sensor (mj_energyPos / mj_energyVel run for it)
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
+  int32_t has_fluid;         // mj_fluid runs (opt.density / opt.viscosity > 0, passive forces enabled): 1 inertia-box
+                             // model only, 2 some body uses the ellipsoid model (engine_passive.c:403-431)
   int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)
   double timestep, impratio;
   double gravity[3];
   double magnetic[3];        // opt.magnetic (magnetometer sensors)
+  double density, viscosity; // opt.density, opt.viscosity (mj_fluid)
+  double wind[3];            // opt.wind
   int32_t nrun;             // runs of the candidate list for the tree-level broadphase (0: flat scan)
   int32_t ntree;            // kinematic trees with collidable geoms
   int32_t ioff[MJB_NI];     // element offsets into the int section
@@ -368,6 +376,8 @@ enum { MJB_CAMLIGHT_FIXED = 0, MJB_CAMLIGHT_TRACK, MJB_CAMLIGHT_TRACKCOM, MJB_CA
 enum { MJB_SAMEFRAME_NONE = 0, MJB_SAMEFRAME_BODY, MJB_SAMEFRAME_INERTIA, MJB_SAMEFRAME_BODYROT,
        MJB_SAMEFRAME_INERTIAROT };
 enum { MJB_WRAP_NONE = 0, MJB_WRAP_JOINT, MJB_WRAP_PULLEY, MJB_WRAP_SITE, MJB_WRAP_SPHERE, MJB_WRAP_CYLINDER };
+enum { MJB_FLUID_NONE = 0, MJB_FLUID_BOX, MJB_FLUID_ELLIPSOID };   // fluid_body[4*b]
+#define MJB_FLUID_NG 16   // doubles per geom in fluid_geom: geom_fluid[mjNFLUID = 12], semi-axes[3], 0
 #define MJB_MINVAL 1E-15
 #define MJB_MINMU 1E-5
 #define MJB_MINIMP 0.0001

@@ -99,6 +99,183 @@ MJB_HD inline void body_geoms(Ctx& c, int b, const double* pos, const double* qu
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// mj_fluid (engine_passive.c:403-431): forces of the surrounding medium (opt.density, opt.viscosity,
+// opt.wind) on every body with mass, either on the body's equivalent inertia box
+// (mj_inertiaBoxFluidModel :527-583) or, when one of its geoms asks for it, on the ellipsoids that
+// approximate its geoms (mj_ellipsoidFluidModel :588-646, mj_addedMassForces :650-690,
+// mj_viscousForces :705-789). The reference applies each force with mj_applyFT into qfrc_fluid; here
+// it is a wrench about the tree origin on the passive-wrench carrier of the forward sweep, which the
+// backward sweep projects on the dofs of the body's chain (the same J'f without the Jacobian).
+// The force laws are functions of a local velocity and model constants: out-of-line leaf functions.
+
+// local 6D velocity [ang, lin] of the body at world point p in the frame with axes R (columns), relative
+// to the wind: mj_objectVelocity(flg_local) followed by the rotated wind (engine_passive.c:539-549)
+MJB_DI void fluid_local_velocity(double* lvel, const double* V, const double* O, const double* p,
+                                 const double* R, const double* wind) {
+  const double dif[3] = {p[0] - O[0], p[1] - O[1], p[2] - O[2]};
+  double cr[3];
+  cross3(cr, dif, V);
+  const double lin[3] = {V[3] - cr[0], V[4] - cr[1], V[5] - cr[2]};
+  for (int k = 0; k < 3; k++) {            // mju_mulMatTVec3
+    lvel[k] = R[k]*V[0] + R[3 + k]*V[1] + R[6 + k]*V[2];
+    lvel[3 + k] = R[k]*lin[0] + R[3 + k]*lin[1] + R[6 + k]*lin[2];
+    lvel[3 + k] -= R[k]*wind[0] + R[3 + k]*wind[1] + R[6 + k]*wind[2];
+  }
+}
+
+// inertia-box model: Stokes drag of the equivalent sphere plus quadratic drag of the box faces (:551-575)
+MJB_COLD inline void fluid_box_force(double* lfrc, const double* lvel, const double* box, double density,
+                                     double viscosity) {
+  for (int k = 0; k < 6; k++) lfrc[k] = 0;
+  if (viscosity > 0) {
+    const double diam = (box[0] + box[1] + box[2])/3.0;
+    const double sa = -MJB_PI*diam*diam*diam*viscosity;
+    const double sl = -3.0*MJB_PI*diam*viscosity;
+    for (int k = 0; k < 3; k++) { lfrc[k] = lvel[k]*sa; lfrc[3 + k] = lvel[3 + k]*sl; }
+  }
+  if (density > 0) {
+    lfrc[3] -= 0.5*density*box[1]*box[2]*fabs(lvel[3])*lvel[3];
+    lfrc[4] -= 0.5*density*box[0]*box[2]*fabs(lvel[4])*lvel[4];
+    lfrc[5] -= 0.5*density*box[0]*box[1]*fabs(lvel[5])*lvel[5];
+    lfrc[0] -= density*box[0]*(box[1]*box[1]*box[1]*box[1] + box[2]*box[2]*box[2]*box[2])*fabs(lvel[0])*lvel[0]/64.0;
+    lfrc[1] -= density*box[1]*(box[0]*box[0]*box[0]*box[0] + box[2]*box[2]*box[2]*box[2])*fabs(lvel[1])*lvel[1]/64.0;
+    lfrc[2] -= density*box[2]*(box[0]*box[0]*box[0]*box[0] + box[1]*box[1]*box[1]*box[1])*fabs(lvel[2])*lvel[2]/64.0;
+  }
+}
+
+MJB_DI double fluid_sq(double x) { return x*x; }
+MJB_DI double fluid_p4(double x) { return (x*x)*(x*x); }
+
+// ellipsoid model of one geom: fg = its MJB_FLUID_NG record (interaction, blunt / slender / angular drag,
+// Kutta and Magnus lift coefficients, virtual mass[3] and inertia[3], semi-axes[3])
+MJB_COLD inline void fluid_ellipsoid_force(double* lfrc, const double* lvel, const double* fg, double density,
+                                           double viscosity) {
+  const double blunt = fg[1], slender = fg[2], angdrag = fg[3], kutta = fg[4], magnus = fg[5];
+  const double* vmass = fg + 6; const double* vinertia = fg + 9; const double* size = fg + 12;
+  const double lin[3] = {lvel[3], lvel[4], lvel[5]};
+  const double ang[3] = {lvel[0], lvel[1], lvel[2]};
+  for (int k = 0; k < 6; k++) lfrc[k] = 0;
+
+  // momentum of the fluid that moves with the body (added mass; the acceleration terms are off in the reference)
+  {
+    const double plin[3] = {density*vmass[0]*lin[0], density*vmass[1]*lin[1], density*vmass[2]*lin[2]};
+    const double pang[3] = {density*vinertia[0]*ang[0], density*vinertia[1]*ang[1], density*vinertia[2]*ang[2]};
+    double f[3], t1[3], t2[3];
+    cross3(f, plin, ang); cross3(t1, plin, lin); cross3(t2, pang, ang);
+    for (int k = 0; k < 3; k++) { lfrc[k] += t1[k]; lfrc[k] += t2[k]; lfrc[3 + k] += f[k]; }
+  }
+
+  // lift and drag
+  const double volume = 4.0/3.0 * MJB_PI * size[0] * size[1] * size[2];
+  const double m01 = size[0] > size[1] ? size[0] : size[1], n01 = size[0] < size[1] ? size[0] : size[1];
+  const double d_max = m01 > size[2] ? m01 : size[2];
+  const double d_min = n01 < size[2] ? n01 : size[2];
+  const double d_mid = size[0] + size[1] + size[2] - d_max - d_min;
+  const double A_max = MJB_PI * d_max * d_mid;
+
+  double fmag[3];
+  cross3(fmag, ang, lin);
+  for (int k = 0; k < 3; k++) fmag[k] *= magnus * density * volume;
+
+  // projection of the ellipsoid along the velocity: area and the cosine to its (unnormalised) normal
+  const double proj_denom = fluid_p4(size[1] * size[2]) * fluid_sq(lin[0]) +
+                            fluid_p4(size[2] * size[0]) * fluid_sq(lin[1]) +
+                            fluid_p4(size[0] * size[1]) * fluid_sq(lin[2]);
+  const double proj_num = fluid_sq(size[1] * size[2] * lin[0]) +
+                          fluid_sq(size[2] * size[0] * lin[1]) +
+                          fluid_sq(size[0] * size[1] * lin[2]);
+  const double A_proj = MJB_PI * sqrt(proj_denom / (proj_num > MJB_MINVAL ? proj_num : MJB_MINVAL));
+  const double nrm[3] = {fluid_sq(size[1] * size[2]) * lin[0], fluid_sq(size[2] * size[0]) * lin[1],
+                         fluid_sq(size[0] * size[1]) * lin[2]};
+  const double speed = sqrt(lin[0]*lin[0] + lin[1]*lin[1] + lin[2]*lin[2]);
+  const double cden = speed * proj_denom;
+  const double cos_alpha = proj_num / (cden > MJB_MINVAL ? cden : MJB_MINVAL);
+  double circ[3], fkut[3];
+  cross3(circ, nrm, lin);
+  for (int k = 0; k < 3; k++) circ[k] *= kutta * density * cos_alpha * A_proj;
+  cross3(fkut, circ, lin);
+
+  // Stokes terms of the equivalent sphere and the moments that scale the quadratic angular drag
+  const double eqD = 2.0/3.0 * (size[0] + size[1] + size[2]);
+  const double cforce = 3.0 * MJB_PI * eqD;
+  const double ctorq = MJB_PI * eqD*eqD*eqD;
+  const double I_max = 8.0/15.0 * MJB_PI * d_mid * fluid_p4(d_max);
+  double II[3];
+  for (int k = 0; k < 3; k++) {
+    const double d0 = size[k], d1 = size[(k + 1) % 3], d2 = size[(k + 2) % 3];
+    II[k] = 8.0/15.0 * MJB_PI * d0 * fluid_p4(d1 > d2 ? d1 : d2);
+  }
+  const double mom[3] = {ang[0] * (angdrag*II[0] + slender*(I_max - II[0])),
+                         ang[1] * (angdrag*II[1] + slender*(I_max - II[1])),
+                         ang[2] * (angdrag*II[2] + slender*(I_max - II[2]))};
+  const double drag_lin = viscosity*cforce + density*speed*(A_proj*blunt + slender*(A_max - A_proj));
+  const double drag_ang = viscosity * ctorq + density * sqrt(mom[0]*mom[0] + mom[1]*mom[1] + mom[2]*mom[2]);
+  for (int k = 0; k < 3; k++) {
+    lfrc[k] -= drag_ang * ang[k];
+    lfrc[3 + k] += fmag[k] + fkut[k] - drag_lin*lin[k];
+  }
+  for (int k = 0; k < 6; k++) lfrc[k] = lfrc[k]*fg[0];
+}
+
+// local wrench lfrc acting at world point p, frame R -> wrench about the tree origin O, added to wg
+MJB_DI void fluid_add_wrench(double* wg, const double* lfrc, const double* R, const double* p, const double* O) {
+  double T[3], F[3], cr[3];
+  mulMatVec3(T, R, lfrc); mulMatVec3(F, R, lfrc + 3);
+  const double r[3] = {p[0] - O[0], p[1] - O[1], p[2] - O[2]};
+  cross3(cr, r, F);
+  for (int k = 0; k < 3; k++) { wg[k] += cr[k] + T[k]; wg[3 + k] += F[k]; }
+}
+
+// the fluid wrench of one body. Out of line and free of the per-state context (an out-of-line call that
+// takes Ctx& would push the whole context into local memory): the caller packs the body's kinematics
+//   kin = [ V 6 (velocity about O) | O 3 | pos 3 | quat 4 | mat 9 | ip 3 | im 9 ]
+// inside its `has_fluid` branch, so models without a medium pay one warp-uniform branch and no registers.
+// fb: the body's fluid_body record; geom tables as in the model blob; [g0, g0 + gn) the body's geoms.
+#define MJB_FLUID_KIN 37
+MJB_COLD inline void fluid_wrench(double* wg, const double* kin, const double* fb, const mjbHdr* hdr,
+                                  const int* geom_sameframe, const double* geom_pos, const double* geom_quat,
+                                  const double* fluid_geom, int g0, int gn) {
+  const double* V = kin; const double* O = kin + 6; const double* pos = kin + 9; const double* quat = kin + 12;
+  const double* mat = kin + 16; const double* ip = kin + 25; const double* im = kin + 28;
+  const int kind = (int)fb[0];
+  double lvel[6], lfrc[6];
+  if (kind == MJB_FLUID_BOX) {
+    fluid_local_velocity(lvel, V, O, ip, im, hdr->wind);
+    fluid_box_force(lfrc, lvel, fb + 1, hdr->density, hdr->viscosity);
+    fluid_add_wrench(wg, lfrc, im, ip, O);
+    return;
+  }
+  if (kind != MJB_FLUID_ELLIPSOID) return;
+  for (int g = g0; g < g0 + gn; g++) {
+    const double* fg = fluid_geom + MJB_FLUID_NG*g;
+    if (fg[0] == 0.0) continue;
+    // the geom's pose as mj_kinematics forms it (engine_core_smooth.c:139-157, sameframe shortcuts)
+    const int sf = geom_sameframe[g];
+    double gp[3], gm[9];
+    if (sf == MJB_SAMEFRAME_BODY) {
+      gp[0] = pos[0]; gp[1] = pos[1]; gp[2] = pos[2];
+    } else if (sf == MJB_SAMEFRAME_INERTIA) {
+      gp[0] = ip[0]; gp[1] = ip[1]; gp[2] = ip[2];
+    } else {
+      mulMatVec3(gp, mat, geom_pos + 3*g);
+      gp[0] += pos[0]; gp[1] += pos[1]; gp[2] += pos[2];
+    }
+    if (sf == MJB_SAMEFRAME_NONE) {
+      double tq[4];
+      mulQuat(tq, quat, geom_quat + 4*g);
+      quat2Mat(gm, tq);
+    } else if (sf == MJB_SAMEFRAME_BODY || sf == MJB_SAMEFRAME_BODYROT) {
+      for (int k = 0; k < 9; k++) gm[k] = mat[k];
+    } else {
+      for (int k = 0; k < 9; k++) gm[k] = im[k];
+    }
+    fluid_local_velocity(lvel, V, O, gp, gm, hdr->wind);
+    fluid_ellipsoid_force(lfrc, lvel, fg, hdr->density, hdr->viscosity);
+    fluid_add_wrench(wg, lfrc, gm, gp, O);
+  }
+}
+
 // Body range [kLo, kHi) (kHi = 0: up to nbody). The generic kernels run the whole tree in one call;
 // the model-specialised build cuts the expanded sweep into stages of a few thousand instructions,
 // one kernel each, so that the code of a kernel stays resident in the instruction cache (measured:
@@ -409,6 +586,19 @@ MJB_HD inline void forward_sweep(Ctx& c) {
           const double F[3] = {H.gravity[0]*sgc, H.gravity[1]*sgc, H.gravity[2]*sgc};
           cross3(wg, off, F);
           wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
+        }
+        if (H.has_fluid) {
+          const double* fb = MD(fluid_body) + 4*b;
+          if (fb[0] != 0.0) {
+            double kin[MJB_FLUID_KIN], wf[6] = {0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 6; k++) kin[k] = V[k];
+            for (int k = 0; k < 3; k++) { kin[6 + k] = O[k]; kin[9 + k] = pos[k]; kin[25 + k] = ip[k]; }
+            for (int k = 0; k < 4; k++) kin[12 + k] = quat[k];
+            for (int k = 0; k < 9; k++) { kin[16 + k] = mat[k]; kin[28 + k] = im[k]; }
+            fluid_wrench(wf, kin, fb, c.H, MI(geom_sameframe), MD(geom_pos), MD(geom_quat), MD(fluid_geom),
+                         MI(body_geomadr)[b], MI(body_geomnum)[b]);
+            for (int k = 0; k < 6; k++) wg[k] += wf[k];
+          }
         }
         stn(SC(cfrc_gc), 6*b, wg, 6);
       }

@@ -196,9 +196,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   // ---- validation: everything outside the supported path is refused here, never approximated
   if (m->nflex) { err = "flex objects are not supported (nflex > 0)"; return false; }
   if (m->nplugin) { err = "engine plugins are not supported (nplugin > 0)"; return false; }
-  if (!(dsbl & mjDSBL_PASSIVE) && (m->opt.density > 0 || m->opt.viscosity > 0)) {
-    err = "fluid forces are not supported (opt.density / opt.viscosity > 0)"; return false;
-  }
+  // mj_fluid (engine_passive.c:403-431) runs iff this holds
+  const bool fluid = !(dsbl & mjDSBL_PASSIVE) && (m->opt.density > 0 || m->opt.viscosity > 0);
   // gravity compensation (engine_passive.c:381-401) runs iff this holds
   const bool gravcomp = !(dsbl & mjDSBL_PASSIVE) && m->ngravcomp && !(dsbl & mjDSBL_GRAVITY) &&
       (m->opt.gravity[0] != 0 || m->opt.gravity[1] != 0 || m->opt.gravity[2] != 0);
@@ -764,12 +763,49 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     if (pas && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_passive = true;
     if (tendon_active[t] && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_active = true;
   }
-  if (spatial_passive && gravcomp) {
+  if ((spatial_passive || fluid) && gravcomp) {
     for (int j = 0; j < m->njnt; j++) {
       if (m->jnt_actgravcomp[j]) {
-        err = "spatial-tendon springs/dampers together with actuator-routed gravity compensation "
-              "(jnt_actgravcomp) are not supported";
+        err = "spatial-tendon springs/dampers or fluid forces together with actuator-routed gravity "
+              "compensation (jnt_actgravcomp) are not supported";
         return false;
+      }
+    }
+  }
+  // Fluid forces (mj_fluid, engine_passive.c:403-431): per body either the inertia-box model or, if one
+  // of its geoms has geom_fluid[0] > 0, the ellipsoid model on its geoms. Everything that does not
+  // depend on the state is formed here: the box sides (:530-536) and the semi-axes (mju_geomSemiAxes).
+  std::vector<double> fluid_body, fluid_geom;
+  bool fluid_ellipsoid = false;
+  if (fluid) {
+    if (discrete >= 2) {
+      err = "mjENBL_INVDISCRETE with implicit / implicitfast: fluid forces (their velocity derivatives are not formed)";
+      return false;
+    }
+    fluid_body.assign((size_t)4 * m->nbody, 0.0);
+    for (int i = 1; i < m->nbody; i++) {
+      if (m->body_mass[i] < mjMINVAL) continue;
+      bool ell = false;
+      for (int j = 0; j < m->body_geomnum[i] && !ell; j++) ell = m->geom_fluid[mjNFLUID*(m->body_geomadr[i] + j)] > 0;
+      fluid_ellipsoid = fluid_ellipsoid || ell;
+      fluid_body[4*i] = ell ? MJB_FLUID_ELLIPSOID : MJB_FLUID_BOX;
+      const mjtNum* inertia = m->body_inertia + 3*i;
+      fluid_body[4*i + 1] = std::sqrt(std::max((mjtNum)mjMINVAL, (inertia[1] + inertia[2] - inertia[0])) / m->body_mass[i] * 6.0);
+      fluid_body[4*i + 2] = std::sqrt(std::max((mjtNum)mjMINVAL, (inertia[0] + inertia[2] - inertia[1])) / m->body_mass[i] * 6.0);
+      fluid_body[4*i + 3] = std::sqrt(std::max((mjtNum)mjMINVAL, (inertia[0] + inertia[1] - inertia[2])) / m->body_mass[i] * 6.0);
+    }
+    if (fluid_ellipsoid) {
+      fluid_geom.assign((size_t)MJB_FLUID_NG * m->ngeom, 0.0);
+      for (int g = 0; g < m->ngeom; g++) {
+        double* r = fluid_geom.data() + (size_t)MJB_FLUID_NG * g;
+        for (int k = 0; k < mjNFLUID; k++) r[k] = m->geom_fluid[mjNFLUID*g + k];
+        const mjtNum* size = m->geom_size + 3*g;
+        switch (m->geom_type[g]) {
+          case mjGEOM_SPHERE: r[12] = size[0]; r[13] = size[0]; r[14] = size[0]; break;
+          case mjGEOM_CAPSULE: r[12] = size[0]; r[13] = size[0]; r[14] = size[1] + size[0]; break;
+          case mjGEOM_CYLINDER: r[12] = size[0]; r[13] = size[0]; r[14] = size[1]; break;
+          default: r[12] = size[0]; r[13] = size[1]; r[14] = size[2];
+        }
       }
     }
   }
@@ -786,7 +822,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.simple_pairs = simple_pairs ? 1 : 0;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
-  H.passive_wrench = (gravcomp || spatial_passive) ? 1 : 0;
+  H.passive_wrench = (gravcomp || spatial_passive || fluid) ? 1 : 0;
+  H.has_fluid = fluid ? (fluid_ellipsoid ? 2 : 1) : 0;
+  H.density = m->opt.density; H.viscosity = m->opt.viscosity;
+  for (int k = 0; k < 3; k++) H.wind[k] = m->opt.wind[k];
   H.has_spatial = spatial_active ? 1 : 0;
   H.discrete_acc = discrete;
   H.discrete_trn = discrete_trn ? 1 : 0;
@@ -997,6 +1036,8 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushNums(MJB_N_scan_misc, scan_misc.data(), scan_misc.size());
   pushNums(MJB_N_sensor_cutoff, sensor_cutoff.data(), sensor_cutoff.size());
   pushNums(MJB_N_act_biasvel, act_biasvel.data(), act_biasvel.size());
+  pushNums(MJB_N_fluid_body, fluid_body.data(), fluid_body.size());
+  pushNums(MJB_N_fluid_geom, fluid_geom.data(), fluid_geom.size());
   {
     // focal lengths in pixels exactly as cam_project forms them (engine_sensor.c:155-160: float
     // arithmetic for the intrinsic form, the host's tan for the field-of-view form)
@@ -1030,7 +1071,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     sizes[MJB_SC_qfrc_passive] = nv;
     sizes[MJB_SC_ten_length] = nt; sizes[MJB_SC_ten_velocity] = nt; sizes[MJB_SC_ten_acc] = nt;
     sizes[MJB_SC_crb] = 10*nb; sizes[MJB_SC_ia] = 21*nb;
-    sizes[MJB_SC_cfrc_gc] = (gravcomp || spatial_passive) ? 6*nb : 0;
+    sizes[MJB_SC_cfrc_gc] = (gravcomp || spatial_passive || fluid) ? 6*nb : 0;
     {
       bool has_weld = false;
       for (int i = 0; i < m->neq; i++) has_weld = has_weld || m->eq_type[i] == mjEQ_WELD;

@@ -77,6 +77,9 @@ CASES = {
     "adhesion_elliptic": ("repo:tests/golden/models/adhesion.xml", {"cone": 1}, 128, (0.0, 0.3), 48, 200),
     # one actuator per branch of mj_transmission (outputs: TRANSMISSION_CASES)
     "transmission": ("repo:tests/golden/models/transmission.xml", {}, 128, (0.2, 1.2), 16, 64),
+    # mj_fluid: inertia-box and ellipsoid models in a dense, viscous medium with wind; Stokes terms alone
+    "fluid": ("repo:tests/golden/models/fluid.xml", {}, 256, (0.0, 1.2), 8, 32),
+    "fluid_box": ("repo:tests/golden/models/fluid_box.xml", {}, 128, (0.5, 1.5), 8, 16),
 }
 
 

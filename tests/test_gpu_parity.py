@@ -20,7 +20,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic"]
+         "adhesion_elliptic", "fluid", "fluid_box"]
 
 
 def _run(mjb, name, gold, outmask):

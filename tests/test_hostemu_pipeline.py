@@ -22,7 +22,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic"]
+         "adhesion_elliptic", "fluid", "fluid_box"]
 
 
 def _run(name):
@@ -378,3 +378,27 @@ def test_dense_and_sparse_jacobian_give_the_same_result():
     np.testing.assert_array_equal(dense["ncon"][:n], sparse["ncon"])
     np.testing.assert_array_equal(dense["nefc"][:n], sparse["nefc"])
     np.testing.assert_allclose(dense["qfrc_inverse"][:n], sparse["qfrc_inverse"], rtol=1e-9, atol=1e-9)
+
+
+def test_fluid_forces_follow_the_passive_flag_and_refuse_implicit_invdiscrete():
+    """mj_fluid runs inside mj_passive (engine_passive.c:436-462): with mjDSBL_PASSIVE the medium exerts
+    nothing; mjENBL_INVDISCRETE with an implicit integrator would need the fluid velocity derivatives
+    (mjd_passive_vel), which are not formed: refused at upload."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    path, ref = util.golden("fluid")
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = generate_states(model, 16, z_range=tuple(ref["z_range"]))
+    on = emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+    damping = -model.array("dof_damping").ravel() * qvel
+    assert np.abs(on["qfrc_passive"] - damping).max() > 1.0          # the fish in water: tens of newtons
+    model.set_opt_int("disableflags", model.get_opt_int("disableflags") | (1 << 5))    # mjDSBL_PASSIVE
+    off = emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+    assert np.abs(off["qfrc_passive"]).max() == 0.0
+    model.set_opt_int("disableflags", 0)
+    model.set_opt_int("enableflags", 1 << 3)                          # mjENBL_INVDISCRETE
+    model.set_opt_int("integrator", 3)                                # implicitfast
+    with pytest.raises(RuntimeError, match="fluid"):
+        emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+    model.set_opt_int("integrator", 0)                                # Euler: dof damping only, accepted
+    emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
