@@ -80,6 +80,8 @@
   X(geom_store) /* ngeom: bit0 position + z axis read by a later phase, bit1 full frame, bit2 full frame in runs with transmission / sensor outputs only */ \
   X(dof_frow)  /* nv   : friction-loss row of the dof within the friction block, -1 if none   */ \
   X(sensor_int) /* nsensor*MJB_SEN_NI : sensors evaluated on the device, see MJB_SEN_*       */ \
+  X(sensor_pairs) /* 4 per geom pair of the geom-distance sensors: geom 1, geom 2 (type-ordered like        \
+                     mj_geomDistance, engine_support.c:1412-1417), narrow-phase function, 1 if flipped */ \
   X(scan_int)  /* ncand*2 : compact rows of the bounding-sphere scan: geom 1 | filter kind << 28, geom 2      */ \
   X(scan_run)  /* nrun*4  : runs of consecutive candidates with the same (tree of body 1, tree of body 2):   \
                             first candidate, count, tree 1, tree 2 (-1: static body, never culled)           */ \
@@ -228,7 +230,8 @@ enum { MJB_SENS_TOUCH = 0, MJB_SENS_ACCELEROMETER = 1, MJB_SENS_VELOCIMETER = 2,
        MJB_SENS_FRAMEQUAT = 26, MJB_SENS_FRAMEXAXIS = 27, MJB_SENS_FRAMEYAXIS = 28, MJB_SENS_FRAMEZAXIS = 29,
        MJB_SENS_FRAMELINVEL = 30, MJB_SENS_FRAMEANGVEL = 31, MJB_SENS_FRAMELINACC = 32,
        MJB_SENS_FRAMEANGACC = 33, MJB_SENS_SUBTREECOM = 34, MJB_SENS_SUBTREELINVEL = 35,
-       MJB_SENS_SUBTREEANGMOM = 36, MJB_SENS_E_POTENTIAL = 40, MJB_SENS_E_KINETIC = 41, MJB_SENS_CLOCK = 42 };
+       MJB_SENS_SUBTREEANGMOM = 36, MJB_SENS_GEOMDIST = 37, MJB_SENS_GEOMNORMAL = 38, MJB_SENS_GEOMFROMTO = 39,
+       MJB_SENS_E_POTENTIAL = 40, MJB_SENS_E_KINETIC = 41, MJB_SENS_CLOCK = 42 };
 enum { MJB_OBJ_BODY = 1, MJB_OBJ_XBODY = 2, MJB_OBJ_GEOM = 5, MJB_OBJ_SITE = 6 };
 enum { MJB_DATATYPE_REAL = 0, MJB_DATATYPE_POSITIVE = 1 };
 

@@ -250,6 +250,28 @@ MJB_HD inline void cam_project(double* px, const double* target, const double* c
   px[1] = pix[1] / denom;
 }
 
+// one geom pair of mj_geomDistance (engine_support.c:1434-1449): the pair's primitive collision function with
+// the sensor cutoff as margin; returns the number of contacts written to con (normal in frame[0..2]).
+// Free of the per-state context, out of line: the sensor kernel carries one copy of the primitives.
+MJB_COLD inline int geom_pair_contacts(Con* con, int fn, double margin, const double* pos1, const double* mat1,
+                                       const double* size1, const double* pos2, const double* mat2,
+                                       const double* size2) {
+  switch (fn) {
+    case MJB_FN_PLANE_SPHERE: return plane_sphere(con, margin, pos1, mat1, pos2, size2[0]);
+    case MJB_FN_PLANE_CAPSULE: return plane_capsule(con, margin, pos1, mat1, pos2, mat2, size2);
+    case MJB_FN_PLANE_CYLINDER: return plane_cylinder(con, margin, pos1, mat1, pos2, mat2, size2);
+    case MJB_FN_PLANE_BOX: return plane_box(con, margin, pos1, mat1, pos2, mat2, size2);
+    case MJB_FN_PLANE_ELLIPSOID: return plane_ellipsoid(con, margin, pos1, mat1, pos2, mat2, size2);
+    case MJB_FN_SPHERE_SPHERE: return sphere_sphere(con, margin, pos1, mat1, size1[0], pos2, mat2, size2[0]);
+    case MJB_FN_SPHERE_CAPSULE: return sphere_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    case MJB_FN_SPHERE_CYLINDER: return sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    case MJB_FN_SPHERE_BOX: return sphere_box(con, margin, pos1, size1, pos2, mat2, size2);
+    case MJB_FN_CAPSULE_CAPSULE: return capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    case MJB_FN_CAPSULE_BOX: return capsule_box(con, margin, pos1, mat1, size1, pos2, mat2, size2);
+    default: return 0;
+  }
+}
+
 MJB_HD inline void sensors(Ctx& c) {
   const mjbHdr& H = *c.H;
   const size_t N = (size_t)c.N;
@@ -262,8 +284,44 @@ MJB_HD inline void sensors(Ctx& c) {
     const int* si = sen + MJB_SEN_NI*i;
     const int type = si[MJB_SEN_TYPE], objtype = si[MJB_SEN_OBJTYPE], objid = si[MJB_SEN_OBJID];
     const int reftype = si[MJB_SEN_REFTYPE], refid = si[MJB_SEN_REFID];
-    double v[4] = {0, 0, 0, 0};
-    if (type == MJB_SENS_TOUCH) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (type == MJB_SENS_GEOMDIST || type == MJB_SENS_GEOMNORMAL || type == MJB_SENS_GEOMFROMTO) {
+      // smallest signed distance between the geoms of two objects, its direction, its end points
+      // (engine_sensor.c:378-463); the pairs and their collision functions are listed at upload
+      const double margin = cutoff[i];
+      const int* pr = MI(sensor_pairs) + 4*objid;
+      double dist = margin, fromto[6] = {0, 0, 0, 0, 0, 0};
+      for (int p = 0; p < refid; p++, pr += 4) {
+        double p1[3], q1[4], m1[9], p2[3], q2[4], m2[9];
+        sensor_object(c, MJB_OBJ_GEOM, pr[0], p1, q1); quat2Mat(m1, q1);
+        sensor_object(c, MJB_OBJ_GEOM, pr[1], p2, q2); quat2Mat(m2, q2);
+        Con con[8];
+        const int num = geom_pair_contacts(con, pr[2], margin, p1, m1, MD(geom_size) + 3*pr[0], p2, m2,
+                                           MD(geom_size) + 3*pr[1]);
+        double dnew = margin;
+        int smallest = -1;
+        for (int k = 0; k < num; k++) {
+          if (con[k].dist < dnew) { dnew = con[k].dist; smallest = k; }
+        }
+        if (smallest >= 0 && dnew < dist) {
+          dist = dnew;
+          const double sign = pr[3] ? -1 : 1;
+          for (int k = 0; k < 3; k++) {
+            fromto[k] = con[smallest].pos[k] + con[smallest].frame[k]*(-0.5*sign*dnew);
+            fromto[3 + k] = con[smallest].pos[k] + con[smallest].frame[k]*(0.5*sign*dnew);
+          }
+        }
+      }
+      if (type == MJB_SENS_GEOMDIST) {
+        v[0] = dist;
+      } else if (type == MJB_SENS_GEOMNORMAL) {
+        double nrm[3] = {fromto[3] - fromto[0], fromto[4] - fromto[1], fromto[5] - fromto[2]};
+        if (nrm[0] != 0 || nrm[1] != 0 || nrm[2] != 0) normalize3(nrm);
+        v[0] = nrm[0]; v[1] = nrm[1]; v[2] = nrm[2];
+      } else {
+        for (int k = 0; k < 6; k++) v[k] = fromto[k];
+      }
+    } else if (type == MJB_SENS_TOUCH) {
       // sum of the normal forces of the contacts of the site's body whose normal ray meets the site
       // volume (engine_sensor.c:750-793); mj_contactForce's normal component is the row force
       // (frictionless, elliptic) or the sum of the pyramid's row forces (engine_support.c:1459-1490)
@@ -500,9 +558,9 @@ MJB_HD inline void sensors(Ctx& c) {
     // apply_cutoff (engine_sensor.c:40-68): real values on both sides, positive ones from above
     const double cut = cutoff[i];
     const int dt = si[MJB_SEN_DATATYPE];
-    for (int k = 0; k < si[MJB_SEN_DIM] && k < 4; k++) {
+    for (int k = 0; k < si[MJB_SEN_DIM] && k < 6; k++) {
       double x = v[k];
-      if (cut > 0) {
+      if (cut > 0 && type != MJB_SENS_GEOMFROMTO) {
         if (dt == MJB_DATATYPE_REAL) x = x < -cut ? -cut : (x > cut ? cut : x);
         else if (dt == MJB_DATATYPE_POSITIVE) x = cut < x ? cut : x;
       }

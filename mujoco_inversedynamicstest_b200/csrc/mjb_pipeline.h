@@ -432,7 +432,7 @@ MJB_HD inline void smooth_tail(Ctx& c) {
   passive_tendons<kSpatial>(c);
   wmask_clear(c);          // no wrench on any body yet (the accumulator rows themselves are not cleared)
   if (rows_enabled(H)) {
-    equality_rows(c);      // rows [0, ne)
+    equality_rows<kSpatial>(c);      // rows [0, ne)
     tendon_friction_rows<kSpatial>(c);
     tendon_limit_rows<kSpatial>(c);
     c.nf = H.nf_rows;

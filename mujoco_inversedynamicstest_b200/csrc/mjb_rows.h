@@ -552,6 +552,7 @@ MJB_HD inline int ne_base(Ctx& c) {
   return n;
 }
 
+template <bool kSpatial>
 MJB_HD inline void equality_rows(Ctx& c) {
   const mjbHdr& H = *c.H;
   if (H.neq == 0 || (H.disableflags & MJB_DSBL_EQUALITY)) return;
@@ -654,6 +655,11 @@ MJB_HD inline void equality_rows(Ctx& c) {
           v[j] = QVEL(jnt_dofadr[id]); a[j] = QACC(jnt_dofadr[id]);
         } else {
           pos[j] = AT(SC(ten_length), id); ref[j] = MD(tendon_length0)[id];
+          if (kSpatial && MI(wrap_type)[tendon_adr[id]] != MJB_WRAP_JOINT) {
+            // spatial tendon: J*qvel, J*qacc of its path (tendon_kinematics, relative point motion)
+            v[j] = AT(SC(ten_velocity), id); a[j] = AT(SC(ten_acc), id);
+            continue;
+          }
           for (int w = 0; w < tendon_num[id]; w++) {
             const int dof = jnt_dofadr[wrap_objid[tendon_adr[id] + w]];
             v[j] += wrap_prm[tendon_adr[id] + w]*QVEL(dof);
@@ -678,6 +684,8 @@ MJB_HD inline void equality_rows(Ctx& c) {
         const double fj = j == 0 ? f : -deriv*f;
         if (type == 2) {
           AT(qc, jnt_dofadr[id]) += fj;
+        } else if (kSpatial && MI(wrap_type)[tendon_adr[id]] != MJB_WRAP_JOINT) {
+          spatial_tendon_apply(c, id, fj, false);      // opposite forces along every segment of the path
         } else {
           for (int w = 0; w < tendon_num[id]; w++) {
             AT(qc, jnt_dofadr[wrap_objid[tendon_adr[id] + w]]) += wrap_prm[tendon_adr[id] + w]*fj;

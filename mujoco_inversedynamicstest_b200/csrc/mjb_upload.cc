@@ -252,18 +252,44 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   }
   // Sensors (mj_sensorPos / mj_sensorVel / mj_sensorAcc, engine_sensor.c:222,527,708): the types
   // whose inputs exist on this path are evaluated by the sensor kernel; the others (rangefinder,
-  // magnetometer, camera, geom distances, actuator quantities, energies, clock, user / plugin) are refused unless mjDSBL_SENSOR is set.
+  // geom distances through mjc_ccd, actuator forces, user / plugin) are refused unless mjDSBL_SENSOR is set.
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
   bool sensor_post = false, sensor_subtreevel = false, sensor_touch = false;
   bool sensor_cam = false, sensor_trn = false, sensor_energy = false, sensor_ray = false;
-  std::vector<int> sensor_int;
+  std::vector<int> sensor_int, sensor_pairs;
   std::vector<double> sensor_cutoff;
+  static_assert((int)mjSENS_GEOMDIST == (int)MJB_SENS_GEOMDIST && (int)mjSENS_GEOMFROMTO == (int)MJB_SENS_GEOMFROMTO, "mjtSensor");
   for (int i = 0; i < m->nsensor && sensors; i++) {
     const int t = m->sensor_type[i], ot = m->sensor_objtype[i], rt = m->sensor_reftype[i];
     const int rid = m->sensor_refid[i];
     auto frame_obj = [](int o) { return o == mjOBJ_BODY || o == mjOBJ_XBODY || o == mjOBJ_GEOM || o == mjOBJ_SITE; };
     bool ok = false;
+    int pair_first = -1, pair_count = 0;
     switch (t) {
+      case mjSENS_GEOMDIST: case mjSENS_GEOMNORMAL: case mjSENS_GEOMFROMTO:
+        // mj_geomDistance (engine_support.c:1406-1452) over every geom pair of the two objects: pairs whose
+        // entry of the collision table is a primitive function run that function with the cutoff as margin;
+        // pairs that go through mjc_ccd there (mjc_Convex, mjc_BoxBox) are not restated
+        ok = (ot == mjOBJ_BODY || ot == mjOBJ_GEOM) && (rt == mjOBJ_BODY || rt == mjOBJ_GEOM);
+        if (ok) {
+          const int oid = m->sensor_objid[i];
+          const int n1 = ot == mjOBJ_BODY ? m->body_geomnum[oid] : 1, id1 = ot == mjOBJ_BODY ? m->body_geomadr[oid] : oid;
+          const int n2 = rt == mjOBJ_BODY ? m->body_geomnum[rid] : 1, id2 = rt == mjOBJ_BODY ? m->body_geomadr[rid] : rid;
+          pair_first = (int)sensor_pairs.size() / 4;
+          for (int ga = id1; ga < id1 + n1 && ok; ga++) {
+            for (int gb = id2; gb < id2 + n2 && ok; gb++) {
+              const int flip = m->geom_type[ga] > m->geom_type[gb];
+              const int g1 = flip ? gb : ga, g2 = flip ? ga : gb;
+              const int fn = narrowphaseId(m->geom_type[g1], m->geom_type[g2]);
+              if (fn == -1) continue;                 // no collision function: the distance stays at the cutoff
+              if (fn < 0 || fn == MJB_FN_BOX_BOX) { ok = false; break; }
+              const int rec4[4] = {g1, g2, fn, flip};
+              sensor_pairs.insert(sensor_pairs.end(), rec4, rec4 + 4);
+              pair_count++;
+            }
+          }
+        }
+        break;
       case mjSENS_JOINTPOS: case mjSENS_JOINTVEL: case mjSENS_BALLQUAT: case mjSENS_BALLANGVEL:
       case mjSENS_SUBTREECOM:
         ok = true; break;
@@ -331,8 +357,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       setError(err, "sensor %d (mjtSensor %d) is not evaluated on the device: set mjDSBL_SENSOR or remove it", i, t);
       return false;
     }
-    const int rec[MJB_SEN_NI] = {t, m->sensor_datatype[i], ot, m->sensor_objid[i], rt, rid, m->sensor_dim[i],
-                                 m->sensor_adr[i]};
+    // geom-distance sensors: the object columns hold the range of their rows in sensor_pairs
+    const int rec[MJB_SEN_NI] = {t, m->sensor_datatype[i], ot, pair_first >= 0 ? pair_first : m->sensor_objid[i], rt,
+                                 pair_first >= 0 ? pair_count : rid, m->sensor_dim[i], m->sensor_adr[i]};
     sensor_int.insert(sensor_int.end(), rec, rec + MJB_SEN_NI);
     sensor_cutoff.push_back(m->sensor_cutoff[i]);
   }
@@ -359,11 +386,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     const int adr = m->tendon_adr[t];
     if (m->wrap_type[adr] != mjWRAP_JOINT) {
       // spatial tendon: its path is walked on the device when it carries a force (limit, friction
-      // loss, spring, damper); couplings through equality constraints are not supported yet
-      if (tendon_in_equality[t]) {
-        setError(err, "spatial tendon %d is used by an equality constraint (not supported)", t);
-        return false;
-      }
+      // loss, spring, damper, equality constraint)
       for (int j = 0; j < m->tendon_num[t]; j++) {
         const int wt = m->wrap_type[adr + j];
         if (wt != mjWRAP_SITE && wt != mjWRAP_SPHERE && wt != mjWRAP_CYLINDER && wt != mjWRAP_PULLEY) {
@@ -759,7 +782,13 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
     const bool lim = m->tendon_limited[t] && !(dsbl & mjDSBL_LIMIT) && constraints && !tendon_empty[t];
     const bool fric = m->tendon_frictionloss[t] > 0 && !(dsbl & mjDSBL_FRICTIONLOSS) && constraints && !tendon_empty[t];
     const bool pas = (m->tendon_stiffness[t] != 0 || m->tendon_damping[t] != 0) && !(dsbl & mjDSBL_PASSIVE);
-    tendon_active[t] = lim || fric || pas;
+    const bool spatial = m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT;
+    if (spatial && tendon_in_equality[t] && tendon_empty[t]) {
+      // the reference drops such a row in sparse mode and keeps a zero row in dense mode (mj_addConstraint)
+      setError(err, "spatial tendon %d between static bodies is used by an equality constraint (not supported)", t);
+      return false;
+    }
+    tendon_active[t] = lim || fric || pas || (spatial && tendon_in_equality[t]);
     if (pas && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_passive = true;
     if (tendon_active[t] && m->wrap_type[m->tendon_adr[t]] != mjWRAP_JOINT) spatial_active = true;
   }
@@ -918,6 +947,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   pushInts(MJB_I_sensor_int, sensor_int.data(), sensor_int.size());
   pushInts(MJB_I_body_static, body_static.data(), body_static.size());
   pushInts(MJB_I_tendon_active, tendon_active.data(), tendon_active.size());
+  pushInts(MJB_I_sensor_pairs, sensor_pairs.data(), sensor_pairs.size());
   pushInts(MJB_I_actuator_trn, m->actuator_trnid, (size_t)2 * m->nu);
   {
     // rangefinder sensors: the state-independent part of ray_eliminate (engine_ray.c:69-100; flg_static = 1,

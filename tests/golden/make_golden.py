@@ -80,6 +80,10 @@ CASES = {
     # mj_fluid: inertia-box and ellipsoid models in a dense, viscous medium with wind; Stokes terms alone
     "fluid": ("repo:tests/golden/models/fluid.xml", {}, 256, (0.0, 1.2), 8, 32),
     "fluid_box": ("repo:tests/golden/models/fluid_box.xml", {}, 128, (0.5, 1.5), 8, 16),
+    # equality constraints on spatial tendons (offset, quartic coupling, coupling with a fixed tendon)
+    "tendon_eq": ("repo:tests/golden/models/tendon_eq.xml", {}, 256, (0.3, 1.3), 8, 32),
+    # geom-distance sensors (distance / normal / fromto) over primitive pairs, geom-geom and body-body
+    "geomdist": ("repo:tests/golden/models/geomdist.xml", {}, 256, (0.0, 0.8), 8, 16),
 }
 
 

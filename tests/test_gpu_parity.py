@@ -20,7 +20,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic", "fluid", "fluid_box"]
+         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -274,6 +274,18 @@ def test_golden_sensordata_camlight_transmission_energy():
     # the stages came with the sensors
     assert np.isfinite(bd.camlight()["cam_xmat"]).all()
     assert np.isfinite(bd.transmission()["actuator_moment"]).all()
+
+
+def test_golden_geom_distance_sensors():
+    """distance / normal / fromto sensors (engine_sensor.c:378-463, mj_geomDistance engine_support.c:1406-1452)
+    over primitive geom pairs, geom-geom and body-body, cutoffs reached and not; pairs that need mjc_ccd
+    (box-box, convex) are refused at upload."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "geomdist", True, 0)
+    assert nbad == 0
+    nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    assert (ref["sensordata"] < 0).any() and (ref["sensordata"] == 2.0).any()      # penetrations and cutoffs occur
 
 
 @pytest.mark.parametrize("name", util.KNOWN_ANSWER_CASES)

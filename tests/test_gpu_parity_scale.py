@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256", "fluid", "fluid_box"]
+         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256", "fluid", "fluid_box", "tendon_eq"]
 
 # fixture -> (most entries allowed outside the strict bound, largest ratio to the bound allowed).
 # Everything not listed must have ZERO entries outside 1e-9*|ref| + 1e-12.

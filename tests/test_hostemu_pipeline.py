@@ -22,7 +22,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic", "fluid", "fluid_box"]
+         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq"]
 
 
 def _run(name):
@@ -235,7 +235,7 @@ def test_per_state_mocap_poses():
     assert nviol == 0, (nviol, worst)
 
 
-@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic"])
+@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic", "geomdist"])
 def test_sensordata(case):
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
     every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml;
