@@ -530,11 +530,51 @@ def make_known_answer_case(name):
     print(f"{name}: nq={m.int('nq')} nv={m.int('nv')} nsensordata={m.int('nsensordata')} reference reads {np.round(sd, 6)}")
 
 
+# Properties the reference's tests hold for mj_passive (test/engine/engine_passive_test.cc), restated on the inverse
+# path: the state of the test, the reference's own qfrc_passive next to it, the property checked by the tests here.
+#   fluid_*: :42-106, two models whose qfrc_passive must agree to 1e-14 (qvel = 1..6, quaternion 0.5 0.5 0.5 0.5)
+#   tendon_deadband: :143-165, spring force == stiffness * (springlength[1] - length) outside the deadband
+#     (EXPECT_EQ), exactly 0 inside (qpos[0] = -1)
+PROPERTY_CASES = {
+    "ka_fluid_two_bodies": "repo:tests/golden/models/ref_fluid_two_bodies.xml",
+    "ka_fluid_one_body": "repo:tests/golden/models/ref_fluid_one_body.xml",
+    "ka_tendon_deadband": "test/engine/testdata/tendon_springlength.xml",
+}
+
+
+def make_property_case(name):
+    xml = PROPERTY_CASES[name]
+    m = reflib.Model.from_xml(os.path.join(ROOT, xml[5:]) if xml.startswith("repo:") else reflib.reference_path(xml))
+    raw = os.path.join(HERE, name + ".mjb")
+    m.save_mjb(raw)
+    with open(raw, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".mjb.gz"), "wb", compresslevel=9, mtime=0) as g:
+        g.write(f.read())
+    os.remove(raw)
+    nq, nv = m.int("nq"), m.int("nv")
+    qpos = m.array("qpos0").reshape(1, nq).copy()
+    if name.startswith("ka_fluid"):
+        qpos[0, 3:7] = 0.5
+        qvel = np.arange(1.0, 7.0)[None]
+    else:
+        qpos = np.vstack([qpos, qpos]); qpos[1, 0] = -1
+        qvel = np.zeros((2, nv))
+    qacc = np.zeros_like(qvel)
+    fields = {"qfrc_passive": None}
+    if m.int("nsensordata") > 0:
+        fields["sensordata"] = None
+    out, _ = m.inverse_batch(qpos, qvel, qacc, fields=fields)
+    save = {"qpos": qpos, "qvel": qvel, "qacc": qacc}
+    for k, v in out.items():
+        save["ref_" + k] = v[..., 0] if (v.ndim == 3 and v.shape[2] == 1) else v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(f"{name}: nq={nq} nv={nv} reference qfrc_passive {np.round(save['ref_qfrc_passive'], 6)}")
+
+
 if __name__ == "__main__":
     for case in (sys.argv[1:] or list(CASES) + list(FD_CASES) + list(POST_CASES) + list(FWDINV_CASES) +
                  list(MOCAP_CASES) + list(REDUCED_CASES) + list(EDGE_CASES) + list(CAMLIGHT_CASES) +
                  list(TRANSMISSION_CASES) + list(XFRC_CASES) + list(EQACTIVE_CASES) +
-                 list(KNOWN_ANSWER_CASES)):
-        (make_known_answer_case if case in KNOWN_ANSWER_CASES else make_eqactive_case if case in EQACTIVE_CASES else make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
+                 list(KNOWN_ANSWER_CASES) + list(PROPERTY_CASES)):
+        (make_property_case if case in PROPERTY_CASES else make_known_answer_case if case in KNOWN_ANSWER_CASES else make_eqactive_case if case in EQACTIVE_CASES else make_xfrc_case if case in XFRC_CASES else make_transmission_case if case in TRANSMISSION_CASES else make_camlight_case if case in CAMLIGHT_CASES else make_edge_case if case in EDGE_CASES else make_reduced_case if case in REDUCED_CASES else make_fd_case if case in FD_CASES else make_post_case if case in POST_CASES else
          make_fwdinv_case if case in FWDINV_CASES else make_mocap_case if case in MOCAP_CASES else
          make_case)(case)

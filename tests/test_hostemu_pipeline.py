@@ -101,7 +101,7 @@ def test_rne_post_constraint_outputs(name):
 
 
 @pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld", "arm26", "transmission",
-                                  "humanoid_invdiscrete", "mocap"])
+                                  "humanoid_invdiscrete", "mocap", "fluid", "fluid_box", "tendon_eq", "geomdist"])
 def test_outputs_do_not_depend_on_the_debug_dump(name):
     """The product stores a scratch row only where a later stage reads it; the debug dump (mjbOUT_INTERNAL,
     used by the other tests of this file) stores everything. Same results either way, bit for bit."""
@@ -402,3 +402,38 @@ def test_fluid_forces_follow_the_passive_flag_and_refuse_implicit_invdiscrete():
         emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
     model.set_opt_int("integrator", 0)                                # Euler: dof damping only, accepted
     emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+
+
+def _property_fixture(name):
+    z = np.load(os.path.join(util.GOLDEN, name + ".npz"))
+    return os.path.join(util.GOLDEN, name + ".mjb.gz"), {k: z[k] for k in z.files}
+
+
+def test_reference_property_fluid_geoms_equivalent_to_bodies():
+    """test/engine/engine_passive_test.cc:42-106: two fluid-interacting boxes as geoms of one floating body or on
+    two child bodies of it give the same qfrc_passive (1e-14 in the reference's test); each model also against the
+    reference's own output."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    got = {}
+    for name in ("ka_fluid_two_bodies", "ka_fluid_one_body"):
+        path, z = _property_fixture(name)
+        model = mjb.Model.from_mjb(path)
+        out = emu.run(model, z["qpos"], z["qvel"], z["qacc"], nconmax=4, njmax=8)
+        got[name] = out["qfrc_passive"][0]
+        np.testing.assert_allclose(got[name], z["ref_qfrc_passive"][0], rtol=0, atol=1e-14)
+    assert np.abs(got["ka_fluid_one_body"]).max() > 1.0
+    np.testing.assert_allclose(got["ka_fluid_two_bodies"], got["ka_fluid_one_body"], rtol=0, atol=1e-14)
+
+
+def test_reference_property_tendon_spring_deadband():
+    """test/engine/engine_passive_test.cc:143-165: outside the deadband the spring force of the spatial tendon is
+    stiffness * (springlength[1] - length), inside it is exactly zero."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, z = _property_fixture("ka_tendon_deadband")
+    model = mjb.Model.from_mjb(path)
+    out = emu.run(model, z["qpos"], z["qvel"], z["qacc"], nconmax=4, njmax=8)
+    length = out["sensordata"][0, 0]
+    expected = model.array("tendon_stiffness").ravel()[0] * (model.array("tendon_lengthspring").ravel()[1] - length)
+    assert expected == -5.0
+    assert out["qfrc_passive"][0, 0] == expected
+    assert out["qfrc_passive"][1, 0] == 0.0
