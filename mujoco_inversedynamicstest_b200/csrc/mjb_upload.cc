@@ -330,6 +330,10 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
         break;
       case mjSENS_ACTUATORPOS: case mjSENS_ACTUATORVEL:
         ok = true; sensor_trn = true; break;
+      case mjSENS_ACTUATORFRC: case mjSENS_JOINTACTFRC:
+        // d->actuator_force / d->qfrc_actuator are not computed on the inverse path and are not batched
+        // inputs: 0, what a fresh mjData holds (the sensor kernel leaves these readings at zero)
+        ok = true; break;
       case mjSENS_E_POTENTIAL: case mjSENS_E_KINETIC:
         ok = true; sensor_energy = true; break;
       case mjSENS_TOUCH:

@@ -310,6 +310,18 @@ def test_reference_property_tendon_spring_deadband():
     assert qp[1, 0] == 0.0
 
 
+def test_golden_actuator_force_sensors_read_zero():
+    """actuatorfrc / jointactuatorfrc under mj_inverse copy d->actuator_force / d->qfrc_actuator, which the inverse
+    path never computes: zeros of a fresh mjData, with the neighbouring readings in their places."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    model, bd, ref, nbad, _ = _run(mjb, "actfrc", True, 0)
+    assert nbad == 0
+    got = bd.sensordata()
+    nviol, worst = util.sensor_violations(model, got, ref["sensordata"])
+    assert nviol == 0, (nviol, worst)
+    assert (got[:, [1, 3, 4]] == 0).all() and (got[:, [0, 2, 5]] != 0).all()
+
+
 def test_golden_geom_distance_sensors():
     """distance / normal / fromto sensors (engine_sensor.c:378-463, mj_geomDistance engine_support.c:1406-1452)
     over primitive geom pairs, geom-geom and body-body, cutoffs reached and not; pairs that need mjc_ccd

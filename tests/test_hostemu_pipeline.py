@@ -235,7 +235,7 @@ def test_per_state_mocap_poses():
     assert nviol == 0, (nviol, worst)
 
 
-@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic", "geomdist"])
+@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic", "geomdist", "actfrc"])
 def test_sensordata(case):
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
     every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml;
