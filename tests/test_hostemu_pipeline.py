@@ -325,7 +325,7 @@ def test_upload_rejections():
     # a sensor type that is not evaluated on the device is refused unless sensors are disabled
     sm = mjb.Model.from_mjb(util.golden("sensors")[0])
     assert len(emu.candidates(sm)) > 0
-    sm.array("sensor_type")[0] = 15             # mjSENS_ACTUATORFRC: the inverse path computes no actuation
+    sm.array("sensor_type")[0] = 44             # mjSENS_USER: filled by the mjcb_sensor callback, which does not exist on the device
     with pytest.raises(RuntimeError, match="sensor 0"):
         emu.candidates(sm)
     sm.set_opt_int("disableflags", 1 << 12)     # mjDSBL_SENSOR
