@@ -437,3 +437,34 @@ def test_reference_property_tendon_spring_deadband():
     assert expected == -5.0
     assert out["qfrc_passive"][0, 0] == expected
     assert out["qfrc_passive"][1, 0] == 0.0
+
+
+@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist"])
+def test_live_reference_on_fresh_states(name):
+    """4096 states that are in no fixture, against the reference run live (oracle/_ref): counters and equality /
+    limit rows bit-identical, qfrc_inverse inside the element-wise bound, qfrc_passive and sensordata to rounding."""
+    if not util.ref_available():
+        pytest.skip("reference library not built")
+    import mujoco_inversedynamicstest_b200 as mjb
+    from mujoco_inversedynamicstest_b200.states import generate_states
+    from bench import load_reference_model
+    path, gold = util.golden(name)
+    model = mjb.Model.from_mjb(path)
+    n = 4096
+    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(gold["z_range"]), first=3_000_000)
+    fields = {"ncon": 1, "nefc": 1, "efc_type": 32, "efc_state": 32, "qfrc_passive": None}
+    if model.int("nsensordata") > 0:
+        fields["sensordata"] = None
+    ref, _ = load_reference_model(name).inverse_batch(qpos, qvel, qacc, fields=fields, nthread=4)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+    assert (out["status"] == 0).all()
+    np.testing.assert_array_equal(out["ncon"], ref["ncon"])
+    np.testing.assert_array_equal(out["nefc"], ref["nefc"])
+    np.testing.assert_array_equal(out["efc_type"], ref["efc_type"][..., 0])
+    np.testing.assert_array_equal(out["efc_state"], ref["efc_state"][..., 0])
+    nviol, worst = util.qfrc_violations(out["qfrc_inverse"], ref["qfrc_inverse"])
+    assert nviol == 0, (nviol, worst)
+    np.testing.assert_allclose(out["qfrc_passive"], ref["qfrc_passive"][..., 0], rtol=1e-11, atol=1e-12)
+    if "sensordata" in fields:
+        nviol, worst = util.sensor_violations(model, out["sensordata"], ref["sensordata"][..., 0])
+        assert nviol == 0, (nviol, worst)
