@@ -822,8 +822,9 @@ __device__ __forceinline__ int warp_seg_incl_scan(int v, int key, int lane) {
   return v;
 }
 
-template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(LaunchArgs a) {
+// kConvex: the instantiation for models with mjc_Convex pairs (GJK / EPA, ~60 KB of stack per thread)
+template <bool kModelInSmem, bool kConvex = false>
+__global__ void __launch_bounds__(kThreads, kConvex ? 1 : MJB_CTAS_CONTACT) contact_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   // fallback of the item-parallel path: runs only when that path overflowed its lists
@@ -1006,7 +1007,7 @@ __global__ void __launch_bounds__(kThreads, MJB_CTAS_CONTACT) contact_kernel(Lau
           o = (unsigned)hits[j] >> 27; ci = hits[j] & 0x7ffffff;
           Ctx co = c;
           bind_state(co, a, wbase + o);
-          num = narrow_pair(co, ci, con);
+          num = narrow_pair<false, kConvex>(co, ci, con);
         }
         const int nincl = warp_incl_scan(num, lane);
         const int dst = pool_n + nincl - num;
@@ -1053,8 +1054,8 @@ constexpr int kNarrowTiles = 4;      // tiles of 256 items tested per dense narr
 #ifndef MJB_NARROW_SIMPLE_CTAS
 #define MJB_NARROW_SIMPLE_CTAS 4
 #endif
-template <bool kModelInSmem, bool kSimple>
-__global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : 2) contact_narrow_kernel(LaunchArgs a) {
+template <bool kModelInSmem, bool kSimple, bool kConvex = false>
+__global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : (kConvex ? 1 : 2)) contact_narrow_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   __shared__ int hitlist[256 * kNarrowTiles];
@@ -1097,7 +1098,7 @@ __global__ void __launch_bounds__(256, kSimple ? MJB_NARROW_SIMPLE_CTAS : 2) con
         it = a.items[item];
         Ctx& co = c;      // (a by-value copy of the context is what faulted here; rebinding c is enough)
         bind_state(co, a, it.state);
-        num = narrow_pair<kSimple>(co, it.ci, con);
+        num = narrow_pair<kSimple, kConvex>(co, it.ci, con);
       }
       if (__any_sync(0xffffffffu, num > 0)) {
         const int incl = warp_incl_scan(num, lane);
@@ -1695,7 +1696,10 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
         // the narrow / rows kernels walk lists whose length is only known on the device: full grids
         // (the grid follows the ITEM list, not the states: a 22-humanoid scene has 1,200 items per state,
         // and a grid of chunk_n / 256 CTAs left most of the chip idle -- one CTA per state, capped)
-        if (args.simple_pairs) {
+        if (args.has_convex) {
+          // GJK / EPA pairs: one resident CTA (the polytope lives on the threads' stacks), model from global memory
+          e = launch_phase(contact_narrow_kernel<false, false, true>, args, 0, 2, stream, 256, 0, 1);
+        } else if (args.simple_pairs) {
           e = (in_smem && !MJB_NARROW_GLOBAL) ? launch_phase(contact_narrow_kernel<true, true>, args, smem, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256, 0, 1)
                       : launch_phase(contact_narrow_kernel<false, true>, args, 0, 2 * MJB_NARROW_SIMPLE_CTAS, stream, 256, 0, 1);
         } else {
@@ -1728,7 +1732,8 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
     const bool csm = in_smem && MJB_CONTACT_MODEL_SMEM;
     const size_t csmem = contact_smem_bytes(args.model_bytes, csm, args.max_pair_contacts);
     { PhaseScope ps(timer, stream, kPhaseContact);
-    e = csm ? launch_phase(contact_kernel<true>, args, csmem, 8, stream, kThreads, MJB_CTAS_CONTACT)
+    e = args.has_convex ? launch_phase(contact_kernel<false, true>, args, contact_smem_bytes(args.model_bytes, false, args.max_pair_contacts), 8, stream, kThreads, 1)
+        : csm ? launch_phase(contact_kernel<true>, args, csmem, 8, stream, kThreads, MJB_CTAS_CONTACT)
             : launch_phase(contact_kernel<false>, args, csmem, 8, stream, kThreads, MJB_CTAS_CONTACT); }
     if (e != cudaSuccess) return e;
     *launches += 1;

@@ -271,6 +271,7 @@ enum {
   MJB_FN_CAPSULE_CAPSULE,
   MJB_FN_CAPSULE_BOX,
   MJB_FN_BOX_BOX,
+  MJB_FN_CONVEX,     // mjc_Convex: GJK / EPA on the two support mappings (csrc/mjb_convex.h)
   MJB_FN_COUNT
 };
 
@@ -343,12 +344,15 @@ typedef struct mjbHdr_ {
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
   int32_t has_fluid;         // mj_fluid runs (opt.density / opt.viscosity > 0, passive forces enabled): 1 inertia-box
                              // model only, 2 some body uses the ellipsoid model (engine_passive.c:403-431)
+  int32_t has_convex;        // some candidate pair goes through mjc_Convex (GJK / EPA, csrc/mjb_convex.h)
+  int32_t ccd_iterations;    // opt.ccd_iterations (<= MJB_CVX_MAXIT)
   int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)
   double timestep, impratio;
   double gravity[3];
   double magnetic[3];        // opt.magnetic (magnetometer sensors)
   double density, viscosity; // opt.density, opt.viscosity (mj_fluid)
   double wind[3];            // opt.wind
+  double ccd_tolerance;      // opt.ccd_tolerance
   int32_t nrun;             // runs of the candidate list for the tree-level broadphase (0: flat scan)
   int32_t ntree;            // kinematic trees with collidable geoms
   int32_t ioff[MJB_NI];     // element offsets into the int section
@@ -381,6 +385,7 @@ enum { MJB_SAMEFRAME_NONE = 0, MJB_SAMEFRAME_BODY, MJB_SAMEFRAME_INERTIA, MJB_SA
 enum { MJB_WRAP_NONE = 0, MJB_WRAP_JOINT, MJB_WRAP_PULLEY, MJB_WRAP_SITE, MJB_WRAP_SPHERE, MJB_WRAP_CYLINDER };
 enum { MJB_FLUID_NONE = 0, MJB_FLUID_BOX, MJB_FLUID_ELLIPSOID };   // fluid_body[4*b]
 #define MJB_FLUID_NG 16   // doubles per geom in fluid_geom: geom_fluid[mjNFLUID = 12], semi-axes[3], 0
+#define MJB_CVX_MAXIT 64   // most GJK / EPA iterations a model may ask for (opt.ccd_iterations; default 50)
 #define MJB_MINVAL 1E-15
 #define MJB_MINMU 1E-5
 #define MJB_MINIMP 0.0001

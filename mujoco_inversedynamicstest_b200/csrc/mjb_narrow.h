@@ -949,7 +949,14 @@ MJB_COLD inline int box_box(Con* con, double margin, const double* pos1, const d
 // kSimple: the model's pairs are all plane / sphere / capsule against sphere / capsule (mjbHdr::simple_pairs),
 // so that at most two contacts come back and `con` can stay in registers (no dynamically indexed primitive
 // is compiled in).
-template <bool kSimple = false>
+// kConvex: the GJK / EPA pairs are compiled in (their polytope takes ~60 KB of the thread's stack): only the kernel
+// instantiations that models with such pairs launch, and the CPU build
+#if defined(__CUDACC__)
+#define MJB_CONVEX_DEFAULT false
+#else
+#define MJB_CONVEX_DEFAULT true
+#endif
+template <bool kSimple = false, bool kConvex = MJB_CONVEX_DEFAULT>
 MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
   const int* cint = MI(cand_int) + MJB_CAND_NI*ci;
   const double* cn = MD(cand_num) + MJB_CAND_NN*ci;
@@ -990,6 +997,10 @@ MJB_HD inline int narrow_pair(Ctx& c, int ci, Con* con) {
       if (!kSimple) num = sphere_cylinder(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
     case MJB_FN_CAPSULE_CAPSULE:
       num = capsule_capsule(con, margin, pos1, mat1, size1, pos2, mat2, size2); break;
+    case MJB_FN_CONVEX:
+      if (kConvex) num = convex_pair(con, margin, MI(geom_type)[g1], pos1, mat1, size1, MI(geom_type)[g2], pos2, mat2, size2,
+                                     c.H->ccd_tolerance, c.H->ccd_iterations);
+      break;
     default: break;
   }
   for (int k = 0; k < num; k++) makeFrame(con[k].frame);

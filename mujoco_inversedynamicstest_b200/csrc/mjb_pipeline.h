@@ -392,6 +392,7 @@ MJB_DI double dot6(const double* a, const double* b) {
 #include "mjb_rows.h"
 #include "mjb_sweep.h"
 #include "mjb_contact.h"
+#include "mjb_convex.h"
 #include "mjb_narrow.h"
 #include "mjb_backward.h"
 #include "mjb_outputs.h"

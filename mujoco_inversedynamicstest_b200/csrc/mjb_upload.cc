@@ -77,6 +77,7 @@ int narrowphaseId(int t1, int t2) {
       switch (t2) {
         case mjGEOM_SPHERE: return MJB_FN_SPHERE_SPHERE;
         case mjGEOM_CAPSULE: return MJB_FN_SPHERE_CAPSULE;
+        case mjGEOM_ELLIPSOID: return MJB_FN_CONVEX;
         case mjGEOM_CYLINDER: return MJB_FN_SPHERE_CYLINDER;
         case mjGEOM_BOX: return MJB_FN_SPHERE_BOX;
         default: return -2;
@@ -84,9 +85,14 @@ int narrowphaseId(int t1, int t2) {
     case mjGEOM_CAPSULE:
       switch (t2) {
         case mjGEOM_CAPSULE: return MJB_FN_CAPSULE_CAPSULE;
+        case mjGEOM_ELLIPSOID: case mjGEOM_CYLINDER: return MJB_FN_CONVEX;
         case mjGEOM_BOX: return MJB_FN_CAPSULE_BOX;
         default: return -2;
       }
+    case mjGEOM_ELLIPSOID:
+      return (t2 == mjGEOM_ELLIPSOID || t2 == mjGEOM_CYLINDER || t2 == mjGEOM_BOX) ? MJB_FN_CONVEX : -2;
+    case mjGEOM_CYLINDER:
+      return (t2 == mjGEOM_CYLINDER || t2 == mjGEOM_BOX) ? MJB_FN_CONVEX : -2;
     case mjGEOM_BOX:
       return (t2 == mjGEOM_BOX) ? MJB_FN_BOX_BOX : -2;
     default:
@@ -282,7 +288,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
               const int g1 = flip ? gb : ga, g2 = flip ? ga : gb;
               const int fn = narrowphaseId(m->geom_type[g1], m->geom_type[g2]);
               if (fn == -1) continue;                 // no collision function: the distance stays at the cutoff
-              if (fn < 0 || fn == MJB_FN_BOX_BOX) { ok = false; break; }
+              if (fn < 0 || fn == MJB_FN_BOX_BOX || fn == MJB_FN_CONVEX) { ok = false; break; }
               const int rec4[4] = {g1, g2, fn, flip};
               sensor_pairs.insert(sensor_pairs.end(), rec4, rec4 + 4);
               pair_count++;
@@ -508,7 +514,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   std::vector<int> cand_int;
   std::vector<double> cand_num;
   int ncand = 0, max_pair_contacts = 1;
-  bool simple_pairs = true;
+  bool simple_pairs = true, has_convex = false;
   for (const Candidate& cd : cands) {
     int g1 = cd.g1, g2 = cd.g2;
     const int ipair = cd.ipair;
@@ -527,6 +533,17 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
                     g1, geomTypeName(t1), g2, geomTypeName(t2));
       err = buf;
       return false;
+    }
+
+    if (fn == MJB_FN_CONVEX) {
+      // mjc_Convex (engine_collision_convex.c:911-1003) as the reference runs it by default: its own GJK / EPA,
+      // one contact per pair
+      if (dsbl & mjDSBL_NATIVECCD) { err = "convex geom pairs with mjDSBL_NATIVECCD (libccd) are not supported"; return false; }
+      if (enbl & mjENBL_MULTICCD) { err = "convex geom pairs with mjENBL_MULTICCD are not supported"; return false; }
+      if (m->opt.ccd_iterations > MJB_CVX_MAXIT) {
+        setError(err, "opt.ccd_iterations = %d exceeds %d", m->opt.ccd_iterations, MJB_CVX_MAXIT); return false;
+      }
+      has_convex = true;
     }
 
     int condim;
@@ -853,6 +870,9 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.nrun = nrun; H.ntree = ntree;
   H.max_pair_contacts = max_pair_contacts;
   H.simple_pairs = simple_pairs ? 1 : 0;
+  H.has_convex = has_convex ? 1 : 0;
+  H.ccd_iterations = m->opt.ccd_iterations;
+  H.ccd_tolerance = m->opt.ccd_tolerance;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;
   H.has_gravcomp = gravcomp ? 1 : 0;
   H.passive_wrench = (gravcomp || spatial_passive || fluid) ? 1 : 0;

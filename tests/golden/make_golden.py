@@ -86,6 +86,10 @@ CASES = {
     "geomdist": ("repo:tests/golden/models/geomdist.xml", {}, 256, (0.0, 0.8), 8, 16),
     # actuator-force sensors read what a fresh mjData holds (mj_inverse computes no actuation)
     "actfrc": ("repo:tests/golden/models/actfrc.xml", {}, 32, (0.0, 1.0), 8, 16),
+    # geom pairs of mjc_Convex (GJK / EPA): the reference's slider-crank model with contacts on, and a scene with
+    # every convex pair type
+    "slider_crank": ("model/slider_crank/slider_crank.xml", {}, 256, (0.0, 1.5), 16, 64),
+    "convex": ("repo:tests/golden/models/convex.xml", {}, 1024, (0.1, 0.6), 48, 200),
 }
 
 

@@ -20,7 +20,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq"]
+         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq", "slider_crank", "convex"]
 
 
 def _run(mjb, name, gold, outmask):
@@ -584,7 +584,13 @@ def test_unsupported_models_are_rejected_at_upload(tmp_path):
     path, _ = util.golden("slider_crank_nocontact")
     model = mjb.Model.from_mjb(path)
     mjb.BatchData(model, 8)                       # contacts disabled: accepted
-    model.set_opt_int("disableflags", 0)          # contacts on: capsule-cylinder pairs -> mjc_Convex
+    model.set_opt_int("disableflags", 0)          # contacts on: capsule-cylinder pairs -> mjc_Convex (GJK / EPA)
+    mjb.BatchData(model, 8)
+    model.set_opt_int("enableflags", 1 << 4)      # mjENBL_MULTICCD
+    with pytest.raises(mjb.MjbError, match="MULTICCD"):
+        mjb.BatchData(model, 8)
+    model.set_opt_int("enableflags", 0)
+    model.array("geom_type")[1] = 7               # a mesh geom: no collision function here
     with pytest.raises(mjb.MjbError, match="collision function"):
         mjb.BatchData(model, 8)
 

@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256", "fluid", "fluid_box", "tendon_eq"]
+         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256", "fluid", "fluid_box", "tendon_eq", "slider_crank", "convex"]
 
 # fixture -> (most entries allowed outside the strict bound, largest ratio to the bound allowed).
 # Everything not listed must have ZERO entries outside 1e-9*|ref| + 1e-12.
@@ -185,7 +185,7 @@ def test_live_reference_1m_states(name, kernels):
 
 @pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kernels", ["specialised", "generic"])
-@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist"])
+@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
 def test_live_reference_passive_and_sensor_paths(name, kernels):
     """Fluid forces, equality constraints on spatial tendons and geom-distance sensors on 2^16 states that are in
     no fixture, against the reference run live: counters and row types / states bit-identical, qfrc_inverse inside
@@ -195,13 +195,14 @@ def test_live_reference_passive_and_sensor_paths(name, kernels):
     path, gold = util.golden(name)
     rm = _reference_model(path)
     model = mjb.Model.from_mjb(path)
-    n, nconmax, njmax = 1 << 16, 8, 32
+    n, nconmax, njmax = 1 << 16, int(gold["nconmax"]), int(gold["njmax"])
     qpos, qvel, qacc = generate_states(model, n, z_range=tuple(gold["z_range"]), first=5_000_000)
-    fields = {"ncon": 1, "nefc": 1, "efc_type": njmax, "efc_state": njmax, "qfrc_passive": None}
+    fields = {"ncon": 1, "nefc": 1, "efc_type": njmax, "efc_state": njmax, "qfrc_passive": None, "contact_geom": nconmax}
     if model.int("nsensordata") > 0:
         fields["sensordata"] = None
     ref, _ = rm.inverse_batch(qpos, qvel, qacc, fields=fields, nthread=max(1, len(os.sched_getaffinity(0))))
-    bd = mjb.BatchData(model, n, outmask=mjb.OUT_QFRC | mjb.OUT_COUNTS | mjb.OUT_EFC, nconmax=nconmax, njmax=njmax)
+    bd = mjb.BatchData(model, n, outmask=mjb.OUT_QFRC | mjb.OUT_COUNTS | mjb.OUT_EFC | mjb.OUT_CONTACT, nconmax=nconmax,
+                       njmax=njmax)
     if kernels == "specialised":
         try:
             bd.specialize()
@@ -211,6 +212,7 @@ def test_live_reference_passive_and_sensor_paths(name, kernels):
     assert bd.inverse() == 0
     cnt = bd.counts()
     np.testing.assert_array_equal(cnt["ncon"], ref["ncon"])
+    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
     np.testing.assert_array_equal(cnt["nefc"], ref["nefc"])
     efc = bd.efc()
     np.testing.assert_array_equal(efc["type"], ref["efc_type"][..., 0])

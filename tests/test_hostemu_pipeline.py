@@ -22,7 +22,7 @@ CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
          "sensors", "mocap", "touch", "touch_elliptic", "camlight", "transmission", "sensors2",
          "humanoid_invdiscrete_fast", "implicitfast", "humanoid_invdiscrete_implicit", "implicit", "adhesion",
-         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq"]
+         "adhesion_elliptic", "fluid", "fluid_box", "tendon_eq", "slider_crank", "convex"]
 
 
 def _run(name):
@@ -101,7 +101,7 @@ def test_rne_post_constraint_outputs(name):
 
 
 @pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld", "arm26", "transmission",
-                                  "humanoid_invdiscrete", "mocap", "fluid", "fluid_box", "tendon_eq", "geomdist"])
+                                  "humanoid_invdiscrete", "mocap", "fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
 def test_outputs_do_not_depend_on_the_debug_dump(name):
     """The product stores a scratch row only where a later stage reads it; the debug dump (mjbOUT_INTERNAL,
     used by the other tests of this file) stores everything. Same results either way, bit for bit."""
@@ -319,7 +319,17 @@ def test_upload_rejections():
     import mujoco_inversedynamicstest_b200 as mjb
     model = mjb.Model.from_mjb(util.golden("slider_crank_nocontact")[0])
     assert len(emu.candidates(model)) == 0
+    model.set_opt_int("disableflags", 0)          # contacts on: capsule-cylinder pairs -> mjc_Convex (GJK / EPA)
+    assert len(emu.candidates(model)) > 0
+    model.set_opt_int("enableflags", 1 << 4)      # mjENBL_MULTICCD: several contacts per convex pair
+    with pytest.raises(RuntimeError, match="MULTICCD"):
+        emu.candidates(model)
+    model.set_opt_int("enableflags", 0)
+    model.set_opt_int("disableflags", 1 << 16)    # mjDSBL_NATIVECCD: libccd's MPR
+    with pytest.raises(RuntimeError, match="NATIVECCD"):
+        emu.candidates(model)
     model.set_opt_int("disableflags", 0)
+    model.array("geom_type")[1] = 7               # a mesh geom: no collision function here
     with pytest.raises(RuntimeError, match="collision function"):
         emu.candidates(model)
     # a sensor type that is not evaluated on the device is refused unless sensors are disabled
@@ -439,7 +449,7 @@ def test_reference_property_tendon_spring_deadband():
     assert out["qfrc_passive"][1, 0] == 0.0
 
 
-@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist"])
+@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
 def test_live_reference_on_fresh_states(name):
     """4096 states that are in no fixture, against the reference run live (oracle/_ref): counters and equality /
     limit rows bit-identical, qfrc_inverse inside the element-wise bound, qfrc_passive and sensordata to rounding."""
@@ -452,11 +462,15 @@ def test_live_reference_on_fresh_states(name):
     model = mjb.Model.from_mjb(path)
     n = 4096
     qpos, qvel, qacc = generate_states(model, n, z_range=tuple(gold["z_range"]), first=3_000_000)
-    fields = {"ncon": 1, "nefc": 1, "efc_type": 32, "efc_state": 32, "qfrc_passive": None}
+    ncm, njm = int(gold["nconmax"]), int(gold["njmax"])
+    fields = {"ncon": 1, "nefc": 1, "efc_type": njm, "efc_state": njm, "qfrc_passive": None, "contact_geom": ncm,
+              "contact_dist": ncm}
     if model.int("nsensordata") > 0:
         fields["sensordata"] = None
     ref, _ = load_reference_model(name).inverse_batch(qpos, qvel, qacc, fields=fields, nthread=4)
-    out = emu.run(model, qpos, qvel, qacc, nconmax=8, njmax=32)
+    out = emu.run(model, qpos, qvel, qacc, nconmax=ncm, njmax=njm)
+    np.testing.assert_array_equal(out["contact_geom"], ref["contact_geom"])
+    np.testing.assert_array_equal(out["contact_dist"], ref["contact_dist"][..., 0])     # bit-identical in the CPU build
     assert (out["status"] == 0).all()
     np.testing.assert_array_equal(out["ncon"], ref["ncon"])
     np.testing.assert_array_equal(out["nefc"], ref["nefc"])
