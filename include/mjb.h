@@ -101,7 +101,7 @@ typedef enum mjbField_ {
 
 /* Validate `m`, flatten its constant tables, upload them to CUDA device `device` and allocate
  * batch buffers for up to nbatch_max states. Returns NULL and writes a message into err (if not
- * NULL) when the model uses a feature outside the supported path (convex/mesh/hfield/SDF geom
+ * NULL) when the model uses a feature outside the supported path (mesh/hfield/SDF geom
  * pairs that survive the static collision filters, flex, plugins, sensor types that
  * are not evaluated on the device (geom distances of box-box / convex pairs, user / plugin) without mjDSBL_SENSOR, INVDISCRETE
  * with RK4; full list in DESIGN.md section 5) or when CUDA fails.

@@ -763,6 +763,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.max_pair_contacts = d->hdr.max_pair_contacts;
   a.simple_pairs = d->hdr.simple_pairs;
   a.has_convex = d->hdr.has_convex;
+  a.sensor_ccd = d->hdr.sensor_ccd;
   a.cq = d->d_cq; a.items = d->d_items; a.item_con = d->d_item_con; a.contacts = d->d_contacts;
   a.items_cap = d->items_cap; a.contacts_cap = d->contacts_cap;
   a.slot_rec = d->d_slot_rec;

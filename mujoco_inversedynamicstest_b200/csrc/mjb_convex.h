@@ -676,18 +676,17 @@ MJB_NP inline int cvx_epa(CvxPoly& P, CvxRun& r, const CvxGeom& A, const CvxGeom
   return face;
 }
 
-// ---- the driver (mjc_ccd :2215-2343 with max_contacts = 1, dist_cutoff = 0) and the contact (mjc_CCDIteration)
-// geom 1 / geom 2 in the pair's type order; returns the number of contacts (0 or 1)
-MJB_NP inline int convex_pair(Con* con, double margin, int type1, const double* pos1, const double* mat1,
-                              const double* size1, int type2, const double* pos2, const double* mat2,
-                              const double* size2, double tolerance, int maxit) {
+// ---- the driver (mjc_ccd :2215-2343 with max_contacts = 1): geom 1 / geom 2 in the pair's type order, `margin` the
+// contact margin carried by the support mappings, `cutoff` the largest distance worth reporting (0: contact only).
+// Leaves the distance (negative: penetration, MJB_MAXVAL: beyond the cut-off) and the witness points in r.
+MJB_NP inline void cvx_ccd(CvxRun& r, double margin, double cutoff, int type1, const double* pos1, const double* mat1,
+                           const double* size1, int type2, const double* pos2, const double* mat2,
+                           const double* size2, double tolerance, int maxit) {
   CvxGeom A = {type1, type1, pos1, mat1, size1, margin};
   CvxGeom B = {type2, type2, pos2, mat2, size2, margin};
-  CvxRun r;
   cvx_cpy(r.xa, pos1); cvx_cpy(r.xb, pos2);
-  r.iter = 0; r.tolerance = tolerance; r.maxit = maxit; r.cutoff = 0;
+  r.iter = 0; r.tolerance = tolerance; r.maxit = maxit; r.cutoff = cutoff;
   r.nx = 0; r.nsimplex = 0; r.dist = 0;
-  bool done = false;
   if (type1 == MJB_GEOM_SPHERE || type2 == MJB_GEOM_SPHERE || type1 == MJB_GEOM_CAPSULE || type2 == MJB_GEOM_CAPSULE) {
     // spheres and capsules as points / segments first: their radius (and their half of the margin) comes back
     // by inflating the witness points, unless the cores themselves come closer than the tolerance
@@ -704,7 +703,7 @@ MJB_NP inline int convex_pair(Con* con, double margin, int type1, const double* 
     }
     r.cutoff += full1 + full2;
     cvx_gjk(r, A, B);
-    r.cutoff = 0;
+    r.cutoff = cutoff;
     A.shape = type1; A.margin = margin;
     B.shape = type2; B.margin = margin;
     if (r.dist > r.tolerance) {
@@ -715,25 +714,30 @@ MJB_NP inline int convex_pair(Con* con, double margin, int type1, const double* 
       if (full2) { r.xb[0] -= full2 * n[0]; r.xb[1] -= full2 * n[1]; r.xb[2] -= full2 * n[2]; }
       r.dist -= (full1 + full2);
       if (r.dist > r.cutoff) r.dist = MJB_MAXVAL;
-      done = true;
-    } else {
-      r.iter = 0;
-      cvx_cpy(r.xa, pos1); cvx_cpy(r.xb, pos2);
+      return;
     }
+    r.iter = 0;
+    cvx_cpy(r.xa, pos1); cvx_cpy(r.xb, pos2);
   }
-  if (!done) {
-    cvx_gjk(r, A, B);
-    if (r.dist <= tolerance && r.nsimplex > 1) {
-      r.dist = 0;
-      CvxPoly P;
-      P.nfaces = P.ncand = P.nverts = 0;
-      int bad;
-      if (r.nsimplex == 2) bad = cvx_start_segment(P, r, A, B);
-      else if (r.nsimplex == 3) bad = cvx_start_triangle(P, r, A, B);
-      else bad = cvx_start_tetrahedron(P, r, A, B);
-      if (!bad) cvx_epa(P, r, A, B);
-    }
+  cvx_gjk(r, A, B);
+  if (r.dist <= tolerance && r.nsimplex > 1) {
+    r.dist = 0;
+    CvxPoly P;
+    P.nfaces = P.ncand = P.nverts = 0;
+    int bad;
+    if (r.nsimplex == 2) bad = cvx_start_segment(P, r, A, B);
+    else if (r.nsimplex == 3) bad = cvx_start_triangle(P, r, A, B);
+    else bad = cvx_start_tetrahedron(P, r, A, B);
+    if (!bad) cvx_epa(P, r, A, B);
   }
+}
+
+// the contact of a convex pair (mjc_CCDIteration, engine_collision_convex.c:791-819); returns 0 or 1
+MJB_NP inline int convex_pair(Con* con, double margin, int type1, const double* pos1, const double* mat1,
+                              const double* size1, int type2, const double* pos2, const double* mat2,
+                              const double* size2, double tolerance, int maxit) {
+  CvxRun r;
+  cvx_ccd(r, margin, 0, type1, pos1, mat1, size1, type2, pos2, mat2, size2, tolerance, maxit);
   if (!(r.dist < 0)) return 0;
   if (r.nx < 1) return 0;
   Con& c = con[0];

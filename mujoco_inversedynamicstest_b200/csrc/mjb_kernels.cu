@@ -1399,8 +1399,8 @@ __global__ void __launch_bounds__(kThreads, 4) fwdinv_kernel(LaunchArgs a) {
 
 // sensordata of the chunk (mj_sensorPos / Vel / Acc); launched only for models with sensors, after
 // the backward kernel has left cacc / cfrc_int in the outputs
-template <bool kModelInSmem>
-__global__ void __launch_bounds__(kThreads, 4) sensor_kernel(LaunchArgs a) {
+template <bool kModelInSmem, bool kCcd = false>
+__global__ void __launch_bounds__(kThreads, kCcd ? 1 : 4) sensor_kernel(LaunchArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mbar;
   Ctx c;
@@ -1408,7 +1408,7 @@ __global__ void __launch_bounds__(kThreads, 4) sensor_kernel(LaunchArgs a) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.chunk_n;
        i += (long long)gridDim.x * kThreads) {
     bind_state(c, a, i);
-    sensors(c);
+    sensors<kCcd>(c);
   }
 }
 
@@ -1778,7 +1778,8 @@ cudaError_t launch_inverse(const LaunchArgs& args, cudaStream_t stream, int* lau
   }
   // sensors last: they read the energies, the camera poses and the transmission outputs
   if (args.out.sensordata && !args.skip_sensors) {
-    e = (in_smem && !args.sensor_cold) ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
+    e = args.sensor_ccd ? launch_phase(sensor_kernel<false, true>, args, 0, 2, stream)
+        : (in_smem && !args.sensor_cold) ? launch_phase(sensor_kernel<true>, args, smem, 8, stream)
                                        : launch_phase(sensor_kernel<false>, args, 0, 8, stream);
     if (e != cudaSuccess) return e;
     ++*launches;

@@ -66,6 +66,7 @@ struct LaunchArgs {
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
   int simple_pairs;             // mjbHdr::simple_pairs (selects the narrow-phase kernel instantiation)
+  int sensor_ccd;               // mjbHdr::sensor_ccd (the sensor kernel instantiation that carries GJK / EPA)
   int has_convex;               // mjbHdr::has_convex (the instantiations that carry GJK / EPA and its polytope)
   int skip_sensors;             // mj_inverseSkip(skipsensor = 1): leave sensordata as it is
   int inertia_subwarp;          // 1: mj_crb + mj_factorM by inertia_subwarp_kernel (8 lanes per state, on-chip intermediates)

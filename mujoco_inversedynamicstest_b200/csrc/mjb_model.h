@@ -344,6 +344,7 @@ typedef struct mjbHdr_ {
   int32_t sensor_touch;      // some touch sensor reads the contact list and the contact rows' forces
   int32_t has_fluid;         // mj_fluid runs (opt.density / opt.viscosity > 0, passive forces enabled): 1 inertia-box
                              // model only, 2 some body uses the ellipsoid model (engine_passive.c:403-431)
+  int32_t sensor_ccd;        // some geom-distance sensor measures a box-box or convex pair (mjc_ccd with a cut-off)
   int32_t has_convex;        // some candidate pair goes through mjc_Convex (GJK / EPA, csrc/mjb_convex.h)
   int32_t ccd_iterations;    // opt.ccd_iterations (<= MJB_CVX_MAXIT)
   int32_t simple_pairs;      // every candidate pair is plane/sphere/capsule against sphere/capsule (<= 2 contacts, z axes only)

@@ -272,6 +272,9 @@ MJB_COLD inline int geom_pair_contacts(Con* con, int fn, double margin, const do
   }
 }
 
+// kCcd: geom-distance sensors over pairs that the reference measures with mjc_ccd (box-box and the convex pairs,
+// mj_geomDistanceCCD engine_support.c:1376-1402) are compiled in -- the kernel instantiation for models with such sensors
+template <bool kCcd = MJB_CONVEX_DEFAULT>
 MJB_HD inline void sensors(Ctx& c) {
   const mjbHdr& H = *c.H;
   const size_t N = (size_t)c.N;
@@ -295,6 +298,19 @@ MJB_HD inline void sensors(Ctx& c) {
         double p1[3], q1[4], m1[9], p2[3], q2[4], m2[9];
         sensor_object(c, MJB_OBJ_GEOM, pr[0], p1, q1); quat2Mat(m1, q1);
         sensor_object(c, MJB_OBJ_GEOM, pr[1], p2, q2); quat2Mat(m2, q2);
+        if (pr[2] == MJB_FN_CONVEX || pr[2] == MJB_FN_BOX_BOX) {
+          // GJK distance with the cutoff, EPA depth when penetrating; the end points stay in the pair's type order
+          if (kCcd) {
+            CvxRun r;
+            cvx_ccd(r, 0, margin, MI(geom_type)[pr[0]], p1, m1, MD(geom_size) + 3*pr[0], MI(geom_type)[pr[1]], p2, m2,
+                    MD(geom_size) + 3*pr[1], H.ccd_tolerance, H.ccd_iterations);
+            if (r.dist < dist) {
+              dist = r.dist;
+              for (int k = 0; k < 3; k++) { fromto[k] = r.nx > 0 ? r.xa[k] : 0; fromto[3 + k] = r.nx > 0 ? r.xb[k] : 0; }
+            }
+          }
+          continue;
+        }
         Con con[8];
         const int num = geom_pair_contacts(con, pr[2], margin, p1, m1, MD(geom_size) + 3*pr[0], p2, m2,
                                            MD(geom_size) + 3*pr[1]);

@@ -597,7 +597,7 @@ MJB_HD inline void inverse_one_state(Ctx& c, double* qacc_discrete = nullptr) {
   if (c.out.energy) energy(c);
   if (c.out.cam_xpos) camlight(c);
   if (c.out.actuator_length) transmission(c);
-  if (c.out.sensordata) sensors(c);
+  if (c.out.sensordata) sensors<>(c);
   if (c.out.fwdinv) compare_fwdinv(c);
 }
 

@@ -262,6 +262,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   const bool sensors = m->nsensor > 0 && !(dsbl & mjDSBL_SENSOR);
   bool sensor_post = false, sensor_subtreevel = false, sensor_touch = false;
   bool sensor_cam = false, sensor_trn = false, sensor_energy = false, sensor_ray = false;
+  bool sensor_ccd = false;
   std::vector<int> sensor_int, sensor_pairs;
   std::vector<double> sensor_cutoff;
   static_assert((int)mjSENS_GEOMDIST == (int)MJB_SENS_GEOMDIST && (int)mjSENS_GEOMFROMTO == (int)MJB_SENS_GEOMFROMTO, "mjtSensor");
@@ -275,7 +276,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
       case mjSENS_GEOMDIST: case mjSENS_GEOMNORMAL: case mjSENS_GEOMFROMTO:
         // mj_geomDistance (engine_support.c:1406-1452) over every geom pair of the two objects: pairs whose
         // entry of the collision table is a primitive function run that function with the cutoff as margin;
-        // pairs that go through mjc_ccd there (mjc_Convex, mjc_BoxBox) are not restated
+        // pairs that go through mjc_ccd there (mjc_Convex, mjc_BoxBox) run GJK / EPA with the cutoff
         ok = (ot == mjOBJ_BODY || ot == mjOBJ_GEOM) && (rt == mjOBJ_BODY || rt == mjOBJ_GEOM);
         if (ok) {
           const int oid = m->sensor_objid[i];
@@ -288,7 +289,11 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
               const int g1 = flip ? gb : ga, g2 = flip ? ga : gb;
               const int fn = narrowphaseId(m->geom_type[g1], m->geom_type[g2]);
               if (fn == -1) continue;                 // no collision function: the distance stays at the cutoff
-              if (fn < 0 || fn == MJB_FN_BOX_BOX || fn == MJB_FN_CONVEX) { ok = false; break; }
+              if (fn < 0) { ok = false; break; }
+              if (fn == MJB_FN_BOX_BOX || fn == MJB_FN_CONVEX) {       // measured by mjc_ccd in the reference
+                if ((dsbl & mjDSBL_NATIVECCD) || m->opt.ccd_iterations > MJB_CVX_MAXIT) { ok = false; break; }
+                sensor_ccd = true;
+              }
               const int rec4[4] = {g1, g2, fn, flip};
               sensor_pairs.insert(sensor_pairs.end(), rec4, rec4 + 4);
               pair_count++;
@@ -871,6 +876,7 @@ bool buildModelBlob(const mjModel* m, std::vector<unsigned char>& blob, std::str
   H.max_pair_contacts = max_pair_contacts;
   H.simple_pairs = simple_pairs ? 1 : 0;
   H.has_convex = has_convex ? 1 : 0;
+  H.sensor_ccd = sensor_ccd ? 1 : 0;
   H.ccd_iterations = m->opt.ccd_iterations;
   H.ccd_tolerance = m->opt.ccd_tolerance;
   H.disableflags = dsbl; H.enableflags = enbl; H.cone = m->opt.cone;

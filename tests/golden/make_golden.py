@@ -84,6 +84,7 @@ CASES = {
     "tendon_eq": ("repo:tests/golden/models/tendon_eq.xml", {}, 256, (0.3, 1.3), 8, 32),
     # geom-distance sensors (distance / normal / fromto) over primitive pairs, geom-geom and body-body
     "geomdist": ("repo:tests/golden/models/geomdist.xml", {}, 256, (0.0, 0.8), 8, 16),
+    "geomdist_ccd": ("repo:tests/golden/models/geomdist_ccd.xml", {}, 256, (0.0, 0.8), 8, 16),
     # actuator-force sensors read what a fresh mjData holds (mj_inverse computes no actuation)
     "actfrc": ("repo:tests/golden/models/actfrc.xml", {}, 32, (0.0, 1.0), 8, 16),
     # geom pairs of mjc_Convex (GJK / EPA): the reference's slider-crank model with contacts on, and a scene with

@@ -322,12 +322,14 @@ def test_golden_actuator_force_sensors_read_zero():
     assert (got[:, [1, 3, 4]] == 0).all() and (got[:, [0, 2, 5]] != 0).all()
 
 
-def test_golden_geom_distance_sensors():
+@pytest.mark.parametrize("name", ["geomdist", "geomdist_ccd"])
+def test_golden_geom_distance_sensors(name):
     """distance / normal / fromto sensors (engine_sensor.c:378-463, mj_geomDistance engine_support.c:1406-1452)
-    over primitive geom pairs, geom-geom and body-body, cutoffs reached and not; pairs that need mjc_ccd
-    (box-box, convex) are refused at upload."""
+    over primitive geom pairs, geom-geom and body-body, cutoffs reached and not (geomdist), and over the pairs
+    the reference measures with mjc_ccd: box-box and the convex pairs (geomdist_ccd; GJK with the cutoff, EPA
+    when penetrating)."""
     import mujoco_inversedynamicstest_b200 as mjb
-    model, bd, ref, nbad, _ = _run(mjb, "geomdist", True, 0)
+    model, bd, ref, nbad, _ = _run(mjb, name, True, 0)
     assert nbad == 0
     nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"])
     assert nviol == 0, (nviol, worst)

@@ -185,7 +185,7 @@ def test_live_reference_1m_states(name, kernels):
 
 @pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kernels", ["specialised", "generic"])
-@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
+@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "geomdist_ccd", "slider_crank", "convex"])
 def test_live_reference_passive_and_sensor_paths(name, kernels):
     """Fluid forces, equality constraints on spatial tendons and geom-distance sensors on 2^16 states that are in
     no fixture, against the reference run live: counters and row types / states bit-identical, qfrc_inverse inside

@@ -101,7 +101,7 @@ def test_rne_post_constraint_outputs(name):
 
 
 @pytest.mark.parametrize("name", ["humanoid", "zoo", "sensors", "sensors2", "touch", "implicit", "tendons", "weld", "arm26", "transmission",
-                                  "humanoid_invdiscrete", "mocap", "fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
+                                  "humanoid_invdiscrete", "mocap", "fluid", "fluid_box", "tendon_eq", "geomdist", "geomdist_ccd", "slider_crank", "convex"])
 def test_outputs_do_not_depend_on_the_debug_dump(name):
     """The product stores a scratch row only where a later stage reads it; the debug dump (mjbOUT_INTERNAL,
     used by the other tests of this file) stores everything. Same results either way, bit for bit."""
@@ -235,7 +235,7 @@ def test_per_state_mocap_poses():
     assert nviol == 0, (nviol, worst)
 
 
-@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic", "geomdist", "actfrc"])
+@pytest.mark.parametrize("case", ["sensors", "sensors2", "touch", "touch_elliptic", "geomdist", "geomdist_ccd", "actfrc"])
 def test_sensordata(case):
     """d->sensordata of the reference's mj_inverse (mj_sensorPos / Vel / Acc, engine_sensor.c) for
     every sensor type evaluated on the device, cutoffs included (tests/golden/models/sensors.xml;
@@ -449,7 +449,7 @@ def test_reference_property_tendon_spring_deadband():
     assert out["qfrc_passive"][1, 0] == 0.0
 
 
-@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "slider_crank", "convex"])
+@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "geomdist_ccd", "slider_crank", "convex"])
 def test_live_reference_on_fresh_states(name):
     """4096 states that are in no fixture, against the reference run live (oracle/_ref): counters and equality /
     limit rows bit-identical, qfrc_inverse inside the element-wise bound, qfrc_passive and sensordata to rounding."""
