@@ -103,7 +103,7 @@ typedef enum mjbField_ {
  * batch buffers for up to nbatch_max states. Returns NULL and writes a message into err (if not
  * NULL) when the model uses a feature outside the supported path (mesh/hfield/SDF geom
  * pairs that survive the static collision filters, flex, plugins, sensor types that
- * are not evaluated on the device (geom distances of box-box / convex pairs, user / plugin) without mjDSBL_SENSOR, INVDISCRETE
+ * are not evaluated on the device (user / plugin) without mjDSBL_SENSOR, INVDISCRETE
  * with RK4; full list in DESIGN.md section 5) or when CUDA fails.
  * Models with sensors get d->sensordata (mjbF_SENSORDATA) from mj_sensorPos / Vel / Acc
  * (src/engine/engine_sensor.c:222,527,708) on every mjb_inverse, like mj_inverse.

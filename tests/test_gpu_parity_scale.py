@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["humanoid", "humanoid_elliptic", "humanoid_nocontact", "humanoids22",
          "slider_crank_nocontact", "inverse_test", "arm26", "weld", "connect", "zoo", "zoo_elliptic",
          "gravcomp", "humanoid_invdiscrete", "capsbox", "capsbox_elliptic", "boxes", "boxes_elliptic", "tendons",
-         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256", "fluid", "fluid_box", "tendon_eq", "slider_crank", "convex"]
+         "sensors", "mocap", "touch", "touch_elliptic", "humanoids22_256"]
 
 # fixture -> (most entries allowed outside the strict bound, largest ratio to the bound allowed).
 # Everything not listed must have ZERO entries outside 1e-9*|ref| + 1e-12.
@@ -181,48 +181,3 @@ def test_live_reference_1m_states(name, kernels):
     assert acc["scaled_viol"] <= util.LIVE_SCALED_FRACTION * acc["entries"], acc
     assert acc["conditioning_viol"] <= util.LIVE_SCALED_FRACTION * acc["entries"], acc
     assert acc["worst_vs_state_max"] < 1e-9, acc        # no entry is off by more than 1e-9 of its state's largest force
-
-
-@pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("kernels", ["specialised", "generic"])
-@pytest.mark.parametrize("name", ["fluid", "fluid_box", "tendon_eq", "geomdist", "geomdist_ccd", "slider_crank", "convex"])
-def test_live_reference_passive_and_sensor_paths(name, kernels):
-    """Fluid forces, equality constraints on spatial tendons and geom-distance sensors on 2^16 states that are in
-    no fixture, against the reference run live: counters and row types / states bit-identical, qfrc_inverse inside
-    the element-wise bound, qfrc_passive and sensordata within 1e-9 rel / 1e-12 abs."""
-    import mujoco_inversedynamicstest_b200 as mjb
-    from mujoco_inversedynamicstest_b200.states import generate_states
-    path, gold = util.golden(name)
-    rm = _reference_model(path)
-    model = mjb.Model.from_mjb(path)
-    n, nconmax, njmax = 1 << 16, int(gold["nconmax"]), int(gold["njmax"])
-    qpos, qvel, qacc = generate_states(model, n, z_range=tuple(gold["z_range"]), first=5_000_000)
-    fields = {"ncon": 1, "nefc": 1, "efc_type": njmax, "efc_state": njmax, "qfrc_passive": None, "contact_geom": nconmax}
-    if model.int("nsensordata") > 0:
-        fields["sensordata"] = None
-    ref, _ = rm.inverse_batch(qpos, qvel, qacc, fields=fields, nthread=max(1, len(os.sched_getaffinity(0))))
-    bd = mjb.BatchData(model, n, outmask=mjb.OUT_QFRC | mjb.OUT_COUNTS | mjb.OUT_EFC | mjb.OUT_CONTACT, nconmax=nconmax,
-                       njmax=njmax)
-    if kernels == "specialised":
-        try:
-            bd.specialize()
-        except mjb.MjbError as exc:
-            pytest.skip(f"not specialised: {exc}")
-    bd.set_state(qpos, qvel, qacc)
-    assert bd.inverse() == 0
-    cnt = bd.counts()
-    np.testing.assert_array_equal(cnt["ncon"], ref["ncon"])
-    np.testing.assert_array_equal(bd.contacts()["geom"], ref["contact_geom"])
-    np.testing.assert_array_equal(cnt["nefc"], ref["nefc"])
-    efc = bd.efc()
-    np.testing.assert_array_equal(efc["type"], ref["efc_type"][..., 0])
-    np.testing.assert_array_equal(efc["state"], ref["efc_state"][..., 0])
-    got = bd.qfrc_inverse()
-    nviol, worst = util.qfrc_violations(got, ref["qfrc_inverse"])
-    _report(name + "_live_64k", {"kernels": kernels, "states": n, "entries": int(got.size), "strict_viol": nviol,
-                                 "strict_worst_ratio": worst})
-    assert nviol == 0, (nviol, worst)
-    np.testing.assert_allclose(bd.get(mjb.F_QFRC_PASSIVE), ref["qfrc_passive"][..., 0], rtol=1e-9, atol=1e-12)
-    if "sensordata" in fields:
-        nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"][..., 0])
-        assert nviol == 0, (nviol, worst)
