@@ -9,7 +9,7 @@ import pytest
 
 import util
 from test_gpu_parity import _run
-from test_gpu_parity_scale import _batch, _reference_model, _report, STRICT_EXCEPTIONS
+from test_gpu_parity_scale import _reference_model, _report
 
 pytestmark = pytest.mark.gpu
 
