@@ -138,3 +138,26 @@ def test_live_reference_passive_and_sensor_paths(name, kernels):
     if "sensordata" in fields:
         nviol, worst = util.sensor_violations(model, bd.sensordata(), ref["sensordata"][..., 0])
         assert nviol == 0, (nviol, worst)
+
+
+@pytest.mark.skipif(not util.ref_available(), reason="oracle/_ref not built")
+def test_convex_pairs_in_degenerate_configurations():
+    """GJK / EPA on their degenerate branches (coincident centres, coaxial cylinders, parallel faces, 1e-9 offsets; up
+    to 20 contacts per state): contact sets bit-identical to the reference run live, distances / positions / frames
+    within 1e-9 rel / 1e-12 abs."""
+    import mujoco_inversedynamicstest_b200 as mjb
+    path, _ = util.golden("convex")
+    model = mjb.Model.from_mjb(path)
+    qpos, qvel, qacc = util.convex_degenerate_states(model)
+    ncm = 64
+    ref, _ = _reference_model(path).inverse_batch(qpos, qvel, qacc, nthread=4, fields={
+        "ncon": 1, "contact_geom": ncm, "contact_dist": ncm, "contact_pos": ncm, "contact_frame": ncm})
+    bd = mjb.BatchData(model, len(qpos), outmask=mjb.OUT_COUNTS | mjb.OUT_CONTACT, nconmax=ncm, njmax=400)
+    bd.set_state(qpos, qvel, qacc)
+    assert bd.inverse() == 0
+    np.testing.assert_array_equal(bd.counts()["ncon"], ref["ncon"])
+    con = bd.contacts()
+    np.testing.assert_array_equal(con["geom"], ref["contact_geom"])
+    np.testing.assert_allclose(con["dist"], ref["contact_dist"][..., 0], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(con["pos"], ref["contact_pos"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(con["frame"], ref["contact_frame"], rtol=1e-9, atol=1e-11)

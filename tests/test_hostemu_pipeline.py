@@ -482,3 +482,25 @@ def test_live_reference_on_fresh_states(name):
     if "sensordata" in fields:
         nviol, worst = util.sensor_violations(model, out["sensordata"], ref["sensordata"][..., 0])
         assert nviol == 0, (nviol, worst)
+
+
+def test_convex_pairs_in_degenerate_configurations():
+    """GJK / EPA on their degenerate branches (coincident centres, coaxial cylinders, parallel faces, 1e-9 offsets; up
+    to 20 contacts per state, penetrations of 0.15): contact sets, distances, positions and frames bit-identical to
+    the reference run live."""
+    if not util.ref_available():
+        pytest.skip("reference library not built")
+    import mujoco_inversedynamicstest_b200 as mjb
+    from bench import load_reference_model
+    model = mjb.Model.from_mjb(util.golden("convex")[0])
+    qpos, qvel, qacc = util.convex_degenerate_states(model)
+    ncm = 64
+    ref, _ = load_reference_model("convex").inverse_batch(qpos, qvel, qacc, nthread=4, fields={
+        "ncon": 1, "contact_geom": ncm, "contact_dist": ncm, "contact_pos": ncm, "contact_frame": ncm})
+    out = emu.run(model, qpos, qvel, qacc, nconmax=ncm, njmax=400)
+    assert (out["status"] == 0).all() and ref["ncon"].max() >= 15
+    np.testing.assert_array_equal(out["ncon"], ref["ncon"])
+    np.testing.assert_array_equal(out["contact_geom"], ref["contact_geom"])
+    np.testing.assert_array_equal(out["contact_dist"], ref["contact_dist"][..., 0])
+    np.testing.assert_array_equal(out["contact_pos"], ref["contact_pos"])
+    np.testing.assert_array_equal(out["contact_frame"], ref["contact_frame"])

@@ -261,3 +261,30 @@ def fwdinv_violations(got, z, rtol=RTOL, atol=ATOL):
     tol = atol + rtol * np.maximum(np.abs(z["fwdinv"]), scale)
     d = np.abs(got - z["fwdinv"])
     return int((d > tol).sum()), float((d / tol).max())
+
+
+def convex_degenerate_states(model):
+    """States of tests/golden/models/convex.xml that put GJK / EPA on their degenerate branches: the free bodies
+    exactly on the centres of the fixed shapes and of each other (zero first search direction, origin on simplex
+    faces), aligned and 90-degree orientations (coaxial cylinders, parallel faces), offsets of 1e-9."""
+    import itertools
+    nq, nv = model.int("nq"), model.int("nv")
+    targets = [(0, 0, 0.3), (0.35, 0, 0.3), (-0.35, 0, 0.3), (0, 0, 0.05), (0.1, 0.05, 0.3)]
+    quats = [(1, 0, 0, 0), (0.7071067811865476, 0.7071067811865476, 0, 0), (0.5, 0.5, 0.5, 0.5),
+             (0.9238795325112867, 0, 0.3826834323650898, 0)]
+    rows = []
+    rng = np.random.default_rng(1)
+    for perm in itertools.permutations(range(5), 5):
+        q = np.zeros(nq)
+        for b in range(5):
+            q[7*b:7*b + 3] = targets[perm[b]]
+            q[7*b + 3:7*b + 7] = quats[(b + perm[0]) % 4]
+        rows.append(q)
+    for k in range(100):
+        q = np.zeros(nq)
+        for b in range(5):
+            q[7*b:7*b + 3] = np.array(targets[k % 5]) + (0 if k < 50 else 1e-9 * rng.standard_normal(3))
+            q[7*b + 3:7*b + 7] = quats[k % 4]
+        rows.append(q)
+    qpos = np.array(rows)
+    return qpos, np.zeros((len(qpos), nv)), np.zeros((len(qpos), nv))
