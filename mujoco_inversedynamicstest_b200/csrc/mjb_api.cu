@@ -768,7 +768,7 @@ bool launchRange(mjbData* d, long long first, long long count) {
   a.items_cap = d->items_cap; a.contacts_cap = d->contacts_cap;
   a.slot_rec = d->d_slot_rec;
   a.has_gravcomp = d->hdr.passive_wrench;
-  a.has_spatial = d->hdr.has_spatial;
+  a.has_spatial = d->hdr.has_spatial || d->hdr.has_fluid;    // selects the smooth kernel with the rarer features
   a.skip_sensors = d->skip_sensors;
   a.scan_ngeom = d->hdr.ngeom;
   a.pair_ci = d->d_pair_ci;

@@ -62,7 +62,7 @@ struct LaunchArgs {
   SlotRec* slot_rec;            // slot (state's first slot + k) -> contact record and its numbering
   int items_cap, contacts_cap;
   int has_contacts;             // run the contact kernel (ncand > 0 and contacts enabled)
-  int has_spatial;              // mjbHdr::has_spatial (force-carrying spatial tendons: smooth kernel variant)
+  int has_spatial;              // mjbHdr::has_spatial || has_fluid (force-carrying spatial tendons, fluid forces: smooth kernel variant)
   int has_gravcomp;             // mjbHdr::has_gravcomp (selects the backward kernel instantiation)
   int max_pair_contacts;        // mjbHdr::max_pair_contacts (sizes the per-warp contact pool)
   int simple_pairs;             // mjbHdr::simple_pairs (selects the narrow-phase kernel instantiation)

@@ -420,7 +420,14 @@ MJB_HD inline void phase_smooth(Ctx& c) {
   } else {
     load_counters(c);      // a later stage of the sweep: running limit-row count and status bits
   }
-  forward_sweep<kLo, kHi>(c);   // incl. input checks, joint springs/dampers, dof friction and joint limit rows
+  // generic CUDA kernels: fluid forces live in the instantiation for the rarer features (kSpatial), which
+  // mjb_inverse launches for models with force-carrying spatial tendons or a medium
+#if defined(__CUDACC__) && !defined(MJB_SPECIALIZED)
+  constexpr bool kFluid = kSpatial;
+#else
+  constexpr bool kFluid = true;
+#endif
+  forward_sweep<kLo, kHi, true, kFluid>(c);   // incl. input checks, joint springs/dampers, dof friction and joint limit rows
   if (kHi != 0 && kHi < H.nbody) { save_counters(c); return; }
   smooth_tail<kSpatial>(c);
 }

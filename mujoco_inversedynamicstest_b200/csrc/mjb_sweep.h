@@ -290,7 +290,10 @@ MJB_HD inline void store_cdof(Ctx& c, double* cdof, int dof, const double* cd) {
   if (c.lcd) { for (int k = 0; k < 6; k++) c.lcd[6*(dof - c.ldof0) + k] = cd[k]; }
 }
 
-template <int kLo = 1, int kHi = 0, bool kHandOver = true>
+// kFluid: mj_fluid is compiled in. The generic CUDA kernels keep it out of the plain smooth-kernel instantiation
+// (phase_smooth), whose register budget is tuned on models without a medium; everywhere else the flag of the model
+// decides (a constant in the specialised build).
+template <int kLo = 1, int kHi = 0, bool kHandOver = true, bool kFluid = true>
 MJB_HD inline void forward_sweep(Ctx& c) {
   const mjbHdr& H = *c.H;
   const int nbody = H.nbody;
@@ -587,7 +590,7 @@ MJB_HD inline void forward_sweep(Ctx& c) {
           cross3(wg, off, F);
           wg[3] = F[0]; wg[4] = F[1]; wg[5] = F[2];
         }
-        if (H.has_fluid) {
+        if (kFluid && H.has_fluid) {
           const double* fb = MD(fluid_body) + 4*b;
           if (fb[0] != 0.0) {
             double kin[MJB_FLUID_KIN], wf[6] = {0, 0, 0, 0, 0, 0};
